@@ -1,0 +1,199 @@
+"""ctypes binding of include/b200rt.h (the C ABI) — mirrors the header field for field.
+
+The product path has NO CPU fallback: if ``libb200rt.so`` is missing or the box
+has no CUDA device, rendering calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+c_f = C.c_float
+c_i = C.c_int32
+c_u = C.c_uint32
+
+SEM_HW1, SEM_HW2, SEM_HW3, SEM_HW4, SEM_HW5, SEM_HW6, SEM_HW7, SEM_PPM = range(1, 9)
+SEM_BY_NAME = {"hw1": SEM_HW1, "hw2": SEM_HW2, "hw3": SEM_HW3, "hw4": SEM_HW4, "hw5": SEM_HW5,
+               "hw6": SEM_HW6, "hw7": SEM_HW7, "ppm": SEM_PPM}
+
+KIND_INNER, KIND_TRI, KIND_SPHERE, KIND_TRIPRIM, KIND_INSTANCE, KIND_NONE = 0, 1, 2, 3, 4, 15
+
+LIGHT_POINT, LIGHT_AREA, LIGHT_SPOT, LIGHT_DIRECTIONAL, LIGHT_ENV, LIGHT_MESH, LIGHT_SPHERE = range(7)
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("lmin", c_f * 3), ("lmax", c_f * 3), ("rmin", c_f * 3), ("rmax", c_f * 3),
+                ("left", c_u), ("right", c_u), ("pad", c_u * 2)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("root", c_u), ("root_box", c_f * 6), ("tri_begin", c_i), ("tri_count", c_i),
+                ("node_begin", c_i), ("node_count", c_i)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("inv", c_f * 12), ("nrm", c_f * 9), ("fwd", c_f * 16), ("box", c_f * 6),
+                ("velocity", c_f * 3), ("mesh", c_i), ("material", c_i), ("texture", c_i),
+                ("flags", c_u), ("rank", c_i), ("pad", c_i * 3)]
+
+
+class Sphere(C.Structure):
+    _fields_ = [("center", c_f * 3), ("radius", c_f), ("inv", c_f * 12), ("nrm", c_f * 9),
+                ("fwd", c_f * 16), ("velocity", c_f * 3), ("material", c_i), ("texture", c_i),
+                ("flags", c_u), ("rank", c_i), ("pad", c_i * 2)]
+
+
+class TriPrim(C.Structure):
+    _fields_ = [("v0", c_f * 3), ("a1", c_f * 3), ("a2", c_f * 3), ("normal", c_f * 3),
+                ("inv", c_f * 12), ("nrm", c_f * 9), ("material", c_i), ("flags", c_u), ("rank", c_i)]
+
+
+class Material(C.Structure):
+    _fields_ = [("ambient", c_f * 3), ("diffuse", c_f * 3), ("specular", c_f * 3), ("mirror", c_f * 3),
+                ("transparency", c_f * 3), ("roughness", c_f), ("refraction_index", c_f),
+                ("phong_exponent", c_f), ("brdf", c_i), ("degamma", c_i), ("pad", c_f * 4)]
+
+
+class Light(C.Structure):
+    _fields_ = [("kind", c_i), ("position", c_f * 3), ("intensity", c_f * 3), ("edge1", c_f * 3),
+                ("edge2", c_f * 3), ("normal", c_f * 3), ("object", c_i), ("pad", c_f * 4)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("e", c_f * 3), ("u", c_f * 3), ("v", c_f * 3), ("w", c_f * 3),
+                ("top_left", c_f * 3), ("su", c_f * 3), ("sv", c_f * 3),
+                ("left", c_f), ("right", c_f), ("bottom", c_f), ("top", c_f), ("distance", c_f),
+                ("width", c_i), ("height", c_i), ("samples_sqrt", c_i), ("aperture", c_f),
+                ("pad", c_i * 3)]
+
+
+class CameraIn(C.Structure):
+    _fields_ = [("position", c_f * 3), ("gaze", c_f * 3), ("up", c_f * 3), ("near_plane", c_f * 4),
+                ("near_distance", c_f), ("width", c_i), ("height", c_i), ("num_samples", c_i),
+                ("focus_distance", c_f), ("aperture_size", c_f)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [
+        ("semantics", c_i), ("max_depth", c_i), ("background", c_f * 3), ("ambient", c_f * 3),
+        ("shadow_eps", c_f), ("isect_eps", c_f), ("root", c_u), ("root_box", c_f * 6),
+        ("n_nodes", c_i), ("nodes", C.POINTER(BvhNode)),
+        ("n_tris", c_i), ("tri_geom", C.POINTER(c_f)), ("tri_vidx", C.POINTER(c_i)),
+        ("tri_info", C.POINTER(c_i)),
+        ("n_verts", c_i), ("vert_pos", C.POINTER(c_f)), ("vert_normal", C.POINTER(c_f)),
+        ("n_meshes", c_i), ("meshes", C.POINTER(Mesh)),
+        ("n_instances", c_i), ("instances", C.POINTER(Instance)),
+        ("n_spheres", c_i), ("spheres", C.POINTER(Sphere)),
+        ("n_triprims", c_i), ("triprims", C.POINTER(TriPrim)),
+        ("n_materials", c_i), ("materials", C.POINTER(Material)),
+        ("n_lights", c_i), ("lights", C.POINTER(Light)),
+        ("n_cameras", c_i), ("cameras", C.POINTER(Camera)),
+    ]
+
+
+class RenderOpts(C.Structure):
+    _fields_ = [("row_begin", c_i), ("row_end", c_i), ("row_stride", c_i), ("seed", C.c_uint64),
+                ("sample_begin", c_i), ("sample_end", c_i), ("exact_traversal", c_i), ("pad", c_i * 5)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_secondary", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("spheres_tested", C.c_uint64),
+                ("instances_entered", C.c_uint64),
+                ("ms_generate", c_f), ("ms_extend", c_f), ("ms_shade", c_f), ("ms_shadow", c_f),
+                ("ms_total", c_f), ("waves", c_i), ("launches", c_i)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+    @property
+    def rays_total(self) -> int:
+        return self.rays_primary + self.rays_shadow + self.rays_secondary
+
+
+class B200RTError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load libb200rt.so (building it in-tree first when nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing:
+        try:
+            _build.build_lib()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    if not os.path.exists(path):
+        raise B200RTError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                          "There is no CPU fallback.")
+    L = C.CDLL(path)
+    P = C.POINTER
+    fp = P(c_f)
+    sig = {
+        "b200rt_xf_identity": (None, [fp]),
+        "b200rt_xf_scaling": (None, [c_f, c_f, c_f, fp]),
+        "b200rt_xf_translation": (None, [c_f, c_f, c_f, fp]),
+        "b200rt_xf_rotation": (None, [c_f, c_f, c_f, c_f, fp]),
+        "b200rt_xf_mul": (None, [fp, fp, fp]),
+        "b200rt_xf_invert": (C.c_int, [fp, fp]),
+        "b200rt_builder_create": (C.c_void_p, [C.c_int]),
+        "b200rt_builder_destroy": (None, [C.c_void_p]),
+        "b200rt_builder_set_globals": (C.c_int, [C.c_void_p, fp, fp, c_f, C.c_int]),
+        "b200rt_builder_add_camera": (C.c_int, [C.c_void_p, P(CameraIn)]),
+        "b200rt_builder_add_material": (C.c_int, [C.c_void_p, P(Material)]),
+        "b200rt_builder_add_light": (C.c_int, [C.c_void_p, P(Light)]),
+        "b200rt_builder_set_vertices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+        "b200rt_builder_add_mesh": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, fp, fp]),
+        "b200rt_builder_add_instance": (C.c_int, [C.c_void_p, C.c_int, C.c_int, fp, fp]),
+        "b200rt_builder_add_triangle": (C.c_int, [C.c_void_p, C.c_int, P(c_i), fp]),
+        "b200rt_builder_add_sphere": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f, fp, fp]),
+        "b200rt_builder_finish": (C.c_int, [C.c_void_p, P(P(SceneDesc))]),
+        "b200rt_device_count": (C.c_int, []),
+        "b200rt_scene_create": (C.c_int, [P(SceneDesc), C.c_int, P(C.c_void_p)]),
+        "b200rt_scene_destroy": (None, [C.c_void_p]),
+        "b200rt_render": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), C.c_void_p, P(RenderStats)]),
+        "b200rt_render_device": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), P(C.c_void_p), P(RenderStats)]),
+        "b200rt_primary_ids": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), C.c_void_p, C.c_void_p]),
+        "b200rt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                        C.c_void_p, P(RenderStats)]),
+        "b200rt_last_error": (C.c_char_p, []),
+        "b200rt_version": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError = header/lib drift: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+#: every symbol include/b200rt.h declares (tests/test_abi.py checks the .so exports them all)
+def declared_symbols() -> list[str]:
+    import re
+    hdr = os.path.join(_build.ROOT, "include", "b200rt.h")
+    text = open(hdr).read()
+    return sorted(set(re.findall(r"\b(b200rt_[a-z0-9_]+)\s*\(", text)))
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        L = load()
+        msg = (L.b200rt_last_error() or b"").decode()
+        raise B200RTError(f"{what} failed (rc={rc}): {msg}")
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.POINTER(c_f))

@@ -1,0 +1,754 @@
+// host_build.cpp — host-side scene assembly for the B200 rendering core.
+//
+// This is the "host stays" half of the boundary written for a
+// host that does not link the reference: it restates, operation for operation
+// in IEEE binary32 (compile with -ffp-contract=off), the load-time arithmetic
+// whose results the hot path consumes:
+//   * Matrix4x4 / Transformation        HW3/src/Matrix4x4.cpp:29-233, HW3/src/Transformation.cpp:6-84
+//   * Camera frame                      HW3/include/Camera.h:11-34, HW1/Camera.h:11-23
+//   * Mesh_triangle / Triangle records  HW3/src/Mesh_triangle.cpp:4-37, HW3/src/Triangle.cpp:4-44
+//   * vertex normals                    HW3/include/Vertex.h:13-22, HW3/src/Scene.cpp:690-697,872-877
+//   * Bounding_box expand/apply_transform HW3/src/bounding_box.cpp:5-15,39-113
+//   * BVH topology                      HW3/src/Bounding_volume_hierarchy.cpp:3-29
+//   * object order of Scene::bvh        HW3/src/Scene.cpp:703-869
+// The output is a B200SceneDesc (include/b200rt.h).  tests/test_host_build.py
+// compares it against a dump made by walking the real reference objects
+// (oracle/ref_probe.cpp built into oracle/_ref/).
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/b200rt.h"
+
+namespace {
+
+thread_local std::string g_host_error;
+
+struct V3 {
+  float x, y, z;
+  V3() : x(0.f), y(0.f), z(0.f) {}
+  V3(float a) : x(a), y(a), z(a) {}
+  V3(float a, float b, float c) : x(a), y(b), z(c) {}
+  float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+  float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); }
+};
+inline V3 operator+(V3 a, V3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(V3 a, V3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator-(V3 a) { return V3(-a.x, -a.y, -a.z); }
+inline V3 operator*(V3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+inline V3 operator*(float s, V3 a) { return a * s; }
+inline V3 operator/(V3 a, float s) { return V3(a.x / s, a.y / s, a.z / s); }
+inline bool operator==(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+inline bool operator!=(V3 a, V3 b) { return !(a == b); }
+inline float dot(V3 a, V3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+inline V3 cross(V3 a, V3 b) {
+  return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+inline float length(V3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline V3 normalize(V3 a) { return a / length(a); }
+inline V3 load3(const float* p) { return V3(p[0], p[1], p[2]); }
+inline void store3(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+const float kInf = std::numeric_limits<float>::infinity();
+
+// ---- Matrix4x4 -------------------------------------------------------------
+struct M4 {
+  float e[4][4];
+  M4() { std::memset(e, 0, sizeof(e)); }
+  static M4 identity() {
+    M4 m;
+    for (int i = 0; i < 4; i++) m.e[i][i] = 1.0f;
+    return m;
+  }
+  static M4 from(const float* p) {
+    M4 m;
+    std::memcpy(m.e, p, sizeof(m.e));
+    return m;
+  }
+  void to(float* p) const { std::memcpy(p, e, sizeof(e)); }
+};
+// Matrix4x4::operator* — HW3/src/Matrix4x4.cpp:52-62 (accumulates into 0).
+M4 mul(const M4& a, const M4& b) {
+  M4 r;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++)
+      for (int k = 0; k < 4; k++) r.e[i][j] += a.e[i][k] * b.e[k][j];
+  return r;
+}
+M4 transpose(const M4& a) {
+  M4 t;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) t.e[i][j] = a.e[j][i];
+  return t;
+}
+// Matrix4x4::multiply — HW3/src/Matrix4x4.cpp:29-50.
+V3 mul_point(const M4& m, V3 p) {
+  V3 r;
+  for (int i = 0; i < 3; i++) {
+    r[i] = m.e[i][3];
+    for (int j = 0; j < 3; j++) r[i] += m.e[i][j] * p[j];
+  }
+  return r;
+}
+bool is_identity(const M4& m) {
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++)
+      if (m.e[i][j] != (i == j ? 1.0f : 0.0f)) return false;
+  return true;
+}
+// Matrix4x4::invert_matrix — HW3/src/Matrix4x4.cpp:97-233 (cofactor expansion;
+// the signed products are evaluated left to right exactly as written there).
+bool invert(const M4& a, M4& out) {
+  float inv[16], m[16], det;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) m[i * 4 + j] = a.e[i][j];
+  inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] +
+           m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+  inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] -
+           m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+  inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] +
+           m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+  inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] -
+            m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+  inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] -
+           m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+  inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] +
+           m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+  inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] -
+           m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+  inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] +
+            m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+  inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] +
+           m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+  inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] -
+           m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+  inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] +
+            m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+  inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] -
+            m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+  inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] -
+           m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+  inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] +
+           m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+  inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] -
+            m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+  inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] +
+            m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+  det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+  if (det == 0.0f) return false;
+  det = 1.0f / det;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) out.e[i][j] = inv[i * 4 + j] * det;
+  return true;
+}
+
+// ---- Bounding_box ----------------------------------------------------------
+struct Box {
+  V3 mn, mx, center;
+  Box() : mn(kInf), mx(-kInf), center(0.f) {}
+  Box(V3 a, V3 b) : mn(a), mx(b), center((b + a) / 2.0f) {}
+  // Bounding_box::expand — HW3/src/bounding_box.cpp:5-15
+  void expand(const Box& o) {
+    mn.x = std::fmin(mn.x, o.mn.x);
+    mn.y = std::fmin(mn.y, o.mn.y);
+    mn.z = std::fmin(mn.z, o.mn.z);
+    mx.x = std::fmax(mx.x, o.mx.x);
+    mx.y = std::fmax(mx.y, o.mx.y);
+    mx.z = std::fmax(mx.z, o.mx.z);
+    center = (mx + mn) / 2.0f;
+  }
+};
+// Bounding_box::apply_transform — HW3/src/bounding_box.cpp:39-113
+Box apply_transform(const Box& b, const M4& m) {
+  V3 c[8];
+  int k = 0;
+  for (int ix = 0; ix < 2; ix++)
+    for (int iy = 0; iy < 2; iy++)
+      for (int iz = 0; iz < 2; iz++)
+        c[k++] = mul_point(m, V3(ix ? b.mx.x : b.mn.x, iy ? b.mx.y : b.mn.y, iz ? b.mx.z : b.mn.z));
+  V3 mn = c[0], mx = c[0];
+  for (int i = 1; i < 8; i++) {
+    mn.x = std::fmin(mn.x, c[i].x);
+    mn.y = std::fmin(mn.y, c[i].y);
+    mn.z = std::fmin(mn.z, c[i].z);
+    mx.x = std::fmax(mx.x, c[i].x);
+    mx.y = std::fmax(mx.y, c[i].y);
+    mx.z = std::fmax(mx.z, c[i].z);
+  }
+  return Box(mn, mx);
+}
+Box tri_box(V3 v0, V3 v1, V3 v2) {
+  V3 mn = v0, mx = v0;
+  mn.x = std::fmin(mn.x, v1.x); mn.y = std::fmin(mn.y, v1.y); mn.z = std::fmin(mn.z, v1.z);
+  mx.x = std::fmax(mx.x, v1.x); mx.y = std::fmax(mx.y, v1.y); mx.z = std::fmax(mx.z, v1.z);
+  mn.x = std::fmin(mn.x, v2.x); mn.y = std::fmin(mn.y, v2.y); mn.z = std::fmin(mn.z, v2.z);
+  mx.x = std::fmax(mx.x, v2.x); mx.y = std::fmax(mx.y, v2.y); mx.z = std::fmax(mx.z, v2.z);
+  return Box(mn, mx);
+}
+void motion_expand(Box& b, V3 vel) {  // HW3/include/Mesh.h:104-110, Sphere.h:30-36
+  if (vel != V3(0.0f)) {
+    V3 mn = b.mn, mx = b.mx;
+    b.expand(Box(mn + vel, mx + vel));
+    b.expand(Box(mn - vel, mx - vel));
+  }
+}
+
+// ---- BVH in the reference's topology ---------------------------------------
+struct Obj {
+  uint32_t ref;
+  Box box;
+};
+struct BuildOut {
+  std::vector<b200rt_bvh_node>* nodes;
+  std::vector<uint32_t>* leaf_order;  // refs in DFS order
+};
+void put_box(float* mn, float* mx, const Box& b) {
+  store3(mn, b.mn);
+  store3(mx, b.mx);
+}
+// BVH::BVH — HW3/src/Bounding_volume_hierarchy.cpp:3-29.  Returns the node's
+// index; `box_out` receives the node's own box (stored by the parent).
+uint32_t build_bvh(std::vector<Obj>& objs, int start, int end, int dim, BuildOut& out, Box& box_out) {
+  Box box;
+  for (int i = start; i < end; i++) box.expand(objs[i].box);
+  const float center = box.center[dim];
+  int mid = start;
+  for (int i = start; i < end; i++) {
+    if (objs[i].box.center[dim] < center) {
+      std::swap(objs[i], objs[mid]);
+      mid++;
+    }
+  }
+  if (mid == start || mid == end) mid = start + ((end - start) / 2);
+  const uint32_t me = (uint32_t)out.nodes->size();
+  out.nodes->push_back(b200rt_bvh_node());
+  b200rt_bvh_node n;
+  std::memset(&n, 0, sizeof(n));
+  Box lb, rb;
+  if (start + 1 == mid) {
+    n.left = objs[start].ref;
+    lb = objs[start].box;
+    out.leaf_order->push_back(objs[start].ref);
+  } else {
+    uint32_t c = build_bvh(objs, start, mid, (dim + 1) % 3, out, lb);
+    n.left = B200RT_REF(B200RT_KIND_INNER, c);
+  }
+  if (mid + 1 == end) {
+    n.right = objs[mid].ref;
+    rb = objs[mid].box;
+    out.leaf_order->push_back(objs[mid].ref);
+  } else {
+    uint32_t c = build_bvh(objs, mid, end, (dim + 1) % 3, out, rb);
+    n.right = B200RT_REF(B200RT_KIND_INNER, c);
+  }
+  put_box(n.lmin, n.lmax, lb);
+  put_box(n.rmin, n.rmax, rb);
+  (*out.nodes)[me] = n;
+  box_out = box;
+  return me;
+}
+
+struct MeshIn {
+  int material, smooth;
+  std::vector<int32_t> faces;
+  M4 base_xf;
+  V3 velocity;
+};
+struct InstIn {
+  int mesh, material;
+  M4 xf;
+  V3 velocity;
+  bool direct;
+};
+struct TriIn {
+  int material;
+  int32_t idx[3];
+  M4 xf;
+};
+struct SphIn {
+  int material, center_vertex;
+  float radius;
+  M4 xf;
+  V3 velocity;
+};
+
+void fill_xf(const M4& m, float inv12[12], float nrm9[9], float fwd16[16], bool& ok) {
+  // Arbitrary_transformation — HW3/src/Transformation.cpp:73-84
+  M4 inv;
+  ok = invert(m, inv);
+  if (!ok) return;
+  M4 nrm = transpose(inv);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 4; j++) inv12[i * 4 + j] = inv.e[i][j];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) nrm9[i * 3 + j] = nrm.e[i][j];
+  if (fwd16) m.to(fwd16);
+}
+
+}  // namespace
+
+struct b200rt_builder {
+  int semantics;
+  B200SceneDesc desc;
+  std::vector<float> verts;
+  std::vector<b200rt_camera> cameras;
+  std::vector<b200rt_material> materials;
+  std::vector<b200rt_light> lights;
+  std::vector<MeshIn> meshes_in;
+  std::vector<InstIn> inst_in;
+  std::vector<TriIn> tri_in;
+  std::vector<SphIn> sph_in;
+  // flattened
+  std::vector<b200rt_bvh_node> nodes;
+  std::vector<float> tri_geom;
+  std::vector<int32_t> tri_vidx, tri_info;
+  std::vector<float> vert_normal;
+  std::vector<b200rt_mesh> meshes;
+  std::vector<b200rt_instance> instances;
+  std::vector<b200rt_sphere> spheres;
+  std::vector<b200rt_triprim> triprims;
+  bool finished;
+};
+
+extern "C" {
+
+const char* b200rt_last_error(void) { return g_host_error.c_str(); }
+// internal (not part of the ABI): lets the CUDA translation units report errors
+void b200rt_internal_set_error(const char* msg) { g_host_error = msg ? msg : ""; }
+
+void b200rt_xf_identity(float out[16]) { M4::identity().to(out); }
+// Scaling — HW3/src/Transformation.cpp:6-17 (forward matrix only; inverses are
+// always recomputed by Arbitrary_transformation on the composed product).
+void b200rt_xf_scaling(float x, float y, float z, float out[16]) {
+  M4 m;
+  m.e[0][0] = x; m.e[1][1] = y; m.e[2][2] = z; m.e[3][3] = 1.0f;
+  m.to(out);
+}
+void b200rt_xf_translation(float x, float y, float z, float out[16]) {
+  M4 m = M4::identity();
+  m.e[0][3] = x; m.e[1][3] = y; m.e[2][3] = z;
+  m.to(out);
+}
+// Rotation — HW3/src/Transformation.cpp:35-70
+void b200rt_xf_rotation(float angle_deg, float x, float y, float z, float out[16]) {
+  const float degree_to_pi = M_PI / 180.0f;  // HW3/src/Scene.cpp:322
+  const float angle = angle_deg * degree_to_pi;
+  const V3 u = normalize(V3(x, y, z));
+  const V3 v = normalize((x != 0.0f || y != 0.0f) ? V3(-u.y, u.x, 0.0f) : V3(0.0f, 1.0f, 0.0f));
+  const V3 w = cross(u, v);
+  M4 m;
+  m.e[0][0] = u.x; m.e[0][1] = u.y; m.e[0][2] = u.z;
+  m.e[1][0] = v.x; m.e[1][1] = v.y; m.e[1][2] = v.z;
+  m.e[2][0] = w.x; m.e[2][1] = w.y; m.e[2][2] = w.z;
+  m.e[3][3] = 1.0f;
+  M4 rot;
+  rot.e[0][0] = 1.0f;
+  rot.e[1][1] = std::cos(angle);
+  rot.e[1][2] = -std::sin(angle);
+  rot.e[2][1] = -rot.e[1][2];
+  rot.e[2][2] = rot.e[1][1];
+  rot.e[3][3] = 1.0f;
+  M4 mt = transpose(m);
+  mul(mt, mul(rot, m)).to(out);
+}
+void b200rt_xf_mul(const float a[16], const float b[16], float out[16]) {
+  mul(M4::from(a), M4::from(b)).to(out);
+}
+int b200rt_xf_invert(const float m[16], float out[16]) {
+  M4 inv;
+  if (!invert(M4::from(m), inv)) return B200RT_E_SINGULAR;
+  inv.to(out);
+  return B200RT_OK;
+}
+
+b200rt_builder* b200rt_builder_create(int semantics) {
+  if (semantics < B200RT_SEM_HW1 || semantics > B200RT_SEM_PPM) return nullptr;
+  b200rt_builder* b = new b200rt_builder();
+  b->semantics = semantics;
+  std::memset(&b->desc, 0, sizeof(b->desc));
+  b->desc.semantics = semantics;
+  b->desc.shadow_eps = 0.001f;
+  b->desc.isect_eps = (semantics == B200RT_SEM_PPM) ? 0.0001f : 0.000001f;
+  b->finished = false;
+  return b;
+}
+void b200rt_builder_destroy(b200rt_builder* b) { delete b; }
+
+int b200rt_builder_set_globals(b200rt_builder* b, const float bg[3], const float amb[3],
+                               float shadow_eps, int max_depth) {
+  if (!b) return B200RT_E_INVALID;
+  std::memcpy(b->desc.background, bg, 12);
+  std::memcpy(b->desc.ambient, amb, 12);
+  b->desc.shadow_eps = shadow_eps;
+  b->desc.max_depth = max_depth;
+  return B200RT_OK;
+}
+
+// Camera::Camera — HW3/include/Camera.h:11-34 (HW1/Camera.h:11-23 has no
+// s_u/s_v constants and no DOF; the fields are still filled for uniformity).
+int b200rt_builder_add_camera(b200rt_builder* b, const b200rt_camera_in* in) {
+  if (!b || !in) return B200RT_E_INVALID;
+  b200rt_camera c;
+  std::memset(&c, 0, sizeof(c));
+  const V3 e = load3(in->position), gaze = load3(in->gaze), up = load3(in->up);
+  float left = in->near_plane[0], right = in->near_plane[1], bottom = in->near_plane[2],
+        top = in->near_plane[3], distance = in->near_distance;
+  const V3 w = -(normalize(gaze));
+  const V3 u = normalize(cross(normalize(up), w));
+  const V3 v = normalize(cross(w, u));
+  if (b->semantics >= B200RT_SEM_HW3 && in->aperture_size != 0.0f) {
+    const float ratio = in->focus_distance / distance;
+    left = ratio * left; right = ratio * right; bottom = ratio * bottom; top = ratio * top;
+    distance = in->focus_distance;
+  }
+  const V3 tl = e - w * distance + left * u + top * v;
+  const V3 su = ((right - left) / in->width) * u;
+  const V3 sv = ((top - bottom) / in->height) * v;
+  store3(c.e, e); store3(c.u, u); store3(c.v, v); store3(c.w, w);
+  store3(c.top_left, tl); store3(c.su, su); store3(c.sv, sv);
+  c.left = left; c.right = right; c.bottom = bottom; c.top = top; c.distance = distance;
+  c.width = in->width; c.height = in->height;
+  int s = (int)std::sqrt(in->num_samples);  // HW3/src/Scene.cpp:412 (int -> double sqrt)
+  if (s <= 0) s = 1;
+  c.samples_sqrt = (b->semantics == B200RT_SEM_HW1) ? 1 : s;
+  c.aperture = (b->semantics >= B200RT_SEM_HW3) ? in->aperture_size : 0.0f;
+  b->cameras.push_back(c);
+  return (int)b->cameras.size() - 1;
+}
+
+int b200rt_builder_add_material(b200rt_builder* b, const b200rt_material* m) {
+  if (!b || !m) return B200RT_E_INVALID;
+  b->materials.push_back(*m);
+  return (int)b->materials.size() - 1;
+}
+int b200rt_builder_add_light(b200rt_builder* b, const b200rt_light* l) {
+  if (!b || !l) return B200RT_E_INVALID;
+  b200rt_light c = *l;
+  if (c.kind == B200RT_LIGHT_AREA) {
+    // HW3/src/Scene.cpp:484
+    store3(c.normal, normalize(cross(load3(c.edge1), load3(c.edge2))));
+  }
+  b->lights.push_back(c);
+  return (int)b->lights.size() - 1;
+}
+int b200rt_builder_set_vertices(b200rt_builder* b, const float* xyz, int n) {
+  if (!b || (n > 0 && !xyz)) return B200RT_E_INVALID;
+  b->verts.assign(xyz, xyz + 3 * (size_t)n);
+  return B200RT_OK;
+}
+int b200rt_builder_add_mesh(b200rt_builder* b, int material, int smooth, const int32_t* faces,
+                            int n_faces, const float base_xf[16], const float velocity[3]) {
+  if (!b || n_faces < 0 || (n_faces > 0 && !faces)) return B200RT_E_INVALID;
+  MeshIn m;
+  m.material = material;
+  m.smooth = smooth;
+  m.faces.assign(faces, faces + 3 * (size_t)n_faces);
+  m.base_xf = base_xf ? M4::from(base_xf) : M4::identity();
+  m.velocity = velocity ? load3(velocity) : V3(0.f);
+  b->meshes_in.push_back(std::move(m));
+  const int id = (int)b->meshes_in.size() - 1;
+  if (b->semantics != B200RT_SEM_HW1) {
+    InstIn i;
+    i.mesh = id;
+    i.material = material;
+    i.xf = b->meshes_in[id].base_xf;
+    i.velocity = b->meshes_in[id].velocity;
+    i.direct = (b->semantics == B200RT_SEM_HW2);
+    b->inst_in.push_back(i);  // base instances precede explicit ones as long as
+                              // all meshes are added first (the loader does so).
+  }
+  return id;
+}
+int b200rt_builder_add_instance(b200rt_builder* b, int base_mesh, int material,
+                                const float xf[16], const float velocity[3]) {
+  if (!b || base_mesh < 0 || base_mesh >= (int)b->meshes_in.size() || !xf) return B200RT_E_INVALID;
+  if (b->semantics < B200RT_SEM_HW3) return B200RT_E_UNSUPPORTED;
+  InstIn i;
+  i.mesh = base_mesh;
+  i.material = material;
+  i.xf = M4::from(xf);
+  i.velocity = velocity ? load3(velocity) : V3(0.f);
+  i.direct = false;
+  b->inst_in.push_back(i);
+  return (int)b->inst_in.size() - 1;
+}
+int b200rt_builder_add_triangle(b200rt_builder* b, int material, const int32_t idx[3],
+                                const float xf[16]) {
+  if (!b || !idx) return B200RT_E_INVALID;
+  TriIn t;
+  t.material = material;
+  std::memcpy(t.idx, idx, 12);
+  t.xf = xf ? M4::from(xf) : M4::identity();
+  b->tri_in.push_back(t);
+  return (int)b->tri_in.size() - 1;
+}
+int b200rt_builder_add_sphere(b200rt_builder* b, int material, int center_vertex, float radius,
+                              const float xf[16], const float velocity[3]) {
+  if (!b) return B200RT_E_INVALID;
+  SphIn s;
+  s.material = material;
+  s.center_vertex = center_vertex;
+  s.radius = radius;
+  s.xf = xf ? M4::from(xf) : M4::identity();
+  s.velocity = velocity ? load3(velocity) : V3(0.f);
+  b->sph_in.push_back(s);
+  return (int)b->sph_in.size() - 1;
+}
+
+int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
+  if (!b || !out) return B200RT_E_INVALID;
+  if (b->finished) {
+    *out = &b->desc;
+    return B200RT_OK;
+  }
+  const int nv = (int)(b->verts.size() / 3);
+  auto vert = [&](int i) { return load3(&b->verts[3 * (size_t)i]); };
+  auto check_idx = [&](int i) { return i >= 0 && i < nv; };
+  const bool hw1 = b->semantics == B200RT_SEM_HW1;
+
+  // ---- mesh triangles: records, vertex-normal accumulation, per-mesh BVH ----
+  std::vector<V3> vnorm((size_t)nv, V3(0.f));
+  std::vector<char> vhas((size_t)nv, 0);
+  b->meshes.clear();
+  for (size_t mi = 0; mi < b->meshes_in.size(); mi++) {
+    const MeshIn& m = b->meshes_in[mi];
+    const int nf = (int)(m.faces.size() / 3);
+    std::vector<Obj> objs((size_t)nf);
+    std::vector<V3> normals((size_t)nf);
+    for (int f = 0; f < nf; f++) {
+      const int i0 = m.faces[3 * f], i1 = m.faces[3 * f + 1], i2 = m.faces[3 * f + 2];
+      if (!check_idx(i0) || !check_idx(i1) || !check_idx(i2)) {
+        g_host_error = "mesh face index out of range";
+        return B200RT_E_INVALID;
+      }
+      const V3 v0 = vert(i0), v1 = vert(i1), v2 = vert(i2);
+      const V3 c = cross(v1 - v0, v2 - v0);
+      const V3 n = normalize(c);                       // Mesh_triangle.cpp:17
+      normals[f] = n;
+      objs[f].ref = B200RT_REF(B200RT_KIND_TRI, f);    // local face id for now
+      objs[f].box = tri_box(v0, v1, v2);
+      if (!hw1) {
+        const float area = length(c) / 2;              // get_surface_area, Mesh_triangle.cpp:70-75
+        // Vertex::add_vertex_normal — HW3/src/Scene.cpp:694-696
+        vnorm[i0] = vnorm[i0] + n * area; vhas[i0] = 1;
+        vnorm[i1] = vnorm[i1] + n * area; vhas[i1] = 1;
+        vnorm[i2] = vnorm[i2] + n * area; vhas[i2] = 1;
+      }
+    }
+    b200rt_mesh fm;
+    std::memset(&fm, 0, sizeof(fm));
+    fm.tri_begin = (int)(b->tri_info.size() / 2);
+    fm.tri_count = nf;
+    fm.node_begin = (int)b->nodes.size();
+    std::vector<uint32_t> order;
+    Box root_box;
+    if (hw1 || nf == 0) {
+      // HW1 has no BVH (HW1/Scene.cpp:35-54): keep file order.
+      for (int f = 0; f < nf; f++) order.push_back(B200RT_REF(B200RT_KIND_TRI, f));
+      fm.root = B200RT_REF_NONE;
+    } else if (nf == 1) {
+      order.push_back(objs[0].ref);  // BVH::create_bvh size==1 — Bounding_volume_hierarchy.h:13-14
+      root_box = objs[0].box;
+      fm.root = B200RT_REF(B200RT_KIND_TRI, fm.tri_begin);
+    } else {
+      BuildOut bo{&b->nodes, &order};
+      uint32_t r = build_bvh(objs, 0, nf, 0, bo, root_box);
+      fm.root = B200RT_REF(B200RT_KIND_INNER, r);
+    }
+    fm.node_count = (int)b->nodes.size() - fm.node_begin;
+    put_box(fm.root_box, fm.root_box + 3, root_box);
+    // local face id -> global triangle index in DFS order
+    std::vector<int32_t> remap((size_t)nf);
+    for (int k = 0; k < nf; k++) remap[B200RT_REF_INDEX(order[k])] = fm.tri_begin + k;
+    for (int n = fm.node_begin; n < fm.node_begin + fm.node_count; n++) {
+      b200rt_bvh_node& nd = b->nodes[n];
+      if (B200RT_REF_KIND(nd.left) == B200RT_KIND_TRI)
+        nd.left = B200RT_REF(B200RT_KIND_TRI, remap[B200RT_REF_INDEX(nd.left)]);
+      if (B200RT_REF_KIND(nd.right) == B200RT_KIND_TRI)
+        nd.right = B200RT_REF(B200RT_KIND_TRI, remap[B200RT_REF_INDEX(nd.right)]);
+    }
+    for (int k = 0; k < nf; k++) {
+      const int f = (int)B200RT_REF_INDEX(order[k]);
+      const int i0 = m.faces[3 * f], i1 = m.faces[3 * f + 1], i2 = m.faces[3 * f + 2];
+      const V3 v0 = vert(i0), v1 = vert(i1), v2 = vert(i2);
+      float g[12];
+      store3(g, v0); store3(g + 3, v0 - v1); store3(g + 6, v0 - v2); store3(g + 9, normals[f]);
+      b->tri_geom.insert(b->tri_geom.end(), g, g + 12);
+      b->tri_vidx.push_back(i0); b->tri_vidx.push_back(i1); b->tri_vidx.push_back(i2);
+      b->tri_info.push_back(m.material);
+      b->tri_info.push_back(m.smooth ? 1 : 0);
+    }
+    b->meshes.push_back(fm);
+  }
+  // HW1 stand-alone triangles are plain triangles scanned after the meshes
+  // (HW1/Scene.cpp:44-49): append them to the triangle arrays.
+  if (hw1) {
+    for (const TriIn& t : b->tri_in) {
+      if (!check_idx(t.idx[0]) || !check_idx(t.idx[1]) || !check_idx(t.idx[2])) {
+        g_host_error = "triangle index out of range";
+        return B200RT_E_INVALID;
+      }
+      const V3 v0 = vert(t.idx[0]), v1 = vert(t.idx[1]), v2 = vert(t.idx[2]);
+      float g[12];
+      store3(g, v0); store3(g + 3, v0 - v1); store3(g + 6, v0 - v2);
+      store3(g + 9, normalize(cross(v1 - v0, v2 - v0)));
+      b->tri_geom.insert(b->tri_geom.end(), g, g + 12);
+      b->tri_vidx.push_back(t.idx[0]); b->tri_vidx.push_back(t.idx[1]); b->tri_vidx.push_back(t.idx[2]);
+      b->tri_info.push_back(t.material);
+      b->tri_info.push_back(0);
+    }
+  }
+  // Vertex::finalize_normal — HW3/src/Scene.cpp:872-877
+  b->vert_normal.assign((size_t)nv * 3, 0.f);
+  for (int i = 0; i < nv; i++) {
+    V3 n = vnorm[i];
+    if (vhas[i]) n = normalize(n);
+    store3(&b->vert_normal[3 * (size_t)i], n);
+  }
+
+  // ---- top-level objects in the reference's push order ----------------------
+  std::vector<Obj> top;
+  b->instances.clear(); b->spheres.clear(); b->triprims.clear();
+  for (const InstIn& in : b->inst_in) {
+    b200rt_instance fi;
+    std::memset(&fi, 0, sizeof(fi));
+    const b200rt_mesh& fm = b->meshes[in.mesh];
+    Box mb(load3(fm.root_box), load3(fm.root_box + 3));
+    Box ib;
+    if (in.direct) {
+      ib = mb;  // HW2: Mesh::get_bounding_box = bvh box (HW2/Mesh.h:17-19)
+      M4 id = M4::identity();
+      bool ok;
+      fill_xf(id, fi.inv, fi.nrm, fi.fwd, ok);
+      fi.flags |= B200RT_INST_DIRECT;
+    } else {
+      bool ok;
+      fill_xf(in.xf, fi.inv, fi.nrm, fi.fwd, ok);
+      if (!ok) {
+        g_host_error = "NOT INVERTIBLE MATRIX (mesh instance)";
+        return B200RT_E_SINGULAR;
+      }
+      ib = apply_transform(mb, in.xf);  // Mesh_instance ctor HW3/include/Mesh.h:101-111
+      motion_expand(ib, in.velocity);
+      if (in.velocity != V3(0.f)) fi.flags |= B200RT_INST_MOVING;
+    }
+    put_box(fi.box, fi.box + 3, ib);
+    store3(fi.velocity, in.velocity);
+    fi.mesh = in.mesh;
+    fi.material = in.material;
+    fi.texture = -1;
+    Obj o;
+    o.ref = B200RT_REF(B200RT_KIND_INSTANCE, b->instances.size());
+    o.box = ib;
+    top.push_back(o);
+    b->instances.push_back(fi);
+  }
+  if (!hw1) {
+    for (const TriIn& t : b->tri_in) {
+      if (!check_idx(t.idx[0]) || !check_idx(t.idx[1]) || !check_idx(t.idx[2])) {
+        g_host_error = "triangle index out of range";
+        return B200RT_E_INVALID;
+      }
+      b200rt_triprim ft;
+      std::memset(&ft, 0, sizeof(ft));
+      const V3 v0 = vert(t.idx[0]), v1 = vert(t.idx[1]), v2 = vert(t.idx[2]);
+      store3(ft.v0, v0); store3(ft.a1, v0 - v1); store3(ft.a2, v0 - v2);
+      store3(ft.normal, normalize(cross(v1 - v0, v2 - v0)));
+      Box tb = tri_box(v0, v1, v2);
+      const bool ident = is_identity(t.xf);  // Triangle ctor HW3/src/Triangle.cpp:20-41
+      bool ok;
+      fill_xf(t.xf, ft.inv, ft.nrm, nullptr, ok);
+      if (!ok) {
+        g_host_error = "NOT INVERTIBLE MATRIX (triangle)";
+        return B200RT_E_SINGULAR;
+      }
+      if (ident) ft.flags |= B200RT_XF_IDENTITY; else tb = apply_transform(tb, t.xf);
+      ft.material = t.material;
+      Obj o;
+      o.ref = B200RT_REF(B200RT_KIND_TRIPRIM, b->triprims.size());
+      o.box = tb;
+      top.push_back(o);
+      b->triprims.push_back(ft);
+    }
+  }
+  for (const SphIn& s : b->sph_in) {
+    if (!check_idx(s.center_vertex)) {
+      g_host_error = "sphere centre index out of range";
+      return B200RT_E_INVALID;
+    }
+    b200rt_sphere fs;
+    std::memset(&fs, 0, sizeof(fs));
+    const V3 c = vert(s.center_vertex);
+    store3(fs.center, c);
+    fs.radius = s.radius;
+    const bool ident = is_identity(s.xf);
+    bool ok;
+    fill_xf(s.xf, fs.inv, fs.nrm, fs.fwd, ok);
+    if (!ok) {
+      g_host_error = "NOT INVERTIBLE MATRIX (sphere)";
+      return B200RT_E_SINGULAR;
+    }
+    const V3 delta(s.radius);
+    Box sb(c - delta, c + delta);  // Sphere ctor HW3/include/Sphere.h:18-37
+    if (ident) fs.flags |= B200RT_XF_IDENTITY; else sb = apply_transform(sb, s.xf);
+    motion_expand(sb, s.velocity);
+    if (s.velocity != V3(0.f)) fs.flags |= B200RT_XF_MOVING;
+    store3(fs.velocity, s.velocity);
+    fs.material = s.material;
+    fs.texture = -1;
+    Obj o;
+    o.ref = B200RT_REF(B200RT_KIND_SPHERE, b->spheres.size());
+    o.box = sb;
+    top.push_back(o);
+    b->spheres.push_back(fs);
+  }
+
+  // ---- Scene::bvh = BVH::create_bvh(objects) — HW3/src/Scene.cpp:871 --------
+  Box root_box;
+  std::vector<uint32_t> order;
+  if (hw1 || top.empty()) {
+    b->desc.root = B200RT_REF_NONE;
+    for (const Obj& o : top) order.push_back(o.ref);
+  } else if (top.size() == 1) {
+    b->desc.root = top[0].ref;
+    root_box = top[0].box;
+    order.push_back(top[0].ref);
+  } else {
+    BuildOut bo{&b->nodes, &order};
+    uint32_t r = build_bvh(top, 0, (int)top.size(), 0, bo, root_box);
+    b->desc.root = B200RT_REF(B200RT_KIND_INNER, r);
+  }
+  put_box(b->desc.root_box, b->desc.root_box + 3, root_box);
+  for (size_t k = 0; k < order.size(); k++) {
+    const uint32_t r = order[k];
+    const uint32_t idx = B200RT_REF_INDEX(r);
+    switch (B200RT_REF_KIND(r)) {
+      case B200RT_KIND_INSTANCE: b->instances[idx].rank = (int)k; break;
+      case B200RT_KIND_SPHERE: b->spheres[idx].rank = (int)k; break;
+      case B200RT_KIND_TRIPRIM: b->triprims[idx].rank = (int)k; break;
+      default: break;
+    }
+  }
+
+  B200SceneDesc& d = b->desc;
+  d.n_nodes = (int)b->nodes.size();           d.nodes = b->nodes.data();
+  d.n_tris = (int)(b->tri_info.size() / 2);   d.tri_geom = b->tri_geom.data();
+  d.tri_vidx = b->tri_vidx.data();            d.tri_info = b->tri_info.data();
+  d.n_verts = nv;                             d.vert_pos = b->verts.data();
+  d.vert_normal = b->vert_normal.data();
+  d.n_meshes = (int)b->meshes.size();         d.meshes = b->meshes.data();
+  d.n_instances = (int)b->instances.size();   d.instances = b->instances.data();
+  d.n_spheres = (int)b->spheres.size();       d.spheres = b->spheres.data();
+  d.n_triprims = (int)b->triprims.size();     d.triprims = b->triprims.data();
+  d.n_materials = (int)b->materials.size();   d.materials = b->materials.data();
+  d.n_lights = (int)b->lights.size();         d.lights = b->lights.data();
+  d.n_cameras = (int)b->cameras.size();       d.cameras = b->cameras.data();
+  b->finished = true;
+  *out = &b->desc;
+  return B200RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+"""Output quantisation of each reference tree (last row).
+
+The reference does this on the host after the hot path (Pixel::get_color and
+main.cpp); it stays on the host here too and is shared by the GPU arm and the
+oracle arm, so image parity tests compare the float accumulators *through the
+same quantiser* the reference binary applies before lodepng.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import SEM_HW1, SEM_HW2, SEM_HW3, SEM_HW4
+
+
+def quantise(rgbw: np.ndarray, semantics: int) -> np.ndarray:
+    """rgbw[H,W,4] = Pixel{sum color*w, sum w} -> uint8[H,W,3] as the tree's main.cpp writes it."""
+    rgbw = np.asarray(rgbw, np.float32)
+    w = rgbw[..., 3:4]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        col = np.where(w == 0, np.float32(0), rgbw[..., :3] / w).astype(np.float32)
+    if semantics in (SEM_HW1, SEM_HW2):
+        # HW1/Scene.cpp:20-22, HW2/Pixel.h:24-26: min(255, max(0, int(c))) — C truncation toward zero
+        q = np.clip(np.trunc(np.nan_to_num(col, nan=0.0, posinf=3e9, neginf=-3e9)), 0, 255)
+        return q.astype(np.uint8)
+    if semantics in (SEM_HW3, SEM_HW4):
+        # HW3/include/Pixel.h:25-28 clamps in float, HW3/src/main.cpp then stores into unsigned char
+        q = np.minimum(np.float32(255), np.maximum(np.float32(0), np.nan_to_num(col, nan=0.0, posinf=3e9, neginf=-3e9)))
+        return np.trunc(q).astype(np.uint8)
+    raise NotImplementedError(f"quantise: semantics {semantics}")
+
+
+def read_png(path: str) -> np.ndarray:
+    from PIL import Image
+    return np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
+
+
+def write_png(path: str, rgb8: np.ndarray) -> None:
+    from PIL import Image
+    Image.fromarray(np.ascontiguousarray(rgb8, np.uint8), "RGB").save(path)
+
+
+def compare_8bit(a: np.ndarray, b: np.ndarray) -> dict:
+    """Pixel-level agreement: exact fraction, within-1-LSB fraction, max abs diff."""
+    d = np.abs(a.astype(np.int16) - b.astype(np.int16)).max(axis=-1)
+    return {"exact": float((d == 0).mean()), "within1": float((d <= 1).mean()), "max": int(d.max()),
+            "n": int(d.size)}

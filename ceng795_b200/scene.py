@@ -1,0 +1,413 @@
+"""Host-side mirror of the reference's ``Scene`` for the hot path.
+
+``Scene(xml_path, semantics)`` plays the role of ``Scene::Scene(const std::string&)``
+(HW3/src/Scene.cpp:314-878, HW1/Scene.cpp:125-348) for the XML elements the hot
+path consumes, and ``Scene.render_image(camera_index)`` the role of the thread
+fan-out over ``Scene::render_image`` (HW7/src/main.cpp:35-46).  XML text is
+parsed here; every float that feeds the renderer is then produced by the C++
+host builder (csrc/host_build.cpp) in the reference's arithmetic.
+
+There is no CPU fallback: rendering requires libb200rt.so and a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200RTError, SEM_BY_NAME, SEM_HW1, SEM_HW2, SEM_HW3
+
+
+def _floats(text, n=None):
+    a = np.array((text or "").split(), dtype=np.float64).astype(np.float32)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} numbers, got {a.size}: {text!r}")
+    return a
+
+
+def _big_floats(text):
+    return np.fromstring(text or "", sep=" ", dtype=np.float64).astype(np.float32)
+
+
+def _big_ints(text):
+    return np.fromstring(text or "", sep=" ", dtype=np.float64).astype(np.int32)
+
+
+def _child_text(el, name, default=None):
+    c = el.find(name)
+    if c is None or c.text is None:
+        return default
+    return c.text
+
+
+@dataclass
+class MeshSpec:
+    material: int
+    smooth: bool
+    faces: np.ndarray          # (F,3) int32, 0-based, vertex offset applied
+    transforms: list = field(default_factory=list)   # [(type, index0), ...]
+    velocity: np.ndarray = None
+
+
+@dataclass
+class InstanceSpec:
+    base_mesh: int
+    material: int
+    reset_transform: bool
+    transforms: list
+    velocity: np.ndarray
+
+
+@dataclass
+class SceneSpec:
+    semantics: int
+    background: np.ndarray
+    ambient: np.ndarray
+    shadow_eps: float
+    max_depth: int
+    cameras: list
+    point_lights: list
+    area_lights: list
+    materials: list
+    scalings: list
+    translations: list
+    rotations: list
+    vertices: np.ndarray
+    meshes: list
+    instances: list
+    triangles: list
+    spheres: list
+
+
+def _parse_transform_list(text):
+    toks = (text or "").split()
+    out = []
+    i = 0
+    # the reference reads `char type; int index;` pairs, so "t1" and "t 1" both parse
+    while i < len(toks):
+        tok = toks[i]
+        if len(tok) > 1:
+            out.append((tok[0], int(tok[1:]) - 1))
+            i += 1
+        else:
+            out.append((tok, int(toks[i + 1]) - 1))
+            i += 2
+    return out
+
+
+def parse_xml(path_or_text: str, semantics) -> SceneSpec:
+    """Parse the ceng795 XML dialect (elements on the hot path only)."""
+    sem = SEM_BY_NAME[semantics] if isinstance(semantics, str) else int(semantics)
+    if path_or_text.lstrip().startswith("<"):
+        root = ET.fromstring(path_or_text)
+    else:
+        root = ET.parse(path_or_text).getroot()
+    bg = _floats(_child_text(root, "BackgroundColor", "0 0 0"), 3)
+    seps = float(_floats(_child_text(root, "ShadowRayEpsilon", "0.001"), 1)[0])
+    depth = int(float(_child_text(root, "MaxRecursionDepth", "0")))
+    cams = []
+    for cel in root.find("Cameras").findall("Camera"):
+        if cel.get("type") == "simple":
+            raise B200RTError("Camera type=simple is not supported yet")
+        res = _floats(_child_text(cel, "ImageResolution"), 2)
+        cams.append(dict(
+            position=_floats(_child_text(cel, "Position"), 3), gaze=_floats(_child_text(cel, "Gaze"), 3),
+            up=_floats(_child_text(cel, "Up"), 3), near_plane=_floats(_child_text(cel, "NearPlane"), 4),
+            near_distance=float(_floats(_child_text(cel, "NearDistance"), 1)[0]),
+            width=int(res[0]), height=int(res[1]),
+            num_samples=int(float(_child_text(cel, "NumSamples", "1"))),
+            focus_distance=float(_floats(_child_text(cel, "FocusDistance", "0"), 1)[0]),
+            aperture_size=float(_floats(_child_text(cel, "ApertureSize", "0"), 1)[0]),
+            image_name=(_child_text(cel, "ImageName", "out.png") or "out.png").strip()))
+    lights = root.find("Lights")
+    ambient = _floats(_child_text(lights, "AmbientLight", "0 0 0"), 3)
+    pls = [dict(position=_floats(_child_text(l, "Position"), 3), intensity=_floats(_child_text(l, "Intensity"), 3))
+           for l in lights.findall("PointLight")]
+    als = []
+    if sem >= SEM_HW3:
+        for l in lights.findall("AreaLight"):
+            als.append(dict(position=_floats(_child_text(l, "Position"), 3),
+                            intensity=_floats(_child_text(l, "Intensity"), 3),
+                            edge1=_floats(_child_text(l, "EdgeVector1"), 3),
+                            edge2=_floats(_child_text(l, "EdgeVector2"), 3)))
+    mats = []
+    for m in root.find("Materials").findall("Material"):
+        mats.append(dict(
+            ambient=_floats(_child_text(m, "AmbientReflectance", "0 0 0"), 3),
+            diffuse=_floats(_child_text(m, "DiffuseReflectance", "0 0 0"), 3),
+            specular=_floats(_child_text(m, "SpecularReflectance", "0 0 0"), 3),
+            mirror=_floats(_child_text(m, "MirrorReflectance", "0 0 0"), 3),
+            roughness=float(_floats(_child_text(m, "Roughness", "0"), 1)[0]) if sem >= SEM_HW3 else 0.0,
+            phong_exponent=float(_floats(_child_text(m, "PhongExponent", "1"), 1)[0]),
+            transparency=_floats(_child_text(m, "Transparency", "0 0 0"), 3) if sem >= SEM_HW2 else np.zeros(3, np.float32),
+            refraction_index=float(_floats(_child_text(m, "RefractionIndex", "1.0"), 1)[0]) if sem >= SEM_HW2 else 1.0))
+    scal, tran, rot = [], [], []
+    tel = root.find("Transformations")
+    if tel is not None and sem >= SEM_HW3:
+        scal = [_floats(e.text, 3) for e in tel.findall("Scaling")]
+        tran = [_floats(e.text, 3) for e in tel.findall("Translation")]
+        rot = [_floats(e.text, 4) for e in tel.findall("Rotation")]
+    verts = _big_floats(root.find("VertexData").text).reshape(-1, 3)
+    objs = root.find("Objects")
+    meshes, insts, tris, sphs = [], [], [], []
+    for mel in objs.findall("Mesh"):
+        fel = mel.find("Faces")
+        if fel.get("plyFile"):
+            raise B200RTError("plyFile meshes are host I/O (out of scope, SURVEY §2b)")
+        off = int(fel.get("vertexOffset", "0")) if sem >= SEM_HW3 else 0
+        faces = _big_ints(fel.text).reshape(-1, 3) - 1 + off
+        vel = _floats(_child_text(mel, "MotionBlur", "0 0 0"), 3) if sem >= SEM_HW3 else np.zeros(3, np.float32)
+        meshes.append(MeshSpec(
+            material=int(float(_child_text(mel, "Material"))) - 1,
+            smooth=(mel.get("shadingMode") == "smooth") and sem >= SEM_HW3,
+            faces=np.ascontiguousarray(faces, dtype=np.int32),
+            transforms=_parse_transform_list(_child_text(mel, "Transformations", "")) if sem >= SEM_HW3 else [],
+            velocity=vel))
+    if sem >= SEM_HW3:
+        for iel in objs.findall("MeshInstance"):
+            insts.append(InstanceSpec(
+                base_mesh=int(iel.get("baseMeshId")) - 1,
+                material=int(float(_child_text(iel, "Material"))) - 1,
+                reset_transform=(iel.get("resetTransform") == "true"),
+                transforms=_parse_transform_list(_child_text(iel, "Transformations", "")),
+                velocity=_floats(_child_text(iel, "MotionBlur", "0 0 0"), 3)))
+    for tel_ in objs.findall("Triangle"):
+        idx = _floats(_child_text(tel_, "Indices"), 3).astype(np.int32) - 1
+        tris.append(dict(material=int(float(_child_text(tel_, "Material"))) - 1, idx=idx,
+                         transforms=_parse_transform_list(_child_text(tel_, "Transformations", "")) if sem >= SEM_HW3 else []))
+    for sel in objs.findall("Sphere"):
+        sphs.append(dict(material=int(float(_child_text(sel, "Material"))) - 1,
+                         center=int(float(_child_text(sel, "Center"))) - 1,
+                         radius=float(_floats(_child_text(sel, "Radius"), 1)[0]),
+                         transforms=_parse_transform_list(_child_text(sel, "Transformations", "")) if sem >= SEM_HW3 else [],
+                         velocity=_floats(_child_text(sel, "MotionBlur", "0 0 0"), 3) if sem >= SEM_HW3 else np.zeros(3, np.float32)))
+    if sem == SEM_HW1 and tris:
+        # HW1/Scene.cpp:320 passes `mesh.material_id` (the last mesh's) for every stand-alone
+        # triangle; without any mesh the reference reads an uninitialised int.
+        if meshes:
+            for t in tris:
+                t["material"] = meshes[-1].material
+    return SceneSpec(sem, bg, ambient, seps, depth, cams, pls, als, mats, scal, tran, rot,
+                     np.ascontiguousarray(verts, dtype=np.float32), meshes, insts, tris, sphs)
+
+
+def _arr3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class HostScene:
+    """Owns a b200rt_builder and the flattened B200SceneDesc it produced."""
+
+    def __init__(self, spec: SceneSpec):
+        L = _lib.load()
+        self._L = L
+        self.spec = spec
+        self._b = L.b200rt_builder_create(spec.semantics)
+        if not self._b:
+            raise B200RTError("b200rt_builder_create failed")
+        self._keep = []
+        fp = _lib.fptr
+        bg = np.ascontiguousarray(spec.background, np.float32)
+        am = np.ascontiguousarray(spec.ambient, np.float32)
+        _lib.check(L.b200rt_builder_set_globals(self._b, fp(bg), fp(am), spec.shadow_eps, spec.max_depth), "set_globals")
+        for c in spec.cameras:
+            ci = _lib.CameraIn()
+            ci.position = _arr3(c["position"]); ci.gaze = _arr3(c["gaze"]); ci.up = _arr3(c["up"])
+            ci.near_plane = (C.c_float * 4)(*[float(x) for x in c["near_plane"]])
+            ci.near_distance = c["near_distance"]; ci.width = c["width"]; ci.height = c["height"]
+            ci.num_samples = c["num_samples"]; ci.focus_distance = c["focus_distance"]
+            ci.aperture_size = c["aperture_size"]
+            rc = L.b200rt_builder_add_camera(self._b, C.byref(ci))
+            if rc < 0:
+                _lib.check(rc, "add_camera")
+        for m in spec.materials:
+            mm = _lib.Material()
+            mm.ambient = _arr3(m["ambient"]); mm.diffuse = _arr3(m["diffuse"]); mm.specular = _arr3(m["specular"])
+            mm.mirror = _arr3(m["mirror"]); mm.transparency = _arr3(m["transparency"])
+            mm.roughness = m["roughness"]; mm.refraction_index = m["refraction_index"]
+            mm.phong_exponent = m["phong_exponent"]; mm.brdf = -1
+            L.b200rt_builder_add_material(self._b, C.byref(mm))
+        for l in spec.point_lights:
+            ll = _lib.Light(); ll.kind = _lib.LIGHT_POINT
+            ll.position = _arr3(l["position"]); ll.intensity = _arr3(l["intensity"]); ll.object = -1
+            L.b200rt_builder_add_light(self._b, C.byref(ll))
+        for l in spec.area_lights:
+            ll = _lib.Light(); ll.kind = _lib.LIGHT_AREA
+            ll.position = _arr3(l["position"]); ll.intensity = _arr3(l["intensity"])
+            ll.edge1 = _arr3(l["edge1"]); ll.edge2 = _arr3(l["edge2"]); ll.object = -1
+            L.b200rt_builder_add_light(self._b, C.byref(ll))
+        v = np.ascontiguousarray(spec.vertices, np.float32)
+        self._keep.append(v)
+        _lib.check(L.b200rt_builder_set_vertices(self._b, v.ctypes.data, v.shape[0]), "set_vertices")
+        for m in spec.meshes:
+            xf = self._compose(m.transforms, None)
+            vel = np.ascontiguousarray(m.velocity, np.float32)
+            rc = L.b200rt_builder_add_mesh(self._b, m.material, int(m.smooth), m.faces.ctypes.data,
+                                           m.faces.shape[0], fp(xf), fp(vel))
+            if rc < 0:
+                _lib.check(rc, "add_mesh")
+        for i in spec.instances:
+            base = None if i.reset_transform else self._compose(spec.meshes[i.base_mesh].transforms, None)
+            xf = self._compose(i.transforms, base)
+            vel = np.ascontiguousarray(i.velocity, np.float32)
+            rc = L.b200rt_builder_add_instance(self._b, i.base_mesh, i.material, fp(xf), fp(vel))
+            if rc < 0:
+                _lib.check(rc, "add_instance")
+        for t in spec.triangles:
+            xf = self._compose(t["transforms"], None)
+            idx = (C.c_int32 * 3)(*[int(x) for x in t["idx"]])
+            rc = L.b200rt_builder_add_triangle(self._b, t["material"], idx, fp(xf))
+            if rc < 0:
+                _lib.check(rc, "add_triangle")
+        for s in spec.spheres:
+            xf = self._compose(s["transforms"], None)
+            vel = np.ascontiguousarray(s["velocity"], np.float32)
+            rc = L.b200rt_builder_add_sphere(self._b, s["material"], s["center"], s["radius"], fp(xf), fp(vel))
+            if rc < 0:
+                _lib.check(rc, "add_sphere")
+        out = C.POINTER(_lib.SceneDesc)()
+        _lib.check(L.b200rt_builder_finish(self._b, C.byref(out)), "builder_finish")
+        self.desc_ptr = out
+        self.desc = out.contents
+
+    def _compose(self, ops, base):
+        """`M = T_k * M` in list order — HW3/src/Scene.cpp:636-657."""
+        L = self._L
+        fp = _lib.fptr
+        m = np.zeros(16, np.float32)
+        if base is None:
+            L.b200rt_xf_identity(fp(m))
+        else:
+            m[:] = base
+        t = np.zeros(16, np.float32)
+        o = np.zeros(16, np.float32)
+        for kind, idx in ops:
+            if kind == "s":
+                s = self.spec.scalings[idx]
+                L.b200rt_xf_scaling(float(s[0]), float(s[1]), float(s[2]), fp(t))
+            elif kind == "t":
+                s = self.spec.translations[idx]
+                L.b200rt_xf_translation(float(s[0]), float(s[1]), float(s[2]), fp(t))
+            elif kind == "r":
+                s = self.spec.rotations[idx]
+                L.b200rt_xf_rotation(float(s[0]), float(s[1]), float(s[2]), float(s[3]), fp(t))
+            else:
+                continue  # the reference's switch ignores unknown letters
+            L.b200rt_xf_mul(fp(t), fp(m), fp(o))
+            m[:] = o
+        return m
+
+    # -- numpy views of the flattened description (tests / tools) ---------------
+    def nodes(self):
+        d = self.desc
+        if d.n_nodes == 0:
+            return np.zeros((0, 16), np.uint32)
+        return np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint32)), shape=(d.n_nodes, 16))
+
+    def tri_geom(self):
+        d = self.desc
+        return np.ctypeslib.as_array(d.tri_geom, shape=(d.n_tris, 12)) if d.n_tris else np.zeros((0, 12), np.float32)
+
+    def close(self):
+        if getattr(self, "_b", None):
+            self._L.b200rt_builder_destroy(self._b)
+            self._b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scene:
+    """Reference-facing object: ``Scene(xml).render_image(camera_index)``."""
+
+    def __init__(self, xml: str, semantics="hw3", device: int = 0, upload: bool = True):
+        self.spec = parse_xml(xml, semantics)
+        self.host = HostScene(self.spec)
+        self.semantics = self.spec.semantics
+        self.device = device
+        self._scene = None
+        self._L = _lib.load()
+        if upload:
+            self.upload()
+
+    @property
+    def cameras(self):
+        return self.spec.cameras
+
+    def upload(self):
+        if self._scene is not None:
+            return
+        h = C.c_void_p()
+        _lib.check(self._L.b200rt_scene_create(self.host.desc_ptr, self.device, C.byref(h)), "b200rt_scene_create")
+        self._scene = h
+
+    def _opts(self, **kw):
+        o = _lib.RenderOpts()
+        o.row_stride = 1
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def image_size(self, camera_index=0):
+        c = self.spec.cameras[camera_index]
+        return c["width"], c["height"]
+
+    def render_image(self, camera_index: int = 0, out: np.ndarray | None = None, **opts):
+        """Returns (rgbw[H,W,4] float32, RenderStats).  rgbw = Pixel{color, weight}."""
+        self.upload()
+        w, h = self.image_size(camera_index)
+        if out is None:
+            out = np.zeros((h, w, 4), np.float32)
+        st = _lib.RenderStats()
+        o = self._opts(**opts)
+        _lib.check(self._L.b200rt_render(self._scene, camera_index, C.byref(o), out.ctypes.data, C.byref(st)),
+                   "b200rt_render")
+        return out, st
+
+    def render_device(self, camera_index: int = 0, **opts):
+        self.upload()
+        st = _lib.RenderStats()
+        o = self._opts(**opts)
+        p = C.c_void_p()
+        _lib.check(self._L.b200rt_render_device(self._scene, camera_index, C.byref(o), C.byref(p), C.byref(st)),
+                   "b200rt_render_device")
+        return p.value, st
+
+    def primary_ids(self, camera_index: int = 0, **opts):
+        self.upload()
+        w, h = self.image_size(camera_index)
+        ids = np.zeros((h, w, 2), np.int32)
+        t = np.zeros((h, w), np.float32)
+        o = self._opts(**opts)
+        _lib.check(self._L.b200rt_primary_ids(self._scene, camera_index, C.byref(o), ids.ctypes.data, t.ctypes.data),
+                   "b200rt_primary_ids")
+        return ids, t
+
+    def trace_rays(self, rays: np.ndarray, exact: bool = False):
+        self.upload()
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        ids = np.zeros((n, 2), np.int32)
+        t = np.zeros(n, np.float32)
+        st = _lib.RenderStats()
+        _lib.check(self._L.b200rt_trace_rays(self._scene, rays.ctypes.data, n, int(exact), ids.ctypes.data,
+                                             t.ctypes.data, C.byref(st)), "b200rt_trace_rays")
+        return ids, t, st
+
+    def close(self):
+        if self._scene is not None:
+            self._L.b200rt_scene_destroy(self._scene)
+            self._scene = None
+        self.host.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

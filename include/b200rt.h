@@ -1,0 +1,303 @@
+/*
+ * b200rt.h — C ABI of the B200-native rendering core that sits behind the
+ * ceng795 ray tracer's `Scene::render_image` seam.
+ *
+ * The reference has no FFI; its only stable seam is the set of `Scene` member
+ * functions that `main.cpp` fans out over std::threads:
+ *   HW1      void Scene::render_image(int, Vector3i*, int, int) const   HW1/Scene.h:34-35
+ *   HW2..HW7 void Scene::render_image(int, Pixel*,    int, int) const   HW7/include/Scene.h:59-60
+ *   PPM      reset_hash_grid / eye_trace_lines / build_hash_grid /
+ *            trace_n_photons / density_estimation                      PPM/include/Scene.h:48-55
+ *
+ * Every entry point below replaces one of those calls (cited per function).
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ * All functions return 0 on success or a negative B200RT_E_* code; they never
+ * throw.  `b200rt_last_error()` returns a thread-local message.
+ *
+ * Two layers live in this header:
+ *   1. b200rt_builder_*  — host-side scene assembly.  Restates (in C++, IEEE
+ *      binary32, no FMA contraction) the host arithmetic the reference does at
+ *      load time: transformation matrices, camera frames, triangle records,
+ *      vertex normals and — crucially — the reference's BVH *topology*
+ *      (HW7/src/Bounding_volume_hierarchy.cpp:3-29) so that the flattened
+ *      tree's DFS leaf order equals the reference's tie-breaking order.
+ *      INTEGRATION.md shows the alternative producer of the same B200SceneDesc:
+ *      a flatten.cpp TU compiled inside the reference tree.
+ *   2. b200rt_scene_* / b200rt_render* / b200rt_ppm_* — the device side.
+ */
+#ifndef B200RT_H_
+#define B200RT_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------ */
+#define B200RT_OK 0
+#define B200RT_E_INVALID (-1)   /* bad argument / malformed description      */
+#define B200RT_E_CUDA (-2)      /* CUDA runtime error (see last_error)        */
+#define B200RT_E_NOGPU (-3)     /* no CUDA device: there is NO CPU fallback   */
+#define B200RT_E_UNSUPPORTED (-4)
+#define B200RT_E_SINGULAR (-5)  /* reference exit(-1): "NOT INVERTIBLE MATRIX" HW3/src/Transformation.cpp:78-82 */
+
+/* ---- per-tree semantics -------------------------- */
+enum b200rt_semantics {
+  B200RT_SEM_HW1 = 1,
+  B200RT_SEM_HW2 = 2,
+  B200RT_SEM_HW3 = 3,
+  B200RT_SEM_HW4 = 4,
+  B200RT_SEM_HW5 = 5,
+  B200RT_SEM_HW6 = 6,
+  B200RT_SEM_HW7 = 7,
+  B200RT_SEM_PPM = 8
+};
+
+/* ---- BVH child references ----------------------------------------------- */
+#define B200RT_KIND_INNER 0u    /* index into nodes[]                          */
+#define B200RT_KIND_TRI 1u      /* mesh triangle: index into tri_* arrays      */
+#define B200RT_KIND_SPHERE 2u   /* index into spheres[]                        */
+#define B200RT_KIND_TRIPRIM 3u  /* stand-alone Triangle with own transform     */
+#define B200RT_KIND_INSTANCE 4u /* index into instances[]                      */
+#define B200RT_KIND_NONE 15u
+#define B200RT_REF(kind, idx) ((((uint32_t)(kind)) << 28) | ((uint32_t)(idx)))
+#define B200RT_REF_KIND(r) ((r) >> 28)
+#define B200RT_REF_INDEX(r) ((r)&0x0FFFFFFFu)
+#define B200RT_REF_NONE B200RT_REF(B200RT_KIND_NONE, 0)
+
+/* One inner node = the reference's `BVH` object (HW7 72 B pointer node) with
+ * its two children's gate boxes pulled in, 64 B, 64-byte aligned.  The box of
+ * a child is only meaningful (and only tested) for INNER and INSTANCE
+ * children: the reference gates exactly those with Bounding_box::intersect
+ * (BVH::intersect HW3/src/Bounding_volume_hierarchy.cpp:32-35,
+ *  Mesh_instance::intersect HW3/include/Mesh.h:59-62); triangles and spheres
+ * are tested unconditionally once their parent is visited. */
+typedef struct b200rt_bvh_node {
+  float lmin[3], lmax[3];
+  float rmin[3], rmax[3];
+  uint32_t left, right;
+  uint32_t pad[2];
+} b200rt_bvh_node;
+
+typedef struct b200rt_mesh {
+  uint32_t root;      /* child ref of Mesh::bvh (INNER, or TRI when 1 triangle) */
+  float root_box[6];  /* min xyz, max xyz of the root (gate when INNER)         */
+  int32_t tri_begin, tri_count; /* triangles [begin,begin+count) in DFS order  */
+  int32_t node_begin, node_count;
+} b200rt_mesh;
+
+#define B200RT_INST_MOVING 1u     /* velocity != 0: per-ray inverse (HW3/include/Mesh.h:76-95) */
+#define B200RT_INST_DIRECT 2u     /* HW2: Mesh sits in the top BVH itself, no gate / transform  */
+#define B200RT_INST_REFRACTIVE 4u /* HW7: culling off inside glass (HW7/include/Mesh.h:73-75)   */
+typedef struct b200rt_instance {
+  float inv[12];      /* rows 0..2 of M^-1 (point: + column 3)                */
+  float nrm[9];       /* upper 3x3 of transpose(M^-1)                         */
+  float fwd[16];      /* M, only used when MOVING                              */
+  float box[6];       /* world-space gate box                                 */
+  float velocity[3];
+  int32_t mesh;
+  int32_t material;
+  int32_t texture;
+  uint32_t flags;
+  int32_t rank;       /* DFS position among top-level objects (tie-break)     */
+  int32_t pad[3];
+} b200rt_instance;
+
+#define B200RT_XF_IDENTITY 1u
+#define B200RT_XF_MOVING 2u
+typedef struct b200rt_sphere {
+  float center[3];
+  float radius;
+  float inv[12];
+  float nrm[9];
+  float fwd[16];
+  float velocity[3];
+  int32_t material;
+  int32_t texture;
+  uint32_t flags;
+  int32_t rank;
+  int32_t pad[2];
+} b200rt_sphere;
+
+typedef struct b200rt_triprim {
+  float v0[3], a1[3], a2[3], normal[3]; /* a1 = v0-v1, a2 = v0-v2 (object space) */
+  float inv[12];
+  float nrm[9];
+  int32_t material;
+  uint32_t flags;
+  int32_t rank;
+} b200rt_triprim;
+
+typedef struct b200rt_material {
+  float ambient[3], diffuse[3], specular[3], mirror[3], transparency[3];
+  float roughness, refraction_index, phong_exponent;
+  int32_t brdf;      /* -1 = built-in Blinn-Phong                               */
+  int32_t degamma;
+  float pad[4];
+} b200rt_material;  /* 96 B */
+
+enum b200rt_light_kind {
+  B200RT_LIGHT_POINT = 0,
+  B200RT_LIGHT_AREA = 1,
+  B200RT_LIGHT_SPOT = 2,
+  B200RT_LIGHT_DIRECTIONAL = 3,
+  B200RT_LIGHT_ENV = 4,
+  B200RT_LIGHT_MESH = 5,
+  B200RT_LIGHT_SPHERE = 6
+};
+typedef struct b200rt_light {
+  int32_t kind;
+  float position[3];
+  float intensity[3];
+  float edge1[3], edge2[3], normal[3]; /* area; spot: edge1 = direction, edge2 = {cos(cov/2), cos(fall/2), 0} */
+  int32_t object;                      /* mesh / sphere lights: index of the emissive object */
+  float pad[4];
+} b200rt_light;
+
+typedef struct b200rt_camera {
+  float e[3], u[3], v[3], w[3];
+  float top_left[3], su[3], sv[3];       /* Camera ctor HW3/include/Camera.h:17-34 */
+  float left, right, bottom, top, distance; /* image plane as used (after DOF rescale) */
+  int32_t width, height;
+  int32_t samples_sqrt;                  /* (int)sqrt(NumSamples), min 1            */
+  float aperture;
+  int32_t pad[3];
+} b200rt_camera;
+
+typedef struct B200SceneDesc {
+  int32_t semantics;
+  int32_t max_depth;
+  float background[3];
+  float ambient[3];
+  float shadow_eps;
+  float isect_eps;     /* kEpsilon / intersection_test_epsilon: 1e-6 (PPM 1e-4) */
+
+  uint32_t root;       /* Scene::bvh: INNER, a single object, or NONE          */
+  float root_box[6];
+
+  int32_t n_nodes;
+  const b200rt_bvh_node* nodes;
+
+  int32_t n_tris;
+  const float* tri_geom;    /* 12 floats per triangle: v0, a1=v0-v1, a2=v0-v2, face normal */
+  const int32_t* tri_vidx;  /* 3 per triangle: indices into vert_* (smooth shading, uv)     */
+  const int32_t* tri_info;  /* 2 per triangle: material, flags (bit0 = smooth)             */
+
+  int32_t n_verts;
+  const float* vert_pos;    /* 3 per vertex */
+  const float* vert_normal; /* 3 per vertex, finalised (HW3/src/Scene.cpp:872-877) */
+
+  int32_t n_meshes;
+  const b200rt_mesh* meshes;
+  int32_t n_instances;
+  const b200rt_instance* instances;
+  int32_t n_spheres;
+  const b200rt_sphere* spheres;
+  int32_t n_triprims;
+  const b200rt_triprim* triprims;
+  int32_t n_materials;
+  const b200rt_material* materials;
+  int32_t n_lights;
+  const b200rt_light* lights;
+  int32_t n_cameras;
+  const b200rt_camera* cameras;
+} B200SceneDesc;
+
+/* ======================================================================== */
+/* 1. Host-side builder (restates the reference's load-time arithmetic)      */
+/* ======================================================================== */
+typedef struct b200rt_builder b200rt_builder;
+
+/* Transformation helpers: row-major 4x4, same arithmetic as
+ * Scaling/Translation/Rotation ctors (HW3/src/Transformation.cpp:6-70) and
+ * Matrix4x4::operator* (HW3/src/Matrix4x4.cpp:52-62). angle in DEGREES, the
+ * helper applies the reference's `angle*degree_to_pi` (HW3/src/Scene.cpp:322,615). */
+void b200rt_xf_identity(float out[16]);
+void b200rt_xf_scaling(float x, float y, float z, float out[16]);
+void b200rt_xf_translation(float x, float y, float z, float out[16]);
+void b200rt_xf_rotation(float angle_deg, float x, float y, float z, float out[16]);
+void b200rt_xf_mul(const float a[16], const float b[16], float out[16]);
+int b200rt_xf_invert(const float m[16], float out[16]); /* Matrix4x4::invert_matrix */
+
+typedef struct b200rt_camera_in {
+  float position[3], gaze[3], up[3];
+  float near_plane[4]; /* l r b t */
+  float near_distance;
+  int32_t width, height;
+  int32_t num_samples;     /* as written in the XML; builder applies (int)sqrt */
+  float focus_distance, aperture_size;
+} b200rt_camera_in;
+
+b200rt_builder* b200rt_builder_create(int semantics);
+void b200rt_builder_destroy(b200rt_builder*);
+int b200rt_builder_set_globals(b200rt_builder*, const float background[3], const float ambient[3],
+                               float shadow_eps, int max_depth);
+int b200rt_builder_add_camera(b200rt_builder*, const b200rt_camera_in*);
+int b200rt_builder_add_material(b200rt_builder*, const b200rt_material*);
+int b200rt_builder_add_light(b200rt_builder*, const b200rt_light*);
+int b200rt_builder_set_vertices(b200rt_builder*, const float* xyz, int n);
+/* faces: 0-based indices, vertex_offset already added. Returns mesh id (>=0).
+ * HW3+: also appends the implicit base instance (HW3/src/Scene.cpp:703-707). */
+int b200rt_builder_add_mesh(b200rt_builder*, int material, int smooth, const int32_t* faces,
+                            int n_faces, const float base_xf[16], const float velocity[3]);
+int b200rt_builder_add_instance(b200rt_builder*, int base_mesh, int material,
+                                const float xf[16], const float velocity[3]);
+int b200rt_builder_add_triangle(b200rt_builder*, int material, const int32_t idx[3],
+                                const float xf[16]);
+int b200rt_builder_add_sphere(b200rt_builder*, int material, int center_vertex, float radius,
+                              const float xf[16], const float velocity[3]);
+/* Builds per-mesh and top-level BVHs in the reference's topology, finalises
+ * vertex normals and flattens.  The returned desc is owned by the builder. */
+int b200rt_builder_finish(b200rt_builder*, const B200SceneDesc** out);
+
+/* ======================================================================== */
+/* 2. Device side                                                            */
+/* ======================================================================== */
+typedef struct b200rt_scene b200rt_scene;
+
+typedef struct B200RenderOpts {
+  int32_t row_begin, row_end; /* render rows [begin,end) (0,0 = all) : multi-GPU tile split */
+  int32_t row_stride;         /* 1 = contiguous; >1 = reference-style interleave `j += height_increase` */
+  uint64_t seed;              /* counter-based RNG key for stochastic configs */
+  int32_t sample_begin, sample_end; /* strata subset [begin,end) of samples_sqrt^2 (0,0 = all) */
+  int32_t exact_traversal;    /* 1 = visit every gated node like the reference (no t-pruning) */
+  int32_t pad[5];
+} B200RenderOpts;
+
+typedef struct B200RenderStats {
+  uint64_t rays_primary, rays_shadow, rays_secondary;
+  uint64_t nodes_visited, tris_tested, spheres_tested, instances_entered;
+  float ms_generate, ms_extend, ms_shade, ms_shadow, ms_total;
+  int32_t waves, launches;
+} B200RenderStats;
+
+int b200rt_device_count(void);
+/* Copies the description into HBM on `device`; the caller keeps its host data. */
+int b200rt_scene_create(const B200SceneDesc*, int device, b200rt_scene** out);
+void b200rt_scene_destroy(b200rt_scene*);
+
+/* Replaces the thread fan-out over Scene::render_image (HW7/src/main.cpp:35-46):
+ * renders camera `camera_index` and writes W*H float4 {sum(color*w).rgb, sum(w)}
+ * — the contents of the reference's Pixel{color, weight} — into caller-owned
+ * HOST memory. */
+int b200rt_render(b200rt_scene*, int camera_index, const B200RenderOpts*, float* rgbw_out,
+                  B200RenderStats* stats_out);
+/* Same, but the result stays in HBM (device pointer returned, owned by scene). */
+int b200rt_render_device(b200rt_scene*, int camera_index, const B200RenderOpts*,
+                         float** d_rgbw_out, B200RenderStats* stats_out);
+/* Parity hook: closest primary hit per pixel. ids_out[2*p] = top-level object
+ * rank (DFS position in Scene::bvh, -1 = miss), ids_out[2*p+1] = triangle index
+ * inside the mesh's DFS order (or -1); t_out[p] = hit t (inf on miss). */
+int b200rt_primary_ids(b200rt_scene*, int camera_index, const B200RenderOpts*, int32_t* ids_out,
+                       float* t_out);
+/* Generic closest-hit query on caller-provided rays (host arrays, 8 floats per
+ * ray: o.xyz, time, d.xyz, tmax-unused).  Test/measurement hook for a4-a8. */
+int b200rt_trace_rays(b200rt_scene*, const float* rays, int64_t n, int32_t exact_traversal,
+                      int32_t* ids_out, float* t_out, B200RenderStats* stats_out);
+
+const char* b200rt_last_error(void);
+const char* b200rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RT_H_ */

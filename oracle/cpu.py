@@ -1,0 +1,140 @@
+"""Python handle on the CPU oracle (oracle/oracle.c -> liboracle.so) and on the
+compiled, untouched reference binaries in oracle/_ref/ (built by build_ref.sh).
+
+TEST INFRASTRUCTURE ONLY: the checker, never the thing measured or shipped.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+_TREE_BIN = {"hw1": "hw1_raytracer", "hw2": "hw2_raytracer", "hw3": "hw3_raytracer",
+             "hw4": "hw4_raytracer", "hw7": "hw7_raytracer", "ppm": "ppm_raytracer"}
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays_primary", "rays_shadow", "rays_secondary", "nodes_visited",
+                                          "tris_tested", "spheres_tested", "instances_entered")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+    @property
+    def rays_total(self):
+        return int(self.rays_primary + self.rays_shadow + self.rays_secondary)
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            from ceng795_b200 import _build
+            _build.build_oracle()
+        _lib = C.CDLL(path)
+        _lib.oracle_render.restype = C.c_int
+        _lib.oracle_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.POINTER(Counters)]
+        _lib.oracle_trace_rays.restype = C.c_int
+        _lib.oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.POINTER(Counters)]
+        _lib.oracle_box_intersect.restype = C.c_float
+        _lib.oracle_box_intersect.argtypes = [C.c_void_p] * 4 + [C.c_float]
+        _lib.oracle_tri_intersect.restype = C.c_int
+        _lib.oracle_tri_intersect.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_float, C.c_void_p]
+    return _lib
+
+
+def _desc_addr(host_scene):
+    return C.cast(host_scene.desc_ptr, C.c_void_p)
+
+
+def render(host_scene, camera_index=0, rows=(0, 0), seed=0, want_image=True, want_ids=False, threads=None):
+    """Returns (rgbw[H,W,4] or None, ids[H,W,2] or None, t[H,W] or None, Counters)."""
+    L = load()
+    cam = host_scene.spec.cameras[camera_index]
+    w, h = cam["width"], cam["height"]
+    rgbw = np.zeros((h, w, 4), np.float32) if want_image else None
+    ids = np.full((h, w, 2), -1, np.int32) if want_ids else None
+    t = np.full((h, w), np.inf, np.float32) if want_ids else None
+    cnt = Counters()
+    old = os.environ.get("OMP_NUM_THREADS")
+    rc = L.oracle_render(_desc_addr(host_scene), camera_index, rows[0], rows[1], seed,
+                         rgbw.ctypes.data if want_image else None,
+                         ids.ctypes.data if want_ids else None, t.ctypes.data if want_ids else None,
+                         C.byref(cnt))
+    if rc != 0:
+        raise RuntimeError(f"oracle_render rc={rc}")
+    return rgbw, ids, t, cnt
+
+
+def trace_rays(host_scene, rays):
+    L = load()
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    n = rays.shape[0]
+    ids = np.zeros((n, 2), np.int32)
+    t = np.zeros(n, np.float32)
+    cnt = Counters()
+    rc = L.oracle_trace_rays(_desc_addr(host_scene), rays.ctypes.data, n, ids.ctypes.data, t.ctypes.data,
+                             C.byref(cnt))
+    if rc != 0:
+        raise RuntimeError(f"oracle_trace_rays rc={rc}")
+    return ids, t, cnt
+
+
+def have_ref(tree: str) -> bool:
+    return os.path.exists(os.path.join(REF_DIR, _TREE_BIN[tree]))
+
+
+_TIME_UNITS = {"day": 86400e3, "hour": 3600e3, "minute": 60e3, "second": 1e3, "millisecond": 1.0,
+               "microsecond": 1e-3}
+
+
+def parse_time_ms(text: str) -> float:
+    """Inverse of print_time_diff (HW3/include/timeutil.h:3-44)."""
+    ms = 0.0
+    for val, unit in re.findall(r"(\d+) (day|hour|minute|second|millisecond|microsecond)s?", text):
+        ms += int(val) * _TIME_UNITS[unit]
+    return ms
+
+
+def run_reference(tree: str, xml_text: str, workdir: str | None = None, timeout: float = 3600.0):
+    """Runs the untouched reference binary on the XML.  Returns dict(images={name: uint8[H,W,3]},
+    ms=<the reference's own "is saved in" timer>, threads=N, stdout=...)."""
+    from ceng795_b200.image import read_png
+    exe = os.path.join(REF_DIR, _TREE_BIN[tree])
+    if not os.path.exists(exe):
+        raise FileNotFoundError(exe)
+    own = workdir is None
+    tmp = tempfile.mkdtemp(prefix="b200rt_ref_") if own else workdir
+    xml_path = os.path.join(tmp, "scene.xml")
+    with open(xml_path, "w") as f:
+        f.write(xml_text)
+    r = subprocess.run([exe, xml_path], cwd=tmp, capture_output=True, text=True, timeout=timeout,
+                       stdin=subprocess.DEVNULL)
+    out = r.stdout
+    if r.returncode != 0:
+        raise RuntimeError(f"reference {tree} failed rc={r.returncode}: {out[-500:]} {r.stderr[-500:]}")
+    res = {"stdout": out, "images": {}, "ms": {}, "threads": 1}
+    m = re.search(r"Starting rendering on #(\d+) thread", out)
+    if m:
+        res["threads"] = int(m.group(1))
+    for name, tail in re.findall(r"(\S+)\(\d+x\d+\) is saved in: ([^\n]*)", out):
+        res["ms"][name] = parse_time_ms(tail)
+        p = os.path.join(tmp, name)
+        if os.path.exists(p) and name.lower().endswith(".png"):
+            res["images"][name] = read_png(p)
+    if own:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    return res

@@ -1,0 +1,748 @@
+/*
+ * oracle.c — TEST INFRASTRUCTURE ONLY (never linked into or called from the
+ * product path; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it).
+ *
+ * A plain-C, CPU restatement of the ceng795 hot path: ray generation, the
+ * reference's recursive *unpruned* BVH traversal, Cramer's-rule triangle and
+ * quadratic sphere intersection, instancing, and the Whitted shading loop, in
+ * the reference's operation order and IEEE binary32 (build with
+ * -ffp-contract=off).  Every function cites the reference lines it follows.
+ * It consumes the same flattened B200SceneDesc the CUDA core consumes.
+ *
+ * Pinning: the reference ships no tests or golden vectors, so
+ * this restatement is pinned against the reference ITSELF: oracle/build_ref.sh
+ * compiles the untouched trees into oracle/_ref/, and tests/test_oracle_vs_ref.py
+ * checks that this file reproduces their PNGs byte for byte on deterministic
+ * scenes; tests/golden/ holds small reference-rendered fixtures (with the
+ * generating script) for boxes where /root/reference is absent.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/b200rt.h"
+
+typedef struct { float x, y, z; } v3;
+static inline v3 V(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 ld(const float* p) { return V(p[0], p[1], p[2]); }
+static inline v3 add(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 sub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 mulv(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline v3 muls(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+static inline v3 divs(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }
+static inline v3 neg(v3 a) { return V(-a.x, -a.y, -a.z); }
+static inline float dot(v3 a, v3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+static inline v3 cross(v3 a, v3 b) {
+  return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+static inline float len(v3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+static inline v3 normalize(v3 a) { return divs(a, len(a)); }
+static inline int is_zero(v3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
+static inline float comp(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+typedef struct {
+  v3 o, d;
+  float time;
+  int in_medium;
+  int is_shadow;
+} Ray;
+
+typedef struct {
+  float t;
+  int top_rank;   /* DFS rank of the top-level object, -1 none */
+  int tri;        /* triangle index (mesh DFS order) or -1      */
+  uint32_t shape; /* ref of the object that owns the material   */
+  int material;
+  v3 normal;
+  int valid;      /* shape != NULL */
+} Hit;
+
+typedef struct OracleCounters {
+  uint64_t rays_primary, rays_shadow, rays_secondary;
+  uint64_t nodes_visited, tris_tested, spheres_tested, instances_entered;
+} OracleCounters;
+
+typedef struct {
+  const B200SceneDesc* d;
+  OracleCounters* c;
+} Ctx;
+
+/* Matrix4x4::multiply — HW3/src/Matrix4x4.cpp:29-50 (3x4 rows) */
+static v3 xf_point(const float* m, v3 p) {
+  float r[3];
+  const float q[3] = {p.x, p.y, p.z};
+  for (int i = 0; i < 3; i++) {
+    r[i] = m[i * 4 + 3];
+    for (int j = 0; j < 3; j++) r[i] += m[i * 4 + j] * q[j];
+  }
+  return V(r[0], r[1], r[2]);
+}
+static v3 xf_vector(const float* m, int stride, v3 p) {
+  float r[3];
+  const float q[3] = {p.x, p.y, p.z};
+  for (int i = 0; i < 3; i++) {
+    r[i] = 0;
+    for (int j = 0; j < 3; j++) r[i] += m[i * stride + j] * q[j];
+  }
+  return V(r[0], r[1], r[2]);
+}
+
+/* 4x4 helpers for the motion-blur branch (HW3/include/Mesh.h:76-95) */
+static void m4_mul(const float* a, const float* b, float* r) {
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      float s = 0.0f;
+      for (int k = 0; k < 4; k++) s += a[i * 4 + k] * b[k * 4 + j];
+      r[i * 4 + j] = s;
+    }
+}
+/* Matrix4x4::invert_matrix — HW3/src/Matrix4x4.cpp:97-233 */
+static int m4_invert(const float* m, float* out) {
+  float inv[16], det;
+  inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] +
+           m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+  inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] -
+           m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+  inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] +
+           m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+  inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] -
+            m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+  inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] -
+           m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+  inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] +
+           m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+  inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] -
+           m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+  inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] +
+            m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+  inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] +
+           m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+  inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] -
+           m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+  inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] +
+            m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+  inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] -
+            m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+  inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] -
+           m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+  inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] +
+           m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+  inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] -
+            m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+  inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] +
+            m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+  det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+  if (det == 0.0f) return 0;
+  det = 1.0f / det;
+  for (int i = 0; i < 16; i++) out[i] = inv[i] * det;
+  return 1;
+}
+/* Translation(time*velocity) * M, inverse and normal matrix per ray. */
+static void moving_xf(const float* fwd, const float* vel, float time, float* inv16, float* nrm16) {
+  float tr[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  const v3 dp = muls(ld(vel), time); /* ray.time * velocity */
+  tr[3] = dp.x; tr[7] = dp.y; tr[11] = dp.z;
+  float prod[16];
+  m4_mul(tr, fwd, prod);
+  if (!m4_invert(prod, inv16)) { /* reference exit(-1)s; keep going with identity */
+    memset(inv16, 0, 64);
+    inv16[0] = inv16[5] = inv16[10] = inv16[15] = 1.0f;
+  }
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) nrm16[i * 4 + j] = inv16[j * 4 + i];
+}
+
+/* Bounding_box::intersect — HW3/src/bounding_box.cpp:17-37 */
+static float box_intersect(const float* mn, const float* mx, const Ray* ray, float eps) {
+  float tmin = -INFINITY, tmax = INFINITY;
+  for (int i = 0; i < 3; i++) {
+    const float di = comp(ray->d, i), oi = comp(ray->o, i);
+    if (fabsf(di) < eps) continue;
+    float ti_min = (mn[i] - oi) / di;
+    float ti_max = (mx[i] - oi) / di;
+    if (di < 0) { float tmp = ti_min; ti_min = ti_max; ti_max = tmp; }
+    if (ti_min > tmin) tmin = ti_min;
+    if (ti_max < tmax) tmax = ti_max;
+    if (tmin > tmax) return INFINITY;
+  }
+  return (tmin > 0.0f) ? tmin : tmax;
+}
+
+/* Mesh_triangle::determinant — HW3/include/Mesh_triangle.h:42-47 */
+static inline float det3(v3 c1, v3 c2, v3 c3) {
+  return c1.x * (c2.y * c3.z - c3.y * c2.z) + c2.x * (c3.y * c1.z - c1.y * c3.z) +
+         c3.x * (c1.y * c2.z - c2.y * c1.z);
+}
+
+/* Cramer's-rule core shared by Mesh_triangle/Triangle of every tree.  mode:
+ *   1 = HW1 band (HW1/Triangle.cpp:29-47), 2 = exact [0,1] t>0
+ *   (HW3/src/Mesh_triangle.cpp:85-97), 7 = HW7/PPM mesh band (no beta>1 test). */
+static int tri_core(const float* g, v3 o, v3 d, int mode, float eps, float* t_out, float* beta_out,
+                    float* gamma_out) {
+  const v3 v0 = ld(g), a1 = ld(g + 3), a2 = ld(g + 6);
+  const float det_a = det3(a1, a2, d);
+  if (det_a == 0.0f) return 0;
+  const v3 b = divs(sub(v0, o), det_a);
+  const float beta = det3(b, a2, d);
+  if (mode == 1) {
+    if (beta < 0.0f - eps || beta > 1.0f + eps) return 0;
+  } else if (mode == 2) {
+    if (beta < 0.0f || beta > 1.0f) return 0;
+  } else {
+    if (beta < -eps) return 0;
+  }
+  const float gamma = det3(a1, b, d);
+  if (mode == 1) {
+    if (gamma < 0.0f - eps || beta + gamma > 1.0f + eps) return 0;
+  } else if (mode == 2) {
+    if (gamma < 0.0f || beta + gamma > 1.0f) return 0;
+  } else {
+    if (gamma < -eps || beta + gamma > 1.0f + eps) return 0;
+  }
+  const float t = det3(a1, a2, b);
+  if (mode == 2) {
+    if (!(t > 0.0f)) return 0;
+  } else {
+    if (!(t > -eps)) return 0;
+  }
+  *t_out = t; *beta_out = beta; *gamma_out = gamma;
+  return 1;
+}
+
+static int shape_intersect(const Ctx* cx, uint32_t ref, const float* box, const Ray* ray, Hit* hit);
+
+/* Mesh_triangle::intersect — HW3/src/Mesh_triangle.cpp:75-114 */
+static int mesh_tri_intersect(const Ctx* cx, int tri, const Ray* ray, Hit* hit) {
+  const B200SceneDesc* d = cx->d;
+  cx->c->tris_tested++;
+  float t, beta, gamma;
+  if (!tri_core(d->tri_geom + 12 * (size_t)tri, ray->o, ray->d, 2, d->isect_eps, &t, &beta, &gamma))
+    return 0;
+  hit->t = t;
+  hit->tri = tri;
+  hit->shape = B200RT_REF(B200RT_KIND_TRI, tri);
+  hit->material = d->tri_info[2 * (size_t)tri];
+  hit->valid = 1;
+  if (d->tri_info[2 * (size_t)tri + 1] & 1) {
+    const int32_t* vi = d->tri_vidx + 3 * (size_t)tri;
+    const v3 n0 = ld(d->vert_normal + 3 * (size_t)vi[0]);
+    const v3 n1 = ld(d->vert_normal + 3 * (size_t)vi[1]);
+    const v3 n2 = ld(d->vert_normal + 3 * (size_t)vi[2]);
+    hit->normal = normalize(add(add(muls(n0, 1 - beta - gamma), muls(n1, beta)), muls(n2, gamma)));
+  } else {
+    hit->normal = ld(d->tri_geom + 12 * (size_t)tri + 9);
+  }
+  return 1;
+}
+
+/* Triangle::intersect (stand-alone primitive) — HW3/src/Triangle.cpp:51-109 */
+static int triprim_intersect(const Ctx* cx, int idx, const Ray* ray, Hit* hit) {
+  const b200rt_triprim* p = cx->d->triprims + idx;
+  cx->c->tris_tested++;
+  float g[12];
+  memcpy(g, p->v0, 12); memcpy(g + 3, p->a1, 12); memcpy(g + 6, p->a2, 12);
+  v3 o = ray->o, dd = ray->d;
+  const int ident = (p->flags & B200RT_XF_IDENTITY) != 0;
+  if (!ident) {
+    o = xf_point(p->inv, ray->o);
+    dd = xf_vector(p->inv, 4, ray->d);
+  }
+  float t, beta, gamma;
+  if (!tri_core(g, o, dd, 2, cx->d->isect_eps, &t, &beta, &gamma)) return 0;
+  hit->t = t;
+  hit->tri = -1;
+  hit->shape = B200RT_REF(B200RT_KIND_TRIPRIM, idx);
+  hit->material = p->material;
+  hit->top_rank = p->rank;
+  hit->valid = 1;
+  hit->normal = ident ? ld(p->normal) : normalize(xf_vector(p->nrm, 3, ld(p->normal)));
+  return 1;
+}
+
+/* Sphere::intersect — HW3/include/Sphere.h:44-155 (three branches) and
+ * HW1/Sphere.h:20-49.  Returns 1 even when t < 0, like the reference. */
+static int sphere_intersect(const Ctx* cx, int idx, const Ray* ray, Hit* hit) {
+  const b200rt_sphere* s = cx->d->spheres + idx;
+  const float eps = cx->d->isect_eps;
+  cx->c->spheres_tested++;
+  const v3 center = ld(s->center);
+  const float radius = s->radius;
+  v3 o = ray->o, dd = ray->d;
+  float inv16[16], nrm16[16];
+  const float* nrm = NULL;
+  int nstride = 3;
+  const int moving = (s->flags & B200RT_XF_MOVING) != 0;
+  const int ident = (s->flags & B200RT_XF_IDENTITY) != 0;
+  if (moving) {
+    moving_xf(s->fwd, s->velocity, ray->time, inv16, nrm16);
+    o = xf_point(inv16, ray->o);
+    dd = xf_vector(inv16, 4, ray->d);
+    nrm = nrm16; nstride = 4;
+  } else if (!ident) {
+    o = xf_point(s->inv, ray->o);
+    dd = xf_vector(s->inv, 4, ray->d);
+    nrm = s->nrm; nstride = 3;
+  }
+  const v3 cto = sub(o, center);
+  const float a = dot(dd, dd);
+  const float b = 2 * dot(dd, cto);
+  const float c = dot(cto, cto) - radius * radius;
+  const float disc = b * b - 4 * a * c;
+  float t;
+  if (disc < -eps) return 0;
+  if (disc < eps) {
+    t = -b / (2 * a);
+  } else {
+    const float sq = sqrtf(disc);
+    const float t1 = (-b + sq) / (2 * a);
+    const float t2 = (-b - sq) / (2 * a);
+    t = (t2 < .0) ? t1 : t2;
+  }
+  hit->t = t;
+  v3 n = normalize(sub(add(o, muls(dd, t)), center));
+  if (nrm) n = normalize(xf_vector(nrm, nstride, n));
+  hit->normal = n;
+  hit->tri = -1;
+  hit->shape = B200RT_REF(B200RT_KIND_SPHERE, idx);
+  hit->material = s->material;
+  hit->top_rank = s->rank;
+  hit->valid = 1;
+  return 1;
+}
+
+/* Mesh_instance::intersect — HW3/include/Mesh.h:55-98 (HW2: Mesh::intersect HW2/Mesh.h:13-15) */
+static int instance_intersect(const Ctx* cx, int idx, const float* box, const Ray* ray, Hit* hit) {
+  const B200SceneDesc* d = cx->d;
+  const b200rt_instance* in = d->instances + idx;
+  const b200rt_mesh* m = d->meshes + in->mesh;
+  if (in->flags & B200RT_INST_DIRECT) {
+    if (!shape_intersect(cx, m->root, m->root_box, ray, hit)) return 0;
+    hit->top_rank = in->rank;
+    return 1;
+  }
+  const float bt = box_intersect(box, box + 3, ray, d->isect_eps);
+  if (bt < 0.0f || bt == INFINITY) return 0;
+  cx->c->instances_entered++;
+  Ray local = *ray;
+  float inv16[16], nrm16[16];
+  const float* nrm = in->nrm;
+  int nstride = 3;
+  if (in->flags & B200RT_INST_MOVING) {
+    moving_xf(in->fwd, in->velocity, ray->time, inv16, nrm16);
+    local.o = xf_point(inv16, ray->o);
+    local.d = xf_vector(inv16, 4, ray->d);
+    nrm = nrm16; nstride = 4;
+  } else {
+    local.o = xf_point(in->inv, ray->o);
+    local.d = xf_vector(in->inv, 4, ray->d);
+  }
+  if (m->root == B200RT_REF_NONE) return 0;
+  if (!shape_intersect(cx, m->root, m->root_box, &local, hit)) return 0;
+  hit->normal = normalize(xf_vector(nrm, nstride, hit->normal));
+  hit->shape = B200RT_REF(B200RT_KIND_INSTANCE, idx);
+  hit->material = in->material;
+  hit->top_rank = in->rank;
+  return 1;
+}
+
+/* BVH::intersect — HW3/src/Bounding_volume_hierarchy.cpp:31-55 */
+static int bvh_intersect(const Ctx* cx, uint32_t node, const float* box, const Ray* ray, Hit* hit) {
+  const b200rt_bvh_node* n = cx->d->nodes + node;
+  cx->c->nodes_visited++;
+  const float bt = box_intersect(box, box + 3, ray, cx->d->isect_eps);
+  if (bt < 0.0f || bt == INFINITY) return 0;
+  int any = 0;
+  Hit lh; memset(&lh, 0, sizeof(lh)); lh.t = INFINITY; lh.top_rank = -1; lh.tri = -1;
+  if (shape_intersect(cx, n->left, n->lmin, ray, &lh) && lh.t > 0.0f && lh.t < hit->t) {
+    *hit = lh; any = 1;
+  }
+  Hit rh; memset(&rh, 0, sizeof(rh)); rh.t = INFINITY; rh.top_rank = -1; rh.tri = -1;
+  if (shape_intersect(cx, n->right, n->rmin, ray, &rh) && rh.t > 0.0f && rh.t < hit->t) {
+    *hit = rh; any = 1;
+  }
+  return any;
+}
+
+static int shape_intersect(const Ctx* cx, uint32_t ref, const float* box, const Ray* ray, Hit* hit) {
+  const uint32_t idx = B200RT_REF_INDEX(ref);
+  switch (B200RT_REF_KIND(ref)) {
+    case B200RT_KIND_INNER: return bvh_intersect(cx, idx, box, ray, hit);
+    case B200RT_KIND_TRI: return mesh_tri_intersect(cx, (int)idx, ray, hit);
+    case B200RT_KIND_SPHERE: return sphere_intersect(cx, (int)idx, ray, hit);
+    case B200RT_KIND_TRIPRIM: return triprim_intersect(cx, (int)idx, ray, hit);
+    case B200RT_KIND_INSTANCE: return instance_intersect(cx, (int)idx, box, ray, hit);
+    default: return 0;
+  }
+}
+
+/* Scene-level closest hit: `hit_data.t = inf; bvh->intersect(ray, hit_data)`
+ * (HW3/src/Scene.cpp:121-124) or the HW1 brute-force scan (HW1/Scene.cpp:33-55). */
+static int scene_intersect(const Ctx* cx, const Ray* ray, Hit* hit) {
+  const B200SceneDesc* d = cx->d;
+  memset(hit, 0, sizeof(*hit));
+  hit->t = INFINITY; hit->top_rank = -1; hit->tri = -1;
+  if (d->semantics == B200RT_SEM_HW1) {
+    const float eps = d->isect_eps;
+    for (int i = 0; i < d->n_tris; i++) {
+      float t, beta, gamma;
+      cx->c->tris_tested++;
+      if (!tri_core(d->tri_geom + 12 * (size_t)i, ray->o, ray->d, 1, eps, &t, &beta, &gamma)) continue;
+      if (t < hit->t - eps && t > 0.0f) {
+        hit->t = t; hit->tri = i; hit->top_rank = i; hit->valid = 1;
+        hit->shape = B200RT_REF(B200RT_KIND_TRI, i);
+        hit->material = d->tri_info[2 * (size_t)i];
+        hit->normal = ld(d->tri_geom + 12 * (size_t)i + 9);
+      }
+    }
+    for (int i = 0; i < d->n_spheres; i++) {
+      Hit h; memset(&h, 0, sizeof(h)); h.t = INFINITY;
+      if (!sphere_intersect(cx, i, ray, &h)) continue;
+      if (h.t < hit->t - eps && h.t > 0.0f) {
+        *hit = h; hit->top_rank = d->n_tris + i; hit->tri = -1;
+      }
+    }
+    return hit->valid;
+  }
+  if (d->root == B200RT_REF_NONE) return 0;
+  return shape_intersect(cx, d->root, d->root_box, ray, hit);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Counter-based RNG shared (as a specification) with the CUDA core: the    */
+/* reference seeds everything from the clock / random_device, so matched    */
+/* sampling needs an injectable stream.                     */
+/* ------------------------------------------------------------------------ */
+static inline uint32_t rng_mix(uint32_t a, uint32_t b) {
+  uint32_t h = a * 0x9E3779B1u + b;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+static inline float rng_u01(uint32_t key, uint32_t dim) {
+  return (float)(rng_mix(key, dim ^ 0xA511E9B3u) >> 8) * (1.0f / 16777216.0f);
+}
+
+typedef struct {
+  uint32_t key;   /* stream of this path vertex */
+  int pixel;
+} PathState;
+
+/* Scene::refract_ray — HW3/src/Scene.cpp:100-114 */
+static int refract_ray(v3 du, v3 n, float index, v3* out) {
+  const float n_ratio = 1 / index;
+  const float cos_theta = dot(neg(du), n);
+  const float delta = 1 - (n_ratio) * (n_ratio) * (1 - (cos_theta * cos_theta));
+  if (delta < 0.0f) return 0;
+  *out = normalize(sub(muls(add(du, muls(n, cos_theta)), n_ratio), muls(n, sqrtf(delta))));
+  return 1;
+}
+
+/* Scene::trace_ray — HW1/Scene.cpp:28-123 and HW3/src/Scene.cpp:116-312. */
+static v3 trace_ray(const Ctx* cx, const Ray* ray, int depth, uint32_t key, int count_as) {
+  const B200SceneDesc* d = cx->d;
+  const int hw1 = d->semantics == B200RT_SEM_HW1;
+  v3 color = V(0, 0, 0);
+  Hit hit;
+  if (count_as == 0) cx->c->rays_primary++; else cx->c->rays_secondary++;
+  const int found = scene_intersect(cx, ray, &hit);
+  if (!found) {
+    if (d->max_depth == depth) return ld(d->background);
+    return color;
+  }
+  const v3 p = add(ray->o, muls(ray->d, hit.t));
+  const b200rt_material* m = d->materials + hit.material;
+  const v3 w0 = normalize(sub(ray->o, p));
+  const v3 n = hit.normal;
+  const float seps = d->shadow_eps;
+  const v3 kd = ld(m->diffuse), ks = ld(m->specular);
+  if (hw1 || !ray->in_medium) {
+    color = add(color, mulv(ld(m->ambient), ld(d->ambient)));
+    int rdim = 0;
+    for (int li = 0; li < d->n_lights; li++) {
+      const b200rt_light* L = d->lights + li;
+      const int has_d = !is_zero(kd), has_s = !is_zero(ks);
+      if (!hw1 && !has_d && !has_s) continue;
+      v3 lpos = ld(L->position);
+      if (L->kind == B200RT_LIGHT_AREA) {
+        /* HW3/src/Scene.cpp:184-191; the clock-seeded engine is replaced by the shared stream */
+        const float e1 = rng_u01(key, 16 + 2 * rdim), e2 = rng_u01(key, 17 + 2 * rdim);
+        rdim++;
+        lpos = add(add(lpos, muls(ld(L->edge1), e1)), muls(ld(L->edge2), e2));
+      }
+      const v3 lvec = sub(lpos, p);
+      const v3 wi = normalize(lvec);
+      const float ldist = len(lvec);
+      Ray sr; memset(&sr, 0, sizeof(sr));
+      sr.o = add(p, muls(wi, seps)); sr.d = wi; sr.time = ray->time; sr.is_shadow = 1;
+      cx->c->rays_shadow++;
+      Hit sh;
+      scene_intersect(cx, &sr, &sh);
+      if (hw1) {
+        /* HW1 tests every primitive separately: any 0 < t < dist-eps (HW1/Scene.cpp:72-101).
+         * scene_intersect's HW1 scan keeps a running best with the -eps rule, which is not the
+         * same predicate, so redo it literally. */
+        int in_shadow = 0;
+        for (int i = 0; i < d->n_tris && !in_shadow; i++) {
+          float t, be, ga;
+          if (tri_core(d->tri_geom + 12 * (size_t)i, sr.o, sr.d, 1, d->isect_eps, &t, &be, &ga) &&
+              t < (ldist - seps) && t > 0.0f)
+            in_shadow = 1;
+        }
+        for (int i = 0; i < d->n_spheres && !in_shadow; i++) {
+          Hit h; memset(&h, 0, sizeof(h)); h.t = INFINITY;
+          OracleCounters dummy; memset(&dummy, 0, sizeof(dummy));
+          Ctx c2 = {d, &dummy};
+          if (sphere_intersect(&c2, i, &sr, &h) && h.t < (ldist - seps) && h.t > 0.0f) in_shadow = 1;
+        }
+        if (in_shadow) continue;
+      } else {
+        if (sh.t < (ldist - seps) && sh.t > 0.0f) continue;
+      }
+      const float d2 = ldist * ldist;
+      v3 inten = ld(L->intensity);
+      if (L->kind == B200RT_LIGHT_AREA) {
+        const float icos = dot(neg(wi), ld(L->normal));  /* HW3/src/Scene.cpp:208 */
+        if (has_d) {
+          const float dc = dot(n, wi);
+          color = add(color, divs(muls(muls(mulv(kd, inten), icos), dc), d2));
+        }
+        if (has_s) {
+          const float sc = fmaxf(0.0f, dot(n, normalize(add(w0, wi))));
+          color = add(color, divs(muls(muls(mulv(ks, inten), icos), (float)pow((double)sc, (double)m->phong_exponent)), d2));
+        }
+      } else {
+        if (hw1 || has_d) {
+          const float dc = dot(n, wi);
+          color = add(color, divs(muls(mulv(kd, inten), dc), d2));
+        }
+        if (hw1 || has_s) {
+          const float sc = fmaxf(0.0f, dot(n, normalize(add(w0, wi))));
+          color = add(color, divs(muls(mulv(ks, inten), (float)pow((double)sc, (double)m->phong_exponent)), d2));
+        }
+      }
+    }
+  }
+  const v3 km = ld(m->mirror);
+  if (!is_zero(km) && depth > 0) {
+    const v3 wr = normalize(sub(muls(n, 2 * dot(n, w0)), w0));
+    v3 dir = wr;
+    if (!hw1 && m->roughness != 0.0f) {
+      /* glossy — HW3/src/Scene.cpp:236-260 */
+      v3 rp;
+      if (wr.x < wr.y && wr.x < wr.z) rp = V(1.0f, wr.y, wr.z);
+      else if (wr.y < wr.z && wr.y < wr.x) rp = V(wr.x, 1.0f, wr.z);
+      else rp = V(wr.x, wr.y, 1.0f);
+      const v3 u = normalize(cross(rp, wr));
+      const v3 v = normalize(cross(u, wr));
+      const float eu = rng_u01(key, 2) - 0.5f, ev = rng_u01(key, 3) - 0.5f;
+      dir = normalize(add(wr, muls(add(muls(u, eu), muls(v, ev)), m->roughness)));
+    }
+    Ray mr; memset(&mr, 0, sizeof(mr));
+    mr.o = add(p, muls(dir, seps)); mr.d = dir; mr.time = ray->time;
+    color = add(color, mulv(km, trace_ray(cx, &mr, depth - 1, rng_mix(key, 0x101u), 1)));
+  }
+  const v3 kt = ld(m->transparency);
+  if (!hw1 && !is_zero(kt) && depth > 0) {
+    /* dielectric — HW3/src/Scene.cpp:264-310 (HW2 flips the Beer sign, HW2/Scene.cpp:166-168) */
+    const v3 wr = normalize(sub(muls(n, 2 * dot(n, w0)), w0));
+    v3 tdir = V(0, 0, 0);
+    float cos_theta = 0.0f;
+    v3 k = V(0, 0, 0);
+    const v3 dn = normalize(ray->d);
+    const float ni = m->refraction_index;
+    int tir = 0, entering;
+    if (dot(dn, n) < 0.0f) {
+      refract_ray(dn, n, ni, &tdir);
+      cos_theta = dot(neg(dn), n);
+      k = V(1.0f, 1.0f, 1.0f);
+      entering = 1;
+    } else {
+      const float ht = hit.t;
+      /* unqualified exp/log resolve to the DOUBLE overloads in the reference TU */
+      if (d->semantics == B200RT_SEM_HW2) {
+        k = V((float)exp(-log((double)kt.x) * (double)ht), (float)exp(-log((double)kt.y) * (double)ht),
+              (float)exp(-log((double)kt.z) * (double)ht));
+      } else {
+        k = V((float)exp(log((double)kt.x) * (double)ht), (float)exp(log((double)kt.y) * (double)ht),
+              (float)exp(log((double)kt.z) * (double)ht));
+      }
+      entering = 0;
+      if (refract_ray(dn, neg(n), 1.0f / ni, &tdir)) cos_theta = dot(tdir, n);
+      else tir = 1;
+    }
+    Ray rr; memset(&rr, 0, sizeof(rr));
+    rr.o = add(p, muls(wr, seps)); rr.d = wr; rr.time = ray->time;
+    if (tir) {
+      rr.in_medium = 1;
+      color = add(color, mulv(k, trace_ray(cx, &rr, depth - 1, rng_mix(key, 0x102u), 1)));
+    } else {
+      const float r0 = ((ni - 1) * (ni - 1)) / ((ni + 1) * (ni + 1));
+      /* `pow(float,int)` is the double overload: the whole sum is evaluated in double */
+      const float r = (float)((double)r0 + (double)(1 - r0) * pow((double)(1.0f - cos_theta), 5.0));
+      rr.in_medium = !entering;
+      Ray tr; memset(&tr, 0, sizeof(tr));
+      tr.o = add(p, muls(tdir, seps)); tr.d = tdir; tr.time = ray->time; tr.in_medium = entering;
+      const v3 cr = trace_ray(cx, &rr, depth - 1, rng_mix(key, 0x102u), 1);
+      const v3 ct = trace_ray(cx, &tr, depth - 1, rng_mix(key, 0x103u), 1);
+      color = add(color, mulv(k, add(muls(cr, r), muls(ct, 1 - r))));
+    }
+  }
+  return color;
+}
+
+/* Camera::calculate_ray_at — HW1/Camera.h:24-32, HW3/include/Camera.h:35-47 */
+static Ray camera_ray(const B200SceneDesc* d, const b200rt_camera* c, float x, float y, int use_dof,
+                      float ex, float ey, float time) {
+  Ray r; memset(&r, 0, sizeof(r));
+  r.time = time;
+  const v3 e = ld(c->e), u = ld(c->u), v = ld(c->v);
+  if (d->semantics == B200RT_SEM_HW1) {
+    const float su = (c->right - c->left) * (x + 0.5f) / c->width;
+    const float sv = (c->top - c->bottom) * (y + 0.5f) / c->height;
+    const v3 s = sub(add(ld(c->top_left), muls(u, su)), muls(v, sv));
+    r.o = e; r.d = sub(s, e);
+    return r;
+  }
+  const v3 s = sub(add(ld(c->top_left), muls(ld(c->su), x + 0.5f)), muls(ld(c->sv), y + 0.5f));
+  if (use_dof) {
+    const v3 ne = add(e, muls(muls(add(muls(u, ex), muls(v, ey)), c->aperture), 0.5f));
+    r.o = ne; r.d = normalize(sub(s, ne));
+  } else {
+    r.o = e; r.d = normalize(sub(s, e));
+  }
+  return r;
+}
+
+/* gaussian_filter — HW3/src/Scene.cpp:15-17 */
+static inline float gaussian_filter(float x, float y, float sigma) {
+  return (float)(exp(-(x * x + y * y) / (2 * sigma * sigma)) / (float)(2 * M_PI * sigma));
+}
+
+/* Scene::render_image — HW1/Scene.cpp:9-27, HW3/src/Scene.cpp:21-99.
+ * rgbw: W*H*4 floats {sum color*w, sum w}. ids (2 per pixel) / tout may be NULL.
+ * For HW1 `rgbw` receives the raw float colour with w=1; quantisation lives in
+ * the host mirror (ceng795_b200/image.py) for both arms. */
+int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int row_end, uint64_t seed,
+                  float* rgbw, int32_t* ids, float* tout, OracleCounters* counters) {
+  if (!d || camera_index < 0 || camera_index >= d->n_cameras) return -1;
+  const b200rt_camera* c = d->cameras + camera_index;
+  const int W = c->width, H = c->height;
+  if (row_end <= 0 || row_end > H) row_end = H;
+  if (row_begin < 0) row_begin = 0;
+  OracleCounters total; memset(&total, 0, sizeof(total));
+  const int ns = c->samples_sqrt;
+  const uint32_t s0 = rng_mix((uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma omp parallel
+  {
+    OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
+    Ctx cx = {d, &cnt};
+#pragma omp for schedule(dynamic, 4)
+    for (int j = row_begin; j < row_end; j++) {
+      for (int i = 0; i < W; i++) {
+        const int pix = j * W + i;
+        if (ns == 1) {
+          Ray r = camera_ray(d, c, (float)i, (float)j, 0, 0, 0, 0.0f);
+          if (ids || tout) {
+            Hit h; OracleCounters dummy; memset(&dummy, 0, sizeof(dummy));
+            Ctx c2 = {d, &dummy};
+            const int f = scene_intersect(&c2, &r, &h);
+            if (ids) { ids[2 * pix] = f ? h.top_rank : -1; ids[2 * pix + 1] = f ? h.tri : -1; }
+            if (tout) tout[pix] = f ? h.t : INFINITY;
+          }
+          if (rgbw) {
+            const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), 0u);
+            const v3 col = trace_ray(&cx, &r, d->max_depth, key, 0);
+            rgbw[4 * pix] = col.x * 1.0f; rgbw[4 * pix + 1] = col.y * 1.0f;
+            rgbw[4 * pix + 2] = col.z * 1.0f; rgbw[4 * pix + 3] = 1.0f;
+          }
+        }
+      }
+    }
+#pragma omp critical
+    {
+      total.rays_primary += cnt.rays_primary; total.rays_shadow += cnt.rays_shadow;
+      total.rays_secondary += cnt.rays_secondary; total.nodes_visited += cnt.nodes_visited;
+      total.tris_tested += cnt.tris_tested; total.spheres_tested += cnt.spheres_tested;
+      total.instances_entered += cnt.instances_entered;
+    }
+  }
+  if (ns > 1 && rgbw) {
+    /* multi-sample path with the 3x3 Gaussian splat: sequential over pixels so
+     * that the accumulation order is defined (the reference's is thread-racy). */
+    OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
+    Ctx cx = {d, &cnt};
+    for (int j = row_begin; j < row_end; j++)
+      for (int i = 0; i < W; i++) {
+        const int pix = j * W + i;
+        for (int x = 0; x < ns; x++)
+          for (int y = 0; y < ns; y++) {
+            const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), (uint32_t)(x * ns + y));
+            const float ex = rng_u01(key, 4), ey = rng_u01(key, 5);
+            const float sx = (x + ex) / ns, sy = (y + ey) / ns;
+            const float time = rng_u01(key, 6);
+            Ray r;
+            if (c->aperture == 0.0f) {
+              r = camera_ray(d, c, i + sx - 0.5f, j + sy - 0.5f, 0, 0, 0, time);
+            } else {
+              const float dx = rng_u01(key, 7) * 2.0f - 1.0f, dy = rng_u01(key, 8) * 2.0f - 1.0f;
+              r = camera_ray(d, c, i + sx - 0.5f, j + sy - 0.5f, 1, dx, dy, time);
+            }
+            const v3 col = trace_ray(&cx, &r, d->max_depth, key, 0);
+            for (int aj = j - 1; aj < j + 2; aj++) {
+              if (aj < 0 || aj >= H) continue;
+              for (int ai = i - 1; ai < i + 2; ai++) {
+                if (ai < 0 || ai >= W) continue;
+                const float fx = (i + sx) - (ai + 0.5f);
+                const float fy = (j + sy) - (aj + 0.5f);
+                const float w = gaussian_filter(fx, fy, 1.0f / 3.0f);
+                float* px = rgbw + 4 * (size_t)(aj * W + ai);
+                px[0] += col.x * w; px[1] += col.y * w; px[2] += col.z * w; px[3] += w;
+              }
+            }
+          }
+      }
+    total.rays_primary += cnt.rays_primary; total.rays_shadow += cnt.rays_shadow;
+    total.rays_secondary += cnt.rays_secondary; total.nodes_visited += cnt.nodes_visited;
+    total.tris_tested += cnt.tris_tested; total.spheres_tested += cnt.spheres_tested;
+    total.instances_entered += cnt.instances_entered;
+  }
+  if (counters) *counters = total;
+  return 0;
+}
+
+/* Closest-hit on caller rays (8 floats per ray: o.xyz, time, d.xyz, unused). */
+int oracle_trace_rays(const B200SceneDesc* d, const float* rays, int64_t n, int32_t* ids, float* tout,
+                      OracleCounters* counters) {
+  OracleCounters total; memset(&total, 0, sizeof(total));
+#pragma omp parallel
+  {
+    OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
+    Ctx cx = {d, &cnt};
+#pragma omp for schedule(dynamic, 256)
+    for (int64_t k = 0; k < n; k++) {
+      Ray r; memset(&r, 0, sizeof(r));
+      r.o = ld(rays + 8 * k); r.time = rays[8 * k + 3]; r.d = ld(rays + 8 * k + 4);
+      Hit h;
+      const int f = scene_intersect(&cx, &r, &h);
+      if (ids) { ids[2 * k] = f ? h.top_rank : -1; ids[2 * k + 1] = f ? h.tri : -1; }
+      if (tout) tout[k] = f ? h.t : INFINITY;
+    }
+#pragma omp critical
+    {
+      total.nodes_visited += cnt.nodes_visited; total.tris_tested += cnt.tris_tested;
+      total.spheres_tested += cnt.spheres_tested; total.instances_entered += cnt.instances_entered;
+    }
+  }
+  if (counters) *counters = total;
+  return 0;
+}
+
+/* Leaf known-answer hooks (compared with oracle/_ref/ref_probe on seeded inputs). */
+float oracle_box_intersect(const float* mn, const float* mx, const float* o, const float* dd, float eps) {
+  Ray r; memset(&r, 0, sizeof(r)); r.o = ld(o); r.d = ld(dd);
+  return box_intersect(mn, mx, &r, eps);
+}
+int oracle_tri_intersect(const float* g12, const float* o, const float* dd, int mode, float eps, float* out3) {
+  return tri_core(g12, ld(o), ld(dd), mode, eps, out3, out3 + 1, out3 + 2);
+}
