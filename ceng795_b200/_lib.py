@@ -102,6 +102,8 @@ class RenderStats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_secondary", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("spheres_tested", C.c_uint64),
                 ("instances_entered", C.c_uint64),
+                ("sh_nodes_visited", C.c_uint64), ("sh_tris_tested", C.c_uint64), ("sh_spheres_tested", C.c_uint64),
+                ("sh_instances_entered", C.c_uint64),
                 ("ms_generate", c_f), ("ms_extend", c_f), ("ms_shade", c_f), ("ms_shadow", c_f),
                 ("ms_total", c_f), ("waves", c_i), ("launches", c_i)]
 
@@ -169,6 +171,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_primary_ids": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), C.c_void_p, C.c_void_p]),
         "b200rt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_void_p, P(RenderStats)]),
+        "b200rt_scene_stream": (C.c_void_p, [C.c_void_p]),
+        "b200rt_scene_bytes": (C.c_uint64, [C.c_void_p]),
         "b200rt_last_error": (C.c_char_p, []),
         "b200rt_version": (C.c_char_p, []),
     }

@@ -1,12 +1,525 @@
-// temporary stub
-#include "../../include/b200rt.h"
-extern "C" {
-int b200rt_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
-int b200rt_scene_create(const B200SceneDesc*, int, b200rt_scene**) { return B200RT_E_UNSUPPORTED; }
-void b200rt_scene_destroy(b200rt_scene*) {}
-int b200rt_render(b200rt_scene*, int, const B200RenderOpts*, float*, B200RenderStats*) { return B200RT_E_UNSUPPORTED; }
-int b200rt_render_device(b200rt_scene*, int, const B200RenderOpts*, float**, B200RenderStats*) { return B200RT_E_UNSUPPORTED; }
-int b200rt_primary_ids(b200rt_scene*, int, const B200RenderOpts*, int32_t*, float*) { return B200RT_E_UNSUPPORTED; }
-int b200rt_trace_rays(b200rt_scene*, const float*, int64_t, int32_t, int32_t*, float*, B200RenderStats*) { return B200RT_E_UNSUPPORTED; }
-const char* b200rt_version(void) { return "b200rt 0.1"; }
+// b200rt_api.cu — device side of the C ABI (include/b200rt.h): scene upload,
+// the wavefront driver, and the parity / measurement hooks.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_kernels.cuh"
+
+extern "C" void b200rt_internal_set_error(const char* msg);
+
+namespace {
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      char buf_[512];                                                                 \
+      snprintf(buf_, sizeof(buf_), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      b200rt_internal_set_error(buf_);                                                \
+      return B200RT_E_CUDA;                                                           \
+    }                                                                                 \
+  } while (0)
+
+template <typename T>
+int upload(const T* src, size_t n, T** dst) {
+  *dst = nullptr;
+  if (n == 0) n = 1;  // keep pointers valid
+  CK(cudaMalloc((void**)dst, n * sizeof(T)));
+  if (src) CK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return B200RT_OK;
 }
+
+constexpr int kMaxWaves = 66;
+enum Stage { ST_GENERATE = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_COUNT };
+
+}  // namespace
+
+struct b200rt_scene {
+  int device;
+  DScene S;                    // device pointers (camera filled per render)
+  std::vector<b200rt_camera> cameras;
+  bool has_transparency;
+  int sm_count;
+  // device allocations owned by the scene
+  std::vector<void*> allocs;
+  // cached wavefront state
+  Pool P;
+  ShadowQueue Q;
+  WaveInfo* d_waves;
+  Counters* d_counters;
+  float4* d_accum;
+  size_t accum_pixels;
+  cudaStream_t stream;
+  cudaEvent_t ev[2];
+  size_t scene_bytes;
+};
+
+namespace {
+
+template <typename T>
+int pool_alloc(b200rt_scene* sc, T** p, size_t n) {
+  CK(cudaMalloc((void**)p, n * sizeof(T)));
+  return B200RT_OK;
+}
+
+void pool_free(b200rt_scene* sc) {
+  Pool& P = sc->P;
+  void* ptrs[] = {P.ray_o, P.ray_d, P.key, P.pixel, P.sample, P.hit_a, P.hit_b, P.nrm, P.rec0, P.rec1, P.rec2,
+                  P.rec3, P.final_c, sc->Q.o, sc->Q.d, sc->Q.time, sc->Q.vis};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  memset(&sc->P, 0, sizeof(Pool));
+  memset(&sc->Q, 0, sizeof(ShadowQueue));
+}
+
+int ensure_pool(b200rt_scene* sc, size_t slots, size_t shadow_slots) {
+  if (sc->P.capacity >= slots && sc->Q.capacity >= shadow_slots) return B200RT_OK;
+  pool_free(sc);
+  Pool& P = sc->P;
+  int rc;
+#define PA(field, n) if ((rc = pool_alloc(sc, &field, (n))) != B200RT_OK) return rc
+  PA(P.ray_o, slots); PA(P.ray_d, slots); PA(P.key, slots); PA(P.pixel, slots); PA(P.sample, slots);
+  PA(P.hit_a, slots); PA(P.hit_b, slots); PA(P.nrm, slots); PA(P.rec0, slots); PA(P.rec1, slots);
+  PA(P.rec2, slots); PA(P.rec3, slots); PA(P.final_c, slots);
+  P.capacity = (uint32_t)slots;
+  ShadowQueue& Q = sc->Q;
+  PA(Q.o, shadow_slots); PA(Q.d, shadow_slots); PA(Q.time, shadow_slots);
+  PA(Q.vis, slots * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1));
+#undef PA
+  Q.capacity = (uint32_t)shadow_slots;
+  return B200RT_OK;
+}
+
+int ensure_accum(b200rt_scene* sc, size_t pixels) {
+  if (sc->accum_pixels >= pixels) return B200RT_OK;
+  if (sc->d_accum) cudaFree(sc->d_accum);
+  sc->d_accum = nullptr;
+  CK(cudaMalloc((void**)&sc->d_accum, pixels * sizeof(float4)));
+  sc->accum_pixels = pixels;
+  return B200RT_OK;
+}
+
+struct Timers {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> stage;
+  cudaStream_t s;
+  bool on;
+  void mark(int st) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back(e);
+    stage.push_back(st);
+  }
+  void collect(float* ms) {
+    for (int i = 0; i < ST_COUNT; i++) ms[i] = 0.f;
+    for (size_t i = 1; i < ev.size(); i++) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i - 1], ev[i]);
+      ms[stage[i]] += t;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear(); stage.clear();
+  }
+};
+
+// Runs the wave loop for paths already placed in wave 0 by k_generate / k_import_rays.
+// primary_only: stop after the first extend (parity hooks).
+int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading, Timers& tm, int* launches,
+              int* waves_run) {
+  const DScene& S = sc->S;
+  cudaStream_t st = sc->stream;
+  const int grid_p = sc->sm_count * 8;  // persistent traversal grid: 8 CTAs of 128 threads per SM
+  const int grid_s = sc->sm_count * 8;
+  const bool hw1 = S.semantics == B200RT_SEM_HW1;
+  const int max_d = primary_only ? 0 : S.max_depth;
+  int d_last = 0;
+  for (int d = 0; d <= max_d; d++) {
+    k_next_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->d_counters);
+    (*launches)++;
+    if (hw1) {
+      k_extend_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
+    } else if (S.semantics >= B200RT_SEM_HW7) {
+      if (exact) k_extend<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
+      else k_extend<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
+    } else {
+      if (exact) k_extend<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
+      else k_extend<false, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
+    }
+    (*launches)++;
+    tm.mark(ST_EXTEND);
+    d_last = d;
+    if (!with_shading) break;
+    k_shade_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    k_clamp_shadow_count<<<1, 1, 0, st>>>(sc->Q, sc->d_counters);
+    (*launches) += 2;
+    tm.mark(ST_SHADE);
+    if (hw1) {
+      k_shadow_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
+    } else if (S.semantics >= B200RT_SEM_HW7) {
+      if (exact) k_shadow<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
+      else k_shadow<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
+    } else {
+      if (exact) k_shadow<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
+      else k_shadow<false, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
+    }
+    (*launches)++;
+    tm.mark(ST_SHADOW);
+    k_shade_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    k_finish_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->P, sc->d_counters);
+    (*launches) += 2;
+    tm.mark(ST_SHADE);
+  }
+  if (with_shading) {
+    for (int d = d_last; d >= 0; d--) {
+      k_combine<<<grid_s, 256, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_accum);
+      (*launches)++;
+    }
+    tm.mark(ST_SHADE);
+  }
+  *waves_run = d_last + 1;
+  CK(cudaGetLastError());
+  return B200RT_OK;
+}
+
+int resolve_rows(const b200rt_camera& c, const B200RenderOpts* o, RenderParams* R) {
+  int rb = 0, re = c.height, rs = 1;
+  if (o) {
+    if (o->row_end > 0) { rb = o->row_begin; re = o->row_end; }
+    if (o->row_stride > 1) rs = o->row_stride;
+  }
+  if (rb < 0 || re > c.height || rb > re) return B200RT_E_INVALID;
+  R->row_begin = rb; R->row_end = re; R->row_stride = rs;
+  R->n_rows = (re - rb + rs - 1) / rs;
+  const int total = c.samples_sqrt * c.samples_sqrt;
+  int sb = 0, se = total;
+  if (o && o->sample_end > 0) { sb = o->sample_begin; se = o->sample_end; }
+  if (sb < 0 || se > total || sb > se) return B200RT_E_INVALID;
+  R->sample_begin = sb; R->sample_count = se - sb;
+  const uint64_t seed = o ? o->seed : 0;
+  R->seed_key = rng_mix((uint32_t)seed, (uint32_t)(seed >> 32));
+  return B200RT_OK;
+}
+
+int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, B200RenderStats* stats) {
+  if (!sc || camera_index < 0 || camera_index >= (int)sc->cameras.size()) {
+    b200rt_internal_set_error("b200rt_render: bad scene or camera index");
+    return B200RT_E_INVALID;
+  }
+  CK(cudaSetDevice(sc->device));
+  sc->S.cam = sc->cameras[camera_index];
+  const b200rt_camera& c = sc->S.cam;
+  RenderParams R;
+  if (resolve_rows(c, opts, &R) != B200RT_OK) {
+    b200rt_internal_set_error("b200rt_render: bad row / sample range");
+    return B200RT_E_INVALID;
+  }
+  if (sc->S.max_depth + 2 > kMaxWaves) {
+    b200rt_internal_set_error("MaxRecursionDepth too large");
+    return B200RT_E_UNSUPPORTED;
+  }
+  const bool exact = opts && opts->exact_traversal;
+  const size_t pixels = (size_t)c.width * c.height;
+  int rc = ensure_accum(sc, pixels);
+  if (rc) return rc;
+  cudaStream_t st = sc->stream;
+  CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), st));
+  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
+
+  // batches of pixel rows so that the vertex pool stays bounded
+  const size_t paths_per_row = (size_t)c.width * R.sample_count;
+  const size_t growth = (size_t)(sc->S.max_depth + 1) * (sc->has_transparency ? 3 : 1);
+  const size_t max_paths = (size_t)16 << 20;  // 16 Mi camera paths per batch
+  size_t rows_per_batch = max_paths / (paths_per_row ? paths_per_row : 1);
+  if (rows_per_batch < 1) rows_per_batch = 1;
+  if (rows_per_batch > (size_t)R.n_rows) rows_per_batch = R.n_rows;
+  const size_t batch_paths = rows_per_batch * paths_per_row;
+  size_t slots = batch_paths * growth + 1024;
+  if (slots > 0xF0000000ull / (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1)) {
+    b200rt_internal_set_error("vertex pool too large for 32-bit slots");
+    return B200RT_E_UNSUPPORTED;
+  }
+  const size_t per_wave = batch_paths * (sc->has_transparency ? 9 : 1);
+  rc = ensure_pool(sc, slots, per_wave * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1) + 1024);
+  if (rc) return rc;
+
+  Timers tm;
+  tm.s = st; tm.on = stats != nullptr;
+  int launches = 0, waves_total = 0;
+  cudaEventRecord(sc->ev[0], st);
+  tm.mark(ST_GENERATE);
+  for (int r0 = 0; r0 < R.n_rows; r0 += (int)rows_per_batch) {
+    RenderParams B = R;
+    const int nr = (int)((size_t)(R.n_rows - r0) < rows_per_batch ? (R.n_rows - r0) : rows_per_batch);
+    B.row_begin = R.row_begin + r0 * R.row_stride;
+    B.n_rows = nr;
+    B.n_paths = (uint32_t)((size_t)nr * paths_per_row);
+    k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, B, sc->d_waves, sc->d_counters);
+    launches++;
+    tm.mark(ST_GENERATE);
+    int wr = 0;
+    rc = run_waves(sc, exact, false, true, tm, &launches, &wr);
+    if (rc) return rc;
+    waves_total += wr;
+  }
+  cudaEventRecord(sc->ev[1], st);
+  CK(cudaStreamSynchronize(st));
+  Counters hc;
+  CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (hc.overflow) {
+    b200rt_internal_set_error("vertex pool / shadow queue overflow (recursion tree larger than the pool)");
+    return B200RT_E_UNSUPPORTED;
+  }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->rays_primary = hc.rays_primary; stats->rays_shadow = hc.rays_shadow;
+    stats->rays_secondary = hc.rays_secondary; stats->nodes_visited = hc.nodes_visited;
+    stats->tris_tested = hc.tris_tested; stats->spheres_tested = hc.spheres_tested;
+    stats->instances_entered = hc.instances_entered;
+    stats->sh_nodes_visited = hc.sh_nodes_visited; stats->sh_tris_tested = hc.sh_tris_tested;
+    stats->sh_spheres_tested = hc.sh_spheres_tested; stats->sh_instances_entered = hc.sh_instances_entered;
+    float ms[ST_COUNT];
+    tm.collect(ms);
+    stats->ms_generate = ms[ST_GENERATE]; stats->ms_extend = ms[ST_EXTEND];
+    stats->ms_shade = ms[ST_SHADE]; stats->ms_shadow = ms[ST_SHADOW];
+    cudaEventElapsedTime(&stats->ms_total, sc->ev[0], sc->ev[1]);
+    stats->waves = waves_total; stats->launches = launches;
+  }
+  return B200RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* b200rt_version(void) { return "b200rt 0.1 (sm_100a)"; }
+
+int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) {
+  if (!d || !out) {
+    b200rt_internal_set_error("b200rt_scene_create: null argument");
+    return B200RT_E_INVALID;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    b200rt_internal_set_error("no CUDA device: the B200 core has no CPU fallback");
+    return B200RT_E_NOGPU;
+  }
+  if (device < 0 || device >= ndev) {
+    b200rt_internal_set_error("b200rt_scene_create: bad device index");
+    return B200RT_E_INVALID;
+  }
+  if (d->semantics != B200RT_SEM_HW1 && d->semantics != B200RT_SEM_HW2 && d->semantics != B200RT_SEM_HW3) {
+    b200rt_internal_set_error("b200rt_scene_create: semantics not implemented on the device yet");
+    return B200RT_E_UNSUPPORTED;
+  }
+  CK(cudaSetDevice(device));
+  b200rt_scene* sc = new b200rt_scene();
+  memset(&sc->S, 0, sizeof(DScene));
+  memset(&sc->P, 0, sizeof(Pool));
+  memset(&sc->Q, 0, sizeof(ShadowQueue));
+  sc->device = device;
+  sc->d_accum = nullptr; sc->accum_pixels = 0;
+  sc->d_waves = nullptr; sc->d_counters = nullptr;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  sc->sm_count = prop.multiProcessorCount;
+  DScene& S = sc->S;
+  S.semantics = d->semantics; S.max_depth = d->max_depth;
+  S.background = ld3(d->background); S.ambient = ld3(d->ambient);
+  S.shadow_eps = d->shadow_eps; S.isect_eps = d->isect_eps;
+  S.root = d->root;
+  memcpy(S.root_box, d->root_box, sizeof(S.root_box));
+  S.n_lights = d->n_lights; S.n_tris = d->n_tris; S.n_spheres = d->n_spheres; S.n_inst = d->n_instances;
+  int rc = B200RT_OK;
+  size_t bytes = 0;
+#define UP(dst, src, n, T)                                                 \
+  do {                                                                     \
+    T* p_ = nullptr;                                                       \
+    rc = upload<T>((const T*)(src), (size_t)(n), &p_);                     \
+    if (rc) { b200rt_scene_destroy(sc); return rc; }                       \
+    sc->allocs.push_back(p_);                                              \
+    dst = reinterpret_cast<decltype(dst)>(p_);                             \
+    bytes += (size_t)(n) * sizeof(T);                                      \
+  } while (0)
+  UP(S.nodes, d->nodes, d->n_nodes, b200rt_bvh_node);
+  {
+    // 12 floats per triangle -> 3 float4 (same bytes)
+    float* p = nullptr;
+    rc = upload<float>(d->tri_geom, (size_t)d->n_tris * 12, &p);
+    if (rc) { b200rt_scene_destroy(sc); return rc; }
+    sc->allocs.push_back(p);
+    S.tris = reinterpret_cast<const float4*>(p);
+    bytes += (size_t)d->n_tris * 48;
+  }
+  UP(S.tri_info, d->tri_info, (size_t)d->n_tris * 2, int32_t);
+  UP(S.tri_vidx, d->tri_vidx, (size_t)d->n_tris * 3, int32_t);
+  {
+    std::vector<float4> vn((size_t)(d->n_verts > 0 ? d->n_verts : 1));
+    for (int i = 0; i < d->n_verts; i++)
+      vn[i] = make_float4(d->vert_normal[3 * (size_t)i], d->vert_normal[3 * (size_t)i + 1],
+                          d->vert_normal[3 * (size_t)i + 2], 0.f);
+    UP(S.vnormal, vn.data(), vn.size(), float4);
+  }
+  UP(S.meshes, d->meshes, d->n_meshes, b200rt_mesh);
+  UP(S.inst, d->instances, d->n_instances, b200rt_instance);
+  UP(S.spheres, d->spheres, d->n_spheres, b200rt_sphere);
+  UP(S.triprims, d->triprims, d->n_triprims, b200rt_triprim);
+  UP(S.mats, d->materials, d->n_materials, b200rt_material);
+  UP(S.lights, d->lights, d->n_lights, b200rt_light);
+#undef UP
+  sc->scene_bytes = bytes;
+  sc->cameras.assign(d->cameras, d->cameras + d->n_cameras);
+  sc->has_transparency = false;
+  for (int i = 0; i < d->n_materials; i++) {
+    const float* t = d->materials[i].transparency;
+    if (t[0] != 0.f || t[1] != 0.f || t[2] != 0.f) sc->has_transparency = true;
+  }
+  CK(cudaMalloc((void**)&sc->d_waves, sizeof(WaveInfo) * kMaxWaves));
+  CK(cudaMalloc((void**)&sc->d_counters, sizeof(Counters)));
+  CK(cudaMemset(sc->d_waves, 0, sizeof(WaveInfo) * kMaxWaves));
+  CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&sc->ev[0]));
+  CK(cudaEventCreate(&sc->ev[1]));
+  *out = sc;
+  return B200RT_OK;
+}
+
+void b200rt_scene_destroy(b200rt_scene* sc) {
+  if (!sc) return;
+  cudaSetDevice(sc->device);
+  pool_free(sc);
+  for (void* p : sc->allocs)
+    if (p) cudaFree(p);
+  if (sc->d_accum) cudaFree(sc->d_accum);
+  if (sc->d_waves) cudaFree(sc->d_waves);
+  if (sc->d_counters) cudaFree(sc->d_counters);
+  if (sc->stream) cudaStreamDestroy(sc->stream);
+  if (sc->ev[0]) cudaEventDestroy(sc->ev[0]);
+  if (sc->ev[1]) cudaEventDestroy(sc->ev[1]);
+  delete sc;
+}
+
+void* b200rt_scene_stream(b200rt_scene* sc) { return sc ? (void*)sc->stream : nullptr; }
+uint64_t b200rt_scene_bytes(b200rt_scene* sc) { return sc ? (uint64_t)sc->scene_bytes : 0; }
+
+int b200rt_render_device(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, float** d_rgbw_out,
+                         B200RenderStats* stats) {
+  int rc = render_impl(sc, camera_index, opts, stats);
+  if (rc) return rc;
+  if (d_rgbw_out) *d_rgbw_out = reinterpret_cast<float*>(sc->d_accum);
+  return B200RT_OK;
+}
+
+int b200rt_render(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, float* rgbw_out,
+                  B200RenderStats* stats) {
+  if (!rgbw_out) {
+    b200rt_internal_set_error("b200rt_render: null output");
+    return B200RT_E_INVALID;
+  }
+  int rc = render_impl(sc, camera_index, opts, stats);
+  if (rc) return rc;
+  const b200rt_camera& c = sc->cameras[camera_index];
+  CK(cudaMemcpy(rgbw_out, sc->d_accum, (size_t)c.width * c.height * sizeof(float4), cudaMemcpyDeviceToHost));
+  return B200RT_OK;
+}
+
+int b200rt_primary_ids(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, int32_t* ids_out,
+                       float* t_out) {
+  if (!sc || !ids_out || !t_out || camera_index < 0 || camera_index >= (int)sc->cameras.size()) {
+    b200rt_internal_set_error("b200rt_primary_ids: bad argument");
+    return B200RT_E_INVALID;
+  }
+  CK(cudaSetDevice(sc->device));
+  sc->S.cam = sc->cameras[camera_index];
+  const b200rt_camera& c = sc->S.cam;
+  if (c.samples_sqrt != 1) {
+    b200rt_internal_set_error("b200rt_primary_ids: defined for 1-spp cameras only");
+    return B200RT_E_UNSUPPORTED;
+  }
+  RenderParams R;
+  if (resolve_rows(c, opts, &R) != B200RT_OK) return B200RT_E_INVALID;
+  R.n_paths = (uint32_t)((size_t)R.n_rows * c.width);
+  const size_t pixels = (size_t)c.width * c.height;
+  int rc = ensure_pool(sc, R.n_paths + 1024, 1024);
+  if (rc) return rc;
+  cudaStream_t st = sc->stream;
+  int32_t* d_ids = nullptr;
+  float* d_t = nullptr;
+  CK(cudaMalloc((void**)&d_ids, pixels * 2 * sizeof(int32_t)));
+  CK(cudaMalloc((void**)&d_t, pixels * sizeof(float)));
+  CK(cudaMemsetAsync(d_ids, 0xff, pixels * 2 * sizeof(int32_t), st));
+  {
+    std::vector<float> inf(pixels, __builtin_inff());
+    CK(cudaMemcpyAsync(d_t, inf.data(), pixels * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
+  k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, R, sc->d_waves, sc->d_counters);
+  Timers tm; tm.s = st; tm.on = false;
+  int launches = 0, wr = 0;
+  rc = run_waves(sc, opts && opts->exact_traversal, true, false, tm, &launches, &wr);
+  if (rc) { cudaFree(d_ids); cudaFree(d_t); return rc; }
+  k_export_ids<<<sc->sm_count * 4, 256, 0, st>>>(sc->P, R.n_paths, d_ids, d_t);
+  CK(cudaMemcpyAsync(ids_out, d_ids, pixels * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(t_out, d_t, pixels * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d_ids); cudaFree(d_t);
+  return B200RT_OK;
+}
+
+int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t exact, int32_t* ids_out, float* t_out,
+                      B200RenderStats* stats) {
+  if (!sc || !rays || n < 0 || !ids_out || !t_out || n > 0x7fffffffll) {
+    b200rt_internal_set_error("b200rt_trace_rays: bad argument");
+    return B200RT_E_INVALID;
+  }
+  if (n == 0) return B200RT_OK;
+  CK(cudaSetDevice(sc->device));
+  int rc = ensure_pool(sc, (size_t)n + 1024, 1024);
+  if (rc) return rc;
+  cudaStream_t st = sc->stream;
+  float* d_rays = nullptr;
+  int32_t* d_ids = nullptr;
+  float* d_t = nullptr;
+  CK(cudaMalloc((void**)&d_rays, (size_t)n * 8 * sizeof(float)));
+  CK(cudaMalloc((void**)&d_ids, (size_t)n * 2 * sizeof(int32_t)));
+  CK(cudaMalloc((void**)&d_t, (size_t)n * sizeof(float)));
+  CK(cudaMemcpyAsync(d_rays, rays, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
+  k_import_rays<<<sc->sm_count * 4, 256, 0, st>>>(sc->P, d_rays, (uint32_t)n, sc->d_waves);
+  Timers tm; tm.s = st; tm.on = stats != nullptr;
+  tm.mark(ST_GENERATE);
+  int launches = 0, wr = 0;
+  rc = run_waves(sc, exact != 0, true, false, tm, &launches, &wr);
+  if (rc) return rc;
+  k_export_ids<<<sc->sm_count * 4, 256, 0, st>>>(sc->P, (uint32_t)n, d_ids, d_t);
+  CK(cudaMemcpyAsync(ids_out, d_ids, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(t_out, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (stats) {
+    Counters hc;
+    CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
+    memset(stats, 0, sizeof(*stats));
+    stats->nodes_visited = hc.nodes_visited; stats->tris_tested = hc.tris_tested;
+    stats->spheres_tested = hc.spheres_tested; stats->instances_entered = hc.instances_entered;
+    stats->rays_primary = (uint64_t)n;
+    float ms[ST_COUNT];
+    tm.collect(ms);
+    stats->ms_extend = ms[ST_EXTEND];
+    stats->launches = launches; stats->waves = 1;
+  }
+  cudaFree(d_rays); cudaFree(d_ids); cudaFree(d_t);
+  return B200RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// rt_common.cuh — shared device types for the B200 rendering core.
+//
+// Arithmetic policy: this translation unit is compiled with -fmad=false and the
+// default -prec-div=true / -prec-sqrt=true, so `a*b+c`, `/` and sqrtf are plain
+// IEEE binary32 operations in source order — the same values the reference's
+// x86-64 build produces (no FMA contraction there either).
+// Where the reference's unqualified pow/exp/log bind to the double overloads
+// the kernels call the double functions too.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200rt.h"
+
+#define RT_INF __int_as_float(0x7f800000)
+
+struct v3 {
+  float x, y, z;
+};
+__host__ __device__ __forceinline__ v3 mk3(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ __forceinline__ v3 ld3(const float* p) { return mk3(p[0], p[1], p[2]); }
+__device__ __forceinline__ v3 operator+(v3 a, v3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ v3 operator-(v3 a, v3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ v3 operator-(v3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ v3 operator*(v3 a, v3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ v3 operator*(v3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ v3 operator*(float s, v3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ v3 operator/(v3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+// Vector3::dot — (x*x') + (y*y') + (z*z') left to right (HW3/include/Vector3.h:107-109)
+__device__ __forceinline__ float dot(v3 a, v3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+__device__ __forceinline__ v3 cross(v3 a, v3 b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float length(v3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+__device__ __forceinline__ v3 normalize(v3 a) { return a / length(a); }
+__device__ __forceinline__ bool is_zero(v3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
+
+// ---- counter-based RNG (specification shared with oracle/oracle.c) ----------
+__host__ __device__ __forceinline__ uint32_t rng_mix(uint32_t a, uint32_t b) {
+  uint32_t h = a * 0x9E3779B1u + b;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__host__ __device__ __forceinline__ float rng_u01(uint32_t key, uint32_t dim) {
+  return (float)(rng_mix(key, dim ^ 0xA511E9B3u) >> 8) * (1.0f / 16777216.0f);
+}
+
+// ---- device scene -----------------------------------------------------------
+struct DScene {
+  int semantics, max_depth;
+  v3 background, ambient;
+  float shadow_eps, isect_eps;
+  uint32_t root;
+  float root_box[6];
+  const float4* nodes;      // 4 x float4 per inner node (b200rt_bvh_node verbatim)
+  const float4* tris;       // 3 x float4 per triangle: v0|a1.x, a1.yz|a2.xy, a2.z|n
+  const int2* tri_info;     // material, flags
+  const int* tri_vidx;      // 3 per triangle
+  const float4* vnormal;    // per vertex
+  const b200rt_mesh* meshes;
+  const b200rt_instance* inst;
+  const b200rt_sphere* spheres;
+  const b200rt_triprim* triprims;
+  const b200rt_material* mats;
+  const b200rt_light* lights;
+  int n_lights, n_tris, n_spheres, n_inst;
+  b200rt_camera cam;
+};
+
+// ---- vertex pool (wavefront state) -----------------------------------------
+// One slot per path vertex. Wave d occupies the contiguous slot range
+// [wave[d].begin, wave[d].begin + wave[d].count); children are appended to the
+// next wave with warp-aggregated atomics.
+#define RT_META_DEPTH(m) ((m)&0xFFu)
+#define RT_META_INMEDIUM 0x100u
+#define RT_META_PRIMARY 0x200u
+
+struct WaveInfo {
+  uint32_t begin, count;
+};
+
+struct Pool {
+  uint32_t capacity;
+  float4* ray_o;     // o.xyz, time
+  float4* ray_d;     // d.xyz, as_float(meta)
+  uint32_t* key;     // RNG stream of the vertex
+  uint32_t* pixel;   // pixel index (wave 0: also sample id in the high bits via sample[])
+  uint32_t* sample;  // stratum index of the camera sample (wave 0 only)
+  float4* hit_a;     // t, beta, gamma, as_float(top_ref)
+  int2* hit_b;       // top_rank, tri
+  float4* nrm;       // shading normal xyz, as_float(material)
+  float4* rec0;      // local colour rgb, fresnel r
+  float4* rec1;      // km rgb, as_float(child_mirror)
+  float4* rec2;      // k  rgb, as_float(child_reflect)
+  uint32_t* rec3;    // child_transmit
+  float4* final_c;   // combined colour (after the backward pass)
+};
+
+struct ShadowQueue {
+  uint32_t capacity;
+  float4* o;         // o.xyz, t_limit
+  float4* d;         // d.xyz, as_float(result slot)
+  float* time;
+  uint8_t* vis;      // per (vertex slot * n_lights + light): 1 = lit, 0 = occluded / inactive
+};
+
+struct Counters {
+  unsigned long long rays_primary, rays_shadow, rays_secondary;
+  unsigned long long nodes_visited, tris_tested, spheres_tested, instances_entered;
+  unsigned long long sh_nodes_visited, sh_tris_tested, sh_spheres_tested, sh_instances_entered;
+  unsigned int overflow;   // pool / queue overflow flag
+  unsigned int shadow_count;
+  unsigned int work_extend, work_shadow;  // persistent-kernel work cursors
+  unsigned int pad;
+};

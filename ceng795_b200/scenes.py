@@ -153,7 +153,7 @@ def heightfield(n, seed=SEED, extent=4.0):
 
 
 def cfg2_hw3(n=724, width=1920, height=1080, n_instances=8, depth=2, seed=SEED, image_name="cfg2.png",
-             smooth=False) -> str:
+             smooth=False, cam_angle_deg=0.0) -> str:
     """Config 2 — HW2-era features in the HW3 dialect (the HW2 tree lacks MeshInstance):
     a (2*n*n)-triangle heightfield (n=724 -> 1 048 352), `n_instances` transformed
     instances of it, 4 spheres, 2 point lights, mirror depth 2, 1 spp."""
@@ -188,9 +188,12 @@ def cfg2_hw3(n=724, width=1920, height=1080, n_instances=8, depth=2, seed=SEED, 
                 f"      <Center>{cb + i + 1}</Center>\n      <Radius>{_f([sph_r[i]])}</Radius>\n    </Sphere>\n")
     aspect = width / height
     shading = ' shadingMode="smooth"' if smooth else ""
+    ca, sa = np.cos(np.radians(cam_angle_deg)), np.sin(np.radians(cam_angle_deg))
+    cam_pos = [5.6 * sa, 3.1, 5.6 * ca]       # orbit about +y (angle 0 = the canonical camera)
+    cam_gaze = [-sa, -0.62, -ca]
     return ("<Scene>\n  <BackgroundColor>30 40 60</BackgroundColor>\n  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
             f"  <MaxRecursionDepth>{depth}</MaxRecursionDepth>\n  <Cameras>\n    <Camera id=\"1\">\n"
-            "      <Position>0 3.1 5.6</Position>\n      <Gaze>0 -0.62 -1</Gaze>\n      <Up>0 1 0</Up>\n"
+            f"      <Position>{_f(cam_pos)}</Position>\n      <Gaze>{_f(cam_gaze)}</Gaze>\n      <Up>0 1 0</Up>\n"
             f"      <NearPlane>{_f([-0.45 * aspect, 0.45 * aspect, -0.45, 0.45])}</NearPlane>\n"
             "      <NearDistance>1</NearDistance>\n"
             f"      <ImageResolution>{width} {height}</ImageResolution>\n      <NumSamples>1</NumSamples>\n"

@@ -265,7 +265,10 @@ typedef struct B200RenderOpts {
 
 typedef struct B200RenderStats {
   uint64_t rays_primary, rays_shadow, rays_secondary;
+  /* closest-hit (extend) launches only: */
   uint64_t nodes_visited, tris_tested, spheres_tested, instances_entered;
+  /* any-hit (shadow) launches only: */
+  uint64_t sh_nodes_visited, sh_tris_tested, sh_spheres_tested, sh_instances_entered;
   float ms_generate, ms_extend, ms_shade, ms_shadow, ms_total;
   int32_t waves, launches;
 } B200RenderStats;
@@ -293,6 +296,12 @@ int b200rt_primary_ids(b200rt_scene*, int camera_index, const B200RenderOpts*, i
  * ray: o.xyz, time, d.xyz, tmax-unused).  Test/measurement hook for a4-a8. */
 int b200rt_trace_rays(b200rt_scene*, const float* rays, int64_t n, int32_t exact_traversal,
                       int32_t* ids_out, float* t_out, B200RenderStats* stats_out);
+
+/* The CUDA stream (cudaStream_t) every launch of this scene is issued on, so a
+ * caller can bracket calls with its own events. */
+void* b200rt_scene_stream(b200rt_scene*);
+/* Bytes of scene data resident in HBM (nodes + triangles + tables). */
+uint64_t b200rt_scene_bytes(b200rt_scene*);
 
 const char* b200rt_last_error(void);
 const char* b200rt_version(void);

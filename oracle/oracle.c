@@ -350,9 +350,9 @@ static int instance_intersect(const Ctx* cx, int idx, const float* box, const Ra
 /* BVH::intersect — HW3/src/Bounding_volume_hierarchy.cpp:31-55 */
 static int bvh_intersect(const Ctx* cx, uint32_t node, const float* box, const Ray* ray, Hit* hit) {
   const b200rt_bvh_node* n = cx->d->nodes + node;
-  cx->c->nodes_visited++;
   const float bt = box_intersect(box, box + 3, ray, cx->d->isect_eps);
   if (bt < 0.0f || bt == INFINITY) return 0;
+  cx->c->nodes_visited++; /* nodes whose gate passed = 64-byte node records a flattened traversal fetches */
   int any = 0;
   Hit lh; memset(&lh, 0, sizeof(lh)); lh.t = INFINITY; lh.top_rank = -1; lh.tri = -1;
   if (shape_intersect(cx, n->left, n->lmin, ray, &lh) && lh.t > 0.0f && lh.t < hit->t) {

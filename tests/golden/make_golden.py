@@ -1,0 +1,41 @@
+"""Regenerates tests/golden/*.png by running the UNTOUCHED reference binaries
+(oracle/_ref/, built by oracle/build_ref.sh from /root/reference) on the seeded
+scenes below.  Run in the build container; the fixtures are committed so that
+the GPU box (no /root/reference) can still pin both the oracle and the CUDA path.
+
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from ceng795_b200 import image, scenes  # noqa: E402
+from oracle import cpu  # noqa: E402
+
+#: name -> (tree, generator, kwargs)
+CASES = {
+    "cfg1_hw1_96": ("hw1", "cfg1_hw1", dict(width=96, height=96)),
+    "cfg1_hw1_depth0": ("hw1", "cfg1_hw1", dict(width=64, height=48, depth=0, n_spheres=12)),
+    "cfg2_hw3_n32": ("hw3", "cfg2_hw3", dict(n=32, width=160, height=90)),
+    "cfg2_hw3_n48_smooth": ("hw3", "cfg2_hw3", dict(n=48, width=128, height=96, smooth=True, depth=3)),
+}
+
+
+def scene_xml(name):
+    tree, gen, kw = CASES[name]
+    return tree, getattr(scenes, gen)(**kw)
+
+
+if __name__ == "__main__":
+    meta = {}
+    for name in CASES:
+        tree, xml = scene_xml(name)
+        res = cpu.run_reference(tree, xml)
+        img = list(res["images"].values())[0]
+        image.write_png(os.path.join(HERE, name + ".png"), img)
+        meta[name] = {"tree": tree, "shape": list(img.shape), "threads": res["threads"]}
+        print(name, img.shape)
+    json.dump(meta, open(os.path.join(HERE, "golden.json"), "w"), indent=1)

@@ -1,0 +1,116 @@
+"""GPU: parity of the CUDA core (through the C ABI) with the CPU oracle, the
+reference-rendered golden PNGs and, at BASELINE sizes, size-independent
+properties.  Integer outputs (hit ids) must be bit-exact; 8-bit images within
+1 LSB on >= 99.9 % of pixels (BASELINE.json north_star) — and in practice the
+float accumulators are compared bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from ceng795_b200 import image, scene, scenes
+from oracle import cpu
+from tests.golden.make_golden import CASES, scene_xml
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+pytestmark = pytest.mark.gpu
+
+
+def _render_pair(xml, tree, **opts):
+    sc = scene.Scene(xml, tree)
+    rgbw, st = sc.render_image(0, **opts)
+    o_rgbw, o_ids, o_t, cnt = cpu.render(sc.host, 0, want_ids=True)
+    return sc, rgbw, st, o_rgbw, o_ids, o_t, cnt
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_image_matches_golden_and_oracle(gpu, name):
+    tree, xml = scene_xml(name)
+    sc, rgbw, st, o_rgbw, o_ids, o_t, cnt = _render_pair(xml, tree)
+    got = image.quantise(rgbw, sc.semantics)
+    want = image.read_png(os.path.join(GOLDEN, name + ".png"))
+    cmp = image.compare_8bit(got, want)
+    assert cmp["within1"] >= 0.999 and cmp["max"] <= 2, cmp
+    cmp_o = image.compare_8bit(got, image.quantise(o_rgbw, sc.semantics))
+    assert cmp_o["within1"] >= 0.999, cmp_o
+    # ray bookkeeping is integer work: identical recursion trees => identical counts
+    assert st.rays_primary == cnt.rays_primary
+    assert st.rays_shadow == cnt.rays_shadow
+    assert st.rays_secondary == cnt.rays_secondary
+    # float accumulators: identical arithmetic order => (almost) all bits equal
+    same = np.mean(rgbw.view(np.uint32) == o_rgbw.view(np.uint32))
+    assert same >= 0.999, same
+
+
+@pytest.mark.parametrize("name", ["cfg1_hw1_96", "cfg2_hw3_n32", "cfg2_hw3_n48_smooth"])
+def test_primary_hit_ids_bit_exact(gpu, name):
+    tree, xml = scene_xml(name)
+    sc = scene.Scene(xml, tree)
+    _, o_ids, o_t, _ = cpu.render(sc.host, 0, want_image=False, want_ids=True)
+    for exact in (0, 1):
+        ids, t = sc.primary_ids(0, exact_traversal=exact)
+        assert np.array_equal(ids, o_ids), (exact, float(np.mean(np.all(ids == o_ids, -1))))
+        assert np.array_equal(t.view(np.uint32), o_t.view(np.uint32))
+
+
+def test_random_rays_pruned_equals_exact_equals_oracle(gpu):
+    xml = scenes.cfg2_hw3(n=96, width=16, height=16, seed=5)
+    sc = scene.Scene(xml, "hw3")
+    rng = np.random.default_rng(7)
+    n = 200_000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(-5, 5, (n, 3)); rays[:, 1] = rng.uniform(0.5, 6, n)
+    d = rng.normal(size=(n, 3)); d[:, 1] = -np.abs(d[:, 1])
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    # edge cases: axis-parallel directions (box test skips |d| < 1e-6 axes) and zero direction
+    rays[:64, 4:7] = 0; rays[:64, 5] = -1
+    rays[64:96, 4:7] = [1, 0, 0]
+    rays[96:100, 4:7] = 0
+    ids_p, t_p, st_p = sc.trace_rays(rays, exact=False)
+    ids_e, t_e, st_e = sc.trace_rays(rays, exact=True)
+    o_ids, o_t, cnt = cpu.trace_rays(sc.host, rays)
+    assert np.array_equal(ids_e, o_ids) and np.array_equal(t_e.view(np.uint32), o_t.view(np.uint32))
+    assert np.array_equal(ids_p, o_ids) and np.array_equal(t_p.view(np.uint32), o_t.view(np.uint32))
+    # exact mode visits exactly the reference's node set
+    assert st_e.nodes_visited == cnt.nodes_visited
+    assert st_e.tris_tested == cnt.tris_tested
+    assert st_p.nodes_visited < st_e.nodes_visited
+
+
+def test_row_ranges_tile_the_frame(gpu):
+    """multi-GPU split primitive: rendering row ranges separately == the full frame."""
+    tree, xml = scene_xml("cfg2_hw3_n32")
+    sc = scene.Scene(xml, tree)
+    full, _ = sc.render_image(0)
+    w, h = sc.image_size(0)
+    parts = np.zeros_like(full)
+    for r0, r1 in ((0, h // 3), (h // 3, h // 2), (h // 2, h)):
+        part, _ = sc.render_image(0, row_begin=r0, row_end=r1)
+        parts[r0:r1] = part[r0:r1]
+        assert not part[:r0].any() and not part[r1:].any()
+    assert np.array_equal(parts.view(np.uint32), full.view(np.uint32))
+    inter = np.zeros_like(full)
+    for k in range(4):  # the reference's own interleave `j += height_increase`
+        part, _ = sc.render_image(0, row_begin=k, row_end=h, row_stride=4)
+        inter += part
+    assert np.array_equal(inter.view(np.uint32), full.view(np.uint32))
+
+
+def test_full_size_cfg2_properties(gpu):
+    """BASELINE size (1M triangles, 1080p): idempotence, pruned == exact ids, and oracle
+    agreement on a sample of rows (the full oracle frame is the bench's cpu_baseline)."""
+    xml = scenes.cfg2_hw3()
+    sc = scene.Scene(xml, "hw3")
+    a, st = sc.render_image(0)
+    b, _ = sc.render_image(0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    ids_p, t_p = sc.primary_ids(0)
+    ids_e, t_e = sc.primary_ids(0, exact_traversal=1)
+    assert np.array_equal(ids_p, ids_e) and np.array_equal(t_p.view(np.uint32), t_e.view(np.uint32))
+    rows = (500, 540)
+    o_rgbw, o_ids, o_t, _ = cpu.render(sc.host, 0, rows=rows, want_ids=True)
+    sl = slice(*rows)
+    assert np.array_equal(ids_p[sl], o_ids[sl])
+    cmp = image.compare_8bit(image.quantise(a[sl], sc.semantics), image.quantise(o_rgbw[sl], sc.semantics))
+    assert cmp["within1"] >= 0.999, cmp
+    assert st.rays_primary == 1920 * 1080

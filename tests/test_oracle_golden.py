@@ -1,0 +1,48 @@
+"""CPU: the C oracle must reproduce the reference binaries' images byte for byte
+(golden PNGs rendered by oracle/_ref/*, see tests/golden/make_golden.py), and —
+when the compiled reference is present — live renders too."""
+import os
+
+import numpy as np
+import pytest
+
+from ceng795_b200 import image, scene
+from oracle import cpu
+from tests.golden.make_golden import CASES, scene_xml
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_golden_png(name):
+    tree, xml = scene_xml(name)
+    spec = scene.parse_xml(xml, tree)
+    hs = scene.HostScene(spec)
+    rgbw, _, _, cnt = cpu.render(hs, 0)
+    got = image.quantise(rgbw, spec.semantics)
+    want = image.read_png(os.path.join(GOLDEN, name + ".png"))
+    assert got.shape == want.shape
+    cmp = image.compare_8bit(got, want)
+    assert cmp["exact"] == 1.0, cmp  # bit-exact: same compiler, same IEEE arithmetic
+    assert cnt.rays_primary == got.shape[0] * got.shape[1]
+
+
+@pytest.mark.parametrize("tree,gen_kw", [("hw1", dict(width=80, height=60, seed=11)),
+                                         ("hw3", dict(n=24, width=96, height=64, seed=12, depth=4))])
+def test_oracle_matches_live_reference(tree, gen_kw):
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.cfg1_hw1(**gen_kw) if tree == "hw1" else scenes.cfg2_hw3(**gen_kw)
+    ref = cpu.run_reference(tree, xml)
+    want = list(ref["images"].values())[0]
+    spec = scene.parse_xml(xml, tree)
+    hs = scene.HostScene(spec)
+    rgbw, _, _, _ = cpu.render(hs, 0)
+    cmp = image.compare_8bit(image.quantise(rgbw, spec.semantics), want)
+    assert cmp["exact"] == 1.0, cmp
+
+
+def test_parse_time():
+    assert cpu.parse_time_ms("4 seconds 790 milliseconds 898 microseconds") == pytest.approx(4790.898)
+    assert cpu.parse_time_ms("1 minute 2 seconds 0 milliseconds 5 microseconds") == pytest.approx(62000.005)
