@@ -26,8 +26,8 @@ struct TravCounters {
 // Bounding_box::intersect — HW3/src/bounding_box.cpp:17-37.  Returns the
 // reference's accept decision (`!(bbox_t < 0 || bbox_t == inf)`) with exactly
 // the reference's arithmetic; *entry gets max(tmin, 0) for ordering/pruning.
-__device__ __forceinline__ bool box_gate(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, float mxy,
-                                         float mxz, float eps, float* entry) {
+__device__ __noinline__ bool box_gate_exact(v3 o, v3 d, float mnx, float mny, float mnz, float mxx, float mxy,
+                                            float mxz, float eps, float* entry) {
   float tmin = -RT_INF, tmax = RT_INF;
   if (!(fabsf(d.x) < eps)) {
     float a = (mnx - o.x) / d.x, b = (mxx - o.x) / d.x;
@@ -54,6 +54,39 @@ __device__ __forceinline__ bool box_gate(v3 o, v3 d, float mnx, float mny, float
   if (bt < 0.0f || bt == RT_INF) return false;
   *entry = fmaxf(tmin, 0.0f);
   return true;
+}
+
+// Ray with the per-ray constants of the filtered box test.
+struct RayCtx {
+  v3 o, d, inv;
+  bool slow;  // some |d_i| < eps (axis skipped by the reference): always take the exact path
+};
+__device__ __forceinline__ RayCtx make_ray(v3 o, v3 d, float eps) {
+  RayCtx r;
+  r.o = o; r.d = d;
+  r.slow = (fabsf(d.x) < eps) || (fabsf(d.y) < eps) || (fabsf(d.z) < eps);
+  r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  return r;
+}
+
+// Filtered gate: decides with (b - o) * (1/d) when the outcome is clear by a
+// margin that covers the rounding difference to the reference's (b - o) / d
+// (|diff| <= 2^-24 + 2^-23 relative, margin 5e-7), and falls back to the exact
+// division-based test otherwise.  The accept/reject DECISION is therefore always
+// the reference's; only the instruction count changes.
+__device__ __forceinline__ bool box_gate(const RayCtx& r, float mnx, float mny, float mnz, float mxx, float mxy,
+                                         float mxz, float eps, float* entry) {
+  if (!r.slow) {
+    const float ax = (mnx - r.o.x) * r.inv.x, bx = (mxx - r.o.x) * r.inv.x;
+    const float ay = (mny - r.o.y) * r.inv.y, by = (mxy - r.o.y) * r.inv.y;
+    const float az = (mnz - r.o.z) * r.inv.z, bz = (mxz - r.o.z) * r.inv.z;
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    const float m = 5e-7f * fmaxf(fabsf(tn), fabsf(tf));
+    if (tn + m < tf && tf > 1e-30f && tf < 1e30f && tn > -1e30f) { *entry = fmaxf(tn, 0.0f); return true; }
+    if (tn > tf + m || tf < -1e-30f) return false;
+  }
+  return box_gate_exact(r.o, r.d, mnx, mny, mnz, mxx, mxy, mxz, eps, entry);
 }
 
 // Mesh_triangle::determinant — HW3/include/Mesh_triangle.h:42-47
@@ -245,7 +278,9 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
   best.tri = 0x7fffffff;
   bool found = false;
 
-  v3 co = o, cd = d;            // ray in the current space
+  const RayCtx wr = make_ray(o, d, eps);
+  RayCtx cr = wr;               // ray in the current space
+  v3 co = o, cd = d;
   int cur_rank = 0x7fffffff;    // rank of the instance being traversed
   uint32_t cur_top = B200RT_REF_NONE;
 
@@ -256,7 +291,7 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
     float e = 0.0f;
     bool ok = true;
     if (k == B200RT_KIND_INNER || k == B200RT_KIND_INSTANCE)
-      ok = box_gate(co, cd, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
+      ok = box_gate(cr, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
                     S.root_box[5], eps, &e);
     if (!ok) return false;
     stack[sp] = S.root; stack_t[sp] = e; sp++;
@@ -269,7 +304,7 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
     const uint32_t kind = B200RT_REF_KIND(ref);
     const uint32_t idx = B200RT_REF_INDEX(ref);
     if (kind == 14u) {  // leave instance
-      co = o; cd = d; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE;
+      co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE;
       continue;
     }
     if (!EXACT) {
@@ -291,9 +326,8 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
         const uint32_t ci = B200RT_REF_INDEX(child[c]);
         if (ck == B200RT_KIND_INNER || ck == B200RT_KIND_INSTANCE) {
           bool ok;
-          if (c == 0) ok = box_gate(co, cd, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &entry[0]);
-          else ok = box_gate(co, cd, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &entry[1]);
-          if (ok && ck == B200RT_KIND_INSTANCE && (S.inst[ci].flags & B200RT_INST_DIRECT)) ok = true;
+          if (c == 0) ok = box_gate(cr, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &entry[0]);
+          else ok = box_gate(cr, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &entry[1]);
           push[c] = ok;
         } else if (ck == B200RT_KIND_TRI) {
           cnt.tris++;
@@ -362,12 +396,13 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
           co = xf_point(in->inv, o); cd = xf_vector4(in->inv, d);
         }
       }
+      cr = make_ray(co, cd, eps);
       cur_rank = in->rank; cur_top = ref;
-      if (sp + 2 > RT_STACK) { co = o; cd = d; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; continue; }
+      if (sp + 2 > RT_STACK) { co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; continue; }
       stack[sp] = RT_SENTINEL; stack_t[sp] = 0.f; sp++;
       if (mk == B200RT_KIND_INNER) {
         float e;
-        if (box_gate(co, cd, m->root_box[0], m->root_box[1], m->root_box[2], m->root_box[3], m->root_box[4],
+        if (box_gate(cr, m->root_box[0], m->root_box[1], m->root_box[2], m->root_box[3], m->root_box[4],
                      m->root_box[5], eps, &e)) {
           stack[sp] = m->root; stack_t[sp] = e; sp++;
         }
