@@ -19,6 +19,7 @@ SEM_BY_NAME = {"hw1": SEM_HW1, "hw2": SEM_HW2, "hw3": SEM_HW3, "hw4": SEM_HW4, "
                "hw6": SEM_HW6, "hw7": SEM_HW7, "ppm": SEM_PPM}
 
 KIND_INNER, KIND_TRI, KIND_SPHERE, KIND_TRIPRIM, KIND_INSTANCE, KIND_NONE = 0, 1, 2, 3, 4, 15
+KIND_LEAF1, KIND_LEAF4, KIND_FNODE = 5, 8, 9
 
 LIGHT_POINT, LIGHT_AREA, LIGHT_SPOT, LIGHT_DIRECTIONAL, LIGHT_ENV, LIGHT_MESH, LIGHT_SPHERE = range(7)
 
@@ -30,7 +31,7 @@ class BvhNode(C.Structure):
 
 class Mesh(C.Structure):
     _fields_ = [("root", c_u), ("root_box", c_f * 6), ("tri_begin", c_i), ("tri_count", c_i),
-                ("node_begin", c_i), ("node_count", c_i)]
+                ("node_begin", c_i), ("node_count", c_i), ("fast_root", c_u), ("pad", c_i)]
 
 
 class Instance(C.Structure):
@@ -82,6 +83,9 @@ class SceneDesc(C.Structure):
         ("n_nodes", c_i), ("nodes", C.POINTER(BvhNode)),
         ("n_tris", c_i), ("tri_geom", C.POINTER(c_f)), ("tri_vidx", C.POINTER(c_i)),
         ("tri_info", C.POINTER(c_i)),
+        ("n_fast_nodes", c_i), ("fast_nodes", C.POINTER(BvhNode)), ("n_fast_tris", c_i),
+        ("fast_tri_geom", C.POINTER(c_f)),
+        ("fast_tri_ref", C.POINTER(c_i)), ("tri_gate", C.POINTER(c_f)),
         ("n_verts", c_i), ("vert_pos", C.POINTER(c_f)), ("vert_normal", C.POINTER(c_f)),
         ("n_meshes", c_i), ("meshes", C.POINTER(Mesh)),
         ("n_instances", c_i), ("instances", C.POINTER(Instance)),

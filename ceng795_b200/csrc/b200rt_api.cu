@@ -144,10 +144,10 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
       k_extend_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
     } else if (S.semantics >= B200RT_SEM_HW7) {
       if (exact) k_extend<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
-      else k_extend<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
+      else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     } else {
       if (exact) k_extend<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
-      else k_extend<false, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
+      else k_trace_fast<false, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     }
     (*launches)++;
     tm.mark(ST_EXTEND);
@@ -161,10 +161,10 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
       k_shadow_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
     } else if (S.semantics >= B200RT_SEM_HW7) {
       if (exact) k_shadow<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
-      else k_shadow<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
+      else k_trace_fast<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     } else {
       if (exact) k_shadow<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
-      else k_shadow<false, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
+      else k_trace_fast<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     }
     (*launches)++;
     tm.mark(ST_SHADOW);
@@ -270,7 +270,8 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
   Counters hc;
   CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
   if (hc.overflow) {
-    b200rt_internal_set_error("vertex pool / shadow queue overflow (recursion tree larger than the pool)");
+    b200rt_internal_set_error(hc.overflow == 2 ? "traversal stack overflow (BVH deeper than RT_FSTACK)"
+                                               : "vertex pool / shadow queue overflow (recursion tree larger than the pool)");
     return B200RT_E_UNSUPPORTED;
   }
   if (stats) {
@@ -361,6 +362,10 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     S.tris = reinterpret_cast<const float4*>(p);
     bytes += (size_t)d->n_tris * 48;
   }
+  UP(S.fast_nodes, d->fast_nodes, d->n_fast_nodes, b200rt_bvh_node);
+  UP(S.fast_tris, d->fast_tri_geom, (size_t)d->n_fast_tris * 12, float);
+  UP(S.fast_tri_ref, d->fast_tri_ref, (size_t)d->n_fast_tris, int32_t);
+  UP(S.tri_gate, d->tri_gate, (size_t)d->n_tris * 6, float);
   UP(S.tri_info, d->tri_info, (size_t)d->n_tris * 2, int32_t);
   UP(S.tri_vidx, d->tri_vidx, (size_t)d->n_tris * 3, int32_t);
   {

@@ -1,0 +1,155 @@
+// fast_bvh.cpp — binned-SAH BVH builder for the device traversal (see fast_bvh.h).
+#include "fast_bvh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace b200rt_fast {
+namespace {
+
+constexpr int kBins = 16;
+constexpr int kMaxLeaf = 4;
+constexpr float kTraversalCost = 1.5f;  // relative to one triangle test
+
+struct Prim {
+  float mn[3], mx[3], c[3];
+  int32_t id;
+};
+struct Bx {
+  float mn[3], mx[3];
+  Bx() {
+    for (int i = 0; i < 3; i++) { mn[i] = std::numeric_limits<float>::infinity(); mx[i] = -mn[i]; }
+  }
+  void add(const float* a, const float* b) {
+    for (int i = 0; i < 3; i++) { mn[i] = std::min(mn[i], a[i]); mx[i] = std::max(mx[i], b[i]); }
+  }
+  void add(const Bx& o) { add(o.mn, o.mx); }
+  float area() const {
+    const float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+    if (!(dx >= 0.f)) return 0.f;
+    return 2.f * (dx * dy + dy * dz + dz * dx);
+  }
+};
+
+struct Ctx {
+  std::vector<Prim> prims;
+  std::vector<b200rt_bvh_node>* nodes;
+  std::vector<int32_t>* order;
+  float grow;
+};
+
+void put(float* mn, float* mx, const Bx& b, float g) {
+  for (int i = 0; i < 3; i++) { mn[i] = b.mn[i] - g; mx[i] = b.mx[i] + g; }
+}
+
+uint32_t make_leaf(Ctx& cx, int s, int e) {
+  const int n = e - s;
+  const uint32_t start = (uint32_t)cx.order->size();
+  for (int i = s; i < e; i++) cx.order->push_back(cx.prims[i].id);
+  return B200RT_REF(B200RT_KIND_LEAF1 + (uint32_t)(n - 1), start);
+}
+
+// Returns the child ref of the subtree over prims[s,e); *box = its tight bounds.
+uint32_t build_rec(Ctx& cx, int s, int e, Bx* box) {
+  Bx b, cb;
+  for (int i = s; i < e; i++) {
+    b.add(cx.prims[i].mn, cx.prims[i].mx);
+    cb.add(cx.prims[i].c, cx.prims[i].c);
+  }
+  *box = b;
+  const int n = e - s;
+  if (n == 1) return make_leaf(cx, s, e);
+
+  // best binned split over the three axes
+  float best_cost = std::numeric_limits<float>::infinity();
+  int best_axis = -1, best_bin = -1;
+  for (int ax = 0; ax < 3; ax++) {
+    const float ext = cb.mx[ax] - cb.mn[ax];
+    if (!(ext > 0.f)) continue;
+    Bx bb[kBins];
+    int cnt[kBins] = {0};
+    const float scale = (float)kBins / ext;
+    for (int i = s; i < e; i++) {
+      int k = (int)((cx.prims[i].c[ax] - cb.mn[ax]) * scale);
+      k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+      bb[k].add(cx.prims[i].mn, cx.prims[i].mx);
+      cnt[k]++;
+    }
+    float la[kBins - 1], ra[kBins - 1];
+    int ln[kBins - 1], rn[kBins - 1];
+    Bx acc;
+    int c = 0;
+    for (int k = 0; k < kBins - 1; k++) { acc.add(bb[k]); c += cnt[k]; la[k] = acc.area(); ln[k] = c; }
+    acc = Bx(); c = 0;
+    for (int k = kBins - 1; k > 0; k--) { acc.add(bb[k]); c += cnt[k]; ra[k - 1] = acc.area(); rn[k - 1] = c; }
+    for (int k = 0; k < kBins - 1; k++) {
+      if (ln[k] == 0 || rn[k] == 0) continue;
+      const float cost = la[k] * ln[k] + ra[k] * rn[k];
+      if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = k; }
+    }
+  }
+  const float pa = b.area();
+  if (n <= kMaxLeaf) {
+    const float leaf_cost = (float)n * pa;
+    const float split_cost = kTraversalCost * pa + best_cost;
+    if (best_axis < 0 || leaf_cost <= split_cost) return make_leaf(cx, s, e);
+  }
+  int mid;
+  if (best_axis < 0) {
+    mid = s + n / 2;  // coincident centroids: split by position in the array
+  } else {
+    const float ext = cb.mx[best_axis] - cb.mn[best_axis];
+    const float scale = (float)kBins / ext;
+    const float cmin = cb.mn[best_axis];
+    const int ax = best_axis, bin = best_bin;
+    Prim* first = cx.prims.data() + s;
+    Prim* last = cx.prims.data() + e;
+    Prim* m = std::partition(first, last, [=](const Prim& p) {
+      int k = (int)((p.c[ax] - cmin) * scale);
+      k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+      return k <= bin;
+    });
+    mid = (int)(m - cx.prims.data());
+    if (mid == s || mid == e) mid = s + n / 2;
+  }
+  const uint32_t me = (uint32_t)cx.nodes->size();
+  cx.nodes->push_back(b200rt_bvh_node());
+  Bx lb, rb;
+  const uint32_t l = build_rec(cx, s, mid, &lb);
+  const uint32_t r = build_rec(cx, mid, e, &rb);
+  b200rt_bvh_node nd;
+  std::memset(&nd, 0, sizeof(nd));
+  put(nd.lmin, nd.lmax, lb, cx.grow);
+  put(nd.rmin, nd.rmax, rb, cx.grow);
+  nd.left = l;
+  nd.right = r;
+  (*cx.nodes)[me] = nd;
+  return B200RT_REF(B200RT_KIND_FNODE, me);
+}
+
+}  // namespace
+
+uint32_t build(const float* boxes6, int n, int tri_base, float grow, std::vector<b200rt_bvh_node>& nodes,
+               std::vector<int32_t>& order) {
+  if (n <= 0) return B200RT_REF_NONE;
+  Ctx cx;
+  cx.nodes = &nodes;
+  cx.order = &order;
+  cx.grow = grow;
+  cx.prims.resize((size_t)n);
+  for (int i = 0; i < n; i++) {
+    Prim& p = cx.prims[i];
+    for (int k = 0; k < 3; k++) {
+      p.mn[k] = boxes6[6 * (size_t)i + k];
+      p.mx[k] = boxes6[6 * (size_t)i + 3 + k];
+      p.c[k] = 0.5f * (p.mn[k] + p.mx[k]);
+    }
+    p.id = tri_base + i;
+  }
+  Bx root;
+  return build_rec(cx, 0, n, &root);
+}
+
+}  // namespace b200rt_fast

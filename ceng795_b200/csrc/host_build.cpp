@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/b200rt.h"
+#include "fast_bvh.h"
 
 namespace {
 
@@ -204,6 +205,7 @@ struct Obj {
 struct BuildOut {
   std::vector<b200rt_bvh_node>* nodes;
   std::vector<uint32_t>* leaf_order;  // refs in DFS order
+  std::vector<Box>* gate;             // optional: per leaf (by ref index) the box of the node that holds it
 };
 void put_box(float* mn, float* mx, const Box& b) {
   store3(mn, b.mn);
@@ -232,6 +234,7 @@ uint32_t build_bvh(std::vector<Obj>& objs, int start, int end, int dim, BuildOut
     n.left = objs[start].ref;
     lb = objs[start].box;
     out.leaf_order->push_back(objs[start].ref);
+    if (out.gate) (*out.gate)[B200RT_REF_INDEX(objs[start].ref)] = box;
   } else {
     uint32_t c = build_bvh(objs, start, mid, (dim + 1) % 3, out, lb);
     n.left = B200RT_REF(B200RT_KIND_INNER, c);
@@ -240,6 +243,7 @@ uint32_t build_bvh(std::vector<Obj>& objs, int start, int end, int dim, BuildOut
     n.right = objs[mid].ref;
     rb = objs[mid].box;
     out.leaf_order->push_back(objs[mid].ref);
+    if (out.gate) (*out.gate)[B200RT_REF_INDEX(objs[mid].ref)] = box;
   } else {
     uint32_t c = build_bvh(objs, mid, end, (dim + 1) % 3, out, rb);
     n.right = B200RT_REF(B200RT_KIND_INNER, c);
@@ -306,6 +310,9 @@ struct b200rt_builder {
   std::vector<float> tri_geom;
   std::vector<int32_t> tri_vidx, tri_info;
   std::vector<float> vert_normal;
+  std::vector<b200rt_bvh_node> fast_nodes;
+  std::vector<float> fast_tri_geom, tri_gate;
+  std::vector<int32_t> fast_tri_ref;
   std::vector<b200rt_mesh> meshes;
   std::vector<b200rt_instance> instances;
   std::vector<b200rt_sphere> spheres;
@@ -544,7 +551,9 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
     fm.tri_count = nf;
     fm.node_begin = (int)b->nodes.size();
     std::vector<uint32_t> order;
+    std::vector<Box> gate((size_t)nf);
     Box root_box;
+    fm.fast_root = B200RT_REF_NONE;
     if (hw1 || nf == 0) {
       // HW1 has no BVH (HW1/Scene.cpp:35-54): keep file order.
       for (int f = 0; f < nf; f++) order.push_back(B200RT_REF(B200RT_KIND_TRI, f));
@@ -554,7 +563,7 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
       root_box = objs[0].box;
       fm.root = B200RT_REF(B200RT_KIND_TRI, fm.tri_begin);
     } else {
-      BuildOut bo{&b->nodes, &order};
+      BuildOut bo{&b->nodes, &order, &gate};
       uint32_t r = build_bvh(objs, 0, nf, 0, bo, root_box);
       fm.root = B200RT_REF(B200RT_KIND_INNER, r);
     }
@@ -580,6 +589,32 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
       b->tri_vidx.push_back(i0); b->tri_vidx.push_back(i1); b->tri_vidx.push_back(i2);
       b->tri_info.push_back(m.material);
       b->tri_info.push_back(m.smooth ? 1 : 0);
+      float gb[6];
+      put_box(gb, gb + 3, gate[f]);
+      b->tri_gate.insert(b->tri_gate.end(), gb, gb + 6);
+    }
+    if (!hw1 && nf >= 2) {
+      // SAH tree for the device over the same triangles (global ids = DFS order)
+      std::vector<float> tb((size_t)nf * 6);
+      float ext = 0.f;
+      for (int k = 0; k < nf; k++) {
+        const int f = (int)B200RT_REF_INDEX(order[k]);
+        const Box bx = tri_box(vert(m.faces[3 * f]), vert(m.faces[3 * f + 1]), vert(m.faces[3 * f + 2]));
+        put_box(&tb[6 * (size_t)k], &tb[6 * (size_t)k + 3], bx);
+      }
+      for (int a = 0; a < 3; a++) {
+        ext = std::fmax(ext, root_box.mx[a] - root_box.mn[a]);
+        ext = std::fmax(ext, std::fmax(std::fabs(root_box.mx[a]), std::fabs(root_box.mn[a])));
+      }
+      // conservative growth: covers the rounding slop of the Cramer test and the
+      // HW7/PPM acceptance band (beta, gamma >= -eps) — DESIGN.md §4b
+      const float grow = ext * (2e-5f + 4.0f * b->desc.isect_eps) + 1e-30f;
+      const size_t o0 = b->fast_tri_ref.size();
+      fm.fast_root = b200rt_fast::build(tb.data(), nf, fm.tri_begin, grow, b->fast_nodes, b->fast_tri_ref);
+      for (size_t k = o0; k < b->fast_tri_ref.size(); k++) {
+        const float* g = &b->tri_geom[12 * (size_t)b->fast_tri_ref[k]];
+        b->fast_tri_geom.insert(b->fast_tri_geom.end(), g, g + 12);
+      }
     }
     b->meshes.push_back(fm);
   }
@@ -599,6 +634,7 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
       b->tri_vidx.push_back(t.idx[0]); b->tri_vidx.push_back(t.idx[1]); b->tri_vidx.push_back(t.idx[2]);
       b->tri_info.push_back(t.material);
       b->tri_info.push_back(0);
+      b->tri_gate.insert(b->tri_gate.end(), 6, 0.0f);
     }
   }
   // Vertex::finalize_normal — HW3/src/Scene.cpp:872-877
@@ -717,7 +753,7 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
     root_box = top[0].box;
     order.push_back(top[0].ref);
   } else {
-    BuildOut bo{&b->nodes, &order};
+    BuildOut bo{&b->nodes, &order, nullptr};
     uint32_t r = build_bvh(top, 0, (int)top.size(), 0, bo, root_box);
     b->desc.root = B200RT_REF(B200RT_KIND_INNER, r);
   }
@@ -737,6 +773,10 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
   d.n_nodes = (int)b->nodes.size();           d.nodes = b->nodes.data();
   d.n_tris = (int)(b->tri_info.size() / 2);   d.tri_geom = b->tri_geom.data();
   d.tri_vidx = b->tri_vidx.data();            d.tri_info = b->tri_info.data();
+  d.n_fast_nodes = (int)b->fast_nodes.size(); d.fast_nodes = b->fast_nodes.data();
+  d.n_fast_tris = (int)b->fast_tri_ref.size();
+  d.fast_tri_geom = b->fast_tri_geom.data();  d.fast_tri_ref = b->fast_tri_ref.data();
+  d.tri_gate = b->tri_gate.data();
   d.n_verts = nv;                             d.vert_pos = b->verts.data();
   d.vert_normal = b->vert_normal.data();
   d.n_meshes = (int)b->meshes.size();         d.meshes = b->meshes.data();

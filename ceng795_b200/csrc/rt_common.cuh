@@ -54,6 +54,10 @@ struct DScene {
   float root_box[6];
   const float4* nodes;      // 4 x float4 per inner node (b200rt_bvh_node verbatim)
   const float4* tris;       // 3 x float4 per triangle: v0|a1.x, a1.yz|a2.xy, a2.z|n
+  const float4* fast_nodes; // SAH tree (csrc/fast_bvh.h), same 64-byte records
+  const float4* fast_tris;  // triangles again, in SAH leaf order
+  const int* fast_tri_ref;  // leaf-order position -> triangle index (DFS order)
+  const float* tri_gate;    // 6 floats per triangle: the reference's innermost gate box
   const int2* tri_info;     // material, flags
   const int* tri_vidx;      // 3 per triangle
   const float4* vnormal;    // per vertex

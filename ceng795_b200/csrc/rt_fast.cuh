@@ -1,0 +1,293 @@
+// rt_fast.cuh — the default traversal: persistent warps with per-lane ray
+// replacement, walking the reference's (small) top-level tree with its exact
+// gates and, inside a mesh, the SAH "fast" BVH (csrc/fast_bvh.h).
+//
+// Why the answer is still the reference's.  In the reference a
+// mesh triangle k is reachable iff every BVH node on its root path passes
+// Bounding_box::intersect (HW7/src/Bounding_volume_hierarchy.cpp:31-35).  All
+// those boxes are nested (Bounding_box::expand is min/max, bounding_box.cpp:6-17)
+// and the slab test is monotone under IEEE rounding — a superset box yields a
+// superset [tmin,tmax] at every stage — so the whole chain passes iff the
+// innermost box does.  That box (the reference node holding k) is stored per
+// triangle in `tri_gate`; a triangle found through the SAH tree is admitted iff
+// `box_gate(tri_gate[k])` passes, with the reference's own division-based
+// arithmetic.  The SAH boxes themselves only need to be conservative (they are
+// grown, and tested with slack), because every candidate is re-decided by the
+// reference's triangle test + gate.  The winner is chosen by the key
+// (t, top-level DFS rank, triangle DFS index), independent of visiting order.
+#pragma once
+#include "rt_traverse.cuh"
+
+#define RT_FSTACK 64
+#define RT_REFILL_MIN_IDLE 8  // refill the warp when at least this many lanes are idle
+
+// Conservative slab test for SAH boxes (grown on the host): may accept a box
+// the exact test would reject, never the reverse by more than the growth.
+__device__ __forceinline__ bool box_loose(const RayCtx& r, float mnx, float mny, float mnz, float mxx, float mxy,
+                                          float mxz, float eps, float* entry) {
+  if (!r.slow) {
+    const float ax = (mnx - r.o.x) * r.inv.x, bx = (mxx - r.o.x) * r.inv.x;
+    const float ay = (mny - r.o.y) * r.inv.y, by = (mxy - r.o.y) * r.inv.y;
+    const float az = (mnz - r.o.z) * r.inv.z, bz = (mxz - r.o.z) * r.inv.z;
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    const float tfa = tf + 2e-6f * fmaxf(fabsf(tn), fabsf(tf));
+    *entry = fmaxf(tn, 0.0f);
+    return tn <= tfa && tfa >= 0.0f;
+  }
+  // a direction component below the reference's axis-skip threshold: the
+  // reference test itself on the (superset) box is conservative by monotonicity
+  return box_gate_exact(r.o, r.d, mnx, mny, mnz, mxx, mxy, mxz, eps, entry);
+}
+
+template <bool ANY, int TRI_MODE>
+__global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves,
+                                                         int d, Counters* C) {
+  const uint32_t begin = ANY ? 0u : waves[d].begin;
+  const uint32_t count = ANY ? C->shadow_count : waves[d].count;
+  unsigned int* cursor = ANY ? &C->work_shadow : &C->work_extend;
+  const float eps = S.isect_eps;
+  const unsigned lane = lane_id();
+  TravCounters tc = {0, 0, 0, 0};
+
+  uint32_t stack[RT_FSTACK];
+  float stack_t[RT_FSTACK];
+  int sp = 0;
+  bool has_ray = false, exhausted = false;
+  uint32_t out_slot = 0;
+  v3 o = mk3(0, 0, 0), dir = mk3(0, 0, 0);
+  float time = 0.f, tlimit = RT_INF;
+  RayCtx wr, cr;
+  wr.o = o; wr.d = dir; wr.inv = dir; wr.slow = false;
+  cr = wr;
+  HitRec best;
+  best.t = RT_INF; best.beta = 0.f; best.gamma = 0.f; best.top_ref = B200RT_REF_NONE; best.top_rank = 0x7fffffff;
+  best.tri = 0x7fffffff;
+  bool found = false;
+  int cur_rank = 0x7fffffff;
+  uint32_t cur_top = B200RT_REF_NONE;
+  uint32_t cur = B200RT_REF_NONE;  // node to process next without going through the stack
+  float cur_t = 0.f;
+
+  for (;;) {
+    // ---- refill idle lanes from the wave's work cursor ----------------------
+    const unsigned need = __ballot_sync(0xffffffffu, !has_ray);
+    if (need != 0u && !exhausted) {
+      uint32_t base = 0;
+      const int leader = __ffs(need) - 1;
+      if ((int)lane == leader) base = atomicAdd(cursor, (unsigned)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (base + (uint32_t)__popc(need) >= count) exhausted = true;
+      if (!has_ray) {
+        const uint32_t k = base + __popc(need & ((1u << lane) - 1u));
+        if (k < count) {
+          float4 ro, rd;
+          if (ANY) {
+            ro = Q.o[k]; rd = Q.d[k];
+            time = Q.time[k]; tlimit = ro.w;
+            out_slot = __float_as_uint(rd.w);
+          } else {
+            out_slot = begin + k;
+            ro = P.ray_o[out_slot]; rd = P.ray_d[out_slot];
+            time = ro.w; tlimit = RT_INF;
+          }
+          o = mk3(ro.x, ro.y, ro.z); dir = mk3(rd.x, rd.y, rd.z);
+          wr = make_ray(o, dir, eps);
+          cr = wr;
+          best.t = RT_INF; best.beta = 0.f; best.gamma = 0.f; best.top_ref = B200RT_REF_NONE;
+          best.top_rank = 0x7fffffff; best.tri = 0x7fffffff;
+          found = false;
+          cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE;
+          sp = 0;
+          cur = B200RT_REF_NONE;
+          has_ray = true;
+          // root: a gate for INNER / INSTANCE, unconditional for primitives
+          const uint32_t rk = B200RT_REF_KIND(S.root);
+          if (rk != B200RT_KIND_NONE) {
+            float e = 0.0f;
+            bool ok = true;
+            if (rk == B200RT_KIND_INNER || rk == B200RT_KIND_INSTANCE)
+              ok = box_gate(cr, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
+                            S.root_box[5], eps, &e);
+            if (ok) { cur = S.root; cur_t = e; }
+          }
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, has_ray)) break;
+
+    // ---- traversal steps until enough lanes went idle ------------------------
+    for (;;) {
+      if (has_ray) {
+        uint32_t ref = cur;
+        float te = cur_t;
+        cur = B200RT_REF_NONE;
+        bool finished = false;
+        if (ref == B200RT_REF_NONE) {
+          if (sp == 0) finished = true;
+          else { sp--; ref = stack[sp]; te = stack_t[sp]; }
+        }
+        if (!finished) {
+          const uint32_t kind = B200RT_REF_KIND(ref);
+          const uint32_t idx = B200RT_REF_INDEX(ref);
+          const float bound = ANY ? tlimit : best.t;
+          if (kind == 14u) {  // leave instance
+            cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE;
+          } else if (te > bound + fabsf(bound) * 1e-4f) {
+            // pruned: cannot contain a closer / in-range hit
+          } else if (kind == B200RT_KIND_FNODE) {
+            tc.nodes++;
+            const float4 n0 = __ldg(S.fast_nodes + 4 * (size_t)idx);
+            const float4 n1 = __ldg(S.fast_nodes + 4 * (size_t)idx + 1);
+            const float4 n2 = __ldg(S.fast_nodes + 4 * (size_t)idx + 2);
+            const float4 n3 = __ldg(S.fast_nodes + 4 * (size_t)idx + 3);
+            float e0, e1;
+            const bool h0 = box_loose(cr, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &e0);
+            const bool h1 = box_loose(cr, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &e1);
+            const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+            if (h0 && h1) {
+              const bool swap = e1 < e0;
+              cur = swap ? c1 : c0; cur_t = swap ? e1 : e0;
+              if (sp < RT_FSTACK) { stack[sp] = swap ? c0 : c1; stack_t[sp] = swap ? e0 : e1; sp++; }
+              else atomicExch(&C->overflow, 2u);
+            } else if (h0) { cur = c0; cur_t = e0; }
+            else if (h1) { cur = c1; cur_t = e1; }
+          } else if (kind >= B200RT_KIND_LEAF1 && kind <= B200RT_KIND_LEAF4) {
+            const int n = (int)(kind - B200RT_KIND_LEAF1) + 1;
+            for (int i = 0; i < n; i++) {
+              const size_t fi = (size_t)idx + i;
+              tc.tris++;
+              const float4 t0 = __ldg(S.fast_tris + 3 * fi);
+              const float4 t1 = __ldg(S.fast_tris + 3 * fi + 1);
+              const float4 t2 = __ldg(S.fast_tris + 3 * fi + 2);
+              float t, be, ga;
+              if (tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), cr.o, cr.d,
+                                     eps, &t, &be, &ga) && t > 0.0f && (ANY ? (t < tlimit) : (t <= best.t))) {
+                const int tri = __ldg(S.fast_tri_ref + fi);
+                if (ANY || better(t, cur_rank, tri, best)) {
+                  // the reference's innermost gate for this triangle
+                  const float2* g = reinterpret_cast<const float2*>(S.tri_gate + 6 * (size_t)tri);
+                  const float2 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+                  float e;
+                  if (box_gate(cr, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, eps, &e)) {
+                    if (ANY) { found = true; finished = true; break; }
+                    best.t = t; best.beta = be; best.gamma = ga; best.top_ref = cur_top; best.top_rank = cur_rank;
+                    best.tri = tri; found = true;
+                  }
+                }
+              }
+            }
+          } else if (kind == B200RT_KIND_INNER) {
+            // top-level node of the reference tree: exact gates, primitives inline
+            tc.nodes++;
+            const float4 n0 = __ldg(S.nodes + 4 * (size_t)idx);
+            const float4 n1 = __ldg(S.nodes + 4 * (size_t)idx + 1);
+            const float4 n2 = __ldg(S.nodes + 4 * (size_t)idx + 2);
+            const float4 n3 = __ldg(S.nodes + 4 * (size_t)idx + 3);
+            const uint32_t child[2] = {__float_as_uint(n3.x), __float_as_uint(n3.y)};
+            float entry[2] = {0.f, 0.f};
+            bool push[2] = {false, false};
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              const uint32_t ck = B200RT_REF_KIND(child[c]);
+              if (ck == B200RT_KIND_INNER || ck == B200RT_KIND_INSTANCE) {
+                if (c == 0) push[0] = box_gate(cr, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &entry[0]);
+                else push[1] = box_gate(cr, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &entry[1]);
+              } else if (ck != B200RT_KIND_NONE) {
+                push[c] = true;  // primitive: tested when popped
+                entry[c] = 0.f;
+              }
+            }
+            if (push[0] && push[1]) {
+              const int far_c = (entry[0] > entry[1]) ? 0 : 1;
+              if (sp + 2 <= RT_FSTACK) {
+                stack[sp] = child[far_c]; stack_t[sp] = entry[far_c]; sp++;
+                stack[sp] = child[1 - far_c]; stack_t[sp] = entry[1 - far_c]; sp++;
+              } else atomicExch(&C->overflow, 2u);
+            } else if (push[0] || push[1]) {
+              const int c = push[0] ? 0 : 1;
+              cur = child[c]; cur_t = entry[c];
+            }
+          } else if (kind == B200RT_KIND_INSTANCE) {
+            // Mesh_instance::intersect — HW3/include/Mesh.h:55-98 (gate already passed)
+            const b200rt_instance* in = S.inst + idx;
+            const b200rt_mesh* m = S.meshes + in->mesh;
+            const uint32_t froot = (m->fast_root != B200RT_REF_NONE) ? m->fast_root : m->root;
+            if (B200RT_REF_KIND(froot) != B200RT_KIND_NONE) {
+              tc.insts++;
+              v3 co = o, cd = dir;
+              if (!(in->flags & B200RT_INST_DIRECT)) {
+                if (in->flags & B200RT_INST_MOVING) {
+                  float inv16[16];
+                  moving_inverse(in->fwd, in->velocity, time, inv16);
+                  co = xf_point(inv16, o); cd = xf_vector4(inv16, dir);
+                } else {
+                  co = xf_point(in->inv, o); cd = xf_vector4(in->inv, dir);
+                }
+              }
+              if (sp + 1 <= RT_FSTACK) {
+                cr = make_ray(co, cd, eps);
+                cur_rank = in->rank; cur_top = ref;
+                stack[sp] = RT_SENTINEL; stack_t[sp] = 0.f; sp++;
+                cur = froot; cur_t = 0.f;
+              } else atomicExch(&C->overflow, 2u);
+            }
+          } else if (kind == B200RT_KIND_TRI) {
+            // a mesh whose BVH is a single triangle (create_bvh size==1): no gate at all
+            tc.tris++;
+            const float4 t0 = __ldg(S.tris + 3 * (size_t)idx);
+            const float4 t1 = __ldg(S.tris + 3 * (size_t)idx + 1);
+            const float4 t2 = __ldg(S.tris + 3 * (size_t)idx + 2);
+            float t, be, ga;
+            if (tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), cr.o, cr.d, eps,
+                                   &t, &be, &ga) && t > 0.0f) {
+              if (ANY) { if (t < tlimit) { found = true; finished = true; } }
+              else if (better(t, cur_rank, (int)idx, best)) {
+                best.t = t; best.beta = be; best.gamma = ga; best.top_ref = cur_top; best.top_rank = cur_rank;
+                best.tri = (int)idx; found = true;
+              }
+            }
+          } else if (kind == B200RT_KIND_SPHERE) {
+            tc.spheres++;
+            const b200rt_sphere* s = S.spheres + idx;
+            float t;
+            if (sphere_test(s, cr.o, cr.d, time, eps, &t) && t > 0.0f) {
+              if (ANY) { if (t < tlimit) { found = true; finished = true; } }
+              else if (better(t, s->rank, -1, best)) {
+                best.t = t; best.beta = 0.f; best.gamma = 0.f; best.top_ref = ref; best.top_rank = s->rank;
+                best.tri = -1; found = true;
+              }
+            }
+          } else if (kind == B200RT_KIND_TRIPRIM) {
+            tc.tris++;
+            const b200rt_triprim* p = S.triprims + idx;
+            v3 lo = cr.o, ldir = cr.d;
+            if (!(p->flags & B200RT_XF_IDENTITY)) { lo = xf_point(p->inv, cr.o); ldir = xf_vector4(p->inv, cr.d); }
+            float t, be, ga;
+            if (tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
+              if (ANY) { if (t < tlimit) { found = true; finished = true; } }
+              else if (better(t, p->rank, -1, best)) {
+                best.t = t; best.beta = be; best.gamma = ga; best.top_ref = ref; best.top_rank = p->rank;
+                best.tri = -1; found = true;
+              }
+            }
+          }
+        }
+        if (finished) {
+          if (ANY) {
+            Q.vis[out_slot] = found ? 0 : 1;
+          } else {
+            P.hit_a[out_slot] = make_float4(found ? best.t : RT_INF, best.beta, best.gamma,
+                                            __uint_as_float(found ? best.top_ref : B200RT_REF_NONE));
+            P.hit_b[out_slot] = make_int2(found ? best.top_rank : -1, found ? best.tri : -1);
+          }
+          has_ray = false;
+        }
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, has_ray);
+      if (act == 0u) break;
+      if (!exhausted && __popc(~act) >= RT_REFILL_MIN_IDLE) break;
+    }
+  }
+  flush_counters(C, tc, ANY);
+}

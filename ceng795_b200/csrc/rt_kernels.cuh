@@ -116,7 +116,9 @@ __device__ __forceinline__ void flush_counters(Counters* C, const TravCounters& 
   }
 }
 
-// ---- extend: closest hit, persistent warps pulling 32-ray batches -----------
+#include "rt_fast.cuh"
+
+// ---- extend (exact mode): closest hit, persistent warps pulling 32-ray batches
 template <bool EXACT, int TRI_MODE>
 __global__ void __launch_bounds__(RT_BLOCK) k_extend(DScene S, Pool P, const WaveInfo* waves, int d, Counters* C) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;

@@ -58,6 +58,9 @@ enum b200rt_semantics {
 #define B200RT_KIND_SPHERE 2u   /* index into spheres[]                        */
 #define B200RT_KIND_TRIPRIM 3u  /* stand-alone Triangle with own transform     */
 #define B200RT_KIND_INSTANCE 4u /* index into instances[]                      */
+#define B200RT_KIND_LEAF1 5u    /* fast-BVH leaf of 1..4 triangles (kinds 5..8):  */
+#define B200RT_KIND_LEAF4 8u    /*   index = first entry in fast_tri_* arrays     */
+#define B200RT_KIND_FNODE 9u    /* index into fast_nodes[]                        */
 #define B200RT_KIND_NONE 15u
 #define B200RT_REF(kind, idx) ((((uint32_t)(kind)) << 28) | ((uint32_t)(idx)))
 #define B200RT_REF_KIND(r) ((r) >> 28)
@@ -83,6 +86,8 @@ typedef struct b200rt_mesh {
   float root_box[6];  /* min xyz, max xyz of the root (gate when INNER)         */
   int32_t tri_begin, tri_count; /* triangles [begin,begin+count) in DFS order  */
   int32_t node_begin, node_count;
+  uint32_t fast_root; /* FNODE / LEAFn ref into the SAH tree the device walks, or NONE */
+  int32_t pad;
 } b200rt_mesh;
 
 #define B200RT_INST_MOVING 1u     /* velocity != 0: per-ray inverse (HW3/include/Mesh.h:76-95) */
@@ -181,6 +186,17 @@ typedef struct B200SceneDesc {
   const float* tri_geom;    /* 12 floats per triangle: v0, a1=v0-v1, a2=v0-v2, face normal */
   const int32_t* tri_vidx;  /* 3 per triangle: indices into vert_* (smooth shading, uv)     */
   const int32_t* tri_info;  /* 2 per triangle: material, flags (bit0 = smooth)             */
+
+  /* Device-oriented SAH BVH over the same triangles (csrc/fast_bvh.h).  A triangle
+   * found through it is admitted only if the reference's innermost gate for it
+   * (tri_gate: the box of the reference BVH node that holds it) passes
+   * Bounding_box::intersect — all outer gates are supersets and pass with it. */
+  int32_t n_fast_nodes;
+  const b200rt_bvh_node* fast_nodes;
+  int32_t n_fast_tris;         /* triangles of meshes with >= 2 triangles        */
+  const float* fast_tri_geom;  /* 12 floats per triangle, leaf order             */
+  const int32_t* fast_tri_ref; /* leaf-order position -> triangle index above    */
+  const float* tri_gate;       /* 6 floats per triangle (DFS order): min, max    */
 
   int32_t n_verts;
   const float* vert_pos;    /* 3 per vertex */

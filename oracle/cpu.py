@@ -38,9 +38,12 @@ def load():
     global _lib
     if _lib is None:
         path = os.path.join(HERE, "liboracle.so")
-        if not os.path.exists(path):
+        try:  # rebuild when oracle.c / b200rt.h changed (struct layout must match)
             from ceng795_b200 import _build
             _build.build_oracle()
+        except Exception:
+            if not os.path.exists(path):
+                raise
         _lib = C.CDLL(path)
         _lib.oracle_render.restype = C.c_int
         _lib.oracle_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p,
