@@ -299,7 +299,7 @@ def run_b200(args):
                 "h2d_bytes_per_step": 176 + 64, "d2h_bytes_per_step": H * W * 16 * (world if split == "cameras" else 1)},
         "gpu_launches": launches_all,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_extend<false,2> (closest-hit traversal)", "achieved": ext_gbs,
+        "roofline": {"bound": "hbm", "kernel": "k_trace_fast<false,2> (closest-hit traversal, SAH tree + reference gate)", "achieved": ext_gbs,
                      "peak": hbm, "peak_source": hbm_src, "unit": "GB/s",
                      "frac": (ext_gbs / hbm) if ext_gbs else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": ext_bytes / n_ext_launch,

@@ -132,7 +132,7 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
               int* waves_run) {
   const DScene& S = sc->S;
   cudaStream_t st = sc->stream;
-  const int grid_p = sc->sm_count * 8;  // persistent traversal grid: 8 CTAs of 128 threads per SM
+  const int grid_p = sc->sm_count * (RT_FAST_MIN_BLOCKS > 8 ? RT_FAST_MIN_BLOCKS : 8);  // persistent traversal grid: resident CTAs of 128 threads per SM
   const int grid_s = sc->sm_count * 8;
   const bool hw1 = S.semantics == B200RT_SEM_HW1;
   const int max_d = primary_only ? 0 : S.max_depth;
@@ -235,6 +235,7 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
   const size_t max_paths = (size_t)16 << 20;  // 16 Mi camera paths per batch
   size_t rows_per_batch = max_paths / (paths_per_row ? paths_per_row : 1);
   if (rows_per_batch < 1) rows_per_batch = 1;
+  if (rows_per_batch >= 4) rows_per_batch &= ~(size_t)3;  // keeps k_generate's 8x4 tiling available
   if (rows_per_batch > (size_t)R.n_rows) rows_per_batch = R.n_rows;
   const size_t batch_paths = rows_per_batch * paths_per_row;
   size_t slots = batch_paths * growth + 1024;

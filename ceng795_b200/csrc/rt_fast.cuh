@@ -19,19 +19,44 @@
 #include "rt_traverse.cuh"
 
 #define RT_FSTACK 64
-#define RT_REFILL_MIN_IDLE 8  // refill the warp when at least this many lanes are idle
+#ifndef RT_REFILL_MIN_IDLE
+#define RT_REFILL_MIN_IDLE 32  // lanes idle before the warp refills: 32 = whole-warp batches (measured fastest, profiles/r01b)
+#endif
+#ifndef RT_FAST_MIN_BLOCKS
+#define RT_FAST_MIN_BLOCKS 8  // resident CTAs per SM the register budget is held to (64 regs; measured sweet spot, profiles/r01b)
+#endif
+
+// Ray in the space being traversed, with the constants of the two box tests.
+struct FastRay {
+  v3 o, d, inv, oi;  // oi = o * inv (for the fused loose test)
+  bool slow;         // some |d_i| < eps: the reference skips that axis; take the generic path
+};
+__device__ __forceinline__ FastRay make_fast_ray(v3 o, v3 d, float eps) {
+  FastRay r;
+  r.o = o; r.d = d;
+  r.slow = (fabsf(d.x) < eps) || (fabsf(d.y) < eps) || (fabsf(d.z) < eps);
+  r.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  r.oi = mk3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
+  return r;
+}
+__device__ __forceinline__ RayCtx as_ctx(const FastRay& r) {
+  RayCtx c;
+  c.o = r.o; c.d = r.d; c.inv = r.inv; c.slow = r.slow;
+  return c;
+}
 
 // Conservative slab test for SAH boxes (grown on the host): may accept a box
-// the exact test would reject, never the reverse by more than the growth.
-__device__ __forceinline__ bool box_loose(const RayCtx& r, float mnx, float mny, float mnz, float mxx, float mxy,
+// the exact test would reject, never the reverse by more than the growth.  Not
+// an accept/reject decision of the reference, so FMA is allowed here.
+__device__ __forceinline__ bool box_loose(const FastRay& r, float mnx, float mny, float mnz, float mxx, float mxy,
                                           float mxz, float eps, float* entry) {
   if (!r.slow) {
-    const float ax = (mnx - r.o.x) * r.inv.x, bx = (mxx - r.o.x) * r.inv.x;
-    const float ay = (mny - r.o.y) * r.inv.y, by = (mxy - r.o.y) * r.inv.y;
-    const float az = (mnz - r.o.z) * r.inv.z, bz = (mxz - r.o.z) * r.inv.z;
+    const float ax = __fmaf_rn(mnx, r.inv.x, -r.oi.x), bx = __fmaf_rn(mxx, r.inv.x, -r.oi.x);
+    const float ay = __fmaf_rn(mny, r.inv.y, -r.oi.y), by = __fmaf_rn(mxy, r.inv.y, -r.oi.y);
+    const float az = __fmaf_rn(mnz, r.inv.z, -r.oi.z), bz = __fmaf_rn(mxz, r.inv.z, -r.oi.z);
     const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
     const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-    const float tfa = tf + 2e-6f * fmaxf(fabsf(tn), fabsf(tf));
+    const float tfa = __fmaf_rn(2e-6f, fmaxf(fabsf(tn), fabsf(tf)), tf);
     *entry = fmaxf(tn, 0.0f);
     return tn <= tfa && tfa >= 0.0f;
   }
@@ -41,8 +66,9 @@ __device__ __forceinline__ bool box_loose(const RayCtx& r, float mnx, float mny,
 }
 
 template <bool ANY, int TRI_MODE>
-__global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves,
-                                                         int d, Counters* C) {
+__global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DScene S, Pool P, ShadowQueue Q,
+                                                                             const WaveInfo* waves, int d,
+                                                                             Counters* C) {
   const uint32_t begin = ANY ? 0u : waves[d].begin;
   const uint32_t count = ANY ? C->shadow_count : waves[d].count;
   unsigned int* cursor = ANY ? &C->work_shadow : &C->work_extend;
@@ -54,12 +80,10 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
   float stack_t[RT_FSTACK];
   int sp = 0;
   bool has_ray = false, exhausted = false;
-  uint32_t out_slot = 0;
-  v3 o = mk3(0, 0, 0), dir = mk3(0, 0, 0);
+  uint32_t out_slot = 0, src = 0;
   float time = 0.f, tlimit = RT_INF;
-  RayCtx wr, cr;
-  wr.o = o; wr.d = dir; wr.inv = dir; wr.slow = false;
-  cr = wr;
+  FastRay cr;
+  cr.o = mk3(0, 0, 0); cr.d = cr.o; cr.inv = cr.o; cr.oi = cr.o; cr.slow = false;
   HitRec best;
   best.t = RT_INF; best.beta = 0.f; best.gamma = 0.f; best.top_ref = B200RT_REF_NONE; best.top_rank = 0x7fffffff;
   best.tri = 0x7fffffff;
@@ -68,6 +92,13 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
   uint32_t cur_top = B200RT_REF_NONE;
   uint32_t cur = B200RT_REF_NONE;  // node to process next without going through the stack
   float cur_t = 0.f;
+
+  // the world-space ray lives in the queue; it is re-read on the (rare) instance switches
+  auto world_ray = [&](v3* o, v3* dir) {
+    const float4 ro = ANY ? Q.o[src] : P.ray_o[src];
+    const float4 rd = ANY ? Q.d[src] : P.ray_d[src];
+    *o = mk3(ro.x, ro.y, ro.z); *dir = mk3(rd.x, rd.y, rd.z);
+  };
 
   for (;;) {
     // ---- refill idle lanes from the wave's work cursor ----------------------
@@ -83,17 +114,16 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
         if (k < count) {
           float4 ro, rd;
           if (ANY) {
+            src = k;
             ro = Q.o[k]; rd = Q.d[k];
             time = Q.time[k]; tlimit = ro.w;
             out_slot = __float_as_uint(rd.w);
           } else {
-            out_slot = begin + k;
+            out_slot = begin + k; src = out_slot;
             ro = P.ray_o[out_slot]; rd = P.ray_d[out_slot];
             time = ro.w; tlimit = RT_INF;
           }
-          o = mk3(ro.x, ro.y, ro.z); dir = mk3(rd.x, rd.y, rd.z);
-          wr = make_ray(o, dir, eps);
-          cr = wr;
+          cr = make_fast_ray(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), eps);
           best.t = RT_INF; best.beta = 0.f; best.gamma = 0.f; best.top_ref = B200RT_REF_NONE;
           best.top_rank = 0x7fffffff; best.tri = 0x7fffffff;
           found = false;
@@ -107,7 +137,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
             float e = 0.0f;
             bool ok = true;
             if (rk == B200RT_KIND_INNER || rk == B200RT_KIND_INSTANCE)
-              ok = box_gate(cr, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
+              ok = box_gate(as_ctx(cr), S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
                             S.root_box[5], eps, &e);
             if (ok) { cur = S.root; cur_t = e; }
           }
@@ -116,42 +146,53 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
     }
     if (!__any_sync(0xffffffffu, has_ray)) break;
 
-    // ---- traversal steps until enough lanes went idle ------------------------
     for (;;) {
       if (has_ray) {
-        uint32_t ref = cur;
-        float te = cur_t;
-        cur = B200RT_REF_NONE;
         bool finished = false;
-        if (ref == B200RT_REF_NONE) {
-          if (sp == 0) finished = true;
-          else { sp--; ref = stack[sp]; te = stack_t[sp]; }
+        // ---- phase 1: inner nodes of the SAH tree until this lane holds something else
+        for (;;) {
+          if (cur == B200RT_REF_NONE) {
+            if (sp == 0) { finished = true; break; }
+            sp--; cur = stack[sp]; cur_t = stack_t[sp];
+          }
+          if (B200RT_REF_KIND(cur) != B200RT_KIND_FNODE) break;
+          const float bound = ANY ? tlimit : best.t;
+          const uint32_t idx = B200RT_REF_INDEX(cur);
+          const float te = cur_t;
+          cur = B200RT_REF_NONE;
+          if (te > bound + fabsf(bound) * 1e-4f) continue;  // pruned
+          tc.nodes++;
+          const float4 n0 = __ldg(S.fast_nodes + 4 * (size_t)idx);
+          const float4 n1 = __ldg(S.fast_nodes + 4 * (size_t)idx + 1);
+          const float4 n2 = __ldg(S.fast_nodes + 4 * (size_t)idx + 2);
+          const float4 n3 = __ldg(S.fast_nodes + 4 * (size_t)idx + 3);
+          float e0, e1;
+          const bool h0 = box_loose(cr, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &e0);
+          const bool h1 = box_loose(cr, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &e1);
+          const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+          if (h0 && h1) {
+            const bool swap = e1 < e0;
+            cur = swap ? c1 : c0; cur_t = swap ? e1 : e0;
+            if (sp < RT_FSTACK) { stack[sp] = swap ? c0 : c1; stack_t[sp] = swap ? e0 : e1; sp++; }
+            else atomicExch(&C->overflow, 2u);
+          } else if (h0) { cur = c0; cur_t = e0; }
+          else if (h1) { cur = c1; cur_t = e1; }
         }
+        // ---- phase 2: leaf / instance / top-level node / primitive
         if (!finished) {
+          const uint32_t ref = cur;
+          const float te = cur_t;
+          cur = B200RT_REF_NONE;
           const uint32_t kind = B200RT_REF_KIND(ref);
           const uint32_t idx = B200RT_REF_INDEX(ref);
           const float bound = ANY ? tlimit : best.t;
           if (kind == 14u) {  // leave instance
-            cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE;
+            v3 o, dir;
+            world_ray(&o, &dir);
+            cr = make_fast_ray(o, dir, eps);
+            cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE;
           } else if (te > bound + fabsf(bound) * 1e-4f) {
             // pruned: cannot contain a closer / in-range hit
-          } else if (kind == B200RT_KIND_FNODE) {
-            tc.nodes++;
-            const float4 n0 = __ldg(S.fast_nodes + 4 * (size_t)idx);
-            const float4 n1 = __ldg(S.fast_nodes + 4 * (size_t)idx + 1);
-            const float4 n2 = __ldg(S.fast_nodes + 4 * (size_t)idx + 2);
-            const float4 n3 = __ldg(S.fast_nodes + 4 * (size_t)idx + 3);
-            float e0, e1;
-            const bool h0 = box_loose(cr, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &e0);
-            const bool h1 = box_loose(cr, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &e1);
-            const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
-            if (h0 && h1) {
-              const bool swap = e1 < e0;
-              cur = swap ? c1 : c0; cur_t = swap ? e1 : e0;
-              if (sp < RT_FSTACK) { stack[sp] = swap ? c0 : c1; stack_t[sp] = swap ? e0 : e1; sp++; }
-              else atomicExch(&C->overflow, 2u);
-            } else if (h0) { cur = c0; cur_t = e0; }
-            else if (h1) { cur = c1; cur_t = e1; }
           } else if (kind >= B200RT_KIND_LEAF1 && kind <= B200RT_KIND_LEAF4) {
             const int n = (int)(kind - B200RT_KIND_LEAF1) + 1;
             for (int i = 0; i < n; i++) {
@@ -169,7 +210,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
                   const float2* g = reinterpret_cast<const float2*>(S.tri_gate + 6 * (size_t)tri);
                   const float2 g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2);
                   float e;
-                  if (box_gate(cr, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, eps, &e)) {
+                  if (box_gate(as_ctx(cr), g0.x, g0.y, g1.x, g1.y, g2.x, g2.y, eps, &e)) {
                     if (ANY) { found = true; finished = true; break; }
                     best.t = t; best.beta = be; best.gamma = ga; best.top_ref = cur_top; best.top_rank = cur_rank;
                     best.tri = tri; found = true;
@@ -178,7 +219,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
               }
             }
           } else if (kind == B200RT_KIND_INNER) {
-            // top-level node of the reference tree: exact gates, primitives inline
+            // top-level node of the reference tree: exact gates; primitives are tested when popped
             tc.nodes++;
             const float4 n0 = __ldg(S.nodes + 4 * (size_t)idx);
             const float4 n1 = __ldg(S.nodes + 4 * (size_t)idx + 1);
@@ -187,23 +228,23 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
             const uint32_t child[2] = {__float_as_uint(n3.x), __float_as_uint(n3.y)};
             float entry[2] = {0.f, 0.f};
             bool push[2] = {false, false};
+            const RayCtx rc = as_ctx(cr);
 #pragma unroll
             for (int c = 0; c < 2; c++) {
               const uint32_t ck = B200RT_REF_KIND(child[c]);
               if (ck == B200RT_KIND_INNER || ck == B200RT_KIND_INSTANCE) {
-                if (c == 0) push[0] = box_gate(cr, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &entry[0]);
-                else push[1] = box_gate(cr, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &entry[1]);
+                if (c == 0) push[0] = box_gate(rc, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &entry[0]);
+                else push[1] = box_gate(rc, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &entry[1]);
               } else if (ck != B200RT_KIND_NONE) {
-                push[c] = true;  // primitive: tested when popped
+                push[c] = true;
                 entry[c] = 0.f;
               }
             }
             if (push[0] && push[1]) {
               const int far_c = (entry[0] > entry[1]) ? 0 : 1;
-              if (sp + 2 <= RT_FSTACK) {
-                stack[sp] = child[far_c]; stack_t[sp] = entry[far_c]; sp++;
-                stack[sp] = child[1 - far_c]; stack_t[sp] = entry[1 - far_c]; sp++;
-              } else atomicExch(&C->overflow, 2u);
+              cur = child[1 - far_c]; cur_t = entry[1 - far_c];
+              if (sp < RT_FSTACK) { stack[sp] = child[far_c]; stack_t[sp] = entry[far_c]; sp++; }
+              else atomicExch(&C->overflow, 2u);
             } else if (push[0] || push[1]) {
               const int c = push[0] ? 0 : 1;
               cur = child[c]; cur_t = entry[c];
@@ -215,6 +256,8 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
             const uint32_t froot = (m->fast_root != B200RT_REF_NONE) ? m->fast_root : m->root;
             if (B200RT_REF_KIND(froot) != B200RT_KIND_NONE) {
               tc.insts++;
+              v3 o, dir;
+              world_ray(&o, &dir);
               v3 co = o, cd = dir;
               if (!(in->flags & B200RT_INST_DIRECT)) {
                 if (in->flags & B200RT_INST_MOVING) {
@@ -225,8 +268,8 @@ __global__ void __launch_bounds__(RT_BLOCK) k_trace_fast(DScene S, Pool P, Shado
                   co = xf_point(in->inv, o); cd = xf_vector4(in->inv, dir);
                 }
               }
-              if (sp + 1 <= RT_FSTACK) {
-                cr = make_ray(co, cd, eps);
+              if (sp < RT_FSTACK) {
+                cr = make_fast_ray(co, cd, eps);
                 cur_rank = in->rank; cur_top = ref;
                 stack[sp] = RT_SENTINEL; stack_t[sp] = 0.f; sp++;
                 cur = froot; cur_t = 0.f;

@@ -60,11 +60,20 @@ __global__ void k_generate(DScene S, Pool P, RenderParams R, WaveInfo* waves, Co
   const uint32_t stride = gridDim.x * blockDim.x;
   const int W = S.cam.width;
   const int ns = S.cam.samples_sqrt;
+  const bool tiled = (W % 8 == 0) && (R.n_rows % 4 == 0);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < R.n_paths; k += stride) {
     const uint32_t pl = k / (uint32_t)R.sample_count;
     const uint32_t sidx = R.sample_begin + (k - pl * (uint32_t)R.sample_count);
-    const int row = R.row_begin + (int)(pl / (uint32_t)W) * R.row_stride;
-    const int col = (int)(pl % (uint32_t)W);
+    uint32_t rowi = pl / (uint32_t)W, coli = pl % (uint32_t)W;
+    if (tiled) {
+      // 8x4 pixel tiles: the 32 rays of a warp start out spatially coherent
+      const uint32_t tile = pl >> 5, in = pl & 31u;
+      const uint32_t tiles_per_row = (uint32_t)W >> 3;
+      rowi = (tile / tiles_per_row) * 4u + (in >> 3);
+      coli = (tile % tiles_per_row) * 8u + (in & 7u);
+    }
+    const int row = R.row_begin + (int)rowi * R.row_stride;
+    const int col = (int)coli;
     const uint32_t pix = (uint32_t)row * (uint32_t)W + (uint32_t)col;
     const uint32_t key = rng_mix(rng_mix(R.seed_key, pix), ns == 1 ? 0u : sidx);
     v3 o, d;
