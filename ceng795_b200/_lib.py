@@ -19,9 +19,14 @@ SEM_BY_NAME = {"hw1": SEM_HW1, "hw2": SEM_HW2, "hw3": SEM_HW3, "hw4": SEM_HW4, "
                "hw6": SEM_HW6, "hw7": SEM_HW7, "ppm": SEM_PPM}
 
 KIND_INNER, KIND_TRI, KIND_SPHERE, KIND_TRIPRIM, KIND_INSTANCE, KIND_NONE = 0, 1, 2, 3, 4, 15
-KIND_LEAF1, KIND_LEAF4, KIND_FNODE = 5, 8, 9
+KIND_LEAF1, KIND_LEAF4, KIND_FNODE, KIND_LIGHTINST = 5, 8, 9, 10
 
 LIGHT_POINT, LIGHT_AREA, LIGHT_SPOT, LIGHT_DIRECTIONAL, LIGHT_ENV, LIGHT_MESH, LIGHT_SPHERE = range(7)
+TEX_IMAGE, TEX_PERLIN = 0, 1
+TEX_NEAREST, TEX_BILINEAR = 0, 1
+TEX_REPLACE_KD, TEX_BLEND_KD, TEX_REPLACE_ALL = 0, 1, 2
+TEX_REPEAT, TEX_CLAMP, TEX_VEIN, TEX_PATCH = 0, 1, 2, 3
+BRDF_PHONG, BRDF_MODIFIED_PHONG, BRDF_BLINN_PHONG, BRDF_MODIFIED_BLINN_PHONG, BRDF_TORRANCE_SPARROW = range(5)
 
 
 class BvhNode(C.Structure):
@@ -37,13 +42,13 @@ class Mesh(C.Structure):
 class Instance(C.Structure):
     _fields_ = [("inv", c_f * 12), ("nrm", c_f * 9), ("fwd", c_f * 16), ("box", c_f * 6),
                 ("velocity", c_f * 3), ("mesh", c_i), ("material", c_i), ("texture", c_i),
-                ("flags", c_u), ("rank", c_i), ("pad", c_i * 3)]
+                ("flags", c_u), ("rank", c_i), ("light", c_i), ("pad", c_i * 2)]
 
 
 class Sphere(C.Structure):
     _fields_ = [("center", c_f * 3), ("radius", c_f), ("inv", c_f * 12), ("nrm", c_f * 9),
                 ("fwd", c_f * 16), ("velocity", c_f * 3), ("material", c_i), ("texture", c_i),
-                ("flags", c_u), ("rank", c_i), ("pad", c_i * 2)]
+                ("flags", c_u), ("rank", c_i), ("light", c_i), ("pad", c_i)]
 
 
 class TriPrim(C.Structure):
@@ -59,7 +64,18 @@ class Material(C.Structure):
 
 class Light(C.Structure):
     _fields_ = [("kind", c_i), ("position", c_f * 3), ("intensity", c_f * 3), ("edge1", c_f * 3),
-                ("edge2", c_f * 3), ("normal", c_f * 3), ("object", c_i), ("pad", c_f * 4)]
+                ("edge2", c_f * 3), ("normal", c_f * 3), ("object", c_i), ("cdf_begin", c_i),
+                ("cdf_count", c_i), ("total_area", c_f), ("pad", c_f)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("kind", c_i), ("interp", c_i), ("decal", c_i), ("appearance", c_i), ("normalizer", c_f),
+                ("scaling", c_f), ("bump_multiplier", c_f), ("is_bump", c_i), ("width", c_i), ("height", c_i),
+                ("texel_offset", C.c_int64), ("perm", c_i * 16)]
+
+
+class Brdf(C.Structure):
+    _fields_ = [("kind", c_i), ("exponent", c_f), ("normalized", c_i), ("refractive_index", c_f)]
 
 
 class Camera(C.Structure):
@@ -73,7 +89,8 @@ class Camera(C.Structure):
 class CameraIn(C.Structure):
     _fields_ = [("position", c_f * 3), ("gaze", c_f * 3), ("up", c_f * 3), ("near_plane", c_f * 4),
                 ("near_distance", c_f), ("width", c_i), ("height", c_i), ("num_samples", c_i),
-                ("focus_distance", c_f), ("aperture_size", c_f)]
+                ("focus_distance", c_f), ("aperture_size", c_f), ("left_handed", c_i), ("simple", c_i),
+                ("fov_y", c_f)]
 
 
 class SceneDesc(C.Structure):
@@ -94,6 +111,12 @@ class SceneDesc(C.Structure):
         ("n_materials", c_i), ("materials", C.POINTER(Material)),
         ("n_lights", c_i), ("lights", C.POINTER(Light)),
         ("n_cameras", c_i), ("cameras", C.POINTER(Camera)),
+        ("tri_uv", C.POINTER(c_f)), ("tri_tex", C.POINTER(c_i)),
+        ("n_textures", c_i), ("textures", C.POINTER(Texture)),
+        ("n_texels", C.c_int64), ("texels", C.POINTER(c_f)),
+        ("n_brdfs", c_i), ("brdfs", C.POINTER(Brdf)),
+        ("n_light_cdf", c_i), ("light_cdf", C.POINTER(c_f)), ("light_tri", C.POINTER(c_i)),
+        ("background_texture", c_i), ("env_light", c_i), ("integrator", c_i), ("importance_sampling", c_i),
     ]
 
 
@@ -166,6 +189,15 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_builder_add_instance": (C.c_int, [C.c_void_p, C.c_int, C.c_int, fp, fp]),
         "b200rt_builder_add_triangle": (C.c_int, [C.c_void_p, C.c_int, P(c_i), fp]),
         "b200rt_builder_add_sphere": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f, fp, fp]),
+        "b200rt_builder_set_texcoords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+        "b200rt_builder_add_texture": (C.c_int, [C.c_void_p, P(Texture), C.c_void_p]),
+        "b200rt_builder_add_brdf": (C.c_int, [C.c_void_p, P(Brdf)]),
+        "b200rt_builder_set_mesh_texture": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+        "b200rt_builder_set_sphere_texture": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+        "b200rt_builder_add_light_mesh": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, fp, fp]),
+        "b200rt_builder_add_light_sphere": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f, fp, fp]),
+        "b200rt_builder_set_integrator": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+        "b200rt_builder_set_background_texture": (C.c_int, [C.c_void_p, C.c_int]),
         "b200rt_builder_finish": (C.c_int, [C.c_void_p, P(P(SceneDesc))]),
         "b200rt_device_count": (C.c_int, []),
         "b200rt_scene_create": (C.c_int, [P(SceneDesc), C.c_int, P(C.c_void_p)]),
@@ -175,6 +207,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_primary_ids": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), C.c_void_p, C.c_void_p]),
         "b200rt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_void_p, P(RenderStats)]),
+        "b200rt_debug_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
         "b200rt_scene_stream": (C.c_void_p, [C.c_void_p]),
         "b200rt_scene_bytes": (C.c_uint64, [C.c_void_p]),
         "b200rt_last_error": (C.c_char_p, []),

@@ -5,7 +5,7 @@
 #include <string>
 #include <vector>
 
-#include "rt_kernels.cuh"
+#include "rt_shade7.cuh"
 
 extern "C" void b200rt_internal_set_error(const char* msg);
 
@@ -40,7 +40,7 @@ struct b200rt_scene {
   int device;
   DScene S;                    // device pointers (camera filled per render)
   std::vector<b200rt_camera> cameras;
-  bool has_transparency;
+  bool has_transparency, has_mirror;
   int sm_count;
   // device allocations owned by the scene
   std::vector<void*> allocs;
@@ -67,7 +67,7 @@ int pool_alloc(b200rt_scene* sc, T** p, size_t n) {
 void pool_free(b200rt_scene* sc) {
   Pool& P = sc->P;
   void* ptrs[] = {P.ray_o, P.ray_d, P.key, P.pixel, P.sample, P.hit_a, P.hit_b, P.nrm, P.rec0, P.rec1, P.rec2,
-                  P.rec3, P.final_c, sc->Q.o, sc->Q.d, sc->Q.time, sc->Q.vis};
+                  P.rec3, P.final_c, P.kd, P.rec4, sc->Q.o, sc->Q.d, sc->Q.time, sc->Q.vis};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   memset(&sc->P, 0, sizeof(Pool));
@@ -83,6 +83,7 @@ int ensure_pool(b200rt_scene* sc, size_t slots, size_t shadow_slots) {
   PA(P.ray_o, slots); PA(P.ray_d, slots); PA(P.key, slots); PA(P.pixel, slots); PA(P.sample, slots);
   PA(P.hit_a, slots); PA(P.hit_b, slots); PA(P.nrm, slots); PA(P.rec0, slots); PA(P.rec1, slots);
   PA(P.rec2, slots); PA(P.rec3, slots); PA(P.final_c, slots);
+  if (sc->S.semantics >= B200RT_SEM_HW4) { PA(P.kd, slots); PA(P.rec4, slots); }
   P.capacity = (uint32_t)slots;
   ShadowQueue& Q = sc->Q;
   PA(Q.o, shadow_slots); PA(Q.d, shadow_slots); PA(Q.time, shadow_slots);
@@ -153,7 +154,9 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     tm.mark(ST_EXTEND);
     d_last = d;
     if (!with_shading) break;
-    k_shade_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    const bool hw7 = S.semantics >= B200RT_SEM_HW7;
+    if (hw7) k_shade7_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    else k_shade_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     k_clamp_shadow_count<<<1, 1, 0, st>>>(sc->Q, sc->d_counters);
     (*launches) += 2;
     tm.mark(ST_SHADE);
@@ -168,14 +171,16 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     }
     (*launches)++;
     tm.mark(ST_SHADOW);
-    k_shade_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    if (hw7) k_shade7_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    else k_shade_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     k_finish_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->P, sc->d_counters);
     (*launches) += 2;
     tm.mark(ST_SHADE);
   }
   if (with_shading) {
     for (int d = d_last; d >= 0; d--) {
-      k_combine<<<grid_s, 256, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_accum);
+      if (S.semantics >= B200RT_SEM_HW7) k_combine7<<<grid_s, 256, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_accum);
+      else k_combine<<<grid_s, 256, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_accum);
       (*launches)++;
     }
     tm.mark(ST_SHADE);
@@ -226,54 +231,73 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
   int rc = ensure_accum(sc, pixels);
   if (rc) return rc;
   cudaStream_t st = sc->stream;
-  CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), st));
-  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
 
-  // batches of pixel rows so that the vertex pool stays bounded
+  // batches of pixel rows so that the vertex pool stays bounded.  The recursion is a TREE
+  // (mirror + two dielectric children + the path tracer's hemisphere sample), so the pool is
+  // sized from an estimate and, if a batch overflows it, the frame is redone with half the rows
+  // per batch (same pool: twice the slots per camera path).
   const size_t paths_per_row = (size_t)c.width * R.sample_count;
-  const size_t growth = (size_t)(sc->S.max_depth + 1) * (sc->has_transparency ? 3 : 1);
+  const size_t fan = (sc->has_mirror ? 1 : 0) + (sc->has_transparency ? 2 : 0) + (sc->S.integrator ? 1 : 0);
+  const size_t growth = 1 + (size_t)sc->S.max_depth * (fan > 1 ? fan : 1);
   const size_t max_paths = (size_t)16 << 20;  // 16 Mi camera paths per batch
   size_t rows_per_batch = max_paths / (paths_per_row ? paths_per_row : 1);
   if (rows_per_batch < 1) rows_per_batch = 1;
   if (rows_per_batch >= 4) rows_per_batch &= ~(size_t)3;  // keeps k_generate's 8x4 tiling available
   if (rows_per_batch > (size_t)R.n_rows) rows_per_batch = R.n_rows;
-  const size_t batch_paths = rows_per_batch * paths_per_row;
-  size_t slots = batch_paths * growth + 1024;
-  if (slots > 0xF0000000ull / (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1)) {
-    b200rt_internal_set_error("vertex pool too large for 32-bit slots");
-    return B200RT_E_UNSUPPORTED;
+  const size_t nl = (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1);
+  {
+    const size_t batch_paths = rows_per_batch * paths_per_row;
+    size_t slots = batch_paths * growth + 1024;
+    const size_t cap = 0xF0000000ull / nl;
+    if (slots > cap) slots = cap;
+    if (slots < batch_paths + 1024) {
+      b200rt_internal_set_error("vertex pool too large for 32-bit slots");
+      return B200RT_E_UNSUPPORTED;
+    }
+    const size_t per_wave = batch_paths * (fan > 1 ? 2 * fan : 1);
+    rc = ensure_pool(sc, slots, per_wave * nl + 1024);
+    if (rc) return rc;
   }
-  const size_t per_wave = batch_paths * (sc->has_transparency ? 9 : 1);
-  rc = ensure_pool(sc, slots, per_wave * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1) + 1024);
-  if (rc) return rc;
 
   Timers tm;
   tm.s = st; tm.on = stats != nullptr;
   int launches = 0, waves_total = 0;
-  cudaEventRecord(sc->ev[0], st);
-  tm.mark(ST_GENERATE);
-  for (int r0 = 0; r0 < R.n_rows; r0 += (int)rows_per_batch) {
-    RenderParams B = R;
-    const int nr = (int)((size_t)(R.n_rows - r0) < rows_per_batch ? (R.n_rows - r0) : rows_per_batch);
-    B.row_begin = R.row_begin + r0 * R.row_stride;
-    B.n_rows = nr;
-    B.n_paths = (uint32_t)((size_t)nr * paths_per_row);
-    k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, B, sc->d_waves, sc->d_counters);
-    launches++;
-    tm.mark(ST_GENERATE);
-    int wr = 0;
-    rc = run_waves(sc, exact, false, true, tm, &launches, &wr);
-    if (rc) return rc;
-    waves_total += wr;
-  }
-  cudaEventRecord(sc->ev[1], st);
-  CK(cudaStreamSynchronize(st));
   Counters hc;
-  CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
-  if (hc.overflow) {
-    b200rt_internal_set_error(hc.overflow == 2 ? "traversal stack overflow (BVH deeper than RT_FSTACK)"
-                                               : "vertex pool / shadow queue overflow (recursion tree larger than the pool)");
-    return B200RT_E_UNSUPPORTED;
+  for (int attempt = 0;; attempt++) {
+    CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), st));
+    CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
+    launches = 0; waves_total = 0;
+    if (tm.on) { float dummy[ST_COUNT]; tm.collect(dummy); }
+    cudaEventRecord(sc->ev[0], st);
+    tm.mark(ST_GENERATE);
+    for (int r0 = 0; r0 < R.n_rows; r0 += (int)rows_per_batch) {
+      RenderParams B = R;
+      const int nr = (int)((size_t)(R.n_rows - r0) < rows_per_batch ? (R.n_rows - r0) : rows_per_batch);
+      B.row_begin = R.row_begin + r0 * R.row_stride;
+      B.n_rows = nr;
+      B.n_paths = (uint32_t)((size_t)nr * paths_per_row);
+      k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, B, sc->d_waves, sc->d_counters);
+      launches++;
+      tm.mark(ST_GENERATE);
+      int wr = 0;
+      rc = run_waves(sc, exact, false, true, tm, &launches, &wr);
+      if (rc) return rc;
+      waves_total += wr;
+    }
+    cudaEventRecord(sc->ev[1], st);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
+    if (!hc.overflow) break;
+    if (hc.overflow == 2) {
+      b200rt_internal_set_error("traversal stack overflow (BVH deeper than RT_FSTACK)");
+      return B200RT_E_UNSUPPORTED;
+    }
+    if (rows_per_batch <= 1 || attempt >= 8) {
+      b200rt_internal_set_error("vertex pool / shadow queue overflow (recursion tree larger than the pool)");
+      return B200RT_E_UNSUPPORTED;
+    }
+    rows_per_batch = (rows_per_batch + 1) / 2;
+    if (rows_per_batch >= 4) rows_per_batch &= ~(size_t)3;
   }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -320,7 +344,8 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     b200rt_internal_set_error("b200rt_scene_create: bad device index");
     return B200RT_E_INVALID;
   }
-  if (d->semantics != B200RT_SEM_HW1 && d->semantics != B200RT_SEM_HW2 && d->semantics != B200RT_SEM_HW3) {
+  if (d->semantics != B200RT_SEM_HW1 && d->semantics != B200RT_SEM_HW2 && d->semantics != B200RT_SEM_HW3 &&
+      d->semantics != B200RT_SEM_HW7) {
     b200rt_internal_set_error("b200rt_scene_create: semantics not implemented on the device yet");
     return B200RT_E_UNSUPPORTED;
   }
@@ -382,13 +407,26 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   UP(S.triprims, d->triprims, d->n_triprims, b200rt_triprim);
   UP(S.mats, d->materials, d->n_materials, b200rt_material);
   UP(S.lights, d->lights, d->n_lights, b200rt_light);
+  UP(S.vert_pos, d->vert_pos, (size_t)d->n_verts * 3, float);
+  UP(S.tri_uv, d->tri_uv, (size_t)d->n_tris * 6, float);
+  UP(S.tri_tex, d->tri_tex, (size_t)d->n_tris, int32_t);
+  UP(S.textures, d->textures, d->n_textures, b200rt_texture);
+  UP(S.texels, d->texels, (size_t)d->n_texels, float);
+  UP(S.brdfs, d->brdfs, d->n_brdfs, b200rt_brdf);
+  UP(S.light_cdf, d->light_cdf, d->n_light_cdf, float);
+  UP(S.light_tri, d->light_tri, d->n_light_cdf, int32_t);
+  S.background_texture = d->background_texture; S.env_light = d->env_light;
+  S.integrator = d->integrator; S.importance_sampling = d->importance_sampling;
 #undef UP
   sc->scene_bytes = bytes;
   sc->cameras.assign(d->cameras, d->cameras + d->n_cameras);
   sc->has_transparency = false;
+  sc->has_mirror = false;
   for (int i = 0; i < d->n_materials; i++) {
     const float* t = d->materials[i].transparency;
     if (t[0] != 0.f || t[1] != 0.f || t[2] != 0.f) sc->has_transparency = true;
+    const float* mr = d->materials[i].mirror;
+    if (mr[0] != 0.f || mr[1] != 0.f || mr[2] != 0.f) sc->has_mirror = true;
   }
   CK(cudaMalloc((void**)&sc->d_waves, sizeof(WaveInfo) * kMaxWaves));
   CK(cudaMalloc((void**)&sc->d_counters, sizeof(Counters)));
@@ -413,6 +451,18 @@ void b200rt_scene_destroy(b200rt_scene* sc) {
   if (sc->ev[0]) cudaEventDestroy(sc->ev[0]);
   if (sc->ev[1]) cudaEventDestroy(sc->ev[1]);
   delete sc;
+}
+
+int b200rt_debug_pool(b200rt_scene* sc, int field, void* out, int64_t count) {
+  if (!sc || !out || count < 0 || (uint64_t)count > sc->P.capacity) return B200RT_E_INVALID;
+  const Pool& P = sc->P;
+  const void* src[] = {P.ray_o, P.ray_d, P.hit_a, P.nrm, P.rec0, P.rec1, P.rec2, P.rec4, P.final_c, P.kd,
+                       P.pixel, P.key, P.hit_b, P.rec3};
+  const size_t esz[] = {16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 4, 4, 8, 4};
+  if (field < 0 || field >= 14 || !src[field]) return B200RT_E_INVALID;
+  CK(cudaSetDevice(sc->device));
+  CK(cudaMemcpy(out, src[field], esz[field] * (size_t)count, cudaMemcpyDeviceToHost));
+  return B200RT_OK;
 }
 
 void* b200rt_scene_stream(b200rt_scene* sc) { return sc ? (void*)sc->stream : nullptr; }

@@ -260,12 +260,16 @@ struct MeshIn {
   std::vector<int32_t> faces;
   M4 base_xf;
   V3 velocity;
+  int texture = -1, texture_offset = 0;
+  bool is_light = false;
+  V3 radiance;
 };
 struct InstIn {
   int mesh, material;
   M4 xf;
   V3 velocity;
   bool direct;
+  bool is_light = false;
 };
 struct TriIn {
   int material;
@@ -277,6 +281,9 @@ struct SphIn {
   float radius;
   M4 xf;
   V3 velocity;
+  int texture = -1;
+  bool is_light = false;
+  V3 radiance;
 };
 
 void fill_xf(const M4& m, float inv12[12], float nrm9[9], float fwd16[16], bool& ok) {
@@ -303,6 +310,14 @@ struct b200rt_builder {
   std::vector<b200rt_light> lights;
   std::vector<MeshIn> meshes_in;
   std::vector<InstIn> inst_in;
+  std::vector<InstIn> light_inst_in;   // LightMesh objects: after the instances (HW7/src/Scene.cpp:1246-1311)
+  std::vector<SphIn> light_sph_in;     // LightSphere objects: after the triangles (HW7/src/Scene.cpp:1366-1424)
+  std::vector<float> texcoords;
+  std::vector<b200rt_texture> textures;
+  std::vector<float> texels;
+  std::vector<b200rt_brdf> brdfs;
+  std::vector<float> tri_uv, light_cdf;
+  std::vector<int32_t> tri_tex, light_tri;
   std::vector<TriIn> tri_in;
   std::vector<SphIn> sph_in;
   // flattened
@@ -379,6 +394,8 @@ b200rt_builder* b200rt_builder_create(int semantics) {
   b->desc.semantics = semantics;
   b->desc.shadow_eps = 0.001f;
   b->desc.isect_eps = (semantics == B200RT_SEM_PPM) ? 0.0001f : 0.000001f;
+  b->desc.background_texture = -1;
+  b->desc.env_light = -1;
   b->finished = false;
   return b;
 }
@@ -400,12 +417,30 @@ int b200rt_builder_add_camera(b200rt_builder* b, const b200rt_camera_in* in) {
   if (!b || !in) return B200RT_E_INVALID;
   b200rt_camera c;
   std::memset(&c, 0, sizeof(c));
-  const V3 e = load3(in->position), gaze = load3(in->gaze), up = load3(in->up);
+  const V3 e = load3(in->position), up = load3(in->up);
+  V3 gaze = load3(in->gaze);
   float left = in->near_plane[0], right = in->near_plane[1], bottom = in->near_plane[2],
         top = in->near_plane[3], distance = in->near_distance;
+  if (b->semantics >= B200RT_SEM_HW4 && in->simple) {
+    // HW7/src/Scene.cpp:590-607
+    const float degrees_to_radians = (float)(M_PI / 180.0f);
+    const float half_y_radian = degrees_to_radians * in->fov_y / 2;
+    top = tanf(half_y_radian) * distance;
+    const float aspect_ratio = 1.0f * in->width / in->height;
+    bottom = -1.0f * top;
+    right = top * aspect_ratio;
+    left = -1.0f * right;
+    gaze = normalize(gaze - e);
+  }
   const V3 w = -(normalize(gaze));
-  const V3 u = normalize(cross(normalize(up), w));
-  const V3 v = normalize(cross(w, u));
+  V3 u, v;
+  if (b->semantics >= B200RT_SEM_HW7 && in->left_handed) {
+    u = normalize(cross(w, normalize(up)));
+    v = normalize(cross(u, w));
+  } else {
+    u = normalize(cross(normalize(up), w));
+    v = normalize(cross(w, u));
+  }
   if (b->semantics >= B200RT_SEM_HW3 && in->aperture_size != 0.0f) {
     const float ratio = in->focus_distance / distance;
     left = ratio * left; right = ratio * right; bottom = ratio * bottom; top = ratio * top;
@@ -428,7 +463,17 @@ int b200rt_builder_add_camera(b200rt_builder* b, const b200rt_camera_in* in) {
 
 int b200rt_builder_add_material(b200rt_builder* b, const b200rt_material* m) {
   if (!b || !m) return B200RT_E_INVALID;
-  b->materials.push_back(*m);
+  b200rt_material c = *m;
+  if (b->semantics < B200RT_SEM_HW6) c.brdf = -1;
+  if (b->semantics >= B200RT_SEM_HW7 && c.degamma) {
+    // HW7/src/Scene.cpp:951-961: pow(float, 2.2f) -> powf
+    for (int i = 0; i < 3; i++) {
+      c.ambient[i] = std::pow(c.ambient[i], 2.2f);
+      c.diffuse[i] = std::pow(c.diffuse[i], 2.2f);
+      c.specular[i] = std::pow(c.specular[i], 2.2f);
+    }
+  }
+  b->materials.push_back(c);
   return (int)b->materials.size() - 1;
 }
 int b200rt_builder_add_light(b200rt_builder* b, const b200rt_light* l) {
@@ -438,6 +483,16 @@ int b200rt_builder_add_light(b200rt_builder* b, const b200rt_light* l) {
     // HW3/src/Scene.cpp:484
     store3(c.normal, normalize(cross(load3(c.edge1), load3(c.edge2))));
   }
+  if (c.kind == B200RT_LIGHT_SPOT) {
+    // Spot_light ctor — HW7/src/Spot_light.cpp:5-12.  In: edge1 = direction, edge2 = {coverage, falloff} in DEGREES
+    const float d2r = (float)(M_PI / 180.0f);
+    const float cov = c.edge2[0] * d2r, fall = c.edge2[1] * d2r;
+    store3(c.edge1, normalize(load3(c.edge1)));
+    c.edge2[0] = std::cos(cov / 2);
+    c.edge2[1] = std::cos(fall / 2);
+    c.edge2[2] = 0.f;
+  }
+  if (c.kind == B200RT_LIGHT_ENV) b->desc.env_light = (int)b->lights.size();
   b->lights.push_back(c);
   return (int)b->lights.size() - 1;
 }
@@ -503,6 +558,88 @@ int b200rt_builder_add_sphere(b200rt_builder* b, int material, int center_vertex
   s.velocity = velocity ? load3(velocity) : V3(0.f);
   b->sph_in.push_back(s);
   return (int)b->sph_in.size() - 1;
+}
+
+int b200rt_builder_set_texcoords(b200rt_builder* b, const float* uv, int n) {
+  if (!b || (n > 0 && !uv)) return B200RT_E_INVALID;
+  b->texcoords.assign(uv, uv + 2 * (size_t)n);
+  return B200RT_OK;
+}
+int b200rt_builder_add_texture(b200rt_builder* b, const b200rt_texture* t, const float* texels) {
+  if (!b || !t) return B200RT_E_INVALID;
+  b200rt_texture c = *t;
+  c.texel_offset = (int64_t)b->texels.size();
+  if (c.kind == B200RT_TEX_IMAGE) {
+    if (!texels || c.width <= 0 || c.height <= 0) return B200RT_E_INVALID;
+    b->texels.insert(b->texels.end(), texels, texels + (size_t)c.width * c.height * 3);
+  }
+  b->textures.push_back(c);
+  return (int)b->textures.size() - 1;
+}
+int b200rt_builder_add_brdf(b200rt_builder* b, const b200rt_brdf* r) {
+  if (!b || !r) return B200RT_E_INVALID;
+  b->brdfs.push_back(*r);
+  return (int)b->brdfs.size() - 1;
+}
+int b200rt_builder_set_mesh_texture(b200rt_builder* b, int mesh, int texture, int texture_offset) {
+  if (!b || mesh < 0 || mesh >= (int)b->meshes_in.size()) return B200RT_E_INVALID;
+  b->meshes_in[mesh].texture = texture;
+  b->meshes_in[mesh].texture_offset = texture_offset;
+  return B200RT_OK;
+}
+int b200rt_builder_set_sphere_texture(b200rt_builder* b, int sphere, int texture) {
+  if (!b || sphere < 0 || sphere >= (int)b->sph_in.size()) return B200RT_E_INVALID;
+  b->sph_in[sphere].texture = texture;
+  return B200RT_OK;
+}
+int b200rt_builder_add_light_mesh(b200rt_builder* b, int material, const int32_t* faces, int n_faces,
+                                  const float xf[16], const float radiance[3]) {
+  if (!b || n_faces <= 0 || !faces || !radiance) return B200RT_E_INVALID;
+  if (b->semantics < B200RT_SEM_HW7) return B200RT_E_UNSUPPORTED;
+  MeshIn m;
+  m.material = material;
+  m.smooth = 0;
+  m.faces.assign(faces, faces + 3 * (size_t)n_faces);
+  m.base_xf = xf ? M4::from(xf) : M4::identity();
+  m.velocity = V3(0.f);
+  m.is_light = true;
+  m.radiance = load3(radiance);
+  b->meshes_in.push_back(std::move(m));
+  InstIn i;
+  i.mesh = (int)b->meshes_in.size() - 1;
+  i.material = material;
+  i.xf = b->meshes_in.back().base_xf;
+  i.velocity = V3(0.f);
+  i.direct = false;
+  i.is_light = true;
+  b->light_inst_in.push_back(i);
+  return i.mesh;
+}
+int b200rt_builder_add_light_sphere(b200rt_builder* b, int material, int center_vertex, float radius,
+                                    const float xf[16], const float radiance[3]) {
+  if (!b || !radiance) return B200RT_E_INVALID;
+  if (b->semantics < B200RT_SEM_HW7) return B200RT_E_UNSUPPORTED;
+  SphIn s;
+  s.material = material;
+  s.center_vertex = center_vertex;
+  s.radius = radius;
+  s.xf = xf ? M4::from(xf) : M4::identity();
+  s.velocity = V3(0.f);
+  s.is_light = true;
+  s.radiance = load3(radiance);
+  b->light_sph_in.push_back(s);
+  return (int)b->light_sph_in.size() - 1;
+}
+int b200rt_builder_set_integrator(b200rt_builder* b, int path_tracing, int importance_sampling) {
+  if (!b) return B200RT_E_INVALID;
+  b->desc.integrator = path_tracing ? 1 : 0;
+  b->desc.importance_sampling = importance_sampling ? 1 : 0;
+  return B200RT_OK;
+}
+int b200rt_builder_set_background_texture(b200rt_builder* b, int texture) {
+  if (!b) return B200RT_E_INVALID;
+  b->desc.background_texture = texture;
+  return B200RT_OK;
 }
 
 int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
@@ -589,6 +726,21 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
       b->tri_vidx.push_back(i0); b->tri_vidx.push_back(i1); b->tri_vidx.push_back(i2);
       b->tri_info.push_back(m.material);
       b->tri_info.push_back(m.smooth ? 1 : 0);
+      {
+        // texture coordinates: texture_coord_data[vertex_index + texture_offset], where vertex_index is
+        // the face index BEFORE the vertex offset (HW7/src/Mesh_triangle.cpp:119-124); the Python/XML
+        // host passes faces with the vertex offset applied and texture_offset relative to that.
+        float uv[6] = {0, 0, 0, 0, 0, 0};
+        const int ntc = (int)(b->texcoords.size() / 2);
+        const int idx3[3] = {i0, i1, i2};
+        if (m.texture >= 0)
+          for (int c = 0; c < 3; c++) {
+            const int ti = idx3[c] + m.texture_offset;
+            if (ti >= 0 && ti < ntc) { uv[2 * c] = b->texcoords[2 * (size_t)ti]; uv[2 * c + 1] = b->texcoords[2 * (size_t)ti + 1]; }
+          }
+        b->tri_uv.insert(b->tri_uv.end(), uv, uv + 6);
+        b->tri_tex.push_back(m.texture);
+      }
       float gb[6];
       put_box(gb, gb + 3, gate[f]);
       b->tri_gate.insert(b->tri_gate.end(), gb, gb + 6);
@@ -635,6 +787,8 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
       b->tri_info.push_back(t.material);
       b->tri_info.push_back(0);
       b->tri_gate.insert(b->tri_gate.end(), 6, 0.0f);
+      b->tri_uv.insert(b->tri_uv.end(), 6, 0.0f);
+      b->tri_tex.push_back(-1);
     }
   }
   // Vertex::finalize_normal — HW3/src/Scene.cpp:872-877
@@ -648,13 +802,54 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
   // ---- top-level objects in the reference's push order ----------------------
   std::vector<Obj> top;
   b->instances.clear(); b->spheres.clear(); b->triprims.clear();
-  for (const InstIn& in : b->inst_in) {
+  std::vector<InstIn> all_inst(b->inst_in);
+  all_inst.insert(all_inst.end(), b->light_inst_in.begin(), b->light_inst_in.end());
+  for (const InstIn& in : all_inst) {
     b200rt_instance fi;
     std::memset(&fi, 0, sizeof(fi));
+    fi.light = -1;
     const b200rt_mesh& fm = b->meshes[in.mesh];
     Box mb(load3(fm.root_box), load3(fm.root_box + 3));
     Box ib;
-    if (in.direct) {
+    if (in.is_light) {
+      // Light_mesh sits in Scene::bvh itself; its box is the OBJECT-space mesh box
+      // and it has no gate of its own (HW7/include/Light_mesh.h:52-68).
+      bool ok;
+      fill_xf(in.xf, fi.inv, fi.nrm, fi.fwd, ok);
+      if (!ok) {
+        g_host_error = "NOT INVERTIBLE MATRIX (light mesh)";
+        return B200RT_E_SINGULAR;
+      }
+      ib = mb;
+      fi.flags |= B200RT_INST_LIGHT;
+      // Light_mesh ctor: areas of the TRANSFORMED triangles in the (BVH-reordered) vector order
+      const MeshIn& lm = b->meshes_in[in.mesh];
+      b200rt_light L;
+      std::memset(&L, 0, sizeof(L));
+      L.kind = B200RT_LIGHT_MESH;
+      store3(L.intensity, lm.radiance);
+      L.object = (int)b->instances.size();
+      L.cdf_begin = (int)b->light_cdf.size();
+      L.cdf_count = fm.tri_count;
+      float total = 0.0f;
+      std::vector<float> areas;
+      for (int k = 0; k < fm.tri_count; k++) {
+        const int32_t* vi = &b->tri_vidx[3 * (size_t)(fm.tri_begin + k)];
+        const V3 v0 = mul_point(in.xf, vert(vi[0])), v1 = mul_point(in.xf, vert(vi[1])), v2 = mul_point(in.xf, vert(vi[2]));
+        const float area = length(cross(v1 - v0, v2 - v0)) / 2;
+        total += area;
+        areas.push_back(area);
+      }
+      float cum = 0.0f;
+      for (int k = 0; k < fm.tri_count; k++) {
+        cum += areas[k];
+        b->light_cdf.push_back(cum / total);
+        b->light_tri.push_back(fm.tri_begin + k);
+      }
+      L.total_area = total;
+      fi.light = (int)b->lights.size();
+      b->lights.push_back(L);
+    } else if (in.direct) {
       ib = mb;  // HW2: Mesh::get_bounding_box = bvh box (HW2/Mesh.h:17-19)
       M4 id = M4::identity();
       bool ok;
@@ -675,9 +870,13 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
     store3(fi.velocity, in.velocity);
     fi.mesh = in.mesh;
     fi.material = in.material;
-    fi.texture = -1;
+    fi.texture = b->meshes_in[in.mesh].texture;  // instances take the base mesh's texture (HW7/src/Scene.cpp:1182)
+    if (b->semantics >= B200RT_SEM_HW7 && in.material >= 0 && in.material < (int)b->materials.size()) {
+      const float* tr = b->materials[in.material].transparency;
+      if (tr[0] != 0.f || tr[1] != 0.f || tr[2] != 0.f) fi.flags |= B200RT_INST_REFRACTIVE;
+    }
     Obj o;
-    o.ref = B200RT_REF(B200RT_KIND_INSTANCE, b->instances.size());
+    o.ref = B200RT_REF(in.is_light ? B200RT_KIND_LIGHTINST : B200RT_KIND_INSTANCE, b->instances.size());
     o.box = ib;
     top.push_back(o);
     b->instances.push_back(fi);
@@ -710,7 +909,9 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
       b->triprims.push_back(ft);
     }
   }
-  for (const SphIn& s : b->sph_in) {
+  std::vector<SphIn> all_sph(b->light_sph_in);
+  all_sph.insert(all_sph.end(), b->sph_in.begin(), b->sph_in.end());
+  for (const SphIn& s : all_sph) {
     if (!check_idx(s.center_vertex)) {
       g_host_error = "sphere centre index out of range";
       return B200RT_E_INVALID;
@@ -734,7 +935,18 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
     if (s.velocity != V3(0.f)) fs.flags |= B200RT_XF_MOVING;
     store3(fs.velocity, s.velocity);
     fs.material = s.material;
-    fs.texture = -1;
+    fs.texture = s.texture;
+    fs.light = -1;
+    if (s.is_light) {
+      fs.flags |= B200RT_XF_LIGHT;
+      b200rt_light L;
+      std::memset(&L, 0, sizeof(L));
+      L.kind = B200RT_LIGHT_SPHERE;
+      store3(L.intensity, s.radiance);
+      L.object = (int)b->spheres.size();
+      fs.light = (int)b->lights.size();
+      b->lights.push_back(L);
+    }
     Obj o;
     o.ref = B200RT_REF(B200RT_KIND_SPHERE, b->spheres.size());
     o.box = sb;
@@ -762,6 +974,7 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
     const uint32_t r = order[k];
     const uint32_t idx = B200RT_REF_INDEX(r);
     switch (B200RT_REF_KIND(r)) {
+      case B200RT_KIND_LIGHTINST:
       case B200RT_KIND_INSTANCE: b->instances[idx].rank = (int)k; break;
       case B200RT_KIND_SPHERE: b->spheres[idx].rank = (int)k; break;
       case B200RT_KIND_TRIPRIM: b->triprims[idx].rank = (int)k; break;
@@ -786,6 +999,12 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
   d.n_materials = (int)b->materials.size();   d.materials = b->materials.data();
   d.n_lights = (int)b->lights.size();         d.lights = b->lights.data();
   d.n_cameras = (int)b->cameras.size();       d.cameras = b->cameras.data();
+  d.tri_uv = b->tri_uv.data();                d.tri_tex = b->tri_tex.data();
+  d.n_textures = (int)b->textures.size();     d.textures = b->textures.data();
+  d.n_texels = (int64_t)b->texels.size();     d.texels = b->texels.data();
+  d.n_brdfs = (int)b->brdfs.size();           d.brdfs = b->brdfs.data();
+  d.n_light_cdf = (int)b->light_cdf.size();   d.light_cdf = b->light_cdf.data();
+  d.light_tri = b->light_tri.data();
   b->finished = true;
   *out = &b->desc;
   return B200RT_OK;

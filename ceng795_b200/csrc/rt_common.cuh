@@ -68,6 +68,16 @@ struct DScene {
   const b200rt_material* mats;
   const b200rt_light* lights;
   int n_lights, n_tris, n_spheres, n_inst;
+  // HW4..HW7
+  const float* vert_pos;           // 3 per vertex
+  const float* tri_uv;             // 6 per triangle
+  const int* tri_tex;              // 1 per triangle
+  const b200rt_texture* textures;
+  const float* texels;
+  const b200rt_brdf* brdfs;
+  const float* light_cdf;
+  const int* light_tri;
+  int background_texture, env_light, integrator, importance_sampling;
   b200rt_camera cam;
 };
 
@@ -78,6 +88,7 @@ struct DScene {
 #define RT_META_DEPTH(m) ((m)&0xFFu)
 #define RT_META_INMEDIUM 0x100u
 #define RT_META_PRIMARY 0x200u
+#define RT_META_LIGHTHIT 0x400u   /* HW7 Ray::light_hit */
 
 struct WaveInfo {
   uint32_t begin, count;
@@ -98,6 +109,9 @@ struct Pool {
   float4* rec2;      // k  rgb, as_float(child_reflect)
   uint32_t* rec3;    // child_transmit
   float4* final_c;   // combined colour (after the backward pass)
+  // HW7
+  float4* kd;        // texture-blended diffuse constant rgb, as_float(flags: bit0 replace_all, bit1 emissive)
+  float4* rec4;      // path tracing: weight of the hemisphere-sample child rgb, as_float(child_diffuse)
 };
 
 struct ShadowQueue {

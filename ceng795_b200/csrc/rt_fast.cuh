@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
   uint32_t cur_top = B200RT_REF_NONE;
   uint32_t cur = B200RT_REF_NONE;  // node to process next without going through the stack
   float cur_t = 0.f;
+  bool culling = true;             // HW7/PPM back-face culling, off inside refractive instances
 
   // the world-space ray lives in the queue; it is re-read on the (rare) instance switches
   auto world_ray = [&](v3* o, v3* dir) {
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
           best.t = RT_INF; best.beta = 0.f; best.gamma = 0.f; best.top_ref = B200RT_REF_NONE;
           best.top_rank = 0x7fffffff; best.tri = 0x7fffffff;
           found = false;
-          cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE;
+          cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true;
           sp = 0;
           cur = B200RT_REF_NONE;
           has_ray = true;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
             v3 o, dir;
             world_ray(&o, &dir);
             cr = make_fast_ray(o, dir, eps);
-            cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE;
+            cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true;
           } else if (te > bound + fabsf(bound) * 1e-4f) {
             // pruned: cannot contain a closer / in-range hit
           } else if (kind >= B200RT_KIND_LEAF1 && kind <= B200RT_KIND_LEAF4) {
@@ -202,7 +203,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
               const float4 t1 = __ldg(S.fast_tris + 3 * fi + 1);
               const float4 t2 = __ldg(S.fast_tris + 3 * fi + 2);
               float t, be, ga;
-              if (tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), cr.o, cr.d,
+              if (!(TRI_MODE == 7 && culling && dot(cr.d, mk3(t2.y, t2.z, t2.w)) > 0.0f) &&
+                  tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), cr.o, cr.d,
                                      eps, &t, &be, &ga) && t > 0.0f && (ANY ? (t < tlimit) : (t <= best.t))) {
                 const int tri = __ldg(S.fast_tri_ref + fi);
                 if (ANY || better(t, cur_rank, tri, best)) {
@@ -249,8 +251,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
               const int c = push[0] ? 0 : 1;
               cur = child[c]; cur_t = entry[c];
             }
-          } else if (kind == B200RT_KIND_INSTANCE) {
-            // Mesh_instance::intersect — HW3/include/Mesh.h:55-98 (gate already passed)
+          } else if (kind == B200RT_KIND_INSTANCE || kind == B200RT_KIND_LIGHTINST) {
+            // Mesh_instance::intersect — HW3/include/Mesh.h:55-98 (gate already passed; a Light_mesh has none)
             const b200rt_instance* in = S.inst + idx;
             const b200rt_mesh* m = S.meshes + in->mesh;
             const uint32_t froot = (m->fast_root != B200RT_REF_NONE) ? m->fast_root : m->root;
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
               if (sp < RT_FSTACK) {
                 cr = make_fast_ray(co, cd, eps);
                 cur_rank = in->rank; cur_top = ref;
+                culling = !(in->flags & B200RT_INST_REFRACTIVE);
                 stack[sp] = RT_SENTINEL; stack_t[sp] = 0.f; sp++;
                 cur = froot; cur_t = 0.f;
               } else atomicExch(&C->overflow, 2u);
@@ -282,7 +285,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
             const float4 t1 = __ldg(S.tris + 3 * (size_t)idx + 1);
             const float4 t2 = __ldg(S.tris + 3 * (size_t)idx + 2);
             float t, be, ga;
-            if (tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), cr.o, cr.d, eps,
+            if (!(TRI_MODE == 7 && culling && dot(cr.d, mk3(t2.y, t2.z, t2.w)) > 0.0f) &&
+                tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), cr.o, cr.d, eps,
                                    &t, &be, &ga) && t > 0.0f) {
               if (ANY) { if (t < tlimit) { found = true; finished = true; } }
               else if (better(t, cur_rank, (int)idx, best)) {
@@ -307,7 +311,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
             v3 lo = cr.o, ldir = cr.d;
             if (!(p->flags & B200RT_XF_IDENTITY)) { lo = xf_point(p->inv, cr.o); ldir = xf_vector4(p->inv, cr.d); }
             float t, be, ga;
-            if (tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
+            if (!(TRI_MODE == 7 && culling && dot(ldir, ld3(p->normal)) > 0.0f) &&
+                tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
               if (ANY) { if (t < tlimit) { found = true; finished = true; } }
               else if (better(t, p->rank, -1, best)) {
                 best.t = t; best.beta = be; best.gamma = ga; best.top_ref = ref; best.top_rank = p->rank;

@@ -47,7 +47,10 @@ __device__ __forceinline__ void camera_ray(const DScene& S, float x, float y, bo
     *o = e; *d = s - e;
     return;
   }
-  const v3 s = (ld3(c.top_left) + (ld3(c.su) * (x + 0.5f))) - (ld3(c.sv) * (y + 0.5f));
+  // HW4..HW7 callers pass the absolute sample position (HW7/include/Camera.h:66-84)
+  const v3 s = (S.semantics >= B200RT_SEM_HW4)
+                   ? (ld3(c.top_left) + (ld3(c.su) * x)) - (ld3(c.sv) * y)
+                   : (ld3(c.top_left) + (ld3(c.su) * (x + 0.5f))) - (ld3(c.sv) * (y + 0.5f));
   if (dof) {
     const v3 ne = e + (((u * ex) + (v * ey)) * c.aperture) * 0.5f;
     *o = ne; *d = normalize(s - ne);
@@ -78,19 +81,23 @@ __global__ void k_generate(DScene S, Pool P, RenderParams R, WaveInfo* waves, Co
     const uint32_t key = rng_mix(rng_mix(R.seed_key, pix), ns == 1 ? 0u : sidx);
     v3 o, d;
     float time = 0.0f;
+    const bool abs_pos = S.semantics >= B200RT_SEM_HW4;
     if (ns == 1) {
-      camera_ray(S, (float)col, (float)row, false, 0.f, 0.f, &o, &d);
+      if (abs_pos) camera_ray(S, col + 0.5f, row + 0.5f, false, 0.f, 0.f, &o, &d);
+      else camera_ray(S, (float)col, (float)row, false, 0.f, 0.f, &o, &d);
     } else {
       // HW3/src/Scene.cpp:55-78 with the clock-seeded engines replaced by the shared stream
       const int x = (int)(sidx / (uint32_t)ns), y = (int)(sidx % (uint32_t)ns);
       const float ex = rng_u01(key, 4), ey = rng_u01(key, 5);
       const float sx = ((float)x + ex) / (float)ns, sy = ((float)y + ey) / (float)ns;
       time = rng_u01(key, 6);
+      const float px = abs_pos ? ((float)col + sx) : (((float)col + sx) - 0.5f);
+      const float py = abs_pos ? ((float)row + sy) : (((float)row + sy) - 0.5f);
       if (S.cam.aperture == 0.0f) {
-        camera_ray(S, ((float)col + sx) - 0.5f, ((float)row + sy) - 0.5f, false, 0.f, 0.f, &o, &d);
+        camera_ray(S, px, py, false, 0.f, 0.f, &o, &d);
       } else {
         const float dx = rng_u01(key, 7) * 2.0f - 1.0f, dy = rng_u01(key, 8) * 2.0f - 1.0f;
-        camera_ray(S, ((float)col + sx) - 0.5f, ((float)row + sy) - 0.5f, true, dx, dy, &o, &d);
+        camera_ray(S, px, py, true, dx, dy, &o, &d);
       }
     }
     P.ray_o[k] = make_float4(o.x, o.y, o.z, time);

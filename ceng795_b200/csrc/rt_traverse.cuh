@@ -283,6 +283,7 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
   v3 co = o, cd = d;
   int cur_rank = 0x7fffffff;    // rank of the instance being traversed
   uint32_t cur_top = B200RT_REF_NONE;
+  bool culling = true;          // HW7/PPM: back-face culling, off inside refractive instances
 
   // root: a gate for INNER / INSTANCE, unconditional for primitives
   {
@@ -304,7 +305,7 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
     const uint32_t kind = B200RT_REF_KIND(ref);
     const uint32_t idx = B200RT_REF_INDEX(ref);
     if (kind == 14u) {  // leave instance
-      co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE;
+      co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true;
       continue;
     }
     if (!EXACT) {
@@ -329,13 +330,16 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
           if (c == 0) ok = box_gate(cr, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &entry[0]);
           else ok = box_gate(cr, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &entry[1]);
           push[c] = ok;
+        } else if (ck == B200RT_KIND_LIGHTINST) {
+          push[c] = true; entry[c] = 0.f;   // Light_mesh has no gate of its own
         } else if (ck == B200RT_KIND_TRI) {
           cnt.tris++;
           const float4 t0 = __ldg(S.tris + 3 * (size_t)ci);
           const float4 t1 = __ldg(S.tris + 3 * (size_t)ci + 1);
           const float4 t2 = __ldg(S.tris + 3 * (size_t)ci + 2);
           float t, be, ga;
-          if (tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), co, cd, eps,
+          if (!(TRI_MODE == 7 && culling && dot(cd, mk3(t2.y, t2.z, t2.w)) > 0.0f) &&
+              tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), co, cd, eps,
                                  &t, &be, &ga) && t > 0.0f) {
             if (ANY) { if (t < tlimit) return true; }
             else if (better(t, cur_rank, (int)ci, best)) {
@@ -360,7 +364,8 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
           v3 lo = co, ldir = cd;
           if (!(p->flags & B200RT_XF_IDENTITY)) { lo = xf_point(p->inv, co); ldir = xf_vector4(p->inv, cd); }
           float t, be, ga;
-          if (tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
+          if (!(TRI_MODE == 7 && culling && dot(ldir, ld3(p->normal)) > 0.0f) &&
+              tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
             if (ANY) { if (t < tlimit) return true; }
             else if (better(t, p->rank, -1, best)) {
               best.t = t; best.beta = be; best.gamma = ga; best.top_ref = child[c]; best.top_rank = p->rank;
@@ -380,7 +385,7 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
         if (sp + 1 > RT_STACK) { continue; }
         stack[sp] = child[c]; stack_t[sp] = entry[c]; sp++;
       }
-    } else if (kind == B200RT_KIND_INSTANCE) {
+    } else if (kind == B200RT_KIND_INSTANCE || kind == B200RT_KIND_LIGHTINST) {
       // Mesh_instance::intersect — HW3/include/Mesh.h:55-98 (gate already passed)
       const b200rt_instance* in = S.inst + idx;
       const b200rt_mesh* m = S.meshes + in->mesh;
@@ -398,7 +403,8 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
       }
       cr = make_ray(co, cd, eps);
       cur_rank = in->rank; cur_top = ref;
-      if (sp + 2 > RT_STACK) { co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; continue; }
+      culling = !(in->flags & B200RT_INST_REFRACTIVE);
+      if (sp + 2 > RT_STACK) { co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true; continue; }
       stack[sp] = RT_SENTINEL; stack_t[sp] = 0.f; sp++;
       if (mk == B200RT_KIND_INNER) {
         float e;
@@ -416,7 +422,8 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
       const float4 t1 = __ldg(S.tris + 3 * (size_t)idx + 1);
       const float4 t2 = __ldg(S.tris + 3 * (size_t)idx + 2);
       float t, be, ga;
-      if (tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), co, cd, eps, &t,
+      if (!(TRI_MODE == 7 && culling && dot(cd, mk3(t2.y, t2.z, t2.w)) > 0.0f) &&
+          tri_test<TRI_MODE>(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), co, cd, eps, &t,
                              &be, &ga) && t > 0.0f) {
         if (ANY) { if (t < tlimit) return true; }
         else if (better(t, cur_rank, (int)idx, best)) {
@@ -440,7 +447,8 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
       v3 lo = co, ldir = cd;
       if (!(p->flags & B200RT_XF_IDENTITY)) { lo = xf_point(p->inv, co); ldir = xf_vector4(p->inv, cd); }
       float t, be, ga;
-      if (tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
+      if (!(TRI_MODE == 7 && culling && dot(ldir, ld3(p->normal)) > 0.0f) &&
+          tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
         if (ANY) { if (t < tlimit) return true; }
         else if (better(t, p->rank, -1, best)) {
           best.t = t; best.beta = be; best.gamma = ga; best.top_ref = ref; best.top_rank = p->rank; best.tri = -1;

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._lib import SEM_HW1, SEM_HW2, SEM_HW3, SEM_HW4
+from ._lib import SEM_HW1, SEM_HW2, SEM_HW3, SEM_HW4, SEM_HW5, SEM_HW6, SEM_HW7
 
 
 def quantise(rgbw: np.ndarray, semantics: int) -> np.ndarray:
@@ -22,7 +22,8 @@ def quantise(rgbw: np.ndarray, semantics: int) -> np.ndarray:
         # HW1/Scene.cpp:20-22, HW2/Pixel.h:24-26: min(255, max(0, int(c))) — C truncation toward zero
         q = np.clip(np.trunc(np.nan_to_num(col, nan=0.0, posinf=3e9, neginf=-3e9)), 0, 255)
         return q.astype(np.uint8)
-    if semantics in (SEM_HW3, SEM_HW4):
+    if semantics in (SEM_HW3, SEM_HW4, SEM_HW5, SEM_HW6, SEM_HW7):
+        # HW7 without a tonemapper: write_png clamps to [0,255] and stores into unsigned char (HW7/src/main.cpp:105-115)
         # HW3/include/Pixel.h:25-28 clamps in float, HW3/src/main.cpp then stores into unsigned char
         q = np.minimum(np.float32(255), np.maximum(np.float32(0), np.nan_to_num(col, nan=0.0, posinf=3e9, neginf=-3e9)))
         return np.trunc(q).astype(np.uint8)

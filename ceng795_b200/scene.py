@@ -18,7 +18,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import B200RTError, SEM_BY_NAME, SEM_HW1, SEM_HW2, SEM_HW3
+from ._lib import B200RTError, SEM_BY_NAME, SEM_HW1, SEM_HW2, SEM_HW3, SEM_HW4, SEM_HW5, SEM_HW6, SEM_HW7, SEM_PPM
 
 
 def _floats(text, n=None):
@@ -50,6 +50,9 @@ class MeshSpec:
     faces: np.ndarray          # (F,3) int32, 0-based, vertex offset applied
     transforms: list = field(default_factory=list)   # [(type, index0), ...]
     velocity: np.ndarray = None
+    texture: int = -1
+    texture_offset: int = 0        # relative to the (offset-applied) face indices
+    radiance: np.ndarray = None    # LightMesh only
 
 
 @dataclass
@@ -80,6 +83,16 @@ class SceneSpec:
     instances: list
     triangles: list
     spheres: list
+    texcoords: np.ndarray = None
+    textures: list = field(default_factory=list)
+    brdfs: list = field(default_factory=list)
+    other_lights: list = field(default_factory=list)   # spot / directional / env, in the reference's push order
+    light_meshes: list = field(default_factory=list)
+    light_spheres: list = field(default_factory=list)
+    background_texture: int = -1
+    path_tracing: bool = False
+    importance_sampling: bool = False
+    ppm: dict = None
 
 
 def _parse_transform_list(text):
@@ -98,41 +111,106 @@ def _parse_transform_list(text):
     return out
 
 
-def parse_xml(path_or_text: str, semantics) -> SceneSpec:
-    """Parse the ceng795 XML dialect (elements on the hot path only)."""
+def _load_image_texels(path: str, degamma: bool) -> tuple:
+    """stbi_load(..., 3) + the float conversion of Texture::Texture (HW7/src/Texture.cpp:13-24)."""
+    from PIL import Image
+    img = np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
+    h, w = img.shape[:2]
+    if degamma:
+        # std::pow(texture_image[i] / 255.0f, 2.2) * 255.0f : float ratio, DOUBLE pow and product, stored as float
+        r = (img.astype(np.float32) / np.float32(255.0)).astype(np.float64)
+        tex = (np.power(r, 2.2) * 255.0).astype(np.float32)
+    else:
+        tex = img.astype(np.float32)
+    return np.ascontiguousarray(tex.reshape(-1)), w, h
+
+
+def _default_perm(index: int) -> list:
+    """The reference shuffles 0..15 with a clock-seeded mt19937 (HW7/src/Perlin_noise.cpp:17-20):
+    not reproducible, so the host supplies the table."""
+    import random
+    p = list(range(16))
+    random.Random(795 + index).shuffle(p)
+    return p
+
+
+def parse_xml(path_or_text: str, semantics, base_dir: str | None = None) -> SceneSpec:
+    """Parse the ceng795 XML dialect (elements on the hot path only); mirrors the section
+    order of Scene::Scene (HW7/src/Scene.cpp:449-1591, HW3/src/Scene.cpp:314-878)."""
+    import os
     sem = SEM_BY_NAME[semantics] if isinstance(semantics, str) else int(semantics)
     if path_or_text.lstrip().startswith("<"):
         root = ET.fromstring(path_or_text)
+        base_dir = base_dir or os.getcwd()
     else:
         root = ET.parse(path_or_text).getroot()
+        base_dir = base_dir or os.path.dirname(os.path.abspath(path_or_text))
     bg = _floats(_child_text(root, "BackgroundColor", "0 0 0"), 3)
     seps = float(_floats(_child_text(root, "ShadowRayEpsilon", "0.001"), 1)[0])
     depth = int(float(_child_text(root, "MaxRecursionDepth", "0")))
     cams = []
     for cel in root.find("Cameras").findall("Camera"):
-        if cel.get("type") == "simple":
-            raise B200RTError("Camera type=simple is not supported yet")
+        simple = cel.get("type") == "simple" and sem >= SEM_HW4
         res = _floats(_child_text(cel, "ImageResolution"), 2)
-        cams.append(dict(
-            position=_floats(_child_text(cel, "Position"), 3), gaze=_floats(_child_text(cel, "Gaze"), 3),
-            up=_floats(_child_text(cel, "Up"), 3), near_plane=_floats(_child_text(cel, "NearPlane"), 4),
+        gaze_txt = _child_text(cel, "Gaze") or _child_text(cel, "GazePoint")
+        cam = dict(
+            position=_floats(_child_text(cel, "Position"), 3), gaze=_floats(gaze_txt, 3),
+            up=_floats(_child_text(cel, "Up"), 3),
+            near_plane=np.zeros(4, np.float32) if simple else _floats(_child_text(cel, "NearPlane"), 4),
             near_distance=float(_floats(_child_text(cel, "NearDistance"), 1)[0]),
             width=int(res[0]), height=int(res[1]),
             num_samples=int(float(_child_text(cel, "NumSamples", "1"))),
             focus_distance=float(_floats(_child_text(cel, "FocusDistance", "0"), 1)[0]),
             aperture_size=float(_floats(_child_text(cel, "ApertureSize", "0"), 1)[0]),
-            image_name=(_child_text(cel, "ImageName", "out.png") or "out.png").strip()))
+            image_name=(_child_text(cel, "ImageName", "out.png") or "out.png").strip(),
+            left_handed=(cel.get("handedness") == "left") and sem >= SEM_HW7,
+            simple=simple, fov_y=float(_floats(_child_text(cel, "FovY", "0"), 1)[0]) if simple else 0.0,
+            tonemap=None)
+        tm = cel.find("Tonemap")
+        if tm is not None and sem >= SEM_HW5 and (_child_text(tm, "TMO", "") or "").strip() == "Photographic":
+            o = _floats(_child_text(tm, "TMOOptions"), 2)
+            cam["tonemap"] = dict(key=float(o[0]), burn=float(o[1]),
+                                  saturation=float(_floats(_child_text(tm, "Saturation", "1"), 1)[0]))
+        cams.append(cam)
+    brdfs = []
+    bel = root.find("BRDFs")
+    if bel is not None and sem >= SEM_HW6:
+        brdfs = [None] * len(list(bel))
+        kinds = {"OriginalPhong": _lib.BRDF_PHONG, "ModifiedPhong": _lib.BRDF_MODIFIED_PHONG,
+                 "OriginalBlinnPhong": _lib.BRDF_BLINN_PHONG, "ModifiedBlinnPhong": _lib.BRDF_MODIFIED_BLINN_PHONG,
+                 "TorranceSparrow": _lib.BRDF_TORRANCE_SPARROW}
+        for e in bel:
+            if e.tag not in kinds:
+                continue
+            brdfs[int(e.get("id")) - 1] = dict(
+                kind=kinds[e.tag], exponent=float(_floats(_child_text(e, "Exponent", "1"), 1)[0]),
+                normalized=(e.get("normalized") == "true"),
+                refractive_index=float(_floats(_child_text(e, "RefractiveIndex", "1"), 1)[0]))
     lights = root.find("Lights")
-    ambient = _floats(_child_text(lights, "AmbientLight", "0 0 0"), 3)
-    pls = [dict(position=_floats(_child_text(l, "Position"), 3), intensity=_floats(_child_text(l, "Intensity"), 3))
-           for l in lights.findall("PointLight")]
-    als = []
-    if sem >= SEM_HW3:
-        for l in lights.findall("AreaLight"):
-            als.append(dict(position=_floats(_child_text(l, "Position"), 3),
-                            intensity=_floats(_child_text(l, "Intensity"), 3),
-                            edge1=_floats(_child_text(l, "EdgeVector1"), 3),
-                            edge2=_floats(_child_text(l, "EdgeVector2"), 3)))
+    ambient = _floats(_child_text(lights, "AmbientLight", "0 0 0"), 3) if lights is not None else np.zeros(3, np.float32)
+    pls, als, others = [], [], []
+    if lights is not None:
+        pls = [dict(position=_floats(_child_text(l, "Position"), 3), intensity=_floats(_child_text(l, "Intensity"), 3))
+               for l in lights.findall("PointLight")]
+        if sem >= SEM_HW3:
+            for l in lights.findall("AreaLight"):
+                als.append(dict(position=_floats(_child_text(l, "Position"), 3),
+                                intensity=_floats(_child_text(l, "Intensity"), 3),
+                                edge1=_floats(_child_text(l, "EdgeVector1"), 3),
+                                edge2=_floats(_child_text(l, "EdgeVector2"), 3)))
+        if sem >= SEM_HW5 and sem != SEM_PPM:
+            for l in lights.findall("SpotLight"):
+                others.append(dict(kind=_lib.LIGHT_SPOT, position=_floats(_child_text(l, "Position"), 3),
+                                   intensity=_floats(_child_text(l, "Intensity"), 3),
+                                   direction=_floats(_child_text(l, "Direction"), 3),
+                                   coverage=float(_floats(_child_text(l, "CoverageAngle"), 1)[0]),
+                                   falloff=float(_floats(_child_text(l, "FalloffAngle"), 1)[0])))
+            for l in lights.findall("DirectionalLight"):
+                others.append(dict(kind=_lib.LIGHT_DIRECTIONAL, direction=_floats(_child_text(l, "Direction"), 3),
+                                   radiance=_floats(_child_text(l, "Radiance"), 3)))
+            l = lights.find("SphericalDirectionalLight")
+            if l is not None and sem >= SEM_HW7:
+                others.append(dict(kind=_lib.LIGHT_ENV, envmap=(_child_text(l, "EnvMapName") or "").strip()))
     mats = []
     for m in root.find("Materials").findall("Material"):
         mats.append(dict(
@@ -143,29 +221,48 @@ def parse_xml(path_or_text: str, semantics) -> SceneSpec:
             roughness=float(_floats(_child_text(m, "Roughness", "0"), 1)[0]) if sem >= SEM_HW3 else 0.0,
             phong_exponent=float(_floats(_child_text(m, "PhongExponent", "1"), 1)[0]),
             transparency=_floats(_child_text(m, "Transparency", "0 0 0"), 3) if sem >= SEM_HW2 else np.zeros(3, np.float32),
-            refraction_index=float(_floats(_child_text(m, "RefractionIndex", "1.0"), 1)[0]) if sem >= SEM_HW2 else 1.0))
+            refraction_index=float(_floats(_child_text(m, "RefractionIndex", "1.0"), 1)[0]) if sem >= SEM_HW2 else 1.0,
+            brdf=(int(m.get("BRDF", "0")) - 1) if sem >= SEM_HW6 else -1,
+            degamma=(m.get("degamma") == "true") and sem >= SEM_HW7))
     scal, tran, rot = [], [], []
     tel = root.find("Transformations")
     if tel is not None and sem >= SEM_HW3:
         scal = [_floats(e.text, 3) for e in tel.findall("Scaling")]
         tran = [_floats(e.text, 3) for e in tel.findall("Translation")]
         rot = [_floats(e.text, 4) for e in tel.findall("Rotation")]
-    verts = _big_floats(root.find("VertexData").text).reshape(-1, 3)
+    vel_ = root.find("VertexData")
+    if vel_.get("binaryFile"):
+        raise B200RTError("binaryFile vertex data is host I/O (out of scope, SURVEY §2b)")
+    verts = _big_floats(vel_.text).reshape(-1, 3)
+    texcoords = None
+    tcel = root.find("TexCoordData")
+    if tcel is not None and sem >= SEM_HW4:
+        texcoords = np.ascontiguousarray(_big_floats(tcel.text).reshape(-1, 2), np.float32)
     objs = root.find("Objects")
-    meshes, insts, tris, sphs = [], [], [], []
+    meshes, insts, tris, sphs, lmeshes, lsphs = [], [], [], [], [], []
+
+    def xf_list(el):
+        return _parse_transform_list(_child_text(el, "Transformations", "")) if sem >= SEM_HW3 else []
+
+    def tex_id(el):
+        t = _child_text(el, "Texture")
+        return (int(float(t)) - 1) if (t is not None and sem >= SEM_HW4) else -1
+
     for mel in objs.findall("Mesh"):
         fel = mel.find("Faces")
-        if fel.get("plyFile"):
-            raise B200RTError("plyFile meshes are host I/O (out of scope, SURVEY §2b)")
+        if fel.get("plyFile") or fel.get("binaryFile"):
+            raise B200RTError("plyFile / binaryFile meshes are host I/O (out of scope, SURVEY §2b)")
         off = int(fel.get("vertexOffset", "0")) if sem >= SEM_HW3 else 0
+        toff = int(fel.get("textureOffset", "0")) if sem >= SEM_HW4 else 0
         faces = _big_ints(fel.text).reshape(-1, 3) - 1 + off
         vel = _floats(_child_text(mel, "MotionBlur", "0 0 0"), 3) if sem >= SEM_HW3 else np.zeros(3, np.float32)
         meshes.append(MeshSpec(
             material=int(float(_child_text(mel, "Material"))) - 1,
             smooth=(mel.get("shadingMode") == "smooth") and sem >= SEM_HW3,
             faces=np.ascontiguousarray(faces, dtype=np.int32),
-            transforms=_parse_transform_list(_child_text(mel, "Transformations", "")) if sem >= SEM_HW3 else [],
-            velocity=vel))
+            transforms=xf_list(mel), velocity=vel, texture=tex_id(mel),
+            # the reference indexes texcoords with (face index + textureOffset), faces BEFORE the vertex offset
+            texture_offset=toff - off))
     if sem >= SEM_HW3:
         for iel in objs.findall("MeshInstance"):
             insts.append(InstanceSpec(
@@ -174,16 +271,73 @@ def parse_xml(path_or_text: str, semantics) -> SceneSpec:
                 reset_transform=(iel.get("resetTransform") == "true"),
                 transforms=_parse_transform_list(_child_text(iel, "Transformations", "")),
                 velocity=_floats(_child_text(iel, "MotionBlur", "0 0 0"), 3)))
+    if sem == SEM_HW7:
+        for lel in objs.findall("LightMesh"):
+            fel = lel.find("Faces")
+            off = int(fel.get("vertexOffset", "0"))
+            faces = _big_ints(fel.text).reshape(-1, 3) - 1 + off
+            lmeshes.append(MeshSpec(material=int(float(_child_text(lel, "Material"))) - 1, smooth=False,
+                                    faces=np.ascontiguousarray(faces, dtype=np.int32), transforms=xf_list(lel),
+                                    velocity=np.zeros(3, np.float32),
+                                    radiance=_floats(_child_text(lel, "Radiance"), 3)))
     for tel_ in objs.findall("Triangle"):
         idx = _floats(_child_text(tel_, "Indices"), 3).astype(np.int32) - 1
-        tris.append(dict(material=int(float(_child_text(tel_, "Material"))) - 1, idx=idx,
-                         transforms=_parse_transform_list(_child_text(tel_, "Transformations", "")) if sem >= SEM_HW3 else []))
+        tris.append(dict(material=int(float(_child_text(tel_, "Material"))) - 1, idx=idx, transforms=xf_list(tel_)))
+    if sem == SEM_HW7:
+        for sel in objs.findall("LightSphere"):
+            lsphs.append(dict(material=int(float(_child_text(sel, "Material"))) - 1,
+                              center=int(float(_child_text(sel, "Center"))) - 1,
+                              radius=float(_floats(_child_text(sel, "Radius"), 1)[0]),
+                              transforms=xf_list(sel), radiance=_floats(_child_text(sel, "Radiance"), 3)))
     for sel in objs.findall("Sphere"):
         sphs.append(dict(material=int(float(_child_text(sel, "Material"))) - 1,
                          center=int(float(_child_text(sel, "Center"))) - 1,
                          radius=float(_floats(_child_text(sel, "Radius"), 1)[0]),
-                         transforms=_parse_transform_list(_child_text(sel, "Transformations", "")) if sem >= SEM_HW3 else [],
+                         transforms=xf_list(sel), texture=tex_id(sel),
                          velocity=_floats(_child_text(sel, "MotionBlur", "0 0 0"), 3) if sem >= SEM_HW3 else np.zeros(3, np.float32)))
+    textures = []
+    txs = root.find("Textures")
+    names = {"nearest": _lib.TEX_NEAREST, "bilinear": _lib.TEX_BILINEAR}
+    if txs is not None and sem >= SEM_HW4:
+        for k, tel_ in enumerate(txs.findall("Texture")):
+            name = (_child_text(tel_, "ImageName") or "").strip()
+            interp = (_child_text(tel_, "Interpolation", "bilinear") or "").strip()
+            decal = (_child_text(tel_, "DecalMode", "blend_kd") or "").strip()
+            app = (_child_text(tel_, "Appearance", "repeat") or "").strip()
+            t = dict(name=name,
+                     interp=_lib.TEX_NEAREST if interp == "nearest" else _lib.TEX_BILINEAR,
+                     decal=_lib.TEX_REPLACE_KD if decal == "replace_kd" else (_lib.TEX_BLEND_KD if decal == "blend_kd" else _lib.TEX_REPLACE_ALL),
+                     normalizer=float(_floats(_child_text(tel_, "Normalizer", "255.0"), 1)[0]),
+                     scaling=float(_floats(_child_text(tel_, "ScalingFactor", "1.0"), 1)[0]),
+                     is_bump=(tel_.get("bumpmap") == "true"),
+                     bump_multiplier=float(tel_.get("bumpmapMultiplier", "1.0")),
+                     degamma=(tel_.get("degamma") == "true") and sem >= SEM_HW7)
+            if name == "perlin":
+                t["kind"] = _lib.TEX_PERLIN
+                t["appearance"] = _lib.TEX_VEIN if app == "vein" else _lib.TEX_PATCH
+                ptxt = _child_text(tel_, "Permutation")   # our extension: the host object's table
+                t["perm"] = [int(x) for x in ptxt.split()] if ptxt else _default_perm(k)
+            else:
+                t["kind"] = _lib.TEX_IMAGE
+                t["appearance"] = _lib.TEX_REPEAT if app == "repeat" else _lib.TEX_CLAMP
+                t["texels"], t["width"], t["height"] = _load_image_texels(os.path.join(base_dir, name), t["degamma"])
+            textures.append(t)
+    bg_tex = -1
+    bgt = _child_text(root, "BackgroundTexture")
+    if bgt and sem >= SEM_HW4:
+        # Texture(bg, "bilinear", "replace_all", "clamp", 255, 1.0f, false, 1.0f, false) — HW7/src/Scene.cpp:479-480
+        t = dict(name=bgt.strip(), kind=_lib.TEX_IMAGE, interp=_lib.TEX_BILINEAR, decal=_lib.TEX_REPLACE_ALL,
+                 appearance=_lib.TEX_CLAMP, normalizer=255.0, scaling=1.0, is_bump=False, bump_multiplier=1.0,
+                 degamma=False)
+        t["texels"], t["width"], t["height"] = _load_image_texels(os.path.join(base_dir, t["name"]), False)
+        bg_tex = len(textures)
+        textures.append(t)
+    for o in others:
+        if o["kind"] == _lib.LIGHT_ENV:
+            o["texels"], o["width"], o["height"] = _load_envmap(os.path.join(base_dir, o["envmap"]))
+    integ = (_child_text(root, "Integrator", "") or "").strip()
+    path_tracing = (integ == "PathTracing") and sem == SEM_HW7
+    importance = path_tracing and (_child_text(root, "IntegratorParams", "") or "").strip() == "ImportanceSampling"
     if sem == SEM_HW1 and tris:
         # HW1/Scene.cpp:320 passes `mesh.material_id` (the last mesh's) for every stand-alone
         # triangle; without any mesh the reference reads an uninitialised int.
@@ -191,7 +345,22 @@ def parse_xml(path_or_text: str, semantics) -> SceneSpec:
             for t in tris:
                 t["material"] = meshes[-1].material
     return SceneSpec(sem, bg, ambient, seps, depth, cams, pls, als, mats, scal, tran, rot,
-                     np.ascontiguousarray(verts, dtype=np.float32), meshes, insts, tris, sphs)
+                     np.ascontiguousarray(verts, dtype=np.float32), meshes, insts, tris, sphs,
+                     texcoords=texcoords, textures=textures, brdfs=brdfs, other_lights=others,
+                     light_meshes=lmeshes, light_spheres=lsphs, background_texture=bg_tex,
+                     path_tracing=path_tracing, importance_sampling=importance)
+
+
+def _load_envmap(path: str):
+    """The reference loads an EXR (tinyexr, host I/O).  This mirror accepts a .npy float array
+    [H, W, 3] (or an 8-bit image scaled to 0..1) — the device side only sees RGB floats."""
+    if path.endswith(".npy"):
+        a = np.load(path).astype(np.float32)
+    else:
+        from PIL import Image
+        a = np.asarray(Image.open(path).convert("RGB"), dtype=np.float32) / np.float32(255.0)
+    h, w = a.shape[:2]
+    return np.ascontiguousarray(a[..., :3].reshape(-1)), w, h
 
 
 def _arr3(v):
@@ -220,6 +389,9 @@ class HostScene:
             ci.near_distance = c["near_distance"]; ci.width = c["width"]; ci.height = c["height"]
             ci.num_samples = c["num_samples"]; ci.focus_distance = c["focus_distance"]
             ci.aperture_size = c["aperture_size"]
+            ci.left_handed = int(bool(c.get("left_handed", False)))
+            ci.simple = int(bool(c.get("simple", False)))
+            ci.fov_y = float(c.get("fov_y", 0.0))
             rc = L.b200rt_builder_add_camera(self._b, C.byref(ci))
             if rc < 0:
                 _lib.check(rc, "add_camera")
@@ -228,8 +400,27 @@ class HostScene:
             mm.ambient = _arr3(m["ambient"]); mm.diffuse = _arr3(m["diffuse"]); mm.specular = _arr3(m["specular"])
             mm.mirror = _arr3(m["mirror"]); mm.transparency = _arr3(m["transparency"])
             mm.roughness = m["roughness"]; mm.refraction_index = m["refraction_index"]
-            mm.phong_exponent = m["phong_exponent"]; mm.brdf = -1
+            mm.phong_exponent = m["phong_exponent"]; mm.brdf = int(m.get("brdf", -1))
+            mm.degamma = int(bool(m.get("degamma", False)))
             L.b200rt_builder_add_material(self._b, C.byref(mm))
+        # textures / BRDFs / texcoords (HW4+) — before the lights so that the env map can refer to a texture
+        n_tex = 0
+        for t in spec.textures:
+            n_tex = self._add_texture(t) + 1
+        for r in spec.brdfs:
+            rr = _lib.Brdf()
+            if r is not None:
+                rr.kind = r["kind"]; rr.exponent = r["exponent"]; rr.normalized = int(r["normalized"])
+                rr.refractive_index = r["refractive_index"]
+            L.b200rt_builder_add_brdf(self._b, C.byref(rr))
+        if spec.texcoords is not None and len(spec.texcoords):
+            tc = np.ascontiguousarray(spec.texcoords, np.float32)
+            self._keep.append(tc)
+            _lib.check(L.b200rt_builder_set_texcoords(self._b, tc.ctypes.data, tc.shape[0]), "set_texcoords")
+        if spec.background_texture >= 0:
+            L.b200rt_builder_set_background_texture(self._b, spec.background_texture)
+        if spec.semantics == SEM_HW7:
+            L.b200rt_builder_set_integrator(self._b, int(spec.path_tracing), int(spec.importance_sampling))
         for l in spec.point_lights:
             ll = _lib.Light(); ll.kind = _lib.LIGHT_POINT
             ll.position = _arr3(l["position"]); ll.intensity = _arr3(l["intensity"]); ll.object = -1
@@ -238,6 +429,19 @@ class HostScene:
             ll = _lib.Light(); ll.kind = _lib.LIGHT_AREA
             ll.position = _arr3(l["position"]); ll.intensity = _arr3(l["intensity"])
             ll.edge1 = _arr3(l["edge1"]); ll.edge2 = _arr3(l["edge2"]); ll.object = -1
+            L.b200rt_builder_add_light(self._b, C.byref(ll))
+        for l in spec.other_lights:
+            ll = _lib.Light(); ll.kind = l["kind"]; ll.object = -1
+            if l["kind"] == _lib.LIGHT_SPOT:
+                ll.position = _arr3(l["position"]); ll.intensity = _arr3(l["intensity"])
+                ll.edge1 = _arr3(l["direction"]); ll.edge2 = _arr3([l["coverage"], l["falloff"], 0.0])
+            elif l["kind"] == _lib.LIGHT_DIRECTIONAL:
+                ll.edge1 = _arr3(l["direction"]); ll.intensity = _arr3(l["radiance"])
+            elif l["kind"] == _lib.LIGHT_ENV:
+                t = dict(kind=_lib.TEX_IMAGE, interp=_lib.TEX_NEAREST, decal=_lib.TEX_REPLACE_ALL,
+                         appearance=_lib.TEX_CLAMP, normalizer=1.0, scaling=1.0, is_bump=False, bump_multiplier=1.0,
+                         texels=l["texels"], width=l["width"], height=l["height"])
+                ll.object = self._add_texture(t)
             L.b200rt_builder_add_light(self._b, C.byref(ll))
         v = np.ascontiguousarray(spec.vertices, np.float32)
         self._keep.append(v)
@@ -249,6 +453,20 @@ class HostScene:
                                            m.faces.shape[0], fp(xf), fp(vel))
             if rc < 0:
                 _lib.check(rc, "add_mesh")
+            if m.texture >= 0:
+                _lib.check(L.b200rt_builder_set_mesh_texture(self._b, rc, m.texture, m.texture_offset), "set_mesh_texture")
+        for m in spec.light_meshes:
+            xf = self._compose(m.transforms, None)
+            rad = np.ascontiguousarray(m.radiance, np.float32)
+            rc = L.b200rt_builder_add_light_mesh(self._b, m.material, m.faces.ctypes.data, m.faces.shape[0], fp(xf), fp(rad))
+            if rc < 0:
+                _lib.check(rc, "add_light_mesh")
+        for s_ in spec.light_spheres:
+            xf = self._compose(s_["transforms"], None)
+            rad = np.ascontiguousarray(s_["radiance"], np.float32)
+            rc = L.b200rt_builder_add_light_sphere(self._b, s_["material"], s_["center"], s_["radius"], fp(xf), fp(rad))
+            if rc < 0:
+                _lib.check(rc, "add_light_sphere")
         for i in spec.instances:
             base = None if i.reset_transform else self._compose(spec.meshes[i.base_mesh].transforms, None)
             xf = self._compose(i.transforms, base)
@@ -268,10 +486,29 @@ class HostScene:
             rc = L.b200rt_builder_add_sphere(self._b, s["material"], s["center"], s["radius"], fp(xf), fp(vel))
             if rc < 0:
                 _lib.check(rc, "add_sphere")
+            if s.get("texture", -1) >= 0:
+                _lib.check(L.b200rt_builder_set_sphere_texture(self._b, rc, s["texture"]), "set_sphere_texture")
         out = C.POINTER(_lib.SceneDesc)()
         _lib.check(L.b200rt_builder_finish(self._b, C.byref(out)), "builder_finish")
         self.desc_ptr = out
         self.desc = out.contents
+
+    def _add_texture(self, t) -> int:
+        tt = _lib.Texture()
+        tt.kind = t["kind"]; tt.interp = t["interp"]; tt.decal = t["decal"]; tt.appearance = t["appearance"]
+        tt.normalizer = t["normalizer"]; tt.scaling = t["scaling"]; tt.bump_multiplier = t["bump_multiplier"]
+        tt.is_bump = int(bool(t["is_bump"]))
+        tex = None
+        if t["kind"] == _lib.TEX_IMAGE:
+            tt.width = t["width"]; tt.height = t["height"]
+            tex = np.ascontiguousarray(t["texels"], np.float32)
+            self._keep.append(tex)
+        else:
+            tt.perm = (C.c_int32 * 16)(*[int(x) for x in t["perm"]])
+        rc = self._L.b200rt_builder_add_texture(self._b, C.byref(tt), tex.ctypes.data if tex is not None else None)
+        if rc < 0:
+            _lib.check(rc, "add_texture")
+        return rc
 
     def _compose(self, ops, base):
         """`M = T_k * M` in list order — HW3/src/Scene.cpp:636-657."""
@@ -326,8 +563,8 @@ class HostScene:
 class Scene:
     """Reference-facing object: ``Scene(xml).render_image(camera_index)``."""
 
-    def __init__(self, xml: str, semantics="hw3", device: int = 0, upload: bool = True):
-        self.spec = parse_xml(xml, semantics)
+    def __init__(self, xml: str, semantics="hw3", device: int = 0, upload: bool = True, base_dir: str | None = None):
+        self.spec = parse_xml(xml, semantics, base_dir=base_dir)
         self.host = HostScene(self.spec)
         self.semantics = self.spec.semantics
         self.device = device

@@ -205,3 +205,177 @@ def cfg2_hw3(n=724, width=1920, height=1080, n_instances=8, depth=2, seed=SEED, 
             + _rows(allv, "%.9g") + "  </VertexData>\n  <Objects>\n"
             + f'    <Mesh id="1"{shading}>\n      <Material>1</Material>\n      <Faces>\n' + _rows(f + 1, "%d")
             + "      </Faces>\n    </Mesh>\n" + inst + sph + "  </Objects>\n</Scene>\n")
+
+
+# --------------------------------------------------------------------------- HW7
+def write_test_texture(path, w=64, h=48, seed=SEED):
+    """A seeded RGB image (checker x gradient x noise) for the image-texture paths."""
+    from PIL import Image
+    rng = np.random.default_rng(seed + 7)
+    yy, xx = np.mgrid[0:h, 0:w]
+    chk = (((xx // 8) + (yy // 6)) % 2).astype(np.float32)
+    img = np.stack([60 + 150 * chk + 40 * xx / w, 200 - 120 * chk + 30 * yy / h, 80 + 100 * (xx + yy) / (w + h)], -1)
+    img = np.clip(img + rng.uniform(-12, 12, img.shape), 0, 255).astype(np.uint8)
+    Image.fromarray(img, "RGB").save(path)
+    return path
+
+
+def _material7(mid, amb, dif, spec, phong, mirror=None, transparency=None, refr=None, roughness=None, brdf=None,
+               degamma=False):
+    attrs = f' id="{mid}"' + (f' BRDF="{brdf}"' if brdf else "") + (' degamma="true"' if degamma else "")
+    s = f"    <Material{attrs}>\n"
+    s += f"      <AmbientReflectance>{_f(amb)}</AmbientReflectance>\n"
+    s += f"      <DiffuseReflectance>{_f(dif)}</DiffuseReflectance>\n"
+    s += f"      <SpecularReflectance>{_f(spec)}</SpecularReflectance>\n"
+    if mirror is not None:
+        s += f"      <MirrorReflectance>{_f(mirror)}</MirrorReflectance>\n"
+    if roughness is not None:
+        s += f"      <Roughness>{_f([roughness])}</Roughness>\n"
+    s += f"      <PhongExponent>{_f([phong])}</PhongExponent>\n"
+    if transparency is not None:
+        s += f"      <Transparency>{_f(transparency)}</Transparency>\n"
+        s += f"      <RefractionIndex>{_f([refr])}</RefractionIndex>\n"
+    s += "    </Material>\n"
+    return s
+
+
+def hw7_scene(asset_dir, width=160, height=120, n=12, spp=1, depth=3, path_tracing=False, importance=True,
+              stochastic_lights=False, perlin=False, seed=SEED, image_name="hw7.png", light_scale=1.0,
+              mesh_slices=(10, 12), tonemap=False) -> str:
+    """HW7 dialect: Cornell-style room (stand-alone triangles) + an image-textured, smooth-shaded
+    heightfield mesh with texture coordinates + instanced UV-sphere meshes (one material per BRDF
+    kind, one mirror, one glass) + textured spheres; point / spot / directional lights.
+    `stochastic_lights` adds an AreaLight, a LightMesh and a LightSphere (random sampling: RMSE parity);
+    without it every pixel is deterministic at 1 spp (byte parity against the HW7 binary).
+    `perlin` adds Perlin textures (the reference shuffles their table from the clock: GPU-vs-oracle only).
+    Writes the texture image into `asset_dir`; the XML refers to it by bare file name."""
+    import os
+    rng = np.random.default_rng(seed + 4)
+    if not os.path.exists(os.path.join(asset_dir, "tex_checker.png")):
+        write_test_texture(os.path.join(asset_dir, "tex_checker.png"), seed=SEED)
+    verts, tcs = [], []
+    nv = 0
+
+    def push(v, uv=None):
+        nonlocal nv
+        base = nv
+        v = np.asarray(v, np.float32)
+        verts.append(v)
+        tcs.append(np.zeros((len(v), 2), np.float32) if uv is None else np.asarray(uv, np.float32))
+        nv += len(v)
+        return base
+
+    R = 5.0
+    room = np.array([[-R, -1, -R], [R, -1, -R], [R, -1, R], [-R, -1, R],
+                     [-R, 2 * R - 1, -R], [R, 2 * R - 1, -R], [R, 2 * R - 1, R], [-R, 2 * R - 1, R]], np.float32)
+    rb = push(room)
+    quads = [(0, 3, 2, 1), (0, 1, 5, 4), (0, 4, 7, 3), (1, 2, 6, 5), (4, 5, 6, 7)]
+    tri_xml = ""
+    tid = 1
+    for qi, q in enumerate(quads):
+        for tri in ((q[0], q[1], q[2]), (q[0], q[2], q[3])):
+            idx = [rb + t + 1 for t in tri]
+            tri_xml += (f'    <Triangle id="{tid}">\n      <Material>{1 + (qi % 3)}</Material>\n'
+                        f"      <Indices>{idx[0]} {idx[1]} {idx[2]}</Indices>\n    </Triangle>\n")
+            tid += 1
+    # textured heightfield patch with uv = position in the patch (repeats 2x)
+    hv, hf = heightfield(n, seed, extent=2.2)
+    hv = hv * np.array([1, 0.8, 1], np.float32) + np.array([0, -0.55, 0.2], np.float32)
+    huv = np.stack([(hv[:, 0] + 2.2) / 2.2, (hv[:, 2] + 2.0) / 2.2], -1)
+    hb = push(hv, huv)
+    mesh_xml = (f'    <Mesh id="1" shadingMode="smooth">\n      <Material>4</Material>\n      <Texture>1</Texture>\n'
+                f'      <Faces vertexOffset="{hb}" textureOffset="{hb}">\n' + _rows(hf + 1, "%d") + "      </Faces>\n    </Mesh>\n")
+    # base UV-sphere mesh, instanced with the BRDF materials
+    sv, sf = _uv_sphere((0, 0, 0), 1.0, mesh_slices[0], mesh_slices[1])
+    sb = push(sv)
+    mesh_xml += (f'    <Mesh id="2" shadingMode="smooth">\n      <Material>5</Material>\n'
+                 f'      <Transformations>s1 t1</Transformations>\n'
+                 f'      <Faces vertexOffset="{sb}">\n' + _rows(sf + 1, "%d") + "      </Faces>\n    </Mesh>\n")
+    xf = "  <Transformations>\n    <Scaling id=\"1\">0.55 0.55 0.55</Scaling>\n    <Translation id=\"1\">-2.4 0.3 -1.2</Translation>\n"
+    inst = ""
+    for k in range(6):
+        s = 0.38 + 0.05 * k
+        xf += f'    <Scaling id="{k + 2}">{_f([s, s * (1.0 + 0.15 * k), s])}</Scaling>\n'
+        xf += f'    <Translation id="{k + 2}">{_f([-2.0 + 0.85 * k, 0.25 + 0.35 * (k % 3), -0.2 + 0.6 * (k % 2) - 0.25 * k])}</Translation>\n'
+        xf += f'    <Rotation id="{k + 1}">{_f([37.0 * k + 11, *rng.normal(size=3)])}</Rotation>\n'
+        inst += (f'    <MeshInstance id="{k + 1}" baseMeshId="2" resetTransform="true">\n'
+                 f"      <Material>{6 + k}</Material>\n"
+                 f"      <Transformations>s{k + 2} r{k + 1} t{k + 2}</Transformations>\n    </MeshInstance>\n")
+    xf += "  </Transformations>\n"
+    # spheres: textured (nearest/clamp replace_kd), glass, mirror, blend_kd bilinear
+    sph_c = np.array([[1.9, 0.0, 1.6], [-1.0, 0.1, 2.0], [0.4, 1.9, -2.2], [2.8, 1.3, -0.5]], np.float32)
+    sph_r = [0.7, 0.6, 0.9, 0.55]
+    cb = push(sph_c)
+    sph_tex = [2, None, None, 3]
+    sph_mat = [4, 12, 13, 4]
+    sph = ""
+    for i in range(4):
+        tx = f"      <Texture>{sph_tex[i]}</Texture>\n" if sph_tex[i] else ""
+        sph += (f'    <Sphere id="{i + 1}">\n      <Material>{sph_mat[i]}</Material>\n{tx}'
+                f"      <Center>{cb + i + 1}</Center>\n      <Radius>{_f([sph_r[i]])}</Radius>\n    </Sphere>\n")
+    if perlin:
+        pc = push(np.array([[-2.9, 1.6, 0.9]], np.float32))
+        sph += (f'    <Sphere id="5">\n      <Material>4</Material>\n      <Texture>4</Texture>\n'
+                f"      <Center>{pc + 1}</Center>\n      <Radius>0.6</Radius>\n    </Sphere>\n")
+    L = light_scale
+    mats = (_material7(1, [0.25, 0.25, 0.25], [0.6, 0.6, 0.55], [0.05, 0.05, 0.05], 5)
+            + _material7(2, [0.25, 0.2, 0.2], [0.65, 0.2, 0.2], [0.05, 0.05, 0.05], 5)
+            + _material7(3, [0.2, 0.25, 0.2], [0.2, 0.6, 0.25], [0.05, 0.05, 0.05], 5)
+            + _material7(4, [0.2, 0.2, 0.2], [0.5, 0.5, 0.5], [0.3, 0.3, 0.3], 30)
+            + _material7(5, [0.2, 0.2, 0.25], [0.3, 0.3, 0.7], [0.4, 0.4, 0.4], 60, degamma=True)
+            + "".join(_material7(6 + k, [0.15, 0.15, 0.15], rng.uniform(0.2, 0.7, 3), rng.uniform(0.2, 0.5, 3),
+                                 float(10 + 15 * k), brdf=(k + 1) if k < 5 else None) for k in range(6))
+            + _material7(12, [0, 0, 0], [0.02, 0.02, 0.02], [0.1, 0.1, 0.1], 80, transparency=[0.9, 0.95, 0.9], refr=1.5)
+            + _material7(13, [0.05, 0.05, 0.05], [0.05, 0.05, 0.05], [0.3, 0.3, 0.3], 90, mirror=[0.8, 0.8, 0.8],
+                         roughness=(0.12 if stochastic_lights else None)))
+    brdfs = ('  <BRDFs>\n    <OriginalPhong id="1"><Exponent>20</Exponent></OriginalPhong>\n'
+             '    <ModifiedPhong id="2" normalized="true"><Exponent>30</Exponent></ModifiedPhong>\n'
+             '    <OriginalBlinnPhong id="3"><Exponent>40</Exponent></OriginalBlinnPhong>\n'
+             '    <ModifiedBlinnPhong id="4" normalized="true"><Exponent>50</Exponent></ModifiedBlinnPhong>\n'
+             '    <TorranceSparrow id="5"><Exponent>60</Exponent><RefractiveIndex>2.1</RefractiveIndex></TorranceSparrow>\n'
+             "  </BRDFs>\n")
+    textures = ('  <Textures>\n'
+                '    <Texture id="1"><ImageName>tex_checker.png</ImageName><Interpolation>bilinear</Interpolation>'
+                '<DecalMode>replace_kd</DecalMode><Appearance>repeat</Appearance></Texture>\n'
+                '    <Texture id="2" degamma="true"><ImageName>tex_checker.png</ImageName><Interpolation>nearest</Interpolation>'
+                '<DecalMode>replace_kd</DecalMode><Appearance>clamp</Appearance></Texture>\n'
+                '    <Texture id="3" bumpmap="true" bumpmapMultiplier="0.02"><ImageName>tex_checker.png</ImageName>'
+                '<Interpolation>bilinear</Interpolation><DecalMode>blend_kd</DecalMode><Appearance>clamp</Appearance>'
+                '<Normalizer>255</Normalizer></Texture>\n'
+                + ('    <Texture id="4" bumpmap="true" bumpmapMultiplier="0.6"><ImageName>perlin</ImageName>'
+                   '<DecalMode>blend_kd</DecalMode><Appearance>patch</Appearance><ScalingFactor>3.5</ScalingFactor>'
+                   '<Permutation>11 3 7 0 14 9 2 13 5 8 1 15 6 12 4 10</Permutation></Texture>\n' if perlin else "")
+                + "  </Textures>\n")
+    lights = ("  <Lights>\n    <AmbientLight>20 20 20</AmbientLight>\n"
+              f'    <PointLight id="1"><Position>-2 7.5 3</Position><Intensity>{_f(np.array([2600, 2500, 2300]) * L)}</Intensity></PointLight>\n'
+              + (f'    <AreaLight id="1"><Position>1 8.2 -1</Position><Intensity>{_f(np.array([1800, 1800, 1700]) * L)}</Intensity>'
+                 '<EdgeVector1>1.2 0 0</EdgeVector1><EdgeVector2>0 0 1.2</EdgeVector2></AreaLight>\n' if stochastic_lights else "")
+              + f'    <SpotLight id="1"><Position>3.5 6 3.5</Position><Direction>-0.5 -1 -0.45</Direction>'
+              f'<Intensity>{_f(np.array([3000, 3200, 3400]) * L)}</Intensity><CoverageAngle>50</CoverageAngle><FalloffAngle>30</FalloffAngle></SpotLight>\n'
+              f'    <DirectionalLight id="1"><Direction>0.3 -1 -0.6</Direction><Radiance>{_f(np.array([30, 28, 25]) * L)}</Radiance></DirectionalLight>\n'
+              "  </Lights>\n")
+    lobj = ""
+    if stochastic_lights:
+        lq = push(np.array([[-0.8, 8.7, -0.8], [0.8, 8.7, -0.8], [0.8, 8.7, 0.8], [-0.8, 8.7, 0.8]], np.float32))
+        lobj += (f'    <LightMesh id="1">\n      <Material>1</Material>\n      <Radiance>{_f(np.array([900, 900, 850]) * L)}</Radiance>\n'
+                 f'      <Faces vertexOffset="{lq}">\n1 2 3\n1 3 4\n      </Faces>\n    </LightMesh>\n')
+        lc = push(np.array([[-3.2, 5.0, -2.5]], np.float32))
+        lobj += (f'    <LightSphere id="1">\n      <Material>1</Material>\n      <Center>{lc + 1}</Center>\n      <Radius>0.45</Radius>\n'
+                 f"      <Radiance>{_f(np.array([1200, 1000, 800]) * L)}</Radiance>\n    </LightSphere>\n")
+    allv = np.concatenate(verts, 0)
+    alluv = np.concatenate(tcs, 0)
+    aspect = width / height
+    integ = ""
+    if path_tracing:
+        integ = "  <Integrator>PathTracing</Integrator>\n" + ("  <IntegratorParams>ImportanceSampling</IntegratorParams>\n" if importance else "")
+    tm = ("      <Tonemap><TMO>Photographic</TMO><TMOOptions>0.18 1</TMOOptions><Saturation>1.0</Saturation></Tonemap>\n"
+          if tonemap else "")
+    return ("<Scene>\n  <BackgroundColor>12 16 30</BackgroundColor>\n  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
+            f"  <MaxRecursionDepth>{depth}</MaxRecursionDepth>\n" + integ + "  <Cameras>\n    <Camera id=\"1\">\n"
+            "      <Position>0 2.6 4.8</Position>\n      <Gaze>0 -0.32 -1</Gaze>\n      <Up>0 1 0</Up>\n"
+            f"      <NearPlane>{_f([-0.6 * aspect, 0.6 * aspect, -0.6, 0.6])}</NearPlane>\n      <NearDistance>1</NearDistance>\n"
+            f"      <ImageResolution>{width} {height}</ImageResolution>\n      <NumSamples>{spp}</NumSamples>\n"
+            f"      <ImageName>{image_name}</ImageName>\n" + tm + "    </Camera>\n  </Cameras>\n"
+            + brdfs + lights + "  <Materials>\n" + mats + "  </Materials>\n" + xf + "  <VertexData>\n"
+            + _rows(allv, "%.9g") + "  </VertexData>\n  <TexCoordData>\n" + _rows(alluv, "%.9g") + "  </TexCoordData>\n"
+            + textures + "  <Objects>\n" + mesh_xml + inst + lobj + tri_xml + sph + "  </Objects>\n</Scene>\n")

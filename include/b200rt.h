@@ -61,6 +61,7 @@ enum b200rt_semantics {
 #define B200RT_KIND_LEAF1 5u    /* fast-BVH leaf of 1..4 triangles (kinds 5..8):  */
 #define B200RT_KIND_LEAF4 8u    /*   index = first entry in fast_tri_* arrays     */
 #define B200RT_KIND_FNODE 9u    /* index into fast_nodes[]                        */
+#define B200RT_KIND_LIGHTINST 10u /* HW7 Light_mesh: index into instances[], entered WITHOUT a gate box */
 #define B200RT_KIND_NONE 15u
 #define B200RT_REF(kind, idx) ((((uint32_t)(kind)) << 28) | ((uint32_t)(idx)))
 #define B200RT_REF_KIND(r) ((r) >> 28)
@@ -93,6 +94,7 @@ typedef struct b200rt_mesh {
 #define B200RT_INST_MOVING 1u     /* velocity != 0: per-ray inverse (HW3/include/Mesh.h:76-95) */
 #define B200RT_INST_DIRECT 2u     /* HW2: Mesh sits in the top BVH itself, no gate / transform  */
 #define B200RT_INST_REFRACTIVE 4u /* HW7: culling off inside glass (HW7/include/Mesh.h:73-75)   */
+#define B200RT_INST_LIGHT 8u      /* HW7 Light_mesh: no own gate box, emissive (HW7/include/Light_mesh.h:52-68) */
 typedef struct b200rt_instance {
   float inv[12];      /* rows 0..2 of M^-1 (point: + column 3)                */
   float nrm[9];       /* upper 3x3 of transpose(M^-1)                         */
@@ -104,11 +106,13 @@ typedef struct b200rt_instance {
   int32_t texture;
   uint32_t flags;
   int32_t rank;       /* DFS position among top-level objects (tie-break)     */
-  int32_t pad[3];
+  int32_t light;      /* LIGHT: index into lights[] (radiance), else -1        */
+  int32_t pad[2];
 } b200rt_instance;
 
 #define B200RT_XF_IDENTITY 1u
 #define B200RT_XF_MOVING 2u
+#define B200RT_XF_LIGHT 4u        /* HW7 Light_sphere (HW7/include/Light_sphere.h:16-24) */
 typedef struct b200rt_sphere {
   float center[3];
   float radius;
@@ -120,7 +124,8 @@ typedef struct b200rt_sphere {
   int32_t texture;
   uint32_t flags;
   int32_t rank;
-  int32_t pad[2];
+  int32_t light;      /* LIGHT: index into lights[], else -1 */
+  int32_t pad;
 } b200rt_sphere;
 
 typedef struct b200rt_triprim {
@@ -131,6 +136,35 @@ typedef struct b200rt_triprim {
   uint32_t flags;
   int32_t rank;
 } b200rt_triprim;
+
+/* HW4+ textures (HW7/include/Texture.h:40-55).  Image texels are floats 0..255
+ * (after the optional degamma, HW7/src/Texture.cpp:13-24), 3 per texel, in
+ * `texels` starting at texel_offset (in floats). */
+enum b200rt_tex_kind { B200RT_TEX_IMAGE = 0, B200RT_TEX_PERLIN = 1 };
+enum b200rt_tex_interp { B200RT_TEX_NEAREST = 0, B200RT_TEX_BILINEAR = 1 };
+enum b200rt_tex_decal { B200RT_TEX_REPLACE_KD = 0, B200RT_TEX_BLEND_KD = 1, B200RT_TEX_REPLACE_ALL = 2 };
+enum b200rt_tex_appearance { B200RT_TEX_REPEAT = 0, B200RT_TEX_CLAMP = 1, B200RT_TEX_VEIN = 2, B200RT_TEX_PATCH = 3 };
+typedef struct b200rt_texture {
+  int32_t kind, interp, decal, appearance;
+  float normalizer, scaling, bump_multiplier;
+  int32_t is_bump;
+  int32_t width, height;
+  int64_t texel_offset;
+  int32_t perm[16];   /* Perlin permutation of the HOST object (the reference shuffles with a
+                         clock-seeded mt19937, HW7/src/Perlin_noise.cpp:17-20)              */
+} b200rt_texture;
+
+/* HW6+ BRDFs (HW7/src/*_BRDF.cpp) */
+enum b200rt_brdf_kind {
+  B200RT_BRDF_PHONG = 0, B200RT_BRDF_MODIFIED_PHONG = 1, B200RT_BRDF_BLINN_PHONG = 2,
+  B200RT_BRDF_MODIFIED_BLINN_PHONG = 3, B200RT_BRDF_TORRANCE_SPARROW = 4
+};
+typedef struct b200rt_brdf {
+  int32_t kind;
+  float exponent;
+  int32_t normalized;
+  float refractive_index;
+} b200rt_brdf;
 
 typedef struct b200rt_material {
   float ambient[3], diffuse[3], specular[3], mirror[3], transparency[3];
@@ -154,8 +188,10 @@ typedef struct b200rt_light {
   float position[3];
   float intensity[3];
   float edge1[3], edge2[3], normal[3]; /* area; spot: edge1 = direction, edge2 = {cos(cov/2), cos(fall/2), 0} */
-  int32_t object;                      /* mesh / sphere lights: index of the emissive object */
-  float pad[4];
+  int32_t object;                      /* mesh light: instance index; sphere light: sphere index; env: texture index */
+  int32_t cdf_begin, cdf_count;        /* mesh light: range in light_cdf[] / light_tri[] (HW7/include/Light_mesh.h:19-50) */
+  float total_area;
+  float pad;
 } b200rt_light;
 
 typedef struct b200rt_camera {
@@ -216,6 +252,23 @@ typedef struct B200SceneDesc {
   const b200rt_light* lights;
   int32_t n_cameras;
   const b200rt_camera* cameras;
+
+  /* ---- HW4..HW7 ---- */
+  const float* tri_uv;         /* 6 floats per triangle: uv of the three vertices (0 if the mesh has no image texture) */
+  const int32_t* tri_tex;      /* 1 per triangle: texture id of its mesh, -1 none (HW7/src/Mesh_triangle.cpp:107) */
+  int32_t n_textures;
+  const b200rt_texture* textures;
+  int64_t n_texels;            /* floats */
+  const float* texels;
+  int32_t n_brdfs;
+  const b200rt_brdf* brdfs;
+  int32_t n_light_cdf;
+  const float* light_cdf;      /* cumulative area / total area */
+  const int32_t* light_tri;    /* triangle index per cdf entry (file order of the LightMesh faces) */
+  int32_t background_texture;  /* texture id or -1 (HW7/src/Scene.cpp:476-484) */
+  int32_t env_light;           /* index into lights[] of the SphericalDirectionalLight or -1 */
+  int32_t integrator;          /* 0 ray tracing, 1 path tracing (HW7/src/Scene.cpp:1573-1582) */
+  int32_t importance_sampling; /* path tracing: 1 = cosine sampling */
 } B200SceneDesc;
 
 /* ======================================================================== */
@@ -241,6 +294,9 @@ typedef struct b200rt_camera_in {
   int32_t width, height;
   int32_t num_samples;     /* as written in the XML; builder applies (int)sqrt */
   float focus_distance, aperture_size;
+  int32_t left_handed;     /* HW7 handedness="left" (HW7/include/Camera.h:24-26) */
+  int32_t simple;          /* HW7 type="simple": `gaze` holds the gaze POINT, near plane from fov_y (HW7/src/Scene.cpp:590-607) */
+  float fov_y;             /* degrees */
 } b200rt_camera_in;
 
 b200rt_builder* b200rt_builder_create(int semantics);
@@ -261,6 +317,22 @@ int b200rt_builder_add_triangle(b200rt_builder*, int material, const int32_t idx
                                 const float xf[16]);
 int b200rt_builder_add_sphere(b200rt_builder*, int material, int center_vertex, float radius,
                               const float xf[16], const float velocity[3]);
+/* ---- HW4..HW7 additions (ignored by earlier semantics) ---- */
+int b200rt_builder_set_texcoords(b200rt_builder*, const float* uv, int n);
+/* texels: width*height*3 floats 0..255 already degamma'd (NULL for Perlin). Returns texture id. */
+int b200rt_builder_add_texture(b200rt_builder*, const b200rt_texture*, const float* texels);
+int b200rt_builder_add_brdf(b200rt_builder*, const b200rt_brdf*);
+/* Texture / texcoord offset of the mesh added last (HW7/src/Scene.cpp:1088-1098). */
+int b200rt_builder_set_mesh_texture(b200rt_builder*, int mesh, int texture, int texture_offset);
+int b200rt_builder_set_sphere_texture(b200rt_builder*, int sphere, int texture);
+/* LightMesh (HW7/src/Scene.cpp:1246-1311): faces 0-based with the vertex offset applied. */
+int b200rt_builder_add_light_mesh(b200rt_builder*, int material, const int32_t* faces, int n_faces,
+                                  const float xf[16], const float radiance[3]);
+int b200rt_builder_add_light_sphere(b200rt_builder*, int material, int center_vertex, float radius,
+                                    const float xf[16], const float radiance[3]);
+int b200rt_builder_set_integrator(b200rt_builder*, int path_tracing, int importance_sampling);
+int b200rt_builder_set_background_texture(b200rt_builder*, int texture);
+
 /* Builds per-mesh and top-level BVHs in the reference's topology, finalises
  * vertex normals and flattens.  The returned desc is owned by the builder. */
 int b200rt_builder_finish(b200rt_builder*, const B200SceneDesc** out);
@@ -312,6 +384,11 @@ int b200rt_primary_ids(b200rt_scene*, int camera_index, const B200RenderOpts*, i
  * ray: o.xyz, time, d.xyz, tmax-unused).  Test/measurement hook for a4-a8. */
 int b200rt_trace_rays(b200rt_scene*, const float* rays, int64_t n, int32_t exact_traversal,
                       int32_t* ids_out, float* t_out, B200RenderStats* stats_out);
+
+/* Debug / test hook: copies `count` elements of one wavefront-pool array of the LAST render batch to
+ * host memory.  field: 0 ray_o(f4) 1 ray_d(f4) 2 hit_a(f4) 3 nrm(f4) 4 rec0(f4) 5 rec1(f4) 6 rec2(f4)
+ * 7 rec4(f4) 8 final_c(f4) 9 kd(f4) 10 pixel(u32) 11 key(u32) 12 hit_b(i32x2) 13 rec3(u32). */
+int b200rt_debug_pool(b200rt_scene*, int field, void* out, int64_t count);
 
 /* The CUDA stream (cudaStream_t) every launch of this scene is issued on, so a
  * caller can bracket calls with its own events. */

@@ -135,7 +135,9 @@ def run_reference(tree: str, xml_text: str, workdir: str | None = None, timeout:
     for name, tail in re.findall(r"(\S+)\(\d+x\d+\) is saved in: ([^\n]*)", out):
         res["ms"][name] = parse_time_ms(tail)
         p = os.path.join(tmp, name)
-        if os.path.exists(p) and name.lower().endswith(".png"):
+        if not os.path.exists(p) and os.path.exists(p + ".png"):
+            p = p + ".png"   # HW7/PPM print the name without its extension (HW7/src/main.cpp:56-57,97)
+        if os.path.exists(p) and p.lower().endswith(".png"):
             res["images"][name] = read_png(p)
     if own:
         import shutil

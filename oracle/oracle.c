@@ -47,6 +47,9 @@ typedef struct {
   float time;
   int in_medium;
   int is_shadow;
+  int light_hit;   /* HW7 Ray::light_hit */
+  int primary;     /* HW7 ray_type == r_primary */
+  float bg_u, bg_v;
 } Ray;
 
 typedef struct {
@@ -57,6 +60,10 @@ typedef struct {
   int material;
   v3 normal;
   int valid;      /* shape != NULL */
+  /* HW4..HW7 */
+  float u, v, perlin;
+  int texture;    /* texture id of the shape that owns the hit (instance / sphere), -1 none */
+  int light;      /* is_light_object: index into lights[] (radiance), else -1 */
 } Hit;
 
 typedef struct OracleCounters {
@@ -68,6 +75,7 @@ typedef struct {
   const B200SceneDesc* d;
   OracleCounters* c;
 } Ctx;
+static inline int sem_hw7(const B200SceneDesc* d) { return d->semantics >= B200RT_SEM_HW7; }
 
 /* Matrix4x4::multiply — HW3/src/Matrix4x4.cpp:29-50 (3x4 rows) */
 static v3 xf_point(const float* m, v3 p) {
@@ -211,20 +219,26 @@ static int tri_core(const float* g, v3 o, v3 d, int mode, float eps, float* t_ou
   return 1;
 }
 
-static int shape_intersect(const Ctx* cx, uint32_t ref, const float* box, const Ray* ray, Hit* hit);
+static int shape_intersect(const Ctx* cx, uint32_t ref, const float* box, const Ray* ray, Hit* hit, int culling);
+static void tex_surface_tri(const B200SceneDesc* d, int tri, float beta, float gamma, v3 local_p, Hit* hit);
+static void tex_surface_sphere(const B200SceneDesc* d, const b200rt_sphere* s, v3 local_coords, v3 local_p, Hit* hit);
 
-/* Mesh_triangle::intersect — HW3/src/Mesh_triangle.cpp:75-114 */
-static int mesh_tri_intersect(const Ctx* cx, int tri, const Ray* ray, Hit* hit) {
+/* Mesh_triangle::intersect — HW3/src/Mesh_triangle.cpp:75-114, HW7/src/Mesh_triangle.cpp:56-157 */
+static int mesh_tri_intersect(const Ctx* cx, int tri, const Ray* ray, Hit* hit, int culling) {
   const B200SceneDesc* d = cx->d;
   cx->c->tris_tested++;
+  const int hw7 = sem_hw7(d);
+  if (hw7 && culling && dot(ray->d, ld(d->tri_geom + 12 * (size_t)tri + 9)) > 0.0f) return 0;
   float t, beta, gamma;
-  if (!tri_core(d->tri_geom + 12 * (size_t)tri, ray->o, ray->d, 2, d->isect_eps, &t, &beta, &gamma))
+  if (!tri_core(d->tri_geom + 12 * (size_t)tri, ray->o, ray->d, hw7 ? 7 : 2, d->isect_eps, &t, &beta, &gamma))
     return 0;
   hit->t = t;
   hit->tri = tri;
   hit->shape = B200RT_REF(B200RT_KIND_TRI, tri);
   hit->material = d->tri_info[2 * (size_t)tri];
   hit->valid = 1;
+  hit->light = -1;
+  hit->texture = -1;
   if (d->tri_info[2 * (size_t)tri + 1] & 1) {
     const int32_t* vi = d->tri_vidx + 3 * (size_t)tri;
     const v3 n0 = ld(d->vert_normal + 3 * (size_t)vi[0]);
@@ -234,11 +248,15 @@ static int mesh_tri_intersect(const Ctx* cx, int tri, const Ray* ray, Hit* hit) 
   } else {
     hit->normal = ld(d->tri_geom + 12 * (size_t)tri + 9);
   }
+  if (hw7) {
+    hit->u = -1; hit->v = -1; hit->perlin = -1;
+    if (d->tri_tex[tri] != -1) tex_surface_tri(d, tri, beta, gamma, add(ray->o, muls(ray->d, t)), hit);
+  }
   return 1;
 }
 
 /* Triangle::intersect (stand-alone primitive) — HW3/src/Triangle.cpp:51-109 */
-static int triprim_intersect(const Ctx* cx, int idx, const Ray* ray, Hit* hit) {
+static int triprim_intersect(const Ctx* cx, int idx, const Ray* ray, Hit* hit, int culling) {
   const b200rt_triprim* p = cx->d->triprims + idx;
   cx->c->tris_tested++;
   float g[12];
@@ -249,10 +267,13 @@ static int triprim_intersect(const Ctx* cx, int idx, const Ray* ray, Hit* hit) {
     o = xf_point(p->inv, ray->o);
     dd = xf_vector(p->inv, 4, ray->d);
   }
+  /* HW7/src/Triangle.cpp:69-71,106-108: culling against the object-space normal */
+  if (sem_hw7(cx->d) && culling && dot(dd, ld(p->normal)) > 0) return 0;
   float t, beta, gamma;
   if (!tri_core(g, o, dd, 2, cx->d->isect_eps, &t, &beta, &gamma)) return 0;
   hit->t = t;
   hit->tri = -1;
+  hit->light = -1; hit->texture = -1; hit->u = 0; hit->v = 0; hit->perlin = 0;
   hit->shape = B200RT_REF(B200RT_KIND_TRIPRIM, idx);
   hit->material = p->material;
   hit->top_rank = p->rank;
@@ -301,8 +322,24 @@ static int sphere_intersect(const Ctx* cx, int idx, const Ray* ray, Hit* hit) {
     t = (t2 < .0) ? t1 : t2;
   }
   hit->t = t;
-  v3 n = normalize(sub(add(o, muls(dd, t)), center));
-  if (nrm) n = normalize(xf_vector(nrm, nstride, n));
+  hit->light = -1; hit->texture = -1; hit->u = -1; hit->v = -1; hit->perlin = -1;
+  const v3 local_p = add(o, muls(dd, t));
+  const v3 local_c = sub(local_p, center);
+  v3 n = normalize(local_c);
+  if (sem_hw7(cx->d)) {
+    /* HW7/src/Sphere.cpp:65-97: the normal matrix is ALWAYS applied (a second normalise even for identity) */
+    hit->normal = n;
+    if (s->texture != -1) {
+      hit->texture = s->texture;
+      tex_surface_sphere(cx->d, s, local_c, local_p, hit);
+      n = hit->normal;
+    }
+    if (nrm) n = normalize(xf_vector(nrm, nstride, n));
+    else n = normalize(xf_vector(s->nrm, 3, n));
+    if (s->flags & B200RT_XF_LIGHT) hit->light = s->light;   /* Light_sphere::intersect */
+  } else if (nrm) {
+    n = normalize(xf_vector(nrm, nstride, n));
+  }
   hit->normal = n;
   hit->tri = -1;
   hit->shape = B200RT_REF(B200RT_KIND_SPHERE, idx);
@@ -312,18 +349,22 @@ static int sphere_intersect(const Ctx* cx, int idx, const Ray* ray, Hit* hit) {
   return 1;
 }
 
-/* Mesh_instance::intersect — HW3/include/Mesh.h:55-98 (HW2: Mesh::intersect HW2/Mesh.h:13-15) */
-static int instance_intersect(const Ctx* cx, int idx, const float* box, const Ray* ray, Hit* hit) {
+/* Mesh_instance::intersect — HW3/include/Mesh.h:55-98, HW7/include/Mesh.h:65-115 (HW2: Mesh::intersect
+ * HW2/Mesh.h:13-15; HW7 Light_mesh::intersect HW7/include/Light_mesh.h:52-68) */
+static int instance_intersect(const Ctx* cx, int idx, const float* box, const Ray* ray, Hit* hit, int culling) {
   const B200SceneDesc* d = cx->d;
   const b200rt_instance* in = d->instances + idx;
   const b200rt_mesh* m = d->meshes + in->mesh;
   if (in->flags & B200RT_INST_DIRECT) {
-    if (!shape_intersect(cx, m->root, m->root_box, ray, hit)) return 0;
+    if (!shape_intersect(cx, m->root, m->root_box, ray, hit, culling)) return 0;
     hit->top_rank = in->rank;
     return 1;
   }
-  const float bt = box_intersect(box, box + 3, ray, d->isect_eps);
-  if (bt < 0.0f || bt == INFINITY) return 0;
+  if (!(in->flags & B200RT_INST_LIGHT)) {
+    const float bt = box_intersect(box, box + 3, ray, d->isect_eps);
+    if (bt < 0.0f || bt == INFINITY) return 0;
+  }
+  if (in->flags & B200RT_INST_REFRACTIVE) culling = 0;
   cx->c->instances_entered++;
   Ray local = *ray;
   float inv16[16], nrm16[16];
@@ -339,40 +380,43 @@ static int instance_intersect(const Ctx* cx, int idx, const float* box, const Ra
     local.d = xf_vector(in->inv, 4, ray->d);
   }
   if (m->root == B200RT_REF_NONE) return 0;
-  if (!shape_intersect(cx, m->root, m->root_box, &local, hit)) return 0;
+  if (!shape_intersect(cx, m->root, m->root_box, &local, hit, culling)) return 0;
   hit->normal = normalize(xf_vector(nrm, nstride, hit->normal));
   hit->shape = B200RT_REF(B200RT_KIND_INSTANCE, idx);
   hit->material = in->material;
+  hit->texture = in->texture;
+  hit->light = (in->flags & B200RT_INST_LIGHT) ? in->light : -1;
   hit->top_rank = in->rank;
   return 1;
 }
 
 /* BVH::intersect — HW3/src/Bounding_volume_hierarchy.cpp:31-55 */
-static int bvh_intersect(const Ctx* cx, uint32_t node, const float* box, const Ray* ray, Hit* hit) {
+static int bvh_intersect(const Ctx* cx, uint32_t node, const float* box, const Ray* ray, Hit* hit, int culling) {
   const b200rt_bvh_node* n = cx->d->nodes + node;
   const float bt = box_intersect(box, box + 3, ray, cx->d->isect_eps);
   if (bt < 0.0f || bt == INFINITY) return 0;
   cx->c->nodes_visited++; /* nodes whose gate passed = 64-byte node records a flattened traversal fetches */
   int any = 0;
   Hit lh; memset(&lh, 0, sizeof(lh)); lh.t = INFINITY; lh.top_rank = -1; lh.tri = -1;
-  if (shape_intersect(cx, n->left, n->lmin, ray, &lh) && lh.t > 0.0f && lh.t < hit->t) {
+  if (shape_intersect(cx, n->left, n->lmin, ray, &lh, culling) && lh.t > 0.0f && lh.t < hit->t) {
     *hit = lh; any = 1;
   }
   Hit rh; memset(&rh, 0, sizeof(rh)); rh.t = INFINITY; rh.top_rank = -1; rh.tri = -1;
-  if (shape_intersect(cx, n->right, n->rmin, ray, &rh) && rh.t > 0.0f && rh.t < hit->t) {
+  if (shape_intersect(cx, n->right, n->rmin, ray, &rh, culling) && rh.t > 0.0f && rh.t < hit->t) {
     *hit = rh; any = 1;
   }
   return any;
 }
 
-static int shape_intersect(const Ctx* cx, uint32_t ref, const float* box, const Ray* ray, Hit* hit) {
+static int shape_intersect(const Ctx* cx, uint32_t ref, const float* box, const Ray* ray, Hit* hit, int culling) {
   const uint32_t idx = B200RT_REF_INDEX(ref);
   switch (B200RT_REF_KIND(ref)) {
-    case B200RT_KIND_INNER: return bvh_intersect(cx, idx, box, ray, hit);
-    case B200RT_KIND_TRI: return mesh_tri_intersect(cx, (int)idx, ray, hit);
+    case B200RT_KIND_INNER: return bvh_intersect(cx, idx, box, ray, hit, culling);
+    case B200RT_KIND_TRI: return mesh_tri_intersect(cx, (int)idx, ray, hit, culling);
     case B200RT_KIND_SPHERE: return sphere_intersect(cx, (int)idx, ray, hit);
-    case B200RT_KIND_TRIPRIM: return triprim_intersect(cx, (int)idx, ray, hit);
-    case B200RT_KIND_INSTANCE: return instance_intersect(cx, (int)idx, box, ray, hit);
+    case B200RT_KIND_TRIPRIM: return triprim_intersect(cx, (int)idx, ray, hit, culling);
+    case B200RT_KIND_LIGHTINST:
+    case B200RT_KIND_INSTANCE: return instance_intersect(cx, (int)idx, box, ray, hit, culling);
     default: return 0;
   }
 }
@@ -406,7 +450,9 @@ static int scene_intersect(const Ctx* cx, const Ray* ray, Hit* hit) {
     return hit->valid;
   }
   if (d->root == B200RT_REF_NONE) return 0;
-  return shape_intersect(cx, d->root, d->root_box, ray, hit);
+  hit->light = -1; hit->texture = -1;
+  /* HW7: `bvh->intersect(ray, hit_data, true)` — culling on for every ray type (HW7/src/Scene.cpp:170,286) */
+  return shape_intersect(cx, d->root, d->root_box, ray, hit, 1);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -591,6 +637,556 @@ static v3 trace_ray(const Ctx* cx, const Ray* ray, int depth, uint32_t key, int 
   return color;
 }
 
+/* ======================================================================== */
+/* HW4..HW7: textures, Perlin noise, BRDFs, light sources, path tracing       */
+/* ======================================================================== */
+static inline float texel(const B200SceneDesc* d, const b200rt_texture* T, long i) {
+  const long n = (long)T->width * T->height * 3;
+  if (i < 0 || i >= n) return 0.0f; /* the reference reads past the image here (UB); defined as 0 */
+  return d->texels[T->texel_offset + i];
+}
+/* Texture::get_color_at — HW7/src/Texture.cpp:66-143 */
+static v3 tex_color(const B200SceneDesc* d, const b200rt_texture* T, float u, float v) {
+  const int W = T->width, H = T->height;
+  if (T->appearance == B200RT_TEX_CLAMP) {
+    u = fmaxf(0.0f, fminf(1.0f, u));
+    v = fmaxf(0.0f, fminf(1.0f, v));
+  } else {
+    u = fmaxf(0.0f, fminf(1.0f, u - floorf(u)));
+    v = fmaxf(0.0f, fminf(1.0f, v - floorf(v)));
+  }
+  u *= W;
+  if (u >= W) u--;
+  v *= H;
+  if (v >= H) v--;
+  v3 c;
+  if (T->interp == B200RT_TEX_NEAREST) {
+    const long coord = 3L * W * (unsigned int)v + 3L * (unsigned int)u;
+    return V(texel(d, T, coord), texel(d, T, coord + 1), texel(d, T, coord + 2));
+  }
+  if (T->appearance == B200RT_TEX_REPEAT) {
+    const unsigned int p = ((unsigned int)u) % (unsigned)W, pn = (p + 1) % (unsigned)W;
+    const unsigned int q = ((unsigned int)v) % (unsigned)H, qn = (q + 1) % (unsigned)H;
+    const float dx = u - p, dy = v - q;
+    const long c_p_q = 3L * (W * q + p), c_pn_q = 3L * (W * q + pn), c_p_qn = 3L * (W * qn + p),
+               c_pn_qn = 3L * (W * qn + pn);
+    float* cc = &c.x;
+    for (int k = 0; k < 3; k++) {
+      float x = texel(d, T, c_p_q + k) * (1 - dx) * (1 - dy);
+      x += texel(d, T, c_pn_q + k) * (dx) * (1 - dy);
+      x += texel(d, T, c_pn_qn + k) * (dx) * (dy);
+      x += texel(d, T, c_p_qn + k) * (1 - dx) * (dy);
+      if (k == 0) c.x = x; else if (k == 1) c.y = x; else c.z = x;
+    }
+    (void)cc;
+    return c;
+  }
+  {
+    const unsigned int p = (unsigned int)u, pn = p + 1;
+    const unsigned int q = (unsigned int)v, qn = (unsigned int)(v + 1);
+    const float dx = u - p, dy = v - q;
+    const long c_p_q = 3L * ((long)W * q + p), c_pn_q = 3L * ((long)W * q + pn), c_p_qn = 3L * ((long)W * qn + p),
+               c_pn_qn = 3L * ((long)W * qn + pn);
+    for (int k = 0; k < 3; k++) {
+      float x = texel(d, T, c_p_q + k) * (1 - dx) * (1 - dy);
+      if (pn < (unsigned)W) x += texel(d, T, c_pn_q + k) * (dx) * (1 - dy);
+      if (qn < (unsigned)H) x += texel(d, T, c_pn_qn + k) * (dx) * (dy);       /* crossed guards: Appendix B.4 */
+      if (pn < (unsigned)W && qn < (unsigned)H) x += texel(d, T, c_p_qn + k) * (1 - dx) * (dy);
+      if (k == 0) c.x = x; else if (k == 1) c.y = x; else c.z = x;
+    }
+    return c;
+  }
+}
+/* Texture::blend_color — HW7/src/Texture.cpp:53-65 */
+static v3 tex_blend(const b200rt_texture* T, v3 tc, v3 kd) {
+  if (T->decal == B200RT_TEX_REPLACE_KD) return tc;
+  if (T->decal == B200RT_TEX_BLEND_KD) return divs(add(tc, kd), 2.0f);
+  return V(0, 0, 0);
+}
+/* Perlin_noise — HW7/src/Perlin_noise.cpp:23-62 */
+static const float kPerlinG[16][3] = {{1, 1, 0}, {-1, 1, 0}, {1, -1, 0}, {-1, -1, 0}, {1, 0, 1}, {-1, 0, 1},
+                                      {1, 0, -1}, {-1, 0, -1}, {0, 1, 1}, {0, -1, 1}, {0, 1, -1}, {0, -1, -1},
+                                      {1, 1, 0}, {-1, 1, 0}, {0, -1, 1}, {0, -1, -1}};
+static inline float perlin_weight(float x) {
+  const double a = fabs((double)x);
+  return (float)(-6 * pow(a, 5) + 15 * pow(a, 4) + -10 * pow(a, 3) + 1);
+}
+static float perlin_value(const b200rt_texture* T, v3 pos) {
+  const v3 sp = muls(pos, T->scaling);
+  float value = 0.0f;
+  const int x = (int)floorf(sp.x), y = (int)floorf(sp.y), z = (int)floorf(sp.z);
+  for (int i = x; i <= x + 1; i++)
+    for (int j = y; j <= y + 1; j++)
+      for (int k = z; k <= z + 1; k++) {
+        const v3 vv = V(sp.x - i, sp.y - j, sp.z - k);
+        int a = i % 16, b = j % 16, c = k % 16;
+        if (a < 0) a += 16;
+        if (b < 0) b += 16;
+        if (c < 0) c += 16;
+        const float* g = kPerlinG[T->perm[(a + T->perm[(b + T->perm[c % 16]) % 16]) % 16]];
+        const v3 e = V(g[0], g[1], g[2]);
+        const float wx = perlin_weight(vv.x), wy = perlin_weight(vv.y), wz = perlin_weight(vv.z);
+        value += dot(e, vv) * wx * wy * wz;
+      }
+  if (T->appearance == B200RT_TEX_VEIN) return fabsf(value);
+  return (value + 1.0f) / 2.0f;
+}
+/* Texture::bump_normal (Perlin) — HW7/src/Texture.cpp:145-165 */
+static v3 bump_perlin(const b200rt_texture* T, v3 normal, v3 pos) {
+  const float pv = perlin_value(T, pos);
+  const float epsilon = 0.001;
+  const float dx = (perlin_value(T, add(pos, V(epsilon, 0, 0))) - pv) / epsilon;
+  const float dy = (perlin_value(T, add(pos, V(0, epsilon, 0))) - pv) / epsilon;
+  const float dz = (perlin_value(T, add(pos, V(0, 0, epsilon))) - pv) / epsilon;
+  const v3 g = muls(V(dx, dy, dz), T->bump_multiplier);
+  const v3 g_ii = muls(normal, dot(g, normal));
+  return sub(normal, sub(g, g_ii));
+}
+/* Texture::bump_normal (image) — HW7/src/Texture.cpp:167-181 */
+static v3 bump_image(const B200SceneDesc* d, const b200rt_texture* T, v3 dp_du, v3 dp_dv, v3 normal, float u, float v) {
+  const v3 c0 = tex_color(d, T, u, v);
+  const v3 cu = tex_color(d, T, u + 1.0f / T->width, v);
+  const v3 cv = tex_color(d, T, u, v + 1.0f / T->height);
+  const float v0 = (c0.x + c0.y + c0.z) / 3.0f, vu = (cu.x + cu.y + cu.z) / 3.0f, vv = (cv.x + cv.y + cv.z) / 3.0f;
+  const float dd_du = (vu - v0) * T->bump_multiplier, dd_dv = (vv - v0) * T->bump_multiplier;
+  const v3 dq_du = add(dp_du, muls(normal, dd_du));
+  const v3 dq_dv = add(dp_dv, muls(normal, dd_dv));
+  return normalize(cross(dq_dv, dq_du));
+}
+/* texture part of Mesh_triangle::intersect — HW7/src/Mesh_triangle.cpp:107-149 */
+static void tex_surface_tri(const B200SceneDesc* d, int tri, float beta, float gamma, v3 local_p, Hit* hit) {
+  const b200rt_texture* T = d->textures + d->tri_tex[tri];
+  if (T->kind == B200RT_TEX_PERLIN) {
+    hit->perlin = perlin_value(T, local_p);
+    if (T->is_bump) hit->normal = bump_perlin(T, hit->normal, local_p);
+    return;
+  }
+  const float* uv = d->tri_uv + 6 * (size_t)tri;
+  const float u = uv[0] + beta * (uv[2] - uv[0]) + gamma * (uv[4] - uv[0]);
+  const float v = uv[1] + beta * (uv[3] - uv[1]) + gamma * (uv[5] - uv[1]);
+  hit->u = u; hit->v = v;
+  if (T->is_bump) {
+    const float ub_ua = uv[2] - uv[0], uc_ua = uv[4] - uv[0], vb_va = uv[3] - uv[1], vc_va = uv[5] - uv[1];
+    const float* g = d->tri_geom + 12 * (size_t)tri;
+    /* p1 - p0 and p2 - p0 from the vertex positions themselves */
+    const int32_t* vi = d->tri_vidx + 3 * (size_t)tri;
+    const v3 p0 = ld(d->vert_pos + 3 * (size_t)vi[0]), p1 = ld(d->vert_pos + 3 * (size_t)vi[1]),
+             p2 = ld(d->vert_pos + 3 * (size_t)vi[2]);
+    (void)g;
+    const v3 pb_pa = sub(p1, p0), pc_pa = sub(p2, p0);
+    float ic = (ub_ua * vc_va) - (vb_va * uc_ua);
+    if (ic == 0.0f) ic = 0.000001f;
+    ic = 1.0f / ic;
+    const v3 dp_du = muls(sub(muls(pb_pa, vc_va), muls(pc_pa, vb_va)), ic);
+    const v3 dp_dv = muls(sub(muls(pc_pa, ub_ua), muls(pb_pa, uc_ua)), ic);
+    hit->normal = bump_image(d, T, dp_du, dp_dv, hit->normal, u, v);
+  }
+}
+/* texture part of Sphere::intersect + get_uv — HW7/src/Sphere.cpp:70-112 */
+static void tex_surface_sphere(const B200SceneDesc* d, const b200rt_sphere* s, v3 lc, v3 local_p, Hit* hit) {
+  const b200rt_texture* T = d->textures + s->texture;
+  const float theta = acosf(fmaxf(-1.0f, fminf(1.0f, lc.y / s->radius)));
+  const float phi = (float)atan2((double)lc.z, (double)lc.x); /* unqualified atan2: the double function */
+  const float u = (float)((M_PI - (double)phi) / (2 * M_PI));
+  const float v = (float)((double)theta / M_PI);
+  hit->u = u; hit->v = v;
+  if (T->kind == B200RT_TEX_PERLIN) {
+    hit->perlin = perlin_value(T, local_p);
+    if (T->is_bump) hit->normal = bump_perlin(T, hit->normal, local_p);
+  } else if (T->is_bump) {
+    const float th = (float)(M_PI * (double)v);
+    const float ph = (float)(M_PI * (double)(1 - 2 * u));
+    const v3 dp_du = V((float)((double)(lc.z * 2) * M_PI), 0, (float)((double)(lc.x * -2) * M_PI));
+    const v3 dp_dv = V((float)((double)lc.y * M_PI * cos((double)ph)), (float)((double)(-s->radius) * M_PI * sin((double)th)),
+                       (float)((double)lc.y * M_PI * sin((double)ph)));
+    hit->normal = bump_image(d, T, dp_du, dp_dv, hit->normal, u, v);
+  }
+}
+
+/* BRDF::get_reflectance ×5 — HW7/src/*_BRDF.cpp */
+static v3 brdf_eval(const b200rt_brdf* B, v3 normal, v3 kd, v3 ks, v3 w_i, v3 w_o) {
+  const float cti = dot(normal, w_i);
+  if (cti > 1.0f || cti <= 0.0f) return V(0, 0, 0);
+  const float e = B->exponent;
+  switch (B->kind) {
+    case B200RT_BRDF_PHONG: {
+      const v3 rwi = sub(muls(normal, 2 * cti), w_i);
+      const float car = fmaxf(0.0f, dot(w_o, rwi));
+      return add(divs(muls(ks, powf(car, e)), cti), kd);
+    }
+    case B200RT_BRDF_MODIFIED_PHONG: {
+      const v3 rwi = sub(muls(normal, 2 * cti), w_i);
+      const float car = fmaxf(0.0f, dot(w_o, rwi));
+      v3 k_d = kd, k_s = muls(ks, powf(car, e));
+      if (B->normalized) {
+        /* Vector3::operator/(float): the double divisor is converted to float first */
+        k_s = divs(muls(k_s, e + 2.0f), (float)(2.0f * M_PI));
+        k_d = divs(k_d, (float)M_PI);
+      }
+      return add(k_s, k_d);
+    }
+    case B200RT_BRDF_BLINN_PHONG: {
+      const v3 wh = normalize(add(w_i, w_o));
+      const float cah = dot(wh, normal);
+      return add(divs(muls(ks, powf(cah, e)), cti), kd);
+    }
+    case B200RT_BRDF_MODIFIED_BLINN_PHONG: {
+      const v3 wh = normalize(add(w_i, w_o));
+      const float cah = dot(wh, normal);
+      v3 k_d = kd, k_s = muls(ks, powf(cah, e));
+      if (B->normalized) {
+        k_d = divs(k_d, (float)M_PI);
+        k_s = divs(muls(k_s, e + 8.0f), (float)(8.0f * M_PI));
+      }
+      return add(k_s, k_d);
+    }
+    default: { /* Torrance–Sparrow */
+      const v3 wh = normalize(add(w_i, w_o));
+      const float ca = dot(wh, normal);
+      const float d_alpha = (float)((double)((e + 2) * powf(ca, e)) / (2.0f * M_PI));
+      const float cto = dot(w_o, normal);
+      const float cb = dot(w_o, wh);
+      float g = fminf(2 * ca * cto / cb, 2 * ca * cti / cb);
+      g = fminf(1.0f, g);
+      const float ri = B->refractive_index;
+      const float r0 = (float)(pow((double)(ri - 1.0f), 2) / pow((double)(ri + 1.0f), 2));
+      const float f_beta = (float)((double)r0 + (double)(1 - r0) * pow((double)(1 - cb), 5));
+      const v3 k_d = divs(kd, (float)M_PI);
+      const v3 k_s = divs(muls(muls(muls(ks, d_alpha), f_beta), g), 4 * cti * cto);
+      return add(k_d, k_s);
+    }
+  }
+}
+
+/* ONB sample used by trace_path, the env light and the sphere light: w*cos(theta) + v*sin*cos(phi) + u*sin*sin(phi) */
+static v3 onb_dir(v3 w, float theta, float phi) {
+  const v3 u = normalize((w.x != 0.0f || w.y != 0.0f) ? V(-w.y, w.x, 0.0f) : V(0.0f, 1.0f, 0.0f));
+  const v3 v = cross(w, u);
+  return normalize(add(add(muls(w, cosf(theta)), muls(muls(v, sinf(theta)), cosf(phi))), muls(muls(u, sinf(theta)), sinf(phi))));
+}
+
+static int sphere_intersect(const Ctx* cx, int idx, const Ray* ray, Hit* hit);
+
+/* Light::direction_and_distance — HW7/src/{Point,Area,Spot,Directional,Spherical_directional}_light.cpp,
+ * Light_mesh.cpp:3-49, Light_sphere.cpp:5-55.  RNG: dims 32+4*li+{0,1,2} of the vertex key. */
+static v3 light_dir(const Ctx* cx, int li, v3 p, v3 normal, uint32_t key, float* distance, float* prob) {
+  const B200SceneDesc* d = cx->d;
+  const b200rt_light* L = d->lights + li;
+  const uint32_t dim = 32u + 4u * (uint32_t)li;
+  *prob = 0.0f;
+  switch (L->kind) {
+    case B200RT_LIGHT_AREA: {
+      const float e1 = rng_u01(key, dim), e2 = rng_u01(key, dim + 1);
+      const v3 pos = add(add(ld(L->position), muls(ld(L->edge1), e1)), muls(ld(L->edge2), e2));
+      const v3 dir = sub(pos, p);
+      *distance = len(dir);
+      return dir;
+    }
+    case B200RT_LIGHT_DIRECTIONAL:
+      *distance = 3.402823466e+38f;
+      return neg(ld(L->edge1));
+    case B200RT_LIGHT_ENV: {
+      const float e1 = rng_u01(key, dim), e2 = rng_u01(key, dim + 1);
+      const float phi = (float)(2 * M_PI * (double)e1);
+      const float theta = acosf(e2);
+      *distance = 3.402823466e+38f;
+      *prob = (float)(1.0f / (2.0f * M_PI));
+      return onb_dir(normal, theta, phi);
+    }
+    case B200RT_LIGHT_MESH: {
+      const float e0 = rng_u01(key, dim), e1 = sqrtf(rng_u01(key, dim + 1)), e2 = rng_u01(key, dim + 2);
+      int tri = -1;
+      for (int i = 0; i < L->cdf_count; i++)
+        if (e0 <= d->light_cdf[L->cdf_begin + i]) { tri = d->light_tri[L->cdf_begin + i]; break; }
+      if (tri < 0) tri = d->light_tri[L->cdf_begin + L->cdf_count - 1]; /* reference dereferences NULL here */
+      const int32_t* vi = d->tri_vidx + 3 * (size_t)tri;
+      const v3 p0 = ld(d->vert_pos + 3 * (size_t)vi[0]), p1 = ld(d->vert_pos + 3 * (size_t)vi[1]),
+               p2 = ld(d->vert_pos + 3 * (size_t)vi[2]);
+      const v3 q = add(muls(p1, 1.0f - e2), muls(p2, e2));
+      const v3 po = add(muls(p0, 1.0f - e1), muls(q, e1));
+      const b200rt_instance* in = d->instances + L->object;
+      const v3 pw = xf_point(in->fwd, po);
+      const v3 dir = sub(pw, p);
+      *distance = len(dir);
+      const float cti = fmaxf(0.001f, -dot(normalize(dir), ld(d->tri_geom + 12 * (size_t)tri + 9)));
+      *prob = *distance * *distance / (L->total_area * cti);
+      return dir;
+    }
+    case B200RT_LIGHT_SPHERE: {
+      const float e1 = rng_u01(key, dim), e2 = rng_u01(key, dim + 1);
+      const b200rt_sphere* s = d->spheres + L->object;
+      const v3 ps = xf_point(s->inv, p);
+      v3 w = sub(ld(s->center), ps);
+      const float dd = len(w);
+      w = normalize(w);
+      const float stm = fmaxf(-1.0f, fminf(1.0f, s->radius / dd));
+      const float tmax = asinf(stm);
+      const float ctm = cosf(tmax);
+      const float phi = (float)(2 * M_PI * (double)e1);
+      const float theta = acosf(fmaxf(-1.0f, fminf(1.0f, 1 - e2 + e2 * ctm)));
+      const v3 lo = onb_dir(w, theta, phi);
+      const v3 lw = normalize(xf_vector(s->fwd, 4, lo));
+      Ray r; memset(&r, 0, sizeof(r));
+      r.o = add(p, muls(lw, d->shadow_eps)); r.d = lw;
+      Hit h; memset(&h, 0, sizeof(h)); h.t = INFINITY;
+      OracleCounters dummy; memset(&dummy, 0, sizeof(dummy));
+      Ctx c2 = {d, &dummy};
+      sphere_intersect(&c2, L->object, &r, &h);
+      *distance = h.t;
+      *prob = (float)(1 / (2 * M_PI * (double)(1 - ctm)));
+      return lw;
+    }
+    default: { /* point, spot */
+      const v3 dir = sub(ld(L->position), p);
+      *distance = len(dir);
+      return dir;
+    }
+  }
+}
+/* Light::incoming_radiance */
+static v3 light_radiance(const B200SceneDesc* d, int li, v3 to_light, float prob) {
+  const b200rt_light* L = d->lights + li;
+  const float x = to_light.x, y = to_light.y, z = to_light.z;
+  switch (L->kind) {
+    case B200RT_LIGHT_POINT: return divs(ld(L->intensity), x * x + y * y + z * z);
+    case B200RT_LIGHT_AREA: {
+      const v3 rw = neg(normalize(to_light));
+      return divs(muls(ld(L->intensity), dot(rw, ld(L->normal))), x * x + y * y + z * z);
+    }
+    case B200RT_LIGHT_SPOT: {
+      const v3 rw = neg(normalize(to_light));
+      const float ct = dot(rw, ld(L->edge1));
+      const float ccov = L->edge2[0], cfall = L->edge2[1];
+      if (ct > cfall) return divs(ld(L->intensity), x * x + y * y + z * z);
+      if (ct < ccov) return V(0, 0, 0);
+      const float c = (ct - ccov) / (cfall - ccov);
+      return divs(muls(ld(L->intensity), (float)pow((double)c, 4)), x * x + y * y + z * z);
+    }
+    case B200RT_LIGHT_DIRECTIONAL: return ld(L->intensity);
+    case B200RT_LIGHT_ENV: {
+      const b200rt_texture* T = d->textures + L->object;
+      const float theta = acosf(fminf(1.0f, fmaxf(-1.0f, y))); /* clamp(-1,1,cos) with the swapped-argument helper */
+      const float phi = atan2f(z, x);
+      float u = (float)((M_PI - (double)phi) / (2.0f * M_PI));
+      float v = (float)((double)theta / M_PI);
+      u = fmaxf(0.0f, fminf(1.0f, u));
+      v = fmaxf(0.0f, fminf(1.0f, v));
+      u *= T->width;
+      if (u >= T->width) u--;
+      v *= T->height;
+      if (v >= T->height) v--;
+      const long coord = 3L * T->width * (unsigned int)v + 3L * (unsigned int)u;
+      return divs(V(texel(d, T, coord), texel(d, T, coord + 1), texel(d, T, coord + 2)), prob);
+    }
+    default: return divs(ld(L->intensity), prob); /* mesh, sphere */
+  }
+}
+
+#include <stdio.h>
+static int g_dbg = 0;
+static v3 send_ray7(const Ctx* cx, const Ray* ray, int level, uint32_t key, int count_as);
+
+/* Scene::calculate_diffuse_constant — HW7/src/Scene.cpp:231-258 */
+static int diffuse_constant7(const B200SceneDesc* d, const Hit* hit, v3* out) {
+  const b200rt_material* m = d->materials + hit->material;
+  *out = ld(m->diffuse);
+  if (hit->texture < 0) return 0;
+  const b200rt_texture* T = d->textures + hit->texture;
+  if (T->decal == B200RT_TEX_REPLACE_ALL) {
+    *out = (T->kind == B200RT_TEX_PERLIN) ? V(0, 0, 0) : tex_color(d, T, hit->u, hit->v);
+    return 1;
+  }
+  if (T->kind == B200RT_TEX_PERLIN) *out = tex_blend(T, V(hit->perlin, hit->perlin, hit->perlin), *out);
+  else *out = tex_blend(T, divs(tex_color(d, T, hit->u, hit->v), T->normalizer), *out);
+  return 0;
+}
+/* Scene::calculate_diffuse_and_specular_radiance — HW7/src/Scene.cpp:260-311 */
+static v3 direct7(const Ctx* cx, const Ray* ray, const Hit* hit, v3 kd, uint32_t key) {
+  const B200SceneDesc* d = cx->d;
+  v3 radiance = V(0, 0, 0);
+  const v3 p = add(ray->o, muls(ray->d, hit->t));
+  const b200rt_material* m = d->materials + hit->material;
+  const v3 w_o = normalize(sub(ray->o, p));
+  const v3 n = hit->normal;
+  const b200rt_brdf* B = (m->brdf != -1) ? d->brdfs + m->brdf : NULL;
+  for (int li = 0; li < d->n_lights; li++) {
+    float ldist, prob;
+    const v3 lvec = light_dir(cx, li, p, n, key, &ldist, &prob);
+    const v3 w_i = normalize(lvec);
+    if (dot(n, w_i) >= 0.0f) {
+      Ray sr; memset(&sr, 0, sizeof(sr));
+      sr.o = add(p, muls(w_i, d->shadow_eps)); sr.d = w_i; sr.time = ray->time; sr.is_shadow = 1;
+      cx->c->rays_shadow++;
+      Hit sh;
+      scene_intersect(cx, &sr, &sh);
+      if (g_dbg) fprintf(stderr, "[oracle]     light %d ldist %.9g sh.t %.9g limit %.9g wi %.9g %.9g %.9g so %.9g %.9g %.9g p %.9g %.9g %.9g\n", li, ldist, sh.t,
+                         ldist - d->shadow_eps, w_i.x, w_i.y, w_i.z, sr.o.x, sr.o.y, sr.o.z, p.x, p.y, p.z);
+      if (sh.t < (ldist - d->shadow_eps) && sh.t > 0.0f) continue;
+      const v3 Li = light_radiance(d, li, lvec, prob);
+      const float cti = fmaxf(0.0f, dot(n, w_i));
+      if (B) {
+        radiance = add(radiance, mulv(muls(Li, cti), brdf_eval(B, n, kd, ld(m->specular), w_i, w_o)));
+      } else {
+        radiance = add(radiance, muls(mulv(kd, Li), cti));
+        const float sct = fmaxf(0.0f, dot(n, normalize(add(w_o, w_i))));
+        radiance = add(radiance, muls(mulv(ld(m->specular), Li), (float)pow((double)sct, (double)m->phong_exponent)));
+      }
+    }
+  }
+  return radiance;
+}
+/* Scene::reflect_ray — HW7/src/Scene.cpp:191-229 */
+static v3 reflect7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, uint32_t key) {
+  const B200SceneDesc* d = cx->d;
+  const b200rt_material* m = d->materials + hit->material;
+  const v3 n = hit->normal;
+  const v3 p = add(ray->o, muls(ray->d, hit->t));
+  const v3 w_o = normalize(sub(ray->o, p));
+  const v3 wr = normalize(sub(muls(n, 2 * dot(n, w_o)), w_o));
+  Ray mr; memset(&mr, 0, sizeof(mr));
+  mr.time = ray->time;
+  if (m->roughness == 0.0f) {
+    mr.o = add(p, muls(wr, d->shadow_eps)); mr.d = wr;   /* light_hit NOT propagated here */
+  } else {
+    v3 rp;
+    if (wr.x < wr.y && wr.x < wr.z) rp = V(1.0f, wr.y, wr.z);
+    else if (wr.y < wr.z && wr.y < wr.x) rp = V(wr.x, 1.0f, wr.z);
+    else rp = V(wr.x, wr.y, 1.0f);
+    const v3 u = normalize(cross(rp, wr));
+    const v3 v = normalize(cross(u, wr));
+    const float eu = rng_u01(key, 2) - 0.5f, ev = rng_u01(key, 3) - 0.5f;
+    const v3 wrp = normalize(add(wr, muls(add(muls(u, eu), muls(v, ev)), m->roughness)));
+    mr.o = add(p, muls(wrp, d->shadow_eps)); mr.d = wrp;
+    mr.light_hit = ray->light_hit;
+  }
+  return send_ray7(cx, &mr, level + 1, rng_mix(key, 0x101u), 1);
+}
+/* Scene::refract_ray — HW7/src/Scene.cpp:108-166 */
+static v3 refract7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, uint32_t key) {
+  const B200SceneDesc* d = cx->d;
+  const b200rt_material* m = d->materials + hit->material;
+  const v3 n = hit->normal;
+  const v3 p = add(ray->o, muls(ray->d, hit->t));
+  const v3 w_o = normalize(sub(ray->o, p));
+  const v3 wr = normalize(sub(muls(n, 2 * dot(n, w_o)), w_o));
+  v3 tdir = V(0, 0, 0), k = V(0, 0, 0);
+  float cos_theta = 0.0f;
+  const v3 dn = normalize(ray->d);
+  const float ni = m->refraction_index;
+  int tir = 0, entering;
+  if (dot(dn, n) < 0.0f) {
+    refract_ray(dn, n, ni, &tdir);
+    cos_theta = dot(neg(dn), n);
+    k = V(1.0f, 1.0f, 1.0f);
+    entering = 1;
+  } else {
+    const v3 kt = ld(m->transparency);
+    const float ht = hit->t;
+    k = V((float)exp(log((double)kt.x) * (double)ht), (float)exp(log((double)kt.y) * (double)ht),
+          (float)exp(log((double)kt.z) * (double)ht));
+    entering = 0;
+    if (refract_ray(dn, neg(n), 1.0f / ni, &tdir)) cos_theta = dot(tdir, n);
+    else tir = 1;
+  }
+  Ray rr; memset(&rr, 0, sizeof(rr));
+  rr.o = add(p, muls(wr, d->shadow_eps)); rr.d = wr; rr.time = ray->time; rr.light_hit = ray->light_hit;
+  if (tir) {
+    rr.in_medium = 1;
+    return mulv(k, send_ray7(cx, &rr, level + 1, rng_mix(key, 0x102u), 1));
+  }
+  const float r0 = ((ni - 1) * (ni - 1)) / ((ni + 1) * (ni + 1));
+  const float r = (float)((double)r0 + (double)(1 - r0) * pow((double)(1.0f - cos_theta), 5.0));
+  rr.in_medium = !entering;
+  Ray tr; memset(&tr, 0, sizeof(tr));
+  tr.o = add(p, muls(tdir, d->shadow_eps)); tr.d = tdir; tr.time = ray->time; tr.in_medium = entering;
+  tr.light_hit = ray->light_hit;
+  const v3 cr = send_ray7(cx, &rr, level + 1, rng_mix(key, 0x102u), 1);
+  const v3 ct = send_ray7(cx, &tr, level + 1, rng_mix(key, 0x103u), 1);
+  return mulv(k, add(muls(cr, r), muls(ct, 1 - r)));
+}
+/* Scene::trace_ray — HW7/src/Scene.cpp:415-447 */
+static v3 trace_ray7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, uint32_t key) {
+  const B200SceneDesc* d = cx->d;
+  v3 radiance = V(0, 0, 0);
+  if (hit->light >= 0) return ld(d->lights[hit->light].intensity);
+  const b200rt_material* m = d->materials + hit->material;
+  v3 kd;
+  if (diffuse_constant7(d, hit, &kd)) return kd;
+  if (!ray->in_medium) {
+    radiance = add(radiance, mulv(ld(m->ambient), ld(d->ambient)));
+    radiance = add(radiance, direct7(cx, ray, hit, kd, key));
+  }
+  if (!is_zero(ld(m->mirror)) && level < d->max_depth)
+    radiance = add(radiance, mulv(ld(m->mirror), reflect7(cx, ray, hit, level, key)));
+  if (!is_zero(ld(m->transparency)) && level < d->max_depth)
+    radiance = add(radiance, refract7(cx, ray, hit, level, key));
+  return radiance;
+}
+/* Scene::trace_path — HW7/src/Scene.cpp:312-414 */
+#include <stdio.h>
+static v3 trace_path7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, uint32_t key) {
+  const B200SceneDesc* d = cx->d;
+  v3 radiance = V(0, 0, 0);
+  if (g_dbg) fprintf(stderr, "[oracle] level %d key %08x hit rank %d tri %d t %.9g light %d lh %d n %.6f %.6f %.6f\n", level, key,
+                     hit->top_rank, hit->tri, hit->t, hit->light, ray->light_hit, hit->normal.x, hit->normal.y, hit->normal.z);
+  if (hit->light >= 0) return ray->light_hit ? radiance : ld(d->lights[hit->light].intensity);
+  Ray ray_copy = *ray;
+  v3 kd, direct = V(0, 0, 0);
+  diffuse_constant7(d, hit, &kd);
+  if (!ray->in_medium) direct = direct7(cx, ray, hit, kd, key);
+  if (!is_zero(direct)) { ray_copy.light_hit = 1; radiance = add(radiance, direct); }
+  if (g_dbg) fprintf(stderr, "[oracle]   direct %.6f %.6f %.6f\n", direct.x, direct.y, direct.z);
+  const b200rt_material* m = d->materials + hit->material;
+  const b200rt_brdf* B = (m->brdf != -1) ? d->brdfs + m->brdf : NULL;
+  if (!ray->in_medium && level < d->max_depth) {
+    const v3 p = add(ray->o, muls(ray->d, hit->t));
+    const float e1 = rng_u01(key, 9), e2 = rng_u01(key, 10);
+    const float phi = (float)(2 * M_PI * (double)e1);
+    const float theta = d->importance_sampling ? asinf(sqrtf(e2)) : acosf(e2);
+    const v3 n = hit->normal;
+    const v3 w_i = onb_dir(n, theta, phi);
+    const float cti = fmaxf(0.0f, dot(n, w_i));
+    const v3 w_o = normalize(sub(ray->o, p));
+    Ray sr; memset(&sr, 0, sizeof(sr));
+    sr.o = add(p, muls(w_i, d->shadow_eps)); sr.d = w_i; sr.time = ray->time;
+    sr.in_medium = ray->in_medium; sr.light_hit = ray->light_hit;
+    const v3 Li = send_ray7(cx, &sr, level + 1, rng_mix(key, 0x104u), 1);
+    if (g_dbg) fprintf(stderr, "[oracle]   level %d sample Li %.6f %.6f %.6f cti %.6f wi %.6f %.6f %.6f\n", level, Li.x, Li.y, Li.z, cti, w_i.x, w_i.y, w_i.z);
+    const float prob = d->importance_sampling ? (float)((double)cti / M_PI) : (float)(1.0f / (2 * M_PI));
+    if (prob != 0.0f) {
+      if (B) {
+        radiance = add(radiance, divs(mulv(muls(Li, cti), brdf_eval(B, n, kd, ld(m->specular), w_i, w_o)), prob));
+      } else {
+        radiance = add(radiance, divs(muls(mulv(kd, Li), cti), prob));
+        const float sct = fmaxf(0.0f, dot(n, normalize(add(w_o, w_i))));
+        radiance = add(radiance, divs(muls(mulv(ld(m->specular), Li), (float)pow((double)sct, (double)m->phong_exponent)), prob));
+      }
+    }
+  }
+  if (!is_zero(ld(m->mirror)) && level < d->max_depth)
+    radiance = add(radiance, mulv(ld(m->mirror), reflect7(cx, &ray_copy, hit, level, key)));
+  if (!is_zero(ld(m->transparency)) && level < d->max_depth)
+    radiance = add(radiance, refract7(cx, &ray_copy, hit, level, key));
+  return radiance;
+}
+/* Scene::send_ray — HW7/src/Scene.cpp:168-189 */
+static v3 send_ray7(const Ctx* cx, const Ray* ray, int level, uint32_t key, int count_as) {
+  const B200SceneDesc* d = cx->d;
+  if (count_as == 0) cx->c->rays_primary++; else cx->c->rays_secondary++;
+  Hit hit;
+  if (!scene_intersect(cx, ray, &hit)) {
+    if (ray->primary) {
+      if (d->background_texture >= 0) return tex_color(d, d->textures + d->background_texture, ray->bg_u, ray->bg_v);
+      if (d->env_light >= 0) return light_radiance(d, d->env_light, ray->d, 1.0f);
+      return ld(d->background);
+    }
+    if (d->env_light >= 0) return light_radiance(d, d->env_light, ray->d, 1.0f);
+    return V(0, 0, 0);
+  }
+  if (!d->integrator) return trace_ray7(cx, ray, &hit, level, key);
+  return trace_path7(cx, ray, &hit, level, key);
+}
+
 /* Camera::calculate_ray_at — HW1/Camera.h:24-32, HW3/include/Camera.h:35-47 */
 static Ray camera_ray(const B200SceneDesc* d, const b200rt_camera* c, float x, float y, int use_dof,
                       float ex, float ey, float time) {
@@ -604,7 +1200,13 @@ static Ray camera_ray(const B200SceneDesc* d, const b200rt_camera* c, float x, f
     r.o = e; r.d = sub(s, e);
     return r;
   }
-  const v3 s = sub(add(ld(c->top_left), muls(ld(c->su), x + 0.5f)), muls(ld(c->sv), y + 0.5f));
+  /* HW4..HW7 callers pass the absolute sample position (HW7/include/Camera.h:66-84): x_off = 0 */
+  const float off = (d->semantics >= B200RT_SEM_HW4) ? 0.0f : 0.5f;
+  const v3 s = (d->semantics >= B200RT_SEM_HW4)
+                   ? sub(add(ld(c->top_left), muls(ld(c->su), x)), muls(ld(c->sv), y))
+                   : sub(add(ld(c->top_left), muls(ld(c->su), x + off)), muls(ld(c->sv), y + off));
+  r.primary = 1;
+  r.bg_u = x / c->width; r.bg_v = y / c->height;
   if (use_dof) {
     const v3 ne = add(e, muls(muls(add(muls(u, ex), muls(v, ey)), c->aperture), 0.5f));
     r.o = ne; r.d = normalize(sub(s, ne));
@@ -637,12 +1239,37 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
   {
     OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
     Ctx cx = {d, &cnt};
+    const int hw7 = sem_hw7(d);
 #pragma omp for schedule(dynamic, 4)
     for (int j = row_begin; j < row_end; j++) {
       for (int i = 0; i < W; i++) {
         const int pix = j * W + i;
+        if (hw7 && ns > 1 && rgbw) {
+          /* HW7/src/Scene.cpp:35-85: strata loop, box filter (GAUSSIAN_FILTER is off) */
+          float acc[4] = {0, 0, 0, 0};
+          for (int x = 0; x < ns; x++)
+            for (int y = 0; y < ns; y++) {
+              const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), (uint32_t)(x * ns + y));
+              const float ex = rng_u01(key, 4), ey = rng_u01(key, 5);
+              const float sx = (x + ex) / ns, sy = (y + ey) / ns;
+              const float time = rng_u01(key, 6);
+              Ray r;
+              if (c->aperture == 0.0f) {
+                r = camera_ray(d, c, i + sx, j + sy, 0, 0, 0, time);
+              } else {
+                const float dx = rng_u01(key, 7) * 2.0f - 1.0f, dy = rng_u01(key, 8) * 2.0f - 1.0f;
+                r = camera_ray(d, c, i + sx, j + sy, 1, dx, dy, time);
+              }
+              const v3 col = send_ray7(&cx, &r, 0, key, 0);
+              acc[0] += col.x * 1.0f; acc[1] += col.y * 1.0f; acc[2] += col.z * 1.0f; acc[3] += 1.0f;
+            }
+          memcpy(rgbw + 4 * (size_t)pix, acc, sizeof(acc));
+          continue;
+        }
         if (ns == 1) {
-          Ray r = camera_ray(d, c, (float)i, (float)j, 0, 0, 0, 0.0f);
+          { const char* e = getenv("ORACLE_DEBUG_PIX"); g_dbg = (e && atoi(e) == pix); }
+          Ray r = hw7 ? camera_ray(d, c, i + 0.5f, j + 0.5f, 0, 0, 0, 0.0f)
+                      : camera_ray(d, c, (float)i, (float)j, 0, 0, 0, 0.0f);
           if (ids || tout) {
             Hit h; OracleCounters dummy; memset(&dummy, 0, sizeof(dummy));
             Ctx c2 = {d, &dummy};
@@ -652,7 +1279,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
           }
           if (rgbw) {
             const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), 0u);
-            const v3 col = trace_ray(&cx, &r, d->max_depth, key, 0);
+            const v3 col = hw7 ? send_ray7(&cx, &r, 0, key, 0) : trace_ray(&cx, &r, d->max_depth, key, 0);
             rgbw[4 * pix] = col.x * 1.0f; rgbw[4 * pix + 1] = col.y * 1.0f;
             rgbw[4 * pix + 2] = col.z * 1.0f; rgbw[4 * pix + 3] = 1.0f;
           }
@@ -667,7 +1294,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
       total.instances_entered += cnt.instances_entered;
     }
   }
-  if (ns > 1 && rgbw) {
+  if (ns > 1 && rgbw && !sem_hw7(d)) {
     /* multi-sample path with the 3x3 Gaussian splat: sequential over pixels so
      * that the accumulation order is defined (the reference's is thread-racy). */
     OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));

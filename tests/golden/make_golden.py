@@ -21,11 +21,21 @@ CASES = {
     "cfg1_hw1_depth0": ("hw1", "cfg1_hw1", dict(width=64, height=48, depth=0, n_spheres=12)),
     "cfg2_hw3_n32": ("hw3", "cfg2_hw3", dict(n=32, width=160, height=90)),
     "cfg2_hw3_n48_smooth": ("hw3", "cfg2_hw3", dict(n=48, width=128, height=96, smooth=True, depth=3)),
+    # HW7 Whitted, every pixel deterministic: textures (nearest/bilinear, repeat/clamp, replace_kd/blend_kd,
+    # image bump), 5 BRDFs, point/spot/directional lights, mirror + glass, culling, instancing
+    "hw7_whitted_160": ("hw7", "hw7_scene", dict(width=160, height=120, light_scale=3.0)),
+    "hw7_whitted_depth1": ("hw7", "hw7_scene", dict(width=96, height=80, depth=1, n=8, light_scale=2.0, seed=801)),
 }
+
+
+ASSETS = os.path.join(HERE, "assets")   # texture images the HW7 scenes refer to (committed)
 
 
 def scene_xml(name):
     tree, gen, kw = CASES[name]
+    if gen == "hw7_scene":
+        os.makedirs(ASSETS, exist_ok=True)
+        return tree, getattr(scenes, gen)(ASSETS, **kw)
     return tree, getattr(scenes, gen)(**kw)
 
 
@@ -33,7 +43,7 @@ if __name__ == "__main__":
     meta = {}
     for name in CASES:
         tree, xml = scene_xml(name)
-        res = cpu.run_reference(tree, xml)
+        res = cpu.run_reference(tree, xml, workdir=ASSETS if CASES[name][1] == "hw7_scene" else None)
         img = list(res["images"].values())[0]
         image.write_png(os.path.join(HERE, name + ".png"), img)
         meta[name] = {"tree": tree, "shape": list(img.shape), "threads": res["threads"]}

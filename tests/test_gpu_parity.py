@@ -10,14 +10,14 @@ import pytest
 
 from ceng795_b200 import image, scene, scenes
 from oracle import cpu
-from tests.golden.make_golden import CASES, scene_xml
+from tests.golden.make_golden import ASSETS, CASES, scene_xml
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 pytestmark = pytest.mark.gpu
 
 
 def _render_pair(xml, tree, **opts):
-    sc = scene.Scene(xml, tree)
+    sc = scene.Scene(xml, tree, base_dir=ASSETS)
     rgbw, st = sc.render_image(0, **opts)
     o_rgbw, o_ids, o_t, cnt = cpu.render(sc.host, 0, want_ids=True)
     return sc, rgbw, st, o_rgbw, o_ids, o_t, cnt
@@ -39,7 +39,9 @@ def test_image_matches_golden_and_oracle(gpu, name):
     assert st.rays_secondary == cnt.rays_secondary
     # float accumulators: identical arithmetic order => (almost) all bits equal
     same = np.mean(rgbw.view(np.uint32) == o_rgbw.view(np.uint32))
-    assert same >= 0.999, same
+    # HW7 shading goes through powf / pow / acosf / atan2 (BRDFs, sphere uv, spot falloff): CUDA's libm and
+    # glibc differ by an ulp there, so fewer accumulators are bit-identical (the 8-bit image is still exact)
+    assert same >= (0.99 if tree == "hw7" else 0.999), same
 
 
 @pytest.mark.parametrize("name", ["cfg1_hw1_96", "cfg2_hw3_n32", "cfg2_hw3_n48_smooth"])
@@ -114,3 +116,49 @@ def test_full_size_cfg2_properties(gpu):
     cmp = image.compare_8bit(image.quantise(a[sl], sc.semantics), image.quantise(o_rgbw[sl], sc.semantics))
     assert cmp["within1"] >= 0.999, cmp
     assert st.rays_primary == 1920 * 1080
+
+
+# ---------------------------------------------------------------------------- HW7 stochastic
+def _hw7(tmp, **kw):
+    from ceng795_b200 import scenes as sc_
+    xml = sc_.hw7_scene(str(tmp), **kw)
+    return scene.Scene(xml, "hw7", base_dir=str(tmp))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(width=96, height=72, spp=4, depth=2, stochastic_lights=True, perlin=True, light_scale=2.0),          # Whitted, sampled lights
+    dict(width=80, height=60, spp=4, depth=3, stochastic_lights=True, perlin=True, path_tracing=True,
+         importance=True, light_scale=2.0),                                                                    # path tracing, cosine
+    dict(width=64, height=48, spp=1, depth=2, stochastic_lights=True, path_tracing=True, importance=False),  # uniform sampling
+])
+def test_hw7_stochastic_matches_oracle_with_matched_sampling(gpu, tmp_path, kw):
+    """Area / mesh / sphere lights, glossy mirror, Perlin (host-supplied table) and the branching path tracer:
+    the reference seeds its RNGs from the clock, so both arms draw from the shared counter-based stream
+    (key = pixel, sample, vertex, dimension).  Same rays => same integer bookkeeping; float images agree
+    up to libm ulps and the accumulation order of the samples of a pixel."""
+    sc = _hw7(tmp_path, **kw)
+    rgbw, st = sc.render_image(0, seed=1234)
+    o_rgbw, _, _, cnt = cpu.render(sc.host, 0, seed=1234)
+    a = rgbw[..., :3] / np.maximum(rgbw[..., 3:], 1)
+    b = o_rgbw[..., :3] / np.maximum(o_rgbw[..., 3:], 1)
+    rel = np.abs(a - b) / (np.abs(b) + 1.0)
+    if not kw.get("path_tracing"):
+        assert st.rays_primary == cnt.rays_primary
+        assert st.rays_secondary == cnt.rays_secondary
+        assert st.rays_shadow == cnt.rays_shadow
+        assert np.percentile(rel, 99.9) < 1e-3, float(np.percentile(rel, 99.9))   # tolerance: 1e-3 relative (+1 absolute floor)
+        cmp = image.compare_8bit(image.quantise(rgbw, sc.semantics), image.quantise(o_rgbw, sc.semantics))
+        assert cmp["within1"] >= 0.999, cmp
+    else:
+        # The hemisphere sample goes through acosf/asinf/sinf/cosf: CUDA's libm and glibc differ by an ulp, so a
+        # bounce direction can differ in its last bit.  That is invisible (1e-7) except where the reference itself
+        # is a rounding-level coin flip: its light-mesh shadow test compares the hit on the light (t = dist - eps up
+        # to rounding) with `t < dist - eps` (HW7/src/Scene.cpp:287-290).  So: the same camera paths, most pixels
+        # equal to 1e-3, and the images equal in the mean.
+        assert st.rays_primary == cnt.rays_primary
+        assert abs(st.rays_total - cnt.rays_total) <= 0.002 * cnt.rays_total
+        # (a flip changes one vertex of one sample; with several bounces x samples per pixel about a third of the
+        # pixels contain one)
+        assert np.median(rel) < 1e-5, float(np.median(rel))
+        assert np.mean(rel.max(-1) < 1e-3) >= 0.5, float(np.mean(rel.max(-1) < 1e-3))
+        assert abs(a.mean() - b.mean()) <= 0.01 * b.mean(), (float(a.mean()), float(b.mean()))
