@@ -142,6 +142,21 @@ class RenderStats(C.Structure):
         return self.rays_primary + self.rays_shadow + self.rays_secondary
 
 
+class PpmOpts(C.Structure):
+    _fields_ = [("photons", C.c_int64), ("first_photon", C.c_uint64), ("seed", C.c_uint64), ("pad", c_i * 4)]
+
+
+class PpmStats(C.Structure):
+    _fields_ = [("hit_points", C.c_uint64), ("grid_entries", C.c_uint64), ("photons", C.c_uint64),
+                ("photon_rays", C.c_uint64), ("cell_scans", C.c_uint64), ("deposits", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64),
+                ("ms_eye", c_f), ("ms_grid", c_f), ("ms_photon", c_f), ("ms_extend", c_f), ("ms_deposit", c_f),
+                ("ms_density", c_f), ("initial_radius", c_f), ("launches", c_i)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class B200RTError(RuntimeError):
     pass
 
@@ -208,6 +223,12 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_void_p, P(RenderStats)]),
         "b200rt_debug_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+        "b200rt_ppm_eye_pass": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, P(PpmStats)]),
+        "b200rt_ppm_trace_photons": (C.c_int, [C.c_void_p, P(PpmOpts), P(PpmStats)]),
+        "b200rt_ppm_density": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+        "b200rt_ppm_export": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_int64)]),
+        "b200rt_ppm_density_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+        "b200rt_ppm_get_hit_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, P(C.c_int64)]),
         "b200rt_scene_stream": (C.c_void_p, [C.c_void_p]),
         "b200rt_scene_bytes": (C.c_uint64, [C.c_void_p]),
         "b200rt_last_error": (C.c_char_p, []),

@@ -5,7 +5,9 @@
 #include <string>
 #include <vector>
 
-#include "rt_shade7.cuh"
+#include <cub/device/device_scan.cuh>
+
+#include "ppm_kernels.cuh"
 
 extern "C" void b200rt_internal_set_error(const char* msg);
 
@@ -54,6 +56,16 @@ struct b200rt_scene {
   cudaStream_t stream;
   cudaEvent_t ev[2];
   size_t scene_bytes;
+  // PPM state
+  HitPoints HP;
+  PpmGrid G;
+  PpmCounters* d_pc;
+  float* d_rtab;
+  float4* d_export;
+  void* d_scan_tmp;
+  size_t scan_tmp_bytes, items_capacity;
+  uint32_t n_hp;
+  int ppm_camera;
 };
 
 namespace {
@@ -317,9 +329,287 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
   return B200RT_OK;
 }
 
+void ppm_free(b200rt_scene* sc) {
+  HitPoints& H = sc->HP;
+  void* ptrs[] = {H.count, H.pos, H.nrm, H.wo, H.att, H.n, H.S, sc->G.cell_count, sc->G.cell_start, sc->G.items,
+                  sc->d_pc, sc->d_rtab, sc->d_export, sc->d_scan_tmp};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  memset(&sc->HP, 0, sizeof(HitPoints));
+  memset(&sc->G, 0, sizeof(PpmGrid));
+  sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
+  sc->scan_tmp_bytes = 0; sc->items_capacity = 0; sc->n_hp = 0;
+}
+
+int ppm_ensure_hit_points(b200rt_scene* sc, size_t cap) {
+  HitPoints& H = sc->HP;
+  if (H.capacity >= cap) return B200RT_OK;
+  void* ptrs[] = {H.pos, H.nrm, H.wo, H.att, H.n, H.S, sc->d_export};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (!H.count) CK(cudaMalloc((void**)&H.count, sizeof(unsigned int)));
+  CK(cudaMalloc((void**)&H.pos, cap * sizeof(float4)));
+  CK(cudaMalloc((void**)&H.nrm, cap * sizeof(float4)));
+  CK(cudaMalloc((void**)&H.wo, cap * sizeof(float4)));
+  CK(cudaMalloc((void**)&H.att, cap * sizeof(float4)));
+  CK(cudaMalloc((void**)&H.n, cap * sizeof(unsigned int)));
+  CK(cudaMalloc((void**)&H.S, cap * sizeof(float4)));
+  CK(cudaMalloc((void**)&sc->d_export, cap * sizeof(float4)));
+  H.capacity = (uint32_t)cap;
+  return B200RT_OK;
+}
+
+// R(n) table in the reference's own arithmetic (PPM/src/Scene.cpp:138-141): float product of
+// g = (float)((n*a + a) / (n*a + 1.0))
+int ppm_ensure_rtab(b200rt_scene* sc) {
+  if (sc->d_rtab) return B200RT_OK;
+  std::vector<float> r((size_t)PPM_RTAB);
+  float acc = 1.0f;
+  for (unsigned int n = 0; n < PPM_RTAB; n++) {
+    r[n] = acc;
+    const float g = (float)(((double)((float)n * PPM_ALPHA + PPM_ALPHA)) / ((double)((float)n * PPM_ALPHA) + 1.0));
+    acc = acc * g;
+  }
+  CK(cudaMalloc((void**)&sc->d_rtab, sizeof(float) * PPM_RTAB));
+  CK(cudaMemcpy(sc->d_rtab, r.data(), sizeof(float) * PPM_RTAB, cudaMemcpyHostToDevice));
+  return B200RT_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200PpmStats* stats) {
+  if (!sc || camera_index < 0 || camera_index >= (int)sc->cameras.size() || sc->S.semantics != B200RT_SEM_PPM) {
+    b200rt_internal_set_error("b200rt_ppm_eye_pass: needs a PPM scene and a valid camera index");
+    return B200RT_E_INVALID;
+  }
+  CK(cudaSetDevice(sc->device));
+  sc->S.cam = sc->cameras[camera_index];
+  sc->ppm_camera = camera_index;
+  const b200rt_camera& c = sc->S.cam;
+  if (sc->S.max_depth + 2 > kMaxWaves) return B200RT_E_UNSUPPORTED;
+  cudaStream_t st = sc->stream;
+  RenderParams R;
+  B200RenderOpts o;
+  memset(&o, 0, sizeof(o));
+  o.row_stride = 1; o.seed = seed;
+  if (resolve_rows(c, &o, &R) != B200RT_OK) return B200RT_E_INVALID;
+  const size_t paths = (size_t)c.width * c.height * R.sample_count;
+  R.n_paths = (uint32_t)paths;
+  // every glass vertex can fork: size for one fork per path and level, detect overflow otherwise
+  const size_t slots = paths * (size_t)(1 + (sc->has_transparency ? 2 * sc->S.max_depth : sc->S.max_depth)) + 1024;
+  if (slots > 0xF0000000ull) return B200RT_E_UNSUPPORTED;
+  int rc = ensure_pool(sc, slots, 1024);
+  if (rc) return rc;
+  rc = ppm_ensure_hit_points(sc, slots);
+  if (rc) return rc;
+  rc = ppm_ensure_rtab(sc);
+  if (rc) return rc;
+  if (!sc->d_pc) CK(cudaMalloc((void**)&sc->d_pc, sizeof(PpmCounters)));
+  PpmCounters hpc;
+  memset(&hpc, 0, sizeof(hpc));
+  for (int i = 0; i < 3; i++) { hpc.bbox[i] = 0xffffffffu; hpc.bbox[3 + i] = 0u; }
+  CK(cudaMemcpyAsync(sc->d_pc, &hpc, sizeof(hpc), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(sc->HP.count, 0, sizeof(unsigned int), st));
+  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
+  const int grid_p = sc->sm_count * (RT_FAST_MIN_BLOCKS > 8 ? RT_FAST_MIN_BLOCKS : 8);
+  int launches = 0;
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  cudaEventRecord(e0, st);
+  k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, R, sc->d_waves, sc->d_counters);
+  launches++;
+  for (int d = 0; d <= sc->S.max_depth; d++) {
+    k_next_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->d_counters);
+    k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    k_ppm_eye_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->d_waves, d, sc->HP, sc->d_counters, sc->d_pc);
+    k_finish_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->P, sc->d_counters);
+    launches += 4;
+  }
+  cudaEventRecord(e1, st);
+  CK(cudaStreamSynchronize(st));
+  Counters hc;
+  CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&hpc, sc->d_pc, sizeof(hpc), cudaMemcpyDeviceToHost));
+  unsigned int n_hp = 0;
+  CK(cudaMemcpy(&n_hp, sc->HP.count, sizeof(n_hp), cudaMemcpyDeviceToHost));
+  if (hc.overflow || n_hp > sc->HP.capacity) {
+    b200rt_internal_set_error("PPM eye pass: vertex pool / hit point overflow");
+    return B200RT_E_UNSUPPORTED;
+  }
+  sc->n_hp = n_hp;
+  // Scene::build_hash_grid — PPM/src/Scene.cpp:53-93 (host: the scalars; device: counting sort into CSR)
+  PpmGrid& G = sc->G;
+  const float* rtab = sc->d_rtab;
+  if (G.cell_count) cudaFree(G.cell_count);
+  if (G.cell_start) cudaFree(G.cell_start);
+  G.cell_count = nullptr; G.cell_start = nullptr;
+  G.rtab = rtab;
+  G.num_hash = n_hp;
+  float r0 = 0.f;
+  size_t entries = 0;
+  if (n_hp > 0) {
+    float mn[3], mx[3];
+    for (int i = 0; i < 3; i++) { mn[i] = ord2f_bits(hpc.bbox[i]); mx[i] = ord2f_bits(hpc.bbox[3 + i]); }
+    const float sx = mx[0] - mn[0], sy = mx[1] - mn[1], sz = mx[2] - mn[2];
+    r0 = ((sx + sy + sz) / 3.0f) / ((c.width + c.height) / 2.0f) * 2.0f * 4.0f;
+    G.r0 = r0; G.r0sq = r0 * r0;
+    G.bbox_min = mk3(mn[0] - r0, mn[1] - r0, mn[2] - r0);  // min_i fl(p_i - r0) == fl(min_i p_i - r0)
+    G.hash_scale = (float)(1.0 / ((double)r0 * 2.0));
+    CK(cudaMalloc((void**)&G.cell_count, sizeof(unsigned int) * ((size_t)n_hp + 1)));
+    CK(cudaMalloc((void**)&G.cell_start, sizeof(unsigned int) * ((size_t)n_hp + 1)));
+    CK(cudaMemsetAsync(G.cell_count, 0, sizeof(unsigned int) * ((size_t)n_hp + 1), st));
+    k_ppm_grid<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, G, n_hp, 0, 0, sc->d_pc);
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, G.cell_count, G.cell_start, (int)n_hp + 1, st);
+    if (need > sc->scan_tmp_bytes) {
+      if (sc->d_scan_tmp) cudaFree(sc->d_scan_tmp);
+      CK(cudaMalloc(&sc->d_scan_tmp, need));
+      sc->scan_tmp_bytes = need;
+    }
+    cub::DeviceScan::ExclusiveSum(sc->d_scan_tmp, need, G.cell_count, G.cell_start, (int)n_hp + 1, st);
+    unsigned int total = 0;
+    CK(cudaMemcpyAsync(&total, G.cell_start + n_hp, sizeof(total), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    entries = total;
+    if (entries > sc->items_capacity) {
+      if (G.items) cudaFree(G.items);
+      G.items = nullptr;
+      CK(cudaMalloc((void**)&G.items, sizeof(unsigned int) * (entries + 1)));
+      sc->items_capacity = entries + 1;
+    }
+    CK(cudaMemcpyAsync(G.cell_count, G.cell_start, sizeof(unsigned int) * ((size_t)n_hp + 1), cudaMemcpyDeviceToDevice, st));
+    k_ppm_grid<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, G, n_hp, 1, (uint32_t)sc->items_capacity, sc->d_pc);
+    launches += 4;
+  }
+  cudaEventRecord(e2, st);
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->hit_points = n_hp; stats->grid_entries = entries; stats->initial_radius = r0;
+    cudaEventElapsedTime(&stats->ms_eye, e0, e1);
+    cudaEventElapsedTime(&stats->ms_grid, e1, e2);
+    stats->launches = launches;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  return B200RT_OK;
+}
+
+int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmStats* stats) {
+  if (!sc || !opts || opts->photons < 0 || sc->S.semantics != B200RT_SEM_PPM || sc->ppm_camera < 0) {
+    b200rt_internal_set_error("b200rt_ppm_trace_photons: call b200rt_ppm_eye_pass on a PPM scene first");
+    return B200RT_E_INVALID;
+  }
+  if (sc->S.n_lights < 1) {
+    b200rt_internal_set_error("b200rt_ppm_trace_photons: the reference emits from lights[0]; the scene has no light");
+    return B200RT_E_INVALID;
+  }
+  CK(cudaSetDevice(sc->device));
+  cudaStream_t st = sc->stream;
+  const size_t batch = (size_t)8 << 20;  // photons per wavefront batch
+  int rc = ensure_pool(sc, 2 * batch + 1024, 1024);
+  if (rc) return rc;
+  const uint32_t half = (uint32_t)(sc->P.capacity / 2);
+  const uint32_t s0 = rng_mix((uint32_t)opts->seed, (uint32_t)(opts->seed >> 32));
+  const int grid_p = sc->sm_count * (RT_FAST_MIN_BLOCKS > 8 ? RT_FAST_MIN_BLOCKS : 8);
+  PpmCounters hpc0, hpc1;
+  CK(cudaMemcpy(&hpc0, sc->d_pc, sizeof(hpc0), cudaMemcpyDeviceToHost));
+  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
+  Timers tm;
+  tm.s = st; tm.on = stats != nullptr;
+  int launches = 0;
+  cudaEventRecord(sc->ev[0], st);
+  tm.mark(ST_GENERATE);
+  for (int64_t done = 0; done < opts->photons && sc->S.max_depth > 1; done += (int64_t)batch) {
+    const uint32_t n = (uint32_t)((opts->photons - done) < (int64_t)batch ? (opts->photons - done) : (int64_t)batch);
+    k_ppm_emit<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, sc->d_waves, s0, opts->first_photon + (uint64_t)done, n);
+    launches++;
+    tm.mark(ST_GENERATE);
+    for (int d = 0; d + 1 < sc->S.max_depth; d++) {
+      k_ppm_next_wave<<<1, 1, 0, st>>>(sc->d_waves, d, half, sc->d_counters);
+      k_ppm_count_rays<<<1, 1, 0, st>>>(sc->d_waves, d, sc->d_pc);
+      k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+      tm.mark(ST_EXTEND);
+      k_ppm_photon_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->d_waves, d, sc->HP, sc->G,
+                                                                sc->d_counters, sc->d_pc);
+      tm.mark(ST_SHADE);
+      launches += 4;
+    }
+  }
+  cudaEventRecord(sc->ev[1], st);
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (stats) {
+    CK(cudaMemcpy(&hpc1, sc->d_pc, sizeof(hpc1), cudaMemcpyDeviceToHost));
+    Counters hc;
+    CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
+    memset(stats, 0, sizeof(*stats));
+    stats->hit_points = sc->n_hp; stats->photons = (uint64_t)opts->photons;
+    stats->photon_rays = hpc1.photon_rays - hpc0.photon_rays;
+    stats->cell_scans = hpc1.cell_scans - hpc0.cell_scans;
+    stats->deposits = hpc1.deposits - hpc0.deposits;
+    stats->nodes_visited = hc.nodes_visited; stats->tris_tested = hc.tris_tested;
+    float ms[ST_COUNT];
+    tm.collect(ms);
+    stats->ms_extend = ms[ST_EXTEND]; stats->ms_deposit = ms[ST_SHADE];
+    cudaEventElapsedTime(&stats->ms_photon, sc->ev[0], sc->ev[1]);
+    stats->initial_radius = sc->G.r0;
+    stats->launches = launches;
+  }
+  return B200RT_OK;
+}
+
+int b200rt_ppm_export(b200rt_scene* sc, float** d_S_n, int64_t* n_hit_points) {
+  if (!sc || !d_S_n || sc->ppm_camera < 0) return B200RT_E_INVALID;
+  CK(cudaSetDevice(sc->device));
+  if (sc->n_hp) k_ppm_export<<<sc->sm_count * 4, 256, 0, sc->stream>>>(sc->HP, sc->n_hp, sc->d_export);
+  CK(cudaStreamSynchronize(sc->stream));
+  *d_S_n = reinterpret_cast<float*>(sc->d_export);
+  if (n_hit_points) *n_hit_points = sc->n_hp;
+  return B200RT_OK;
+}
+
+int b200rt_ppm_density_from(b200rt_scene* sc, const float* d_S_n, double total, float* rgbw_out) {
+  if (!sc || !rgbw_out || sc->ppm_camera < 0 || (!d_S_n && sc->n_hp)) return B200RT_E_INVALID;
+  CK(cudaSetDevice(sc->device));
+  const b200rt_camera& c = sc->cameras[sc->ppm_camera];
+  const size_t pixels = (size_t)c.width * c.height;
+  int rc = ensure_accum(sc, pixels);
+  if (rc) return rc;
+  cudaStream_t st = sc->stream;
+  CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), st));
+  if (sc->n_hp)
+    k_ppm_density<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, sc->n_hp, reinterpret_cast<const float4*>(d_S_n), sc->G.r0sq,
+                                                    total, sc->d_accum);
+  CK(cudaMemcpyAsync(rgbw_out, sc->d_accum, pixels * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  return B200RT_OK;
+}
+
+int b200rt_ppm_density(b200rt_scene* sc, double total, float* rgbw_out) {
+  float* p = nullptr;
+  int rc = b200rt_ppm_export(sc, &p, nullptr);
+  if (rc) return rc;
+  return b200rt_ppm_density_from(sc, p, total, rgbw_out);
+}
+
+int b200rt_ppm_get_hit_points(b200rt_scene* sc, float* out16, int64_t capacity, int64_t* n_out) {
+  if (!sc || sc->ppm_camera < 0) return B200RT_E_INVALID;
+  CK(cudaSetDevice(sc->device));
+  if (n_out) *n_out = sc->n_hp;
+  if (!out16 || capacity <= 0 || sc->n_hp == 0) return B200RT_OK;
+  const uint32_t n = (uint32_t)((int64_t)sc->n_hp < capacity ? (int64_t)sc->n_hp : capacity);
+  float* d = nullptr;
+  CK(cudaMalloc((void**)&d, sizeof(float) * 16 * (size_t)n));
+  k_ppm_pack_hit_points<<<sc->sm_count * 4, 256, 0, sc->stream>>>(sc->HP, n, d);
+  CK(cudaMemcpyAsync(out16, d, sizeof(float) * 16 * (size_t)n, cudaMemcpyDeviceToHost, sc->stream));
+  CK(cudaStreamSynchronize(sc->stream));
+  cudaFree(d);
+  return B200RT_OK;
+}
 
 int b200rt_device_count(void) {
   int n = 0;
@@ -345,7 +635,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     return B200RT_E_INVALID;
   }
   if (d->semantics != B200RT_SEM_HW1 && d->semantics != B200RT_SEM_HW2 && d->semantics != B200RT_SEM_HW3 &&
-      d->semantics != B200RT_SEM_HW7) {
+      d->semantics != B200RT_SEM_HW7 && d->semantics != B200RT_SEM_PPM) {
     b200rt_internal_set_error("b200rt_scene_create: semantics not implemented on the device yet");
     return B200RT_E_UNSUPPORTED;
   }
@@ -357,6 +647,10 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   sc->device = device;
   sc->d_accum = nullptr; sc->accum_pixels = 0;
   sc->d_waves = nullptr; sc->d_counters = nullptr;
+  memset(&sc->HP, 0, sizeof(HitPoints));
+  memset(&sc->G, 0, sizeof(PpmGrid));
+  sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
+  sc->scan_tmp_bytes = 0; sc->items_capacity = 0; sc->n_hp = 0; sc->ppm_camera = -1;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   sc->sm_count = prop.multiProcessorCount;
@@ -444,6 +738,7 @@ void b200rt_scene_destroy(b200rt_scene* sc) {
   pool_free(sc);
   for (void* p : sc->allocs)
     if (p) cudaFree(p);
+  ppm_free(sc);
   if (sc->d_accum) cudaFree(sc->d_accum);
   if (sc->d_waves) cudaFree(sc->d_waves);
   if (sc->d_counters) cudaFree(sc->d_counters);

@@ -408,6 +408,7 @@ int b200rt_builder_set_globals(b200rt_builder* b, const float bg[3], const float
   std::memcpy(b->desc.ambient, amb, 12);
   b->desc.shadow_eps = shadow_eps;
   b->desc.max_depth = max_depth;
+  if (b->semantics == B200RT_SEM_PPM && b->desc.max_depth > 20) b->desc.max_depth = 20;  // PPM/src/Scene.cpp:426-429
   return B200RT_OK;
 }
 
@@ -456,6 +457,7 @@ int b200rt_builder_add_camera(b200rt_builder* b, const b200rt_camera_in* in) {
   int s = (int)std::sqrt(in->num_samples);  // HW3/src/Scene.cpp:412 (int -> double sqrt)
   if (s <= 0) s = 1;
   c.samples_sqrt = (b->semantics == B200RT_SEM_HW1) ? 1 : s;
+  if (b->semantics == B200RT_SEM_PPM && c.samples_sqrt > 2) c.samples_sqrt = 2;  // PPM/src/Scene.cpp:268
   c.aperture = (b->semantics >= B200RT_SEM_HW3) ? in->aperture_size : 0.0f;
   b->cameras.push_back(c);
   return (int)b->cameras.size() - 1;
@@ -873,7 +875,11 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
     fi.texture = b->meshes_in[in.mesh].texture;  // instances take the base mesh's texture (HW7/src/Scene.cpp:1182)
     if (b->semantics >= B200RT_SEM_HW7 && in.material >= 0 && in.material < (int)b->materials.size()) {
       const float* tr = b->materials[in.material].transparency;
-      if (tr[0] != 0.f || tr[1] != 0.f || tr[2] != 0.f) fi.flags |= B200RT_INST_REFRACTIVE;
+      const float* mr = b->materials[in.material].mirror;
+      bool refr = (tr[0] != 0.f || tr[1] != 0.f || tr[2] != 0.f);
+      // PPM: material_type == mt_refractive, and mirror wins over transparency (PPM/src/Material.cpp:55-61)
+      if (b->semantics == B200RT_SEM_PPM && (mr[0] != 0.f || mr[1] != 0.f || mr[2] != 0.f)) refr = false;
+      if (refr) fi.flags |= B200RT_INST_REFRACTIVE;
     }
     Obj o;
     o.ref = B200RT_REF(in.is_light ? B200RT_KIND_LIGHTINST : B200RT_KIND_INSTANCE, b->instances.size());
@@ -954,6 +960,15 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
     b->spheres.push_back(fs);
   }
 
+  if (b->semantics == B200RT_SEM_PPM) {
+    // PPM loads spheres before meshes (PPM/src/Scene.cpp:487-498): objects = spheres, base instances, instances
+    std::vector<Obj> reordered;
+    for (const Obj& o : top)
+      if (B200RT_REF_KIND(o.ref) == B200RT_KIND_SPHERE) reordered.push_back(o);
+    for (const Obj& o : top)
+      if (B200RT_REF_KIND(o.ref) != B200RT_KIND_SPHERE) reordered.push_back(o);
+    top.swap(reordered);
+  }
   // ---- Scene::bvh = BVH::create_bvh(objects) — HW3/src/Scene.cpp:871 --------
   Box root_box;
   std::vector<uint32_t> order;

@@ -1,0 +1,388 @@
+// ppm_kernels.cuh — progressive photon mapping:
+//   eye pass        Scene::eye_trace            PPM/src/Scene.cpp:286-362
+//   hash grid       Scene::build_hash_grid      PPM/src/Scene.cpp:53-93, hash PPM/include/Scene.h:65-68
+//   photon pass     Point_light::generate_photon PPM/src/Point_light.cpp:7-30,
+//                   Scene::photon_trace          PPM/src/Scene.cpp:106-249, sample_hemisphere :15-44
+//   density         Scene::density_estimation    PPM/src/Scene.cpp:363-372
+// Both passes are wavefronts over the same vertex pool and the same traversal
+// kernel (k_trace_fast<false,7>) as the image renderers.  See include/b200rt.h
+// for the lock-free restatement of the per-photon radius / flux update.
+#pragma once
+#include "rt_shade7.cuh"
+
+#define PPM_ALPHA 0.7f
+#define PPM_RTAB (1 << 20)
+
+struct HitPoints {
+  uint32_t capacity;
+  unsigned int* count;
+  float4* pos;   // position xyz
+  float4* nrm;   // normal xyz, as_float(material)
+  float4* wo;    // w_o xyz, as_float(pixel)
+  float4* att;   // attenuation rgb, pixel_weight
+  unsigned int* n;
+  float4* S;     // sum f*phi/R(k) rgb
+};
+struct PpmGrid {
+  uint32_t num_hash;
+  unsigned int* cell_count;  // num_hash + 1 (becomes the fill cursor)
+  unsigned int* cell_start;  // num_hash + 1
+  unsigned int* items;
+  v3 bbox_min;
+  float hash_scale, r0, r0sq;
+  const float* rtab;         // R(n) for n < PPM_RTAB
+};
+struct PpmCounters {
+  unsigned long long photon_rays, cell_scans, deposits;
+  unsigned int bbox[6];      // ordered-int min xyz / max xyz of the hit-point positions
+  unsigned int grid_overflow;
+};
+
+__device__ __forceinline__ int ppm_material_type(const b200rt_material& m) {  // PPM/src/Material.cpp:55-61
+  if (!is_zero(ld3(m.mirror))) return 1;
+  if (!is_zero(ld3(m.transparency))) return 2;
+  return 0;
+}
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f_bits(unsigned int o) {
+  const unsigned int u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+// R(n) = prod_{k<n} (k*a + a)/(k*a + 1): table (the reference's float product) or, beyond it, the closed form
+__device__ __forceinline__ float ppm_R(const PpmGrid& G, unsigned int n) {
+  if (n < PPM_RTAB) return __ldg(G.rtab + n);
+  const double ia = 1.0 / (double)PPM_ALPHA;
+  return (float)exp(lgamma((double)n + 1.0) + lgamma(ia) - lgamma((double)n + ia));
+}
+__device__ __forceinline__ uint32_t ppm_hash(uint32_t num_hash, int ix, int iy, int iz) {
+  const uint32_t h = ((uint32_t)ix * 73856093u) ^ ((uint32_t)iy * 19349663u) ^ ((uint32_t)iz * 83492791u);
+  return h % num_hash;
+}
+
+// ---- eye pass ------------------------------------------------------------------
+__global__ void __launch_bounds__(RT_BLOCK) k_ppm_eye_shade(DScene S, Pool P, WaveInfo* waves, int d, HitPoints HP,
+                                                            Counters* C, PpmCounters* PC) {
+  const uint32_t begin = waves[d].begin, count = waves[d].count;
+  const uint32_t next_begin = waves[d + 1].begin;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (count + stride - 1) / stride;
+  for (uint32_t r = 0; r < rounds; r++) {
+    const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = k < count;
+    const uint32_t slot = begin + (act ? k : 0);
+    const float4 ha = P.hit_a[slot];
+    const uint32_t top_ref = __float_as_uint(ha.w);
+    const bool hit = act && B200RT_REF_KIND(top_ref) != B200RT_KIND_NONE;
+    bool want_hp = false, want_r = false, want_t = false;
+    v3 p = mk3(0, 0, 0), n = mk3(0, 0, 0), w_o = mk3(0, 0, 0), att = mk3(1, 1, 1);
+    v3 dir_r = mk3(0, 0, 0), dir_t = mk3(0, 0, 0), att_r = mk3(0, 0, 0), att_t = mk3(0, 0, 0);
+    int mat = 0;
+    uint32_t depth = 0;
+    if (hit) {
+      const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
+      const v3 o = mk3(ro.x, ro.y, ro.z), dir = mk3(rd.x, rd.y, rd.z);
+      depth = RT_META_DEPTH(__float_as_uint(rd.w));
+      if (depth > 0) { const float4 a = P.rec0[slot]; att = mk3(a.x, a.y, a.z); }
+      const Surf7 sf = surface7(S, top_ref, P.hit_b[slot].y, ha.y, ha.z, o, dir, 0.0f, ha.x);
+      n = sf.n; mat = sf.material;
+      p = o + (dir * ha.x);
+      const b200rt_material& m = S.mats[mat];
+      const int type = ppm_material_type(m);
+      w_o = normalize(o - p);
+      if (type == 0) {
+        want_hp = true;
+      } else if ((int)depth >= S.max_depth) {
+        // dropped — PPM/src/Scene.cpp:305-306
+      } else {
+        const v3 w_r = normalize((n * (2.0f * dot(n, w_o))) - w_o);
+        dir_r = w_r;
+        if (type == 1) {
+          want_r = true; att_r = ld3(m.mirror) * att;
+        } else {
+          const v3 nl = dot(n, dir) < 0.0f ? n : n * -1.0f;
+          const bool into = dot(n, nl) > 0.0f;
+          const float air = 1.0f;
+          const float nnt = into ? air / m.refraction_index : m.refraction_index / air;
+          const float ddn = dot(dir, nl);
+          const float cos2t = 1 - nnt * nnt * (1 - ddn * ddn);
+          if (cos2t < 0.0f) {
+            want_r = true; att_r = ld3(m.transparency) * att;
+          } else {
+            dir_t = normalize((dir * nnt) - (n * ((into ? 1 : -1) * (ddn * nnt + sqrtf(cos2t)))));
+            const float a = m.refraction_index - air, b = m.refraction_index + air;
+            const float R0 = a * a / (b * b);
+            const float ca = into ? -ddn : dot(dir_t, n);
+            const float c = 1 - ca;
+            const float fres = R0 + (1 - R0) * c * c * c * c * c;
+            const v3 ac = ld3(m.transparency) * att;
+            want_t = true;
+            if (into) {
+              want_r = true; att_r = att * fres;
+              att_t = ac * (1.0f - fres);
+            } else {
+              att_t = ac;
+            }
+          }
+        }
+      }
+    }
+    const uint32_t hi = warp_append(HP.count, want_hp);
+    if (want_hp) {
+      if (hi < HP.capacity) {
+        HP.pos[hi] = make_float4(p.x, p.y, p.z, 0.f);
+        HP.nrm[hi] = make_float4(n.x, n.y, n.z, __int_as_float(mat));
+        HP.wo[hi] = make_float4(w_o.x, w_o.y, w_o.z, __uint_as_float(P.pixel[slot]));
+        HP.att[hi] = make_float4(att.x, att.y, att.z, 1.0f);
+        atomicMin(&PC->bbox[0], f2ord(p.x)); atomicMin(&PC->bbox[1], f2ord(p.y)); atomicMin(&PC->bbox[2], f2ord(p.z));
+        atomicMax(&PC->bbox[3], f2ord(p.x)); atomicMax(&PC->bbox[4], f2ord(p.y)); atomicMax(&PC->bbox[5], f2ord(p.z));
+      } else {
+        C->overflow = 1;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const bool want = c == 0 ? want_r : want_t;
+      const uint32_t ci = warp_append(&waves[d + 1].count, want);
+      if (want) {
+        const uint32_t cs = next_begin + ci;
+        if (cs < P.capacity) {
+          const v3 cd = c == 0 ? dir_r : dir_t;
+          const v3 ca = c == 0 ? att_r : att_t;
+          const v3 co = p + (cd * S.shadow_eps);
+          P.ray_o[cs] = make_float4(co.x, co.y, co.z, 0.0f);
+          P.ray_d[cs] = make_float4(cd.x, cd.y, cd.z, __uint_as_float(depth + 1));
+          P.rec0[cs] = make_float4(ca.x, ca.y, ca.z, 0.f);
+          P.pixel[cs] = P.pixel[slot];
+          P.key[cs] = 0;
+        } else {
+          C->overflow = 1;
+        }
+      }
+    }
+  }
+}
+
+// ---- hash grid -------------------------------------------------------------------
+// mode 0: count entries per cell; mode 1: fill (cell_count is the running cursor, starting at cell_start)
+__global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uint32_t items_capacity, PpmCounters* PC) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
+    const float4 q = HP.pos[i];
+    if (mode == 0) { HP.n[i] = 0; HP.S[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    const v3 lo = (mk3(q.x - G.r0, q.y - G.r0, q.z - G.r0) - G.bbox_min) * G.hash_scale;
+    const v3 hi = (mk3(q.x + G.r0, q.y + G.r0, q.z + G.r0) - G.bbox_min) * G.hash_scale;
+    for (int iz = abs((int)lo.z); iz <= abs((int)hi.z); iz++)
+      for (int iy = abs((int)lo.y); iy <= abs((int)hi.y); iy++)
+        for (int ix = abs((int)lo.x); ix <= abs((int)hi.x); ix++) {
+          const uint32_t hv = ppm_hash(G.num_hash, ix, iy, iz);
+          const unsigned int at = atomicAdd(&G.cell_count[hv], 1u);
+          if (mode == 1) {
+            if (at < items_capacity) G.items[at] = i; else PC->grid_overflow = 1;
+          }
+        }
+  }
+}
+
+// ---- photon pass -------------------------------------------------------------------
+// RNG: key of photon i = mix(mix(s0 ^ 'PHOT', lo32(i)), hi32(i)); dims: emission 0,1; bounce b: 8b+2,3 hemisphere,
+// 8b+4 roulette, 8b+5 glass roulette (shared with oracle.c).
+__global__ void k_ppm_emit(DScene S, Pool P, WaveInfo* waves, uint32_t s0, unsigned long long first, uint32_t n) {
+  const b200rt_light& L = S.lights[0];
+  const v3 flux = ld3(L.intensity) * (float)(RT_PI * 4.0f);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const unsigned long long i = first + k;
+    const uint32_t key = rng_mix(rng_mix(s0 ^ 0x50484F54u, (uint32_t)i), (uint32_t)(i >> 32));
+    const float phi = (float)(2 * RT_PI * (double)rng_u01(key, 0));
+    const float theta = (float)(2 * RT_PI * (double)rng_u01(key, 1));  // sic
+    const v3 d = onb_dir7(mk3(0.0f, 1.0f, 0.0f), theta, phi);
+    P.ray_o[k] = make_float4(L.position[0], L.position[1], L.position[2], 0.0f);
+    P.ray_d[k] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
+    P.rec0[k] = make_float4(flux.x, flux.y, flux.z, 0.f);
+    P.key[k] = key;
+    P.pixel[k] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { waves[0].begin = 0; waves[0].count = n; }
+}
+// ping-pong wave placement: a photon path is a chain, so two half pools suffice
+__global__ void k_ppm_next_wave(WaveInfo* waves, int d, uint32_t half, Counters* C) {
+  waves[d + 1].begin = ((d + 1) & 1) ? half : 0u;
+  waves[d + 1].count = 0;
+  C->work_extend = 0;
+}
+__global__ void __launch_bounds__(RT_BLOCK) k_ppm_photon_shade(DScene S, Pool P, WaveInfo* waves, int d, HitPoints HP,
+                                                               PpmGrid G, Counters* C, PpmCounters* PC) {
+  const uint32_t begin = waves[d].begin, count = waves[d].count;
+  const uint32_t next_begin = waves[d + 1].begin;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (count + stride - 1) / stride;
+  unsigned int scans = 0, deposits = 0;
+  for (uint32_t r = 0; r < rounds; r++) {
+    const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = k < count;
+    const uint32_t slot = begin + (act ? k : 0);
+    const float4 ha = P.hit_a[slot];
+    const uint32_t top_ref = __float_as_uint(ha.w);
+    const bool hit = act && B200RT_REF_KIND(top_ref) != B200RT_KIND_NONE;
+    bool cont = false;
+    v3 p = mk3(0, 0, 0), ndir = mk3(0, 0, 0), nflux = mk3(0, 0, 0);
+    uint32_t key = 0, b = 0;
+    if (hit) {
+      const float4 ro = P.ray_o[slot], rd = P.ray_d[slot], fl = P.rec0[slot];
+      const v3 o = mk3(ro.x, ro.y, ro.z), dir = mk3(rd.x, rd.y, rd.z);
+      const v3 flux = mk3(fl.x, fl.y, fl.z);
+      b = RT_META_DEPTH(__float_as_uint(rd.w));
+      key = P.key[slot];
+      const uint32_t dim = 8u * b;
+      const Surf7 sf = surface7(S, top_ref, P.hit_b[slot].y, ha.y, ha.z, o, dir, 0.0f, ha.x);
+      const v3 n = sf.n;
+      p = o + (dir * ha.x);
+      const v3 nl = dot(n, dir) < 0 ? n : n * -1.0f;
+      const b200rt_material& m = S.mats[sf.material];
+      const int type = ppm_material_type(m);
+      if (type == 0) {
+        if (G.num_hash > 0) {
+          const v3 hh = (p - G.bbox_min) * G.hash_scale;
+          const uint32_t cell = ppm_hash(G.num_hash, abs((int)hh.x), abs((int)hh.y), abs((int)hh.z));
+          const unsigned int c0 = G.cell_start[cell], c1 = G.cell_start[cell + 1];
+          const v3 w_i = -normalize(dir);
+          for (unsigned int q = c0; q < c1; q++) {
+            const unsigned int hi = G.items[q];
+            const float4 hp = HP.pos[hi], hn = HP.nrm[hi];
+            scans++;
+            const v3 hnrm = mk3(hn.x, hn.y, hn.z);
+            if (!(dot(hnrm, n) > 1e-3f)) continue;
+            const v3 v = mk3(hp.x, hp.y, hp.z) - p;
+            const float d2 = dot(v, v);
+            // claim index n under the radius the reference would test against: r2(n) = r0^2 * R(n)
+            unsigned int n_old = *((volatile unsigned int*)(HP.n + hi));
+            bool accepted = false;
+            for (;;) {
+              if (!(d2 <= G.r0sq * ppm_R(G, n_old))) break;
+              const unsigned int prev = atomicCAS(HP.n + hi, n_old, n_old + 1u);
+              if (prev == n_old) { accepted = true; break; }
+              n_old = prev;
+            }
+            if (!accepted) continue;
+            deposits++;
+            const b200rt_material& hm = S.mats[__float_as_int(hn.w)];
+            const float cti = dot(hnrm, w_i);
+            if (!(cti > 1.0f || cti <= 0.0f)) {
+              const float4 hw = HP.wo[hi], hat = HP.att[hi];
+              const float sct = fmaxf(0.0f, dot(hnrm, normalize(mk3(hw.x, hw.y, hw.z) + w_i)));
+              const v3 color = (ld3(hm.diffuse) + ((ld3(hm.specular) * powf(sct, hm.phong_exponent)) / cti)) *
+                               mk3(hat.x, hat.y, hat.z);
+              const v3 c = (color * flux) / ppm_R(G, n_old);
+              float* Sp = reinterpret_cast<float*>(HP.S + hi);
+              atomicAdd(Sp + 0, c.x); atomicAdd(Sp + 1, c.y); atomicAdd(Sp + 2, c.z);
+            }
+          }
+        }
+        // sample_hemisphere(normal, d, probability): cosine — PPM/src/Scene.cpp:15-44
+        const float e1 = rng_u01(key, dim + 2), e2 = rng_u01(key, dim + 3);
+        const float phi = (float)(2 * RT_PI * (double)e1);
+        const float theta = asinf(sqrtf(e2));
+        const v3 dd = onb_dir7(n, theta, phi);
+        const float prob = (float)((double)fmaxf(0.0f, dot(n, dd)) / RT_PI);
+        v3 base = mk3(0, 0, 0);
+        const v3 w_i = -normalize(dir);
+        const float cti = fmaxf(0.0f, dot(n, w_i));
+        if (!(cti > 1.0f || cti <= 0.0f)) {
+          const float sct = fmaxf(0.0f, dot(nl, normalize(dd + w_i)));
+          base = ld3(m.diffuse) + ((ld3(m.specular) * powf(sct, m.phong_exponent)) / cti);
+        }
+        const float cto = fmaxf(0.0f, dot(n, dd));
+        base = base * cto;
+        if (rng_u01(key, dim + 4) < prob) {   // the pdf doubles as survival probability (Appendix B.8)
+          cont = true; ndir = dd; nflux = (base * flux) / prob;
+        }
+      } else {
+        const v3 w_o = normalize(o - p);
+        const v3 w_r = normalize((n * (2.0f * dot(n, w_o))) - w_o);
+        if (type == 1) {
+          cont = true; ndir = w_r; nflux = ld3(m.mirror) * flux;
+        } else {
+          const bool into = dot(n, nl) > 0.0f;
+          const float air = 1.0f;
+          const float nnt = into ? air / m.refraction_index : m.refraction_index / air;
+          const float ddn = dot(dir, nl);
+          const float cos2t = 1 - nnt * nnt * (1 - ddn * ddn);
+          cont = true; nflux = flux;
+          if (cos2t < 0.0f) {
+            ndir = w_r;
+          } else {
+            const v3 rdir = normalize((dir * nnt) - (n * ((into ? 1 : -1) * (ddn * nnt + sqrtf(cos2t)))));
+            const float a = m.refraction_index - air, bb = m.refraction_index + air;
+            const float R0 = a * a / (bb * bb);
+            const float ca = into ? -ddn : dot(rdir, n);
+            const float c = 1 - ca;
+            const float fres = R0 + (1 - R0) * c * c * c * c * c;
+            ndir = (into && rng_u01(key, dim + 5) < fres) ? w_r : rdir;
+          }
+        }
+      }
+      // photon_trace: depth++ then `depth >= max_recursion_depth` stops BEFORE the next intersection
+      if (cont && (int)(b + 2) >= S.max_depth) cont = false;
+    }
+    const uint32_t ci = warp_append(&waves[d + 1].count, cont);
+    if (cont) {
+      const uint32_t cs = next_begin + ci;
+      const v3 co = p + (ndir * S.shadow_eps);
+      P.ray_o[cs] = make_float4(co.x, co.y, co.z, 0.0f);
+      P.ray_d[cs] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(b + 1));
+      P.rec0[cs] = make_float4(nflux.x, nflux.y, nflux.z, 0.f);
+      P.key[cs] = key;
+      P.pixel[cs] = 0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    scans += __shfl_xor_sync(0xffffffffu, scans, o);
+    deposits += __shfl_xor_sync(0xffffffffu, deposits, o);
+  }
+  if (lane_id() == 0) {
+    atomicAdd(&PC->cell_scans, (unsigned long long)scans);
+    atomicAdd(&PC->deposits, (unsigned long long)deposits);
+  }
+}
+__global__ void k_ppm_count_rays(const WaveInfo* waves, int d, PpmCounters* PC) {
+  PC->photon_rays += waves[d].count;
+}
+
+// ---- density estimation -----------------------------------------------------------------
+// packs {S.rgb, n} per hit point (the additive state; all-reduced across GPUs)
+__global__ void k_ppm_export(HitPoints HP, uint32_t n_hp, float4* out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
+    const float4 s = HP.S[i];
+    out[i] = make_float4(s.x, s.y, s.z, (float)HP.n[i]);
+  }
+}
+// tau/(pi r2 N) = S/(pi r0^2 N) since tau = R(n) S and r2 = r0^2 R(n)
+__global__ void k_ppm_density(HitPoints HP, uint32_t n_hp, const float4* S_n, float r0sq, double total, float4* accum) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
+    const float4 s = S_n[i];
+    const float4 w = HP.wo[i], a = HP.att[i];
+    const uint32_t pix = __float_as_uint(w.w);
+    const float kk = (float)(1.0f / (RT_PI * (double)r0sq * total));
+    const v3 col = mk3(s.x, s.y, s.z) * kk;
+    float* px = reinterpret_cast<float*>(accum + pix);
+    atomicAdd(px + 0, col.x * a.w); atomicAdd(px + 1, col.y * a.w); atomicAdd(px + 2, col.z * a.w);
+    atomicAdd(px + 3, a.w);
+  }
+}
+__global__ void k_ppm_pack_hit_points(HitPoints HP, uint32_t n_hp, float* out16) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
+    const float4 p = HP.pos[i], n = HP.nrm[i], w = HP.wo[i], a = HP.att[i];
+    float* o = out16 + 16 * (size_t)i;
+    o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = n.x; o[4] = n.y; o[5] = n.z; o[6] = w.x; o[7] = w.y; o[8] = w.z;
+    o[9] = a.x; o[10] = a.y; o[11] = a.z; o[12] = (float)__float_as_int(n.w); o[13] = (float)__float_as_uint(w.w);
+    o[14] = a.w; o[15] = (float)HP.n[i];
+  }
+}

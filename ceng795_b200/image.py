@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._lib import SEM_HW1, SEM_HW2, SEM_HW3, SEM_HW4, SEM_HW5, SEM_HW6, SEM_HW7
+from ._lib import SEM_HW1, SEM_HW2, SEM_HW3, SEM_HW4, SEM_HW5, SEM_HW6, SEM_HW7, SEM_PPM
 
 
 def quantise(rgbw: np.ndarray, semantics: int) -> np.ndarray:
@@ -27,6 +27,11 @@ def quantise(rgbw: np.ndarray, semantics: int) -> np.ndarray:
         # HW3/include/Pixel.h:25-28 clamps in float, HW3/src/main.cpp then stores into unsigned char
         q = np.minimum(np.float32(255), np.maximum(np.float32(0), np.nan_to_num(col, nan=0.0, posinf=3e9, neginf=-3e9)))
         return np.trunc(q).astype(np.uint8)
+    if semantics == SEM_PPM:
+        # PPM/src/main.cpp:150-157: int(pow(1 - exp(-x), 1 / 2.2f) * 255 + 0.5f), then write_png's clamp
+        x = np.nan_to_num(col.astype(np.float64), nan=0.0, posinf=1e30, neginf=-1e30)
+        v = np.power(np.maximum(0.0, 1.0 - np.exp(-x)), float(np.float32(1) / np.float32(2.2))) * 255 + 0.5
+        return np.clip(np.trunc(v), 0, 255).astype(np.uint8)
     raise NotImplementedError(f"quantise: semantics {semantics}")
 
 

@@ -147,7 +147,12 @@ def parse_xml(path_or_text: str, semantics, base_dir: str | None = None) -> Scen
         base_dir = base_dir or os.path.dirname(os.path.abspath(path_or_text))
     bg = _floats(_child_text(root, "BackgroundColor", "0 0 0"), 3)
     seps = float(_floats(_child_text(root, "ShadowRayEpsilon", "0.001"), 1)[0])
-    depth = int(float(_child_text(root, "MaxRecursionDepth", "0")))
+    depth = int(float(_child_text(root, "MaxRecursionDepth", "20" if sem == SEM_PPM else "0")))
+    ppm = None
+    if sem == SEM_PPM:
+        # PPM/src/Scene.cpp:398-415
+        ppm = dict(photon_count_per_iteration=int(float(_child_text(root, "PhotonCountPerIteration", "8000"))),
+                   number_of_iterations=int(float(_child_text(root, "NumberOfIterations", "1000"))))
     cams = []
     for cel in root.find("Cameras").findall("Camera"):
         simple = cel.get("type") == "simple" and sem >= SEM_HW4
@@ -348,7 +353,7 @@ def parse_xml(path_or_text: str, semantics, base_dir: str | None = None) -> Scen
                      np.ascontiguousarray(verts, dtype=np.float32), meshes, insts, tris, sphs,
                      texcoords=texcoords, textures=textures, brdfs=brdfs, other_lights=others,
                      light_meshes=lmeshes, light_spheres=lsphs, background_texture=bg_tex,
-                     path_tracing=path_tracing, importance_sampling=importance)
+                     path_tracing=path_tracing, importance_sampling=importance, ppm=ppm)
 
 
 def _load_envmap(path: str):
@@ -636,6 +641,65 @@ class Scene:
         _lib.check(self._L.b200rt_trace_rays(self._scene, rays.ctypes.data, n, int(exact), ids.ctypes.data,
                                              t.ctypes.data, C.byref(st)), "b200rt_trace_rays")
         return ids, t, st
+
+    # ---- PPM: the calls PPM/src/main.cpp makes on Scene (PPM/include/Scene.h:48-55) --------------------
+    def eye_trace_lines(self, camera_index: int = 0, seed: int = 0):
+        """reset_hash_grid + eye_trace_lines + build_hash_grid.  Returns PpmStats."""
+        self.upload()
+        st = _lib.PpmStats()
+        _lib.check(self._L.b200rt_ppm_eye_pass(self._scene, camera_index, seed, C.byref(st)), "b200rt_ppm_eye_pass")
+        self._ppm_camera = camera_index
+        return st
+
+    def trace_n_photons(self, n: int, first_photon: int = 0, seed: int = 0):
+        o = _lib.PpmOpts()
+        o.photons = int(n); o.first_photon = int(first_photon); o.seed = int(seed)
+        st = _lib.PpmStats()
+        _lib.check(self._L.b200rt_ppm_trace_photons(self._scene, C.byref(o), C.byref(st)), "b200rt_ppm_trace_photons")
+        return st
+
+    def density_estimation(self, total_num_of_photons: float, out: np.ndarray | None = None):
+        w, h = self.image_size(self._ppm_camera)
+        if out is None:
+            out = np.zeros((h, w, 4), np.float32)
+        _lib.check(self._L.b200rt_ppm_density(self._scene, float(total_num_of_photons), out.ctypes.data), "b200rt_ppm_density")
+        return out
+
+    def ppm_export(self):
+        """(device pointer of float4 {S.rgb, n} per hit point, count) — the additive state for the all-reduce."""
+        p = C.c_void_p()
+        n = C.c_int64()
+        _lib.check(self._L.b200rt_ppm_export(self._scene, C.byref(p), C.byref(n)), "b200rt_ppm_export")
+        return p.value, n.value
+
+    def density_estimation_from(self, d_S_n: int, total_num_of_photons: float, out: np.ndarray | None = None):
+        w, h = self.image_size(self._ppm_camera)
+        if out is None:
+            out = np.zeros((h, w, 4), np.float32)
+        _lib.check(self._L.b200rt_ppm_density_from(self._scene, C.c_void_p(d_S_n), float(total_num_of_photons),
+                                                   out.ctypes.data), "b200rt_ppm_density_from")
+        return out
+
+    def hit_points(self):
+        n = C.c_int64()
+        _lib.check(self._L.b200rt_ppm_get_hit_points(self._scene, None, 0, C.byref(n)), "b200rt_ppm_get_hit_points")
+        out = np.zeros((n.value, 16), np.float32)
+        if n.value:
+            _lib.check(self._L.b200rt_ppm_get_hit_points(self._scene, out.ctypes.data, n.value, C.byref(n)),
+                       "b200rt_ppm_get_hit_points")
+        return out
+
+    def render_ppm(self, camera_index: int = 0, photons: int | None = None, seed: int = 0, total_num_of_photons=None):
+        """One PPM frame like PPM/src/main.cpp:33-102.  `total_num_of_photons` defaults to the number actually
+        emitted (the reference passes count*count/threads*threads, SURVEY Appendix B.7 — pass that explicitly
+        to reproduce its brightness)."""
+        ppm = self.spec.ppm or dict(photon_count_per_iteration=8000, number_of_iterations=1000)
+        if photons is None:
+            photons = ppm["photon_count_per_iteration"] * ppm["number_of_iterations"]
+        s0 = self.eye_trace_lines(camera_index, seed)
+        s1 = self.trace_n_photons(photons, 0, seed)
+        rgbw = self.density_estimation(photons if total_num_of_photons is None else total_num_of_photons)
+        return rgbw, s0, s1
 
     def close(self):
         if self._scene is not None:

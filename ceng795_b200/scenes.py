@@ -379,3 +379,65 @@ def hw7_scene(asset_dir, width=160, height=120, n=12, spp=1, depth=3, path_traci
             + brdfs + lights + "  <Materials>\n" + mats + "  </Materials>\n" + xf + "  <VertexData>\n"
             + _rows(allv, "%.9g") + "  </VertexData>\n  <TexCoordData>\n" + _rows(alluv, "%.9g") + "  </TexCoordData>\n"
             + textures + "  <Objects>\n" + mesh_xml + inst + lobj + tri_xml + sph + "  </Objects>\n</Scene>\n")
+
+
+# --------------------------------------------------------------------------- PPM
+def cfg5_ppm(width=1920, height=1080, mesh_slices=(160, 158), photons_per_iteration=10_000_000, iterations=100,
+             depth=8, spp=1, seed=SEED, image_name="cfg5.png") -> str:
+    """Config 5 — PPM dialect: a closed diffuse box (a 12-triangle mesh; PPM has no stand-alone Triangle),
+    one mirror sphere, one glass sphere (n = 1.5, T = .95) and one diffuse UV-sphere mesh of
+    2*slices*(stacks-1) triangles (160 x 158 -> 50 240), one point light under the ceiling."""
+    verts = []
+    nv = 0
+
+    def push(v):
+        nonlocal nv
+        base = nv
+        verts.append(np.asarray(v, np.float32))
+        nv += len(v)
+        return base
+
+    R = 4.0
+    room = np.array([[-R, 0, -R], [R, 0, -R], [R, 0, R], [-R, 0, R],
+                     [-R, 2 * R, -R], [R, 2 * R, -R], [R, 2 * R, R], [-R, 2 * R, R]], np.float32)
+    rb = push(room)
+    # faces wound so that their normals point INTO the room (culling is on in PPM)
+    quads = [(0, 3, 2, 1), (0, 1, 5, 4), (0, 4, 7, 3), (1, 2, 6, 5), (4, 5, 6, 7), (3, 7, 6, 2)]
+    groups = {1: [quads[0], quads[1], quads[4], quads[5]], 2: [quads[2]], 3: [quads[3]]}
+    mesh_xml = ""
+    mid = 1
+    for mat, qs in groups.items():
+        faces = []
+        for q in qs:
+            faces += [(q[0], q[1], q[2]), (q[0], q[2], q[3])]
+        mesh_xml += (f'    <Mesh id="{mid}">\n      <Material>{mat}</Material>\n      <Faces vertexOffset="{rb}">\n'
+                     + _rows(np.asarray(faces) + 1, "%d") + "      </Faces>\n    </Mesh>\n")
+        mid += 1
+    sv, sf = _uv_sphere((0, 0, 0), 1.0, mesh_slices[0], mesh_slices[1])
+    sb = push(sv)
+    mesh_xml += (f'    <Mesh id="{mid}" shadingMode="smooth">\n      <Material>4</Material>\n'
+                 f'      <Transformations>s1 t1</Transformations>\n      <Faces vertexOffset="{sb}">\n'
+                 + _rows(sf + 1, "%d") + "      </Faces>\n    </Mesh>\n")
+    cb = push(np.array([[-1.7, 1.0, -0.6], [1.6, 0.9, 1.2]], np.float32))
+    sph = (f'    <Sphere id="1">\n      <Material>5</Material>\n      <Center>{cb + 1}</Center>\n      <Radius>1.0</Radius>\n    </Sphere>\n'
+           f'    <Sphere id="2">\n      <Material>6</Material>\n      <Center>{cb + 2}</Center>\n      <Radius>0.9</Radius>\n    </Sphere>\n')
+    mats = ('    <Material id="1"><DiffuseReflectance>0.75 0.75 0.75</DiffuseReflectance></Material>\n'
+            '    <Material id="2"><DiffuseReflectance>0.75 0.25 0.25</DiffuseReflectance></Material>\n'
+            '    <Material id="3"><DiffuseReflectance>0.25 0.25 0.75</DiffuseReflectance></Material>\n'
+            '    <Material id="4"><DiffuseReflectance>0.6 0.7 0.3</DiffuseReflectance>'
+            '<SpecularReflectance>0.2 0.2 0.2</SpecularReflectance><PhongExponent>20</PhongExponent></Material>\n'
+            '    <Material id="5"><MirrorReflectance>0.95 0.95 0.95</MirrorReflectance></Material>\n'
+            '    <Material id="6"><Transparency>0.95 0.95 0.95</Transparency><RefractionIndex>1.5</RefractionIndex></Material>\n')
+    allv = np.concatenate(verts, 0)
+    aspect = width / height
+    return ("<Scene>\n  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
+            f"  <PhotonCountPerIteration>{photons_per_iteration}</PhotonCountPerIteration>\n"
+            f"  <NumberOfIterations>{iterations}</NumberOfIterations>\n  <MaxRecursionDepth>{depth}</MaxRecursionDepth>\n"
+            "  <Cameras>\n    <Camera id=\"1\">\n      <Position>0 3.6 3.9</Position>\n      <Gaze>0 -0.25 -1</Gaze>\n"
+            f"      <Up>0 1 0</Up>\n      <NearPlane>{_f([-0.62 * aspect, 0.62 * aspect, -0.62, 0.62])}</NearPlane>\n"
+            f"      <NearDistance>1</NearDistance>\n      <ImageResolution>{width} {height}</ImageResolution>\n"
+            f"      <NumSamples>{spp}</NumSamples>\n      <ImageName>{image_name}</ImageName>\n    </Camera>\n  </Cameras>\n"
+            "  <Lights>\n    <PointLight id=\"1\"><Position>0 7.2 0</Position><Intensity>5 5 5</Intensity></PointLight>\n  </Lights>\n"
+            "  <Materials>\n" + mats + "  </Materials>\n"
+            "  <Transformations>\n    <Scaling id=\"1\">0.8 0.8 0.8</Scaling>\n    <Translation id=\"1\">0.1 0.8 -1.9</Translation>\n  </Transformations>\n"
+            "  <VertexData>\n" + _rows(allv, "%.9g") + "  </VertexData>\n  <Objects>\n" + sph + mesh_xml + "  </Objects>\n</Scene>\n")

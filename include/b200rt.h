@@ -385,6 +385,39 @@ int b200rt_primary_ids(b200rt_scene*, int camera_index, const B200RenderOpts*, i
 int b200rt_trace_rays(b200rt_scene*, const float* rays, int64_t n, int32_t exact_traversal,
                       int32_t* ids_out, float* t_out, B200RenderStats* stats_out);
 
+/* ---- PPM: progressive photon mapping (PPM/include/Scene.h:48-55, driven by PPM/src/main.cpp:33-102) ----
+ * The reference updates a hit point under its mutex, one accepted photon at a time:
+ *   g = (n*a + a)/(n*a + 1);  r2 *= g;  n++;  tau = (tau + f*phi) * g         (PPM/src/Scene.cpp:135-169)
+ * so r2 is a function of n alone, r2(n) = r0^2 * R(n) with R(n) = prod_{k<n} g_k, and
+ *   tau_final = R(n_final) * sum_k f_k*phi_k / R(k).
+ * The device keeps n (claimed with atomicCAS after the radius test against r2(n)) and S = sum f*phi/R(k)
+ * (atomicAdd): the same per-photon estimator, lock-free, in some serialisation order like the reference's
+ * threads.  density_estimation's tau/(pi r2 N) is then S/(pi r0^2 N): additive across GPUs. */
+typedef struct B200PpmOpts {
+  int64_t photons;        /* photons to emit in this call                                   */
+  uint64_t first_photon;  /* global index of the first one: RNG stream id (sharding / calls) */
+  uint64_t seed;
+  int32_t pad[4];
+} B200PpmOpts;
+typedef struct B200PpmStats {
+  uint64_t hit_points, grid_entries, photons, photon_rays, cell_scans, deposits;
+  uint64_t nodes_visited, tris_tested;   /* photon-pass traversal counters */
+  float ms_eye, ms_grid, ms_photon, ms_extend, ms_deposit, ms_density;
+  float initial_radius;
+  int32_t launches;
+} B200PpmStats;
+/* reset_hash_grid + eye_trace_lines + build_hash_grid for one camera */
+int b200rt_ppm_eye_pass(b200rt_scene*, int camera_index, uint64_t seed, B200PpmStats*);
+/* trace_n_photons: emits opts->photons photons from lights[0] and deposits them */
+int b200rt_ppm_trace_photons(b200rt_scene*, const B200PpmOpts*, B200PpmStats*);
+/* density_estimation(pixels, total_num_of_photons): W*H float4 {sum c*w, sum w} into host memory */
+int b200rt_ppm_density(b200rt_scene*, double total_num_of_photons, float* rgbw_out);
+/* multi-GPU: device float4 per hit point {S.rgb, n}; all-reduce(sum) it across ranks and feed it back */
+int b200rt_ppm_export(b200rt_scene*, float** d_S_n, int64_t* n_hit_points);
+int b200rt_ppm_density_from(b200rt_scene*, const float* d_S_n, double total_num_of_photons, float* rgbw_out);
+/* test hook: 16 floats per hit point {position, normal, w_o, attenuation, material, pixel, pixel_weight, n} */
+int b200rt_ppm_get_hit_points(b200rt_scene*, float* out16, int64_t capacity, int64_t* n_out);
+
 /* Debug / test hook: copies `count` elements of one wavefront-pool array of the LAST render batch to
  * host memory.  field: 0 ray_o(f4) 1 ray_d(f4) 2 hit_a(f4) 3 nrm(f4) 4 rec0(f4) 5 rec1(f4) 6 rec2(f4)
  * 7 rec4(f4) 8 final_c(f4) 9 kd(f4) 10 pixel(u32) 11 key(u32) 12 hit_b(i32x2) 13 rec3(u32). */

@@ -95,6 +95,29 @@ def trace_rays(host_scene, rays):
     return ids, t, cnt
 
 
+def ppm(host_scene, camera_index=0, seed=0, n_photons=0, total_num_of_photons=None, want_hit_points=True):
+    """The PPM frame through the oracle (single sequential photon stream).  Returns
+    (rgbw[H,W,4], hit_points[n,16], initial_radius, Counters)."""
+    L = load()
+    L.oracle_ppm.restype = C.c_int
+    L.oracle_ppm.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
+                             C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(Counters)]
+    cam = host_scene.spec.cameras[camera_index]
+    w, h = cam["width"], cam["height"]
+    rgbw = np.zeros((h, w, 4), np.float32)
+    cap = w * h * 4 * 64
+    hp = np.zeros((cap, 16), np.float32) if want_hit_points else None
+    n_hp = C.c_int64()
+    r0 = C.c_float()
+    cnt = Counters()
+    total = float(n_photons if total_num_of_photons is None else total_num_of_photons)
+    rc = L.oracle_ppm(_desc_addr(host_scene), camera_index, seed, int(n_photons), total, rgbw.ctypes.data,
+                      hp.ctypes.data if hp is not None else None, cap, C.byref(n_hp), C.byref(r0), C.byref(cnt))
+    if rc != 0:
+        raise RuntimeError(f"oracle_ppm rc={rc}")
+    return rgbw, (hp[: n_hp.value] if hp is not None else None), float(r0.value), cnt
+
+
 def have_ref(tree: str) -> bool:
     return os.path.exists(os.path.join(REF_DIR, _TREE_BIN[tree]))
 
@@ -139,6 +162,19 @@ def run_reference(tree: str, xml_text: str, workdir: str | None = None, timeout:
             p = p + ".png"   # HW7/PPM print the name without its extension (HW7/src/main.cpp:56-57,97)
         if os.path.exists(p) and p.lower().endswith(".png"):
             res["images"][name] = read_png(p)
+    # PPM prints per-phase timers and "Saved png file. [ name ]" instead (PPM/src/main.cpp:56-102, write_png)
+    for label, key in (("Eye pass", "eye"), ("Building hash grid", "grid"), ("Tracing photon rays", "photon"),
+                       ("Density estimation", "density")):
+        m = re.search(label + r" is completed in: ([^\n]*)", out)
+        if m:
+            res["ms"][key] = parse_time_ms(m.group(1))
+    for name in re.findall(r"Saved png file\. \[ (\S+) \]", out):
+        p = os.path.join(tmp, name)
+        if os.path.exists(p) and name not in res["images"]:
+            res["images"][name] = read_png(p)
+    m = re.search(r"Starting photon_trace on #(\d+) thread", out)
+    if m:
+        res["threads"] = int(m.group(1))
     if own:
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)

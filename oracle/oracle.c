@@ -1338,6 +1338,309 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
   return 0;
 }
 
+/* ======================================================================== */
+/* PPM — progressive photon mapping (PPM/src/Scene.cpp:15-372, main.cpp:33-157) */
+/* ======================================================================== */
+typedef struct {
+  v3 position, normal, w_o, attenuation, flux;
+  float radius_squared, pixel_weight;
+  uint32_t n;
+  int material, pixel;
+} OracleHitPoint;
+typedef struct {
+  OracleHitPoint* hp;
+  int64_t n, cap;
+  /* hash grid (CSR) */
+  int64_t num_hash;
+  int64_t* cell_start;
+  int32_t* cell_items;
+  v3 bbox_min;
+  float hash_scale, initial_radius;
+} OraclePpm;
+
+static int ppm_material_type(const b200rt_material* m) { /* PPM/src/Material.cpp:55-61 */
+  if (!is_zero(ld(m->mirror))) return 1;
+  if (!is_zero(ld(m->transparency))) return 2;
+  return 0;
+}
+static void ppm_add_hp(OraclePpm* P, const OracleHitPoint* h) {
+  if (P->n == P->cap) {
+    P->cap = P->cap ? 2 * P->cap : 4096;
+    P->hp = (OracleHitPoint*)realloc(P->hp, sizeof(OracleHitPoint) * (size_t)P->cap);
+  }
+  P->hp[P->n++] = *h;
+}
+/* Scene::eye_trace — PPM/src/Scene.cpp:286-362 */
+static void ppm_eye_trace(const Ctx* cx, OraclePpm* P, const Ray* ray, int depth, v3 att, int pixel, float weight) {
+  const B200SceneDesc* d = cx->d;
+  Hit hit;
+  cx->c->rays_primary += (depth == 0);
+  cx->c->rays_secondary += (depth != 0);
+  if (!scene_intersect(cx, ray, &hit)) return;
+  const v3 p = add(ray->o, muls(ray->d, hit.t));
+  const v3 n = hit.normal;
+  const b200rt_material* m = d->materials + hit.material;
+  const int type = ppm_material_type(m);
+  if (type == 0) {
+    OracleHitPoint h; memset(&h, 0, sizeof(h));
+    h.material = hit.material; h.attenuation = att; h.w_o = normalize(sub(ray->o, p)); h.normal = n; h.position = p;
+    h.pixel = pixel; h.pixel_weight = weight;
+    ppm_add_hp(P, &h);
+    return;
+  }
+  if (depth >= d->max_depth) return;
+  const v3 w_o = normalize(sub(ray->o, p));
+  const v3 w_r = normalize(sub(muls(n, 2.0f * dot(n, w_o)), w_o));
+  Ray rr; memset(&rr, 0, sizeof(rr));
+  rr.o = add(p, muls(w_r, d->shadow_eps)); rr.d = w_r;
+  if (type == 1) {
+    ppm_eye_trace(cx, P, &rr, depth + 1, mulv(ld(m->mirror), att), pixel, weight);
+    return;
+  }
+  const v3 nl = dot(n, ray->d) < 0.0f ? n : muls(n, -1);
+  const int into = dot(n, nl) > 0.0f;
+  const float air = 1.0f;
+  const float nnt = into ? air / m->refraction_index : m->refraction_index / air;
+  const float ddn = dot(ray->d, nl);
+  const float cos2t = 1 - nnt * nnt * (1 - ddn * ddn);
+  if (cos2t < 0.0f) {
+    ppm_eye_trace(cx, P, &rr, depth + 1, mulv(ld(m->transparency), att), pixel, weight);
+    return;
+  }
+  const v3 rdir = normalize(sub(muls(ray->d, nnt), muls(n, (into ? 1 : -1) * (ddn * nnt + sqrtf(cos2t)))));
+  const float a = m->refraction_index - air, b = m->refraction_index + air;
+  const float R0 = a * a / (b * b);
+  const float ca = into ? -ddn : dot(rdir, n);
+  const float c = 1 - ca;
+  const float fres = R0 + (1 - R0) * c * c * c * c * c;
+  Ray tr; memset(&tr, 0, sizeof(tr));
+  tr.o = add(p, muls(rdir, d->shadow_eps)); tr.d = rdir;
+  const v3 ac = mulv(ld(m->transparency), att);
+  if (into) {
+    ppm_eye_trace(cx, P, &rr, depth + 1, muls(att, fres), pixel, weight);
+    ppm_eye_trace(cx, P, &tr, depth + 1, muls(ac, 1.0f - fres), pixel, weight);
+  } else {
+    ppm_eye_trace(cx, P, &tr, depth + 1, ac, pixel, weight);
+  }
+}
+/* Scene::hash — PPM/include/Scene.h:65-68 (signed products wrap; cast to unsigned) */
+static inline int64_t ppm_hash(const OraclePpm* P, int ix, int iy, int iz) {
+  const uint32_t h = ((uint32_t)ix * 73856093u) ^ ((uint32_t)iy * 19349663u) ^ ((uint32_t)iz * 83492791u);
+  return (int64_t)(h % (uint32_t)P->num_hash);
+}
+/* Scene::build_hash_grid — PPM/src/Scene.cpp:53-93 */
+static void ppm_build_grid(OraclePpm* P, int width, int height) {
+  v3 mn = V(INFINITY, INFINITY, INFINITY), mx = V(-INFINITY, -INFINITY, -INFINITY);
+  for (int64_t i = 0; i < P->n; i++) {
+    const v3 q = P->hp[i].position;
+    mn = V(fminf(mn.x, q.x), fminf(mn.y, q.y), fminf(mn.z, q.z));
+    mx = V(fmaxf(mx.x, q.x), fmaxf(mx.y, q.y), fmaxf(mx.z, q.z));
+  }
+  const v3 size = sub(mx, mn);
+  const float r0 = ((size.x + size.y + size.z) / 3.0f) / ((width + height) / 2.0f) * 2.0f * 4.0f;
+  P->initial_radius = r0;
+  mn = V(INFINITY, INFINITY, INFINITY); mx = V(-INFINITY, -INFINITY, -INFINITY);
+  P->num_hash = P->n;
+  for (int64_t i = 0; i < P->n; i++) {
+    OracleHitPoint* h = P->hp + i;
+    h->radius_squared = r0 * r0; h->n = 0; h->flux = V(0, 0, 0);
+    const v3 lo = V(h->position.x - r0, h->position.y - r0, h->position.z - r0);
+    const v3 hi = V(h->position.x + r0, h->position.y + r0, h->position.z + r0);
+    mn = V(fminf(mn.x, lo.x), fminf(mn.y, lo.y), fminf(mn.z, lo.z));
+    mx = V(fmaxf(mx.x, lo.x), fmaxf(mx.y, lo.y), fmaxf(mx.z, lo.z));
+    mn = V(fminf(mn.x, hi.x), fminf(mn.y, hi.y), fminf(mn.z, hi.z));
+    mx = V(fmaxf(mx.x, hi.x), fmaxf(mx.y, hi.y), fmaxf(mx.z, hi.z));
+  }
+  P->bbox_min = mn;
+  P->hash_scale = (float)(1.0 / ((double)r0 * 2.0));
+  free(P->cell_start); free(P->cell_items);
+  P->cell_start = (int64_t*)calloc((size_t)P->num_hash + 1, sizeof(int64_t));
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) {
+      int64_t acc = 0;
+      for (int64_t c = 0; c <= P->num_hash; c++) { const int64_t k = P->cell_start[c]; P->cell_start[c] = acc; acc += k; }
+      P->cell_items = (int32_t*)malloc(sizeof(int32_t) * (size_t)(acc ? acc : 1));
+    }
+    int64_t* fill = NULL;
+    if (pass == 1) { fill = (int64_t*)malloc(sizeof(int64_t) * (size_t)(P->num_hash + 1)); memcpy(fill, P->cell_start, sizeof(int64_t) * (size_t)(P->num_hash + 1)); }
+    for (int64_t i = 0; i < P->n; i++) {
+      const OracleHitPoint* h = P->hp + i;
+      const v3 bmin = muls(sub(V(h->position.x - r0, h->position.y - r0, h->position.z - r0), mn), P->hash_scale);
+      const v3 bmax = muls(sub(V(h->position.x + r0, h->position.y + r0, h->position.z + r0), mn), P->hash_scale);
+      for (int iz = abs((int)bmin.z); iz <= abs((int)bmax.z); iz++)
+        for (int iy = abs((int)bmin.y); iy <= abs((int)bmax.y); iy++)
+          for (int ix = abs((int)bmin.x); ix <= abs((int)bmax.x); ix++) {
+            const int64_t hv = ppm_hash(P, ix, iy, iz);
+            if (pass == 0) P->cell_start[hv]++; else P->cell_items[fill[hv]++] = (int32_t)i;
+          }
+    }
+    free(fill);
+  }
+}
+/* Scene::photon_trace — PPM/src/Scene.cpp:106-249; RNG dims of the photon key: emission 0,1; bounce b: 8b+{2,3} hemisphere,
+ * 8b+4 roulette, 8b+5 glass roulette */
+#define PPM_ALPHA 0.7f
+static void ppm_photon_trace(const Ctx* cx, OraclePpm* P, Ray ray, v3 flux, uint32_t key, OracleCounters* pc) {
+  const B200SceneDesc* d = cx->d;
+  int depth = 0;
+  for (int b = 0;; b++) {
+    depth++;
+    if (depth >= d->max_depth) return;
+    Hit hit;
+    pc->rays_shadow++; /* reused as "photon rays" */
+    if (!scene_intersect(cx, &ray, &hit)) return;
+    const v3 p = add(ray.o, muls(ray.d, hit.t));
+    const v3 n = hit.normal;
+    const v3 nl = dot(n, ray.d) < 0 ? n : muls(n, -1);
+    const b200rt_material* m = d->materials + hit.material;
+    const int type = ppm_material_type(m);
+    const uint32_t dim = 8u * (uint32_t)b;
+    if (type == 0) {
+      if (P->num_hash > 0) {
+        const v3 hh = muls(sub(p, P->bbox_min), P->hash_scale);
+        const int ix = abs((int)hh.x), iy = abs((int)hh.y), iz = abs((int)hh.z);
+        const int64_t cell = ppm_hash(P, ix, iy, iz);
+        for (int64_t k = P->cell_start[cell]; k < P->cell_start[cell + 1]; k++) {
+          OracleHitPoint* h = P->hp + P->cell_items[k];
+          const v3 v = sub(h->position, p);
+          pc->spheres_tested++; /* reused as "hit points scanned" */
+          if ((dot(h->normal, n) > 1e-3f) && (dot(v, v) <= h->radius_squared)) {
+            const float rr = (float)(((double)(h->n * PPM_ALPHA + PPM_ALPHA)) / ((double)(h->n * PPM_ALPHA) + 1.0));
+            h->radius_squared = h->radius_squared * rr;
+            h->n++;
+            pc->instances_entered++; /* reused as "photons accepted" */
+            v3 color = V(0, 0, 0);
+            const v3 w_i = neg(normalize(ray.d));
+            const b200rt_material* hm = d->materials + h->material;
+            const float cti = dot(h->normal, w_i);
+            if (!(cti > 1.0f || cti <= 0.0f)) {
+              const float sct = fmaxf(0.0f, dot(h->normal, normalize(add(h->w_o, w_i))));
+              color = mulv(add(ld(hm->diffuse), divs(muls(ld(hm->specular), powf(sct, hm->phong_exponent)), cti)), h->attenuation);
+            }
+            h->flux = muls(add(h->flux, mulv(color, flux)), rr);
+          }
+        }
+      }
+      /* sample_hemisphere(normal, d, probability) — cosine, PPM/src/Scene.cpp:15-44 */
+      const float e1 = rng_u01(key, dim + 2), e2 = rng_u01(key, dim + 3);
+      const float phi = (float)(2 * M_PI * (double)e1);
+      const float theta = asinf(sqrtf(e2));
+      const v3 dd = onb_dir(n, theta, phi);
+      const float prob = (float)((double)fmaxf(0.0f, dot(n, dd)) / M_PI);
+      v3 base = V(0, 0, 0);
+      const v3 w_i = neg(normalize(ray.d));
+      const float cti = fmaxf(0.0f, dot(n, w_i));
+      if (!(cti > 1.0f || cti <= 0.0f)) {
+        const float sct = fmaxf(0.0f, dot(nl, normalize(add(dd, w_i))));
+        base = add(ld(m->diffuse), divs(muls(ld(m->specular), powf(sct, m->phong_exponent)), cti));
+      }
+      const float cto = fmaxf(0.0f, dot(n, dd));
+      base = muls(base, cto);
+      if (rng_u01(key, dim + 4) < prob) {
+        ray.o = add(p, muls(dd, d->shadow_eps)); ray.d = dd;
+        flux = divs(mulv(base, flux), prob);
+        continue;
+      }
+      return;
+    }
+    const v3 w_o = normalize(sub(ray.o, p));
+    const v3 w_r = normalize(sub(muls(n, 2.0f * dot(n, w_o)), w_o));
+    if (type == 1) {
+      ray.o = add(p, muls(w_r, d->shadow_eps)); ray.d = w_r;
+      flux = mulv(ld(m->mirror), flux);
+      continue;
+    }
+    const int into = dot(n, nl) > 0.0f;
+    const float air = 1.0f;
+    const float nnt = into ? air / m->refraction_index : m->refraction_index / air;
+    const float ddn = dot(ray.d, nl);
+    const float cos2t = 1 - nnt * nnt * (1 - ddn * ddn);
+    if (cos2t < 0.0f) { ray.o = add(p, muls(w_r, d->shadow_eps)); ray.d = w_r; continue; }
+    const v3 rdir = normalize(sub(muls(ray.d, nnt), muls(n, (into ? 1 : -1) * (ddn * nnt + sqrtf(cos2t)))));
+    const float a = m->refraction_index - air, bb = m->refraction_index + air;
+    const float R0 = a * a / (bb * bb);
+    const float ca = into ? -ddn : dot(rdir, n);
+    const float c = 1 - ca;
+    const float fres = R0 + (1 - R0) * c * c * c * c * c;
+    if (into && rng_u01(key, dim + 5) < fres) { ray.o = add(p, muls(w_r, d->shadow_eps)); ray.d = w_r; }
+    else { ray.o = add(p, muls(rdir, d->shadow_eps)); ray.d = rdir; }
+  }
+}
+
+/* The whole PPM frame: reset_hash_grid, eye_trace_lines, build_hash_grid, trace_n_photons (ONE sequential stream,
+ * like the reference built without NDEBUG), density_estimation.  hp_out (optional): 16 floats per hit point
+ * {position, normal, w_o, attenuation, material, pixel, pixel_weight, n}. */
+int oracle_ppm(const B200SceneDesc* d, int camera_index, uint64_t seed, int64_t n_photons, double total_num_of_photons,
+               float* rgbw, float* hp_out, int64_t hp_cap, int64_t* n_hp, float* initial_radius, OracleCounters* counters) {
+  if (!d || camera_index < 0 || camera_index >= d->n_cameras || d->n_lights < 1) return -1;
+  const b200rt_camera* c = d->cameras + camera_index;
+  const int W = c->width, H = c->height, ns = c->samples_sqrt;
+  OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
+  Ctx cx = {d, &cnt};
+  OraclePpm P; memset(&P, 0, sizeof(P));
+  const uint32_t s0 = rng_mix((uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int j = 0; j < H; j++)
+    for (int i = 0; i < W; i++) {
+      const int pix = j * W + i;
+      if (ns == 1) {
+        Ray r = camera_ray(d, c, i + 0.5f, j + 0.5f, 0, 0, 0, 0.0f);
+        ppm_eye_trace(&cx, &P, &r, 0, V(1, 1, 1), pix, 1.0f);
+      } else {
+        for (int x = 0; x < ns; x++)
+          for (int y = 0; y < ns; y++) {
+            const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), (uint32_t)(x * ns + y));
+            const float sx = (x + rng_u01(key, 4)) / ns, sy = (y + rng_u01(key, 5)) / ns;
+            Ray r = camera_ray(d, c, i + sx, j + sy, 0, 0, 0, 0.0f);
+            ppm_eye_trace(&cx, &P, &r, 0, V(1, 1, 1), pix, 1.0f);
+          }
+      }
+    }
+  ppm_build_grid(&P, W, H);
+  if (initial_radius) *initial_radius = P.initial_radius;
+  /* Point_light::generate_photon — PPM/src/Point_light.cpp:7-30 (theta = 2*pi*xi: Appendix B.6) */
+  const b200rt_light* L = d->lights;
+  OracleCounters pc; memset(&pc, 0, sizeof(pc));
+  for (int64_t i = 0; i < n_photons; i++) {
+    const uint32_t key = rng_mix(rng_mix(s0 ^ 0x50484F54u, (uint32_t)i), (uint32_t)((uint64_t)i >> 32));
+    const v3 flux = muls(ld(L->intensity), (float)(M_PI * 4.0f));
+    const float phi = (float)(2 * M_PI * (double)rng_u01(key, 0));
+    const float theta = (float)(2 * M_PI * (double)rng_u01(key, 1));
+    Ray r; memset(&r, 0, sizeof(r));
+    r.d = onb_dir(V(0.0f, 1.0f, 0.0f), theta, phi);
+    r.o = ld(L->position);
+    ppm_photon_trace(&cx, &P, r, flux, key, &pc);
+  }
+  /* Scene::density_estimation — PPM/src/Scene.cpp:363-372 */
+  if (rgbw) {
+    memset(rgbw, 0, sizeof(float) * 4 * (size_t)W * H);
+    for (int64_t i = 0; i < P.n; i++) {
+      const OracleHitPoint* h = P.hp + i;
+      const float k = (float)(1.0f / (M_PI * (double)h->radius_squared * total_num_of_photons));
+      const v3 col = muls(h->flux, k);
+      float* px = rgbw + 4 * (size_t)h->pixel;
+      px[0] += col.x * h->pixel_weight; px[1] += col.y * h->pixel_weight; px[2] += col.z * h->pixel_weight;
+      px[3] += h->pixel_weight;
+    }
+  }
+  if (hp_out)
+    for (int64_t i = 0; i < P.n && i < hp_cap; i++) {
+      const OracleHitPoint* h = P.hp + i;
+      float* o = hp_out + 16 * i;
+      o[0] = h->position.x; o[1] = h->position.y; o[2] = h->position.z; o[3] = h->normal.x; o[4] = h->normal.y; o[5] = h->normal.z;
+      o[6] = h->w_o.x; o[7] = h->w_o.y; o[8] = h->w_o.z; o[9] = h->attenuation.x; o[10] = h->attenuation.y; o[11] = h->attenuation.z;
+      o[12] = (float)h->material; o[13] = (float)h->pixel; o[14] = h->pixel_weight; o[15] = (float)h->n;
+    }
+  if (n_hp) *n_hp = P.n;
+  if (counters) {
+    *counters = cnt;
+    counters->rays_shadow = pc.rays_shadow;            /* photon rays        */
+    counters->spheres_tested = pc.spheres_tested;      /* hit points scanned */
+    counters->instances_entered = pc.instances_entered; /* photons accepted   */
+  }
+  free(P.hp); free(P.cell_start); free(P.cell_items);
+  return 0;
+}
+
 /* Closest-hit on caller rays (8 floats per ray: o.xyz, time, d.xyz, unused). */
 int oracle_trace_rays(const B200SceneDesc* d, const float* rays, int64_t n, int32_t* ids, float* tout,
                       OracleCounters* counters) {
