@@ -29,6 +29,28 @@ def split_interleaved(height: int, rank: int, world: int) -> dict:
     return dict(row_begin=rank, row_end=height, row_stride=world)
 
 
+def split_samples(n_strata: int, rank: int, world: int) -> dict:
+    """RenderOpts for a sample-batch split (cfg 4): rank renders strata [begin, end) of samples_sqrt^2.
+    Pixel{sum c*w, sum w} is additive over samples, so one sum-reduce assembles the frame."""
+    b, e = split_rows(n_strata, rank, world)
+    return dict(sample_begin=b, sample_end=e)
+
+
+def split_photons(n_photons: int, rank: int, world: int) -> tuple[int, int]:
+    """(first_photon, count) of rank: the reference hands photon_count/thread_count photons to each thread
+    (PPM/src/main.cpp:74-88); here every photon index is its own RNG stream, so ranges just partition."""
+    b, e = split_rows(n_photons, rank, world)
+    return b, e - b
+
+
+def allreduce_sum(t):
+    """Sum over ranks (sample-batch frames; PPM {S.rgb, n} per hit point)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def cameras_of(n_cameras: int, rank: int, world: int) -> list[int]:
     return list(range(rank, n_cameras, world))
 

@@ -441,3 +441,43 @@ def cfg5_ppm(width=1920, height=1080, mesh_slices=(160, 158), photons_per_iterat
             "  <Materials>\n" + mats + "  </Materials>\n"
             "  <Transformations>\n    <Scaling id=\"1\">0.8 0.8 0.8</Scaling>\n    <Translation id=\"1\">0.1 0.8 -1.9</Translation>\n  </Transformations>\n"
             "  <VertexData>\n" + _rows(allv, "%.9g") + "  </VertexData>\n  <Objects>\n" + sph + mesh_xml + "  </Objects>\n</Scene>\n")
+
+
+# --------------------------------------------------------------------------- cfg 3
+def cfg3_hw3(n=362, width=1920, height=1080, spp=100, depth=3, seed=SEED, image_name="cfg3.png") -> str:
+    """Config 3 — HW3 distribution ray tracing: the cfg-2 heightfield at 2*n*n triangles (n=362 -> 262 088),
+    two AreaLights, a glossy-mirror floor slab (Roughness .15), one glass sphere, one motion-blurred sphere,
+    depth of field (ApertureSize .1, focus at the scene centre), NumSamples strata."""
+    v, f = heightfield(n, seed)
+    floor = np.array([[-6, -0.6, -6], [6, -0.6, -6], [6, -0.6, 6], [-6, -0.6, 6]], np.float32)
+    sph_c = np.array([[-1.6, 1.1, 1.4], [1.9, 0.9, 0.8], [0.2, 1.5, -1.3]], np.float32)
+    allv = np.concatenate([v, floor, sph_c], 0)
+    fb, cb = len(v), len(v) + 4
+    mats = (_material_xml(1, [0.3, 0.3, 0.3], [0.45, 0.55, 0.35], [0.2, 0.2, 0.2], 20)
+            + _material_xml(2, [0.1, 0.1, 0.1], [0.2, 0.2, 0.25], [0.4, 0.4, 0.4], 60, mirror=[0.55, 0.55, 0.55], roughness=0.15)
+            + _material_xml(3, [0, 0, 0], [0.02, 0.02, 0.02], [0.2, 0.2, 0.2], 80, transparency=[0.9, 0.95, 0.9], refr=1.5)
+            + _material_xml(4, [0.3, 0.3, 0.3], [0.7, 0.3, 0.2], [0.3, 0.3, 0.3], 10)
+            + _material_xml(5, [0.3, 0.3, 0.3], [0.2, 0.4, 0.8], [0.6, 0.6, 0.6], 40))
+    tri = (f'    <Triangle id="1"><Material>2</Material><Indices>{fb + 1} {fb + 4} {fb + 3}</Indices></Triangle>\n'
+           f'    <Triangle id="2"><Material>2</Material><Indices>{fb + 1} {fb + 3} {fb + 2}</Indices></Triangle>\n')
+    sph = (f'    <Sphere id="1"><Material>3</Material><Center>{cb + 1}</Center><Radius>0.7</Radius></Sphere>\n'
+           f'    <Sphere id="2"><Material>4</Material><Center>{cb + 2}</Center><Radius>0.5</Radius>'
+           '<MotionBlur>0.6 0.1 0</MotionBlur></Sphere>\n'
+           f'    <Sphere id="3"><Material>5</Material><Center>{cb + 3}</Center><Radius>0.8</Radius></Sphere>\n')
+    aspect = width / height
+    return ("<Scene>\n  <BackgroundColor>30 40 60</BackgroundColor>\n  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
+            f"  <MaxRecursionDepth>{depth}</MaxRecursionDepth>\n  <Cameras>\n    <Camera id=\"1\">\n"
+            "      <Position>0 3.1 5.6</Position>\n      <Gaze>0 -0.62 -1</Gaze>\n      <Up>0 1 0</Up>\n"
+            f"      <NearPlane>{_f([-0.45 * aspect, 0.45 * aspect, -0.45, 0.45])}</NearPlane>\n"
+            "      <NearDistance>1</NearDistance>\n      <FocusDistance>6.2</FocusDistance>\n      <ApertureSize>0.1</ApertureSize>\n"
+            f"      <ImageResolution>{width} {height}</ImageResolution>\n      <NumSamples>{spp}</NumSamples>\n"
+            f"      <ImageName>{image_name}</ImageName>\n    </Camera>\n  </Cameras>\n"
+            "  <Lights>\n    <AmbientLight>25 25 25</AmbientLight>\n"
+            '    <AreaLight id="1"><Position>-3 6 3</Position><Intensity>5000 4800 4500</Intensity>'
+            '<EdgeVector1>1.5 0 0</EdgeVector1><EdgeVector2>0 0 1.5</EdgeVector2></AreaLight>\n'
+            '    <AreaLight id="2"><Position>3 5 -2</Position><Intensity>2500 3000 3500</Intensity>'
+            '<EdgeVector1>1 0 0</EdgeVector1><EdgeVector2>0 0 1</EdgeVector2></AreaLight>\n'
+            "  </Lights>\n  <Materials>\n" + mats + "  </Materials>\n  <VertexData>\n"
+            + _rows(allv, "%.9g") + "  </VertexData>\n  <Objects>\n"
+            + '    <Mesh id="1" shadingMode="smooth">\n      <Material>1</Material>\n      <Faces>\n' + _rows(f + 1, "%d")
+            + "      </Faces>\n    </Mesh>\n" + tri + sph + "  </Objects>\n</Scene>\n")

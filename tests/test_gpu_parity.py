@@ -162,3 +162,24 @@ def test_hw7_stochastic_matches_oracle_with_matched_sampling(gpu, tmp_path, kw):
         assert np.median(rel) < 1e-5, float(np.median(rel))
         assert np.mean(rel.max(-1) < 1e-3) >= 0.5, float(np.mean(rel.max(-1) < 1e-3))
         assert abs(a.mean() - b.mean()) <= 0.01 * b.mean(), (float(a.mean()), float(b.mean()))
+
+
+def test_hw3_distribution_matches_oracle_with_matched_sampling(gpu):
+    """cfg 3 semantics at test size: strata + per-sample time, DOF, area lights, glossy mirror, glass,
+    motion-blurred sphere, 3x3 Gaussian splat (float atomics: only the accumulation order differs)."""
+    xml = scenes.cfg3_hw3(n=32, width=96, height=64, spp=16, depth=3)
+    sc = scene.Scene(xml, "hw3")
+    rgbw, st = sc.render_image(0, seed=77)
+    o_rgbw, _, _, cnt = cpu.render(sc.host, 0, seed=77)
+    assert (st.rays_primary, st.rays_shadow, st.rays_secondary) == (cnt.rays_primary, cnt.rays_shadow, cnt.rays_secondary)
+    a = rgbw[..., :3] / rgbw[..., 3:]
+    b = o_rgbw[..., :3] / o_rgbw[..., 3:]
+    rel = np.abs(a - b) / (np.abs(b) + 1.0)
+    assert rel.max() < 1e-4, float(rel.max())          # tolerance: 1e-4 relative (+1 absolute floor)
+    cmp = image.compare_8bit(image.quantise(rgbw, sc.semantics), image.quantise(o_rgbw, sc.semantics))
+    assert cmp["within1"] >= 0.999, cmp
+    # sample-batch split (multi-GPU primitive): partial frames over disjoint strata add up to the frame
+    half = sc.cameras[0]["num_samples"] // 2
+    p0, _ = sc.render_image(0, seed=77, sample_begin=0, sample_end=half)
+    p1, _ = sc.render_image(0, seed=77, sample_begin=half, sample_end=16)
+    assert np.allclose(p0 + p1, rgbw, rtol=1e-5, atol=1e-3)

@@ -69,3 +69,21 @@ def test_oracle_hw7_stochastic_statistics_vs_reference(tmp_path, pt):
     noise = np.sqrt(((imgs[0] - imgs[1]) ** 2).mean())
     rmse = np.sqrt(((imgs[0] - ref) ** 2).mean())
     assert rmse <= 1.35 * noise + 0.5, (rmse, noise)
+
+
+def test_oracle_hw3_distribution_statistics_vs_reference():
+    """cfg 3 (area lights, DOF, glossy mirror, motion blur, 3x3 Gaussian splat): clock-seeded in the reference,
+    so validated statistically against the untouched HW3 binary at equal sample count."""
+    if not cpu.have_ref("hw3"):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.cfg3_hw3(n=24, width=48, height=36, spp=64, depth=3)
+    ref = list(cpu.run_reference("hw3", xml)["images"].values())[0].astype(np.float64)
+    hs = scene.HostScene(scene.parse_xml(xml, "hw3"))
+    q = []
+    for seed in (1, 2):
+        rgbw, _, _, _ = cpu.render(hs, 0, seed=seed)
+        q.append(image.quantise(rgbw, hs.spec.semantics).astype(np.float64))
+    assert abs(q[0].mean() - ref.mean()) <= 0.01 * ref.mean()
+    noise = np.sqrt(((q[0] - q[1]) ** 2).mean())
+    assert np.sqrt(((q[0] - ref) ** 2).mean()) <= 1.35 * noise + 0.5
