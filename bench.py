@@ -1,16 +1,21 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric (Mrays/s, ms/frame) on config 2:
-HW2-feature BVH scene in the HW3 dialect, 1 048 352-triangle mesh + 8 instances
-+ 4 spheres, 2 point lights, mirror depth 2, 1920x1080, 1 spp.
+"""bench.py — BASELINE.json's metric (Mrays/s, ms/frame) on the B200 rendering core.
 
-  python bench.py --gpus N --steps K --warmup W            # the CUDA core (one rank per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU renderer on the host cores
+  python bench.py --gpus N --steps K --warmup W                 # config 2 (the default, see below)
+  python bench.py --config cfg4 --spp 64 ...                    # any other BASELINE config
+  python bench.py --impl reference --gpus N --steps K ...       # the reference's own CPU renderer on the host cores
 
-A step = one pass of the hot path (generate -> extend -> shade -> shadow ->
-combine) over one frame per rank.  At N > 1 the frames are independent units
-(rank r renders camera r of an orbit; the scene is replicated): no data-path
-collective, "scaling": "weak".  `--split rows` instead splits ONE frame into row
-bands and gathers them over NCCL (strong scaling; used for the heavy configs).
+Default workload = cfg2, the configuration the metric is quoted on that fits one GPU: HW2-feature BVH scene in
+the HW3 dialect, 1 048 352-triangle mesh + 8 instances + 4 spheres, 2 point lights, mirror depth 2, 1920x1080, 1 spp.
+
+A step = one pass of the hot path over one batch of work per rank:
+  cfg1..cfg4  one frame: generate -> (extend -> shade_a -> shadow -> shade_b)* -> combine
+  cfg5        one photon pass (PhotonCountPerIteration photons): emit -> (extend -> deposit/scatter)*
+Multi-GPU (one process per GPU, scene replicated):
+  --split cameras  rank r renders frame r of a camera orbit; no data-path collective ("weak")      [default, cfg1-3]
+  --split rows     one frame, contiguous row bands, one all-gather of float4 bands over NCCL ("strong")
+  --split samples  one frame, strata split, one all-reduce(sum) of Pixel{sum c*w, sum w} ("strong") [default, cfg4]
+  cfg5             photons of the pass split, all-reduce(sum) of {S.rgb, n} per hit point ("strong")
 """
 from __future__ import annotations
 
@@ -19,6 +24,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -27,7 +33,37 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/sec"
 UNIT = "Mrays/s"
-WORKLOAD = "cfg2: HW3-dialect BVH scene, 1048352-tri heightfield + 8 instances + 4 spheres, 2 point lights, mirror depth 2, 1920x1080, 1 spp"
+
+
+def workloads(args):
+    """name -> dict(tree, xml(rank), base_dir, desc).  Scenes are generated (seeded) on the fly: data = synthetic."""
+    from ceng795_b200 import scenes
+    assets = os.path.join(tempfile.gettempdir(), "b200rt_bench_assets")
+    os.makedirs(assets, exist_ok=True)
+    spp4 = args.spp or 64
+    return {
+        "cfg1": dict(tree="hw1", xml=lambda r: scenes.cfg1_hw1(), base_dir=None,
+                     desc="cfg1: HW1 scene, 64 spheres + 2 meshes (2000 tris) + 10 triangles, 3 point lights, "
+                          "Blinn-Phong + mirror depth 6, 800x800, 1 spp (brute force over all primitives, like HW1)"),
+        "cfg2": dict(tree="hw3", xml=lambda r: scenes.cfg2_hw3(cam_angle_deg=45.0 * r), base_dir=None,
+                     desc="cfg2: HW3-dialect BVH scene, 1048352-tri heightfield + 8 instances + 4 spheres, "
+                          "2 point lights, mirror depth 2, 1920x1080, 1 spp"),
+        "cfg3": dict(tree="hw3", xml=lambda r: scenes.cfg3_hw3(spp=args.spp or 100), base_dir=None,
+                     desc=f"cfg3: HW3 distribution ray tracing, 262088-tri mesh, 2 area lights, DOF, glossy mirror, "
+                          f"glass, motion blur, 1920x1080, {args.spp or 100} spp"),
+        "cfg4": dict(tree="hw7", base_dir=assets,
+                     xml=lambda r: scenes.hw7_scene(assets, width=1920, height=1080, n=224, mesh_slices=(224, 225),
+                                                    spp=spp4, depth=4, path_tracing=True, importance=True,
+                                                    stochastic_lights=True, perlin=True, light_scale=0.25),
+                     desc=f"cfg4: HW7 path tracing (importance sampling, depth 4), 100k-tri textured heightfield + "
+                          f"7 instances of a 100k-tri mesh, 5 BRDFs, image + Perlin textures, LightMesh + LightSphere + "
+                          f"area/point/spot/directional lights, 1920x1080, {spp4} spp"
+                          + ("" if args.spp == 4096 else " (BASELINE: 4096 spp; --spp 4096 runs it)")),
+        "cfg5": dict(tree="ppm", xml=lambda r: scenes.cfg5_ppm(photons_per_iteration=args.photons or 10_000_000),
+                     base_dir=None,
+                     desc=f"cfg5: PPM, closed box + mirror sphere + glass sphere + 50240-tri mesh, 1 point light, depth 8, "
+                          f"1920x1080 eye pass, {args.photons or 10_000_000} photons per pass (a step = one pass)"),
+    }
 
 
 def peaks():
@@ -90,99 +126,96 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def orbit_xml(rank: int):
-    """Camera r of the orbit: the canonical cfg2 camera rotated by r*45 degrees about +y."""
-    from ceng795_b200 import scenes
-    return scenes.cfg2_hw3(cam_angle_deg=45.0 * rank)
+# ------------------------------------------------------------------ reference CPU path
+def reference_sample(args, wl, rays_per_step=None, sample_rays=None):
+    """One bounded sample of the reference's own CPU implementation of the workload on this box's host cores.
+    Returns dict(ms, rays, cores, kind, sample).  rays_per_step: ray count of the FULL step measured on the
+    device (the binaries print only time); scaled to the sample."""
+    from ceng795_b200 import scene, scenes
+    from oracle import cpu
+    tree = wl["tree"]
+    name = args.config
+    if name == "cfg3":
+        spp, full = 4, (args.spp or 100)
+        xml = scenes.cfg3_hw3(spp=spp)
+        frac, what = spp / full, f"{spp} of {full} spp of the same frame"
+    elif name == "cfg4":
+        spp, full = 4, (args.spp or 64)
+        xml = wl["xml"](0).replace(f"<NumSamples>{full}</NumSamples>", f"<NumSamples>{spp}</NumSamples>")
+        frac, what = spp / full, f"{spp} of {full} spp of the same frame"
+    elif name == "cfg5":
+        full = args.photons or 10_000_000
+        n = 400_000
+        xml = scenes.cfg5_ppm(photons_per_iteration=n, iterations=1)
+        frac, what = n / full, f"{n} of the pass's {full} photons (PPM binary built with -DNDEBUG, all threads)"
+    else:
+        xml = wl["xml"](0)
+        frac, what = 1.0, "1 full frame of the same XML"
+    if not cpu.have_ref(tree):
+        # the oracle port (OpenMP) on a band of rows
+        spec = scene.parse_xml(xml, tree, base_dir=wl["base_dir"])
+        hs = scene.HostScene(spec)
+        H = spec.cameras[0]["height"]
+        band = (H // 2 - 30, H // 2 + 30)
+        t0 = time.perf_counter()
+        if tree == "ppm":
+            _, _, _, cnt = cpu.ppm(hs, 0, n_photons=100_000, want_hit_points=False)
+            rays = cnt.rays_shadow
+        else:
+            _, _, _, cnt = cpu.render(hs, 0, rows=band)
+            rays = cnt.rays_total
+        ms = (time.perf_counter() - t0) * 1e3
+        return dict(ms=ms, rays=rays, cores=os.cpu_count(), kind="port",
+                    sample=f"rows {band[0]}..{band[1]} through the C oracle port (OpenMP)")
+    r = cpu.run_reference(tree, xml, workdir=wl["base_dir"])
+    ms = r["ms"]["photon"] if tree == "ppm" else list(r["ms"].values())[0]
+    if sample_rays is not None:
+        rays = sample_rays
+    elif rays_per_step is None:
+        spec = scene.parse_xml(xml, tree, base_dir=wl["base_dir"])
+        hs = scene.HostScene(spec)
+        if tree == "ppm":
+            _, _, _, cnt = cpu.ppm(hs, 0, n_photons=int(frac * (args.photons or 10_000_000)), want_hit_points=False)
+            rays = cnt.rays_shadow
+        else:
+            _, _, _, cnt = cpu.render(hs, 0)   # the restatement's counters (pinned to the device's in tests/)
+            rays = cnt.rays_total
+    else:
+        rays = rays_per_step * frac
+    return dict(ms=ms, rays=rays, cores=r["threads"], kind="reference",
+                sample=f"{what} through the untouched {tree.upper()} binary (oracle/_ref), timed by its own timer; "
+                       "ray count = the device's for the same work (pinned to the oracle's counters by tests/)")
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    from ceng795_b200 import scene, scenes
-    from oracle import cpu
-    xml = scenes.cfg2_hw3()
-    spec = scene.parse_xml(xml, "hw3")
-    hs = scene.HostScene(spec)
-    have = cpu.have_ref("hw3")
-    cores = os.cpu_count() or 1
-    H = spec.cameras[0]["height"]
-    if have:
-        kind = "reference"
-        # one full frame through the untouched HW3 binary tells us how many frames fit in the budget
-        r = cpu.run_reference("hw3", xml)
-        first_ms = list(r["ms"].values())[0]
-        cores = r["threads"]
-        # ray count of a frame: the oracle restatement's counters (the binary reports only time)
-        _, _, _, cnt = cpu.render(hs, 0)
-        rays = cnt.rays_total
-        budget_s = 240.0
-        full = (args.steps + args.warmup) * first_ms / 1e3 <= budget_s
-    else:
-        kind = "port"
-        full = False
-        first_ms = None
-        rays = None
-    times = []
-    if have and full:
-        sample = "full frame per step through oracle/_ref/hw3_raytracer (its own 'is saved in' timer)"
-        for k in range(args.warmup + args.steps):
-            r = cpu.run_reference("hw3", xml)
-            if k >= args.warmup:
-                times.append(list(r["ms"].values())[0])
-        ms = sum(times) / len(times)
-        rays_step = rays
-    else:
-        # bounded sample: a band of rows through the OpenMP oracle port, all host threads
-        band = (H // 2 - 60, H // 2 + 60)
-        sample = f"rows {band[0]}..{band[1]} of the frame per step through the C oracle port (OpenMP, {cores} threads)"
-        kind = "port"
-        rays_step = None
-        for k in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            _, _, _, cnt = cpu.render(hs, 0, rows=band)
-            dt = (time.perf_counter() - t0) * 1e3
-            if k >= args.warmup:
-                times.append(dt)
-            rays_step = cnt.rays_total
-        ms = sum(times) / len(times)
-    value = rays_step / ms / 1e3
+    wl = workloads(args)[args.config]
+    times, rays = [], None
+    s = None
+    budget_s = 240.0
+    t_all = time.perf_counter()
+    for k in range(args.warmup + args.steps):
+        s = reference_sample(args, wl, sample_rays=rays)   # ray count: computed once (it is the same frame)
+        if k >= args.warmup:
+            times.append(s["ms"])
+        rays = s["rays"]
+        if time.perf_counter() - t_all > budget_s and times:
+            break
+    ms = sum(times) / len(times)
+    value = rays / ms / 1e3
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step": rays_step},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "config": {"workload": wl["desc"], "rays_per_step": rays},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": s["cores"], "kind": s["kind"], "sample": s["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
-def cpu_baseline(xml, host_scene, rays_per_frame):
-    """Reference CPU path on this box's host cores, one bounded sample (rank 0, N=1 only)."""
-    from oracle import cpu
-    try:
-        if cpu.have_ref("hw3"):
-            r = cpu.run_reference("hw3", xml)
-            ms = list(r["ms"].values())[0]
-            return {"value": rays_per_frame / ms / 1e3, "unit": UNIT, "cores": r["threads"], "kind": "reference",
-                    "ms_per_frame": ms,
-                    "sample": "1 full frame of the same XML through the untouched HW3 binary (oracle/_ref), "
-                              "timed by its own 'is saved in' timer; ray count = this frame's (pinned to the "
-                              "oracle's count by tests/test_gpu_parity.py)"}
-        H = host_scene.spec.cameras[0]["height"]
-        band = (H // 2 - 60, H // 2 + 60)
-        t0 = time.perf_counter()
-        _, _, _, cnt = cpu.render(host_scene, 0, rows=band)
-        ms = (time.perf_counter() - t0) * 1e3
-        return {"value": cnt.rays_total / ms / 1e3, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                "sample": f"rows {band[0]}..{band[1]} through the C oracle port (OpenMP)"}
-    except Exception as e:  # the baseline is reported, never required
-        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
-
-
+# ------------------------------------------------------------------ the CUDA core
 def run_b200(args):
-    import numpy as np
     import torch
     from ceng795_b200 import dist as rdist
     from ceng795_b200 import scene
@@ -193,15 +226,26 @@ def run_b200(args):
     torch.cuda.set_device(local)
     import torch.distributed as tdist
 
-    split = args.split
-    xml = orbit_xml(rank if split == "cameras" else 0)
-    sc = scene.Scene(xml, "hw3", device=local)
+    wl = workloads(args)[args.config]
+    ppm = wl["tree"] == "ppm"
+    split = args.split or ("samples" if args.config == "cfg4" else "cameras")
+    if ppm:
+        split = "photons"
+    xml = wl["xml"](rank if split == "cameras" else 0)
+    sc = scene.Scene(xml, wl["tree"], device=local, base_dir=wl["base_dir"])
     W, H = sc.image_size(0)
     opts = {}
-    if split == "rows" and world > 1:
+    if world > 1 and split == "rows":
         b, e = rdist.split_rows(H, rank, world)
         opts = dict(row_begin=b, row_end=e)
+    if world > 1 and split == "samples":
+        ns = sc.host.desc.cameras[0].samples_sqrt ** 2
+        opts = rdist.split_samples(ns, rank, world)
     stream = torch.cuda.ExternalStream(sc._L.b200rt_scene_stream(sc._scene), device=local)
+    photons = args.photons or (sc.spec.ppm["photon_count_per_iteration"] if ppm else 0)
+    ph_first, ph_cnt = rdist.split_photons(photons, rank, world) if ppm else (0, 0)
+    pass_no = [0]
+    eye = sc.eye_trace_lines(0, seed=args.seed) if ppm else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -210,20 +254,33 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def one_step():
-        p, st = sc.render_device(0, **opts)
-        if split == "rows" and world > 1:
-            # tiles gathered over NVLink: one all-gather of the row bands
+        if ppm:
+            st = sc.trace_n_photons(ph_cnt, first_photon=pass_no[0] * photons + ph_first, seed=args.seed)
+            pass_no[0] += 1
+            if world > 1:
+                p, n = sc.ppm_export()
+                rdist.allreduce_sum(rdist.tensor_from_ptr(p, (n, 4), local).clone())   # {S.rgb, n} over NVLink
+            return st
+        p, st = sc.render_device(0, seed=args.seed, **opts)
+        if world > 1 and split == "rows":
             frame = rdist.tensor_from_ptr(p, (H, W, 4), local)
             rdist.gather_rows(frame[opts["row_begin"]:opts["row_end"]], H, rank, world)
+        elif world > 1 and split == "samples":
+            rdist.allreduce_sum(rdist.tensor_from_ptr(p, (H, W, 4), local))
         return st
 
-    # ---- device-resident timing ------------------------------------------------
     for _ in range(args.warmup):
         one_step()
-    agg = {k: 0 for k in ("rays_primary", "rays_shadow", "rays_secondary", "nodes_visited", "tris_tested",
-                          "spheres_tested", "instances_entered", "sh_nodes_visited", "sh_tris_tested",
-                          "sh_spheres_tested", "sh_instances_entered", "launches")}
-    ms_stage = {"ms_generate": 0.0, "ms_extend": 0.0, "ms_shade": 0.0, "ms_shadow": 0.0}
+    if ppm:
+        keys = ("photon_rays", "cell_scans", "deposits", "nodes_visited", "tris_tested", "launches")
+        ms_keys = ("ms_extend", "ms_deposit")
+    else:
+        keys = ("rays_primary", "rays_shadow", "rays_secondary", "nodes_visited", "tris_tested", "spheres_tested",
+                "instances_entered", "sh_nodes_visited", "sh_tris_tested", "sh_spheres_tested", "sh_instances_entered",
+                "launches")
+        ms_keys = ("ms_generate", "ms_extend", "ms_shade", "ms_shadow")
+    agg = {k: 0 for k in keys}
+    ms_stage = {k: 0.0 for k in ms_keys}
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -240,19 +297,28 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
-    rays = agg["rays_primary"] + agg["rays_shadow"] + agg["rays_secondary"]
+    rays = agg["photon_rays"] if ppm else agg["rays_primary"] + agg["rays_shadow"] + agg["rays_secondary"]
 
     # ---- end to end through the C ABI with HOST buffers ---------------------------
     pinned = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
     out = pinned.numpy()
+
+    def e2e_step():
+        if ppm:
+            st = sc.trace_n_photons(ph_cnt, first_photon=pass_no[0] * photons + ph_first, seed=args.seed)
+            pass_no[0] += 1
+            sc.density_estimation(photons * pass_no[0], out=out)
+            return st.photon_rays
+        _, st = sc.render_image(0, out=out, seed=args.seed, **opts)
+        return st.rays_total
+
     for _ in range(max(1, min(3, args.warmup))):
-        sc.render_image(0, out=out, **opts)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     e2e_rays = 0
     for _ in range(args.steps):
-        _, st = sc.render_image(0, out=out, **opts)
-        e2e_rays += st.rays_total
+        e2e_rays += e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
@@ -269,48 +335,68 @@ def run_b200(args):
         return 0
 
     hbm, hbm_src = peaks()
-    n_closest = agg["rays_primary"] + agg["rays_secondary"]
-    ext_bytes = (64 * agg["nodes_visited"] + 48 * agg["tris_tested"] + 20 * agg["spheres_tested"]
-                 + 112 * agg["instances_entered"] + (32 + 24) * n_closest)
-    sh_bytes = (64 * agg["sh_nodes_visited"] + 48 * agg["sh_tris_tested"] + 20 * agg["sh_spheres_tested"]
-                + 112 * agg["sh_instances_entered"] + (36 + 1) * agg["rays_shadow"])
+    if ppm:
+        n_closest = agg["photon_rays"]
+        ext_bytes = 64 * agg["nodes_visited"] + 48 * agg["tris_tested"] + (32 + 24) * n_closest
+        n_ext_launch = max(1, args.steps * (sc.spec.max_depth - 1))
+        kernel = "k_trace_fast<false,7> (photon closest-hit traversal)"
+        per_ray = {"nodes": agg["nodes_visited"] / max(1, n_closest), "tris": agg["tris_tested"] / max(1, n_closest),
+                   "hit_points_scanned_per_photon_ray": agg["cell_scans"] / max(1, n_closest)}
+        extra = {"deposit_kernel_bytes": 32 * agg["cell_scans"] + 16 * agg["deposits"]}
+    else:
+        n_closest = agg["rays_primary"] + agg["rays_secondary"]
+        ext_bytes = (64 * agg["nodes_visited"] + 48 * agg["tris_tested"] + 20 * agg["spheres_tested"]
+                     + 112 * agg["instances_entered"] + (32 + 24) * n_closest)
+        sh_bytes = (64 * agg["sh_nodes_visited"] + 48 * agg["sh_tris_tested"] + 20 * agg["sh_spheres_tested"]
+                    + 112 * agg["sh_instances_entered"] + (36 + 1) * agg["rays_shadow"])
+        sh_gbs = sh_bytes / (ms_stage["ms_shadow"] * 1e-3) / 1e9 if ms_stage["ms_shadow"] > 0 else None
+        n_ext_launch = max(1, args.steps * (sc.spec.max_depth + 1))
+        kernel = ("k_extend_hw1 (brute-force closest hit, shared-memory triangle tiles)" if wl["tree"] == "hw1" else
+                  f"k_trace_fast<false,{7 if wl['tree'] == 'hw7' else 2}> (closest-hit traversal, SAH tree + reference gate)")
+        per_ray = {"nodes": agg["nodes_visited"] / max(1, n_closest), "tris": agg["tris_tested"] / max(1, n_closest)}
+        extra = {"shadow_kernel": {"achieved": sh_gbs, "frac": (sh_gbs / hbm) if sh_gbs else None,
+                                   "nodes_per_ray": agg["sh_nodes_visited"] / max(1, agg["rays_shadow"])}}
     ext_gbs = ext_bytes / (ms_stage["ms_extend"] * 1e-3) / 1e9 if ms_stage["ms_extend"] > 0 else None
-    sh_gbs = sh_bytes / (ms_stage["ms_shadow"] * 1e-3) / 1e9 if ms_stage["ms_shadow"] > 0 else None
-    n_ext_launch = args.steps * 3
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("k_extend_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get(args.config, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    frames = world if split == "cameras" else 1
     line = {
         "metric": METRIC, "value": rays / ms_total / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak" if split == "cameras" else "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "split": split, "frames_per_step": world if split == "cameras" else 1,
+        "config": {"workload": wl["desc"], "split": split, "frames_per_step": frames,
                    "rays_per_step": rays / args.steps,
-                   "l2": "working set (112 MB scene + ~1 GB wavefront pool per frame) exceeds the 126 MB L2; no explicit flush",
+                   "l2": "working set (scene + ~1 GB wavefront pool per step) exceeds the 126 MB L2; no explicit flush",
                    "scene_bytes": int(sc._L.b200rt_scene_bytes(sc._scene))},
         "ms_per_frame": ms_total / args.steps,
-        "stage_ms_per_frame": {k: v / args.steps for k, v in ms_stage.items()},
-        "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": UNIT, "ms_per_frame": e2e_s * 1e3 / args.steps,
-                "h2d_bytes_per_step": 176 + 64, "d2h_bytes_per_step": H * W * 16 * (world if split == "cameras" else 1)},
+        "stage_ms_per_step": {k: v / args.steps for k, v in ms_stage.items()},
+        "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": UNIT, "ms_per_step": e2e_s * 1e3 / args.steps,
+                "h2d_bytes_per_step": 176 + 64, "d2h_bytes_per_step": H * W * 16 * frames},
         "gpu_launches": launches_all,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_trace_fast<false,2> (closest-hit traversal, SAH tree + reference gate)", "achieved": ext_gbs,
-                     "peak": hbm, "peak_source": hbm_src, "unit": "GB/s",
-                     "frac": (ext_gbs / hbm) if ext_gbs else None, "traffic": traffic,
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": ext_gbs, "peak": hbm, "peak_source": hbm_src,
+                     "unit": "GB/s", "frac": (ext_gbs / hbm) if ext_gbs else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": ext_bytes / n_ext_launch,
-                     "avg_launch_ms": ms_stage["ms_extend"] / n_ext_launch,
-                     "per_ray": {"nodes": agg["nodes_visited"] / max(1, n_closest),
-                                 "tris": agg["tris_tested"] / max(1, n_closest)},
-                     "shadow_kernel": {"achieved": sh_gbs, "frac": (sh_gbs / hbm) if sh_gbs else None,
-                                       "nodes_per_ray": agg["sh_nodes_visited"] / max(1, agg["rays_shadow"])}},
+                     "avg_launch_ms": ms_stage["ms_extend"] / n_ext_launch, "per_ray": per_ray, **extra},
     }
-    if world == 1:
-        line["cpu_baseline"] = cpu_baseline(xml, sc.host, rays / args.steps)
+    if ppm:
+        line["config"]["photons_per_step"] = photons
+        line["config"]["hit_points"] = int(eye.hit_points)
+        line["photons_per_s"] = photons * args.steps / (ms_total * 1e-3)
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            s = reference_sample(args, wl, rays_per_step=rays / args.steps)
+            line["cpu_baseline"] = {"value": s["rays"] / s["ms"] / 1e3, "unit": UNIT, "cores": s["cores"],
+                                    "kind": s["kind"], "ms": s["ms"], "sample": s["sample"]}
+        except Exception as e:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
+                                    "sample": repr(e)}
     print(json.dumps(line))
     return 0
 
@@ -321,7 +407,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--split", default="cameras", choices=["cameras", "rows"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--split", default=None, choices=["cameras", "rows", "samples"])
+    ap.add_argument("--spp", type=int, default=None, help="NumSamples override for cfg3 / cfg4")
+    ap.add_argument("--photons", type=int, default=None, help="photons per pass override for cfg5")
+    ap.add_argument("--seed", type=int, default=795)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3

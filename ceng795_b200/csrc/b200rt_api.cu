@@ -332,6 +332,7 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
 void ppm_free(b200rt_scene* sc) {
   HitPoints& H = sc->HP;
   void* ptrs[] = {H.count, H.pos, H.nrm, H.wo, H.att, H.n, H.S, sc->G.cell_count, sc->G.cell_start, sc->G.items,
+                  sc->G.cell_pos,
                   sc->d_pc, sc->d_rtab, sc->d_export, sc->d_scan_tmp};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -475,8 +476,10 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
     entries = total;
     if (entries > sc->items_capacity) {
       if (G.items) cudaFree(G.items);
-      G.items = nullptr;
+      if (G.cell_pos) cudaFree(G.cell_pos);
+      G.items = nullptr; G.cell_pos = nullptr;
       CK(cudaMalloc((void**)&G.items, sizeof(unsigned int) * (entries + 1)));
+      CK(cudaMalloc((void**)&G.cell_pos, sizeof(float4) * (entries + 1)));
       sc->items_capacity = entries + 1;
     }
     CK(cudaMemcpyAsync(G.cell_count, G.cell_start, sizeof(unsigned int) * ((size_t)n_hp + 1), cudaMemcpyDeviceToDevice, st));

@@ -27,7 +27,9 @@ struct PpmGrid {
   uint32_t num_hash;
   unsigned int* cell_count;  // num_hash + 1 (becomes the fill cursor)
   unsigned int* cell_start;  // num_hash + 1
-  unsigned int* items;
+  unsigned int* items;       // unused by the photon pass (kept for tests / debugging)
+  float4* cell_pos;          // per grid entry, in cell order: hit-point position xyz, as_float(hit-point index) —
+                             // a photon streams its cell's entries as contiguous 16-byte records
   v3 bbox_min;
   float hash_scale, r0, r0sq;
   const float* rtab;         // R(n) for n < PPM_RTAB
@@ -185,7 +187,12 @@ __global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uin
           const uint32_t hv = ppm_hash(G.num_hash, ix, iy, iz);
           const unsigned int at = atomicAdd(&G.cell_count[hv], 1u);
           if (mode == 1) {
-            if (at < items_capacity) G.items[at] = i; else PC->grid_overflow = 1;
+            if (at < items_capacity) {
+              G.items[at] = i;
+              G.cell_pos[at] = make_float4(q.x, q.y, q.z, __uint_as_float(i));
+            } else {
+              PC->grid_overflow = 1;
+            }
           }
         }
   }
@@ -231,8 +238,9 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_photon_shade(DScene S, Pool P,
     const float4 ha = P.hit_a[slot];
     const uint32_t top_ref = __float_as_uint(ha.w);
     const bool hit = act && B200RT_REF_KIND(top_ref) != B200RT_KIND_NONE;
-    bool cont = false;
+    bool cont = false, dep = false;
     v3 p = mk3(0, 0, 0), ndir = mk3(0, 0, 0), nflux = mk3(0, 0, 0);
+    v3 dep_n = mk3(0, 0, 0), dep_flux = mk3(0, 0, 0), dep_wi = mk3(0, 0, 0);
     uint32_t key = 0, b = 0;
     if (hit) {
       const float4 ro = P.ray_o[slot], rd = P.ray_d[slot], fl = P.rec0[slot];
@@ -248,43 +256,8 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_photon_shade(DScene S, Pool P,
       const b200rt_material& m = S.mats[sf.material];
       const int type = ppm_material_type(m);
       if (type == 0) {
-        if (G.num_hash > 0) {
-          const v3 hh = (p - G.bbox_min) * G.hash_scale;
-          const uint32_t cell = ppm_hash(G.num_hash, abs((int)hh.x), abs((int)hh.y), abs((int)hh.z));
-          const unsigned int c0 = G.cell_start[cell], c1 = G.cell_start[cell + 1];
-          const v3 w_i = -normalize(dir);
-          for (unsigned int q = c0; q < c1; q++) {
-            const unsigned int hi = G.items[q];
-            const float4 hp = HP.pos[hi], hn = HP.nrm[hi];
-            scans++;
-            const v3 hnrm = mk3(hn.x, hn.y, hn.z);
-            if (!(dot(hnrm, n) > 1e-3f)) continue;
-            const v3 v = mk3(hp.x, hp.y, hp.z) - p;
-            const float d2 = dot(v, v);
-            // claim index n under the radius the reference would test against: r2(n) = r0^2 * R(n)
-            unsigned int n_old = *((volatile unsigned int*)(HP.n + hi));
-            bool accepted = false;
-            for (;;) {
-              if (!(d2 <= G.r0sq * ppm_R(G, n_old))) break;
-              const unsigned int prev = atomicCAS(HP.n + hi, n_old, n_old + 1u);
-              if (prev == n_old) { accepted = true; break; }
-              n_old = prev;
-            }
-            if (!accepted) continue;
-            deposits++;
-            const b200rt_material& hm = S.mats[__float_as_int(hn.w)];
-            const float cti = dot(hnrm, w_i);
-            if (!(cti > 1.0f || cti <= 0.0f)) {
-              const float4 hw = HP.wo[hi], hat = HP.att[hi];
-              const float sct = fmaxf(0.0f, dot(hnrm, normalize(mk3(hw.x, hw.y, hw.z) + w_i)));
-              const v3 color = (ld3(hm.diffuse) + ((ld3(hm.specular) * powf(sct, hm.phong_exponent)) / cti)) *
-                               mk3(hat.x, hat.y, hat.z);
-              const v3 c = (color * flux) / ppm_R(G, n_old);
-              float* Sp = reinterpret_cast<float*>(HP.S + hi);
-              atomicAdd(Sp + 0, c.x); atomicAdd(Sp + 1, c.y); atomicAdd(Sp + 2, c.z);
-            }
-          }
-        }
+        dep = G.num_hash > 0;
+        dep_n = n; dep_flux = flux; dep_wi = -normalize(dir);
         // sample_hemisphere(normal, d, probability): cosine — PPM/src/Scene.cpp:15-44
         const float e1 = rng_u01(key, dim + 2), e2 = rng_u01(key, dim + 3);
         const float phi = (float)(2 * RT_PI * (double)e1);
@@ -330,6 +303,55 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_photon_shade(DScene S, Pool P,
       }
       // photon_trace: depth++ then `depth >= max_recursion_depth` stops BEFORE the next intersection
       if (cont && (int)(b + 2) >= S.max_depth) cont = false;
+    }
+    // ---- deposit: the warp scans each depositing photon's cell together (coalesced 16-byte entries) ----
+    unsigned dmask = __ballot_sync(0xffffffffu, dep);
+    while (dmask) {
+      const int src = __ffs(dmask) - 1;
+      dmask &= dmask - 1;
+      const v3 pp = mk3(__shfl_sync(0xffffffffu, p.x, src), __shfl_sync(0xffffffffu, p.y, src), __shfl_sync(0xffffffffu, p.z, src));
+      const v3 pn = mk3(__shfl_sync(0xffffffffu, dep_n.x, src), __shfl_sync(0xffffffffu, dep_n.y, src),
+                        __shfl_sync(0xffffffffu, dep_n.z, src));
+      const v3 pf = mk3(__shfl_sync(0xffffffffu, dep_flux.x, src), __shfl_sync(0xffffffffu, dep_flux.y, src),
+                        __shfl_sync(0xffffffffu, dep_flux.z, src));
+      const v3 w_i = mk3(__shfl_sync(0xffffffffu, dep_wi.x, src), __shfl_sync(0xffffffffu, dep_wi.y, src),
+                         __shfl_sync(0xffffffffu, dep_wi.z, src));
+      const v3 hh = (pp - G.bbox_min) * G.hash_scale;
+      const uint32_t cell = ppm_hash(G.num_hash, abs((int)hh.x), abs((int)hh.y), abs((int)hh.z));
+      const unsigned int c0 = G.cell_start[cell], c1 = G.cell_start[cell + 1];
+      if (lane_id() == 0) scans += c1 - c0;
+      for (unsigned int q = c0 + lane_id(); q < c1; q += 32u) {
+        const float4 hp = __ldg(G.cell_pos + q);
+        const v3 v = mk3(hp.x, hp.y, hp.z) - pp;
+        const float d2 = dot(v, v);
+        if (!(d2 <= G.r0sq)) continue;   // r2(n) <= r0^2: cannot be accepted (same decision, fewer loads)
+        const unsigned int hi = __float_as_uint(hp.w);
+        const float4 hn = HP.nrm[hi];
+        const v3 hnrm = mk3(hn.x, hn.y, hn.z);
+        if (!(dot(hnrm, pn) > 1e-3f)) continue;
+        // claim index n under the radius the reference would test against: r2(n) = r0^2 * R(n)
+        unsigned int n_old = *((volatile unsigned int*)(HP.n + hi));
+        bool accepted = false;
+        for (;;) {
+          if (!(d2 <= G.r0sq * ppm_R(G, n_old))) break;
+          const unsigned int prev = atomicCAS(HP.n + hi, n_old, n_old + 1u);
+          if (prev == n_old) { accepted = true; break; }
+          n_old = prev;
+        }
+        if (!accepted) continue;
+        deposits++;
+        const b200rt_material& hm = S.mats[__float_as_int(hn.w)];
+        const float cti = dot(hnrm, w_i);
+        if (!(cti > 1.0f || cti <= 0.0f)) {
+          const float4 hw = HP.wo[hi], hat = HP.att[hi];
+          const float sct = fmaxf(0.0f, dot(hnrm, normalize(mk3(hw.x, hw.y, hw.z) + w_i)));
+          const v3 color = (ld3(hm.diffuse) + ((ld3(hm.specular) * powf(sct, hm.phong_exponent)) / cti)) *
+                           mk3(hat.x, hat.y, hat.z);
+          const v3 c = (color * pf) / ppm_R(G, n_old);
+          float* Sp = reinterpret_cast<float*>(HP.S + hi);
+          atomicAdd(Sp + 0, c.x); atomicAdd(Sp + 1, c.y); atomicAdd(Sp + 2, c.z);
+        }
+      }
     }
     const uint32_t ci = warp_append(&waves[d + 1].count, cont);
     if (cont) {
