@@ -60,9 +60,26 @@ __device__ __forceinline__ bool box_loose(const FastRay& r, float mnx, float mny
     *entry = fmaxf(tn, 0.0f);
     return tn <= tfa && tfa >= 0.0f;
   }
-  // a direction component below the reference's axis-skip threshold: the
-  // reference test itself on the (superset) box is conservative by monotonicity
-  return box_gate_exact(r.o, r.d, mnx, mny, mnz, mxx, mxy, mxz, eps, entry);
+  // A direction component below the reference's axis-skip threshold.  The reference's OWN gates treat the
+  // box as infinite on such an axis (and tri_gate reproduces that), but this tree is ours: a candidate still
+  // has to pass through its triangle geometrically, so a true slab test on every axis stays conservative —
+  // and keeps an axis-parallel ray from visiting the whole mesh (it does in the reference).
+  float tn = -RT_INF, tf = RT_INF;
+  const float o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
+  const float mn[3] = {mnx, mny, mnz}, mx[3] = {mxx, mxy, mxz};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (d[i] == 0.0f) {
+      if (o[i] < mn[i] || o[i] > mx[i]) return false;
+    } else {
+      const float a = (mn[i] - o[i]) / d[i], b = (mx[i] - o[i]) / d[i];
+      tn = fmaxf(tn, fminf(a, b));
+      tf = fminf(tf, fmaxf(a, b));
+    }
+  }
+  const float tfa = tf + 2e-6f * fmaxf(fabsf(tn), fabsf(tf));
+  *entry = fmaxf(tn, 0.0f);
+  return !(tn > tfa) && !(tfa < 0.0f);
 }
 
 template <bool ANY, int TRI_MODE>
