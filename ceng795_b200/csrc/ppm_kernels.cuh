@@ -224,7 +224,7 @@ __global__ void k_ppm_next_wave(WaveInfo* waves, int d, uint32_t half, Counters*
   waves[d + 1].count = 0;
   C->work_extend = 0;
 }
-__global__ void __launch_bounds__(RT_BLOCK) k_ppm_photon_shade(DScene S, Pool P, WaveInfo* waves, int d, HitPoints HP,
+__global__ void __launch_bounds__(RT_BLOCK, 6) k_ppm_photon_shade(DScene S, Pool P, WaveInfo* waves, int d, HitPoints HP,
                                                                PpmGrid G, Counters* C, PpmCounters* PC) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   const uint32_t next_begin = waves[d + 1].begin;
@@ -305,6 +305,13 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_photon_shade(DScene S, Pool P,
       if (cont && (int)(b + 2) >= S.max_depth) cont = false;
     }
     // ---- deposit: the warp scans each depositing photon's cell together (coalesced 16-byte entries) ----
+    // every lane looks its own cell range up first: one memory latency for the 32 photons of the warp
+    unsigned int my_c0 = 0, my_c1 = 0;
+    if (dep) {
+      const v3 hh = (p - G.bbox_min) * G.hash_scale;
+      const uint32_t cell = ppm_hash(G.num_hash, abs((int)hh.x), abs((int)hh.y), abs((int)hh.z));
+      my_c0 = G.cell_start[cell]; my_c1 = G.cell_start[cell + 1];
+    }
     unsigned dmask = __ballot_sync(0xffffffffu, dep);
     while (dmask) {
       const int src = __ffs(dmask) - 1;
@@ -316,12 +323,19 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_photon_shade(DScene S, Pool P,
                         __shfl_sync(0xffffffffu, dep_flux.z, src));
       const v3 w_i = mk3(__shfl_sync(0xffffffffu, dep_wi.x, src), __shfl_sync(0xffffffffu, dep_wi.y, src),
                          __shfl_sync(0xffffffffu, dep_wi.z, src));
-      const v3 hh = (pp - G.bbox_min) * G.hash_scale;
-      const uint32_t cell = ppm_hash(G.num_hash, abs((int)hh.x), abs((int)hh.y), abs((int)hh.z));
-      const unsigned int c0 = G.cell_start[cell], c1 = G.cell_start[cell + 1];
+      const unsigned int c0 = __shfl_sync(0xffffffffu, my_c0, src), c1 = __shfl_sync(0xffffffffu, my_c1, src);
       if (lane_id() == 0) scans += c1 - c0;
-      for (unsigned int q = c0 + lane_id(); q < c1; q += 32u) {
-        const float4 hp = __ldg(G.cell_pos + q);
+      for (unsigned int base = c0; base < c1; base += 128u) {
+       // four independent 16-byte loads in flight per lane before any of them is consumed
+       float4 ent[4];
+#pragma unroll
+       for (int j = 0; j < 4; j++) {
+         const unsigned int q = base + 32u * j + lane_id();
+         ent[j] = q < c1 ? __ldg(G.cell_pos + q) : make_float4(RT_INF, RT_INF, RT_INF, 0.f);
+       }
+#pragma unroll
+       for (int j = 0; j < 4; j++) {
+        const float4 hp = ent[j];
         const v3 v = mk3(hp.x, hp.y, hp.z) - pp;
         const float d2 = dot(v, v);
         if (!(d2 <= G.r0sq)) continue;   // r2(n) <= r0^2: cannot be accepted (same decision, fewer loads)
@@ -348,9 +362,9 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_photon_shade(DScene S, Pool P,
           const v3 color = (ld3(hm.diffuse) + ((ld3(hm.specular) * powf(sct, hm.phong_exponent)) / cti)) *
                            mk3(hat.x, hat.y, hat.z);
           const v3 c = (color * pf) / ppm_R(G, n_old);
-          float* Sp = reinterpret_cast<float*>(HP.S + hi);
-          atomicAdd(Sp + 0, c.x); atomicAdd(Sp + 1, c.y); atomicAdd(Sp + 2, c.z);
+          atomicAdd(HP.S + hi, make_float4(c.x, c.y, c.z, 0.0f));   // one 16-byte vector atomic (sm_90+)
         }
+       }
       }
     }
     const uint32_t ci = warp_append(&waves[d + 1].count, cont);
