@@ -331,6 +331,9 @@ def run_b200(args):
         rays, e2e_rays, launches_all = float(r[0]), float(r[1]), int(r[2])
     else:
         launches_all = agg["launches"]
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return 0
 

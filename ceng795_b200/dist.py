@@ -71,7 +71,10 @@ def init_from_env(backend: str | None = None):
         if not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29500")
-            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            kw = {}
+            if backend == "nccl":
+                kw["device_id"] = torch.device("cuda", local)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
 
 
