@@ -93,9 +93,12 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
   const unsigned lane = lane_id();
   TravCounters tc = {0, 0, 0, 0};
 
+  // stack[0, n_obj)  : the ray's gated top-level objects, nearest first — a queue consumed through obj_next
+  // stack[n_obj, sp) : SAH nodes pending inside the object being traversed — a stack
+  // (while the top-level tree is expanded, its pending nodes live at the far end, stack[tp, RT_FSTACK))
   uint32_t stack[RT_FSTACK];
   float stack_t[RT_FSTACK];
-  int sp = 0;
+  int sp = 0, n_obj = 0, obj_next = 0;
   bool has_ray = false, exhausted = false;
   uint32_t out_slot = 0, src = 0;
   float time = 0.f, tlimit = RT_INF;
@@ -110,13 +113,6 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
   uint32_t cur = B200RT_REF_NONE;  // node to process next without going through the stack
   float cur_t = 0.f;
   bool culling = true;             // HW7/PPM back-face culling, off inside refractive instances
-
-  // the world-space ray lives in the queue; it is re-read on the (rare) instance switches
-  auto world_ray = [&](v3* o, v3* dir) {
-    const float4 ro = ANY ? Q.o[src] : P.ray_o[src];
-    const float4 rd = ANY ? Q.d[src] : P.ray_d[src];
-    *o = mk3(ro.x, ro.y, ro.z); *dir = mk3(rd.x, rd.y, rd.z);
-  };
 
   for (;;) {
     // ---- refill idle lanes from the wave's work cursor ----------------------
@@ -141,24 +137,68 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
             ro = P.ray_o[out_slot]; rd = P.ray_d[out_slot];
             time = ro.w; tlimit = RT_INF;
           }
-          cr = make_fast_ray(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), eps);
           best.t = RT_INF; best.beta = 0.f; best.gamma = 0.f; best.top_ref = B200RT_REF_NONE;
           best.top_rank = 0x7fffffff; best.tri = 0x7fffffff;
           found = false;
           cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true;
-          sp = 0;
           cur = B200RT_REF_NONE;
           has_ray = true;
-          // root: a gate for INNER / INSTANCE, unconditional for primitives
-          const uint32_t rk = B200RT_REF_KIND(S.root);
-          if (rk != B200RT_KIND_NONE) {
-            float e = 0.0f;
-            bool ok = true;
-            if (rk == B200RT_KIND_INNER || rk == B200RT_KIND_INSTANCE)
-              ok = box_gate(as_ctx(cr), S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
-                            S.root_box[5], eps, &e);
-            if (ok) { cur = S.root; cur_t = e; }
+          // ---- phase 0: expand the reference's top-level tree with its exact gates (BVH::intersect,
+          // HW3/src/Bounding_volume_hierarchy.cpp:31-55; Mesh_instance's own gate HW3/include/Mesh.h:59-62)
+          // into the queue of objects this ray has to enter, nearest first
+          const RayCtx wr = make_ray(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), eps);
+          n_obj = 0; obj_next = 0;
+          int tp = RT_FSTACK;
+          {
+            const uint32_t rk = B200RT_REF_KIND(S.root);
+            if (rk != B200RT_KIND_NONE) {
+              float e = 0.0f;
+              bool ok = true;
+              if (rk == B200RT_KIND_INNER || rk == B200RT_KIND_INSTANCE)
+                ok = box_gate(wr, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
+                              S.root_box[5], eps, &e);
+              if (ok) { tp--; stack[tp] = S.root; stack_t[tp] = e; }
+            }
           }
+          while (tp < RT_FSTACK) {
+            const uint32_t ref = stack[tp];
+            const float te = stack_t[tp];
+            tp++;
+            if (B200RT_REF_KIND(ref) != B200RT_KIND_INNER) {
+              if (n_obj < tp) { stack[n_obj] = ref; stack_t[n_obj] = te; n_obj++; }
+              else atomicExch(&C->overflow, 2u);
+              continue;
+            }
+            tc.nodes++;
+            const uint32_t idx = B200RT_REF_INDEX(ref);
+            const float4 n0 = __ldg(S.nodes + 4 * (size_t)idx);
+            const float4 n1 = __ldg(S.nodes + 4 * (size_t)idx + 1);
+            const float4 n2 = __ldg(S.nodes + 4 * (size_t)idx + 2);
+            const float4 n3 = __ldg(S.nodes + 4 * (size_t)idx + 3);
+            const uint32_t child[2] = {__float_as_uint(n3.x), __float_as_uint(n3.y)};
+            float entry[2] = {0.f, 0.f};
+            bool push[2] = {false, false};
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+              const uint32_t ck = B200RT_REF_KIND(child[c]);
+              if (ck == B200RT_KIND_INNER || ck == B200RT_KIND_INSTANCE) {
+                if (c == 0) push[0] = box_gate(wr, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &entry[0]);
+                else push[1] = box_gate(wr, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &entry[1]);
+              } else if (ck != B200RT_KIND_NONE) {
+                push[c] = true;  // primitives and Light_mesh have no gate of their own
+              }
+            }
+            const int far_c = (push[0] && push[1] && entry[0] > entry[1]) ? 0 : 1;
+#pragma unroll
+            for (int k2 = 0; k2 < 2; k2++) {
+              const int c = k2 == 0 ? far_c : 1 - far_c;  // far first: the near child is popped next
+              if (push[c]) {
+                if (tp - 1 > n_obj) { tp--; stack[tp] = child[c]; stack_t[tp] = entry[c]; }
+                else atomicExch(&C->overflow, 2u);
+              }
+            }
+          }
+          sp = n_obj;
         }
       }
     }
@@ -167,18 +207,17 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
     for (;;) {
       if (has_ray) {
         bool finished = false;
-        // ---- phase 1: inner nodes of the SAH tree until this lane holds something else
+        // ---- phase 1: inner nodes of the SAH tree until this lane holds a leaf or has nothing left in the object
         for (;;) {
           if (cur == B200RT_REF_NONE) {
-            if (sp == 0) { finished = true; break; }
+            if (sp <= n_obj) break;
             sp--; cur = stack[sp]; cur_t = stack_t[sp];
           }
-          if (B200RT_REF_KIND(cur) != B200RT_KIND_FNODE) break;
           const float bound = ANY ? tlimit : best.t;
+          if (cur_t > bound + fabsf(bound) * 1e-4f) { cur = B200RT_REF_NONE; continue; }  // pruned
+          if (B200RT_REF_KIND(cur) != B200RT_KIND_FNODE) break;
           const uint32_t idx = B200RT_REF_INDEX(cur);
-          const float te = cur_t;
           cur = B200RT_REF_NONE;
-          if (te > bound + fabsf(bound) * 1e-4f) continue;  // pruned
           tc.nodes++;
           const float4 n0 = __ldg(S.fast_nodes + 4 * (size_t)idx);
           const float4 n1 = __ldg(S.fast_nodes + 4 * (size_t)idx + 1);
@@ -196,22 +235,82 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
           } else if (h0) { cur = c0; cur_t = e0; }
           else if (h1) { cur = c1; cur_t = e1; }
         }
-        // ---- phase 2: leaf / instance / top-level node / primitive
-        if (!finished) {
-          const uint32_t ref = cur;
-          const float te = cur_t;
+        // ---- phase 2a: nothing pending in the current object -> enter the next one of the queue
+        if (cur == B200RT_REF_NONE) {
+          if (obj_next >= n_obj) {
+            finished = true;
+          } else {
+            const uint32_t ref = stack[obj_next];
+            const float te = stack_t[obj_next];
+            obj_next++;
+            const uint32_t kind = B200RT_REF_KIND(ref);
+            const uint32_t idx = B200RT_REF_INDEX(ref);
+            const float bound = ANY ? tlimit : best.t;
+            if (te > bound + fabsf(bound) * 1e-4f) {
+              // pruned: the object's gate box starts beyond the best hit
+            } else if (kind == B200RT_KIND_INSTANCE || kind == B200RT_KIND_LIGHTINST) {
+              // Mesh_instance::intersect — HW3/include/Mesh.h:55-98 (gate already passed; a Light_mesh has none)
+              const b200rt_instance* in = S.inst + idx;
+              const b200rt_mesh* m = S.meshes + in->mesh;
+              const uint32_t froot = (m->fast_root != B200RT_REF_NONE) ? m->fast_root : m->root;
+              if (B200RT_REF_KIND(froot) != B200RT_KIND_NONE) {
+                tc.insts++;
+                const float4 ro = ANY ? Q.o[src] : P.ray_o[src];
+                const float4 rd = ANY ? Q.d[src] : P.ray_d[src];
+                const v3 o = mk3(ro.x, ro.y, ro.z), dir = mk3(rd.x, rd.y, rd.z);
+                v3 co = o, cd = dir;
+                if (!(in->flags & B200RT_INST_DIRECT)) {
+                  if (in->flags & B200RT_INST_MOVING) {
+                    float inv16[16];
+                    moving_inverse(in->fwd, in->velocity, time, inv16);
+                    co = xf_point(inv16, o); cd = xf_vector4(inv16, dir);
+                  } else {
+                    co = xf_point(in->inv, o); cd = xf_vector4(in->inv, dir);
+                  }
+                }
+                cr = make_fast_ray(co, cd, eps);
+                cur_rank = in->rank; cur_top = ref;
+                culling = !(in->flags & B200RT_INST_REFRACTIVE);
+                cur = froot; cur_t = 0.f;
+              }
+            } else if (kind == B200RT_KIND_SPHERE) {
+              tc.spheres++;
+              const b200rt_sphere* s = S.spheres + idx;
+              const float4 ro = ANY ? Q.o[src] : P.ray_o[src];
+              const float4 rd = ANY ? Q.d[src] : P.ray_d[src];
+              float t;
+              if (sphere_test(s, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), time, eps, &t) && t > 0.0f) {
+                if (ANY) { if (t < tlimit) { found = true; finished = true; } }
+                else if (better(t, s->rank, -1, best)) {
+                  best.t = t; best.beta = 0.f; best.gamma = 0.f; best.top_ref = ref; best.top_rank = s->rank;
+                  best.tri = -1; found = true;
+                }
+              }
+            } else if (kind == B200RT_KIND_TRIPRIM) {
+              tc.tris++;
+              const b200rt_triprim* p = S.triprims + idx;
+              const float4 ro = ANY ? Q.o[src] : P.ray_o[src];
+              const float4 rd = ANY ? Q.d[src] : P.ray_d[src];
+              v3 lo = mk3(ro.x, ro.y, ro.z), ldir = mk3(rd.x, rd.y, rd.z);
+              if (!(p->flags & B200RT_XF_IDENTITY)) { const v3 wo = lo, wd = ldir; lo = xf_point(p->inv, wo); ldir = xf_vector4(p->inv, wd); }
+              float t, be, ga;
+              if (!(TRI_MODE == 7 && dot(ldir, ld3(p->normal)) > 0.0f) &&   // top-level objects are culled (HW7)
+                  tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
+                if (ANY) { if (t < tlimit) { found = true; finished = true; } }
+                else if (better(t, p->rank, -1, best)) {
+                  best.t = t; best.beta = be; best.gamma = ga; best.top_ref = ref; best.top_rank = p->rank;
+                  best.tri = -1; found = true;
+                }
+              }
+            }
+          }
+        }
+        // ---- phase 2b: a leaf of the SAH tree (or the lone triangle of a one-triangle mesh)
+        if (cur != B200RT_REF_NONE && B200RT_REF_KIND(cur) != B200RT_KIND_FNODE) {
+          const uint32_t kind = B200RT_REF_KIND(cur);
+          const uint32_t idx = B200RT_REF_INDEX(cur);
           cur = B200RT_REF_NONE;
-          const uint32_t kind = B200RT_REF_KIND(ref);
-          const uint32_t idx = B200RT_REF_INDEX(ref);
-          const float bound = ANY ? tlimit : best.t;
-          if (kind == 14u) {  // leave instance
-            v3 o, dir;
-            world_ray(&o, &dir);
-            cr = make_fast_ray(o, dir, eps);
-            cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true;
-          } else if (te > bound + fabsf(bound) * 1e-4f) {
-            // pruned: cannot contain a closer / in-range hit
-          } else if (kind >= B200RT_KIND_LEAF1 && kind <= B200RT_KIND_LEAF4) {
+          if (kind >= B200RT_KIND_LEAF1 && kind <= B200RT_KIND_LEAF4) {
             const int n = (int)(kind - B200RT_KIND_LEAF1) + 1;
             for (int i = 0; i < n; i++) {
               const size_t fi = (size_t)idx + i;
@@ -237,64 +336,6 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
                 }
               }
             }
-          } else if (kind == B200RT_KIND_INNER) {
-            // top-level node of the reference tree: exact gates; primitives are tested when popped
-            tc.nodes++;
-            const float4 n0 = __ldg(S.nodes + 4 * (size_t)idx);
-            const float4 n1 = __ldg(S.nodes + 4 * (size_t)idx + 1);
-            const float4 n2 = __ldg(S.nodes + 4 * (size_t)idx + 2);
-            const float4 n3 = __ldg(S.nodes + 4 * (size_t)idx + 3);
-            const uint32_t child[2] = {__float_as_uint(n3.x), __float_as_uint(n3.y)};
-            float entry[2] = {0.f, 0.f};
-            bool push[2] = {false, false};
-            const RayCtx rc = as_ctx(cr);
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-              const uint32_t ck = B200RT_REF_KIND(child[c]);
-              if (ck == B200RT_KIND_INNER || ck == B200RT_KIND_INSTANCE) {
-                if (c == 0) push[0] = box_gate(rc, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, eps, &entry[0]);
-                else push[1] = box_gate(rc, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, eps, &entry[1]);
-              } else if (ck != B200RT_KIND_NONE) {
-                push[c] = true;
-                entry[c] = 0.f;
-              }
-            }
-            if (push[0] && push[1]) {
-              const int far_c = (entry[0] > entry[1]) ? 0 : 1;
-              cur = child[1 - far_c]; cur_t = entry[1 - far_c];
-              if (sp < RT_FSTACK) { stack[sp] = child[far_c]; stack_t[sp] = entry[far_c]; sp++; }
-              else atomicExch(&C->overflow, 2u);
-            } else if (push[0] || push[1]) {
-              const int c = push[0] ? 0 : 1;
-              cur = child[c]; cur_t = entry[c];
-            }
-          } else if (kind == B200RT_KIND_INSTANCE || kind == B200RT_KIND_LIGHTINST) {
-            // Mesh_instance::intersect — HW3/include/Mesh.h:55-98 (gate already passed; a Light_mesh has none)
-            const b200rt_instance* in = S.inst + idx;
-            const b200rt_mesh* m = S.meshes + in->mesh;
-            const uint32_t froot = (m->fast_root != B200RT_REF_NONE) ? m->fast_root : m->root;
-            if (B200RT_REF_KIND(froot) != B200RT_KIND_NONE) {
-              tc.insts++;
-              v3 o, dir;
-              world_ray(&o, &dir);
-              v3 co = o, cd = dir;
-              if (!(in->flags & B200RT_INST_DIRECT)) {
-                if (in->flags & B200RT_INST_MOVING) {
-                  float inv16[16];
-                  moving_inverse(in->fwd, in->velocity, time, inv16);
-                  co = xf_point(inv16, o); cd = xf_vector4(inv16, dir);
-                } else {
-                  co = xf_point(in->inv, o); cd = xf_vector4(in->inv, dir);
-                }
-              }
-              if (sp < RT_FSTACK) {
-                cr = make_fast_ray(co, cd, eps);
-                cur_rank = in->rank; cur_top = ref;
-                culling = !(in->flags & B200RT_INST_REFRACTIVE);
-                stack[sp] = RT_SENTINEL; stack_t[sp] = 0.f; sp++;
-                cur = froot; cur_t = 0.f;
-              } else atomicExch(&C->overflow, 2u);
-            }
           } else if (kind == B200RT_KIND_TRI) {
             // a mesh whose BVH is a single triangle (create_bvh size==1): no gate at all
             tc.tris++;
@@ -309,31 +350,6 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
               else if (better(t, cur_rank, (int)idx, best)) {
                 best.t = t; best.beta = be; best.gamma = ga; best.top_ref = cur_top; best.top_rank = cur_rank;
                 best.tri = (int)idx; found = true;
-              }
-            }
-          } else if (kind == B200RT_KIND_SPHERE) {
-            tc.spheres++;
-            const b200rt_sphere* s = S.spheres + idx;
-            float t;
-            if (sphere_test(s, cr.o, cr.d, time, eps, &t) && t > 0.0f) {
-              if (ANY) { if (t < tlimit) { found = true; finished = true; } }
-              else if (better(t, s->rank, -1, best)) {
-                best.t = t; best.beta = 0.f; best.gamma = 0.f; best.top_ref = ref; best.top_rank = s->rank;
-                best.tri = -1; found = true;
-              }
-            }
-          } else if (kind == B200RT_KIND_TRIPRIM) {
-            tc.tris++;
-            const b200rt_triprim* p = S.triprims + idx;
-            v3 lo = cr.o, ldir = cr.d;
-            if (!(p->flags & B200RT_XF_IDENTITY)) { lo = xf_point(p->inv, cr.o); ldir = xf_vector4(p->inv, cr.d); }
-            float t, be, ga;
-            if (!(TRI_MODE == 7 && culling && dot(ldir, ld3(p->normal)) > 0.0f) &&
-                tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
-              if (ANY) { if (t < tlimit) { found = true; finished = true; } }
-              else if (better(t, p->rank, -1, best)) {
-                best.t = t; best.beta = be; best.gamma = ga; best.top_ref = ref; best.top_rank = p->rank;
-                best.tri = -1; found = true;
               }
             }
           }
