@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -10,8 +11,8 @@ namespace b200rt_fast {
 namespace {
 
 constexpr int kBins = 16;
-constexpr int kMaxLeaf = 4;
-constexpr float kTraversalCost = 1.5f;  // relative to one triangle test
+int kMaxLeaf = 4;
+float kTraversalCost = 1.0f;  // relative to one triangle test (swept on cfg2: profiles/r01b_tuning.txt)
 
 struct Prim {
   float mn[3], mx[3], c[3];
@@ -134,6 +135,8 @@ uint32_t build_rec(Ctx& cx, int s, int e, Bx* box) {
 uint32_t build(const float* boxes6, int n, int tri_base, float grow, std::vector<b200rt_bvh_node>& nodes,
                std::vector<int32_t>& order) {
   if (n <= 0) return B200RT_REF_NONE;
+  if (const char* e = std::getenv("B200RT_SAH_MAXLEAF")) kMaxLeaf = std::max(1, std::min(4, std::atoi(e)));
+  if (const char* e = std::getenv("B200RT_SAH_TCOST")) kTraversalCost = (float)std::atof(e);
   Ctx cx;
   cx.nodes = &nodes;
   cx.order = &order;

@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
               const float4 ro = ANY ? Q.o[src] : P.ray_o[src];
               const float4 rd = ANY ? Q.d[src] : P.ray_d[src];
               float t;
-              if (sphere_test(s, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), time, eps, &t) && t > 0.0f) {
+              // Sphere::intersect returns true even for t < 0 and only a BVH parent filters `t > 0`: a scene whose
+              // root IS the sphere (create_bvh size==1) reports the negative hit
+              const bool lone = !ANY && ref == S.root;
+              if (sphere_test(s, mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), time, eps, &t) && (t > 0.0f || lone)) {
                 if (ANY) { if (t < tlimit) { found = true; finished = true; } }
                 else if (better(t, s->rank, -1, best)) {
                   best.t = t; best.beta = 0.f; best.gamma = 0.f; best.top_ref = ref; best.top_rank = s->rank;

@@ -435,7 +435,8 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
       cnt.spheres++;
       const b200rt_sphere* s = S.spheres + idx;
       float t;
-      if (sphere_test(s, co, cd, time, eps, &t) && t > 0.0f) {
+      const bool lone = !ANY && ref == S.root;  // root is the sphere itself: no parent filters t > 0 (Appendix B.10)
+      if (sphere_test(s, co, cd, time, eps, &t) && (t > 0.0f || lone)) {
         if (ANY) { if (t < tlimit) return true; }
         else if (better(t, s->rank, -1, best)) {
           best.t = t; best.top_ref = ref; best.top_rank = s->rank; best.tri = -1; found = true;

@@ -982,8 +982,6 @@ static v3 light_radiance(const B200SceneDesc* d, int li, v3 to_light, float prob
   }
 }
 
-#include <stdio.h>
-static int g_dbg = 0;
 static v3 send_ray7(const Ctx* cx, const Ray* ray, int level, uint32_t key, int count_as);
 
 /* Scene::calculate_diffuse_constant — HW7/src/Scene.cpp:231-258 */
@@ -1019,8 +1017,6 @@ static v3 direct7(const Ctx* cx, const Ray* ray, const Hit* hit, v3 kd, uint32_t
       cx->c->rays_shadow++;
       Hit sh;
       scene_intersect(cx, &sr, &sh);
-      if (g_dbg) fprintf(stderr, "[oracle]     light %d ldist %.9g sh.t %.9g limit %.9g wi %.9g %.9g %.9g so %.9g %.9g %.9g p %.9g %.9g %.9g\n", li, ldist, sh.t,
-                         ldist - d->shadow_eps, w_i.x, w_i.y, w_i.z, sr.o.x, sr.o.y, sr.o.z, p.x, p.y, p.z);
       if (sh.t < (ldist - d->shadow_eps) && sh.t > 0.0f) continue;
       const v3 Li = light_radiance(d, li, lvec, prob);
       const float cti = fmaxf(0.0f, dot(n, w_i));
@@ -1127,15 +1123,12 @@ static v3 trace_ray7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, u
 static v3 trace_path7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, uint32_t key) {
   const B200SceneDesc* d = cx->d;
   v3 radiance = V(0, 0, 0);
-  if (g_dbg) fprintf(stderr, "[oracle] level %d key %08x hit rank %d tri %d t %.9g light %d lh %d n %.6f %.6f %.6f\n", level, key,
-                     hit->top_rank, hit->tri, hit->t, hit->light, ray->light_hit, hit->normal.x, hit->normal.y, hit->normal.z);
   if (hit->light >= 0) return ray->light_hit ? radiance : ld(d->lights[hit->light].intensity);
   Ray ray_copy = *ray;
   v3 kd, direct = V(0, 0, 0);
   diffuse_constant7(d, hit, &kd);
   if (!ray->in_medium) direct = direct7(cx, ray, hit, kd, key);
   if (!is_zero(direct)) { ray_copy.light_hit = 1; radiance = add(radiance, direct); }
-  if (g_dbg) fprintf(stderr, "[oracle]   direct %.6f %.6f %.6f\n", direct.x, direct.y, direct.z);
   const b200rt_material* m = d->materials + hit->material;
   const b200rt_brdf* B = (m->brdf != -1) ? d->brdfs + m->brdf : NULL;
   if (!ray->in_medium && level < d->max_depth) {
@@ -1151,7 +1144,6 @@ static v3 trace_path7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, 
     sr.o = add(p, muls(w_i, d->shadow_eps)); sr.d = w_i; sr.time = ray->time;
     sr.in_medium = ray->in_medium; sr.light_hit = ray->light_hit;
     const v3 Li = send_ray7(cx, &sr, level + 1, rng_mix(key, 0x104u), 1);
-    if (g_dbg) fprintf(stderr, "[oracle]   level %d sample Li %.6f %.6f %.6f cti %.6f wi %.6f %.6f %.6f\n", level, Li.x, Li.y, Li.z, cti, w_i.x, w_i.y, w_i.z);
     const float prob = d->importance_sampling ? (float)((double)cti / M_PI) : (float)(1.0f / (2 * M_PI));
     if (prob != 0.0f) {
       if (B) {
@@ -1267,7 +1259,6 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
           continue;
         }
         if (ns == 1) {
-          { const char* e = getenv("ORACLE_DEBUG_PIX"); g_dbg = (e && atoi(e) == pix); }
           Ray r = hw7 ? camera_ray(d, c, i + 0.5f, j + 0.5f, 0, 0, 0, 0.0f)
                       : camera_ray(d, c, (float)i, (float)j, 0, 0, 0, 0.0f);
           if (ids || tout) {
