@@ -331,7 +331,7 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
 
 void ppm_free(b200rt_scene* sc) {
   HitPoints& H = sc->HP;
-  void* ptrs[] = {H.count, H.pos, H.nrm, H.wo, H.att, H.n, H.S, sc->G.cell_count, sc->G.cell_start, sc->G.items,
+  void* ptrs[] = {H.count, H.pos, H.nrm, H.wo, H.att, H.n, H.state, H.dep, sc->G.cell_count, sc->G.cell_start, sc->G.items,
                   sc->G.cell_pos,
                   sc->d_pc, sc->d_rtab, sc->d_export, sc->d_scan_tmp};
   for (void* p : ptrs)
@@ -345,7 +345,7 @@ void ppm_free(b200rt_scene* sc) {
 int ppm_ensure_hit_points(b200rt_scene* sc, size_t cap) {
   HitPoints& H = sc->HP;
   if (H.capacity >= cap) return B200RT_OK;
-  void* ptrs[] = {H.pos, H.nrm, H.wo, H.att, H.n, H.S, sc->d_export};
+  void* ptrs[] = {H.pos, H.nrm, H.wo, H.att, H.n, H.state, H.dep, sc->d_export};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (!H.count) CK(cudaMalloc((void**)&H.count, sizeof(unsigned int)));
@@ -354,7 +354,8 @@ int ppm_ensure_hit_points(b200rt_scene* sc, size_t cap) {
   CK(cudaMalloc((void**)&H.wo, cap * sizeof(float4)));
   CK(cudaMalloc((void**)&H.att, cap * sizeof(float4)));
   CK(cudaMalloc((void**)&H.n, cap * sizeof(unsigned int)));
-  CK(cudaMalloc((void**)&H.S, cap * sizeof(float4)));
+  CK(cudaMalloc((void**)&H.state, cap * sizeof(float4)));
+  CK(cudaMalloc((void**)&H.dep, cap * 4 * sizeof(float4)));
   CK(cudaMalloc((void**)&sc->d_export, cap * sizeof(float4)));
   H.capacity = (uint32_t)cap;
   return B200RT_OK;
@@ -461,7 +462,7 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
     CK(cudaMalloc((void**)&G.cell_count, sizeof(unsigned int) * ((size_t)n_hp + 1)));
     CK(cudaMalloc((void**)&G.cell_start, sizeof(unsigned int) * ((size_t)n_hp + 1)));
     CK(cudaMemsetAsync(G.cell_count, 0, sizeof(unsigned int) * ((size_t)n_hp + 1), st));
-    k_ppm_grid<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, G, n_hp, 0, 0, sc->d_pc);
+    k_ppm_grid<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, G, n_hp, 0, 0, sc->d_pc, sc->S.mats);
     size_t need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, need, G.cell_count, G.cell_start, (int)n_hp + 1, st);
     if (need > sc->scan_tmp_bytes) {
@@ -483,7 +484,7 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
       sc->items_capacity = entries + 1;
     }
     CK(cudaMemcpyAsync(G.cell_count, G.cell_start, sizeof(unsigned int) * ((size_t)n_hp + 1), cudaMemcpyDeviceToDevice, st));
-    k_ppm_grid<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, G, n_hp, 1, (uint32_t)sc->items_capacity, sc->d_pc);
+    k_ppm_grid<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, G, n_hp, 1, (uint32_t)sc->items_capacity, sc->d_pc, sc->S.mats);
     launches += 4;
   }
   cudaEventRecord(e2, st);

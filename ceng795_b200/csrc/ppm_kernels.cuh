@@ -12,6 +12,7 @@
 
 #define PPM_ALPHA 0.7f
 #define PPM_RTAB (1 << 20)
+#define PPM_QCAP 12  // deferred deposit candidates per lane
 
 struct HitPoints {
   uint32_t capacity;
@@ -20,9 +21,13 @@ struct HitPoints {
   float4* nrm;   // normal xyz, as_float(material)
   float4* wo;    // w_o xyz, as_float(pixel)
   float4* att;   // attenuation rgb, pixel_weight
-  unsigned int* n;
-  float4* S;     // sum f*phi/R(k) rgb
+  unsigned int* n; // accepted-photon count: a dense 4-byte array (8.7 MB at 1080p) that stays L2-resident, so the
+                   // radius test r2(n) of a scanned entry does not cost a DRAM round trip
+  float4* state;   // S = sum f*phi/R(k) rgb
+  float4* dep;   // 4 per hit point, 64 bytes: what a deposit reads — {normal, phong exponent}, {w_o, att.r},
+                 // {kd, att.g}, {ks, att.b} (built once per eye pass by k_ppm_grid)
 };
+__device__ __forceinline__ unsigned int* hp_n(const HitPoints& HP, unsigned int i) { return HP.n + i; }
 struct PpmGrid {
   uint32_t num_hash;
   unsigned int* cell_count;  // num_hash + 1 (becomes the fill cursor)
@@ -175,10 +180,20 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_eye_shade(DScene S, Pool P, Wa
 
 // ---- hash grid -------------------------------------------------------------------
 // mode 0: count entries per cell; mode 1: fill (cell_count is the running cursor, starting at cell_start)
-__global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uint32_t items_capacity, PpmCounters* PC) {
+__global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uint32_t items_capacity, PpmCounters* PC,
+                           const b200rt_material* mats) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
     const float4 q = HP.pos[i];
-    if (mode == 0) { HP.n[i] = 0; HP.S[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    if (mode == 0) {
+      HP.state[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      HP.n[i] = 0u;
+      const float4 n4 = HP.nrm[i], w4 = HP.wo[i], a4 = HP.att[i];
+      const b200rt_material& m = mats[__float_as_int(n4.w)];
+      HP.dep[4 * (size_t)i + 0] = make_float4(n4.x, n4.y, n4.z, m.phong_exponent);
+      HP.dep[4 * (size_t)i + 1] = make_float4(w4.x, w4.y, w4.z, a4.x);
+      HP.dep[4 * (size_t)i + 2] = make_float4(m.diffuse[0], m.diffuse[1], m.diffuse[2], a4.y);
+      HP.dep[4 * (size_t)i + 3] = make_float4(m.specular[0], m.specular[1], m.specular[2], a4.z);
+    }
     const v3 lo = (mk3(q.x - G.r0, q.y - G.r0, q.z - G.r0) - G.bbox_min) * G.hash_scale;
     const v3 hi = (mk3(q.x + G.r0, q.y + G.r0, q.z + G.r0) - G.bbox_min) * G.hash_scale;
     for (int iz = abs((int)lo.z); iz <= abs((int)hi.z); iz++)
@@ -304,7 +319,60 @@ __global__ void __launch_bounds__(RT_BLOCK, 6) k_ppm_photon_shade(DScene S, Pool
       // photon_trace: depth++ then `depth >= max_recursion_depth` stops BEFORE the next intersection
       if (cont && (int)(b + 2) >= S.max_depth) cont = false;
     }
-    // ---- deposit: the warp scans each depositing photon's cell together (coalesced 16-byte entries) ----
+    // ---- deposit ------------------------------------------------------------------------------------
+    // Scan: the 32 photons of the warp are taken in turn and all lanes scan that photon's cell together
+    // (coalesced 16-byte entries, four loads in flight per lane).  An entry that passes the radius test is
+    // only QUEUED (hit point, distance, photon lane); the queue is drained afterwards with every lane
+    // working on its own candidate, so the dependent DRAM / atomic round trips of an accepted photon
+    // (normal -> CAS on n -> material -> vector atomic) overlap across 32 candidates instead of stalling the
+    // scan of each photon in turn.
+    unsigned int q_hi[PPM_QCAP];
+    float q_d2[PPM_QCAP];
+    int q_src[PPM_QCAP];
+    int qn = 0;
+    auto drain = [&]() {
+      int qmax = qn;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) qmax = max(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
+      for (int j = 0; j < qmax; j++) {
+        const bool has = j < qn;
+        const int src = has ? q_src[j] : (int)lane_id();
+        const v3 pn = mk3(__shfl_sync(0xffffffffu, dep_n.x, src), __shfl_sync(0xffffffffu, dep_n.y, src),
+                          __shfl_sync(0xffffffffu, dep_n.z, src));
+        const v3 pf = mk3(__shfl_sync(0xffffffffu, dep_flux.x, src), __shfl_sync(0xffffffffu, dep_flux.y, src),
+                          __shfl_sync(0xffffffffu, dep_flux.z, src));
+        const v3 w_i = mk3(__shfl_sync(0xffffffffu, dep_wi.x, src), __shfl_sync(0xffffffffu, dep_wi.y, src),
+                           __shfl_sync(0xffffffffu, dep_wi.z, src));
+        if (!has) continue;
+        const unsigned int hi = q_hi[j];
+        const float d2 = q_d2[j];
+        const float4 hn = __ldg(HP.dep + 4 * (size_t)hi);
+        const v3 hnrm = mk3(hn.x, hn.y, hn.z);
+        if (!(dot(hnrm, pn) > 1e-3f)) continue;
+        // claim index n under the radius the reference would test against: r2(n) = r0^2 * R(n)
+        unsigned int n_old = *((volatile unsigned int*)hp_n(HP, hi));
+        bool accepted = false;
+        for (;;) {
+          if (!(d2 <= G.r0sq * ppm_R(G, n_old))) break;
+          const unsigned int prev = atomicCAS(hp_n(HP, hi), n_old, n_old + 1u);
+          if (prev == n_old) { accepted = true; break; }
+          n_old = prev;
+        }
+        if (!accepted) continue;
+        deposits++;
+        const float cti = dot(hnrm, w_i);
+        if (!(cti > 1.0f || cti <= 0.0f)) {
+          const float4 hw = __ldg(HP.dep + 4 * (size_t)hi + 1), hd = __ldg(HP.dep + 4 * (size_t)hi + 2),
+                       hs = __ldg(HP.dep + 4 * (size_t)hi + 3);
+          const float sct = fmaxf(0.0f, dot(hnrm, normalize(mk3(hw.x, hw.y, hw.z) + w_i)));
+          const v3 color = (mk3(hd.x, hd.y, hd.z) + ((mk3(hs.x, hs.y, hs.z) * powf(sct, hn.w)) / cti)) *
+                           mk3(hw.w, hd.w, hs.w);
+          const v3 c = (color * pf) / ppm_R(G, n_old);
+          atomicAdd(HP.state + hi, make_float4(c.x, c.y, c.z, 0.0f));   // one 16-byte vector atomic (sm_90+)
+        }
+      }
+      qn = 0;
+    };
     // every lane looks its own cell range up first: one memory latency for the 32 photons of the warp
     unsigned int my_c0 = 0, my_c1 = 0;
     if (dep) {
@@ -317,56 +385,33 @@ __global__ void __launch_bounds__(RT_BLOCK, 6) k_ppm_photon_shade(DScene S, Pool
       const int src = __ffs(dmask) - 1;
       dmask &= dmask - 1;
       const v3 pp = mk3(__shfl_sync(0xffffffffu, p.x, src), __shfl_sync(0xffffffffu, p.y, src), __shfl_sync(0xffffffffu, p.z, src));
-      const v3 pn = mk3(__shfl_sync(0xffffffffu, dep_n.x, src), __shfl_sync(0xffffffffu, dep_n.y, src),
-                        __shfl_sync(0xffffffffu, dep_n.z, src));
-      const v3 pf = mk3(__shfl_sync(0xffffffffu, dep_flux.x, src), __shfl_sync(0xffffffffu, dep_flux.y, src),
-                        __shfl_sync(0xffffffffu, dep_flux.z, src));
-      const v3 w_i = mk3(__shfl_sync(0xffffffffu, dep_wi.x, src), __shfl_sync(0xffffffffu, dep_wi.y, src),
-                         __shfl_sync(0xffffffffu, dep_wi.z, src));
       const unsigned int c0 = __shfl_sync(0xffffffffu, my_c0, src), c1 = __shfl_sync(0xffffffffu, my_c1, src);
       if (lane_id() == 0) scans += c1 - c0;
       for (unsigned int base = c0; base < c1; base += 128u) {
-       // four independent 16-byte loads in flight per lane before any of them is consumed
-       float4 ent[4];
+        // four independent 16-byte loads in flight per lane before any of them is consumed
+        float4 ent[4];
 #pragma unroll
-       for (int j = 0; j < 4; j++) {
-         const unsigned int q = base + 32u * j + lane_id();
-         ent[j] = q < c1 ? __ldg(G.cell_pos + q) : make_float4(RT_INF, RT_INF, RT_INF, 0.f);
-       }
+        for (int j = 0; j < 4; j++) {
+          const unsigned int q = base + 32u * j + lane_id();
+          ent[j] = q < c1 ? __ldg(G.cell_pos + q) : make_float4(RT_INF, RT_INF, RT_INF, 0.f);
+        }
 #pragma unroll
-       for (int j = 0; j < 4; j++) {
-        const float4 hp = ent[j];
-        const v3 v = mk3(hp.x, hp.y, hp.z) - pp;
-        const float d2 = dot(v, v);
-        if (!(d2 <= G.r0sq)) continue;   // r2(n) <= r0^2: cannot be accepted (same decision, fewer loads)
-        const unsigned int hi = __float_as_uint(hp.w);
-        const float4 hn = HP.nrm[hi];
-        const v3 hnrm = mk3(hn.x, hn.y, hn.z);
-        if (!(dot(hnrm, pn) > 1e-3f)) continue;
-        // claim index n under the radius the reference would test against: r2(n) = r0^2 * R(n)
-        unsigned int n_old = *((volatile unsigned int*)(HP.n + hi));
-        bool accepted = false;
-        for (;;) {
-          if (!(d2 <= G.r0sq * ppm_R(G, n_old))) break;
-          const unsigned int prev = atomicCAS(HP.n + hi, n_old, n_old + 1u);
-          if (prev == n_old) { accepted = true; break; }
-          n_old = prev;
+        for (int j = 0; j < 4; j++) {
+          const float4 hp = ent[j];
+          const v3 v = mk3(hp.x, hp.y, hp.z) - pp;
+          const float d2 = dot(v, v);
+          if (!(d2 <= G.r0sq)) continue;   // r2(n) <= r0^2: cannot be accepted (same decision, fewer loads)
+          const unsigned int hi = __float_as_uint(hp.w);
+          // the reference accepts iff (normals agree) && (|v|^2 <= r2); the radius goes first: n is an L2 hit
+          // and rejects almost every entry once the radii have shrunk
+          const unsigned int n_now = *((volatile unsigned int*)hp_n(HP, hi));
+          if (!(d2 <= G.r0sq * ppm_R(G, n_now))) continue;
+          q_hi[qn] = hi; q_d2[qn] = d2; q_src[qn] = src; qn++;
         }
-        if (!accepted) continue;
-        deposits++;
-        const b200rt_material& hm = S.mats[__float_as_int(hn.w)];
-        const float cti = dot(hnrm, w_i);
-        if (!(cti > 1.0f || cti <= 0.0f)) {
-          const float4 hw = HP.wo[hi], hat = HP.att[hi];
-          const float sct = fmaxf(0.0f, dot(hnrm, normalize(mk3(hw.x, hw.y, hw.z) + w_i)));
-          const v3 color = (ld3(hm.diffuse) + ((ld3(hm.specular) * powf(sct, hm.phong_exponent)) / cti)) *
-                           mk3(hat.x, hat.y, hat.z);
-          const v3 c = (color * pf) / ppm_R(G, n_old);
-          atomicAdd(HP.S + hi, make_float4(c.x, c.y, c.z, 0.0f));   // one 16-byte vector atomic (sm_90+)
-        }
-       }
+        if (__any_sync(0xffffffffu, qn > PPM_QCAP - 4)) drain();
       }
     }
+    drain();
     const uint32_t ci = warp_append(&waves[d + 1].count, cont);
     if (cont) {
       const uint32_t cs = next_begin + ci;
@@ -396,8 +441,8 @@ __global__ void k_ppm_count_rays(const WaveInfo* waves, int d, PpmCounters* PC) 
 // packs {S.rgb, n} per hit point (the additive state; all-reduced across GPUs)
 __global__ void k_ppm_export(HitPoints HP, uint32_t n_hp, float4* out) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
-    const float4 s = HP.S[i];
-    out[i] = make_float4(s.x, s.y, s.z, (float)HP.n[i]);
+    const float4 s = HP.state[i];
+    out[i] = make_float4(s.x, s.y, s.z, (float)*hp_n(HP, i));
   }
 }
 // tau/(pi r2 N) = S/(pi r0^2 N) since tau = R(n) S and r2 = r0^2 R(n)
@@ -419,6 +464,6 @@ __global__ void k_ppm_pack_hit_points(HitPoints HP, uint32_t n_hp, float* out16)
     float* o = out16 + 16 * (size_t)i;
     o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = n.x; o[4] = n.y; o[5] = n.z; o[6] = w.x; o[7] = w.y; o[8] = w.z;
     o[9] = a.x; o[10] = a.y; o[11] = a.z; o[12] = (float)__float_as_int(n.w); o[13] = (float)__float_as_uint(w.w);
-    o[14] = a.w; o[15] = (float)HP.n[i];
+    o[14] = a.w; o[15] = (float)*hp_n(HP, i);
   }
 }

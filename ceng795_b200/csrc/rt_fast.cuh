@@ -113,6 +113,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
   uint32_t cur = B200RT_REF_NONE;  // node to process next without going through the stack
   float cur_t = 0.f;
   bool culling = true;             // HW7/PPM back-face culling, off inside refractive instances
+#ifdef RT_DEBUG_RAY_COST
+  unsigned int ray_nodes0 = 0, ray_tris0 = 0;
+#endif
 
   for (;;) {
     // ---- refill idle lanes from the wave's work cursor ----------------------
@@ -143,6 +146,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
           cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true;
           cur = B200RT_REF_NONE;
           has_ray = true;
+#ifdef RT_DEBUG_RAY_COST
+          ray_nodes0 = tc.nodes; ray_tris0 = tc.tris;
+#endif
           // ---- phase 0: expand the reference's top-level tree with its exact gates (BVH::intersect,
           // HW3/src/Bounding_volume_hierarchy.cpp:31-55; Mesh_instance's own gate HW3/include/Mesh.h:59-62)
           // into the queue of objects this ray has to enter, nearest first
@@ -364,6 +370,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
             P.hit_a[out_slot] = make_float4(found ? best.t : RT_INF, best.beta, best.gamma,
                                             __uint_as_float(found ? best.top_ref : B200RT_REF_NONE));
             P.hit_b[out_slot] = make_int2(found ? best.top_rank : -1, found ? best.tri : -1);
+#ifdef RT_DEBUG_RAY_COST
+            P.rec3[out_slot] = (tc.nodes - ray_nodes0) | ((tc.tris - ray_tris0) << 16);
+#endif
           }
           has_ray = false;
         }
