@@ -153,7 +153,7 @@ def heightfield(n, seed=SEED, extent=4.0):
 
 
 def cfg2_hw3(n=724, width=1920, height=1080, n_instances=8, depth=2, seed=SEED, image_name="cfg2.png",
-             smooth=False, cam_angle_deg=0.0) -> str:
+             smooth=False, cam_angle_deg=0.0, glass=False) -> str:
     """Config 2 — HW2-era features in the HW3 dialect (the HW2 tree lacks MeshInstance):
     a (2*n*n)-triangle heightfield (n=724 -> 1 048 352), `n_instances` transformed
     instances of it, 4 spheres, 2 point lights, mirror depth 2, 1 spp."""
@@ -167,7 +167,9 @@ def cfg2_hw3(n=724, width=1920, height=1080, n_instances=8, depth=2, seed=SEED, 
             + _material_xml(2, [0.1, 0.1, 0.1], [0.15, 0.15, 0.2], [0.5, 0.5, 0.5], 80, mirror=[0.6, 0.6, 0.6])
             + _material_xml(3, [0.1, 0.1, 0.1], [0.3, 0.1, 0.1], [0.4, 0.4, 0.4], 50, mirror=[0.35, 0.3, 0.3])
             + _material_xml(4, [0.3, 0.3, 0.3], [0.7, 0.3, 0.2], [0.3, 0.3, 0.3], 10)
-            + _material_xml(5, [0.3, 0.3, 0.3], [0.2, 0.4, 0.8], [0.6, 0.6, 0.6], 40))
+            + _material_xml(5, [0.3, 0.3, 0.3], [0.2, 0.4, 0.8], [0.6, 0.6, 0.6], 40)
+            + (_material_xml(6, [0, 0, 0], [0.02, 0.02, 0.02], [0.2, 0.2, 0.2], 60, transparency=[0.85, 0.9, 0.95], refr=1.45)
+               if glass else ""))
     xf = "  <Transformations>\n"
     inst = ""
     for k in range(n_instances):
@@ -184,7 +186,7 @@ def cfg2_hw3(n=724, width=1920, height=1080, n_instances=8, depth=2, seed=SEED, 
     xf += "  </Transformations>\n"
     sph = ""
     for i in range(4):
-        sph += (f'    <Sphere id="{i + 1}">\n      <Material>{[2, 4, 3, 5][i]}</Material>\n'
+        sph += (f'    <Sphere id="{i + 1}">\n      <Material>{[2, 6 if glass else 4, 3, 5][i]}</Material>\n'
                 f"      <Center>{cb + i + 1}</Center>\n      <Radius>{_f([sph_r[i]])}</Radius>\n    </Sphere>\n")
     aspect = width / height
     shading = ' shadingMode="smooth"' if smooth else ""

@@ -21,6 +21,10 @@ CASES = {
     "cfg1_hw1_depth0": ("hw1", "cfg1_hw1", dict(width=64, height=48, depth=0, n_spheres=12)),
     "cfg2_hw3_n32": ("hw3", "cfg2_hw3", dict(n=32, width=160, height=90)),
     "cfg2_hw3_n48_smooth": ("hw3", "cfg2_hw3", dict(n=48, width=128, height=96, smooth=True, depth=3)),
+    # HW2 tree: no instancing (MeshInstance elements are ignored by its loader), Mesh sits in the top BVH itself,
+    # dielectric with the flipped Beer sign (HW2/Scene.cpp:166-168)
+    "cfg2_hw2_glass": ("hw2", "cfg2_hw3", dict(n=32, width=128, height=96, n_instances=0, depth=4, glass=True)),
+    "cfg2_hw3_glass": ("hw3", "cfg2_hw3", dict(n=32, width=128, height=96, n_instances=3, depth=4, glass=True)),
     # HW7 Whitted, every pixel deterministic: textures (nearest/bilinear, repeat/clamp, replace_kd/blend_kd,
     # image bump), 5 BRDFs, point/spot/directional lights, mirror + glass, culling, instancing
     "hw7_whitted_160": ("hw7", "hw7_scene", dict(width=160, height=120, light_scale=3.0)),

@@ -12,7 +12,7 @@ from ceng795_b200 import _build, _lib, scene, scenes
 def test_exports_every_declared_symbol():
     L = _lib.load()
     names = _lib.declared_symbols()
-    assert len(names) >= 25
+    assert len(names) >= 40
     for n in names:
         assert hasattr(L, n), f"{n} declared in b200rt.h but not exported"
 
@@ -22,12 +22,15 @@ def test_struct_sizes_match_header(tmp_path):
     src.write_text('#include <stdio.h>\n#include "b200rt.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(b200rt_bvh_node),sizeof(b200rt_mesh),sizeof(b200rt_instance),sizeof(b200rt_sphere),"
                    "sizeof(b200rt_triprim),sizeof(b200rt_material),sizeof(b200rt_light),sizeof(b200rt_camera),"
-                   "sizeof(B200SceneDesc),sizeof(B200RenderOpts),sizeof(B200RenderStats));return 0;}\n")
+                   "sizeof(B200SceneDesc),sizeof(B200RenderOpts),sizeof(B200RenderStats));"
+                   'printf("%zu %zu %zu %zu %zu\\n",sizeof(b200rt_texture),sizeof(b200rt_brdf),sizeof(b200rt_camera_in),'
+                   "sizeof(B200PpmOpts),sizeof(B200PpmStats));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", _build.ROOT + "/include", str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(t) for t in (_lib.BvhNode, _lib.Mesh, _lib.Instance, _lib.Sphere, _lib.TriPrim, _lib.Material,
-                                  _lib.Light, _lib.Camera, _lib.SceneDesc, _lib.RenderOpts, _lib.RenderStats)]
+                                  _lib.Light, _lib.Camera, _lib.SceneDesc, _lib.RenderOpts, _lib.RenderStats,
+                                  _lib.Texture, _lib.Brdf, _lib.CameraIn, _lib.PpmOpts, _lib.PpmStats)]
     assert got == want
     assert got[0] == 64 and got[5] == 96
 
