@@ -155,7 +155,7 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     (*launches)++;
     if (hw1) {
       k_extend_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
-    } else if (S.semantics >= B200RT_SEM_HW7) {
+    } else if (S.semantics >= B200RT_SEM_HW4) {
       if (exact) k_extend<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
       else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     } else {
@@ -167,14 +167,16 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     d_last = d;
     if (!with_shading) break;
     const bool hw7 = S.semantics >= B200RT_SEM_HW7;
+    const bool hw4 = S.semantics == B200RT_SEM_HW4;
     if (hw7) k_shade7_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    else if (hw4) k_shade4_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     else k_shade_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     k_clamp_shadow_count<<<1, 1, 0, st>>>(sc->Q, sc->d_counters);
     (*launches) += 2;
     tm.mark(ST_SHADE);
     if (hw1) {
       k_shadow_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
-    } else if (S.semantics >= B200RT_SEM_HW7) {
+    } else if (S.semantics >= B200RT_SEM_HW4) {
       if (exact) k_shadow<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
       else k_trace_fast<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     } else {
@@ -184,6 +186,7 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     (*launches)++;
     tm.mark(ST_SHADOW);
     if (hw7) k_shade7_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    else if (hw4) k_shade4_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     else k_shade_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     k_finish_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->P, sc->d_counters);
     (*launches) += 2;
@@ -639,7 +642,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     return B200RT_E_INVALID;
   }
   if (d->semantics != B200RT_SEM_HW1 && d->semantics != B200RT_SEM_HW2 && d->semantics != B200RT_SEM_HW3 &&
-      d->semantics != B200RT_SEM_HW7 && d->semantics != B200RT_SEM_PPM) {
+      d->semantics != B200RT_SEM_HW4 && d->semantics != B200RT_SEM_HW7 && d->semantics != B200RT_SEM_PPM) {
     b200rt_internal_set_error("b200rt_scene_create: semantics not implemented on the device yet");
     return B200RT_E_UNSUPPORTED;
   }

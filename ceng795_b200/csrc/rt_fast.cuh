@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
   uint32_t cur_top = B200RT_REF_NONE;
   uint32_t cur = B200RT_REF_NONE;  // node to process next without going through the stack
   float cur_t = 0.f;
-  bool culling = true;             // HW7/PPM back-face culling, off inside refractive instances
+  const bool hw7 = S.semantics >= B200RT_SEM_HW7;  // HW4 has the band triangle test (TRI_MODE 7) but no culling
+  bool culling = hw7;              // HW7/PPM back-face culling, off inside refractive instances
 #ifdef RT_DEBUG_RAY_COST
   unsigned int ray_nodes0 = 0, ray_tris0 = 0;
 #endif
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
           best.t = RT_INF; best.beta = 0.f; best.gamma = 0.f; best.top_ref = B200RT_REF_NONE;
           best.top_rank = 0x7fffffff; best.tri = 0x7fffffff;
           found = false;
-          cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true;
+          cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = hw7;
           cur = B200RT_REF_NONE;
           has_ray = true;
 #ifdef RT_DEBUG_RAY_COST
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
                 }
                 cr = make_fast_ray(co, cd, eps);
                 cur_rank = in->rank; cur_top = ref;
-                culling = !(in->flags & B200RT_INST_REFRACTIVE);
+                culling = hw7 && !(in->flags & B200RT_INST_REFRACTIVE);
                 cur = froot; cur_t = 0.f;
               }
             } else if (kind == B200RT_KIND_SPHERE) {
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
               v3 lo = mk3(ro.x, ro.y, ro.z), ldir = mk3(rd.x, rd.y, rd.z);
               if (!(p->flags & B200RT_XF_IDENTITY)) { const v3 wo = lo, wd = ldir; lo = xf_point(p->inv, wo); ldir = xf_vector4(p->inv, wd); }
               float t, be, ga;
-              if (!(TRI_MODE == 7 && dot(ldir, ld3(p->normal)) > 0.0f) &&   // top-level objects are culled (HW7)
+              if (!(TRI_MODE == 7 && hw7 && dot(ldir, ld3(p->normal)) > 0.0f) &&   // top-level objects are culled (HW7)
                   tri_test<2>(ld3(p->v0), ld3(p->a1), ld3(p->a2), lo, ldir, eps, &t, &be, &ga) && t > 0.0f) {
                 if (ANY) { if (t < tlimit) { found = true; finished = true; } }
                 else if (better(t, p->rank, -1, best)) {

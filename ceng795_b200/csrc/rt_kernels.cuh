@@ -598,7 +598,21 @@ __global__ void k_combine(DScene S, Pool P, const WaveInfo* waves, int d, float4
     } else {
       const uint32_t pix = P.pixel[slot];
       const int ns = S.cam.samples_sqrt;
-      if (ns == 1) {
+      if (ns == 1 && S.semantics == B200RT_SEM_HW4) {
+        // HW4 splats the 3x3 Gaussian (sigma 1/2) even at one sample, with integer offsets (HW4/src/Scene.cpp:26-49)
+        const int W = S.cam.width, H = S.cam.height;
+        const int i = (int)(pix % (uint32_t)W), j = (int)(pix / (uint32_t)W);
+        for (int aj = j - 1; aj < j + 2; aj++) {
+          if (aj < 0 || aj >= H) continue;
+          for (int ai = i - 1; ai < i + 2; ai++) {
+            if (ai < 0 || ai >= W) continue;
+            const float w = gaussian_filter((float)(i - ai), (float)(j - aj), 1.5f / 3.0f);
+            float* px = reinterpret_cast<float*>(accum + (size_t)aj * W + ai);
+            atomicAdd(px + 0, color.x * w); atomicAdd(px + 1, color.y * w);
+            atomicAdd(px + 2, color.z * w); atomicAdd(px + 3, w);
+          }
+        }
+      } else if (ns == 1) {
         // Pixel::add_color(color, 1.0f) on a fresh pixel — HW3/src/Scene.cpp:31-34
         accum[pix] = make_float4(color.x * 1.0f, color.y * 1.0f, color.z * 1.0f, 1.0f);
       } else {
@@ -614,7 +628,7 @@ __global__ void k_combine(DScene S, Pool P, const WaveInfo* waves, int d, float4
             if (ai < 0 || ai >= W) continue;
             const float fx = ((float)i + sx) - ((float)ai + 0.5f);
             const float fy = ((float)j + sy) - ((float)aj + 0.5f);
-            const float w = gaussian_filter(fx, fy, 1.0f / 3.0f);
+            const float w = gaussian_filter(fx, fy, S.semantics == B200RT_SEM_HW4 ? 1.5f / 3.0f : 1.0f / 3.0f);
             float* px = reinterpret_cast<float*>(accum + (size_t)aj * W + ai);
             atomicAdd(px + 0, color.x * w); atomicAdd(px + 1, color.y * w);
             atomicAdd(px + 2, color.z * w); atomicAdd(px + 3, w);

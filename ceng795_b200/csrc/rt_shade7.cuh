@@ -516,6 +516,238 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_a(DScene S, Pool P, ShadowQ
   }
 }
 
+// ---- HW4: HW3's shading loop with the textured diffuse colour (HW4/src/Scene.cpp:129-357) ----------
+// shade_a: surface record through surface7 (HW4's Mesh_triangle / Sphere already are HW7's, minus culling),
+// diffuse colour / replace_all, shadow rays with HW3's rules (no n.w_i gate, lights skipped when kd = ks = 0).
+__global__ void __launch_bounds__(RT_BLOCK) k_shade4_a(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves, int d,
+                                                       Counters* C) {
+  const uint32_t begin = waves[d].begin, count = waves[d].count;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (count + stride - 1) / stride;
+  for (uint32_t r = 0; r < rounds; r++) {
+    const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = k < count;
+    const uint32_t slot = begin + (act ? k : 0);
+    const float4 ha = P.hit_a[slot];
+    const uint32_t top_ref = __float_as_uint(ha.w);
+    const bool hit = act && B200RT_REF_KIND(top_ref) != B200RT_KIND_NONE;
+    v3 p = mk3(0, 0, 0);
+    float time = 0.f;
+    uint32_t key = 0;
+    bool lights_on = false;
+    if (hit) {
+      const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
+      const v3 o = mk3(ro.x, ro.y, ro.z), dir = mk3(rd.x, rd.y, rd.z);
+      const uint32_t meta = __float_as_uint(rd.w);
+      time = ro.w;
+      const Surf7 sf = surface7(S, top_ref, P.hit_b[slot].y, ha.y, ha.z, o, dir, time, ha.x);
+      P.nrm[slot] = make_float4(sf.n.x, sf.n.y, sf.n.z, __int_as_float(sf.material));
+      v3 kd;
+      const bool replace_all = diffuse_constant7(S, sf, &kd);
+      P.kd[slot] = make_float4(kd.x, kd.y, kd.z, __uint_as_float(replace_all ? RT_KDF_REPLACE_ALL : 0u));
+      p = o + (dir * ha.x);
+      key = P.key[slot];
+      const b200rt_material& m = S.mats[sf.material];
+      lights_on = !replace_all && !(meta & RT_META_INMEDIUM) && !(is_zero(ld3(m.diffuse)) && is_zero(ld3(m.specular)));
+    }
+    int area_index = 0;
+    for (int li = 0; li < S.n_lights; li++) {
+      const b200rt_light& L = S.lights[li];
+      v3 wi = mk3(0, 0, 0);
+      float ldist = 0.f;
+      if (lights_on) {
+        const v3 lvec = light_position(L, key, area_index) - p;
+        wi = normalize(lvec);
+        ldist = length(lvec);
+      }
+      if (L.kind == B200RT_LIGHT_AREA) area_index++;
+      const uint32_t vslot = slot * (uint32_t)S.n_lights + (uint32_t)li;
+      if (act) Q.vis[vslot] = 0;
+      const uint32_t qi = warp_append(&C->shadow_count, lights_on);
+      if (lights_on) {
+        if (qi < Q.capacity) {
+          const v3 so = p + (S.shadow_eps * wi);
+          Q.o[qi] = make_float4(so.x, so.y, so.z, ldist - S.shadow_eps);
+          Q.d[qi] = make_float4(wi.x, wi.y, wi.z, __uint_as_float(vslot));
+          Q.time[qi] = time;
+        } else {
+          C->overflow = 1;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RT_BLOCK) k_shade4_b(DScene S, Pool P, ShadowQueue Q, WaveInfo* waves, int d,
+                                                       Counters* C) {
+  const uint32_t begin = waves[d].begin, count = waves[d].count;
+  const uint32_t next_begin = waves[d + 1].begin;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (count + stride - 1) / stride;
+  for (uint32_t r = 0; r < rounds; r++) {
+    const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = k < count;
+    const uint32_t slot = begin + (act ? k : 0);
+    const float4 ha = P.hit_a[slot];
+    const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
+    const uint32_t meta = __float_as_uint(rd.w);
+    const uint32_t depth = RT_META_DEPTH(meta);
+    const uint32_t top_ref = __float_as_uint(ha.w);
+    const bool hit = act && B200RT_REF_KIND(top_ref) != B200RT_KIND_NONE;
+    v3 color = mk3(0, 0, 0);
+    v3 km = mk3(0, 0, 0), kk = mk3(0, 0, 0);
+    float fres = 0.f;
+    bool want_m = false, want_r = false, want_t = false;
+    v3 dir_m = mk3(0, 0, 0), dir_r = mk3(0, 0, 0), dir_t = mk3(0, 0, 0);
+    bool med_r = false, med_t = false;
+    v3 p = mk3(0, 0, 0);
+    const float time = ro.w;
+    const uint32_t key = act ? P.key[slot] : 0u;
+    const v3 o = mk3(ro.x, ro.y, ro.z), dir = mk3(rd.x, rd.y, rd.z);
+    if (act && !hit && (meta & RT_META_PRIMARY)) {
+      // HW4/src/Scene.cpp:135-144: primary by ray type; background texture at (x / width, y / height)
+      if (S.background_texture >= 0) {
+        const uint32_t pix = P.pixel[slot];
+        const int W = S.cam.width, ns = S.cam.samples_sqrt;
+        const int i = (int)(pix % (uint32_t)W), j = (int)(pix / (uint32_t)W);
+        float x, y;
+        if (ns == 1) { x = i + 0.5f; y = j + 0.5f; }
+        else {
+          const uint32_t sidx = P.sample[slot];
+          const int sx = (int)(sidx / (uint32_t)ns), sy = (int)(sidx % (uint32_t)ns);
+          x = i + (sx + rng_u01(key, 4)) / ns; y = j + (sy + rng_u01(key, 5)) / ns;
+        }
+        color = tex_color7(S, S.textures[S.background_texture], x / S.cam.width, y / S.cam.height);
+      } else {
+        color = S.background;
+      }
+    }
+    if (hit) {
+      const float4 nn = P.nrm[slot];
+      const v3 n = mk3(nn.x, nn.y, nn.z);
+      const b200rt_material& m = S.mats[__float_as_int(nn.w)];
+      const float4 kdf = P.kd[slot];
+      const v3 kd = mk3(kdf.x, kdf.y, kdf.z);
+      p = o + (dir * ha.x);
+      const v3 w0 = normalize(o - p);
+      if (__float_as_uint(kdf.w) & RT_KDF_REPLACE_ALL) {
+        color = kd;   // the texel; no lights, no mirror, no refraction (everything sits inside `if (!is_replace_all)`)
+      } else {
+        const v3 ks = ld3(m.specular);
+        const bool has_d = !is_zero(ld3(m.diffuse)), has_s = !is_zero(ks);
+        if (!(meta & RT_META_INMEDIUM)) {
+          color = color + (ld3(m.ambient) * S.ambient);
+          int area_index = 0;
+          for (int li = 0; li < S.n_lights; li++) {
+            const b200rt_light& L = S.lights[li];
+            const int ai = area_index;
+            if (L.kind == B200RT_LIGHT_AREA) area_index++;
+            if (!has_d && !has_s) continue;
+            if (!Q.vis[slot * (uint32_t)S.n_lights + (uint32_t)li]) continue;
+            const v3 lvec = light_position(L, key, ai) - p;
+            const v3 wi = normalize(lvec);
+            const float ldist = length(lvec);
+            const float d2 = ldist * ldist;
+            const v3 inten = ld3(L.intensity);
+            if (L.kind == B200RT_LIGHT_AREA) {
+              const float icos = dot(-wi, ld3(L.normal));
+              if (has_d) color = color + ((((kd * inten) * icos) * dot(n, wi)) / d2);
+              if (has_s) {
+                const float sc = fmaxf(0.0f, dot(n, normalize(w0 + wi)));
+                color = color + ((((ks * inten) * icos) * (float)pow((double)sc, (double)m.phong_exponent)) / d2);
+              }
+            } else {
+              if (has_d) color = color + (((kd * inten) * dot(n, wi)) / d2);
+              if (has_s) {
+                const float sc = fmaxf(0.0f, dot(n, normalize(w0 + wi)));
+                color = color + (((ks * inten) * (float)pow((double)sc, (double)m.phong_exponent)) / d2);
+              }
+            }
+          }
+        }
+        const bool budget = (int)depth < S.max_depth;
+        km = ld3(m.mirror);
+        if (!is_zero(km) && budget) {
+          const v3 wr = normalize((n * (2 * dot(n, w0))) - w0);
+          dir_m = wr;
+          if (m.roughness != 0.0f) {
+            v3 rp;
+            if (wr.x < wr.y && wr.x < wr.z) rp = mk3(1.0f, wr.y, wr.z);
+            else if (wr.y < wr.z && wr.y < wr.x) rp = mk3(wr.x, 1.0f, wr.z);
+            else rp = mk3(wr.x, wr.y, 1.0f);
+            const v3 u = normalize(cross(rp, wr));
+            const v3 v = normalize(cross(u, wr));
+            const float eu = rng_u01(key, 2) - 0.5f, ev = rng_u01(key, 3) - 0.5f;
+            dir_m = normalize(wr + (((u * eu) + (v * ev)) * m.roughness));
+          }
+          want_m = true;
+        }
+        const v3 kt = ld3(m.transparency);
+        if (!is_zero(kt) && budget) {
+          const v3 wr = normalize((n * (2 * dot(n, w0))) - w0);
+          const v3 dn = normalize(dir);
+          const float ni = m.refraction_index;
+          float cos_theta = 0.0f;
+          bool tir = false, entering;
+          if (dot(dn, n) < 0.0f) {
+            refract_ray(dn, n, ni, &dir_t);
+            cos_theta = dot(-dn, n);
+            kk = mk3(1.0f, 1.0f, 1.0f);
+            entering = true;
+          } else {
+            const double ht = (double)ha.x;
+            kk = mk3((float)exp(log((double)kt.x) * ht), (float)exp(log((double)kt.y) * ht),
+                     (float)exp(log((double)kt.z) * ht));
+            entering = false;
+            if (refract_ray(dn, -n, 1.0f / ni, &dir_t)) cos_theta = dot(dir_t, n);
+            else tir = true;
+          }
+          dir_r = wr;
+          want_r = true;
+          if (tir) {
+            med_r = true;
+            fres = -1.0f;
+          } else {
+            const float r0 = ((ni - 1) * (ni - 1)) / ((ni + 1) * (ni + 1));
+            fres = (float)((double)r0 + (double)(1 - r0) * pow((double)(1.0f - cos_theta), 5.0));
+            med_r = !entering;
+            med_t = entering;
+            want_t = true;
+          }
+        }
+      }
+    }
+    uint32_t cm = 0xffffffffu, cr = 0xffffffffu, ct = 0xffffffffu;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const bool want = (c == 0) ? want_m : (c == 1 ? want_r : want_t);
+      const uint32_t ci = warp_append(&waves[d + 1].count, want);
+      if (want) {
+        const uint32_t cs = next_begin + ci;
+        if (cs < P.capacity) {
+          const v3 cdir = (c == 0) ? dir_m : (c == 1 ? dir_r : dir_t);
+          const v3 co = p + (cdir * S.shadow_eps);
+          const bool med = (c == 0) ? false : (c == 1 ? med_r : med_t);
+          const uint32_t cmeta = (depth + 1) | (med ? RT_META_INMEDIUM : 0u);
+          P.ray_o[cs] = make_float4(co.x, co.y, co.z, time);
+          P.ray_d[cs] = make_float4(cdir.x, cdir.y, cdir.z, __uint_as_float(cmeta));
+          P.key[cs] = rng_mix(key, 0x101u + (uint32_t)c);
+          P.pixel[cs] = P.pixel[slot];
+          if (c == 0) cm = cs; else if (c == 1) cr = cs; else ct = cs;
+        } else {
+          C->overflow = 1;
+        }
+      }
+    }
+    if (act) {
+      P.rec0[slot] = make_float4(color.x, color.y, color.z, fres);
+      P.rec1[slot] = make_float4(km.x, km.y, km.z, __uint_as_float(cm));
+      P.rec2[slot] = make_float4(kk.x, kk.y, kk.z, __uint_as_float(cr));
+      P.rec3[slot] = ct;
+    }
+  }
+}
+
 // ---- shade_b (HW7): Scene::send_ray / trace_ray / trace_path bodies -------------------------
 __global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQueue Q, WaveInfo* waves, int d,
                                                        Counters* C) {

@@ -283,7 +283,8 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
   v3 co = o, cd = d;
   int cur_rank = 0x7fffffff;    // rank of the instance being traversed
   uint32_t cur_top = B200RT_REF_NONE;
-  bool culling = true;          // HW7/PPM: back-face culling, off inside refractive instances
+  const bool hw7 = S.semantics >= B200RT_SEM_HW7;  // HW4: band triangle test (TRI_MODE 7) without culling
+  bool culling = hw7;           // HW7/PPM: back-face culling, off inside refractive instances
 
   // root: a gate for INNER / INSTANCE, unconditional for primitives
   {
@@ -305,7 +306,7 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
     const uint32_t kind = B200RT_REF_KIND(ref);
     const uint32_t idx = B200RT_REF_INDEX(ref);
     if (kind == 14u) {  // leave instance
-      co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true;
+      co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = hw7;
       continue;
     }
     if (!EXACT) {
@@ -403,8 +404,8 @@ __device__ __forceinline__ bool traverse(const DScene& S, v3 o, v3 d, float time
       }
       cr = make_ray(co, cd, eps);
       cur_rank = in->rank; cur_top = ref;
-      culling = !(in->flags & B200RT_INST_REFRACTIVE);
-      if (sp + 2 > RT_STACK) { co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = true; continue; }
+      culling = hw7 && !(in->flags & B200RT_INST_REFRACTIVE);
+      if (sp + 2 > RT_STACK) { co = o; cd = d; cr = wr; cur_rank = 0x7fffffff; cur_top = B200RT_REF_NONE; culling = hw7; continue; }
       stack[sp] = RT_SENTINEL; stack_t[sp] = 0.f; sp++;
       if (mk == B200RT_KIND_INNER) {
         float e;

