@@ -223,6 +223,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_void_p, P(RenderStats)]),
         "b200rt_debug_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+        "b200rt_tonemap_photographic": (C.c_int, [C.c_void_p, C.c_int, c_f, c_f, c_f, C.c_void_p]),
         "b200rt_ppm_eye_pass": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, P(PpmStats)]),
         "b200rt_ppm_trace_photons": (C.c_int, [C.c_void_p, P(PpmOpts), P(PpmStats)]),
         "b200rt_ppm_density": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),

@@ -5,9 +5,11 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "ppm_kernels.cuh"
+#include "tonemap_kernels.cuh"
 
 extern "C" void b200rt_internal_set_error(const char* msg);
 
@@ -753,6 +755,52 @@ void b200rt_scene_destroy(b200rt_scene* sc) {
   if (sc->ev[0]) cudaEventDestroy(sc->ev[0]);
   if (sc->ev[1]) cudaEventDestroy(sc->ev[1]);
   delete sc;
+}
+
+int b200rt_tonemap_photographic(b200rt_scene* sc, int camera_index, float key, float burn_percent, float saturation,
+                                uint8_t* rgb8_out) {
+  if (!sc || !rgb8_out || camera_index < 0 || camera_index >= (int)sc->cameras.size() || !sc->d_accum) {
+    b200rt_internal_set_error("b200rt_tonemap_photographic: render the camera first");
+    return B200RT_E_INVALID;
+  }
+  CK(cudaSetDevice(sc->device));
+  const b200rt_camera& c = sc->cameras[camera_index];
+  const uint32_t n = (uint32_t)c.width * (uint32_t)c.height;
+  if (n == 0 || n > sc->accum_pixels) return B200RT_E_INVALID;
+  cudaStream_t st = sc->stream;
+  float* d_f = nullptr;        // lum | scaled | keys | sorted
+  double* d_sum = nullptr;
+  unsigned char* d_rgb = nullptr;
+  void* d_tmp = nullptr;
+  int rc = B200RT_OK;
+  do {
+    if (cudaMalloc((void**)&d_f, sizeof(float) * 4 * (size_t)n) != cudaSuccess ||
+        cudaMalloc((void**)&d_sum, sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void**)&d_rgb, 3 * (size_t)n) != cudaSuccess) { rc = B200RT_E_CUDA; break; }
+    float *lum = d_f, *scaled = d_f + n, *keys = d_f + 2 * (size_t)n, *sorted = d_f + 3 * (size_t)n;
+    cudaMemsetAsync(d_sum, 0, sizeof(double), st);
+    k_tm_luminance<<<sc->sm_count * 4, 256, 0, st>>>(sc->d_accum, n, lum, d_sum);
+    k_tm_scale<<<sc->sm_count * 4, 256, 0, st>>>(n, key, d_sum, lum, scaled, keys);
+    size_t need = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, need, keys, sorted, (int)n, 0, 32, st);
+    if (cudaMalloc(&d_tmp, need) != cudaSuccess) { rc = B200RT_E_CUDA; break; }
+    cub::DeviceRadixSort::SortKeys(d_tmp, need, keys, sorted, (int)n, 0, 32, st);
+    // white point: sorted[size - white_count], the last element when white_count == 0 (Photographic_tmo.cpp:30-37)
+    float wc = (float)n * burn_percent / 100.0f;
+    int white_count = (int)wc;
+    if (white_count < 0) white_count = 0;
+    if (white_count > (int)n) white_count = (int)n;
+    const uint32_t white_index = white_count == 0 ? n - 1 : n - (uint32_t)white_count;
+    k_tm_apply<<<sc->sm_count * 4, 256, 0, st>>>(sc->d_accum, n, lum, scaled, sorted, white_index, saturation, d_rgb);
+    if (cudaMemcpyAsync(rgb8_out, d_rgb, 3 * (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = B200RT_E_CUDA;
+  } while (0);
+  if (rc == B200RT_E_CUDA) b200rt_internal_set_error("b200rt_tonemap_photographic: CUDA error");
+  if (d_f) cudaFree(d_f);
+  if (d_sum) cudaFree(d_sum);
+  if (d_rgb) cudaFree(d_rgb);
+  if (d_tmp) cudaFree(d_tmp);
+  return rc;
 }
 
 int b200rt_debug_pool(b200rt_scene* sc, int field, void* out, int64_t count) {

@@ -50,3 +50,38 @@ def compare_8bit(a: np.ndarray, b: np.ndarray) -> dict:
     d = np.abs(a.astype(np.int16) - b.astype(np.int16)).max(axis=-1)
     return {"exact": float((d == 0).mean()), "within1": float((d <= 1).mean()), "max": int(d.max()),
             "n": int(d.size)}
+
+
+def tonemap_photographic(rgbw: np.ndarray, key: float, burn_percent: float, saturation: float) -> np.ndarray:
+    """Host restatement (test / oracle side) of Photographic_tmo::apply_tmo (HW7/src/Photographic_tmo.cpp:10-49)
+    followed by main's sRGB curve (HW7/src/main.cpp:59-91) and write_png's clamp + uchar store: uint8[H,W,3].
+    The log-average is a sequential float sum in the reference; here it is summed in float32 in the same order."""
+    rgbw = np.asarray(rgbw, np.float32)
+    h, w = rgbw.shape[:2]
+    wt = rgbw[..., 3:4]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        col = np.where(wt == 0, np.float32(0), rgbw[..., :3] / wt).astype(np.float32).reshape(-1, 3)
+    f = np.float32
+    lum = (f(0.21) * col[:, 0] + f(0.72) * col[:, 1]).astype(f) + f(0.07) * col[:, 2]
+    lum = lum.astype(f)
+    logs = np.log((lum + f(0.001)).astype(f)).astype(f)
+    acc = f(0)
+    for chunk in np.array_split(logs, max(1, logs.size // 4096)):      # sequential float32 accumulation
+        for v in chunk:
+            acc = f(acc + v)
+    log_avg = f(np.exp(f(acc / f(lum.size))))
+    lums = (f(key) * lum / log_avg).astype(f)
+    srt = np.sort(lums)
+    white_count = int(f(lum.size) * f(burn_percent) / f(100.0))
+    white_count = max(0, min(lum.size, white_count))
+    white = srt[lum.size - 1] if white_count == 0 else srt[lum.size - white_count]
+    ld = ((lums * (f(1) + lums / f(white * white))) / (lums + f(1))).astype(f)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = (col / lum[:, None]).astype(f)
+        out = (np.power(ratio, f(saturation)).astype(f) * ld[:, None]).astype(f)
+    inv = f(1.0) / f(2.4)
+    c = np.minimum(f(1), np.maximum(f(0), np.nan_to_num(out, nan=0.0, posinf=3e38, neginf=-3e38))).astype(f)
+    g = (f(1.055) * np.power(c, inv).astype(f) - f(0.055)).astype(f)
+    g = np.minimum(f(1), np.maximum(f(0), g)) * f(255.0)
+    q = np.minimum(f(255), np.maximum(f(0), g))
+    return np.trunc(q).astype(np.uint8).reshape(h, w, 3)

@@ -642,6 +642,20 @@ class Scene:
                                              t.ctypes.data, C.byref(st)), "b200rt_trace_rays")
         return ids, t, st
 
+    def tonemap(self, camera_index: int = 0, key: float | None = None, burn: float | None = None,
+                saturation: float | None = None) -> np.ndarray:
+        """Photographic TMO + sRGB of the frame the last render_image / render_device left in HBM
+        (Camera::get_tmo()->apply_tmo + main's gamma loop, HW7/src/main.cpp:59-91).  uint8[H,W,3]."""
+        tm = self.spec.cameras[camera_index].get("tonemap") or {}
+        key = tm.get("key", 0.18) if key is None else key
+        burn = tm.get("burn", 1.0) if burn is None else burn
+        saturation = tm.get("saturation", 1.0) if saturation is None else saturation
+        w, h = self.image_size(camera_index)
+        out = np.zeros((h, w, 3), np.uint8)
+        _lib.check(self._L.b200rt_tonemap_photographic(self._scene, camera_index, key, burn, saturation,
+                                                       out.ctypes.data), "b200rt_tonemap_photographic")
+        return out
+
     # ---- PPM: the calls PPM/src/main.cpp makes on Scene (PPM/include/Scene.h:48-55) --------------------
     def eye_trace_lines(self, camera_index: int = 0, seed: int = 0):
         """reset_hash_grid + eye_trace_lines + build_hash_grid.  Returns PpmStats."""

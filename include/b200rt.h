@@ -418,6 +418,12 @@ int b200rt_ppm_density_from(b200rt_scene*, const float* d_S_n, double total_num_
 /* test hook: 16 floats per hit point {position, normal, w_o, attenuation, material, pixel, pixel_weight, n} */
 int b200rt_ppm_get_hit_points(b200rt_scene*, float* out16, int64_t capacity, int64_t* n_out);
 
+/* ---- next row: Photographic tonemap + sRGB of the frame b200rt_render* left in HBM ----
+ * Replaces Photographic_tmo::apply_tmo + the gamma loop of main (HW7/src/Photographic_tmo.cpp:10-49,
+ * HW7/src/main.cpp:59-91) + write_png's clamp: W*H*3 bytes into caller-owned host memory. */
+int b200rt_tonemap_photographic(b200rt_scene*, int camera_index, float image_key, float burn_percent,
+                                float saturation, uint8_t* rgb8_out);
+
 /* Debug / test hook: copies `count` elements of one wavefront-pool array of the LAST render batch to
  * host memory.  field: 0 ray_o(f4) 1 ray_d(f4) 2 hit_a(f4) 3 nrm(f4) 4 rec0(f4) 5 rec1(f4) 6 rec2(f4)
  * 7 rec4(f4) 8 final_c(f4) 9 kd(f4) 10 pixel(u32) 11 key(u32) 12 hit_b(i32x2) 13 rec3(u32). */

@@ -200,3 +200,19 @@ def test_hw4_multisample_matches_oracle(gpu, tmp_path):
     assert (st.rays_primary, st.rays_shadow, st.rays_secondary) == (cnt.rays_primary, cnt.rays_shadow, cnt.rays_secondary)
     a, b = rgbw[..., :3] / rgbw[..., 3:], o_rgbw[..., :3] / o_rgbw[..., 3:]
     assert np.max(np.abs(a - b) / (np.abs(b) + 1.0)) < 1e-4      # tolerance: 1e-4 relative (+1 absolute floor)
+
+
+def test_photographic_tonemap_on_device(gpu, tmp_path):
+    """Photographic TMO + sRGB on the GPU against the host restatement (which is pinned byte-exact
+    to the HW7 binary's tonemapped PNG in tests/test_oracle_golden.py)."""
+    xml = scenes.hw7_scene(str(tmp_path), width=128, height=96, light_scale=3.0, tonemap=True)
+    sc = scene.Scene(xml, "hw7", base_dir=str(tmp_path))
+    rgbw, _ = sc.render_image(0)
+    tm = sc.spec.cameras[0]["tonemap"]
+    want = image.tonemap_photographic(rgbw, tm["key"], tm["burn"], tm["saturation"])
+    got = sc.tonemap(0)
+    cmp = image.compare_8bit(got, want)
+    assert cmp["within1"] >= 0.999 and cmp["exact"] >= 0.98, cmp      # log-average summed in a different order
+    got2 = sc.tonemap(0, key=0.36, burn=5.0, saturation=0.8)
+    cmp2 = image.compare_8bit(got2, image.tonemap_photographic(rgbw, 0.36, 5.0, 0.8))
+    assert cmp2["within1"] >= 0.999, cmp2

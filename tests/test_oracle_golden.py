@@ -90,3 +90,18 @@ def test_oracle_hw3_distribution_statistics_vs_reference():
     assert abs(q[0].mean() - ref.mean()) <= 0.01 * ref.mean()
     noise = np.sqrt(((q[0] - q[1]) ** 2).mean())
     assert np.sqrt(((q[0] - ref) ** 2).mean()) <= 1.35 * noise + 0.5
+
+
+def test_host_tonemap_matches_reference_png(tmp_path):
+    """Photographic_tmo + sRGB (HW7/src/Photographic_tmo.cpp, main.cpp:59-91): the host restatement against the HW7
+    binary's tonemapped PNG of a deterministic scene."""
+    if not cpu.have_ref("hw7"):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=96, height=72, light_scale=3.0, tonemap=True)
+    want = list(cpu.run_reference("hw7", xml, workdir=str(tmp_path))["images"].values())[0]
+    spec = scene.parse_xml(xml, "hw7", base_dir=str(tmp_path))
+    rgbw, _, _, _ = cpu.render(scene.HostScene(spec), 0)
+    tm = spec.cameras[0]["tonemap"]
+    got = image.tonemap_photographic(rgbw, tm["key"], tm["burn"], tm["saturation"])
+    assert image.compare_8bit(got, want)["exact"] == 1.0
