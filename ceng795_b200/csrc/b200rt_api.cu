@@ -8,6 +8,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include "fast_bvh.h"
 #include "ppm_kernels.cuh"
 #include "tonemap_kernels.cuh"
 
@@ -691,9 +692,50 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     S.tris = reinterpret_cast<const float4*>(p);
     bytes += (size_t)d->n_tris * 48;
   }
-  UP(S.fast_nodes, d->fast_nodes, d->n_fast_nodes, b200rt_bvh_node);
-  UP(S.fast_tris, d->fast_tri_geom, (size_t)d->n_fast_tris * 12, float);
-  UP(S.fast_tri_ref, d->fast_tri_ref, (size_t)d->n_fast_tris, int32_t);
+  // A producer that walks the reference's own objects (flatten.cpp) supplies the reference tree
+  // and tri_gate but need not know how to build the SAH tree the device walks: build it here from tri_geom
+  // (v1 = v0 - a1, v2 = v0 - a2; the boxes are grown anyway, only tri_gate carries the reference's decision).
+  std::vector<b200rt_bvh_node> own_nodes;
+  std::vector<int32_t> own_ref;
+  std::vector<float> own_geom;
+  std::vector<b200rt_mesh> own_meshes;
+  const b200rt_bvh_node* fast_nodes = d->fast_nodes;
+  const float* fast_geom = d->fast_tri_geom;
+  const int32_t* fast_ref = d->fast_tri_ref;
+  const b200rt_mesh* meshes = d->meshes;
+  int n_fast_nodes = d->n_fast_nodes, n_fast_tris = d->n_fast_tris;
+  if (d->semantics != B200RT_SEM_HW1 && d->n_fast_tris == 0 && d->n_tris > 0 && d->tri_gate) {
+    own_meshes.assign(d->meshes, d->meshes + d->n_meshes);
+    for (b200rt_mesh& m : own_meshes) {
+      m.fast_root = B200RT_REF_NONE;
+      if (m.tri_count < 2) continue;
+      std::vector<float> tb((size_t)m.tri_count * 6);
+      float ext = 0.f;
+      for (int k = 0; k < m.tri_count; k++) {
+        const float* g = d->tri_geom + 12 * (size_t)(m.tri_begin + k);
+        for (int a = 0; a < 3; a++) {
+          const float v0 = g[a], v1 = g[a] - g[3 + a], v2 = g[a] - g[6 + a];
+          tb[6 * (size_t)k + a] = fminf(v0, fminf(v1, v2));
+          tb[6 * (size_t)k + 3 + a] = fmaxf(v0, fmaxf(v1, v2));
+        }
+      }
+      for (int a = 0; a < 3; a++) {
+        ext = fmaxf(ext, m.root_box[3 + a] - m.root_box[a]);
+        ext = fmaxf(ext, fmaxf(fabsf(m.root_box[a]), fabsf(m.root_box[3 + a])));
+      }
+      const float grow = ext * (3e-5f + 4.0f * d->isect_eps) + 1e-30f;
+      m.fast_root = b200rt_fast::build(tb.data(), m.tri_count, m.tri_begin, grow, own_nodes, own_ref);
+    }
+    own_geom.resize(own_ref.size() * 12);
+    for (size_t k = 0; k < own_ref.size(); k++)
+      memcpy(&own_geom[12 * k], d->tri_geom + 12 * (size_t)own_ref[k], 48);
+    fast_nodes = own_nodes.data(); fast_geom = own_geom.data(); fast_ref = own_ref.data();
+    meshes = own_meshes.data();
+    n_fast_nodes = (int)own_nodes.size(); n_fast_tris = (int)own_ref.size();
+  }
+  UP(S.fast_nodes, fast_nodes, n_fast_nodes, b200rt_bvh_node);
+  UP(S.fast_tris, fast_geom, (size_t)n_fast_tris * 12, float);
+  UP(S.fast_tri_ref, fast_ref, (size_t)n_fast_tris, int32_t);
   UP(S.tri_gate, d->tri_gate, (size_t)d->n_tris * 6, float);
   UP(S.tri_info, d->tri_info, (size_t)d->n_tris * 2, int32_t);
   UP(S.tri_vidx, d->tri_vidx, (size_t)d->n_tris * 3, int32_t);
@@ -704,7 +746,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
                           d->vert_normal[3 * (size_t)i + 2], 0.f);
     UP(S.vnormal, vn.data(), vn.size(), float4);
   }
-  UP(S.meshes, d->meshes, d->n_meshes, b200rt_mesh);
+  UP(S.meshes, meshes, d->n_meshes, b200rt_mesh);
   UP(S.inst, d->instances, d->n_instances, b200rt_instance);
   UP(S.spheres, d->spheres, d->n_spheres, b200rt_sphere);
   UP(S.triprims, d->triprims, d->n_triprims, b200rt_triprim);

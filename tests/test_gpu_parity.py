@@ -216,3 +216,26 @@ def test_photographic_tonemap_on_device(gpu, tmp_path):
     got2 = sc.tonemap(0, key=0.36, burn=5.0, saturation=0.8)
     cmp2 = image.compare_8bit(got2, image.tonemap_photographic(rgbw, 0.36, 5.0, 0.8))
     assert cmp2["within1"] >= 0.999, cmp2
+
+
+def test_scene_create_builds_the_sah_tree(gpu):
+    """A producer that flattens the reference's own objects supplies the reference tree and
+    tri_gate only: b200rt_scene_create builds the SAH tree itself and the ids stay the reference's."""
+    import ctypes as C
+    from ceng795_b200 import _lib
+    tree, xml = scene_xml("cfg2_hw3_n48_smooth")
+    sc = scene.Scene(xml, tree, upload=False)
+    d = sc.host.desc
+    keep = (d.n_fast_nodes, d.n_fast_tris)
+    assert keep[1] > 0
+    d.n_fast_nodes = 0
+    d.n_fast_tris = 0          # as if the producer knew nothing about the device's tree
+    for i in range(d.n_meshes):
+        d.meshes[i].fast_root = 0xF0000000
+    sc.upload()
+    d.n_fast_nodes, d.n_fast_tris = keep
+    _, o_ids, o_t, _ = cpu.render(sc.host, 0, want_image=False, want_ids=True)
+    ids, t = sc.primary_ids(0)
+    assert np.array_equal(ids, o_ids) and np.array_equal(t.view(np.uint32), o_t.view(np.uint32))
+    _, st = sc.render_image(0)
+    assert st.nodes_visited > 0
