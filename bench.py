@@ -368,6 +368,16 @@ def run_b200(args):
         except Exception:
             traffic = None
     frames = world if split == "cameras" else 1
+    # second ceiling: the scene fetches are served by L1/L2, so also quote the extend kernel's
+    # algorithmic GB/s against the L2 read bandwidth measured here (48 MB working set, after the timed region)
+    l2 = None
+    if rank == 0:
+        import ctypes as C
+        g = C.c_double(0.0)
+        if sc._L.b200rt_measure_read_bandwidth(local, 48 << 20, 50, C.byref(g)) == 0:
+            l2 = g.value
+    extra["l2"] = {"peak": l2, "unit": "GB/s", "peak_source": "measured here: b200rt_measure_read_bandwidth, 48 MB x 50 passes",
+                   "frac": (ext_gbs / l2) if (ext_gbs and l2) else None}
     line = {
         "metric": METRIC, "value": rays / ms_total / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,

@@ -82,7 +82,7 @@ int pool_alloc(b200rt_scene* sc, T** p, size_t n) {
 void pool_free(b200rt_scene* sc) {
   Pool& P = sc->P;
   void* ptrs[] = {P.ray_o, P.ray_d, P.key, P.pixel, P.sample, P.hit_a, P.hit_b, P.nrm, P.rec0, P.rec1, P.rec2,
-                  P.rec3, P.final_c, P.kd, P.rec4, sc->Q.o, sc->Q.d, sc->Q.time, sc->Q.vis};
+                  P.rec3, P.final_c, P.kd, P.rec4, sc->Q.o, sc->Q.d, sc->Q.time, sc->Q.vis, sc->Q.lv};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   memset(&sc->P, 0, sizeof(Pool));
@@ -103,6 +103,7 @@ int ensure_pool(b200rt_scene* sc, size_t slots, size_t shadow_slots) {
   ShadowQueue& Q = sc->Q;
   PA(Q.o, shadow_slots); PA(Q.d, shadow_slots); PA(Q.time, shadow_slots);
   PA(Q.vis, slots * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1));
+  if (sc->S.semantics == B200RT_SEM_HW7) PA(Q.lv, slots * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1));
 #undef PA
   Q.capacity = (uint32_t)shadow_slots;
   return B200RT_OK;
@@ -858,6 +859,54 @@ int b200rt_debug_pool(b200rt_scene* sc, int field, void* out, int64_t count) {
 }
 
 void* b200rt_scene_stream(b200rt_scene* sc) { return sc ? (void*)sc->stream : nullptr; }
+// Read-bandwidth probe ("L2 bandwidth is not in MEASURED_PEAKS.json, the builder must measure it").
+// Every thread streams 16-byte loads over `bytes` of device memory `iters` times; a working set below the
+// 126 MB L2 measures L2, one far above it HBM.  The sum is written so the loads cannot be dropped.
+__global__ void __launch_bounds__(256) k_read_probe(const uint4* __restrict__ src, size_t n16, int iters,
+                                                    unsigned* sink) {
+  unsigned acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; it++)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+      uint4 v;
+      asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "l"(src + i));
+      acc += v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0x9e3779b9u) *sink = acc;
+}
+
+int b200rt_measure_read_bandwidth(int device, uint64_t bytes, int iters, double* gbs_out) {
+  if (!gbs_out || bytes < 4096 || iters < 1) {
+    b200rt_internal_set_error("measure_read_bandwidth: bad argument");
+    return B200RT_E_INVALID;
+  }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  uint4* buf = nullptr;
+  unsigned* sink = nullptr;
+  const size_t n16 = bytes / 16;
+  CK(cudaMalloc(&buf, n16 * 16));
+  CK(cudaMalloc(&sink, 4));
+  CK(cudaMemset(buf, 1, n16 * 16));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int grid = prop.multiProcessorCount * 8;
+  k_read_probe<<<grid, 256>>>(buf, n16, 2, sink);  // warm: brings a sub-L2 working set into L2
+  CK(cudaEventRecord(e0));
+  k_read_probe<<<grid, 256>>>(buf, n16, iters, sink);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf); cudaFree(sink);
+  *gbs_out = (double)n16 * 16.0 * iters / (ms * 1e-3) / 1e9;
+  return B200RT_OK;
+}
+
 uint64_t b200rt_scene_bytes(b200rt_scene* sc) { return sc ? (uint64_t)sc->scene_bytes : 0; }
 
 int b200rt_render_device(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, float** d_rgbw_out,

@@ -25,15 +25,45 @@ __device__ __forceinline__ v3 operator-(v3 a) { return mk3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ v3 operator*(v3 a, v3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ v3 operator*(v3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ v3 operator*(float s, v3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ v3 operator/(v3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+// Vector3::operator/(float): three IEEE divisions.  The shading kernels divide in ~100 places; inlined, those
+// divisions alone were 24 KB of k_shade7_b (profiles/r01f: the shade kernels stall on instruction fetch), so they share
+// one out-of-line copy.  The triangle test keeps the inline form (div3_inl).
+__device__ __forceinline__ v3 div3_inl(v3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+__device__ __noinline__ v3 div3_call(v3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ v3 operator/(v3 a, float s) { return div3_call(a, s); }
 // Vector3::dot — (x*x') + (y*y') + (z*z') left to right (HW3/include/Vector3.h:107-109)
 __device__ __forceinline__ float dot(v3 a, v3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
 __device__ __forceinline__ v3 cross(v3 a, v3 b) {
   return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 __device__ __forceinline__ float length(v3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
-__device__ __forceinline__ v3 normalize(v3 a) { return a / length(a); }
+__device__ __noinline__ v3 normalize(v3 a) { return div3_inl(a, length(a)); }
 __device__ __forceinline__ bool is_zero(v3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
+
+// pow(x, k) for the small integer exponents the reference spells pow(x, 2.0) .. pow(x, 5.0): products in double.
+// glibc's pow is within 0.52 ulp of the exact power; these products (x is a float widened to double, so x*x is exact
+// and x^3, x^4 are correctly rounded) are within 1.5 ulp of it, and every caller rounds the expression to float, so a
+// result differs from the reference's in about one call in 2^27 — the same class as CUDA's pow against glibc's, at a
+// hundredth of the instructions (the double pow was 42 % of k_shade7_a's issued instructions, profiles/r01f).
+__device__ __forceinline__ double pow2d(double x) { return x * x; }
+__device__ __forceinline__ double pow3d(double x) { return (x * x) * x; }
+__device__ __forceinline__ double pow4d(double x) { const double x2 = x * x; return x2 * x2; }
+__device__ __forceinline__ double pow5d(double x) { const double x2 = x * x; return (x2 * x2) * x; }
+// pow(x, y), x >= 0 (clamped cosines), y a material exponent: whole exponents up to 4096 by square-and-multiply
+// (<= 24 roundings of 2^-53: the float result differs from the reference's in about one call in 10^7 at worst), the rest through
+// the double pow.
+__device__ __noinline__ double pow_ref7(double x, double y) {
+  const int n = (int)y;
+  if ((double)n == y && n >= 0 && n <= 4096) {
+    double r = 1.0, b = x;
+    for (int k = n; k > 0; k >>= 1) {
+      if (k & 1) r *= b;
+      b *= b;
+    }
+    return r;
+  }
+  return pow(x, y);
+}
 
 // ---- counter-based RNG (specification shared with oracle/oracle.c) ----------
 __host__ __device__ __forceinline__ uint32_t rng_mix(uint32_t a, uint32_t b) {
@@ -120,6 +150,7 @@ struct ShadowQueue {
   float4* d;         // d.xyz, as_float(result slot)
   float* time;
   uint8_t* vis;      // per (vertex slot * n_lights + light): 1 = lit, 0 = occluded / inactive
+  float4* lv;        // HW7, same index: {vector to the light sample, pdf} drawn by shade_a, reused by shade_b
 };
 
 struct Counters {

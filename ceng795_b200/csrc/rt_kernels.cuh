@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade_b(DScene S, Pool P, ShadowQu
             }
             if (has_s) {
               const float sc = fmaxf(0.0f, dot(n, normalize(w0 + wi)));
-              color = color + ((((ks * inten) * icos) * (float)pow((double)sc, (double)m.phong_exponent)) / d2);
+              color = color + ((((ks * inten) * icos) * (float)pow_ref7((double)sc, (double)m.phong_exponent)) / d2);
             }
           } else {
             if (hw1 || has_d) {
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade_b(DScene S, Pool P, ShadowQu
             }
             if (hw1 || has_s) {
               const float sc = fmaxf(0.0f, dot(n, normalize(w0 + wi)));
-              color = color + (((ks * inten) * (float)pow((double)sc, (double)m.phong_exponent)) / d2);
+              color = color + (((ks * inten) * (float)pow_ref7((double)sc, (double)m.phong_exponent)) / d2);
             }
           }
         }
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade_b(DScene S, Pool P, ShadowQu
           fres = -1.0f;  // marks total internal reflection for combine
         } else {
           const float r0 = ((ni - 1) * (ni - 1)) / ((ni + 1) * (ni + 1));
-          fres = (float)((double)r0 + (double)(1 - r0) * pow((double)(1.0f - cos_theta), 5.0));
+          fres = (float)((double)r0 + (double)(1 - r0) * pow5d((double)(1.0f - cos_theta)));
           med_r = !entering;
           med_t = entering;
           want_t = true;

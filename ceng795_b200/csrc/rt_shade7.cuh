@@ -80,7 +80,7 @@ __device__ __forceinline__ v3 tex_blend7(const b200rt_texture& T, v3 tc, v3 kd) 
 // Perlin_noise — HW7/src/Perlin_noise.cpp:23-62
 __device__ __forceinline__ float perlin_weight7(float x) {
   const double a = fabs((double)x);
-  return (float)(-6 * pow(a, 5.0) + 15 * pow(a, 4.0) + -10 * pow(a, 3.0) + 1);
+  return (float)(-6 * pow5d(a) + 15 * pow4d(a) + -10 * pow3d(a) + 1);
 }
 __device__ __noinline__ float perlin_value7(const b200rt_texture& T, v3 pos) {
   const float G[16][3] = {{1, 1, 0}, {-1, 1, 0}, {1, -1, 0}, {-1, -1, 0}, {1, 0, 1}, {-1, 0, 1}, {1, 0, -1}, {-1, 0, -1},
@@ -320,8 +320,8 @@ __device__ __noinline__ v3 brdf_eval7(const b200rt_brdf& B, v3 normal, v3 kd, v3
       float g = fminf(2 * ca * cto / cb, 2 * ca * cti / cb);
       g = fminf(1.0f, g);
       const float ri = B.refractive_index;
-      const float r0 = (float)(pow((double)(ri - 1.0f), 2.0) / pow((double)(ri + 1.0f), 2.0));
-      const float f_beta = (float)((double)r0 + (double)(1 - r0) * pow((double)(1 - cb), 5.0));
+      const float r0 = (float)(pow2d((double)(ri - 1.0f)) / pow2d((double)(ri + 1.0f)));
+      const float f_beta = (float)((double)r0 + (double)(1 - r0) * pow5d((double)(1 - cb)));
       const v3 k_d = kd / (float)RT_PI;
       const v3 k_s = (((ks * d_alpha) * f_beta) * g) / (4 * cti * cto);
       return k_d + k_s;
@@ -330,7 +330,7 @@ __device__ __noinline__ v3 brdf_eval7(const b200rt_brdf& B, v3 normal, v3 kd, v3
 }
 
 // w*cos(theta) + v*sin(theta)*cos(phi) + u*sin(theta)*sin(phi), normalised (trace_path, env light, sphere light)
-__device__ __forceinline__ v3 onb_dir7(v3 w, float theta, float phi) {
+__device__ __noinline__ v3 onb_dir7(v3 w, float theta, float phi) {
   const v3 u = normalize((w.x != 0.0f || w.y != 0.0f) ? mk3(-w.y, w.x, 0.0f) : mk3(0.0f, 1.0f, 0.0f));
   const v3 v = cross(w, u);
   return normalize(((w * cosf(theta)) + ((v * sinf(theta)) * cosf(phi))) + ((u * sinf(theta)) * sinf(phi)));
@@ -425,7 +425,7 @@ __device__ __noinline__ v3 light_radiance7(const DScene& S, int li, v3 to_light,
       if (ct > cfall) return ld3(L.intensity) / (x * x + y * y + z * z);
       if (ct < ccov) return mk3(0, 0, 0);
       const float c = (ct - ccov) / (cfall - ccov);
-      return (ld3(L.intensity) * (float)pow((double)c, 4.0)) / (x * x + y * y + z * z);
+      return (ld3(L.intensity) * (float)pow4d((double)c)) / (x * x + y * y + z * z);
     }
     case B200RT_LIGHT_DIRECTIONAL: return ld3(L.intensity);
     case B200RT_LIGHT_ENV: {
@@ -493,13 +493,14 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_a(DScene S, Pool P, ShadowQ
       bool want = false;
       v3 wi = mk3(0, 0, 0);
       float ldist = 0.f;
+      const uint32_t vslot = slot * (uint32_t)S.n_lights + (uint32_t)li;
       if (lights_on) {
         float prob;
         const v3 lvec = light_dir7(S, li, p, n, key, &ldist, &prob);
         wi = normalize(lvec);
         want = dot(n, wi) >= 0.0f;  // HW7/src/Scene.cpp:281
+        if (want) Q.lv[vslot] = make_float4(lvec.x, lvec.y, lvec.z, prob);  // shade_b reuses the sample
       }
-      const uint32_t vslot = slot * (uint32_t)S.n_lights + (uint32_t)li;
       if (act) Q.vis[vslot] = 0;
       const uint32_t qi = warp_append(&C->shadow_count, want);
       if (want) {
@@ -654,13 +655,13 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade4_b(DScene S, Pool P, ShadowQ
               if (has_d) color = color + ((((kd * inten) * icos) * dot(n, wi)) / d2);
               if (has_s) {
                 const float sc = fmaxf(0.0f, dot(n, normalize(w0 + wi)));
-                color = color + ((((ks * inten) * icos) * (float)pow((double)sc, (double)m.phong_exponent)) / d2);
+                color = color + ((((ks * inten) * icos) * (float)pow_ref7((double)sc, (double)m.phong_exponent)) / d2);
               }
             } else {
               if (has_d) color = color + (((kd * inten) * dot(n, wi)) / d2);
               if (has_s) {
                 const float sc = fmaxf(0.0f, dot(n, normalize(w0 + wi)));
-                color = color + (((ks * inten) * (float)pow((double)sc, (double)m.phong_exponent)) / d2);
+                color = color + (((ks * inten) * (float)pow_ref7((double)sc, (double)m.phong_exponent)) / d2);
               }
             }
           }
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade4_b(DScene S, Pool P, ShadowQ
             fres = -1.0f;
           } else {
             const float r0 = ((ni - 1) * (ni - 1)) / ((ni + 1) * (ni + 1));
-            fres = (float)((double)r0 + (double)(1 - r0) * pow((double)(1.0f - cos_theta), 5.0));
+            fres = (float)((double)r0 + (double)(1 - r0) * pow5d((double)(1.0f - cos_theta)));
             med_r = !entering;
             med_t = entering;
             want_t = true;
@@ -822,9 +823,11 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQ
         if (!in_medium) {
           // calculate_diffuse_and_specular_radiance — HW7/src/Scene.cpp:260-311
           for (int li = 0; li < S.n_lights; li++) {
-            if (!Q.vis[slot * (uint32_t)S.n_lights + (uint32_t)li]) continue;
-            float ldist, prob;
-            const v3 lvec = light_dir7(S, li, p, n, key, &ldist, &prob);
+            const uint32_t vslot = slot * (uint32_t)S.n_lights + (uint32_t)li;
+            if (!Q.vis[vslot]) continue;
+            const float4 ls = Q.lv[vslot];  // light_dir7's sample, drawn once in shade_a
+            const v3 lvec = mk3(ls.x, ls.y, ls.z);
+            const float prob = ls.w;
             const v3 w_i = normalize(lvec);
             const v3 Li = light_radiance7(S, li, lvec, prob);
             const float cti = fmaxf(0.0f, dot(n, w_i));
@@ -833,7 +836,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQ
             } else {
               direct = direct + ((kd * Li) * cti);
               const float sct = fmaxf(0.0f, dot(n, normalize(w_o + w_i)));
-              direct = direct + ((ks * Li) * (float)pow((double)sct, (double)m.phong_exponent));
+              direct = direct + ((ks * Li) * (float)pow_ref7((double)sct, (double)m.phong_exponent));
             }
           }
         }
@@ -861,7 +864,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQ
               wdiff = (brdf_eval7(S.brdfs[m.brdf], n, kd, ks, w_i, w_o) * cti) / prob;
             } else {
               const float sct = fmaxf(0.0f, dot(n, normalize(w_o + w_i)));
-              wdiff = ((kd * cti) / prob) + ((ks * (float)pow((double)sct, (double)m.phong_exponent)) / prob);
+              wdiff = ((kd * cti) / prob) + ((ks * (float)pow_ref7((double)sct, (double)m.phong_exponent)) / prob);
             }
           }
         }
@@ -912,7 +915,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQ
             fres = -1.0f;
           } else {
             const float r0 = ((ni - 1) * (ni - 1)) / ((ni + 1) * (ni + 1));
-            fres = (float)((double)r0 + (double)(1 - r0) * pow((double)(1.0f - cos_theta), 5.0));
+            fres = (float)((double)r0 + (double)(1 - r0) * pow5d((double)(1.0f - cos_theta)));
             med_r = !entering;
             med_t = entering;
             want_t = true;

@@ -102,7 +102,7 @@ __device__ __forceinline__ bool tri_test(v3 v0, v3 a1, v3 a2, v3 o, v3 d, float 
                                          float* gamma_out) {
   const float det_a = det3(a1, a2, d);
   if (det_a == 0.0f) return false;
-  const v3 b = (v0 - o) / det_a;
+  const v3 b = div3_inl(v0 - o, det_a);
   const float beta = det3(b, a2, d);
   if (MODE == 1) { if (beta < 0.0f - eps || beta > 1.0f + eps) return false; }
   else if (MODE == 2) { if (beta < 0.0f || beta > 1.0f) return false; }

@@ -435,6 +435,10 @@ void* b200rt_scene_stream(b200rt_scene*);
 /* Bytes of scene data resident in HBM (nodes + triangles + tables). */
 uint64_t b200rt_scene_bytes(b200rt_scene*);
 
+/* Measurement aid: streaming-read bandwidth over a `bytes` working set, `iters` passes, in GB/s.
+ * 48 MB measures the L2 (the denominator for scene fetches when the tree is L2-resident), >= 1 GB measures HBM. */
+int b200rt_measure_read_bandwidth(int device, uint64_t bytes, int iters, double* gbs_out);
+
 const char* b200rt_last_error(void);
 const char* b200rt_version(void);
 
