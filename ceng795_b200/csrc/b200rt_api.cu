@@ -103,7 +103,7 @@ int ensure_pool(b200rt_scene* sc, size_t slots, size_t shadow_slots) {
   ShadowQueue& Q = sc->Q;
   PA(Q.o, shadow_slots); PA(Q.d, shadow_slots); PA(Q.time, shadow_slots);
   PA(Q.vis, slots * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1));
-  if (sc->S.semantics == B200RT_SEM_HW7) PA(Q.lv, slots * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1));
+  if (sc->S.semantics >= B200RT_SEM_HW5 && sc->S.semantics <= B200RT_SEM_HW7) PA(Q.lv, slots * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1));
 #undef PA
   Q.capacity = (uint32_t)shadow_slots;
   return B200RT_OK;
@@ -170,7 +170,7 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     tm.mark(ST_EXTEND);
     d_last = d;
     if (!with_shading) break;
-    const bool hw7 = S.semantics >= B200RT_SEM_HW7;
+    const bool hw7 = S.semantics >= B200RT_SEM_HW5;  // HW5/HW6 shade like HW7's ray-tracing mode (flags inside)
     const bool hw4 = S.semantics == B200RT_SEM_HW4;
     if (hw7) k_shade7_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     else if (hw4) k_shade4_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
@@ -198,7 +198,7 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
   }
   if (with_shading) {
     for (int d = d_last; d >= 0; d--) {
-      if (S.semantics >= B200RT_SEM_HW7) k_combine7<<<grid_s, 256, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_accum);
+      if (S.semantics >= B200RT_SEM_HW5) k_combine7<<<grid_s, 256, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_accum);
       else k_combine<<<grid_s, 256, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_accum);
       (*launches)++;
     }
@@ -646,7 +646,8 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     return B200RT_E_INVALID;
   }
   if (d->semantics != B200RT_SEM_HW1 && d->semantics != B200RT_SEM_HW2 && d->semantics != B200RT_SEM_HW3 &&
-      d->semantics != B200RT_SEM_HW4 && d->semantics != B200RT_SEM_HW7 && d->semantics != B200RT_SEM_PPM) {
+      d->semantics != B200RT_SEM_HW4 && d->semantics != B200RT_SEM_HW5 && d->semantics != B200RT_SEM_HW6 &&
+      d->semantics != B200RT_SEM_HW7 && d->semantics != B200RT_SEM_PPM) {
     b200rt_internal_set_error("b200rt_scene_create: semantics not implemented on the device yet");
     return B200RT_E_UNSUPPORTED;
   }

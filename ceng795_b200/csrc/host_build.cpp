@@ -467,12 +467,13 @@ int b200rt_builder_add_material(b200rt_builder* b, const b200rt_material* m) {
   if (!b || !m) return B200RT_E_INVALID;
   b200rt_material c = *m;
   if (b->semantics < B200RT_SEM_HW6) c.brdf = -1;
-  if (b->semantics >= B200RT_SEM_HW7 && c.degamma) {
-    // HW7/src/Scene.cpp:951-961: pow(float, 2.2f) -> powf
+  if (b->semantics >= B200RT_SEM_HW5 && c.degamma) {  // from HW5 on: HW5/src/Scene.cpp:338-348
+    // HW7/src/Scene.cpp:951-961: the unqualified pow(float, 2.2f) there is the double pow (probed with the tree's
+    // own include list), rounded to float by the assignment
     for (int i = 0; i < 3; i++) {
-      c.ambient[i] = std::pow(c.ambient[i], 2.2f);
-      c.diffuse[i] = std::pow(c.diffuse[i], 2.2f);
-      c.specular[i] = std::pow(c.specular[i], 2.2f);
+      c.ambient[i] = (float)std::pow((double)c.ambient[i], (double)2.2f);
+      c.diffuse[i] = (float)std::pow((double)c.diffuse[i], (double)2.2f);
+      c.specular[i] = (float)std::pow((double)c.specular[i], (double)2.2f);
     }
   }
   b->materials.push_back(c);

@@ -219,7 +219,10 @@ __device__ __noinline__ Surf7 surface7(const DScene& S, uint32_t top_ref, int tr
     if (s->texture != -1) {
       sf.texture = s->texture;
       const b200rt_texture& T = S.textures[s->texture];
-      const float theta = acosf(fmaxf(-1.0f, fminf(1.0f, lc.y / s->radius)));
+      // HW7/src/Sphere.cpp:107-108 clamps and calls std::acos; HW4-HW6 call the unqualified (double) acos on the raw
+      // ratio (HW4/src/Sphere.cpp:101, HW6/src/Sphere.cpp:106)
+      const float theta = (S.semantics >= B200RT_SEM_HW7) ? acosf(fmaxf(-1.0f, fminf(1.0f, lc.y / s->radius)))
+                                                          : (float)acos((double)(lc.y / s->radius));
       const float phi = (float)atan2((double)lc.z, (double)lc.x);  // unqualified atan2: the double function
       const float u = (float)((RT_PI - (double)phi) / (2 * RT_PI));
       const float v = (float)((double)theta / RT_PI);
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_a(DScene S, Pool P, ShadowQ
         float prob;
         const v3 lvec = light_dir7(S, li, p, n, key, &ldist, &prob);
         wi = normalize(lvec);
-        want = dot(n, wi) >= 0.0f;  // HW7/src/Scene.cpp:281
+        want = S.semantics < B200RT_SEM_HW7 || dot(n, wi) >= 0.0f;  // HW7/src/Scene.cpp:281; HW5/HW6 have no gate
         if (want) Q.lv[vslot] = make_float4(lvec.x, lvec.y, lvec.z, prob);  // shade_b reuses the sample
       }
       if (act) Q.vis[vslot] = 0;
@@ -819,7 +822,10 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQ
         color = kd;
       } else {
         const v3 ks = ld3(m.specular);
-        v3 direct = mk3(0, 0, 0);
+        // HW7 sums the lights on their own and adds the sum to ambient (HW7/src/Scene.cpp:260-311, 434-437); HW5/HW6
+        // add every term straight onto the colour, which starts as the ambient term (HW6/src/Scene.cpp:169-207)
+        const bool onto_colour = S.semantics < B200RT_SEM_HW7;
+        v3 direct = onto_colour ? (color + (ld3(m.ambient) * S.ambient)) : mk3(0, 0, 0);
         if (!in_medium) {
           // calculate_diffuse_and_specular_radiance — HW7/src/Scene.cpp:260-311
           for (int li = 0; li < S.n_lights; li++) {
@@ -844,8 +850,12 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQ
         if (pt) {
           if (!is_zero(direct)) { copy_light_hit = true; color = color + direct; }
         } else if (!in_medium) {
-          color = color + (ld3(m.ambient) * S.ambient);
-          color = color + direct;
+          if (onto_colour) {
+            color = direct;
+          } else {
+            color = color + (ld3(m.ambient) * S.ambient);
+            color = color + direct;
+          }
         }
         const bool budget = (int)depth < S.max_depth;
         if (pt && !in_medium && budget) {
@@ -993,6 +1003,24 @@ __global__ void k_combine7(DScene S, Pool P, const WaveInfo* waves, int d, float
       const uint32_t pix = P.pixel[slot];
       if (S.cam.samples_sqrt == 1) {
         accum[pix] = make_float4(color.x * 1.0f, color.y * 1.0f, color.z * 1.0f, 1.0f);
+      } else if (S.semantics < B200RT_SEM_HW7) {
+        // HW5/HW6: 3x3 Gaussian splat, sigma 1/2, around the absolute sample position — HW6/src/Scene.cpp:84-97
+        const int W = S.cam.width, H = S.cam.height, ns = S.cam.samples_sqrt;
+        const int i = (int)(pix % (uint32_t)W), j = (int)(pix / (uint32_t)W);
+        const uint32_t sidx = P.sample[slot], key = P.key[slot];
+        const int x = (int)(sidx / (uint32_t)ns), y = (int)(sidx % (uint32_t)ns);
+        const float sx = ((float)x + rng_u01(key, 4)) / (float)ns, sy = ((float)y + rng_u01(key, 5)) / (float)ns;
+        for (int aj = j - 1; aj < j + 2; aj++) {
+          if (aj < 0 || aj >= H) continue;
+          for (int ai = i - 1; ai < i + 2; ai++) {
+            if (ai < 0 || ai >= W) continue;
+            const float w = gaussian_filter(((float)i + sx) - ((float)ai + 0.5f), ((float)j + sy) - ((float)aj + 0.5f),
+                                            1.5f / 3.0f);
+            float* px = reinterpret_cast<float*>(accum + (size_t)aj * W + ai);
+            atomicAdd(px + 0, color.x * w); atomicAdd(px + 1, color.y * w);
+            atomicAdd(px + 2, color.z * w); atomicAdd(px + 3, w);
+          }
+        }
       } else {
         // box filter: Pixel::add_color(color, 1.0f) per sample — HW7/src/Scene.cpp:80
         float* px = reinterpret_cast<float*>(accum + pix);

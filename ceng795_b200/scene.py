@@ -204,13 +204,16 @@ def parse_xml(path_or_text: str, semantics, base_dir: str | None = None) -> Scen
                                 edge1=_floats(_child_text(l, "EdgeVector1"), 3),
                                 edge2=_floats(_child_text(l, "EdgeVector2"), 3)))
         if sem >= SEM_HW5 and sem != SEM_PPM:
-            for l in lights.findall("SpotLight"):
+            # HW5/HW6 advance these two loops with FirstChildElement instead of NextSiblingElement, so they stop
+            # after the first SpotLight / DirectionalLight (HW6/src/Scene.cpp:661,678); HW7 fixed it (:385,404)
+            first_only = sem < SEM_HW7
+            for l in lights.findall("SpotLight")[:1 if first_only else None]:
                 others.append(dict(kind=_lib.LIGHT_SPOT, position=_floats(_child_text(l, "Position"), 3),
                                    intensity=_floats(_child_text(l, "Intensity"), 3),
                                    direction=_floats(_child_text(l, "Direction"), 3),
                                    coverage=float(_floats(_child_text(l, "CoverageAngle"), 1)[0]),
                                    falloff=float(_floats(_child_text(l, "FalloffAngle"), 1)[0])))
-            for l in lights.findall("DirectionalLight"):
+            for l in lights.findall("DirectionalLight")[:1 if first_only else None]:
                 others.append(dict(kind=_lib.LIGHT_DIRECTIONAL, direction=_floats(_child_text(l, "Direction"), 3),
                                    radiance=_floats(_child_text(l, "Radiance"), 3)))
             l = lights.find("SphericalDirectionalLight")
@@ -228,7 +231,7 @@ def parse_xml(path_or_text: str, semantics, base_dir: str | None = None) -> Scen
             transparency=_floats(_child_text(m, "Transparency", "0 0 0"), 3) if sem >= SEM_HW2 else np.zeros(3, np.float32),
             refraction_index=float(_floats(_child_text(m, "RefractionIndex", "1.0"), 1)[0]) if sem >= SEM_HW2 else 1.0,
             brdf=(int(m.get("BRDF", "0")) - 1) if sem >= SEM_HW6 else -1,
-            degamma=(m.get("degamma") == "true") and sem >= SEM_HW7))
+            degamma=(m.get("degamma") == "true") and sem >= SEM_HW5))
     scal, tran, rot = [], [], []
     tel = root.find("Transformations")
     if tel is not None and sem >= SEM_HW3:

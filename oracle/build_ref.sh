@@ -3,7 +3,9 @@
 # lie (default /root/reference) into oracle/_ref/ (git-ignored, travels to the
 # GPU box).  No reference source is copied or edited: the only fixes are
 # forced standard includes and a case shim for HW1.
-# Usage: oracle/build_ref.sh [tree ...]   (default: hw1 hw2 hw3 hw7 ppm)
+# HW5/HW6: their main.cpp needs OpenCV (absent), so every OTHER translation unit of the tree is linked with
+# oracle/ref_driver_hdr.cpp, which calls the same Scene seam and dumps the float pixels.
+# Usage: oracle/build_ref.sh [tree ...]   (default: hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${CENG795_REFERENCE:-/root/reference}"
@@ -12,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw7 ppm)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -38,13 +40,31 @@ build_tree() { # name dir extra
   $CXX -pthread "${objs[@]}" -o "$OUT/${name}_raytracer"
   echo "built $OUT/${name}_raytracer"
 }
+build_tree_driver() { # name dir : the tree's objects except main.cpp + our float-dump driver
+  local name=$1 dir=$2; shift 2
+  local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
+  local objs=()
+  for f in "$dir"/src/*.cpp "$HERE/ref_driver_hdr.cpp"; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    local o="$objdir/$(basename "$f" .cpp).o"; objs+=("$o")
+    if [ ! -f "$o" ] || [ "$f" -nt "$o" ]; then $CXX $FLAGS "$@" -I"$dir/include" -c "$f" -o "$o" & fi
+  done
+  wait
+  $CXX -pthread "${objs[@]}" -o "$OUT/${name}_raytracer"
+  echo "built $OUT/${name}_raytracer"
+}
 for t in "${TREES[@]}"; do
   case "$t" in
     hw1) build_flat hw1 "$REF/HW1" -I"$HERE/shim" ;;
     hw2) build_flat hw2 "$REF/HW2" ;;
     hw3) build_tree hw3 "$REF/HW3" ;;
     hw4) build_tree hw4 "$REF/HW4" ;;
+    hw5) build_tree_driver hw5 "$REF/HW5" ;;
+    hw6) build_tree_driver hw6 "$REF/HW6" ;;
     hw7) build_tree hw7 "$REF/HW7" ;;
+    hw3f) build_tree_driver hw3f "$REF/HW3" ;;   # float-dump twins of trees whose own main writes 8-bit PNGs:
+    hw4f) build_tree_driver hw4f "$REF/HW4" ;;   # they pin the oracle at float level (tests/test_oracle_golden.py)
+    hw7f) build_tree_driver hw7f "$REF/HW7" ;;
     ppm) build_tree ppm "$REF/PPM" -DNDEBUG ;;
     *) echo "unknown tree $t" >&2; exit 2 ;;
   esac

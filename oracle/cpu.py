@@ -16,7 +16,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 _TREE_BIN = {"hw1": "hw1_raytracer", "hw2": "hw2_raytracer", "hw3": "hw3_raytracer",
-             "hw4": "hw4_raytracer", "hw7": "hw7_raytracer", "ppm": "ppm_raytracer"}
+             "hw4": "hw4_raytracer", "hw5": "hw5_raytracer", "hw6": "hw6_raytracer", "hw7": "hw7_raytracer",
+             "ppm": "ppm_raytracer",
+             # float-dump twins (oracle/ref_driver_hdr.cpp instead of the tree's main.cpp)
+             "hw3f": "hw3f_raytracer", "hw4f": "hw4f_raytracer", "hw7f": "hw7f_raytracer"}
 
 
 class Counters(C.Structure):
@@ -151,7 +154,7 @@ def run_reference(tree: str, xml_text: str, workdir: str | None = None, timeout:
     out = r.stdout
     if r.returncode != 0:
         raise RuntimeError(f"reference {tree} failed rc={r.returncode}: {out[-500:]} {r.stderr[-500:]}")
-    res = {"stdout": out, "images": {}, "ms": {}, "threads": 1}
+    res = {"stdout": out, "images": {}, "hdr": {}, "ms": {}, "threads": 1}
     m = re.search(r"Starting rendering on #(\d+) thread", out)
     if m:
         res["threads"] = int(m.group(1))
@@ -162,6 +165,10 @@ def run_reference(tree: str, xml_text: str, workdir: str | None = None, timeout:
             p = p + ".png"   # HW7/PPM print the name without its extension (HW7/src/main.cpp:56-57,97)
         if os.path.exists(p) and p.lower().endswith(".png"):
             res["images"][name] = read_png(p)
+        if os.path.exists(p) and p.endswith(".f32"):
+            # HW5/HW6 through oracle/ref_driver_hdr.cpp: int32 W, H, then W*H*3 float32 of Pixel::get_color()
+            wh = np.fromfile(p, np.int32, 2)
+            res.setdefault("hdr", {})[name[:-4]] = np.fromfile(p, np.float32, offset=8).reshape(int(wh[1]), int(wh[0]), 3)
     # PPM prints per-phase timers and "Saved png file. [ name ]" instead (PPM/src/main.cpp:56-102, write_png)
     for label, key in (("Eye pass", "eye"), ("Building hash grid", "grid"), ("Tracing photon rays", "photon"),
                        ("Density estimation", "density")):

@@ -76,6 +76,10 @@ typedef struct {
   OracleCounters* c;
 } Ctx;
 static inline int sem_hw7(const B200SceneDesc* d) { return d->semantics >= B200RT_SEM_HW7; }
+/* HW5 and HW6 shade like HW7's ray-tracing mode (unified light list, clamped cosine, BRDF objects from HW6 on:
+ * HW6/src/Scene.cpp:119-301) but without back-face culling, without the n.w_i >= 0 gate in front of the shadow ray,
+ * and with the sigma-1/2 Gaussian splat on the multi-sample path (HW6/src/Scene.cpp:18-101). */
+static inline int sem_hw5(const B200SceneDesc* d) { return d->semantics >= B200RT_SEM_HW5; }
 /* HW4 already has the textured Mesh_triangle / Sphere of HW7 (band acceptance, per-call sphere transform), but no culling */
 static inline int sem_hw4(const B200SceneDesc* d) { return d->semantics >= B200RT_SEM_HW4; }
 
@@ -805,7 +809,8 @@ static void tex_surface_tri(const B200SceneDesc* d, int tri, float beta, float g
 /* texture part of Sphere::intersect + get_uv — HW7/src/Sphere.cpp:70-112 */
 static void tex_surface_sphere(const B200SceneDesc* d, const b200rt_sphere* s, v3 lc, v3 local_p, Hit* hit) {
   const b200rt_texture* T = d->textures + s->texture;
-  const float theta = acosf(fmaxf(-1.0f, fminf(1.0f, lc.y / s->radius)));
+  /* HW7/src/Sphere.cpp:107-108 clamps; HW4-HW6 call the unqualified (double) acos on the raw ratio (HW4/src/Sphere.cpp:101, HW6/src/Sphere.cpp:106) */
+  const float theta = sem_hw7(d) ? acosf(fmaxf(-1.0f, fminf(1.0f, lc.y / s->radius))) : (float)acos((double)(lc.y / s->radius));
   const float phi = (float)atan2((double)lc.z, (double)lc.x); /* unqualified atan2: the double function */
   const float u = (float)((M_PI - (double)phi) / (2 * M_PI));
   const float v = (float)((double)theta / M_PI);
@@ -1019,9 +1024,9 @@ static int diffuse_constant7(const B200SceneDesc* d, const Hit* hit, v3* out) {
   return 0;
 }
 /* Scene::calculate_diffuse_and_specular_radiance — HW7/src/Scene.cpp:260-311 */
-static v3 direct7(const Ctx* cx, const Ray* ray, const Hit* hit, v3 kd, uint32_t key) {
+static v3 direct7(const Ctx* cx, const Ray* ray, const Hit* hit, v3 kd, uint32_t key, v3 start) {
   const B200SceneDesc* d = cx->d;
-  v3 radiance = V(0, 0, 0);
+  v3 radiance = start;   /* HW7 sums the lights on their own (0); HW5/HW6 add them straight onto the colour */
   const v3 p = add(ray->o, muls(ray->d, hit->t));
   const b200rt_material* m = d->materials + hit->material;
   const v3 w_o = normalize(sub(ray->o, p));
@@ -1031,7 +1036,7 @@ static v3 direct7(const Ctx* cx, const Ray* ray, const Hit* hit, v3 kd, uint32_t
     float ldist, prob;
     const v3 lvec = light_dir(cx, li, p, n, key, &ldist, &prob);
     const v3 w_i = normalize(lvec);
-    if (dot(n, w_i) >= 0.0f) {
+    if (!sem_hw7(d) || dot(n, w_i) >= 0.0f) {   /* the gate is HW7's (HW7/src/Scene.cpp:281); HW6 has none */
       Ray sr; memset(&sr, 0, sizeof(sr));
       sr.o = add(p, muls(w_i, d->shadow_eps)); sr.d = w_i; sr.time = ray->time; sr.is_shadow = 1;
       cx->c->rays_shadow++;
@@ -1130,7 +1135,8 @@ static v3 trace_ray7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, u
   if (diffuse_constant7(d, hit, &kd)) return kd;
   if (!ray->in_medium) {
     radiance = add(radiance, mulv(ld(m->ambient), ld(d->ambient)));
-    radiance = add(radiance, direct7(cx, ray, hit, kd, key));
+    if (sem_hw7(d)) radiance = add(radiance, direct7(cx, ray, hit, kd, key, V(0, 0, 0)));
+    else radiance = direct7(cx, ray, hit, kd, key, radiance);   /* color += ... per light, HW6/src/Scene.cpp:196-207 */
   }
   if (!is_zero(ld(m->mirror)) && level < d->max_depth)
     radiance = add(radiance, mulv(ld(m->mirror), reflect7(cx, ray, hit, level, key)));
@@ -1147,7 +1153,7 @@ static v3 trace_path7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, 
   Ray ray_copy = *ray;
   v3 kd, direct = V(0, 0, 0);
   diffuse_constant7(d, hit, &kd);
-  if (!ray->in_medium) direct = direct7(cx, ray, hit, kd, key);
+  if (!ray->in_medium) direct = direct7(cx, ray, hit, kd, key, V(0, 0, 0));
   if (!is_zero(direct)) { ray_copy.light_hit = 1; radiance = add(radiance, direct); }
   const b200rt_material* m = d->materials + hit->material;
   const b200rt_brdf* B = (m->brdf != -1) ? d->brdfs + m->brdf : NULL;
@@ -1251,7 +1257,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
   {
     OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
     Ctx cx = {d, &cnt};
-    const int hw7 = sem_hw7(d);
+    const int hw7 = sem_hw7(d), hw5 = sem_hw5(d);
 #pragma omp for schedule(dynamic, 4)
     for (int j = row_begin; j < row_end; j++) {
       for (int i = 0; i < W; i++) {
@@ -1291,7 +1297,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
           if (rgbw && d->semantics == B200RT_SEM_HW4) continue;   /* splatted below, sequentially */
           if (rgbw) {
             const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), 0u);
-            const v3 col = hw7 ? send_ray7(&cx, &r, 0, key, 0) : trace_ray(&cx, &r, d->max_depth, key, 0);
+            const v3 col = hw5 ? send_ray7(&cx, &r, 0, key, 0) : trace_ray(&cx, &r, d->max_depth, key, 0);
             rgbw[4 * pix] = col.x * 1.0f; rgbw[4 * pix + 1] = col.y * 1.0f;
             rgbw[4 * pix + 2] = col.z * 1.0f; rgbw[4 * pix + 3] = 1.0f;
           }
@@ -1337,7 +1343,8 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
      * that the accumulation order is defined (the reference's is thread-racy). */
     OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
     Ctx cx = {d, &cnt};
-    const int hw4ms = d->semantics == B200RT_SEM_HW4;   /* sigma 1/2, absolute sample positions */
+    const int hw4ms = d->semantics >= B200RT_SEM_HW4;   /* HW4-HW6: sigma 1/2, absolute sample positions */
+    const int hw5 = sem_hw5(d);
     for (int j = row_begin; j < row_end; j++)
       for (int i = 0; i < W; i++) {
         const int pix = j * W + i;
@@ -1355,7 +1362,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
               const float dx = rng_u01(key, 7) * 2.0f - 1.0f, dy = rng_u01(key, 8) * 2.0f - 1.0f;
               r = camera_ray(d, c, px_, py_, 1, dx, dy, time);
             }
-            const v3 col = trace_ray(&cx, &r, d->max_depth, key, 0);
+            const v3 col = hw5 ? send_ray7(&cx, &r, 0, key, 0) : trace_ray(&cx, &r, d->max_depth, key, 0);
             for (int aj = j - 1; aj < j + 2; aj++) {
               if (aj < 0 || aj >= H) continue;
               for (int ai = i - 1; ai < i + 2; ai++) {

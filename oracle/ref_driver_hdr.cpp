@@ -1,0 +1,54 @@
+// TEST INFRASTRUCTURE ONLY — a stand-in for HW5/src/main.cpp and HW6/src/main.cpp, which need OpenCV (absent here)
+// for nothing but the EXR write ("link everything except main.cpp with the new repo's driver").
+// It is compiled by oracle/build_ref.sh against the UNMODIFIED objects of the tree and only touches the public
+// seam main() itself uses: Scene::Scene(xml), Scene::cameras, Scene::render_image(camera, Pixel*, first_row, stride)
+// from hardware_concurrency() threads, Pixel::get_color().  Output: <image name>.f32 = int32 W, int32 H, then
+// W*H*3 float32 of the un-tonemapped pixel colours, and the reference's own two log lines so that oracle/cpu.py
+// reads the thread count and the render time the way it does for the other trees.
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <iostream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "Pixel.h"
+#include "Scene.h"
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    std::fprintf(stderr, "usage: %s scene.xml\n", argv[0]);
+    return 1;
+  }
+  Scene scene(argv[1]);
+  unsigned workers = std::thread::hardware_concurrency();
+  for (size_t cam = 0; cam < scene.cameras.size(); cam++) {
+    const Image_plane& plane = scene.cameras[cam].get_image_plane();
+    const int W = plane.width, H = plane.height;
+    std::vector<Pixel> film((size_t)W * H);
+    if (workers == 0 || (unsigned)H < workers) workers = 1;
+    std::cout << "Starting rendering on #" << workers << " thread(s)" << std::endl;
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < workers; w++)
+      pool.emplace_back([&, w] { scene.render_image((int)cam, film.data(), (int)w, (int)workers); });
+    for (std::thread& t : pool) t.join();
+    const auto t1 = std::chrono::steady_clock::now();
+    const long long us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    const std::string name = scene.cameras[cam].get_filename() + ".f32";
+    std::FILE* f = std::fopen(name.c_str(), "wb");
+    if (!f) return 2;
+    const int32_t hdr[2] = {W, H};
+    std::fwrite(hdr, sizeof(hdr), 1, f);
+    for (size_t p = 0; p < film.size(); p++) {
+      const Vector3 c = film[p].get_color();
+      const float rgb[3] = {c.x, c.y, c.z};
+      std::fwrite(rgb, sizeof(rgb), 1, f);
+    }
+    std::fclose(f);
+    std::cout << name << "(" << W << "x" << H << ") is saved in: " << us / 1000 << " milliseconds " << us % 1000
+              << " microseconds" << std::endl;
+  }
+  return 0;
+}

@@ -35,6 +35,18 @@ CASES = {
 }
 
 
+#: float-level pins: name -> (semantics, reference binary, generator, kwargs).  The binary is the tree's own objects
+#: linked with oracle/ref_driver_hdr.cpp (HW5/HW6: their main.cpp needs OpenCV; hw7f: the same twin for HW7), which
+#: dumps Pixel::get_color() as float32 — so these fixtures pin the oracle to the last bit, not to 8 bits.
+FLOAT_CASES = {
+    # HW6: HW7's ray-tracing mode minus culling / the n.w_i gate, lights added straight onto the colour; 5 BRDFs
+    "hw6_brdf_160": ("hw6", "hw6", "hw7_scene", dict(width=160, height=120, light_scale=3.0)),
+    # HW5: the same tree without BRDF objects (the BRDF attributes of the scene are ignored by its loader)
+    "hw5_lights_128": ("hw5", "hw5", "hw7_scene", dict(width=128, height=96, depth=2, n=9, seed=802)),
+    "hw7_whitted_f32": ("hw7", "hw7f", "hw7_scene", dict(width=160, height=120, light_scale=3.0)),
+}
+
+
 ASSETS = os.path.join(HERE, "assets")   # texture images the HW7 scenes refer to (committed)
 
 
@@ -46,7 +58,23 @@ def scene_xml(name):
     return tree, getattr(scenes, gen)(**kw)
 
 
+def float_scene_xml(name):
+    sem, binary, gen, kw = FLOAT_CASES[name]
+    os.makedirs(ASSETS, exist_ok=True)
+    return sem, binary, getattr(scenes, gen)(ASSETS, **kw)
+
+
 if __name__ == "__main__":
+    import numpy as np
+    for name in FLOAT_CASES:
+        sem, binary, xml = float_scene_xml(name)
+        res = cpu.run_reference(binary, xml, workdir=ASSETS)
+        hdr = list(res["hdr"].values())[0]
+        np.save(os.path.join(HERE, name + ".npy"), hdr.astype(np.float32))
+        print(name, hdr.shape, float(hdr.mean()))
+    for f in os.listdir(ASSETS):
+        if f.endswith(".f32") or f == "scene.xml":
+            os.remove(os.path.join(ASSETS, f))
     meta = {}
     for name in CASES:
         tree, xml = scene_xml(name)

@@ -8,7 +8,7 @@ import pytest
 
 from ceng795_b200 import image, scene
 from oracle import cpu
-from tests.golden.make_golden import ASSETS, CASES, scene_xml
+from tests.golden.make_golden import ASSETS, CASES, FLOAT_CASES, float_scene_xml, scene_xml
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -28,6 +28,41 @@ def test_oracle_matches_golden_png(name):
     else:
         assert cmp["exact"] == 1.0, cmp  # bit-exact: same compiler, same IEEE arithmetic
     assert cnt.rays_primary == got.shape[0] * got.shape[1]
+
+
+@pytest.mark.parametrize("name", sorted(FLOAT_CASES))
+def test_oracle_matches_float_golden(name):
+    """HW5 / HW6 (and HW7 again) against float32 dumps of Pixel::get_color() from the tree's own objects
+    (oracle/ref_driver_hdr.cpp): the restatement reproduces every accumulator to the last bit."""
+    sem, _, xml = float_scene_xml(name)
+    spec = scene.parse_xml(xml, sem, base_dir=ASSETS)
+    rgbw, _, _, cnt = cpu.render(scene.HostScene(spec), 0)
+    got = rgbw[..., :3] / rgbw[..., 3:4]
+    want = np.load(os.path.join(GOLDEN, name + ".npy"))
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
+@pytest.mark.parametrize("tree", ["hw5", "hw6"])
+def test_oracle_hw56_multisample_statistics_vs_reference(tmp_path, tree):
+    """HW5 / HW6 multi-sample path (area light, glossy mirror, jitter, sigma-1/2 Gaussian splat): the reference
+    seeds from random_device, so equal mean and an RMSE within the oracle's own seed-to-seed noise."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    import re
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=40, height=30, spp=100, depth=2, stochastic_lights=True, light_scale=0.25)
+    xml = re.sub(r"    <Light(Mesh|Sphere).*?</Light(Mesh|Sphere)>\n", "", xml, flags=re.S)   # HW7-only objects
+    ref = list(cpu.run_reference(tree, xml, workdir=str(tmp_path))["hdr"].values())[0].astype(np.float64)
+    hs = scene.HostScene(scene.parse_xml(xml, tree, base_dir=str(tmp_path)))
+    imgs = []
+    for seed in (7, 8):
+        rgbw, _, _, _ = cpu.render(hs, 0, seed=seed)
+        imgs.append((rgbw[..., :3] / rgbw[..., 3:4]).astype(np.float64))
+    assert abs(imgs[0].mean() - ref.mean()) <= 0.02 * ref.mean(), (imgs[0].mean(), ref.mean())
+    noise = np.sqrt(((imgs[0] - imgs[1]) ** 2).mean())
+    rmse = np.sqrt(((imgs[0] - ref) ** 2).mean())
+    assert rmse <= 1.35 * noise + 0.5, (rmse, noise)
 
 
 @pytest.mark.parametrize("tree,gen_kw", [("hw1", dict(width=80, height=60, seed=11)),
