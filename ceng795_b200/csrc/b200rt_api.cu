@@ -8,6 +8,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <functional>
+
 #include "fast_bvh.h"
 #include "ppm_kernels.cuh"
 #include "tonemap_kernels.cuh"
@@ -668,6 +670,11 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   sc->sm_count = prop.multiProcessorCount;
   DScene& S = sc->S;
   S.semantics = d->semantics; S.max_depth = d->max_depth;
+  S.refill_closest = RT_REFILL_MIN_IDLE; S.refill_any = RT_REFILL_MIN_IDLE;
+  S.node_vote = RT_NODE_VOTE;
+  if (const char* e = getenv("B200RT_NODE_VOTE")) S.node_vote = std::max(1, std::min(32, atoi(e)));
+  if (const char* e = getenv("B200RT_REFILL_CLOSEST")) S.refill_closest = std::max(1, std::min(32, atoi(e)));  // tuning knobs
+  if (const char* e = getenv("B200RT_REFILL_ANY")) S.refill_any = std::max(1, std::min(32, atoi(e)));
   S.background = ld3(d->background); S.ambient = ld3(d->ambient);
   S.shadow_eps = d->shadow_eps; S.isect_eps = d->isect_eps;
   S.root = d->root;
@@ -685,6 +692,52 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     bytes += (size_t)(n) * sizeof(T);                                      \
   } while (0)
   UP(S.nodes, d->nodes, d->n_nodes, b200rt_bvh_node);
+  {
+    // Flat list of the top-level objects, each with the innermost box of the reference's gate chain above it: an
+    // instance's own world box (Mesh_instance::intersect tests it itself), for a primitive the box of the BVH node
+    // that holds it.  Every outer box of the chain contains that one and the slab test is monotone in the box
+    // (DESIGN.md 4b), so "innermost gate passes" == "the reference reaches the object".  A short list tested by all
+    // lanes in lock step replaces the divergent walk of the top-level tree (25 % of the traversal kernels'
+    // instructions on cfg4, profiles/r01g).
+    std::vector<float> flat;
+    bool ok = d->semantics != B200RT_SEM_HW1;
+    std::function<void(uint32_t, const float*, bool)> walk = [&](uint32_t ref, const float* box, bool own) {
+      const uint32_t kind = B200RT_REF_KIND(ref);
+      if (kind == B200RT_KIND_NONE || !ok) return;
+      if (kind == B200RT_KIND_INNER) {
+        const uint32_t idx = B200RT_REF_INDEX(ref);
+        if ((int)idx >= d->n_nodes) { ok = false; return; }
+        const b200rt_bvh_node& n = d->nodes[idx];
+        const uint32_t ch[2] = {n.left, n.right};
+        const float* cb[2] = {n.lmin, n.rmin};   // lmin,lmax / rmin,rmax are contiguous: 6 floats each
+        for (int c = 0; c < 2; c++) {
+          const uint32_t ck = B200RT_REF_KIND(ch[c]);
+          if (ck == B200RT_KIND_INNER) walk(ch[c], cb[c], true);
+          else if (ck == B200RT_KIND_INSTANCE) walk(ch[c], cb[c], true);     // its own box, as stored in the parent
+          else walk(ch[c], box, own);                                         // primitives: the node's own gate
+        }
+        return;
+      }
+      float rec[8] = {box ? box[0] : 0.f, box ? box[1] : 0.f, box ? box[2] : 0.f, 0.f,
+                      box ? box[3] : 0.f, box ? box[4] : 0.f, box ? box[5] : 0.f, 0.f};
+      memcpy(&rec[3], &ref, 4);
+      const uint32_t gated = (own && box) ? 1u : 0u;
+      memcpy(&rec[7], &gated, 4);
+      flat.insert(flat.end(), rec, rec + 8);
+    };
+    if (ok) {
+      const uint32_t rk = B200RT_REF_KIND(d->root);
+      // BVH::intersect and Mesh_instance::intersect test the root's box; a lone primitive has no gate at all
+      walk(d->root, d->root_box, rk == B200RT_KIND_INNER || rk == B200RT_KIND_INSTANCE);
+    }
+    const size_t n_top = flat.size() / 8;
+    if (!ok || n_top == 0 || n_top > RT_TOP_LINEAR_MAX || getenv("B200RT_TOP_TREE")) {
+      S.n_top = 0; S.top_objs = nullptr;
+    } else {
+      S.n_top = (int)n_top;
+      UP(S.top_objs, flat.data(), flat.size(), float);
+    }
+  }
   {
     // 12 floats per triangle -> 3 float4 (same bytes)
     float* p = nullptr;

@@ -78,11 +78,17 @@ __host__ __device__ __forceinline__ float rng_u01(uint32_t key, uint32_t dim) {
 // ---- device scene -----------------------------------------------------------
 struct DScene {
   int semantics, max_depth;
+  int refill_closest, refill_any;  // idle lanes before a traversal warp takes new rays (32 = whole-warp batches)
+  int node_vote;                   // lanes that must hold an inner node for the warp to keep descending (rt_fast.cuh)
   v3 background, ambient;
   float shadow_eps, isect_eps;
   uint32_t root;
   float root_box[6];
   const float4* nodes;      // 4 x float4 per inner node (b200rt_bvh_node verbatim)
+  // top-level objects flattened with the reference's innermost gate of each: 2 x float4 per object
+  // {min.xyz, as_float(ref)}, {max.xyz, as_float(1 if the object has a gate, 0 if it is entered unconditionally)}
+  const float4* top_objs;
+  int n_top;                // 0: walk the reference's top-level tree instead (more than RT_TOP_LINEAR_MAX objects)
   const float4* tris;       // 3 x float4 per triangle: v0|a1.x, a1.yz|a2.xy, a2.z|n
   const float4* fast_nodes; // SAH tree (csrc/fast_bvh.h), same 64-byte records
   const float4* fast_tris;  // triangles again, in SAH leaf order

@@ -22,6 +22,12 @@
 #ifndef RT_REFILL_MIN_IDLE
 #define RT_REFILL_MIN_IDLE 32  // lanes idle before the warp refills: 32 = whole-warp batches (measured fastest, profiles/r01b)
 #endif
+#ifndef RT_TOP_LINEAR_MAX
+#define RT_TOP_LINEAR_MAX 40  // top-level objects up to which phase 0 scans a flat gate list instead of the tree
+#endif
+#ifndef RT_NODE_VOTE
+#define RT_NODE_VOTE 4  // see phase 1 of k_trace_fast (swept in profiles/r01g_tuning.txt)
+#endif
 #ifndef RT_FAST_MIN_BLOCKS
 #define RT_FAST_MIN_BLOCKS 8  // resident CTAs per SM the register budget is held to (64 regs; measured sweet spot, profiles/r01b)
 #endif
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
           const RayCtx wr = make_ray(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), eps);
           n_obj = 0; obj_next = 0;
           int tp = RT_FSTACK;
-          {
+          if (S.n_top == 0) {
             const uint32_t rk = B200RT_REF_KIND(S.root);
             if (rk != B200RT_KIND_NONE) {
               float e = 0.0f;
@@ -165,6 +171,19 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
                 ok = box_gate(wr, S.root_box[0], S.root_box[1], S.root_box[2], S.root_box[3], S.root_box[4],
                               S.root_box[5], eps, &e);
               if (ok) { tp--; stack[tp] = S.root; stack_t[tp] = e; }
+            }
+          } else {
+            // flat list: every lane tests the same object's innermost gate in lock step (uniform loads), then
+            // inserts it into its queue by entry distance
+            for (int k2 = 0; k2 < S.n_top; k2++) {
+              const float4 b0 = __ldg(S.top_objs + 2 * k2), b1 = __ldg(S.top_objs + 2 * k2 + 1);
+              float e = 0.0f;
+              tc.nodes++;
+              if (__float_as_uint(b1.w) != 0u && !box_gate(wr, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, eps, &e)) continue;
+              int at = n_obj;
+              while (at > 0 && stack_t[at - 1] > e) { stack[at] = stack[at - 1]; stack_t[at] = stack_t[at - 1]; at--; }
+              stack[at] = __float_as_uint(b0.w); stack_t[at] = e;
+              n_obj++;
             }
           }
           while (tp < RT_FSTACK) {
@@ -212,17 +231,29 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
     if (!__any_sync(0xffffffffu, has_ray)) break;
 
     for (;;) {
-      if (has_ray) {
-        bool finished = false;
-        // ---- phase 1: inner nodes of the SAH tree until this lane holds a leaf or has nothing left in the object
-        for (;;) {
-          if (cur == B200RT_REF_NONE) {
-            if (sp <= n_obj) break;
-            sp--; cur = stack[sp]; cur_t = stack_t[sp];
+      // ---- phase 1 (warp-synchronous): inner nodes of the SAH tree, one step per lane per iteration, for as long as
+      // enough lanes hold one.  A lane that reaches a leaf, or runs out of nodes in its object, waits — but only
+      // until fewer than S.node_vote lanes are still descending: then everybody goes through phase 2 (the few
+      // descending lanes idle there instead).  node_vote = 1 is the plain while-while loop; incoherent waves
+      // (shadow / bounce rays) ran it at 2-3 active lanes (profiles/r01g).
+      for (;;) {
+        bool want_node = false;
+        if (has_ray) {
+          for (;;) {
+            if (cur == B200RT_REF_NONE) {
+              if (sp <= n_obj) break;
+              sp--; cur = stack[sp]; cur_t = stack_t[sp];
+            }
+            const float bound = ANY ? tlimit : best.t;
+            if (cur_t > bound + fabsf(bound) * 1e-4f) { cur = B200RT_REF_NONE; continue; }  // pruned
+            break;
           }
-          const float bound = ANY ? tlimit : best.t;
-          if (cur_t > bound + fabsf(bound) * 1e-4f) { cur = B200RT_REF_NONE; continue; }  // pruned
-          if (B200RT_REF_KIND(cur) != B200RT_KIND_FNODE) break;
+          want_node = cur != B200RT_REF_NONE && B200RT_REF_KIND(cur) == B200RT_KIND_FNODE;
+        }
+        const unsigned mn = __ballot_sync(0xffffffffu, want_node);
+        if (mn == 0u) break;
+        if (__popc(mn) < S.node_vote && __any_sync(0xffffffffu, has_ray && !want_node)) break;
+        if (want_node) {
           const uint32_t idx = B200RT_REF_INDEX(cur);
           cur = B200RT_REF_NONE;
           tc.nodes++;
@@ -242,6 +273,9 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
           } else if (h0) { cur = c0; cur_t = e0; }
           else if (h1) { cur = c1; cur_t = e1; }
         }
+      }
+      if (has_ray && !(cur != B200RT_REF_NONE && B200RT_REF_KIND(cur) == B200RT_KIND_FNODE)) {
+        bool finished = false;
         // ---- phase 2a: nothing pending in the current object -> enter the next one of the queue
         if (cur == B200RT_REF_NONE) {
           if (obj_next >= n_obj) {
@@ -380,7 +414,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
       }
       const unsigned act = __ballot_sync(0xffffffffu, has_ray);
       if (act == 0u) break;
-      if (!exhausted && __popc(~act) >= RT_REFILL_MIN_IDLE) break;
+      if (!exhausted && __popc(~act) >= (ANY ? S.refill_any : S.refill_closest)) break;
     }
   }
   flush_counters(C, tc, ANY);
