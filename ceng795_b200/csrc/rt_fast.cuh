@@ -20,7 +20,9 @@
 
 #define RT_FSTACK 64
 #ifndef RT_REFILL_MIN_IDLE
-#define RT_REFILL_MIN_IDLE 32  // lanes idle before the warp refills: 32 = whole-warp batches (measured fastest, profiles/r01b)
+// lanes idle before a warp takes new rays.  32 = whole-warp batches.  With the flat phase 0 (uniform cost, no
+// divergence) topping a warp up once it is down to its last few rays pays: 26 (swept in profiles/r01g_tuning.txt)
+#define RT_REFILL_MIN_IDLE 26
 #endif
 #ifndef RT_TOP_LINEAR_MAX
 #define RT_TOP_LINEAR_MAX 40  // top-level objects up to which phase 0 scans a flat gate list instead of the tree

@@ -4,5 +4,5 @@
 var=$1; vals=$2; cfg=${3:-cfg2}; extra=${4:-}
 for v in $vals; do
   env $var=$v python bench.py --config $cfg $extra --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null \
-   | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['stage_ms_per_step']; print('$cfg $var=$v', round(d['ms_per_step'],3), 'extend', round(s['ms_extend'],3), 'shadow', round(s['ms_shadow'],3), 'shade', round(s['ms_shade'],3))"
+   | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); s=d['stage_ms_per_step']; print('$cfg $var=$v', round(d['ms_per_step'],3), {k: round(x,3) for k,x in s.items()})"
 done
