@@ -12,6 +12,7 @@ There is no CPU fallback: rendering requires libb200rt.so and a CUDA device.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
 
@@ -556,6 +557,10 @@ class HostScene:
         d = self.desc
         return np.ctypeslib.as_array(d.tri_geom, shape=(d.n_tris, 12)) if d.n_tris else np.zeros((0, 12), np.float32)
 
+    def save(self, path: str) -> None:
+        """Binary cache of the flattened description (include/b200rt.h: b200rt_scene_desc_save)."""
+        _lib.check(self._L.b200rt_scene_desc_save(self.desc_ptr, os.fsencode(path)), "b200rt_scene_desc_save")
+
     def close(self):
         if getattr(self, "_b", None):
             self._L.b200rt_builder_destroy(self._b)
@@ -568,8 +573,53 @@ class HostScene:
             pass
 
 
+class CachedHostScene:
+    """A flattened description read back from a binary cache: the role of HostScene without parse or BVH build."""
+
+    def __init__(self, path: str):
+        self._L = _lib.load()
+        out = C.POINTER(_lib.SceneDesc)()
+        _lib.check(self._L.b200rt_scene_desc_load(os.fsencode(path), C.byref(out)), "b200rt_scene_desc_load")
+        self.desc_ptr = out
+        self.desc = out.contents
+        d = self.desc
+        cams = [d.cameras[i] for i in range(d.n_cameras)]
+        # only what the device-facing methods of Scene read: semantics and the image size of each camera
+        self.spec = SceneSpec(int(d.semantics), None, None, float(d.shadow_eps), int(d.max_depth),
+                              [dict(width=int(c.width), height=int(c.height)) for c in cams],
+                              [], [], [], [], [], [], None, [], [], [], [])
+
+    def save(self, path: str) -> None:
+        _lib.check(self._L.b200rt_scene_desc_save(self.desc_ptr, os.fsencode(path)), "b200rt_scene_desc_save")
+
+    def close(self):
+        if getattr(self, "desc_ptr", None):
+            self._L.b200rt_scene_desc_free(self.desc_ptr)
+            self.desc_ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Scene:
     """Reference-facing object: ``Scene(xml).render_image(camera_index)``."""
+
+    @classmethod
+    def from_cache(cls, path: str, device: int = 0, upload: bool = True) -> "Scene":
+        """The same object from a file written by ``scene.host.save(path)``: no XML, no BVH build."""
+        self = cls.__new__(cls)
+        self.host = CachedHostScene(path)
+        self.spec = self.host.spec
+        self.semantics = self.spec.semantics
+        self.device = device
+        self._scene = None
+        self._L = _lib.load()
+        if upload:
+            self.upload()
+        return self
 
     def __init__(self, xml: str, semantics="hw3", device: int = 0, upload: bool = True, base_dir: str | None = None):
         self.spec = parse_xml(xml, semantics, base_dir=base_dir)

@@ -435,6 +435,16 @@ void* b200rt_scene_stream(b200rt_scene*);
 /* Bytes of scene data resident in HBM (nodes + triangles + tables). */
 uint64_t b200rt_scene_bytes(b200rt_scene*);
 
+/* ---- next row: binary cache of a flattened scene ----
+ * The reference re-parses its XML through stringstreams on every run and knows "binaryFile" side files for vertex
+ * and face data (HW7/src/Scene.cpp:998-1032, 1839-1904).  These two calls store / restore the WHOLE flattened
+ * description (reference tree, SAH tree, gates, records, textures) so a host skips parse + BVH build.
+ * load() returns one malloc'd block (desc + arrays) to be released with b200rt_scene_desc_free; the file carries
+ * the struct sizes of this header and an FNV-1a checksum and is rejected loudly when either does not match. */
+int b200rt_scene_desc_save(const B200SceneDesc*, const char* path);
+int b200rt_scene_desc_load(const char* path, B200SceneDesc** out);
+void b200rt_scene_desc_free(B200SceneDesc*);
+
 /* Measurement aid: streaming-read bandwidth over a `bytes` working set, `iters` passes, in GB/s.
  * 48 MB measures the L2 (the denominator for scene fetches when the tree is L2-resident), >= 1 GB measures HBM. */
 int b200rt_measure_read_bandwidth(int device, uint64_t bytes, int iters, double* gbs_out);
