@@ -98,6 +98,10 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
   const uint32_t count = ANY ? C->shadow_count : waves[d].count;
   unsigned int* cursor = ANY ? &C->work_shadow : &C->work_extend;
   const float eps = S.isect_eps;
+  // Topping a warp up before it has drained pays when ray costs inside a batch differ a lot (bounce waves, one
+  // sample per pixel); it costs ~10 % when they do not: the strata of one pixel travel together, finish together,
+  // and a partial refill then leaves the warp running 26 wide (cfg3, profiles/r01g_tuning.txt).
+  const int refill_idle = (d == 0 && S.cam.samples_sqrt > 1) ? 32 : (ANY ? S.refill_any : S.refill_closest);
   const unsigned lane = lane_id();
   TravCounters tc = {0, 0, 0, 0};
 
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_FAST_MIN_BLOCKS) k_trace_fast(DSc
       }
       const unsigned act = __ballot_sync(0xffffffffu, has_ray);
       if (act == 0u) break;
-      if (!exhausted && __popc(~act) >= (ANY ? S.refill_any : S.refill_closest)) break;
+      if (!exhausted && __popc(~act) >= refill_idle) break;
     }
   }
   flush_counters(C, tc, ANY);

@@ -607,9 +607,8 @@ __global__ void k_combine(DScene S, Pool P, const WaveInfo* waves, int d, float4
           for (int ai = i - 1; ai < i + 2; ai++) {
             if (ai < 0 || ai >= W) continue;
             const float w = gaussian_filter((float)(i - ai), (float)(j - aj), 1.5f / 3.0f);
-            float* px = reinterpret_cast<float*>(accum + (size_t)aj * W + ai);
-            atomicAdd(px + 0, color.x * w); atomicAdd(px + 1, color.y * w);
-            atomicAdd(px + 2, color.z * w); atomicAdd(px + 3, w);
+            // Pixel::add_color(color, w): one 16-byte vector atomic (sm_90+) instead of four scalar ones
+            atomicAdd(accum + (size_t)aj * W + ai, make_float4(color.x * w, color.y * w, color.z * w, w));
           }
         }
       } else if (ns == 1) {
@@ -629,9 +628,8 @@ __global__ void k_combine(DScene S, Pool P, const WaveInfo* waves, int d, float4
             const float fx = ((float)i + sx) - ((float)ai + 0.5f);
             const float fy = ((float)j + sy) - ((float)aj + 0.5f);
             const float w = gaussian_filter(fx, fy, S.semantics == B200RT_SEM_HW4 ? 1.5f / 3.0f : 1.0f / 3.0f);
-            float* px = reinterpret_cast<float*>(accum + (size_t)aj * W + ai);
-            atomicAdd(px + 0, color.x * w); atomicAdd(px + 1, color.y * w);
-            atomicAdd(px + 2, color.z * w); atomicAdd(px + 3, w);
+            // Pixel::add_color(color, w): one 16-byte vector atomic (sm_90+) instead of four scalar ones
+            atomicAdd(accum + (size_t)aj * W + ai, make_float4(color.x * w, color.y * w, color.z * w, w));
           }
         }
       }

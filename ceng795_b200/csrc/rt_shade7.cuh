@@ -1016,15 +1016,13 @@ __global__ void k_combine7(DScene S, Pool P, const WaveInfo* waves, int d, float
             if (ai < 0 || ai >= W) continue;
             const float w = gaussian_filter(((float)i + sx) - ((float)ai + 0.5f), ((float)j + sy) - ((float)aj + 0.5f),
                                             1.5f / 3.0f);
-            float* px = reinterpret_cast<float*>(accum + (size_t)aj * W + ai);
-            atomicAdd(px + 0, color.x * w); atomicAdd(px + 1, color.y * w);
-            atomicAdd(px + 2, color.z * w); atomicAdd(px + 3, w);
+            // Pixel::add_color(color, w): one 16-byte vector atomic (sm_90+) instead of four scalar ones
+            atomicAdd(accum + (size_t)aj * W + ai, make_float4(color.x * w, color.y * w, color.z * w, w));
           }
         }
       } else {
         // box filter: Pixel::add_color(color, 1.0f) per sample — HW7/src/Scene.cpp:80
-        float* px = reinterpret_cast<float*>(accum + pix);
-        atomicAdd(px + 0, color.x); atomicAdd(px + 1, color.y); atomicAdd(px + 2, color.z); atomicAdd(px + 3, 1.0f);
+        atomicAdd(accum + pix, make_float4(color.x, color.y, color.z, 1.0f));
       }
     }
   }
