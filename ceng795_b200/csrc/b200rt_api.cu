@@ -174,7 +174,7 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     if (!with_shading) break;
     const bool hw7 = S.semantics >= B200RT_SEM_HW5;  // HW5/HW6 shade like HW7's ray-tracing mode (flags inside)
     const bool hw4 = S.semantics == B200RT_SEM_HW4;
-    if (hw7) k_shade7_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    if (hw7) k_shade7_a<<<grid_s * RT_BLOCK / RT_SHADE7_BLOCK, RT_SHADE7_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     else if (hw4) k_shade4_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     else k_shade_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     k_clamp_shadow_count<<<1, 1, 0, st>>>(sc->Q, sc->d_counters);
@@ -191,7 +191,7 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     }
     (*launches)++;
     tm.mark(ST_SHADOW);
-    if (hw7) k_shade7_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    if (hw7) k_shade7_b<<<grid_s * RT_BLOCK / RT_SHADE7_BLOCK, RT_SHADE7_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     else if (hw4) k_shade4_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     else k_shade_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     k_finish_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->P, sc->d_counters);

@@ -12,6 +12,13 @@
 #include "rt_kernels.cuh"
 
 #define RT_PI 3.14159265358979323846
+// The HW7 shade kernels stall on instruction fetch (profiles/r01i: no_instructions 45-59 % of stall samples, 90 KB of
+// code walked by 16 warps per SM).  Warps of a block that walk the same stretch of code together share its cache lines,
+// so the per-light loops are block-uniform and start with a barrier.
+#define RT_SHADE_SYNC 1
+#ifndef RT_SHADE7_BLOCK
+#define RT_SHADE7_BLOCK 256  // threads per block of k_shade7_a/b: more warps behind each barrier
+#endif
 
 __device__ __forceinline__ v3 operator/(v3 a, v3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
 
@@ -453,7 +460,7 @@ __device__ __noinline__ v3 light_radiance7(const DScene& S, int li, v3 to_light,
 // ---- shade_a (HW7): surface record, emissive / replace_all short cuts, shadow-ray emission ----
 #define RT_KDF_REPLACE_ALL 1u
 #define RT_KDF_EMISSIVE 2u
-__global__ void __launch_bounds__(RT_BLOCK) k_shade7_a(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves, int d,
+__global__ void __launch_bounds__(RT_SHADE7_BLOCK) k_shade7_a(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves, int d,
                                                        Counters* C) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -493,6 +500,9 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_a(DScene S, Pool P, ShadowQ
       lights_on = !early && !(meta & RT_META_INMEDIUM);
     }
     for (int li = 0; li < S.n_lights; li++) {
+#ifdef RT_SHADE_SYNC
+      __syncthreads();
+#endif
       bool want = false;
       v3 wi = mk3(0, 0, 0);
       float ldist = 0.f;
@@ -753,7 +763,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade4_b(DScene S, Pool P, ShadowQ
 }
 
 // ---- shade_b (HW7): Scene::send_ray / trace_ray / trace_path bodies -------------------------
-__global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQueue Q, WaveInfo* waves, int d,
+__global__ void __launch_bounds__(RT_SHADE7_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQueue Q, WaveInfo* waves, int d,
                                                        Counters* C) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   const uint32_t next_begin = waves[d + 1].begin;
@@ -805,47 +815,61 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQ
         color = light_radiance7(S, S.env_light, dir, 1.0f);
       }
     }
+    // Surface state of a hit vertex, hoisted so that the light loop below runs in lock step for the whole block
+    v3 n = mk3(0, 0, 0), kd = mk3(0, 0, 0), ks = mk3(0, 0, 0), w_o = mk3(0, 0, 0);
+    int mat = 0;
+    uint32_t flags = 0;
+    const bool in_medium = (meta & RT_META_INMEDIUM) != 0;
+    const bool light_hit = (meta & RT_META_LIGHTHIT) != 0;
     if (hit) {
       const float4 nn = P.nrm[slot];
-      const v3 n = mk3(nn.x, nn.y, nn.z);
-      const b200rt_material& m = S.mats[__float_as_int(nn.w)];
+      n = mk3(nn.x, nn.y, nn.z);
+      mat = __float_as_int(nn.w);
       const float4 kdf = P.kd[slot];
-      const v3 kd = mk3(kdf.x, kdf.y, kdf.z);
-      const uint32_t flags = __float_as_uint(kdf.w);
+      kd = mk3(kdf.x, kdf.y, kdf.z);
+      flags = __float_as_uint(kdf.w);
       p = o + (dir * ha.x);
-      const v3 w_o = normalize(o - p);
-      const bool in_medium = (meta & RT_META_INMEDIUM) != 0;
-      const bool light_hit = (meta & RT_META_LIGHTHIT) != 0;
+      w_o = normalize(o - p);
+      ks = ld3(S.mats[mat].specular);
+    }
+    // trace_ray / trace_path go on past the emissive and replace_all short cuts only for these vertices
+    const bool shaded = hit && !(flags & RT_KDF_EMISSIVE) && !(!pt && (flags & RT_KDF_REPLACE_ALL));
+    // HW7 sums the lights on their own and adds the sum to ambient (HW7/src/Scene.cpp:260-311, 434-437); HW5/HW6
+    // add every term straight onto the colour, which starts as the ambient term (HW6/src/Scene.cpp:169-207)
+    const bool onto_colour = S.semantics < B200RT_SEM_HW7;
+    v3 direct = (shaded && onto_colour) ? (color + (ld3(S.mats[mat].ambient) * S.ambient)) : mk3(0, 0, 0);
+    // calculate_diffuse_and_specular_radiance — HW7/src/Scene.cpp:260-311
+    for (int li = 0; li < S.n_lights; li++) {
+#ifdef RT_SHADE_SYNC
+      __syncthreads();
+#endif
+      const uint32_t vslot = slot * (uint32_t)S.n_lights + (uint32_t)li;
+      if (!(shaded && !in_medium) || !Q.vis[vslot]) continue;
+      const b200rt_material& m = S.mats[mat];
+      const float4 ls = Q.lv[vslot];  // light_dir7's sample, drawn once in shade_a
+      const v3 lvec = mk3(ls.x, ls.y, ls.z);
+      const float prob = ls.w;
+      const v3 w_i = normalize(lvec);
+      const v3 Li = light_radiance7(S, li, lvec, prob);
+      const float cti = fmaxf(0.0f, dot(n, w_i));
+      if (m.brdf != -1) {
+        direct = direct + ((Li * cti) * brdf_eval7(S.brdfs[m.brdf], n, kd, ks, w_i, w_o));
+      } else {
+        direct = direct + ((kd * Li) * cti);
+        const float sct = fmaxf(0.0f, dot(n, normalize(w_o + w_i)));
+        direct = direct + ((ks * Li) * (float)pow_ref7((double)sct, (double)m.phong_exponent));
+      }
+    }
+#ifdef RT_SHADE_SYNC
+    __syncthreads();
+#endif
+    if (hit) {
+      const b200rt_material& m = S.mats[mat];
       if (flags & RT_KDF_EMISSIVE) {
         color = (pt && light_hit) ? mk3(0, 0, 0) : kd;
       } else if (!pt && (flags & RT_KDF_REPLACE_ALL)) {
         color = kd;
       } else {
-        const v3 ks = ld3(m.specular);
-        // HW7 sums the lights on their own and adds the sum to ambient (HW7/src/Scene.cpp:260-311, 434-437); HW5/HW6
-        // add every term straight onto the colour, which starts as the ambient term (HW6/src/Scene.cpp:169-207)
-        const bool onto_colour = S.semantics < B200RT_SEM_HW7;
-        v3 direct = onto_colour ? (color + (ld3(m.ambient) * S.ambient)) : mk3(0, 0, 0);
-        if (!in_medium) {
-          // calculate_diffuse_and_specular_radiance — HW7/src/Scene.cpp:260-311
-          for (int li = 0; li < S.n_lights; li++) {
-            const uint32_t vslot = slot * (uint32_t)S.n_lights + (uint32_t)li;
-            if (!Q.vis[vslot]) continue;
-            const float4 ls = Q.lv[vslot];  // light_dir7's sample, drawn once in shade_a
-            const v3 lvec = mk3(ls.x, ls.y, ls.z);
-            const float prob = ls.w;
-            const v3 w_i = normalize(lvec);
-            const v3 Li = light_radiance7(S, li, lvec, prob);
-            const float cti = fmaxf(0.0f, dot(n, w_i));
-            if (m.brdf != -1) {
-              direct = direct + ((Li * cti) * brdf_eval7(S.brdfs[m.brdf], n, kd, ks, w_i, w_o));
-            } else {
-              direct = direct + ((kd * Li) * cti);
-              const float sct = fmaxf(0.0f, dot(n, normalize(w_o + w_i)));
-              direct = direct + ((ks * Li) * (float)pow_ref7((double)sct, (double)m.phong_exponent));
-            }
-          }
-        }
         bool copy_light_hit = light_hit;
         if (pt) {
           if (!is_zero(direct)) { copy_light_hit = true; color = color + direct; }
@@ -934,6 +958,9 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade7_b(DScene S, Pool P, ShadowQ
       }
     }
     // children -> next wave (order: diffuse sample, mirror, reflect, transmit)
+#ifdef RT_SHADE_SYNC
+    __syncthreads();
+#endif
     uint32_t cd = 0xffffffffu, cm = 0xffffffffu, cr = 0xffffffffu, ct = 0xffffffffu;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
