@@ -174,6 +174,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB
+    if os.environ.get("B200RT_LIB"):   # tuning aid: a variant built by tools/build_variant.sh (same ABI, other -D knobs)
+        path = os.environ["B200RT_LIB"]
+        build_if_missing = False
     if build_if_missing:
         try:
             _build.build_lib()

@@ -68,6 +68,7 @@ struct b200rt_scene {
   float* d_rtab;
   float4* d_export;
   void* d_scan_tmp;
+  uint32_t* d_sort[4];   // PPM: direction keys / photon order (in, out)
   size_t scan_tmp_bytes, items_capacity;
   uint32_t n_hp;
   int ppm_camera;
@@ -342,12 +343,14 @@ void ppm_free(b200rt_scene* sc) {
   HitPoints& H = sc->HP;
   void* ptrs[] = {H.count, H.pos, H.nrm, H.wo, H.att, H.n, H.state, H.dep, sc->G.cell_count, sc->G.cell_start, sc->G.items,
                   sc->G.cell_pos,
-                  sc->d_pc, sc->d_rtab, sc->d_export, sc->d_scan_tmp};
+                  sc->d_pc, sc->d_rtab, sc->d_export, sc->d_scan_tmp, sc->d_sort[0], sc->d_sort[1], sc->d_sort[2],
+                  sc->d_sort[3]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   memset(&sc->HP, 0, sizeof(HitPoints));
   memset(&sc->G, 0, sizeof(PpmGrid));
   sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
+  for (int q = 0; q < 4; q++) sc->d_sort[q] = nullptr;
   sc->scan_tmp_bytes = 0; sc->items_capacity = 0; sc->n_hp = 0;
 }
 
@@ -457,6 +460,7 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
   if (G.cell_start) cudaFree(G.cell_start);
   G.cell_count = nullptr; G.cell_start = nullptr;
   G.rtab = rtab;
+  G.debug = getenv("B200RT_PPM_DEBUG") ? atoi(getenv("B200RT_PPM_DEBUG")) : 0;
   G.num_hash = n_hp;
   float r0 = 0.f;
   size_t entries = 0;
@@ -537,7 +541,33 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
   tm.mark(ST_GENERATE);
   for (int64_t done = 0; done < opts->photons && sc->S.max_depth > 1; done += (int64_t)batch) {
     const uint32_t n = (uint32_t)((opts->photons - done) < (int64_t)batch ? (opts->photons - done) : (int64_t)batch);
-    k_ppm_emit<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, sc->d_waves, s0, opts->first_photon + (uint64_t)done, n);
+    const uint32_t* order = nullptr;
+    if (!getenv("B200RT_PPM_NO_SORT")) {
+      // trace the batch in direction order (ppm_kernels.cuh: k_ppm_emit_keys); cub radix sort on 16-bit keys is a
+      // library call on a once-per-batch step
+      if (!sc->d_sort[0]) {
+        for (int q = 0; q < 4; q++) CK(cudaMalloc((void**)&sc->d_sort[q], batch * sizeof(uint32_t)));
+      }
+      int bits = PPM_SORT_BITS;
+      if (const char* e = getenv("B200RT_PPM_SORT_BITS")) bits = std::max(1, std::min(16, atoi(e)));
+      k_ppm_emit_keys<<<sc->sm_count * 8, 256, 0, st>>>(s0, opts->first_photon + (uint64_t)done, n, bits, sc->d_sort[0],
+                                                        sc->d_sort[1]);
+      size_t need = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, need, sc->d_sort[0], sc->d_sort[2], sc->d_sort[1], sc->d_sort[3], (int)n,
+                                      0, 16, st);
+      if (need > sc->scan_tmp_bytes) {
+        CK(cudaStreamSynchronize(st));
+        if (sc->d_scan_tmp) cudaFree(sc->d_scan_tmp);
+        CK(cudaMalloc(&sc->d_scan_tmp, need));
+        sc->scan_tmp_bytes = need;
+      }
+      cub::DeviceRadixSort::SortPairs(sc->d_scan_tmp, need, sc->d_sort[0], sc->d_sort[2], sc->d_sort[1], sc->d_sort[3],
+                                      (int)n, 0, bits, st);
+      order = sc->d_sort[3];
+      launches += 3;
+    }
+    k_ppm_emit<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, sc->d_waves, s0, opts->first_photon + (uint64_t)done, n,
+                                                 order);
     launches++;
     tm.mark(ST_GENERATE);
     for (int d = 0; d + 1 < sc->S.max_depth; d++) {
@@ -664,6 +694,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   memset(&sc->HP, 0, sizeof(HitPoints));
   memset(&sc->G, 0, sizeof(PpmGrid));
   sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
+  for (int q = 0; q < 4; q++) sc->d_sort[q] = nullptr;
   sc->scan_tmp_bytes = 0; sc->items_capacity = 0; sc->n_hp = 0; sc->ppm_camera = -1;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));

@@ -13,6 +13,15 @@
 #define PPM_ALPHA 0.7f
 #define PPM_RTAB (1 << 20)
 #define PPM_QCAP 12  // deferred deposit candidates per lane
+#ifndef PPM_MIN_BLOCKS
+#define PPM_MIN_BLOCKS 5  // 102 registers: room for two rounds of scan loads per lane (variants measured in profiles/r01j_tuning.txt)
+#endif
+#ifndef PPM_SORT_BITS
+#define PPM_SORT_BITS 4  // direction bins (2^bits) the photons of a batch are grouped into before tracing
+#endif
+#ifndef PPM_SCAN_LOADS
+#define PPM_SCAN_LOADS 4  // grid entries each lane fetches per scan step (32 x this many per warp)
+#endif
 
 struct HitPoints {
   uint32_t capacity;
@@ -38,6 +47,7 @@ struct PpmGrid {
   v3 bbox_min;
   float hash_scale, r0, r0sq;
   const float* rtab;         // R(n) for n < PPM_RTAB
+  int debug;                 // B200RT_PPM_DEBUG (timing experiments only): 1 skip the drain, 2 skip the flux atomic, 4 skip the CAS
 };
 struct PpmCounters {
   unsigned long long photon_rays, cell_scans, deposits;
@@ -216,15 +226,45 @@ __global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uin
 // ---- photon pass -------------------------------------------------------------------
 // RNG: key of photon i = mix(mix(s0 ^ 'PHOT', lo32(i)), hi32(i)); dims: emission 0,1; bounce b: 8b+2,3 hemisphere,
 // 8b+4 roulette, 8b+5 glass roulette (shared with oracle.c).
-__global__ void k_ppm_emit(DScene S, Pool P, WaveInfo* waves, uint32_t s0, unsigned long long first, uint32_t n) {
+// Direction of photon i — Point_light::generate_photon, PPM/src/Point_light.cpp:7-30 (theta = 2 pi xi_2: sic,
+// SURVEY Appendix B.6).  RNG: key = mix(mix(s0 ^ 'PHOT', lo), hi), dims 0, 1.
+__device__ __forceinline__ v3 ppm_photon_dir(uint32_t s0, unsigned long long i, uint32_t* key_out) {
+  const uint32_t key = rng_mix(rng_mix(s0 ^ 0x50484F54u, (uint32_t)i), (uint32_t)(i >> 32));
+  const float phi = (float)(2 * RT_PI * (double)rng_u01(key, 0));
+  const float theta = (float)(2 * RT_PI * (double)rng_u01(key, 1));
+  *key_out = key;
+  return onb_dir7(mk3(0.0f, 1.0f, 0.0f), theta, phi);
+}
+// The photons of a batch are a SET (first .. first+n-1): the order they are traced in is ours.  Tracing them sorted
+// by direction (16-bit Morton code of the octahedral map) makes consecutive photons hit neighbouring surface points:
+// the cell lists a warp streams in the deposit (280 MB of them at 1080p, read at random otherwise: 19 GB of DRAM
+// traffic per 10 M photons, profiles/r01j) are then shared through L1/L2, and the first wave's rays are coherent.
+__global__ void k_ppm_emit_keys(uint32_t s0, unsigned long long first, uint32_t n, int bits, uint32_t* keys,
+                                uint32_t* idx) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    uint32_t key;
+    const v3 d = ppm_photon_dir(s0, first + k, &key);
+    const float a = fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
+    float u = d.x / a, v = d.z / a;
+    if (d.y < 0.0f) {
+      const float uu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), vv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
+      u = uu; v = vv;
+    }
+    uint32_t x = (uint32_t)fminf(255.0f, fmaxf(0.0f, (u * 0.5f + 0.5f) * 256.0f));
+    uint32_t y = (uint32_t)fminf(255.0f, fmaxf(0.0f, (v * 0.5f + 0.5f) * 256.0f));
+    x = (x | (x << 4)) & 0x0F0Fu; x = (x | (x << 2)) & 0x3333u; x = (x | (x << 1)) & 0x5555u;
+    y = (y | (y << 4)) & 0x0F0Fu; y = (y | (y << 2)) & 0x3333u; y = (y | (y << 1)) & 0x5555u;
+    keys[k] = (x | (y << 1)) >> (16 - bits);
+    idx[k] = k;
+  }
+}
+__global__ void k_ppm_emit(DScene S, Pool P, WaveInfo* waves, uint32_t s0, unsigned long long first, uint32_t n,
+                           const uint32_t* order) {
   const b200rt_light& L = S.lights[0];
   const v3 flux = ld3(L.intensity) * (float)(RT_PI * 4.0f);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const unsigned long long i = first + k;
-    const uint32_t key = rng_mix(rng_mix(s0 ^ 0x50484F54u, (uint32_t)i), (uint32_t)(i >> 32));
-    const float phi = (float)(2 * RT_PI * (double)rng_u01(key, 0));
-    const float theta = (float)(2 * RT_PI * (double)rng_u01(key, 1));  // sic
-    const v3 d = onb_dir7(mk3(0.0f, 1.0f, 0.0f), theta, phi);
+    uint32_t key;
+    const v3 d = ppm_photon_dir(s0, first + (order ? order[k] : k), &key);
     P.ray_o[k] = make_float4(L.position[0], L.position[1], L.position[2], 0.0f);
     P.ray_d[k] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
     P.rec0[k] = make_float4(flux.x, flux.y, flux.z, 0.f);
@@ -239,7 +279,7 @@ __global__ void k_ppm_next_wave(WaveInfo* waves, int d, uint32_t half, Counters*
   waves[d + 1].count = 0;
   C->work_extend = 0;
 }
-__global__ void __launch_bounds__(RT_BLOCK, 6) k_ppm_photon_shade(DScene S, Pool P, WaveInfo* waves, int d, HitPoints HP,
+__global__ void __launch_bounds__(RT_BLOCK, PPM_MIN_BLOCKS) k_ppm_photon_shade(DScene S, Pool P, WaveInfo* waves, int d, HitPoints HP,
                                                                PpmGrid G, Counters* C, PpmCounters* PC) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   const uint32_t next_begin = waves[d + 1].begin;
@@ -331,6 +371,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 6) k_ppm_photon_shade(DScene S, Pool
     int q_src[PPM_QCAP];
     int qn = 0;
     auto drain = [&]() {
+      if (G.debug & 1) { qn = 0; return; }
       int qmax = qn;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) qmax = max(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
@@ -354,6 +395,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 6) k_ppm_photon_shade(DScene S, Pool
         bool accepted = false;
         for (;;) {
           if (!(d2 <= G.r0sq * ppm_R(G, n_old))) break;
+          if (G.debug & 4) { accepted = true; break; }
           const unsigned int prev = atomicCAS(hp_n(HP, hi), n_old, n_old + 1u);
           if (prev == n_old) { accepted = true; break; }
           n_old = prev;
@@ -368,7 +410,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 6) k_ppm_photon_shade(DScene S, Pool
           const v3 color = (mk3(hd.x, hd.y, hd.z) + ((mk3(hs.x, hs.y, hs.z) * powf(sct, hn.w)) / cti)) *
                            mk3(hw.w, hd.w, hs.w);
           const v3 c = (color * pf) / ppm_R(G, n_old);
-          atomicAdd(HP.state + hi, make_float4(c.x, c.y, c.z, 0.0f));   // one 16-byte vector atomic (sm_90+)
+          if (!(G.debug & 2)) atomicAdd(HP.state + hi, make_float4(c.x, c.y, c.z, 0.0f));   // one 16-byte vector atomic (sm_90+)
         }
       }
       qn = 0;
@@ -380,36 +422,68 @@ __global__ void __launch_bounds__(RT_BLOCK, 6) k_ppm_photon_shade(DScene S, Pool
       const uint32_t cell = ppm_hash(G.num_hash, abs((int)hh.x), abs((int)hh.y), abs((int)hh.z));
       my_c0 = G.cell_start[cell]; my_c1 = G.cell_start[cell + 1];
     }
+    // The scan is a flat sequence of steps (photon, 32 x PPM_SCAN_LOADS entries of its cell), walked by the whole
+    // warp; the entries of step k+1 are requested before step k is consumed, so a lane always has two rounds of
+    // 16-byte loads in flight (the kernel waits on memory: long-scoreboard 58 % of its stall samples, profiles/r01j).
     unsigned dmask = __ballot_sync(0xffffffffu, dep);
-    while (dmask) {
-      const int src = __ffs(dmask) - 1;
-      dmask &= dmask - 1;
-      const v3 pp = mk3(__shfl_sync(0xffffffffu, p.x, src), __shfl_sync(0xffffffffu, p.y, src), __shfl_sync(0xffffffffu, p.z, src));
-      const unsigned int c0 = __shfl_sync(0xffffffffu, my_c0, src), c1 = __shfl_sync(0xffffffffu, my_c1, src);
-      if (lane_id() == 0) scans += c1 - c0;
-      for (unsigned int base = c0; base < c1; base += 128u) {
-        // four independent 16-byte loads in flight per lane before any of them is consumed
-        float4 ent[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const unsigned int q = base + 32u * j + lane_id();
-          ent[j] = q < c1 ? __ldg(G.cell_pos + q) : make_float4(RT_INF, RT_INF, RT_INF, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float4 hp = ent[j];
-          const v3 v = mk3(hp.x, hp.y, hp.z) - pp;
-          const float d2 = dot(v, v);
-          if (!(d2 <= G.r0sq)) continue;   // r2(n) <= r0^2: cannot be accepted (same decision, fewer loads)
-          const unsigned int hi = __float_as_uint(hp.w);
-          // the reference accepts iff (normals agree) && (|v|^2 <= r2); the radius goes first: n is an L2 hit
-          // and rejects almost every entry once the radii have shrunk
-          const unsigned int n_now = *((volatile unsigned int*)hp_n(HP, hi));
-          if (!(d2 <= G.r0sq * ppm_R(G, n_now))) continue;
-          q_hi[qn] = hi; q_d2[qn] = d2; q_src[qn] = src; qn++;
-        }
-        if (__any_sync(0xffffffffu, qn > PPM_QCAP - 4)) drain();
+    int n_src = -1;                 // photon (lane) the NEXT step belongs to
+    unsigned int n_base = 0, n_c1 = 0;
+    auto advance = [&]() {          // moves (n_src, n_base) to the following step; n_src = -1 when there is none
+      if (n_src >= 0) {
+        n_base += 32u * PPM_SCAN_LOADS;
+        if (n_base < n_c1) return;
       }
+      for (;;) {
+        if (!dmask) { n_src = -1; return; }
+        n_src = __ffs(dmask) - 1;
+        dmask &= dmask - 1;
+        n_base = __shfl_sync(0xffffffffu, my_c0, n_src);
+        n_c1 = __shfl_sync(0xffffffffu, my_c1, n_src);
+        if (lane_id() == 0) scans += n_c1 - n_base;
+        if (n_base < n_c1) return;
+      }
+    };
+    float4 nxt[PPM_SCAN_LOADS];
+    auto fetch = [&]() {            // streaming loads (evict-first): 280 MB of entries, each read once per photon
+#pragma unroll
+      for (int j = 0; j < PPM_SCAN_LOADS; j++) {
+        const unsigned int q = n_base + 32u * j + lane_id();
+        nxt[j] = (n_src >= 0 && q < n_c1) ? __ldcs(G.cell_pos + q) : make_float4(RT_INF, RT_INF, RT_INF, 0.f);
+      }
+    };
+    advance();
+    fetch();
+    while (n_src >= 0) {
+      const int src = n_src;
+      float4 ent[PPM_SCAN_LOADS];
+#pragma unroll
+      for (int j = 0; j < PPM_SCAN_LOADS; j++) ent[j] = nxt[j];
+      advance();
+      fetch();
+      const v3 pp = mk3(__shfl_sync(0xffffffffu, p.x, src), __shfl_sync(0xffffffffu, p.y, src), __shfl_sync(0xffffffffu, p.z, src));
+      // r2(n) <= r0^2, so an entry farther than r0 cannot be accepted (same decision, fewer loads); for the others
+      // the accepted-photon counts are fetched together, THEN tested: one memory round trip per step instead of one
+      // per surviving entry
+      float d2s[PPM_SCAN_LOADS];
+      unsigned int nn[PPM_SCAN_LOADS];
+#pragma unroll
+      for (int j = 0; j < PPM_SCAN_LOADS; j++) {
+        const v3 v = mk3(ent[j].x, ent[j].y, ent[j].z) - pp;
+        d2s[j] = dot(v, v);
+        nn[j] = 0u;
+        if (d2s[j] <= G.r0sq) nn[j] = *((volatile unsigned int*)hp_n(HP, __float_as_uint(ent[j].w)));
+      }
+      float rr[PPM_SCAN_LOADS];
+#pragma unroll
+      for (int j = 0; j < PPM_SCAN_LOADS; j++) rr[j] = (d2s[j] <= G.r0sq) ? ppm_R(G, nn[j]) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < PPM_SCAN_LOADS; j++) {
+        // the reference accepts iff (normals agree) && (|v|^2 <= r2); the radius goes first and rejects almost
+        // every entry once the radii have shrunk
+        if (!(d2s[j] <= G.r0sq) || !(d2s[j] <= G.r0sq * rr[j])) continue;
+        q_hi[qn] = __float_as_uint(ent[j].w); q_d2[qn] = d2s[j]; q_src[qn] = src; qn++;
+      }
+      if (__any_sync(0xffffffffu, qn > PPM_QCAP - PPM_SCAN_LOADS)) drain();
     }
     drain();
     const uint32_t ci = warp_append(&waves[d + 1].count, cont);
