@@ -85,3 +85,55 @@ def tonemap_photographic(rgbw: np.ndarray, key: float, burn_percent: float, satu
     g = np.minimum(f(1), np.maximum(f(0), g)) * f(255.0)
     q = np.minimum(f(255), np.maximum(f(0), g))
     return np.trunc(q).astype(np.uint8).reshape(h, w, 3)
+
+
+class AsyncImageWriter:
+    """PNG encode off the critical path.  The reference's main encodes each camera's image on the
+    thread that then starts the next camera's render (HW7/src/main.cpp:93-199, lodepng); here frames are handed to a
+    worker thread, so the encode of camera i overlaps the render of camera i+1.  `submit` copies nothing: pass an
+    array the caller will not overwrite (b200rt_render / b200rt_tonemap_photographic return fresh host buffers).
+
+        with AsyncImageWriter() as w:
+            for cam in range(n):
+                rgbw, _ = scene.render_image(cam)
+                w.submit(f"cam{cam}.png", quantise(rgbw, scene.semantics))
+    """
+
+    def __init__(self, max_pending: int = 4):
+        import queue
+        import threading
+        self._q = queue.Queue(maxsize=max_pending)   # bounded: a slow disk throttles the producer, not memory
+        self._err = None
+        self.written = []
+        self._t = threading.Thread(target=self._run, name="b200rt-png", daemon=True)
+        self._t.start()
+
+    def _run(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            path, rgb8 = item
+            try:
+                write_png(path, rgb8)
+                self.written.append(path)
+            except Exception as e:  # surfaced by close(): the render loop must not lose an encode error
+                self._err = e
+
+    def submit(self, path: str, rgb8: np.ndarray) -> None:
+        if self._err is not None:
+            raise self._err
+        self._q.put((path, rgb8))
+
+    def close(self) -> None:
+        self._q.put(None)
+        self._t.join()
+        if self._err is not None:
+            raise self._err
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -82,3 +82,4 @@ def test_axis_parallel_primary_rays(gpu):
     xml = scenes.cfg2_hw3(n=12, width=33, height=33).replace("<Gaze>0 -0.62 -1</Gaze>", "<Gaze>0 -1 0</Gaze>") \
         .replace("<Up>0 1 0</Up>", "<Up>0 0 -1</Up>")
     _check(xml, "hw3")
+
