@@ -235,6 +235,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_ppm_get_hit_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, P(C.c_int64)]),
         "b200rt_scene_stream": (C.c_void_p, [C.c_void_p]),
         "b200rt_scene_bytes": (C.c_uint64, [C.c_void_p]),
+        "b200rt_debug_leaf": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_int]),
         "b200rt_scene_desc_save": (C.c_int, [C.POINTER(SceneDesc), C.c_char_p]),
         "b200rt_scene_desc_load": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(SceneDesc))]),
         "b200rt_scene_desc_free": (None, [C.POINTER(SceneDesc)]),

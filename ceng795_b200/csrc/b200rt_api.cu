@@ -992,6 +992,60 @@ int b200rt_measure_read_bandwidth(int device, uint64_t bytes, int iters, double*
   return B200RT_OK;
 }
 
+// Leaf functions of the device path on caller-supplied inputs (tests/test_leaf_vectors.py feeds the known-answer
+// vectors produced by the reference's own functions).
+__global__ void k_debug_leaf(int which, DScene S, b200rt_texture T, b200rt_brdf B, const float* in, int rows, int n_in,
+                             float* out, int n_out) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < rows; k += gridDim.x * blockDim.x) {
+    const float* r = in + (size_t)k * n_in;
+    float* o = out + (size_t)k * n_out;
+    if (which == 0) {          // Bounding_box::intersect: the exact gate and the filtered gate must take the same decision
+      const v3 org = ld3(r + 6), dir = ld3(r + 9);
+      float e0 = 0.f, e1 = 0.f;
+      o[0] = box_gate_exact(org, dir, r[0], r[1], r[2], r[3], r[4], r[5], S.isect_eps, &e0) ? 1.0f : 0.0f;
+      const RayCtx rc = make_ray(org, dir, S.isect_eps);
+      o[1] = box_gate(rc, r[0], r[1], r[2], r[3], r[4], r[5], S.isect_eps, &e1) ? 1.0f : 0.0f;
+    } else if (which == 1) {   // BRDF::get_reflectance
+      const v3 f = brdf_eval7(B, ld3(r), ld3(r + 3), ld3(r + 6), ld3(r + 9), ld3(r + 12));
+      o[0] = f.x; o[1] = f.y; o[2] = f.z;
+    } else if (which == 2) {   // Texture::get_color_at
+      const v3 c = tex_color7(S, T, r[0], r[1]);
+      o[0] = c.x; o[1] = c.y; o[2] = c.z;
+    } else {                   // Perlin_noise::get_value_at
+      o[0] = perlin_value7(T, ld3(r));
+    }
+  }
+}
+
+int b200rt_debug_leaf(int device, int which, const b200rt_texture* tex, const float* texels, int64_t n_texels,
+                      const b200rt_brdf* brdf, const float* in, int rows, int n_in, float* out, int n_out) {
+  if (which < 0 || which > 3 || !in || !out || rows <= 0 || n_in <= 0 || n_out <= 0) return B200RT_E_INVALID;
+  CK(cudaSetDevice(device));
+  DScene S;
+  memset(&S, 0, sizeof(S));
+  S.isect_eps = 0.000001f;
+  b200rt_texture T;
+  memset(&T, 0, sizeof(T));
+  if (tex) T = *tex;
+  b200rt_brdf B;
+  memset(&B, 0, sizeof(B));
+  if (brdf) B = *brdf;
+  float *d_tex = nullptr, *d_in = nullptr, *d_out = nullptr;
+  if (texels && n_texels > 0) {
+    CK(cudaMalloc((void**)&d_tex, (size_t)n_texels * 4));
+    CK(cudaMemcpy(d_tex, texels, (size_t)n_texels * 4, cudaMemcpyHostToDevice));
+    S.texels = d_tex;
+  }
+  CK(cudaMalloc((void**)&d_in, (size_t)rows * n_in * 4));
+  CK(cudaMalloc((void**)&d_out, (size_t)rows * n_out * 4));
+  CK(cudaMemcpy(d_in, in, (size_t)rows * n_in * 4, cudaMemcpyHostToDevice));
+  k_debug_leaf<<<(rows + 127) / 128, 128>>>(which, S, T, B, d_in, rows, n_in, d_out, n_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, d_out, (size_t)rows * n_out * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_tex); cudaFree(d_in); cudaFree(d_out);
+  return B200RT_OK;
+}
+
 uint64_t b200rt_scene_bytes(b200rt_scene* sc) { return sc ? (uint64_t)sc->scene_bytes : 0; }
 
 int b200rt_render_device(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, float** d_rgbw_out,

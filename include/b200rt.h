@@ -429,6 +429,13 @@ int b200rt_tonemap_photographic(b200rt_scene*, int camera_index, float image_key
  * 7 rec4(f4) 8 final_c(f4) 9 kd(f4) 10 pixel(u32) 11 key(u32) 12 hit_b(i32x2) 13 rec3(u32). */
 int b200rt_debug_pool(b200rt_scene*, int field, void* out, int64_t count);
 
+/* Test hook: the device's leaf functions on caller-supplied rows (host pointers).  which: 0 Bounding_box::intersect
+ * (in 12: min, max, o, d; out 2: decision of the exact gate, of the filtered gate), 1 BRDF::get_reflectance (in 15:
+ * normal, kd, ks, w_i, w_o; out 3), 2 Texture::get_color_at (in 2: u, v; out 3), 3 Perlin_noise::get_value_at (in 3;
+ * out 1).  tests/test_leaf_vectors.py runs the reference's own known-answer vectors through it. */
+int b200rt_debug_leaf(int device, int which, const b200rt_texture* tex, const float* texels, int64_t n_texels,
+                      const b200rt_brdf* brdf, const float* in, int rows, int n_in, float* out, int n_out);
+
 /* The CUDA stream (cudaStream_t) every launch of this scene is issued on, so a
  * caller can bracket calls with its own events. */
 void* b200rt_scene_stream(b200rt_scene*);

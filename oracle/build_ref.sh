@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm probe)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -53,6 +53,18 @@ build_tree_driver() { # name dir : the tree's objects except main.cpp + our floa
   $CXX -pthread "${objs[@]}" -o "$OUT/${name}_raytracer"
   echo "built $OUT/${name}_raytracer"
 }
+build_probe() { # leaf known-answer probe: HW7's objects except main.cpp + oracle/ref_probe.cpp
+  local dir="$REF/HW7" objdir="$OUT/obj_hw7"
+  [ -d "$objdir" ] || build_tree hw7 "$dir"
+  local objs=()
+  for f in "$dir"/src/*.cpp; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    objs+=("$objdir/$(basename "$f" .cpp).o")
+  done
+  $CXX $FLAGS -fno-access-control -I"$dir/include" -c "$HERE/ref_probe.cpp" -o "$objdir/ref_probe.o"
+  $CXX -pthread "${objs[@]}" "$objdir/ref_probe.o" -o "$OUT/ref_probe"
+  echo "built $OUT/ref_probe"
+}
 for t in "${TREES[@]}"; do
   case "$t" in
     hw1) build_flat hw1 "$REF/HW1" -I"$HERE/shim" ;;
@@ -65,6 +77,7 @@ for t in "${TREES[@]}"; do
     hw3f) build_tree_driver hw3f "$REF/HW3" ;;   # float-dump twins of trees whose own main writes 8-bit PNGs:
     hw4f) build_tree_driver hw4f "$REF/HW4" ;;   # they pin the oracle at float level (tests/test_oracle_golden.py)
     hw7f) build_tree_driver hw7f "$REF/HW7" ;;
+    probe) build_probe ;;
     ppm) build_tree ppm "$REF/PPM" -DNDEBUG ;;
     *) echo "unknown tree $t" >&2; exit 2 ;;
   esac

@@ -58,6 +58,12 @@ def load():
         _lib.oracle_box_intersect.argtypes = [C.c_void_p] * 4 + [C.c_float]
         _lib.oracle_tri_intersect.restype = C.c_int
         _lib.oracle_tri_intersect.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_float, C.c_void_p]
+        _lib.oracle_brdf_eval.restype = None
+        _lib.oracle_brdf_eval.argtypes = [C.c_int, C.c_float, C.c_int, C.c_float] + [C.c_void_p] * 6
+        _lib.oracle_tex_color.restype = None
+        _lib.oracle_tex_color.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        _lib.oracle_perlin_value.restype = C.c_float
+        _lib.oracle_perlin_value.argtypes = [C.c_void_p, C.c_void_p]
     return _lib
 
 

@@ -1723,3 +1723,18 @@ float oracle_box_intersect(const float* mn, const float* mx, const float* o, con
 int oracle_tri_intersect(const float* g12, const float* o, const float* dd, int mode, float eps, float* out3) {
   return tri_core(g12, ld(o), ld(dd), mode, eps, out3, out3 + 1, out3 + 2);
 }
+/* BRDF::get_reflectance, Texture::get_color_at, Perlin_noise::get_value_at (tests/test_leaf_vectors.py) */
+void oracle_brdf_eval(int kind, float exponent, int normalized, float refractive_index, const float* n, const float* kd,
+                      const float* ks, const float* wi, const float* wo, float* out3) {
+  b200rt_brdf B; memset(&B, 0, sizeof(B));
+  B.kind = kind; B.exponent = exponent; B.normalized = normalized; B.refractive_index = refractive_index;
+  const v3 f = brdf_eval(&B, ld(n), ld(kd), ld(ks), ld(wi), ld(wo));
+  out3[0] = f.x; out3[1] = f.y; out3[2] = f.z;
+}
+void oracle_tex_color(const b200rt_texture* T, const float* texels, float u, float v, float* out3) {
+  B200SceneDesc d; memset(&d, 0, sizeof(d));
+  d.texels = texels;
+  const v3 c = tex_color(&d, T, u, v);
+  out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
+}
+float oracle_perlin_value(const b200rt_texture* T, const float* pos) { return perlin_value(T, ld(pos)); }

@@ -1,0 +1,146 @@
+// TEST INFRASTRUCTURE ONLY — known-answer vectors for the leaf functions of the hot path.
+// Compiled by oracle/build_ref.sh (-fno-access-control) against the UNMODIFIED objects of the HW7 tree, it calls the
+// reference's own functions on seeded inputs and writes inputs and outputs to one file; tests/test_leaf_vectors.py
+// feeds the same inputs to the oracle's hooks and demands the same bits.
+//   ref_probe <out.bin> <asset_dir>
+// File: repeated { char name[24]; int32 rows, n_in, n_out; float32 rows*(n_in+n_out) }.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "Blinn_phong_BRDF.h"
+#include "Bounding_box.h"
+#include "Hit_data.h"
+#include "Modified_blinn_phong_BRDF.h"
+#include "Modified_phong_BRDF.h"
+#include "Perlin_noise.h"
+#include "Phong_BRDF.h"
+#include "Ray.h"
+#include "Texture.h"
+#include "Torrance_sparrow_BRDF.h"
+
+namespace {
+struct Lcg {                                   // our own generator: the vectors must not depend on libstdc++'s <random>
+  uint64_t s;
+  explicit Lcg(uint64_t seed) : s(seed * 2862933555777941757ull + 3037000493ull) {}
+  float u01() {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    return (float)((s >> 40) & 0xFFFFFF) * (1.0f / 16777216.0f);
+  }
+  float range(float a, float b) { return a + (b - a) * u01(); }
+};
+std::FILE* g_out;
+void section(const char* name, int rows, int n_in, int n_out, const std::vector<float>& data) {
+  char nm[24] = {0};
+  std::strncpy(nm, name, 23);
+  const int32_t hdr[3] = {rows, n_in, n_out};
+  std::fwrite(nm, 24, 1, g_out);
+  std::fwrite(hdr, sizeof(hdr), 1, g_out);
+  std::fwrite(data.data(), sizeof(float), data.size(), g_out);
+}
+Vector3 unit(Lcg& r) {
+  Vector3 v(r.range(-1, 1), r.range(-1, 1), r.range(-1, 1));
+  return v.normalize();
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 1;
+  g_out = std::fopen(argv[1], "wb");
+  if (!g_out) return 2;
+  const std::string assets = argv[2];
+  {  // Bounding_box::intersect — HW7/src/bounding_box.cpp:19-39
+    Lcg r(11);
+    std::vector<float> d;
+    const int rows = 2048;
+    for (int k = 0; k < rows; k++) {
+      Vector3 a(r.range(-3, 3), r.range(-3, 3), r.range(-3, 3)), b(r.range(-3, 3), r.range(-3, 3), r.range(-3, 3));
+      Vector3 mn(std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z));
+      Vector3 mx(std::max(a.x, b.x), std::max(a.y, b.y), std::max(a.z, b.z));
+      Vector3 o(r.range(-5, 5), r.range(-5, 5), r.range(-5, 5));
+      Vector3 dir = unit(r);
+      if (k % 8 == 1) dir.x = 0.0f;                       // axis-parallel: the |d| < 1e-6 skip
+      if (k % 8 == 2) { dir.y = 5e-7f; }
+      if (k % 8 == 3) { dir.x = 0.0f; dir.z = -0.0f; }
+      if (k % 16 == 4) o = (mn + mx) / 2.0f;             // origin inside the box
+      if (k % 16 == 5) dir = dir * 37.5f;                 // un-normalised direction (instances)
+      const float t = Bounding_box(mn, mx).intersect(Ray(o, dir, r_primary));
+      const float row[13] = {mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, o.x, o.y, o.z, dir.x, dir.y, dir.z, t};
+      d.insert(d.end(), row, row + 13);
+    }
+    section("box", rows, 12, 1, d);
+  }
+  {  // BRDF::get_reflectance x5 — HW7/src/*_BRDF.cpp
+    Phong_BRDF b0(23.0f);
+    Modified_phong_BRDF b1(31.5f, true), b1n(12.0f, false);
+    Blinn_phong_BRDF b2(40.0f);
+    Modified_blinn_phong_BRDF b3(50.0f, true), b3n(7.0f, false);
+    Torrance_sparrow_BRDF b4(60.0f, 2.1f);
+    const BRDF* all[] = {&b0, &b1, &b1n, &b2, &b3, &b3n, &b4};
+    const char* names[] = {"brdf0_e23", "brdf1_e31.5_n1", "brdf1_e12_n0", "brdf2_e40", "brdf3_e50_n1", "brdf3_e7_n0",
+                           "brdf4_e60_r2.1"};
+    for (int q = 0; q < 7; q++) {
+      Lcg r(100 + q);
+      std::vector<float> d;
+      const int rows = 1024;
+      for (int k = 0; k < rows; k++) {
+        Hit_data h;
+        h.normal = unit(r);
+        Vector3 wi = unit(r), wo = unit(r);
+        if (k % 4 != 0 && h.normal.dot(wi) < 0) wi = -wi;   // mostly the lit hemisphere, some below it
+        if (k % 3 != 0 && h.normal.dot(wo) < 0) wo = -wo;
+        if (k % 64 == 7) wi = h.normal;                       // cos = 1 (or a hair above it)
+        const Vector3 kd(r.u01(), r.u01(), r.u01()), ks(r.u01(), r.u01(), r.u01());
+        const Vector3 f = all[q]->get_reflectance(h, kd, ks, wi, wo);
+        const float row[18] = {h.normal.x, h.normal.y, h.normal.z, kd.x, kd.y, kd.z, ks.x, ks.y, ks.z,
+                               wi.x, wi.y, wi.z, wo.x, wo.y, wo.z, f.x, f.y, f.z};
+        d.insert(d.end(), row, row + 18);
+      }
+      section(names[q], rows, 15, 3, d);
+    }
+  }
+  {  // Texture::get_color_at, all four interpolation x appearance combinations — HW7/src/Texture.cpp:66-143
+    const char* interp[] = {"nearest", "bilinear"};
+    const char* app[] = {"repeat", "clamp"};
+    for (int a = 0; a < 2; a++)
+      for (int b = 0; b < 2; b++) {
+        Texture T(assets + "/tex_checker.png", interp[a], "replace_kd", app[b], 255.0f, 1.0f, false, 1.0f, false);
+        Lcg r(200 + 2 * a + b);
+        std::vector<float> d;
+        const int rows = 2048;
+        for (int k = 0; k < rows; k++) {
+          float u = r.range(-1.5f, 2.5f), v = r.range(-1.5f, 2.5f);
+          if (k % 32 == 0) u = 1.0f;
+          if (k % 32 == 1) v = 1.0f;
+          if (k % 32 == 2) { u = 0.0f; v = 0.0f; }
+          if (k % 32 == 3) { u = 0.999999f; v = 0.999999f; }
+          const Vector3 c = T.get_color_at(u, v);
+          const float row[5] = {u, v, c.x, c.y, c.z};
+          d.insert(d.end(), row, row + 5);
+        }
+        section((std::string("tex_") + interp[a] + "_" + app[b]).c_str(), rows, 2, 3, d);
+      }
+  }
+  {  // Perlin_noise::get_value_at with a FIXED table (the constructor shuffles it from the clock) — Perlin_noise.cpp:23-62
+    const int perm[16] = {11, 3, 7, 0, 14, 9, 2, 13, 5, 8, 1, 15, 6, 12, 4, 10};
+    const char* app[] = {"vein", "patch"};
+    for (int a = 0; a < 2; a++) {
+      Perlin_noise P(app[a], 3.5f);
+      P.p_.assign(perm, perm + 16);                          // -fno-access-control
+      Lcg r(300 + a);
+      std::vector<float> d;
+      const int rows = 2048;
+      for (int k = 0; k < rows; k++) {
+        const Vector3 p(r.range(-6, 6), r.range(-6, 6), r.range(-6, 6));
+        const float v = P.get_value_at(p);
+        const float row[4] = {p.x, p.y, p.z, v};
+        d.insert(d.end(), row, row + 4);
+      }
+      section((std::string("perlin_") + app[a]).c_str(), rows, 3, 1, d);
+    }
+  }
+  std::fclose(g_out);
+  return 0;
+}

@@ -1,0 +1,183 @@
+"""Known-answer vectors of the reference's OWN leaf functions, against the oracle's restatement
+of each: Bounding_box::intersect, the five BRDF::get_reflectance, Texture::get_color_at in its four interpolation x
+appearance combinations, Perlin_noise::get_value_at with a fixed permutation table.  The vectors were produced by
+oracle/_ref/ref_probe — HW7's unmodified objects linked with oracle/ref_probe.cpp (tests/golden/make_leaf_vectors.py) —
+and the oracle has to return the same BITS (the BRDFs go through powf: same glibc on both sides)."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from ceng795_b200 import _lib, scene
+from oracle import cpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _sections():
+    out = {}
+    blob = open(os.path.join(GOLDEN, "leaf_vectors.bin"), "rb").read()
+    pos = 0
+    while pos < len(blob):
+        name = blob[pos:pos + 24].split(b"\0")[0].decode()
+        rows, n_in, n_out = struct.unpack_from("<iii", blob, pos + 24)
+        pos += 36
+        a = np.frombuffer(blob, np.float32, rows * (n_in + n_out), pos).reshape(rows, n_in + n_out).copy()
+        pos += a.nbytes
+        out[name] = (a[:, :n_in].copy(), a[:, n_in:].copy())
+    return out
+
+
+SECTIONS = _sections()
+
+
+def _same_bits(got, want):
+    got, want = np.asarray(got, np.float32), np.asarray(want, np.float32)
+    both_nan = np.isnan(got) & np.isnan(want)
+    return (got.view(np.uint32) == want.view(np.uint32)) | both_nan
+
+
+def test_sections_present():
+    assert {"box", "brdf0_e23", "brdf4_e60_r2.1", "tex_nearest_repeat", "tex_bilinear_clamp", "perlin_vein",
+            "perlin_patch"} <= set(SECTIONS)
+    assert sum(len(v[0]) for v in SECTIONS.values()) > 20000
+
+
+def test_bounding_box_intersect():
+    L = cpu.load()
+    x, want = SECTIONS["box"]
+    got = np.array([L.oracle_box_intersect(r[0:3].ctypes.data, r[3:6].ctypes.data, r[6:9].ctypes.data,
+                                           r[9:12].ctypes.data, C.c_float(1e-6)) for r in np.ascontiguousarray(x)], np.float32)
+    assert _same_bits(got, want[:, 0]).all(), int((~_same_bits(got, want[:, 0])).sum())
+    assert np.isinf(want).any() and (want > 0).any()      # misses and hits are both in the set
+
+
+BRDFS = {"brdf0_e23": (_lib.BRDF_PHONG, 23.0, 0, 1.0), "brdf1_e31.5_n1": (_lib.BRDF_MODIFIED_PHONG, 31.5, 1, 1.0),
+         "brdf1_e12_n0": (_lib.BRDF_MODIFIED_PHONG, 12.0, 0, 1.0), "brdf2_e40": (_lib.BRDF_BLINN_PHONG, 40.0, 0, 1.0),
+         "brdf3_e50_n1": (_lib.BRDF_MODIFIED_BLINN_PHONG, 50.0, 1, 1.0),
+         "brdf3_e7_n0": (_lib.BRDF_MODIFIED_BLINN_PHONG, 7.0, 0, 1.0),
+         "brdf4_e60_r2.1": (_lib.BRDF_TORRANCE_SPARROW, 60.0, 0, 2.1)}
+
+
+@pytest.mark.parametrize("name", sorted(BRDFS))
+def test_brdf_get_reflectance(name):
+    L = cpu.load()
+    kind, e, norm, ri = BRDFS[name]
+    x, want = SECTIONS[name]
+    got = np.zeros_like(want)
+    for k, r in enumerate(np.ascontiguousarray(x)):
+        L.oracle_brdf_eval(kind, e, norm, ri, r[0:3].ctypes.data, r[3:6].ctypes.data, r[6:9].ctypes.data,
+                           r[9:12].ctypes.data, r[12:15].ctypes.data, got[k].ctypes.data)
+    ok = _same_bits(got, want)
+    assert ok.all(), (int((~ok).sum()), got[~ok.all(1)][:3], want[~ok.all(1)][:3])
+    assert (want == 0).all(1).any() and (want > 0).any()   # below-horizon zeros and lit values
+
+
+@pytest.mark.parametrize("interp", ["nearest", "bilinear"])
+@pytest.mark.parametrize("appearance", ["repeat", "clamp"])
+def test_texture_get_color_at(interp, appearance):
+    L = cpu.load()
+    texels, w, h = scene._load_image_texels(os.path.join(GOLDEN, "assets", "tex_checker.png"), False)
+    T = _lib.Texture()
+    T.kind = _lib.TEX_IMAGE
+    T.interp = _lib.TEX_NEAREST if interp == "nearest" else _lib.TEX_BILINEAR
+    T.appearance = _lib.TEX_REPEAT if appearance == "repeat" else _lib.TEX_CLAMP
+    T.decal = _lib.TEX_REPLACE_KD
+    T.normalizer = 255.0; T.scaling = 1.0; T.bump_multiplier = 1.0
+    T.width = w; T.height = h; T.texel_offset = 0
+    x, want = SECTIONS[f"tex_{interp}_{appearance}"]
+    got = np.zeros_like(want)
+    for k, r in enumerate(x):
+        L.oracle_tex_color(C.byref(T), texels.ctypes.data, C.c_float(r[0]), C.c_float(r[1]), got[k].ctypes.data)
+    ok = _same_bits(got, want).all(1)
+    # the clamped bilinear lookup of the reference reads one row / column past the image at u = 1 or v = 1
+    # (undefined behaviour there; the restatement defines those taps as 0)
+    edge = (np.clip(x, 0, 1) >= 1.0).any(1) if appearance == "clamp" and interp == "bilinear" else np.zeros(len(x), bool)
+    assert ok[~edge].all(), (int((~ok[~edge]).sum()), x[~ok & ~edge][:4], got[~ok & ~edge][:4], want[~ok & ~edge][:4])
+
+
+@pytest.mark.parametrize("appearance", ["vein", "patch"])
+def test_perlin_get_value_at(appearance):
+    L = cpu.load()
+    T = _lib.Texture()
+    T.kind = _lib.TEX_PERLIN
+    T.appearance = _lib.TEX_VEIN if appearance == "vein" else _lib.TEX_PATCH
+    T.scaling = 3.5
+    T.perm = (C.c_int32 * 16)(11, 3, 7, 0, 14, 9, 2, 13, 5, 8, 1, 15, 6, 12, 4, 10)
+    x, want = SECTIONS[f"perlin_{appearance}"]
+    got = np.array([L.oracle_perlin_value(C.byref(T), r.ctypes.data) for r in np.ascontiguousarray(x)], np.float32)
+    ok = _same_bits(got, want[:, 0])
+    assert ok.all(), (int((~ok).sum()), got[~ok][:4], want[~ok, 0][:4])
+
+
+# ---------------------------------------------------------------------------- the device's leaf functions
+def _device_leaf(which, x, n_out, tex=None, texels=None, brdf=None):
+    L = _lib.load()
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros((len(x), n_out), np.float32)
+    _lib.check(L.b200rt_debug_leaf(0, which, C.byref(tex) if tex is not None else None,
+                                   texels.ctypes.data if texels is not None else None,
+                                   0 if texels is None else texels.size, C.byref(brdf) if brdf is not None else None,
+                                   x.ctypes.data, len(x), x.shape[1], out.ctypes.data, n_out), "b200rt_debug_leaf")
+    return out
+
+
+@pytest.mark.gpu
+def test_device_box_gates_take_the_references_decision(gpu):
+    x, want = SECTIONS["box"]
+    t = want[:, 0]
+    ref_pass = ~((t < 0) | np.isinf(t))          # BVH::intersect: `bbox_t < 0 || bbox_t == inf` is a miss
+    got = _device_leaf(0, x, 2)
+    assert np.array_equal(got[:, 0] > 0, ref_pass)     # division-exact gate
+    assert np.array_equal(got[:, 1] > 0, ref_pass)     # filtered reciprocal gate with exact fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(BRDFS))
+def test_device_brdf(gpu, name):
+    kind, e, norm, ri = BRDFS[name]
+    B = _lib.Brdf()
+    B.kind = kind; B.exponent = e; B.normalized = norm; B.refractive_index = ri
+    x, want = SECTIONS[name]
+    got = _device_leaf(1, x, 3, brdf=B)
+    rel = np.abs(got - want) / (np.abs(want) + 1e-6)
+    assert np.array_equal(got == 0, want == 0)         # the 0 < cos <= 1 window is decided identically
+    assert rel.max() < 2e-5, float(rel.max())          # CUDA powf against glibc powf
+    assert np.mean(_same_bits(got, want)) > 0.9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("interp", ["nearest", "bilinear"])
+@pytest.mark.parametrize("appearance", ["repeat", "clamp"])
+def test_device_texture(gpu, interp, appearance):
+    texels, w, h = scene._load_image_texels(os.path.join(GOLDEN, "assets", "tex_checker.png"), False)
+    T = _lib.Texture()
+    T.kind = _lib.TEX_IMAGE
+    T.interp = _lib.TEX_NEAREST if interp == "nearest" else _lib.TEX_BILINEAR
+    T.appearance = _lib.TEX_REPEAT if appearance == "repeat" else _lib.TEX_CLAMP
+    T.decal = _lib.TEX_REPLACE_KD
+    T.normalizer = 255.0; T.scaling = 1.0; T.bump_multiplier = 1.0
+    T.width = w; T.height = h; T.texel_offset = 0
+    x, want = SECTIONS[f"tex_{interp}_{appearance}"]
+    got = _device_leaf(2, x, 3, tex=T, texels=texels)
+    ok = _same_bits(got, want).all(1)
+    edge = (np.clip(x, 0, 1) >= 1.0).any(1) if appearance == "clamp" and interp == "bilinear" else np.zeros(len(x), bool)
+    assert ok[~edge].all(), int((~ok[~edge]).sum())    # + - * only: bit-exact
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("appearance", ["vein", "patch"])
+def test_device_perlin(gpu, appearance):
+    T = _lib.Texture()
+    T.kind = _lib.TEX_PERLIN
+    T.appearance = _lib.TEX_VEIN if appearance == "vein" else _lib.TEX_PATCH
+    T.scaling = 3.5
+    T.perm = (C.c_int32 * 16)(11, 3, 7, 0, 14, 9, 2, 13, 5, 8, 1, 15, 6, 12, 4, 10)
+    x, want = SECTIONS[f"perlin_{appearance}"]
+    got = _device_leaf(3, x, 1, tex=T)[:, 0]
+    # the quintic weights are products in double instead of pow: equal to the last float bit
+    # except for a handful of values one ulp away
+    assert np.abs(got - want[:, 0]).max() < 1e-6
+    assert np.mean(_same_bits(got, want[:, 0])) > 0.995
