@@ -12,6 +12,7 @@
 
 #include "fast_bvh.h"
 #include "ppm_kernels.cuh"
+#include "rt_hw1_fast.cuh"
 #include "tonemap_kernels.cuh"
 
 extern "C" void b200rt_internal_set_error(const char* msg);
@@ -160,7 +161,10 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
   for (int d = 0; d <= max_d; d++) {
     k_next_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->d_counters);
     (*launches)++;
-    if (hw1) {
+    const bool hw1_fast = hw1 && S.hw1_fast_root != B200RT_REF_NONE && !exact;
+    if (hw1_fast) {
+      k_trace_hw1_fast<false><<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    } else if (hw1) {
       k_extend_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
     } else if (S.semantics >= B200RT_SEM_HW4) {
       if (exact) k_extend<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
@@ -181,7 +185,9 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     k_clamp_shadow_count<<<1, 1, 0, st>>>(sc->Q, sc->d_counters);
     (*launches) += 2;
     tm.mark(ST_SHADE);
-    if (hw1) {
+    if (hw1_fast) {
+      k_trace_hw1_fast<true><<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    } else if (hw1) {
       k_shadow_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
     } else if (S.semantics >= B200RT_SEM_HW4) {
       if (exact) k_shadow<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
@@ -817,6 +823,31 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
       memcpy(&own_geom[12 * k], d->tri_geom + 12 * (size_t)own_ref[k], 48);
     fast_nodes = own_nodes.data(); fast_geom = own_geom.data(); fast_ref = own_ref.data();
     meshes = own_meshes.data();
+    n_fast_nodes = (int)own_nodes.size(); n_fast_tris = (int)own_ref.size();
+  }
+  S.hw1_fast_root = B200RT_REF_NONE;
+  if (d->semantics == B200RT_SEM_HW1 && d->n_tris >= 2 && !getenv("B200RT_HW1_BRUTE")) {
+    // HW1 has no BVH of its own (the reference tests every primitive): one SAH tree over all triangles, walked by
+    // k_trace_hw1_fast, which replays HW1's order-dependent rule on the near-tie set (rt_hw1_fast.cuh)
+    std::vector<float> tb((size_t)d->n_tris * 6);
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int k = 0; k < d->n_tris; k++) {
+      const float* g = d->tri_geom + 12 * (size_t)k;
+      for (int a = 0; a < 3; a++) {
+        const float v0 = g[a], v1 = g[a] - g[3 + a], v2 = g[a] - g[6 + a];
+        tb[6 * (size_t)k + a] = fminf(v0, fminf(v1, v2));
+        tb[6 * (size_t)k + 3 + a] = fmaxf(v0, fmaxf(v1, v2));
+        lo[a] = fminf(lo[a], tb[6 * (size_t)k + a]); hi[a] = fmaxf(hi[a], tb[6 * (size_t)k + 3 + a]);
+      }
+    }
+    float ext = 0.f;
+    for (int a = 0; a < 3; a++) ext = fmaxf(ext, fmaxf(hi[a] - lo[a], fmaxf(fabsf(lo[a]), fabsf(hi[a]))));
+    const float grow = ext * (3e-5f + 4.0f * d->isect_eps) + 1e-30f;
+    own_nodes.clear(); own_ref.clear();
+    S.hw1_fast_root = b200rt_fast::build(tb.data(), d->n_tris, 0, grow, own_nodes, own_ref);
+    own_geom.resize(own_ref.size() * 12);
+    for (size_t k = 0; k < own_ref.size(); k++) memcpy(&own_geom[12 * k], d->tri_geom + 12 * (size_t)own_ref[k], 48);
+    fast_nodes = own_nodes.data(); fast_geom = own_geom.data(); fast_ref = own_ref.data();
     n_fast_nodes = (int)own_nodes.size(); n_fast_tris = (int)own_ref.size();
   }
   UP(S.fast_nodes, fast_nodes, n_fast_nodes, b200rt_bvh_node);

@@ -88,6 +88,7 @@ struct DScene {
   // top-level objects flattened with the reference's innermost gate of each: 2 x float4 per object
   // {min.xyz, as_float(ref)}, {max.xyz, as_float(1 if the object has a gate, 0 if it is entered unconditionally)}
   const float4* top_objs;
+  uint32_t hw1_fast_root;   // HW1: SAH tree over ALL triangles (rt_hw1_fast.cuh), or NONE
   int n_top;                // 0: walk the reference's top-level tree instead (more than RT_TOP_LINEAR_MAX objects)
   const float4* tris;       // 3 x float4 per triangle: v0|a1.x, a1.yz|a2.xy, a2.z|n
   const float4* fast_nodes; // SAH tree (csrc/fast_bvh.h), same 64-byte records
@@ -166,5 +167,5 @@ struct Counters {
   unsigned int overflow;   // pool / queue overflow flag
   unsigned int shadow_count;
   unsigned int work_extend, work_shadow;  // persistent-kernel work cursors
-  unsigned int pad;
+  unsigned int hw1_fallbacks;  // HW1 rays that took the brute-force loop (rt_hw1_fast.cuh)
 };

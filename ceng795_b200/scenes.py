@@ -483,3 +483,67 @@ def cfg3_hw3(n=362, width=1920, height=1080, spp=100, depth=3, seed=SEED, image_
             + _rows(allv, "%.9g") + "  </VertexData>\n  <Objects>\n"
             + '    <Mesh id="1" shadingMode="smooth">\n      <Material>1</Material>\n      <Faces>\n' + _rows(f + 1, "%d")
             + "      </Faces>\n    </Mesh>\n" + tri + sph + "  </Objects>\n</Scene>\n")
+
+
+def hw1_near_ties(width=96, height=72, layers=5, spacing=6e-7, seed=SEED, image_name="ties.png") -> str:
+    """HW1 dialect, built to make the ORDER of primitives matter: HW1 keeps a hit iff `t < best - 1e-6`, so stacks of
+    coplanar quads `spacing` apart (closer than 1e-6 in t), exact duplicates, quads listed back-to-front and
+    front-to-back, and spheres tangent to the stacks give rays whose answer depends on the order of the list
+    (rt_hw1_fast.cuh replays that order on the near-tie set; this scene is its test).  Every quad is a Mesh of its
+    own: HW1 walks meshes first, in file order, and gives every stand-alone Triangle the LAST mesh's material
+    (HW1/Scene.cpp:320; without any mesh it reads an uninitialised int, so there is always one here)."""
+    rng = np.random.default_rng(seed + 21)
+    verts = []
+    nv = 0
+
+    def push(v):
+        nonlocal nv
+        base = nv
+        verts.append(np.asarray(v, np.float32))
+        nv += len(v)
+        return base
+
+    mats = "".join(_material_xml(m + 1, rng.uniform(0.05, 0.2, 3), rng.uniform(0.2, 0.9, 3), rng.uniform(0.1, 0.6, 3),
+                                 20.0, np.full(3, 0.4) if m == 2 else None) for m in range(6))
+    mesh_xml = ""
+    mid = 1
+
+    def quad(z, x0, x1, y0, y1, mat):
+        nonlocal mesh_xml, mid
+        b = push([[x0, y0, z], [x1, y0, z], [x1, y1, z], [x0, y1, z]])
+        mesh_xml += (f'    <Mesh id="{mid}">\n      <Material>{mat}</Material>\n      <Faces>\n'
+                     f"{b + 1} {b + 2} {b + 3}\n{b + 1} {b + 3} {b + 4}\n      </Faces>\n    </Mesh>\n")
+        mid += 1
+
+    # stack A: back-to-front in the list (the farthest layer first), stack B: front-to-back, stack C: shuffled + duplicates
+    for k in range(layers):
+        quad(-2.0 - spacing * (layers - 1 - k), -2.6, -1.0, -1.0, 1.0, 1 + k % 6)
+    for k in range(layers):
+        quad(-2.0 - spacing * k, -0.8, 0.8, -1.0, 1.0, 1 + (k + 2) % 6)
+    order = rng.permutation(layers)
+    for k in order:
+        quad(-2.0 - spacing * float(k), 1.0, 2.6, -1.0, 1.0, 1 + int(k) % 6)
+        if k % 2 == 0:
+            quad(-2.0 - spacing * float(k), 1.0, 2.6, -1.0, 1.0, 1 + (int(k) + 3) % 6)   # exact duplicate
+    # far wall: two stand-alone triangles (they take the last mesh's material)
+    wb = push([[-5, -4, -6.0], [5, -4, -6.0], [5, 4, -6.0], [-5, 4, -6.0]])
+    tri_xml = "".join(f'    <Triangle id="{i + 1}">\n      <Material>4</Material>\n'
+                      f"      <Indices>{wb + t[0] + 1} {wb + t[1] + 1} {wb + t[2] + 1}</Indices>\n    </Triangle>\n"
+                      for i, t in enumerate(((0, 1, 2), (0, 2, 3))))
+    # spheres tangent to the stacks' front plane (t of the sphere within 1e-6 of the plane's around the tangent point)
+    cs = np.array([[-1.8, 0.4, -2.0 + 0.5], [0.0, -0.3, -2.0 + 0.35], [1.8, 0.2, -2.0 + 0.25 - 3e-7]], np.float32)
+    rs = [0.5, 0.35, 0.25]
+    cb = push(cs)
+    sph_xml = "".join(f'    <Sphere id="{i + 1}">\n      <Material>{1 + i}</Material>\n      <Center>{cb + i + 1}</Center>\n'
+                      f"      <Radius>{_f([rs[i]])}</Radius>\n    </Sphere>\n" for i in range(3))
+    allv = np.concatenate(verts, 0)
+    aspect = width / height
+    return ("<Scene>\n  <BackgroundColor>10 20 40</BackgroundColor>\n  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
+            "  <MaxRecursionDepth>2</MaxRecursionDepth>\n  <Cameras>\n    <Camera id=\"1\">\n"
+            "      <Position>0 0 3</Position>\n      <Gaze>0 0 -1</Gaze>\n      <Up>0 1 0</Up>\n"
+            f"      <NearPlane>{_f([-0.75 * aspect, 0.75 * aspect, -0.75, 0.75])}</NearPlane>\n      <NearDistance>1</NearDistance>\n"
+            f"      <ImageResolution>{width} {height}</ImageResolution>\n      <ImageName>{image_name}</ImageName>\n"
+            "    </Camera>\n  </Cameras>\n  <Lights>\n    <AmbientLight>25 25 25</AmbientLight>\n"
+            '    <PointLight id="1">\n      <Position>1 3 4</Position>\n      <Intensity>900 900 900</Intensity>\n    </PointLight>\n'
+            "  </Lights>\n  <Materials>\n" + mats + "  </Materials>\n  <VertexData>\n" + _rows(allv, "%.9g")
+            + "  </VertexData>\n  <Objects>\n" + mesh_xml + tri_xml + sph_xml + "  </Objects>\n</Scene>\n")

@@ -19,6 +19,9 @@ from oracle import cpu  # noqa: E402
 CASES = {
     "cfg1_hw1_96": ("hw1", "cfg1_hw1", dict(width=96, height=96)),
     "cfg1_hw1_depth0": ("hw1", "cfg1_hw1", dict(width=64, height=48, depth=0, n_spheres=12)),
+    # HW1's `t < best - 1e-6` makes the ORDER of near-tied primitives matter: stacks of coplanar quads 6e-7 apart,
+    # duplicates, tangent spheres (the device replays the order on the near-tie set, csrc/rt_hw1_fast.cuh)
+    "hw1_near_ties": ("hw1", "hw1_near_ties", dict(width=96, height=72)),
     "cfg2_hw3_n32": ("hw3", "cfg2_hw3", dict(n=32, width=160, height=90)),
     "cfg2_hw3_n48_smooth": ("hw3", "cfg2_hw3", dict(n=48, width=128, height=96, smooth=True, depth=3)),
     # HW2 tree: no instancing (MeshInstance elements are ignored by its loader), Mesh sits in the top BVH itself,

@@ -89,7 +89,36 @@ def test_hw56_multisample_matches_oracle_with_matched_sampling(gpu, tmp_path, tr
     assert np.sqrt(np.mean((a - b) ** 2)) < 0.02 * noise
 
 
-@pytest.mark.parametrize("name", ["cfg1_hw1_96", "cfg2_hw3_n32", "cfg2_hw3_n48_smooth", "cfg2_hw2_glass", "hw4_textured",
+def test_hw1_order_dependent_rule_through_the_tree(gpu):
+    """HW1 keeps a hit iff `t < best - 1e-6`: on stacks of coplanar quads 6e-7 apart the answer depends on the order
+    of the primitive list.  The SAH-tree path (rt_hw1_fast.cuh) has to give the brute-force kernel's and the oracle's
+    ids on every ray, and the scene has to be one where a plain closest-hit would NOT."""
+    xml = scenes.hw1_near_ties(width=160, height=120)
+    sc = scene.Scene(xml, "hw1")
+    _, o_ids, o_t, _ = cpu.render(sc.host, 0, want_image=False, want_ids=True)
+    fast_ids, fast_t = sc.primary_ids(0)
+    brute_ids, brute_t = sc.primary_ids(0, exact_traversal=1)
+    assert np.array_equal(brute_ids, o_ids) and np.array_equal(brute_t.view(np.uint32), o_t.view(np.uint32))
+    assert np.array_equal(fast_ids, o_ids), float(np.mean(np.all(fast_ids == o_ids, -1)))
+    assert np.array_equal(fast_t.view(np.uint32), o_t.view(np.uint32))
+    # stack A is listed back to front: HW1 does not end on its front layer (triangles 8, 9) everywhere
+    hit_a = np.isin(o_ids[..., 0], np.arange(0, 10))
+    assert hit_a.sum() > 500 and np.mean(np.isin(o_ids[..., 0][hit_a], (8, 9))) < 0.9
+    # secondary rays too: random rays from inside the scene
+    rng = np.random.default_rng(4)
+    n = 100_000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(-2.5, 2.5, (n, 3)); rays[:, 2] = rng.uniform(-1.5, 3.0, n)
+    dd = rng.normal(size=(n, 3)); dd[:, 2] = -np.abs(dd[:, 2]) * 3
+    rays[:, 4:7] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+    ids_f, t_f, _ = sc.trace_rays(rays, exact=False)
+    ids_b, t_b, _ = sc.trace_rays(rays, exact=True)
+    o_ids2, o_t2, _ = cpu.trace_rays(sc.host, rays)
+    assert np.array_equal(ids_b, o_ids2) and np.array_equal(ids_f, o_ids2)
+    assert np.array_equal(t_f.view(np.uint32), o_t2.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["cfg1_hw1_96", "hw1_near_ties", "cfg2_hw3_n32", "cfg2_hw3_n48_smooth", "cfg2_hw2_glass", "hw4_textured",
                                   "hw7_whitted_160"])
 def test_primary_hit_ids_bit_exact(gpu, name):
     tree, xml = scene_xml(name)
