@@ -89,6 +89,30 @@ def test_hw56_multisample_matches_oracle_with_matched_sampling(gpu, tmp_path, tr
     assert np.sqrt(np.mean((a - b) ** 2)) < 0.02 * noise
 
 
+@pytest.mark.parametrize("tree", ["hw2", "hw3", "hw4", "hw6", "hw7"])
+@pytest.mark.parametrize("spacing", [0.0, 6e-7])
+def test_ties_resolve_like_the_reference(gpu, tree, spacing):
+    """Exact and near ties (duplicate coplanar quads as separate top-level objects, shared edges inside a mesh, tangent
+    spheres): the SAH path, the exact path and the oracle (itself pinned to the binaries on this scene) agree on
+    every id and t bit."""
+    xml = scenes.hw1_near_ties(spacing=spacing, width=128, height=96)
+    sc = scene.Scene(xml, tree)
+    _, o_ids, o_t, _ = cpu.render(sc.host, 0, want_image=False, want_ids=True)
+    for exact in (0, 1):
+        ids, t = sc.primary_ids(0, exact_traversal=exact)
+        assert np.array_equal(ids, o_ids), (exact, float(np.mean(np.all(ids == o_ids, -1))))
+        assert np.array_equal(t.view(np.uint32), o_t.view(np.uint32))
+    rng = np.random.default_rng(9)
+    n = 50_000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(-2.5, 2.5, (n, 3)); rays[:, 2] = rng.uniform(-1.5, 3.0, n)
+    dd = rng.normal(size=(n, 3)); dd[:, 2] = -np.abs(dd[:, 2]) * 3
+    rays[:, 4:7] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+    ids_p, t_p, _ = sc.trace_rays(rays, exact=False)
+    o_ids2, o_t2, _ = cpu.trace_rays(sc.host, rays)
+    assert np.array_equal(ids_p, o_ids2) and np.array_equal(t_p.view(np.uint32), o_t2.view(np.uint32))
+
+
 def test_hw1_order_dependent_rule_through_the_tree(gpu):
     """HW1 keeps a hit iff `t < best - 1e-6`: on stacks of coplanar quads 6e-7 apart the answer depends on the order
     of the primitive list.  The SAH-tree path (rt_hw1_fast.cuh) has to give the brute-force kernel's and the oracle's

@@ -81,6 +81,21 @@ def test_oracle_matches_live_reference(tree, gen_kw):
     assert cmp["exact"] == 1.0, cmp
 
 
+@pytest.mark.parametrize("tree", ["hw2", "hw3", "hw7"])
+@pytest.mark.parametrize("spacing", [0.0, 6e-7])
+def test_oracle_tie_breaking_matches_live_reference(tree, spacing):
+    """Exact ties (duplicate coplanar quads, shared edges) and near ties across top-level objects: the BVH trees keep
+    the first hit in DFS order under `child.t < hit.t`; the restatement has to pick the same one everywhere."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.hw1_near_ties(spacing=spacing, width=128, height=96)
+    want = list(cpu.run_reference(tree, xml)["images"].values())[0]
+    hs = scene.HostScene(scene.parse_xml(xml, tree))
+    rgbw, _, _, _ = cpu.render(hs, 0)
+    assert image.compare_8bit(image.quantise(rgbw, hs.spec.semantics), want)["exact"] == 1.0
+
+
 def test_parse_time():
     assert cpu.parse_time_ms("4 seconds 790 milliseconds 898 microseconds") == pytest.approx(4790.898)
     assert cpu.parse_time_ms("1 minute 2 seconds 0 milliseconds 5 microseconds") == pytest.approx(62000.005)
