@@ -547,3 +547,89 @@ def hw1_near_ties(width=96, height=72, layers=5, spacing=6e-7, seed=SEED, image_
             '    <PointLight id="1">\n      <Position>1 3 4</Position>\n      <Intensity>900 900 900</Intensity>\n    </PointLight>\n'
             "  </Lights>\n  <Materials>\n" + mats + "  </Materials>\n  <VertexData>\n" + _rows(allv, "%.9g")
             + "  </VertexData>\n  <Objects>\n" + mesh_xml + tri_xml + sph_xml + "  </Objects>\n</Scene>\n")
+
+
+def fuzz_scene(seed, width=61, height=47, depth=3) -> str:
+    """HW3-dialect scene for differential testing against the reference binaries (HW3 / HW4 / HW5 / HW6 / HW7 all load
+    it): odd resolution and an axis-aligned camera (the centre ray is exactly (0,0,-1): the box test's skipped axes),
+    meshes under random Scaling / Rotation / Translation chains including NEGATIVE (mirroring) scales, instances with
+    and without resetTransform, transformed stand-alone triangles and spheres (non-uniform scale), zero-area and
+    edge-on triangles, a sphere around the camera, smooth and flat shading, mirror and glass, two point lights."""
+    rng = np.random.default_rng(1000 + seed)
+    verts = []
+    nv = 0
+
+    def push(v):
+        nonlocal nv
+        base = nv
+        verts.append(np.asarray(v, np.float32))
+        nv += len(v)
+        return base
+
+    mats = (_material_xml(1, [0.2, 0.2, 0.2], rng.uniform(0.2, 0.8, 3), rng.uniform(0.1, 0.5, 3), 12.0)
+            + _material_xml(2, [0.1, 0.15, 0.1], rng.uniform(0.2, 0.8, 3), rng.uniform(0.1, 0.5, 3), 40.0,
+                            mirror=[0.5, 0.5, 0.5])
+            + _material_xml(3, [0.05, 0.05, 0.05], [0.05, 0.05, 0.05], [0.2, 0.2, 0.2], 60.0,
+                            transparency=[0.9, 0.85, 0.95], refr=1.45)
+            + _material_xml(4, [0.25, 0.2, 0.15], rng.uniform(0.2, 0.8, 3), [0, 0, 0], 1.0)
+            + _material_xml(5, [0.15, 0.2, 0.25], [0, 0, 0], rng.uniform(0.1, 0.5, 3), 25.0))
+    n_xf = 6
+    xf = "  <Transformations>\n"
+    for k in range(n_xf):
+        s = rng.uniform(0.4, 1.4, 3) * rng.choice([1, 1, -1], 3)      # mirroring scales
+        xf += f'    <Scaling id="{k + 1}">{_f(s)}</Scaling>\n'
+        xf += f'    <Translation id="{k + 1}">{_f(rng.uniform(-2.0, 2.0, 3) * [1, 0.6, 1] + [0, 0, -4])}</Translation>\n'
+        xf += f'    <Rotation id="{k + 1}">{_f([rng.uniform(0, 360), *rng.normal(size=3)])}</Rotation>\n'
+    xf += "  </Transformations>\n"
+
+    def chain():
+        ops = []
+        for _ in range(int(rng.integers(1, 4))):
+            ops.append(f"{rng.choice(['s', 'r', 't'])}{int(rng.integers(1, n_xf + 1))}")
+        return " ".join(ops + [f"t{int(rng.integers(1, n_xf + 1))}"])
+
+    mesh_xml = ""
+    for m in range(3):
+        v, f = _uv_sphere((0, 0, 0), float(rng.uniform(0.5, 0.9)), 7 + m, 8 + m)
+        if m == 1:                                   # a zero-area triangle and an edge-on sliver in the mesh
+            f = np.concatenate([f, [[0, 0, 1], [2, 3, 3]]], 0)
+        b = push(v)
+        mesh_xml += (f'    <Mesh id="{m + 1}"' + (' shadingMode="smooth"' if m != 1 else "") + ">\n"
+                     f"      <Material>{1 + m}</Material>\n      <Transformations>{chain()}</Transformations>\n"
+                     f'      <Faces vertexOffset="{b}">\n' + _rows(f + 1, "%d") + "      </Faces>\n    </Mesh>\n")
+    inst = ""
+    for k in range(4):
+        inst += (f'    <MeshInstance id="{k + 1}" baseMeshId="{1 + k % 3}" resetTransform="{"true" if k % 2 else "false"}">\n'
+                 f"      <Material>{1 + int(rng.integers(0, 5))}</Material>\n"
+                 f"      <Transformations>{chain()}</Transformations>\n    </MeshInstance>\n")
+    # floor + back wall as stand-alone triangles, one of them transformed
+    R = 6.0
+    rb = push([[-R, -2.2, 2], [R, -2.2, 2], [R, -2.2, -10], [-R, -2.2, -10], [-R, 5, -9], [R, 5, -9], [R, -2.2, -9], [-R, -2.2, -9]])
+    tri_xml = ""
+    for i, t in enumerate(((0, 1, 2), (0, 2, 3), (7, 6, 5), (7, 5, 4))):
+        tx = f"      <Transformations>r{1 + i}</Transformations>\n" if i == 3 else ""
+        tri_xml += (f'    <Triangle id="{i + 1}">\n      <Material>{1 + (i % 2) * 3}</Material>\n{tx}'
+                    f"      <Indices>{rb + t[0] + 1} {rb + t[1] + 1} {rb + t[2] + 1}</Indices>\n    </Triangle>\n")
+    # spheres: plain, non-uniformly scaled, glass, and one AROUND the camera (t2 < 0 -> t1)
+    cs = np.array([[-1.5, 0.2, -3.5], [0, 0, 0], [1.2, -0.4, -2.6], [0.0, 0.0, 1.0]], np.float32)
+    cb = push(cs)
+    sph = ""
+    for i, (r, mat, tr) in enumerate(((0.7, 2, ""), (0.6, 1, chain()), (0.5, 3, ""), (2.5, 4, ""))):
+        tx = f"      <Transformations>{tr}</Transformations>\n" if tr else ""
+        sph += (f'    <Sphere id="{i + 1}">\n      <Material>{mat}</Material>\n{tx}      <Center>{cb + i + 1}</Center>\n'
+                f"      <Radius>{_f([r])}</Radius>\n    </Sphere>\n")
+    allv = np.concatenate(verts, 0)
+    aspect = width / height
+    return ("<Scene>\n  <BackgroundColor>12 18 30</BackgroundColor>\n  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
+            f"  <MaxRecursionDepth>{depth}</MaxRecursionDepth>\n  <Cameras>\n    <Camera id=\"1\">\n"
+            "      <Position>0 0 1</Position>\n      <Gaze>0 0 -1</Gaze>\n      <Up>0 1 0</Up>\n"
+            f"      <NearPlane>{_f([-0.8 * aspect, 0.8 * aspect, -0.8, 0.8])}</NearPlane>\n      <NearDistance>1</NearDistance>\n"
+            f"      <ImageResolution>{width} {height}</ImageResolution>\n      <NumSamples>1</NumSamples>\n"
+            "      <ImageName>fuzz.png</ImageName>\n    </Camera>\n  </Cameras>\n  <Lights>\n"
+            "    <AmbientLight>20 20 20</AmbientLight>\n"
+            f'    <PointLight id="1">\n      <Position>{_f(rng.uniform(-3, 3, 3) * [1, 0.3, 0.5] + [0, 3.5, 0])}</Position>\n'
+            "      <Intensity>2500 2400 2200</Intensity>\n    </PointLight>\n"
+            f'    <PointLight id="2">\n      <Position>{_f(rng.uniform(-2, 2, 3) + [0, 1, 0.5])}</Position>\n'
+            "      <Intensity>600 700 900</Intensity>\n    </PointLight>\n  </Lights>\n  <Materials>\n" + mats
+            + "  </Materials>\n" + xf + "  <VertexData>\n" + _rows(allv, "%.9g") + "  </VertexData>\n  <Objects>\n"
+            + mesh_xml + inst + tri_xml + sph + "  </Objects>\n</Scene>\n")

@@ -113,6 +113,25 @@ def test_ties_resolve_like_the_reference(gpu, tree, spacing):
     assert np.array_equal(ids_p, o_ids2) and np.array_equal(t_p.view(np.uint32), o_t2.view(np.uint32))
 
 
+@pytest.mark.parametrize("tree", ["hw3", "hw4", "hw6", "hw7"])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_fuzz_scenes_match_the_oracle(gpu, tree, seed):
+    """scenes.fuzz_scene (mirroring scales, transform chains, degenerate triangles, camera inside a sphere, axis-aligned
+    centre ray; the oracle is pinned to the binaries on these scenes): ids and t bit-equal on both device paths, equal
+    ray counts, images to 1 LSB."""
+    xml = scenes.fuzz_scene(seed)
+    sc = scene.Scene(xml, tree)
+    o_rgbw, o_ids, o_t, cnt = cpu.render(sc.host, 0, want_ids=True)
+    for exact in (0, 1):
+        ids, t = sc.primary_ids(0, exact_traversal=exact)
+        assert np.array_equal(ids, o_ids), (exact, float(np.mean(np.all(ids == o_ids, -1))))
+        assert np.array_equal(t.view(np.uint32), o_t.view(np.uint32))
+    rgbw, st = sc.render_image(0)
+    assert (st.rays_primary, st.rays_shadow, st.rays_secondary) == (cnt.rays_primary, cnt.rays_shadow, cnt.rays_secondary)
+    cmp = image.compare_8bit(image.quantise(rgbw, sc.semantics), image.quantise(o_rgbw, sc.semantics))
+    assert cmp["within1"] >= 0.999, cmp
+
+
 def test_hw1_order_dependent_rule_through_the_tree(gpu):
     """HW1 keeps a hit iff `t < best - 1e-6`: on stacks of coplanar quads 6e-7 apart the answer depends on the order
     of the primitive list.  The SAH-tree path (rt_hw1_fast.cuh) has to give the brute-force kernel's and the oracle's

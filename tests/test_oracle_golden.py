@@ -96,6 +96,28 @@ def test_oracle_tie_breaking_matches_live_reference(tree, spacing):
     assert image.compare_8bit(image.quantise(rgbw, hs.spec.semantics), want)["exact"] == 1.0
 
 
+@pytest.mark.parametrize("tree", ["hw3", "hw4", "hw5", "hw6", "hw7"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_fuzz_scenes_match_live_reference(tree, seed):
+    """Differential test on scenes built to be awkward (scenes.fuzz_scene: mirroring scales, transform chains,
+    resetTransform on and off, zero-area triangles, a sphere around the camera, an axis-aligned centre ray, mirror and
+    glass): PNG trees byte for byte, HW5 / HW6 float for float."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.fuzz_scene(seed)
+    res = cpu.run_reference(tree, xml)
+    hs = scene.HostScene(scene.parse_xml(xml, tree))
+    rgbw, _, _, _ = cpu.render(hs, 0)
+    if res["images"]:
+        cmp = image.compare_8bit(image.quantise(rgbw, hs.spec.semantics), list(res["images"].values())[0])
+        assert cmp["within1"] == 1.0 and (tree == "hw4" or cmp["exact"] == 1.0), cmp
+    else:
+        want = list(res["hdr"].values())[0]
+        got = rgbw[..., :3] / rgbw[..., 3:4]
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_parse_time():
     assert cpu.parse_time_ms("4 seconds 790 milliseconds 898 microseconds") == pytest.approx(4790.898)
     assert cpu.parse_time_ms("1 minute 2 seconds 0 milliseconds 5 microseconds") == pytest.approx(62000.005)
