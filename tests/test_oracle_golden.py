@@ -118,6 +118,30 @@ def test_oracle_fuzz_scenes_match_live_reference(tree, seed):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("seed", [0, 3, 5])
+def test_oracle_textured_scenes_match_live_reference_floats(tmp_path, seed):
+    """Randomised variants of the textured / BRDF scene (image textures in every mode, image bump, five BRDFs, spot and
+    directional lights, mirror, glass, rotated instances) against float dumps of four trees' own objects: HW5, HW6 and
+    HW7 to the last bit, HW4 to the ulp its racy splat order allows."""
+    for tree in ("hw4f", "hw5", "hw6", "hw7f"):
+        if not cpu.have_ref(tree):
+            pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=75, height=57, n=5 + seed % 5, depth=1 + seed % 4, seed=900 + seed,
+                           light_scale=1.0 + seed % 3, mesh_slices=(6 + seed % 4, 7 + seed % 3), image_name="o.png")
+    for tree in ("hw4f", "hw5", "hw6", "hw7f"):
+        sem = tree.rstrip("f")
+        want = list(cpu.run_reference(tree, xml, workdir=str(tmp_path))["hdr"].values())[0]
+        hs = scene.HostScene(scene.parse_xml(xml, sem, base_dir=str(tmp_path)))
+        rgbw, _, _, _ = cpu.render(hs, 0)
+        got = rgbw[..., :3] / rgbw[..., 3:4]
+        if sem == "hw4":
+            got = np.clip(got, 0, 255)          # HW4's Pixel::get_color clamps
+            assert np.max(np.abs(got - want) / (np.abs(want) + 1)) < 1e-6
+        else:
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), tree
+
+
 def test_parse_time():
     assert cpu.parse_time_ms("4 seconds 790 milliseconds 898 microseconds") == pytest.approx(4790.898)
     assert cpu.parse_time_ms("1 minute 2 seconds 0 milliseconds 5 microseconds") == pytest.approx(62000.005)
