@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw4f hw7f probe)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw4f hw7f probe ppmeye)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -65,6 +65,18 @@ build_probe() { # leaf known-answer probe: HW7's objects except main.cpp + oracl
   $CXX -pthread "${objs[@]}" "$objdir/ref_probe.o" -o "$OUT/ref_probe"
   echo "built $OUT/ref_probe"
 }
+build_ppm_eye() { # PPM's objects except main.cpp + oracle/ref_driver_ppm.cpp: eye pass + hash grid only
+  local dir="$REF/PPM" objdir="$OUT/obj_ppm"
+  [ -d "$objdir" ] || build_tree ppm "$dir" -DNDEBUG
+  local objs=()
+  for f in "$dir"/src/*.cpp; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    objs+=("$objdir/$(basename "$f" .cpp).o")
+  done
+  $CXX $FLAGS -DNDEBUG -fno-access-control -I"$dir/include" -c "$HERE/ref_driver_ppm.cpp" -o "$objdir/ref_driver_ppm.o"
+  $CXX -pthread "${objs[@]}" "$objdir/ref_driver_ppm.o" -o "$OUT/ppm_eye"
+  echo "built $OUT/ppm_eye"
+}
 for t in "${TREES[@]}"; do
   case "$t" in
     hw1) build_flat hw1 "$REF/HW1" -I"$HERE/shim" ;;
@@ -78,6 +90,7 @@ for t in "${TREES[@]}"; do
     hw4f) build_tree_driver hw4f "$REF/HW4" ;;   # they pin the oracle at float level (tests/test_oracle_golden.py)
     hw7f) build_tree_driver hw7f "$REF/HW7" ;;
     probe) build_probe ;;
+    ppmeye) build_ppm_eye ;;
     ppm) build_tree ppm "$REF/PPM" -DNDEBUG ;;
     *) echo "unknown tree $t" >&2; exit 2 ;;
   esac

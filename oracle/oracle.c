@@ -1738,3 +1738,26 @@ void oracle_tex_color(const b200rt_texture* T, const float* texels, float u, flo
   out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
 }
 float oracle_perlin_value(const b200rt_texture* T, const float* pos) { return perlin_value(T, ld(pos)); }
+/* Deterministic half of the PPM frame (eye pass at 1 sample + hash grid) for tests/test_ppm.py against oracle/_ref/ppm_eye:
+ * out5 = {r0^2, hash_scale, bbox_min.xyz}; cell_counts[num_hash] = size of every hash-grid cell. */
+int oracle_ppm_grid(const B200SceneDesc* d, int camera_index, float* out5, int32_t* cell_counts, int64_t cap,
+                    int64_t* num_hash) {
+  if (!d || camera_index < 0 || camera_index >= d->n_cameras) return -1;
+  const b200rt_camera* c = d->cameras + camera_index;
+  if (c->samples_sqrt != 1) return -2;
+  OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
+  Ctx cx = {d, &cnt};
+  OraclePpm P; memset(&P, 0, sizeof(P));
+  for (int j = 0; j < c->height; j++)
+    for (int i = 0; i < c->width; i++) {
+      Ray r = camera_ray(d, c, i + 0.5f, j + 0.5f, 0, 0, 0, 0.0f);
+      ppm_eye_trace(&cx, &P, &r, 0, V(1, 1, 1), j * c->width + i, 1.0f);
+    }
+  ppm_build_grid(&P, c->width, c->height);
+  out5[0] = P.initial_radius * P.initial_radius; out5[1] = P.hash_scale;
+  out5[2] = P.bbox_min.x; out5[3] = P.bbox_min.y; out5[4] = P.bbox_min.z;
+  *num_hash = P.num_hash;
+  for (int64_t k = 0; k < P.num_hash && k < cap; k++) cell_counts[k] = (int32_t)(P.cell_start[k + 1] - P.cell_start[k]);
+  free(P.hp); free(P.cell_start); free(P.cell_items);
+  return 0;
+}

@@ -2,6 +2,8 @@
 reference seeds from random_device and interleaves threads), and the CUDA path against the oracle (GPU):
 eye pass and hash grid bit-exact, photon pass statistical (the per-photon radius/flux update is
 order-dependent in the reference itself)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -104,3 +106,43 @@ def test_photon_calls_accumulate(gpu):
     one = sc.density_estimation(100_000)
     assert a.photon_rays + b.photon_rays == c.photon_rays      # identical photon paths
     assert abs(float(two[..., :3].mean()) - float(one[..., :3].mean())) <= 0.02 * float(one[..., :3].mean())
+
+
+def test_oracle_eye_pass_and_hash_grid_match_the_ppm_tree(tmp_path):
+    """Rows a16 / a17 pinned directly: the PPM tree's own eye_trace_lines + build_hash_grid (oracle/ref_driver_ppm.cpp,
+    linked with the tree's unmodified objects) against the oracle — every hit point float for float (position, normal,
+    w_o, attenuation, pixel, weight), the initial radius, hash scale, bounding-box corner, and the size of EVERY cell
+    of the hash grid (the signed-overflow hash, the abs(int()) cell coordinates, the +-r0 box insertion)."""
+    import ctypes as C
+    import subprocess
+    exe = os.path.join(os.path.dirname(cpu.__file__), "_ref", "ppm_eye")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built on this box")
+    xml = _scene_xml(width=80, height=60, depth=6)
+    (tmp_path / "s.xml").write_text(xml)
+    subprocess.run([exe, str(tmp_path / "s.xml"), str(tmp_path / "o.bin")], check=True, capture_output=True,
+                   stdin=subprocess.DEVNULL, cwd=str(tmp_path))
+    blob = open(tmp_path / "o.bin", "rb").read()
+    n_hp, num_hash = np.frombuffer(blob, np.int32, 2)
+    hdr = np.frombuffer(blob, np.float32, 5, 8)
+    ref_hp = np.frombuffer(blob, np.float32, n_hp * 16, 28).reshape(n_hp, 16)
+    ref_cells = np.frombuffer(blob, np.int32, num_hash, 28 + n_hp * 64)
+    hs = scene.HostScene(scene.parse_xml(xml, "ppm"))
+    _, o_hp, o_r0, _ = cpu.ppm(hs, 0, seed=1, n_photons=0)
+    assert len(o_hp) == n_hp > 1000 and num_hash == n_hp
+    # the reference appends hit points in traversal order of ONE thread here; so does the oracle: compare row by row
+    cols = list(range(12)) + [13, 14]          # position, normal, w_o, attenuation, pixel, pixel_weight
+    assert np.array_equal(o_hp[:, cols].view(np.uint32), ref_hp[:, cols].view(np.uint32))
+    L = cpu.load()
+    L.oracle_ppm_grid.restype = C.c_int
+    L.oracle_ppm_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    out5 = np.zeros(5, np.float32)
+    cells = np.zeros(num_hash, np.int32)
+    nh = C.c_int64()
+    assert L.oracle_ppm_grid(C.cast(hs.desc_ptr, C.c_void_p), 0, out5.ctypes.data, cells.ctypes.data, int(num_hash),
+                             C.byref(nh)) == 0
+    assert nh.value == num_hash
+    assert np.array_equal(out5.view(np.uint32), hdr.view(np.uint32)), (out5, hdr)
+    assert np.float32(o_r0) * np.float32(o_r0) == hdr[0]
+    assert np.array_equal(cells, ref_cells), int((cells != ref_cells).sum())
+    assert ref_cells.max() > 8 and (ref_cells == 0).any()
