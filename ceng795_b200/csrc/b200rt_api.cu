@@ -466,7 +466,6 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
   if (G.cell_start) cudaFree(G.cell_start);
   G.cell_count = nullptr; G.cell_start = nullptr;
   G.rtab = rtab;
-  G.debug = getenv("B200RT_PPM_DEBUG") ? atoi(getenv("B200RT_PPM_DEBUG")) : 0;
   G.num_hash = n_hp;
   float r0 = 0.f;
   size_t entries = 0;

@@ -47,7 +47,6 @@ struct PpmGrid {
   v3 bbox_min;
   float hash_scale, r0, r0sq;
   const float* rtab;         // R(n) for n < PPM_RTAB
-  int debug;                 // B200RT_PPM_DEBUG (timing experiments only): 1 skip the drain, 2 skip the flux atomic, 4 skip the CAS
 };
 struct PpmCounters {
   unsigned long long photon_rays, cell_scans, deposits;
@@ -371,7 +370,6 @@ __global__ void __launch_bounds__(RT_BLOCK, PPM_MIN_BLOCKS) k_ppm_photon_shade(D
     int q_src[PPM_QCAP];
     int qn = 0;
     auto drain = [&]() {
-      if (G.debug & 1) { qn = 0; return; }
       int qmax = qn;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) qmax = max(qmax, __shfl_xor_sync(0xffffffffu, qmax, o));
@@ -395,7 +393,6 @@ __global__ void __launch_bounds__(RT_BLOCK, PPM_MIN_BLOCKS) k_ppm_photon_shade(D
         bool accepted = false;
         for (;;) {
           if (!(d2 <= G.r0sq * ppm_R(G, n_old))) break;
-          if (G.debug & 4) { accepted = true; break; }
           const unsigned int prev = atomicCAS(hp_n(HP, hi), n_old, n_old + 1u);
           if (prev == n_old) { accepted = true; break; }
           n_old = prev;
@@ -410,7 +407,7 @@ __global__ void __launch_bounds__(RT_BLOCK, PPM_MIN_BLOCKS) k_ppm_photon_shade(D
           const v3 color = (mk3(hd.x, hd.y, hd.z) + ((mk3(hs.x, hs.y, hs.z) * powf(sct, hn.w)) / cti)) *
                            mk3(hw.w, hd.w, hs.w);
           const v3 c = (color * pf) / ppm_R(G, n_old);
-          if (!(G.debug & 2)) atomicAdd(HP.state + hi, make_float4(c.x, c.y, c.z, 0.0f));   // one 16-byte vector atomic (sm_90+)
+          atomicAdd(HP.state + hi, make_float4(c.x, c.y, c.z, 0.0f));   // one 16-byte vector atomic (sm_90+)
         }
       }
       qn = 0;
