@@ -1253,20 +1253,26 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
   OracleCounters total; memset(&total, 0, sizeof(total));
   const int ns = c->samples_sqrt;
   const uint32_t s0 = rng_mix((uint32_t)seed, (uint32_t)(seed >> 32));
+  /* tools/check_nonfinite_oracle.py: ORACLE_COLS=x0:x1 restricts the per-pixel loop to a column window */
+  int col_begin = 0, col_end = W;
+  int strata_begin = 0, strata_end = 0x7fffffff;   /* ORACLE_STRATA=a:b: only those strata of every pixel (debugging) */
+  if (getenv("ORACLE_STRATA")) sscanf(getenv("ORACLE_STRATA"), "%d:%d", &strata_begin, &strata_end);
+  if (getenv("ORACLE_COLS")) { sscanf(getenv("ORACLE_COLS"), "%d:%d", &col_begin, &col_end); if (col_end > W) col_end = W; }
 #pragma omp parallel
   {
     OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
     Ctx cx = {d, &cnt};
     const int hw7 = sem_hw7(d), hw5 = sem_hw5(d);
-#pragma omp for schedule(dynamic, 4)
+#pragma omp for collapse(2) schedule(dynamic, 64)
     for (int j = row_begin; j < row_end; j++) {
-      for (int i = 0; i < W; i++) {
+      for (int i = col_begin; i < col_end; i++) {
         const int pix = j * W + i;
         if (hw7 && ns > 1 && rgbw) {
           /* HW7/src/Scene.cpp:35-85: strata loop, box filter (GAUSSIAN_FILTER is off) */
           float acc[4] = {0, 0, 0, 0};
           for (int x = 0; x < ns; x++)
             for (int y = 0; y < ns; y++) {
+              if (x * ns + y < strata_begin || x * ns + y >= strata_end) continue;
               const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), (uint32_t)(x * ns + y));
               const float ex = rng_u01(key, 4), ey = rng_u01(key, 5);
               const float sx = (x + ex) / ns, sy = (y + ey) / ns;
