@@ -235,6 +235,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_ppm_get_hit_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, P(C.c_int64)]),
         "b200rt_scene_stream": (C.c_void_p, [C.c_void_p]),
         "b200rt_scene_bytes": (C.c_uint64, [C.c_void_p]),
+        "b200rt_scene_build_bvh_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+        "b200rt_lbvh_ranges": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+        "b200rt_lbvh_morton63": (C.c_uint64, [C.c_float, C.c_float, C.c_float]),
         "b200rt_debug_leaf": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_void_p, C.c_int]),
         "b200rt_scene_desc_save": (C.c_int, [C.POINTER(SceneDesc), C.c_char_p]),

@@ -11,6 +11,7 @@
 #include <functional>
 
 #include "fast_bvh.h"
+#include "lbvh.cuh"
 #include "ppm_kernels.cuh"
 #include "rt_hw1_fast.cuh"
 #include "tonemap_kernels.cuh"
@@ -50,6 +51,7 @@ struct b200rt_scene {
   std::vector<b200rt_camera> cameras;
   bool has_transparency, has_mirror;
   int sm_count;
+  int n_meshes;
   // device allocations owned by the scene
   std::vector<void*> allocs;
   // cached wavefront state
@@ -863,6 +865,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     UP(S.vnormal, vn.data(), vn.size(), float4);
   }
   UP(S.meshes, meshes, d->n_meshes, b200rt_mesh);
+  sc->n_meshes = d->n_meshes;
   UP(S.inst, d->instances, d->n_instances, b200rt_instance);
   UP(S.spheres, d->spheres, d->n_spheres, b200rt_sphere);
   UP(S.triprims, d->triprims, d->n_triprims, b200rt_triprim);
@@ -1073,6 +1076,91 @@ int b200rt_debug_leaf(int device, int which, const b200rt_texture* tex, const fl
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)rows * n_out * 4, cudaMemcpyDeviceToHost));
   cudaFree(d_tex); cudaFree(d_in); cudaFree(d_out);
+  return B200RT_OK;
+}
+
+int b200rt_scene_build_bvh_device(b200rt_scene* sc, float* ms_out) {
+  if (!sc) return B200RT_E_INVALID;
+  if (sc->S.semantics == B200RT_SEM_HW1) {
+    b200rt_internal_set_error("build_bvh_device: HW1 has no per-mesh trees");
+    return B200RT_E_UNSUPPORTED;
+  }
+  CK(cudaSetDevice(sc->device));
+  cudaStream_t st = sc->stream;
+  const int n_meshes = sc->n_meshes;
+  std::vector<b200rt_mesh> meshes((size_t)n_meshes);
+  CK(cudaMemcpy(meshes.data(), sc->S.meshes, sizeof(b200rt_mesh) * n_meshes, cudaMemcpyDeviceToHost));
+  size_t total_tris = 0, max_tris = 0;
+  for (const b200rt_mesh& m : meshes)
+    if (m.tri_count >= 2) { total_tris += (size_t)m.tri_count; max_tris = std::max(max_tris, (size_t)m.tri_count); }
+  if (total_tris == 0) { if (ms_out) *ms_out = 0.f; return B200RT_OK; }
+  // outputs (replace the host-built SAH arrays; the old ones stay allocated until the scene is destroyed)
+  b200rt_bvh_node* d_nodes = nullptr;
+  float4* d_ftris = nullptr;
+  int* d_fref = nullptr;
+  CK(cudaMalloc((void**)&d_nodes, sizeof(b200rt_bvh_node) * total_tris));
+  CK(cudaMalloc((void**)&d_ftris, sizeof(float4) * 3 * total_tris));
+  CK(cudaMalloc((void**)&d_fref, sizeof(int) * total_tris));
+  sc->allocs.push_back(d_nodes); sc->allocs.push_back(d_ftris); sc->allocs.push_back(d_fref);
+  // scratch for the largest mesh
+  uint64_t *d_keys = nullptr, *d_keys2 = nullptr;
+  uint32_t *d_idx = nullptr, *d_idx2 = nullptr;
+  int* d_parent = nullptr;
+  float* d_leaf_box = nullptr;
+  unsigned int* d_visits = nullptr;
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  CK(cudaMalloc((void**)&d_keys, 8 * max_tris));
+  CK(cudaMalloc((void**)&d_keys2, 8 * max_tris));
+  CK(cudaMalloc((void**)&d_idx, 4 * max_tris));
+  CK(cudaMalloc((void**)&d_idx2, 4 * max_tris));
+  CK(cudaMalloc((void**)&d_parent, 4 * 2 * max_tris));
+  CK(cudaMalloc((void**)&d_leaf_box, 4 * 6 * max_tris));
+  CK(cudaMalloc((void**)&d_visits, 4 * max_tris));
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_idx, d_idx2, (int)max_tris, 0, 63, st);
+  CK(cudaMalloc(&d_tmp, tmp_bytes));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  const int grid = sc->sm_count * 8;
+  size_t base = 0;   // nodes and leaves of one mesh share the offset: n-1 nodes, n leaves
+  for (b200rt_mesh& m : meshes) {
+    if (m.tri_count < 2) continue;
+    const int n = m.tri_count;
+    float ext = 0.f;
+    for (int q = 0; q < 3; q++) {
+      ext = fmaxf(ext, m.root_box[3 + q] - m.root_box[q]);
+      ext = fmaxf(ext, fmaxf(fabsf(m.root_box[q]), fabsf(m.root_box[3 + q])));
+    }
+    const float grow = ext * (3e-5f + 4.0f * sc->S.isect_eps) + 1e-30f;   // as the host builder's SAH boxes
+    const float3 lo = make_float3(m.root_box[0], m.root_box[1], m.root_box[2]);
+    const float3 ie = make_float3(1.0f / fmaxf(m.root_box[3] - m.root_box[0], 1e-30f),
+                                  1.0f / fmaxf(m.root_box[4] - m.root_box[1], 1e-30f),
+                                  1.0f / fmaxf(m.root_box[5] - m.root_box[2], 1e-30f));
+    k_lbvh_keys<<<grid, 256, 0, st>>>(sc->S.tris, m.tri_begin, n, lo, ie, d_keys, d_idx);
+    size_t need = tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(d_tmp, need, d_keys, d_keys2, d_idx, d_idx2, n, 0, 63, st);
+    k_lbvh_leaves<<<grid, 256, 0, st>>>(sc->S.tris, m.tri_begin, n, d_idx2, (int)base, d_ftris, d_fref, d_leaf_box);
+    CK(cudaMemsetAsync(d_visits, 0, 4 * (size_t)n, st));
+    k_lbvh_hierarchy<<<grid, 256, 0, st>>>(d_keys2, n, (int)base, (int)base, d_nodes, d_parent);
+    k_lbvh_refit<<<grid, 256, 0, st>>>(n, (int)base, d_parent, d_leaf_box, d_nodes, d_visits, grow);
+    m.fast_root = B200RT_REF(B200RT_KIND_FNODE, (uint32_t)base);
+    base += (size_t)n;
+  }
+  CK(cudaEventRecord(e1, st));
+  CK(cudaMemcpyAsync(const_cast<b200rt_mesh*>(sc->S.meshes), meshes.data(), sizeof(b200rt_mesh) * n_meshes,
+                     cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  if (ms_out) *ms_out = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx); cudaFree(d_idx2); cudaFree(d_parent); cudaFree(d_leaf_box); cudaFree(d_visits); cudaFree(d_tmp);
+  sc->S.fast_nodes = reinterpret_cast<const float4*>(d_nodes);
+  sc->S.fast_tris = d_ftris;
+  sc->S.fast_tri_ref = d_fref;
   return B200RT_OK;
 }
 

@@ -649,6 +649,13 @@ class Scene:
             setattr(o, k, v)
         return o
 
+    def build_bvh_device(self) -> float:
+        """Rebuilds the device-walked tree of every mesh ON the device (LBVH); returns the build time in ms."""
+        self.upload()
+        ms = C.c_float(0.0)
+        _lib.check(self._L.b200rt_scene_build_bvh_device(self._scene, C.byref(ms)), "b200rt_scene_build_bvh_device")
+        return float(ms.value)
+
     def image_size(self, camera_index=0):
         c = self.spec.cameras[camera_index]
         return c["width"], c["height"]

@@ -452,6 +452,17 @@ int b200rt_scene_desc_save(const B200SceneDesc*, const char* path);
 int b200rt_scene_desc_load(const char* path, B200SceneDesc** out);
 void b200rt_scene_desc_free(B200SceneDesc*);
 
+/* ---- next row: the device-walked tree built on the device ----
+ * Rebuilds, on the GPU, the tree k_trace_fast walks inside every mesh (LBVH: Morton order, Karras' hierarchy, bottom-up
+ * boxes) from the triangles already resident, replacing the host-built SAH tree: ~ms instead of ~1 s for 1 M
+ * triangles.  The reference's decisions are not in that tree (they are the triangle test, tri_gate and the tie-break
+ * key), so every result stays bit-identical; traversal is slower than through the SAH tree, hence an explicit call.
+ * The reference builds its own tree recursively on the host (HW7/src/Bounding_volume_hierarchy.cpp:3-29).
+ * ms_out (optional): device time of the build.  b200rt_lbvh_ranges / _morton63: the hierarchy rule on the host (tests). */
+int b200rt_scene_build_bvh_device(b200rt_scene*, float* ms_out);
+int b200rt_lbvh_ranges(const uint64_t* sorted_keys, int n, int32_t* first_last_split);
+uint64_t b200rt_lbvh_morton63(float x, float y, float z);
+
 /* Measurement aid: streaming-read bandwidth over a `bytes` working set, `iters` passes, in GB/s.
  * 48 MB measures the L2 (the denominator for scene fetches when the tree is L2-resident), >= 1 GB measures HBM. */
 int b200rt_measure_read_bandwidth(int device, uint64_t bytes, int iters, double* gbs_out);

@@ -91,3 +91,36 @@ def test_no_cpu_fallback_without_gpu():
     xml = scenes.cfg1_hw1(width=8, height=8, n_spheres=2)
     with pytest.raises(_lib.B200RTError):
         scene.Scene(xml, "hw1")
+
+
+def test_lbvh_hierarchy_rule_on_the_host():
+    """csrc/lbvh.cuh: Karras' range / split rule, run on the CPU over sorted keys including
+    long runs of equal Morton codes (told apart by position).  The n-1 internal nodes must form a binary tree over the n leaves: node 0 covers
+    everything, every node's children partition its range, every leaf and every other node has exactly one parent."""
+    import ctypes as C
+    import numpy as np
+    from ceng795_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(5)
+    for n, spread in ((2, 10), (3, 1), (17, 4), (1000, 50), (4096, 1 << 30), (5000, 3)):
+        morton = np.sort(rng.integers(0, spread, n).astype(np.uint64))          # many duplicates when spread is small
+        keys = np.ascontiguousarray(morton)
+        ranges = np.zeros((n - 1, 3), np.int32)
+        assert L.b200rt_lbvh_ranges(keys.ctypes.data, n, ranges.ctypes.data) == 0
+        first, last, split = ranges[:, 0], ranges[:, 1], ranges[:, 2]
+        assert first[0] == 0 and last[0] == n - 1
+        assert np.all((first <= split) & (split < last))
+        leaf_parents = np.zeros(n, np.int32)
+        node_parents = np.zeros(n - 1, np.int32)
+        for i in range(n - 1):
+            for lo, hi in ((first[i], split[i]), (split[i] + 1, last[i])):
+                if lo == hi:
+                    leaf_parents[lo] += 1
+                else:
+                    child = split[i] if lo == first[i] else split[i] + 1      # Karras: the child node sits at the split
+                    assert first[child] == lo and last[child] == hi, (n, i, child)
+                    node_parents[child] += 1
+        assert np.all(leaf_parents == 1) and node_parents[0] == 0 and np.all(node_parents[1:] == 1)
+    assert L.b200rt_lbvh_morton63(0.0, 0.0, 0.0) == 0
+    assert L.b200rt_lbvh_morton63(1.0, 1.0, 1.0) == (1 << 63) - 1
+    assert L.b200rt_lbvh_morton63(0.999, 0.0, 0.0) > L.b200rt_lbvh_morton63(0.0, 0.999, 0.999)   # x is the top bit

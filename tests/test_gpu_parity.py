@@ -352,3 +352,36 @@ def test_scene_create_builds_the_sah_tree(gpu):
     assert np.array_equal(ids, o_ids) and np.array_equal(t.view(np.uint32), o_t.view(np.uint32))
     _, st = sc.render_image(0)
     assert st.nodes_visited > 0
+
+
+@pytest.mark.parametrize("name", ["cfg2_hw3_n48_smooth", "hw7_whitted_160", "cfg2_hw3_glass"])
+def test_device_built_tree_gives_the_same_answers(gpu, name):
+    """the tree walked inside a mesh rebuilt ON the device (LBVH).  The reference's decisions are
+    not in that tree, so ids, t, ray counts and the image stay bit-identical; only the visit counters change."""
+    tree, xml = scene_xml(name)
+    sc = scene.Scene(xml, tree, base_dir=ASSETS)
+    ids0, t0 = sc.primary_ids(0)
+    img0, st0 = sc.render_image(0)
+    ms = sc.build_bvh_device()
+    assert 0.0 < ms < 1000.0
+    ids1, t1 = sc.primary_ids(0)
+    img1, st1 = sc.render_image(0)
+    _, o_ids, o_t, _ = cpu.render(sc.host, 0, want_image=False, want_ids=True)
+    assert np.array_equal(ids1, o_ids) and np.array_equal(t1.view(np.uint32), o_t.view(np.uint32))
+    assert np.array_equal(ids1, ids0) and np.array_equal(t1.view(np.uint32), t0.view(np.uint32))
+    assert np.array_equal(img1.view(np.uint32), img0.view(np.uint32))
+    assert (st1.rays_primary, st1.rays_shadow, st1.rays_secondary) == (st0.rays_primary, st0.rays_shadow, st0.rays_secondary)
+    assert st1.nodes_visited != st0.nodes_visited        # it IS another tree
+
+
+def test_device_built_tree_full_size(gpu):
+    """1 M triangles: built in milliseconds on the device, same ids as the SAH tree on the full cfg2 frame."""
+    sc = scene.Scene(scenes.cfg2_hw3(), "hw3")
+    ids0, t0 = sc.primary_ids(0)
+    _, st0 = sc.render_image(0)
+    ms = sc.build_bvh_device()
+    ids1, t1 = sc.primary_ids(0)
+    _, st1 = sc.render_image(0)
+    assert np.array_equal(ids1, ids0) and np.array_equal(t1.view(np.uint32), t0.view(np.uint32))
+    print(f"LBVH build of 1 M triangles: {ms:.2f} ms; frame {st0.ms_total:.2f} ms (SAH) -> {st1.ms_total:.2f} ms (LBVH)")
+    assert ms < 100.0
