@@ -113,7 +113,7 @@ def test_ties_resolve_like_the_reference(gpu, tree, spacing):
     assert np.array_equal(ids_p, o_ids2) and np.array_equal(t_p.view(np.uint32), o_t2.view(np.uint32))
 
 
-@pytest.mark.parametrize("tree", ["hw3", "hw4", "hw6", "hw7"])
+@pytest.mark.parametrize("tree", ["hw1", "hw2", "hw3", "hw4", "hw6", "hw7"])
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_fuzz_scenes_match_the_oracle(gpu, tree, seed):
     """scenes.fuzz_scene (mirroring scales, transform chains, degenerate triangles, camera inside a sphere, axis-aligned

@@ -96,7 +96,7 @@ def test_oracle_tie_breaking_matches_live_reference(tree, spacing):
     assert image.compare_8bit(image.quantise(rgbw, hs.spec.semantics), want)["exact"] == 1.0
 
 
-@pytest.mark.parametrize("tree", ["hw3", "hw4", "hw5", "hw6", "hw7"])
+@pytest.mark.parametrize("tree", ["hw1", "hw2", "hw3", "hw4", "hw5", "hw6", "hw7"])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_oracle_fuzz_scenes_match_live_reference(tree, seed):
     """Differential test on scenes built to be awkward (scenes.fuzz_scene: mirroring scales, transform chains,

@@ -108,7 +108,9 @@ def test_photon_calls_accumulate(gpu):
     assert abs(float(two[..., :3].mean()) - float(one[..., :3].mean())) <= 0.02 * float(one[..., :3].mean())
 
 
-def test_oracle_eye_pass_and_hash_grid_match_the_ppm_tree(tmp_path):
+@pytest.mark.parametrize("kw", [dict(width=80, height=60, depth=6), dict(width=57, height=91, depth=3, mesh_slices=(9, 7)),
+                                dict(width=120, height=40, depth=9, mesh_slices=(24, 20))])
+def test_oracle_eye_pass_and_hash_grid_match_the_ppm_tree(tmp_path, kw):
     """Rows a16 / a17 pinned directly: the PPM tree's own eye_trace_lines + build_hash_grid (oracle/ref_driver_ppm.cpp,
     linked with the tree's unmodified objects) against the oracle — every hit point float for float (position, normal,
     w_o, attenuation, pixel, weight), the initial radius, hash scale, bounding-box corner, and the size of EVERY cell
@@ -118,7 +120,7 @@ def test_oracle_eye_pass_and_hash_grid_match_the_ppm_tree(tmp_path):
     exe = os.path.join(os.path.dirname(cpu.__file__), "_ref", "ppm_eye")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref not built on this box")
-    xml = _scene_xml(width=80, height=60, depth=6)
+    xml = _scene_xml(**kw)
     (tmp_path / "s.xml").write_text(xml)
     subprocess.run([exe, str(tmp_path / "s.xml"), str(tmp_path / "o.bin")], check=True, capture_output=True,
                    stdin=subprocess.DEVNULL, cwd=str(tmp_path))
@@ -129,7 +131,7 @@ def test_oracle_eye_pass_and_hash_grid_match_the_ppm_tree(tmp_path):
     ref_cells = np.frombuffer(blob, np.int32, num_hash, 28 + n_hp * 64)
     hs = scene.HostScene(scene.parse_xml(xml, "ppm"))
     _, o_hp, o_r0, _ = cpu.ppm(hs, 0, seed=1, n_photons=0)
-    assert len(o_hp) == n_hp > 1000 and num_hash == n_hp
+    assert len(o_hp) == n_hp > 500 and num_hash == n_hp
     # the reference appends hit points in traversal order of ONE thread here; so does the oracle: compare row by row
     cols = list(range(12)) + [13, 14]          # position, normal, w_o, attenuation, pixel, pixel_weight
     assert np.array_equal(o_hp[:, cols].view(np.uint32), ref_hp[:, cols].view(np.uint32))
