@@ -74,7 +74,8 @@ build_ppm_eye() { # PPM's objects except main.cpp + oracle/ref_driver_ppm.cpp: e
     objs+=("$objdir/$(basename "$f" .cpp).o")
   done
   $CXX $FLAGS -DNDEBUG -fno-access-control -I"$dir/include" -c "$HERE/ref_driver_ppm.cpp" -o "$objdir/ref_driver_ppm.o"
-  $CXX -pthread "${objs[@]}" "$objdir/ref_driver_ppm.o" -o "$OUT/ppm_eye"
+  # our std::random_device::_M_getval comes first and wins over the one in a static libstdc++
+  $CXX -pthread -Wl,--allow-multiple-definition "$objdir/ref_driver_ppm.o" "${objs[@]}" -o "$OUT/ppm_eye"
   echo "built $OUT/ppm_eye"
 }
 for t in "${TREES[@]}"; do

@@ -1533,6 +1533,45 @@ static void ppm_build_grid(OraclePpm* P, int width, int height) {
 /* Scene::photon_trace — PPM/src/Scene.cpp:106-249; RNG dims of the photon key: emission 0,1; bounce b: 8b+{2,3} hemisphere,
  * 8b+4 roulette, 8b+5 glass roulette */
 #define PPM_ALPHA 0.7f
+/* ---- the reference's own random streams, for the bit-exact pin of the photon pass -------------------------------
+ * PPM draws from three function-local `thread_local static std::mt19937 generator(rd())` engines through
+ * `std::uniform_real_distribution<float>(0, 1)`: Point_light::generate_photon (PPM/src/Point_light.cpp:10-14),
+ * Scene::sample_hemisphere (PPM/src/Scene.cpp:17-21), Scene::photon_trace (:107-109).  oracle/ref_driver_ppm.cpp
+ * runs the tree single-threaded with random_device interposed to a constant; with mt mode on, the restatement draws
+ * from the same three streams in the same program order instead of its counter-based generator.
+ * mt19937: the standard recurrence.  uniform_real_distribution<float> in libstdc++ (bits/random.tcc,
+ * generate_canonical<float, 24>): ONE 32-bit draw, float(draw) / 2^32, and nextafter(1, 0) if that rounds to 1. */
+typedef struct { uint32_t x[624]; int i; } Mt19937;
+static void mt_seed(Mt19937* m, uint32_t seed) {
+  m->x[0] = seed;
+  for (int k = 1; k < 624; k++) m->x[k] = 1812433253u * (m->x[k - 1] ^ (m->x[k - 1] >> 30)) + (uint32_t)k;
+  m->i = 624;
+}
+static uint32_t mt_next(Mt19937* m) {
+  if (m->i >= 624) {
+    for (int k = 0; k < 624; k++) {
+      const uint32_t y = (m->x[k] & 0x80000000u) | (m->x[(k + 1) % 624] & 0x7fffffffu);
+      m->x[k] = m->x[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    m->i = 0;
+  }
+  uint32_t y = m->x[m->i++];
+  y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+  return y;
+}
+static float mt_u01(Mt19937* m) {
+  float r = (float)mt_next(m) / 4294967296.0f;
+  if (r >= 1.0f) r = nextafterf(1.0f, 0.0f);
+  return r;
+}
+static struct { int on; Mt19937 light, hemi, trace; float* state_out; int64_t state_cap; } g_mt;   /* test infrastructure: single-threaded use only */
+#define PPM_DRAW(stream, key, dim) (g_mt.on ? mt_u01(&g_mt.stream) : rng_u01((key), (dim)))
+/* state_out (optional): 5 floats per hit point {flux.rgb, radius_squared, n} written by the next oracle_ppm call */
+void oracle_ppm_mt_mode(int on, uint32_t seed, float* state_out, int64_t state_cap) {
+  g_mt.on = on; g_mt.state_out = on ? state_out : NULL; g_mt.state_cap = state_cap;
+  if (on) { mt_seed(&g_mt.light, seed); mt_seed(&g_mt.hemi, seed); mt_seed(&g_mt.trace, seed); }
+}
+
 static void ppm_photon_trace(const Ctx* cx, OraclePpm* P, Ray ray, v3 flux, uint32_t key, OracleCounters* pc) {
   const B200SceneDesc* d = cx->d;
   int depth = 0;
@@ -1575,7 +1614,8 @@ static void ppm_photon_trace(const Ctx* cx, OraclePpm* P, Ray ray, v3 flux, uint
         }
       }
       /* sample_hemisphere(normal, d, probability) — cosine, PPM/src/Scene.cpp:15-44 */
-      const float e1 = rng_u01(key, dim + 2), e2 = rng_u01(key, dim + 3);
+      const float e1 = PPM_DRAW(hemi, key, dim + 2);
+      const float e2 = PPM_DRAW(hemi, key, dim + 3);
       const float phi = (float)(2 * M_PI * (double)e1);
       const float theta = asinf(sqrtf(e2));
       const v3 dd = onb_dir(n, theta, phi);
@@ -1589,7 +1629,7 @@ static void ppm_photon_trace(const Ctx* cx, OraclePpm* P, Ray ray, v3 flux, uint
       }
       const float cto = fmaxf(0.0f, dot(n, dd));
       base = muls(base, cto);
-      if (rng_u01(key, dim + 4) < prob) {
+      if (PPM_DRAW(trace, key, dim + 4) < prob) {
         ray.o = add(p, muls(dd, d->shadow_eps)); ray.d = dd;
         flux = divs(mulv(base, flux), prob);
         continue;
@@ -1615,7 +1655,7 @@ static void ppm_photon_trace(const Ctx* cx, OraclePpm* P, Ray ray, v3 flux, uint
     const float ca = into ? -ddn : dot(rdir, n);
     const float c = 1 - ca;
     const float fres = R0 + (1 - R0) * c * c * c * c * c;
-    if (into && rng_u01(key, dim + 5) < fres) { ray.o = add(p, muls(w_r, d->shadow_eps)); ray.d = w_r; }
+    if (into && PPM_DRAW(trace, key, dim + 5) < fres) { ray.o = add(p, muls(w_r, d->shadow_eps)); ray.d = w_r; }
     else { ray.o = add(p, muls(rdir, d->shadow_eps)); ray.d = rdir; }
   }
 }
@@ -1656,8 +1696,10 @@ int oracle_ppm(const B200SceneDesc* d, int camera_index, uint64_t seed, int64_t 
   for (int64_t i = 0; i < n_photons; i++) {
     const uint32_t key = rng_mix(rng_mix(s0 ^ 0x50484F54u, (uint32_t)i), (uint32_t)((uint64_t)i >> 32));
     const v3 flux = muls(ld(L->intensity), (float)(M_PI * 4.0f));
-    const float phi = (float)(2 * M_PI * (double)rng_u01(key, 0));
-    const float theta = (float)(2 * M_PI * (double)rng_u01(key, 1));
+    const float le1 = PPM_DRAW(light, key, 0);
+    const float le2 = PPM_DRAW(light, key, 1);
+    const float phi = (float)(2 * M_PI * (double)le1);
+    const float theta = (float)(2 * M_PI * (double)le2);
     Ray r; memset(&r, 0, sizeof(r));
     r.d = onb_dir(V(0.0f, 1.0f, 0.0f), theta, phi);
     r.o = ld(L->position);
@@ -1682,6 +1724,12 @@ int oracle_ppm(const B200SceneDesc* d, int camera_index, uint64_t seed, int64_t 
       o[0] = h->position.x; o[1] = h->position.y; o[2] = h->position.z; o[3] = h->normal.x; o[4] = h->normal.y; o[5] = h->normal.z;
       o[6] = h->w_o.x; o[7] = h->w_o.y; o[8] = h->w_o.z; o[9] = h->attenuation.x; o[10] = h->attenuation.y; o[11] = h->attenuation.z;
       o[12] = (float)h->material; o[13] = (float)h->pixel; o[14] = h->pixel_weight; o[15] = (float)h->n;
+    }
+  if (g_mt.state_out)
+    for (int64_t i = 0; i < P.n && i < g_mt.state_cap; i++) {
+      const OracleHitPoint* h = P.hp + i;
+      float* o = g_mt.state_out + 5 * i;
+      o[0] = h->flux.x; o[1] = h->flux.y; o[2] = h->flux.z; o[3] = h->radius_squared; o[4] = (float)h->n;
     }
   if (n_hp) *n_hp = P.n;
   if (counters) {

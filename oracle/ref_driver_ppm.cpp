@@ -6,10 +6,24 @@
 //   n_hp x 16 float32 {position, normal, w_o, attenuation, diffuse.x (material tag), pixel, pixel_weight, 0};
 //   num_hash x int32 = size of every hash-grid cell.
 //   ref_driver_ppm scene.xml out.bin      (NumSamples must be 1: the multi-sample eye pass draws from random_device)
+// With a third argument N it goes on, still on this one thread, with the tree's own photon pass and density estimate:
+//   trace_n_photons(N, 1); density_estimation(pixels, N);                          (PPM/src/main.cpp:77-98)
+// and appends  n_hp x 5 float32 {flux.rgb, radius_squared, n}  and  W*H x 3 float32 Pixel::get_color().
+// The tree seeds its three function-local mt19937 engines from std::random_device; this file defines
+// std::random_device::_M_getval() itself (the executable's definition wins over libstdc++'s), so every engine starts
+// from the constant kSeed and the photon pass becomes one reproducible sequence the oracle can replay draw for draw.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
+#include <random>
+#include <vector>
+
+#include "Pixel.h"
 #include "Scene.h"
+
+static const unsigned kSeed = 795u;
+unsigned int std::random_device::_M_getval() { return kSeed; }
 
 int main(int argc, char** argv) {
   if (argc < 3) return 1;
@@ -35,6 +49,21 @@ int main(int argc, char** argv) {
   for (const auto& cell : scene.hash_grid) {
     const int32_t k = (int32_t)cell.size();
     std::fwrite(&k, 4, 1, f);
+  }
+  if (argc > 3) {
+    const int n_photons = std::atoi(argv[3]);
+    scene.trace_n_photons(n_photons, 1);
+    std::vector<Pixel> film((size_t)plane.width * plane.height);
+    scene.density_estimation(film.data(), n_photons);
+    for (const Hit_point* h : scene.hit_points) {
+      const float row[5] = {h->flux.x, h->flux.y, h->flux.z, h->radius_squared, (float)h->n};
+      std::fwrite(row, sizeof(row), 1, f);
+    }
+    for (size_t p = 0; p < film.size(); p++) {
+      const Vector3 c = film[p].get_color();
+      const float rgb[3] = {c.x, c.y, c.z};
+      std::fwrite(rgb, sizeof(rgb), 1, f);
+    }
   }
   std::fclose(f);
   return 0;

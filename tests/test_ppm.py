@@ -148,3 +148,46 @@ def test_oracle_eye_pass_and_hash_grid_match_the_ppm_tree(tmp_path, kw):
     assert np.float32(o_r0) * np.float32(o_r0) == hdr[0]
     assert np.array_equal(cells, ref_cells), int((cells != ref_cells).sum())
     assert ref_cells.max() > 8 and (ref_cells == 0).any()
+
+
+@pytest.mark.parametrize("n_photons", [50_000])
+def test_oracle_photon_pass_replays_the_ppm_tree_draw_for_draw(tmp_path, n_photons):
+    """Rows a18-a20 pinned EXACTLY.  The PPM tree draws from three mt19937 engines seeded by std::random_device;
+    oracle/ref_driver_ppm.cpp defines random_device::_M_getval itself (constant seed) and runs the tree's own
+    trace_n_photons + density_estimation on one thread.  With `oracle_ppm_mt_mode` the restatement draws from the same
+    three streams (libstdc++'s uniform_real_distribution<float> restated) in the same program order: after 50 000
+    photons every hit point's photon count, radius^2 and flux and every pixel of the image are the same bits — the
+    generate_photon quirk, the cell lookup, the radius / flux update, the cosine sample used as survival probability,
+    the Fresnel roulette, the density estimate."""
+    import ctypes as C
+    import subprocess
+    exe = os.path.join(os.path.dirname(cpu.__file__), "_ref", "ppm_eye")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built on this box")
+    w, h = 80, 60
+    xml = _scene_xml(width=w, height=h, depth=6)
+    (tmp_path / "s.xml").write_text(xml)
+    subprocess.run([exe, str(tmp_path / "s.xml"), str(tmp_path / "o.bin"), str(n_photons)], check=True,
+                   capture_output=True, stdin=subprocess.DEVNULL, cwd=str(tmp_path))
+    blob = open(tmp_path / "o.bin", "rb").read()
+    n_hp, num_hash = np.frombuffer(blob, np.int32, 2)
+    off = 28 + n_hp * 64 + num_hash * 4
+    ref_state = np.frombuffer(blob, np.float32, n_hp * 5, off).reshape(n_hp, 5)
+    ref_img = np.frombuffer(blob, np.float32, w * h * 3, off + n_hp * 20).reshape(h, w, 3)
+    hs = scene.HostScene(scene.parse_xml(xml, "ppm"))
+    L = cpu.load()
+    L.oracle_ppm_mt_mode.restype = None
+    L.oracle_ppm_mt_mode.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_int64]
+    state = np.zeros((n_hp, 5), np.float32)
+    L.oracle_ppm_mt_mode(1, 795, state.ctypes.data, int(n_hp))
+    try:
+        rgbw, _, _, cnt = cpu.ppm(hs, 0, seed=1, n_photons=n_photons, total_num_of_photons=n_photons)
+    finally:
+        L.oracle_ppm_mt_mode(0, 0, None, 0)
+    assert ref_state[:, 4].sum() > 100_000 and ref_state[:, 4].max() > 50          # a real workout
+    assert np.array_equal(state[:, 4], ref_state[:, 4])                              # photon counts n
+    assert np.array_equal(state[:, 3].view(np.uint32), ref_state[:, 3].view(np.uint32))     # radius^2
+    assert np.array_equal(state[:, :3].view(np.uint32), ref_state[:, :3].view(np.uint32))   # flux
+    img = np.where(rgbw[..., 3:4] == 0, np.float32(0), rgbw[..., :3] / np.maximum(rgbw[..., 3:4], np.float32(1e-30)))
+    assert np.array_equal(img.astype(np.float32).view(np.uint32), ref_img.view(np.uint32))
+    assert int(cnt.instances_entered) == int(ref_state[:, 4].sum())
