@@ -50,7 +50,9 @@ build_tree_driver() { # name dir : the tree's objects except main.cpp + our floa
     if [ ! -f "$o" ] || [ "$f" -nt "$o" ]; then $CXX $FLAGS "$@" -I"$dir/include" -c "$f" -o "$o" & fi
   done
   wait
-  $CXX -pthread "${objs[@]}" -o "$OUT/${name}_raytracer"
+  # ref_driver_hdr.cpp defines std::random_device::_M_getval (REF_SEED): it has to win over a static libstdc++'s
+  local drv="$objdir/ref_driver_hdr.o"; local rest=(); for o in "${objs[@]}"; do [ "$o" = "$drv" ] || rest+=("$o"); done
+  $CXX -pthread -Wl,--allow-multiple-definition "$drv" "${rest[@]}" -o "$OUT/${name}_raytracer"
   echo "built $OUT/${name}_raytracer"
 }
 build_probe() { # leaf known-answer probe: HW7's objects except main.cpp + oracle/ref_probe.cpp

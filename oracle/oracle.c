@@ -493,6 +493,59 @@ static int refract_ray(v3 du, v3 n, float index, v3* out) {
 
 /* Scene::trace_ray — HW1/Scene.cpp:28-123 and HW3/src/Scene.cpp:116-312. */
 static int diffuse_constant7(const B200SceneDesc* d, const Hit* hit, v3* out);
+/* ---- the reference's own random streams, for the bit-exact pin of the photon pass -------------------------------
+ * PPM draws from three function-local `thread_local static std::mt19937 generator(rd())` engines through
+ * `std::uniform_real_distribution<float>(0, 1)`: Point_light::generate_photon (PPM/src/Point_light.cpp:10-14),
+ * Scene::sample_hemisphere (PPM/src/Scene.cpp:17-21), Scene::photon_trace (:107-109).  oracle/ref_driver_ppm.cpp
+ * runs the tree single-threaded with random_device interposed to a constant; with mt mode on, the restatement draws
+ * from the same three streams in the same program order instead of its counter-based generator.
+ * mt19937: the standard recurrence.  uniform_real_distribution<float> in libstdc++ (bits/random.tcc,
+ * generate_canonical<float, 24>): ONE 32-bit draw, float(draw) / 2^32, and nextafter(1, 0) if that rounds to 1. */
+typedef struct { uint32_t x[624]; int i; } Mt19937;
+static void mt_seed(Mt19937* m, uint32_t seed) {
+  m->x[0] = seed;
+  for (int k = 1; k < 624; k++) m->x[k] = 1812433253u * (m->x[k - 1] ^ (m->x[k - 1] >> 30)) + (uint32_t)k;
+  m->i = 624;
+}
+static uint32_t mt_next(Mt19937* m) {
+  if (m->i >= 624) {
+    for (int k = 0; k < 624; k++) {
+      const uint32_t y = (m->x[k] & 0x80000000u) | (m->x[(k + 1) % 624] & 0x7fffffffu);
+      m->x[k] = m->x[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    m->i = 0;
+  }
+  uint32_t y = m->x[m->i++];
+  y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+  return y;
+}
+static float mt_u01(Mt19937* m) {
+  float r = (float)mt_next(m) / 4294967296.0f;
+  if (r >= 1.0f) r = nextafterf(1.0f, 0.0f);
+  return r;
+}
+static struct { int on; Mt19937 light, hemi, trace; float* state_out; int64_t state_cap; } g_mt;   /* test infrastructure: single-threaded use only */
+#define PPM_DRAW(stream, key, dim) (g_mt.on ? mt_u01(&g_mt.stream) : rng_u01((key), (dim)))
+/* state_out (optional): 5 floats per hit point {flux.rgb, radius_squared, n} written by the next oracle_ppm call */
+/* HW7 (and HW3-HW6, whose sites are a subset): one engine per draw site, all seeded from random_device —
+ * Scene::render_image (HW7/src/Scene.cpp:36-61: jitter x, y, [lens x, y], time), Area_light.cpp:18-22,
+ * Light_mesh.cpp:7-12, Light_sphere.cpp:9-13, Spherical_directional_light.cpp:18-22, the glossy perturbation
+ * (Scene.cpp:216-220) and the hemisphere sample of trace_path (Scene.cpp:347-351).  oracle/ref_driver_hdr.cpp with
+ * REF_SINGLE_THREAD=1 runs the tree on one thread with random_device interposed. */
+static struct { int on; Mt19937 render, area, mesh, sphere, env, glossy, hemi; } g_mt7;
+#define DRAW7(stream, key, dim) (g_mt7.on ? mt_u01(&g_mt7.stream) : rng_u01((key), (dim)))
+void oracle_hw7_mt_mode(int on, uint32_t seed) {
+  g_mt7.on = on;
+  if (on) {
+    mt_seed(&g_mt7.render, seed); mt_seed(&g_mt7.area, seed); mt_seed(&g_mt7.mesh, seed); mt_seed(&g_mt7.sphere, seed);
+    mt_seed(&g_mt7.env, seed); mt_seed(&g_mt7.glossy, seed); mt_seed(&g_mt7.hemi, seed);
+  }
+}
+void oracle_ppm_mt_mode(int on, uint32_t seed, float* state_out, int64_t state_cap) {
+  g_mt.on = on; g_mt.state_out = on ? state_out : NULL; g_mt.state_cap = state_cap;
+  if (on) { mt_seed(&g_mt.light, seed); mt_seed(&g_mt.hemi, seed); mt_seed(&g_mt.trace, seed); }
+}
+
 static v3 tex_color(const B200SceneDesc* d, const b200rt_texture* T, float u, float v);
 static v3 trace_ray(const Ctx* cx, const Ray* ray, int depth, uint32_t key, int count_as) {
   const B200SceneDesc* d = cx->d;
@@ -605,7 +658,8 @@ static v3 trace_ray(const Ctx* cx, const Ray* ray, int depth, uint32_t key, int 
       else rp = V(wr.x, wr.y, 1.0f);
       const v3 u = normalize(cross(rp, wr));
       const v3 v = normalize(cross(u, wr));
-      const float eu = rng_u01(key, 2) - 0.5f, ev = rng_u01(key, 3) - 0.5f;
+      const float eu = DRAW7(glossy, key, 2) - 0.5f;
+    const float ev = DRAW7(glossy, key, 3) - 0.5f;
       dir = normalize(add(wr, muls(add(muls(u, eu), muls(v, ev)), m->roughness)));
     }
     Ray mr; memset(&mr, 0, sizeof(mr));
@@ -901,7 +955,8 @@ static v3 light_dir(const Ctx* cx, int li, v3 p, v3 normal, uint32_t key, float*
   *prob = 0.0f;
   switch (L->kind) {
     case B200RT_LIGHT_AREA: {
-      const float e1 = rng_u01(key, dim), e2 = rng_u01(key, dim + 1);
+      const float e1 = DRAW7(area, key, dim);
+      const float e2 = DRAW7(area, key, dim + 1);
       const v3 pos = add(add(ld(L->position), muls(ld(L->edge1), e1)), muls(ld(L->edge2), e2));
       const v3 dir = sub(pos, p);
       *distance = len(dir);
@@ -911,7 +966,8 @@ static v3 light_dir(const Ctx* cx, int li, v3 p, v3 normal, uint32_t key, float*
       *distance = 3.402823466e+38f;
       return neg(ld(L->edge1));
     case B200RT_LIGHT_ENV: {
-      const float e1 = rng_u01(key, dim), e2 = rng_u01(key, dim + 1);
+      const float e1 = DRAW7(env, key, dim);
+      const float e2 = DRAW7(env, key, dim + 1);
       const float phi = (float)(2 * M_PI * (double)e1);
       const float theta = acosf(e2);
       *distance = 3.402823466e+38f;
@@ -919,7 +975,9 @@ static v3 light_dir(const Ctx* cx, int li, v3 p, v3 normal, uint32_t key, float*
       return onb_dir(normal, theta, phi);
     }
     case B200RT_LIGHT_MESH: {
-      const float e0 = rng_u01(key, dim), e1 = sqrtf(rng_u01(key, dim + 1)), e2 = rng_u01(key, dim + 2);
+      const float e0 = DRAW7(mesh, key, dim);
+      const float e1 = sqrtf(DRAW7(mesh, key, dim + 1));
+      const float e2 = DRAW7(mesh, key, dim + 2);
       int tri = -1;
       for (int i = 0; i < L->cdf_count; i++)
         if (e0 <= d->light_cdf[L->cdf_begin + i]) { tri = d->light_tri[L->cdf_begin + i]; break; }
@@ -938,7 +996,8 @@ static v3 light_dir(const Ctx* cx, int li, v3 p, v3 normal, uint32_t key, float*
       return dir;
     }
     case B200RT_LIGHT_SPHERE: {
-      const float e1 = rng_u01(key, dim), e2 = rng_u01(key, dim + 1);
+      const float e1 = DRAW7(sphere, key, dim);
+      const float e2 = DRAW7(sphere, key, dim + 1);
       const b200rt_sphere* s = d->spheres + L->object;
       const v3 ps = xf_point(s->inv, p);
       v3 w = sub(ld(s->center), ps);
@@ -1075,7 +1134,8 @@ static v3 reflect7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, uin
     else rp = V(wr.x, wr.y, 1.0f);
     const v3 u = normalize(cross(rp, wr));
     const v3 v = normalize(cross(u, wr));
-    const float eu = rng_u01(key, 2) - 0.5f, ev = rng_u01(key, 3) - 0.5f;
+    const float eu = DRAW7(glossy, key, 2) - 0.5f;
+    const float ev = DRAW7(glossy, key, 3) - 0.5f;
     const v3 wrp = normalize(add(wr, muls(add(muls(u, eu), muls(v, ev)), m->roughness)));
     mr.o = add(p, muls(wrp, d->shadow_eps)); mr.d = wrp;
     mr.light_hit = ray->light_hit;
@@ -1121,8 +1181,16 @@ static v3 refract7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, uin
   Ray tr; memset(&tr, 0, sizeof(tr));
   tr.o = add(p, muls(tdir, d->shadow_eps)); tr.d = tdir; tr.time = ray->time; tr.in_medium = entering;
   tr.light_hit = ray->light_hit;
-  const v3 cr = send_ray7(cx, &rr, level + 1, rng_mix(key, 0x102u), 1);
-  const v3 ct = send_ray7(cx, &tr, level + 1, rng_mix(key, 0x103u), 1);
+  /* `r * send_ray(reflection) + (1 - r) * send_ray(transmission)`: the order of the two calls is unspecified in C++;
+   * the reference as built here (g++ 13 -O3) traces the TRANSMISSION first — visible only when the draws are replayed */
+  v3 cr, ct;
+  if (g_mt7.on) {
+    ct = send_ray7(cx, &tr, level + 1, rng_mix(key, 0x103u), 1);
+    cr = send_ray7(cx, &rr, level + 1, rng_mix(key, 0x102u), 1);
+  } else {
+    cr = send_ray7(cx, &rr, level + 1, rng_mix(key, 0x102u), 1);
+    ct = send_ray7(cx, &tr, level + 1, rng_mix(key, 0x103u), 1);
+  }
   return mulv(k, add(muls(cr, r), muls(ct, 1 - r)));
 }
 /* Scene::trace_ray — HW7/src/Scene.cpp:415-447 */
@@ -1159,7 +1227,8 @@ static v3 trace_path7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, 
   const b200rt_brdf* B = (m->brdf != -1) ? d->brdfs + m->brdf : NULL;
   if (!ray->in_medium && level < d->max_depth) {
     const v3 p = add(ray->o, muls(ray->d, hit->t));
-    const float e1 = rng_u01(key, 9), e2 = rng_u01(key, 10);
+    const float e1 = DRAW7(hemi, key, 9);
+    const float e2 = DRAW7(hemi, key, 10);
     const float phi = (float)(2 * M_PI * (double)e1);
     const float theta = d->importance_sampling ? asinf(sqrtf(e2)) : acosf(e2);
     const v3 n = hit->normal;
@@ -1258,7 +1327,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
   int strata_begin = 0, strata_end = 0x7fffffff;   /* ORACLE_STRATA=a:b: only those strata of every pixel (debugging) */
   if (getenv("ORACLE_STRATA")) sscanf(getenv("ORACLE_STRATA"), "%d:%d", &strata_begin, &strata_end);
   if (getenv("ORACLE_COLS")) { sscanf(getenv("ORACLE_COLS"), "%d:%d", &col_begin, &col_end); if (col_end > W) col_end = W; }
-#pragma omp parallel
+#pragma omp parallel if (!g_mt7.on)
   {
     OracleCounters cnt; memset(&cnt, 0, sizeof(cnt));
     Ctx cx = {d, &cnt};
@@ -1274,14 +1343,18 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
             for (int y = 0; y < ns; y++) {
               if (x * ns + y < strata_begin || x * ns + y >= strata_end) continue;
               const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), (uint32_t)(x * ns + y));
-              const float ex = rng_u01(key, 4), ey = rng_u01(key, 5);
+              /* draw order of HW7/src/Scene.cpp:47-61: jitter x, y, then (lens x, y), then time */
+              const float ex = DRAW7(render, key, 4);
+              const float ey = DRAW7(render, key, 5);
               const float sx = (x + ex) / ns, sy = (y + ey) / ns;
-              const float time = rng_u01(key, 6);
               Ray r;
               if (c->aperture == 0.0f) {
+                const float time = DRAW7(render, key, 6);
                 r = camera_ray(d, c, i + sx, j + sy, 0, 0, 0, time);
               } else {
-                const float dx = rng_u01(key, 7) * 2.0f - 1.0f, dy = rng_u01(key, 8) * 2.0f - 1.0f;
+                const float dx = DRAW7(render, key, 7) * 2.0f - 1.0f;
+                const float dy = DRAW7(render, key, 8) * 2.0f - 1.0f;
+                const float time = DRAW7(render, key, 6);
                 r = camera_ray(d, c, i + sx, j + sy, 1, dx, dy, time);
               }
               const v3 col = send_ray7(&cx, &r, 0, key, 0);
@@ -1357,15 +1430,19 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
         for (int x = 0; x < ns; x++)
           for (int y = 0; y < ns; y++) {
             const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), (uint32_t)(x * ns + y));
-            const float ex = rng_u01(key, 4), ey = rng_u01(key, 5);
+            /* HW5/HW6 draw in this order from one engine (HW6/src/Scene.cpp:60-77): jitter x, y, (lens x, y), time */
+            const float ex = DRAW7(render, key, 4);
+            const float ey = DRAW7(render, key, 5);
             const float sx = (x + ex) / ns, sy = (y + ey) / ns;
-            const float time = rng_u01(key, 6);
             Ray r;
             const float px_ = hw4ms ? (i + sx) : (i + sx - 0.5f), py_ = hw4ms ? (j + sy) : (j + sy - 0.5f);
             if (c->aperture == 0.0f) {
+              const float time = DRAW7(render, key, 6);
               r = camera_ray(d, c, px_, py_, 0, 0, 0, time);
             } else {
-              const float dx = rng_u01(key, 7) * 2.0f - 1.0f, dy = rng_u01(key, 8) * 2.0f - 1.0f;
+              const float dx = DRAW7(render, key, 7) * 2.0f - 1.0f;
+              const float dy = DRAW7(render, key, 8) * 2.0f - 1.0f;
+              const float time = DRAW7(render, key, 6);
               r = camera_ray(d, c, px_, py_, 1, dx, dy, time);
             }
             const v3 col = hw5 ? send_ray7(&cx, &r, 0, key, 0) : trace_ray(&cx, &r, d->max_depth, key, 0);
@@ -1533,45 +1610,6 @@ static void ppm_build_grid(OraclePpm* P, int width, int height) {
 /* Scene::photon_trace — PPM/src/Scene.cpp:106-249; RNG dims of the photon key: emission 0,1; bounce b: 8b+{2,3} hemisphere,
  * 8b+4 roulette, 8b+5 glass roulette */
 #define PPM_ALPHA 0.7f
-/* ---- the reference's own random streams, for the bit-exact pin of the photon pass -------------------------------
- * PPM draws from three function-local `thread_local static std::mt19937 generator(rd())` engines through
- * `std::uniform_real_distribution<float>(0, 1)`: Point_light::generate_photon (PPM/src/Point_light.cpp:10-14),
- * Scene::sample_hemisphere (PPM/src/Scene.cpp:17-21), Scene::photon_trace (:107-109).  oracle/ref_driver_ppm.cpp
- * runs the tree single-threaded with random_device interposed to a constant; with mt mode on, the restatement draws
- * from the same three streams in the same program order instead of its counter-based generator.
- * mt19937: the standard recurrence.  uniform_real_distribution<float> in libstdc++ (bits/random.tcc,
- * generate_canonical<float, 24>): ONE 32-bit draw, float(draw) / 2^32, and nextafter(1, 0) if that rounds to 1. */
-typedef struct { uint32_t x[624]; int i; } Mt19937;
-static void mt_seed(Mt19937* m, uint32_t seed) {
-  m->x[0] = seed;
-  for (int k = 1; k < 624; k++) m->x[k] = 1812433253u * (m->x[k - 1] ^ (m->x[k - 1] >> 30)) + (uint32_t)k;
-  m->i = 624;
-}
-static uint32_t mt_next(Mt19937* m) {
-  if (m->i >= 624) {
-    for (int k = 0; k < 624; k++) {
-      const uint32_t y = (m->x[k] & 0x80000000u) | (m->x[(k + 1) % 624] & 0x7fffffffu);
-      m->x[k] = m->x[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    }
-    m->i = 0;
-  }
-  uint32_t y = m->x[m->i++];
-  y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-  return y;
-}
-static float mt_u01(Mt19937* m) {
-  float r = (float)mt_next(m) / 4294967296.0f;
-  if (r >= 1.0f) r = nextafterf(1.0f, 0.0f);
-  return r;
-}
-static struct { int on; Mt19937 light, hemi, trace; float* state_out; int64_t state_cap; } g_mt;   /* test infrastructure: single-threaded use only */
-#define PPM_DRAW(stream, key, dim) (g_mt.on ? mt_u01(&g_mt.stream) : rng_u01((key), (dim)))
-/* state_out (optional): 5 floats per hit point {flux.rgb, radius_squared, n} written by the next oracle_ppm call */
-void oracle_ppm_mt_mode(int on, uint32_t seed, float* state_out, int64_t state_cap) {
-  g_mt.on = on; g_mt.state_out = on ? state_out : NULL; g_mt.state_cap = state_cap;
-  if (on) { mt_seed(&g_mt.light, seed); mt_seed(&g_mt.hemi, seed); mt_seed(&g_mt.trace, seed); }
-}
-
 static void ppm_photon_trace(const Ctx* cx, OraclePpm* P, Ray ray, v3 flux, uint32_t key, OracleCounters* pc) {
   const B200SceneDesc* d = cx->d;
   int depth = 0;

@@ -8,6 +8,8 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <random>
 #include <iostream>
 #include <string>
 #include <thread>
@@ -16,13 +18,26 @@
 #include "Pixel.h"
 #include "Scene.h"
 
+// REF_SEED=<n> in the environment: every std::random_device draw returns n (this definition wins over libstdc++'s at
+// link time) and the frame is rendered on ONE thread, so that the tree's mt19937 streams — all seeded by
+// `generator(rd())` — become one reproducible sequence which the oracle replays draw for draw (oracle_hw7_mt_mode).
+static long g_ref_seed = -1;
+unsigned int std::random_device::_M_getval() {
+  if (g_ref_seed >= 0) return (unsigned int)g_ref_seed;
+  static std::FILE* ur = std::fopen("/dev/urandom", "rb");
+  unsigned int v = 0;
+  if (!ur || std::fread(&v, sizeof(v), 1, ur) != 1) v = (unsigned int)std::chrono::steady_clock::now().time_since_epoch().count();
+  return v;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) {
     std::fprintf(stderr, "usage: %s scene.xml\n", argv[0]);
     return 1;
   }
+  if (const char* e = std::getenv("REF_SEED")) g_ref_seed = std::atol(e);
   Scene scene(argv[1]);
-  unsigned workers = std::thread::hardware_concurrency();
+  unsigned workers = g_ref_seed >= 0 ? 1u : std::thread::hardware_concurrency();
   for (size_t cam = 0; cam < scene.cameras.size(); cam++) {
     const Image_plane& plane = scene.cameras[cam].get_image_plane();
     const int W = plane.width, H = plane.height;
@@ -30,10 +45,14 @@ int main(int argc, char** argv) {
     if (workers == 0 || (unsigned)H < workers) workers = 1;
     std::cout << "Starting rendering on #" << workers << " thread(s)" << std::endl;
     const auto t0 = std::chrono::steady_clock::now();
-    std::vector<std::thread> pool;
-    for (unsigned w = 0; w < workers; w++)
-      pool.emplace_back([&, w] { scene.render_image((int)cam, film.data(), (int)w, (int)workers); });
-    for (std::thread& t : pool) t.join();
+    if (workers == 1) {
+      scene.render_image((int)cam, film.data(), 0, 1);   // on this thread: its thread_local engines are the ones seeded above
+    } else {
+      std::vector<std::thread> pool;
+      for (unsigned w = 0; w < workers; w++)
+        pool.emplace_back([&, w] { scene.render_image((int)cam, film.data(), (int)w, (int)workers); });
+      for (std::thread& t : pool) t.join();
+    }
     const auto t1 = std::chrono::steady_clock::now();
     const long long us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
     const std::string name = scene.cameras[cam].get_filename() + ".f32";

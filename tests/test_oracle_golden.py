@@ -142,6 +142,65 @@ def test_oracle_textured_scenes_match_live_reference_floats(tmp_path, seed):
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), tree
 
 
+def _replay(tree, xml, workdir):
+    """Reference twin on ONE thread with std::random_device interposed to 795 (REF_SEED) against the oracle replaying
+    the same mt19937 streams (oracle_hw7_mt_mode): returns (oracle floats, reference floats)."""
+    import ctypes as C
+    sem = tree.rstrip("f")
+    os.environ["REF_SEED"] = "795"
+    try:
+        want = list(cpu.run_reference(tree, xml, workdir=workdir)["hdr"].values())[0]
+    finally:
+        del os.environ["REF_SEED"]
+    hs = scene.HostScene(scene.parse_xml(xml, sem, base_dir=workdir))
+    L = cpu.load()
+    L.oracle_hw7_mt_mode.restype = None
+    L.oracle_hw7_mt_mode.argtypes = [C.c_int, C.c_uint32]
+    L.oracle_hw7_mt_mode(1, 795)
+    try:
+        rgbw, _, _, _ = cpu.render(hs, 0)
+    finally:
+        L.oracle_hw7_mt_mode(0, 0)
+    return rgbw[..., :3] / rgbw[..., 3:4], want
+
+
+@pytest.mark.parametrize("tree,pt,spp", [("hw7f", False, 9), ("hw7f", True, 9), ("hw7f", True, 16), ("hw6", False, 9),
+                                         ("hw5", False, 4)])
+def test_oracle_replays_the_stochastic_paths_draw_for_draw(tmp_path, tree, pt, spp):
+    """The stochastic rows (a2 jitter, a10 area / mesh / sphere light sampling, a11 glossy, a14 path tracing) pinned
+    EXACTLY in the one setting where the reference is a function: one thread, known seeds.  Every engine of the tree
+    is `mt19937 generator(rd())`; the float-dump driver defines random_device::_M_getval itself, and the oracle draws
+    from the same per-site streams in the same program order (libstdc++'s uniform_real_distribution<float> restated).
+    All floats of the frame are the same bits — light-mesh CDF pick, cone sampling with its re-intersection, the
+    double-counted direct light of trace_path, the sigma-1/2 splat sums of HW5/HW6.  (It also showed that the tree, as
+    built here, traces the TRANSMISSION child of a dielectric before the reflection child: unspecified in C++.)"""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    import re
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=48, height=36, n=6, spp=spp, depth=3, stochastic_lights=True,
+                           path_tracing=pt, importance=True, light_scale=0.5, mesh_slices=(6, 7), image_name="o.png")
+    if tree != "hw7f":
+        xml = re.sub(r"    <Light(Mesh|Sphere).*?</Light(Mesh|Sphere)>\n", "", xml, flags=re.S)   # HW7-only objects
+        xml = re.sub(r"      <Roughness>.*?</Roughness>\n", "", xml)   # HW5/HW6 seed their glossy engines from the clock
+    got, want = _replay(tree, xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
+@pytest.mark.parametrize("tree", ["hw7f", "hw6"])
+def test_oracle_replays_dof_and_motion_blur_draw_for_draw(tmp_path, tree):
+    """cfg3's features (depth of field, motion blur, area lights, glossy mirror, glass) through the same replay."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    import re
+    from ceng795_b200 import scenes
+    xml = scenes.cfg3_hw3(n=12, width=40, height=30, spp=9, depth=3, image_name="o.png")
+    if tree != "hw7f":
+        xml = re.sub(r"      <Roughness>.*?</Roughness>\n", "", xml)
+    got, want = _replay(tree, xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
 def test_parse_time():
     assert cpu.parse_time_ms("4 seconds 790 milliseconds 898 microseconds") == pytest.approx(4790.898)
     assert cpu.parse_time_ms("1 minute 2 seconds 0 milliseconds 5 microseconds") == pytest.approx(62000.005)
