@@ -534,6 +534,30 @@ static struct { int on; Mt19937 light, hemi, trace; float* state_out; int64_t st
  * REF_SINGLE_THREAD=1 runs the tree on one thread with random_device interposed. */
 static struct { int on; Mt19937 render, area, mesh, sphere, env, glossy, hemi; } g_mt7;
 #define DRAW7(stream, key, dim) (g_mt7.on ? mt_u01(&g_mt7.stream) : rng_u01((key), (dim)))
+/* Clock-seeded engines (HW2-HW4 everywhere; the glossy engines of HW5/HW6): `engine.seed(system_clock::now()...)` on a
+ * FRESH engine per pixel (jitter / lens / time: three engines with the same seed, HW3/src/Scene.cpp:40-53) or per call
+ * (area light :184-189, glossy u and v :247-256).  The drivers interpose std::chrono::system_clock::now() too
+ * (REF_SEED), which turns every such engine into "the first draws of engine(seed)".  HW2/HW3 use
+ * default_random_engine = minstd_rand0, HW4-HW6 mt19937. */
+typedef struct { int is_mt; uint64_t x; Mt19937 mt; } ClockEngine;
+static struct { int on; uint32_t seed; } g_clk;
+static void ce_seed(ClockEngine* e, int is_mt) {
+  e->is_mt = is_mt;
+  if (is_mt) { mt_seed(&e->mt, g_clk.seed); return; }
+  e->x = g_clk.seed % 2147483647u;        /* linear_congruential_engine::seed: 0 becomes 1 */
+  if (e->x == 0) e->x = 1;
+}
+static float ce_u01(ClockEngine* e) {
+  if (e->is_mt) return mt_u01(&e->mt);
+  /* minstd_rand0: x <- 16807 x mod (2^31 - 1), range [1, 2^31 - 2]; generate_canonical<float, 24>: one draw,
+   * float(x - min) / float(range) with range = 2147483646 (rounds to 2^31 as a float) */
+  e->x = (e->x * 16807u) % 2147483647u;
+  float r = (float)(e->x - 1u) / (float)2147483646.0L;
+  if (r >= 1.0f) r = nextafterf(1.0f, 0.0f);
+  return r;
+}
+void oracle_clock_mode(int on, uint32_t seed) { g_clk.on = on; g_clk.seed = seed; }
+
 void oracle_hw7_mt_mode(int on, uint32_t seed) {
   g_mt7.on = on;
   if (on) {
@@ -589,7 +613,13 @@ static v3 trace_ray(const Ctx* cx, const Ray* ray, int depth, uint32_t key, int 
       v3 lpos = ld(L->position);
       if (L->kind == B200RT_LIGHT_AREA) {
         /* HW3/src/Scene.cpp:184-191; the clock-seeded engine is replaced by the shared stream */
-        const float e1 = rng_u01(key, 16 + 2 * rdim), e2 = rng_u01(key, 17 + 2 * rdim);
+        float e1, e2;
+        if (g_clk.on) {   /* a fresh clock-seeded engine per area light per shading point */
+          ClockEngine eng; ce_seed(&eng, sem_hw4(d));
+          e1 = ce_u01(&eng); e2 = ce_u01(&eng);
+        } else {
+          e1 = rng_u01(key, 16 + 2 * rdim); e2 = rng_u01(key, 17 + 2 * rdim);
+        }
         rdim++;
         lpos = add(add(lpos, muls(ld(L->edge1), e1)), muls(ld(L->edge2), e2));
       }
@@ -658,8 +688,12 @@ static v3 trace_ray(const Ctx* cx, const Ray* ray, int depth, uint32_t key, int 
       else rp = V(wr.x, wr.y, 1.0f);
       const v3 u = normalize(cross(rp, wr));
       const v3 v = normalize(cross(u, wr));
-      const float eu = DRAW7(glossy, key, 2) - 0.5f;
-    const float ev = DRAW7(glossy, key, 3) - 0.5f;
+      float eu = DRAW7(glossy, key, 2) - 0.5f;
+    float ev = DRAW7(glossy, key, 3) - 0.5f;
+    if (g_clk.on && !sem_hw7(d)) {   /* fresh clock-seeded engines for u and for v: the same first draw twice */
+      ClockEngine gu; ce_seed(&gu, sem_hw4(d)); eu = ce_u01(&gu) - 0.5f;
+      ClockEngine gv; ce_seed(&gv, sem_hw4(d)); ev = ce_u01(&gv) - 0.5f;
+    }
       dir = normalize(add(wr, muls(add(muls(u, eu), muls(v, ev)), m->roughness)));
     }
     Ray mr; memset(&mr, 0, sizeof(mr));
@@ -1134,8 +1168,12 @@ static v3 reflect7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, uin
     else rp = V(wr.x, wr.y, 1.0f);
     const v3 u = normalize(cross(rp, wr));
     const v3 v = normalize(cross(u, wr));
-    const float eu = DRAW7(glossy, key, 2) - 0.5f;
-    const float ev = DRAW7(glossy, key, 3) - 0.5f;
+    float eu = DRAW7(glossy, key, 2) - 0.5f;
+    float ev = DRAW7(glossy, key, 3) - 0.5f;
+    if (g_clk.on && !sem_hw7(d)) {   /* fresh clock-seeded engines for u and for v: the same first draw twice */
+      ClockEngine gu; ce_seed(&gu, sem_hw4(d)); eu = ce_u01(&gu) - 0.5f;
+      ClockEngine gv; ce_seed(&gv, sem_hw4(d)); ev = ce_u01(&gv) - 0.5f;
+    }
     const v3 wrp = normalize(add(wr, muls(add(muls(u, eu), muls(v, ev)), m->roughness)));
     mr.o = add(p, muls(wrp, d->shadow_eps)); mr.d = wrp;
     mr.light_hit = ray->light_hit;
@@ -1424,25 +1462,30 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
     Ctx cx = {d, &cnt};
     const int hw4ms = d->semantics >= B200RT_SEM_HW4;   /* HW4-HW6: sigma 1/2, absolute sample positions */
     const int hw5 = sem_hw5(d);
+    ClockEngine ce_ms, ce_dof, ce_time;
+    memset(&ce_ms, 0, sizeof(ce_ms)); memset(&ce_dof, 0, sizeof(ce_dof)); memset(&ce_time, 0, sizeof(ce_time));
     for (int j = row_begin; j < row_end; j++)
       for (int i = 0; i < W; i++) {
         const int pix = j * W + i;
         for (int x = 0; x < ns; x++)
           for (int y = 0; y < ns; y++) {
             const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), (uint32_t)(x * ns + y));
-            /* HW5/HW6 draw in this order from one engine (HW6/src/Scene.cpp:60-77): jitter x, y, (lens x, y), time */
-            const float ex = DRAW7(render, key, 4);
-            const float ey = DRAW7(render, key, 5);
+            /* HW5/HW6 draw in this order from one engine (HW6/src/Scene.cpp:60-77): jitter x, y, (lens x, y), time;
+             * HW2-HW4 from three engines re-seeded from the clock at every pixel (HW3/src/Scene.cpp:40-53) */
+            const int clk = g_clk.on && !hw5;
+            if (clk && x == 0 && y == 0) { ce_seed(&ce_ms, sem_hw4(d)); ce_seed(&ce_dof, sem_hw4(d)); ce_seed(&ce_time, sem_hw4(d)); }
+            const float ex = clk ? ce_u01(&ce_ms) : DRAW7(render, key, 4);
+            const float ey = clk ? ce_u01(&ce_ms) : DRAW7(render, key, 5);
             const float sx = (x + ex) / ns, sy = (y + ey) / ns;
             Ray r;
             const float px_ = hw4ms ? (i + sx) : (i + sx - 0.5f), py_ = hw4ms ? (j + sy) : (j + sy - 0.5f);
             if (c->aperture == 0.0f) {
-              const float time = DRAW7(render, key, 6);
+              const float time = clk ? ce_u01(&ce_time) : DRAW7(render, key, 6);
               r = camera_ray(d, c, px_, py_, 0, 0, 0, time);
             } else {
-              const float dx = DRAW7(render, key, 7) * 2.0f - 1.0f;
-              const float dy = DRAW7(render, key, 8) * 2.0f - 1.0f;
-              const float time = DRAW7(render, key, 6);
+              const float dx = (clk ? ce_u01(&ce_dof) : DRAW7(render, key, 7)) * 2.0f - 1.0f;
+              const float dy = (clk ? ce_u01(&ce_dof) : DRAW7(render, key, 8)) * 2.0f - 1.0f;
+              const float time = clk ? ce_u01(&ce_time) : DRAW7(render, key, 6);
               r = camera_ray(d, c, px_, py_, 1, dx, dy, time);
             }
             const v3 col = hw5 ? send_ray7(&cx, &r, 0, key, 0) : trace_ray(&cx, &r, d->max_depth, key, 0);

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <random>
 #include <iostream>
 #include <string>
@@ -21,7 +22,15 @@
 // REF_SEED=<n> in the environment: every std::random_device draw returns n (this definition wins over libstdc++'s at
 // link time) and the frame is rendered on ONE thread, so that the tree's mt19937 streams — all seeded by
 // `generator(rd())` — become one reproducible sequence which the oracle replays draw for draw (oracle_hw7_mt_mode).
+// HW2-HW4 (and the glossy engines of HW5/HW6) seed from std::chrono::system_clock::now() instead: interposed the same
+// way, so `engine.seed(now().time_since_epoch().count())` becomes `engine.seed(REF_SEED)`.
 static long g_ref_seed = -1;
+std::chrono::system_clock::time_point std::chrono::system_clock::now() noexcept {
+  if (g_ref_seed >= 0) return time_point(duration(g_ref_seed));
+  timespec ts;
+  clock_gettime(CLOCK_REALTIME, &ts);
+  return time_point(duration((long long)ts.tv_sec * 1000000000LL + ts.tv_nsec));
+}
 unsigned int std::random_device::_M_getval() {
   if (g_ref_seed >= 0) return (unsigned int)g_ref_seed;
   static std::FILE* ur = std::fopen("/dev/urandom", "rb");

@@ -143,8 +143,9 @@ def test_oracle_textured_scenes_match_live_reference_floats(tmp_path, seed):
 
 
 def _replay(tree, xml, workdir):
-    """Reference twin on ONE thread with std::random_device interposed to 795 (REF_SEED) against the oracle replaying
-    the same mt19937 streams (oracle_hw7_mt_mode): returns (oracle floats, reference floats)."""
+    """Reference twin on ONE thread with std::random_device AND std::chrono::system_clock::now interposed to 795
+    (REF_SEED) against the oracle replaying the same engines (oracle_hw7_mt_mode, oracle_clock_mode):
+    returns (oracle floats, reference floats)."""
     import ctypes as C
     sem = tree.rstrip("f")
     os.environ["REF_SEED"] = "795"
@@ -154,18 +155,24 @@ def _replay(tree, xml, workdir):
         del os.environ["REF_SEED"]
     hs = scene.HostScene(scene.parse_xml(xml, sem, base_dir=workdir))
     L = cpu.load()
-    L.oracle_hw7_mt_mode.restype = None
-    L.oracle_hw7_mt_mode.argtypes = [C.c_int, C.c_uint32]
-    L.oracle_hw7_mt_mode(1, 795)
+    for f in (L.oracle_hw7_mt_mode, L.oracle_clock_mode):
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_uint32]
+    L.oracle_hw7_mt_mode(1, 795)      # engines seeded by random_device
+    L.oracle_clock_mode(1, 795)       # engines seeded by the clock (HW3, HW4; glossy in HW5 / HW6)
     try:
         rgbw, _, _, _ = cpu.render(hs, 0)
     finally:
         L.oracle_hw7_mt_mode(0, 0)
-    return rgbw[..., :3] / rgbw[..., 3:4], want
+        L.oracle_clock_mode(0, 0)
+    got = rgbw[..., :3] / rgbw[..., 3:4]
+    if sem in ("hw3", "hw4"):
+        got = np.clip(got, 0, 255)    # their Pixel::get_color clamps
+    return got, want
 
 
 @pytest.mark.parametrize("tree,pt,spp", [("hw7f", False, 9), ("hw7f", True, 9), ("hw7f", True, 16), ("hw6", False, 9),
-                                         ("hw5", False, 4)])
+                                         ("hw5", False, 4), ("hw4f", False, 9)])
 def test_oracle_replays_the_stochastic_paths_draw_for_draw(tmp_path, tree, pt, spp):
     """The stochastic rows (a2 jitter, a10 area / mesh / sphere light sampling, a11 glossy, a14 path tracing) pinned
     EXACTLY in the one setting where the reference is a function: one thread, known seeds.  Every engine of the tree
@@ -182,21 +189,20 @@ def test_oracle_replays_the_stochastic_paths_draw_for_draw(tmp_path, tree, pt, s
                            path_tracing=pt, importance=True, light_scale=0.5, mesh_slices=(6, 7), image_name="o.png")
     if tree != "hw7f":
         xml = re.sub(r"    <Light(Mesh|Sphere).*?</Light(Mesh|Sphere)>\n", "", xml, flags=re.S)   # HW7-only objects
-        xml = re.sub(r"      <Roughness>.*?</Roughness>\n", "", xml)   # HW5/HW6 seed their glossy engines from the clock
     got, want = _replay(tree, xml, str(tmp_path))
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
-@pytest.mark.parametrize("tree", ["hw7f", "hw6"])
+@pytest.mark.parametrize("tree", ["hw3f", "hw4f", "hw5", "hw6", "hw7f"])
 def test_oracle_replays_dof_and_motion_blur_draw_for_draw(tmp_path, tree):
-    """cfg3's features (depth of field, motion blur, area lights, glossy mirror, glass) through the same replay."""
+    """cfg3's features (depth of field, motion blur, area lights, glossy mirror, glass, the Gaussian splat) through the
+    same replay — including cfg3's own tree, HW3, whose engines are minstd_rand0 re-seeded from the clock at every
+    pixel, area-light sample and glossy bounce (so, under a constant clock, the same few numbers over and over: a
+    degenerate sampler, but the whole code path, and every float of the frame agrees)."""
     if not cpu.have_ref(tree):
         pytest.skip("oracle/_ref not built on this box")
-    import re
     from ceng795_b200 import scenes
     xml = scenes.cfg3_hw3(n=12, width=40, height=30, spp=9, depth=3, image_name="o.png")
-    if tree != "hw7f":
-        xml = re.sub(r"      <Roughness>.*?</Roughness>\n", "", xml)
     got, want = _replay(tree, xml, str(tmp_path))
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
