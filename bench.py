@@ -44,7 +44,7 @@ def workloads(args):
     return {
         "cfg1": dict(tree="hw1", xml=lambda r: scenes.cfg1_hw1(), base_dir=None,
                      desc="cfg1: HW1 scene, 64 spheres + 2 meshes (2000 tris) + 10 triangles, 3 point lights, "
-                          "Blinn-Phong + mirror depth 6, 800x800, 1 spp (brute force over all primitives, like HW1)"),
+                          "Blinn-Phong + mirror depth 6, 800x800, 1 spp (HW1 tests every primitive; here a SAH tree + its order-dependent rule replayed)"),
         "cfg2": dict(tree="hw3", xml=lambda r: scenes.cfg2_hw3(cam_angle_deg=45.0 * r), base_dir=None,
                      desc="cfg2: HW3-dialect BVH scene, 1048352-tri heightfield + 8 instances + 4 spheres, "
                           "2 point lights, mirror depth 2, 1920x1080, 1 spp"),
@@ -342,10 +342,20 @@ def run_b200(args):
         n_closest = agg["photon_rays"]
         ext_bytes = 64 * agg["nodes_visited"] + 48 * agg["tris_tested"] + (32 + 24) * n_closest
         n_ext_launch = max(1, args.steps * (sc.spec.max_depth - 1))
-        kernel = "k_trace_fast<false,7> (photon closest-hit traversal)"
         per_ray = {"nodes": agg["nodes_visited"] / max(1, n_closest), "tris": agg["tris_tested"] / max(1, n_closest),
-                   "hit_points_scanned_per_photon_ray": agg["cell_scans"] / max(1, n_closest)}
-        extra = {"deposit_kernel_bytes": 32 * agg["cell_scans"] + 16 * agg["deposits"]}
+                   "hit_points_scanned_per_photon_ray": agg["cell_scans"] / max(1, n_closest),
+                   "deposits_per_photon_ray": agg["deposits"] / max(1, n_closest)}
+        # the dominant kernel of a pass is the deposit (90 % of it, profiles/r01i_launches_summary.txt): per photon ray
+        # 52 B in + 56 B out of the pool, 16 B per scanned grid entry, 64 B record + 4 B count + 16 B flux per deposit
+        # ("32 k + 16 a", with this layout's record sizes)
+        dep_bytes = 108 * n_closest + 16 * agg["cell_scans"] + 84 * agg["deposits"]
+        trav_gbs = ext_bytes / (ms_stage["ms_extend"] * 1e-3) / 1e9 if ms_stage["ms_extend"] > 0 else None
+        extra = {"traversal_kernel": {"kernel": "k_trace_fast<false,7> (photon closest-hit traversal)",
+                                      "achieved": trav_gbs, "frac": (trav_gbs / hbm) if trav_gbs else None,
+                                      "avg_launch_ms": ms_stage["ms_extend"] / n_ext_launch}}
+        kernel = "k_ppm_photon_shade (scatter + cell scan + hit-point radius / flux update)"
+        ext_bytes = dep_bytes
+        ms_stage = dict(ms_stage, ms_extend_for_roofline=ms_stage["ms_deposit"])
     else:
         n_closest = agg["rays_primary"] + agg["rays_secondary"]
         ext_bytes = (64 * agg["nodes_visited"] + 48 * agg["tris_tested"] + 20 * agg["spheres_tested"]
@@ -354,12 +364,16 @@ def run_b200(args):
                     + 112 * agg["sh_instances_entered"] + (36 + 1) * agg["rays_shadow"])
         sh_gbs = sh_bytes / (ms_stage["ms_shadow"] * 1e-3) / 1e9 if ms_stage["ms_shadow"] > 0 else None
         n_ext_launch = max(1, args.steps * (sc.spec.max_depth + 1))
-        kernel = ("k_extend_hw1 (brute-force closest hit, shared-memory triangle tiles)" if wl["tree"] == "hw1" else
+        kernel = ("k_trace_hw1_fast<false> (SAH tree over all triangles, HW1's order-dependent rule on the near-tie set)"
+                  if wl["tree"] == "hw1" else
                   f"k_trace_fast<false,{7 if wl['tree'] == 'hw7' else 2}> (closest-hit traversal, SAH tree + reference gate)")
         per_ray = {"nodes": agg["nodes_visited"] / max(1, n_closest), "tris": agg["tris_tested"] / max(1, n_closest)}
         extra = {"shadow_kernel": {"achieved": sh_gbs, "frac": (sh_gbs / hbm) if sh_gbs else None,
                                    "nodes_per_ray": agg["sh_nodes_visited"] / max(1, agg["rays_shadow"])}}
-    ext_gbs = ext_bytes / (ms_stage["ms_extend"] * 1e-3) / 1e9 if ms_stage["ms_extend"] > 0 else None
+    dom_ms = ms_stage.pop("ms_extend_for_roofline", None) if ppm else None   # PPM: the deposit stage is the dominant kernel
+    if dom_ms is None:
+        dom_ms = ms_stage["ms_extend"]
+    ext_gbs = ext_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -396,7 +410,7 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": ext_gbs, "peak": hbm, "peak_source": hbm_src,
                      "unit": "GB/s", "frac": (ext_gbs / hbm) if ext_gbs else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": ext_bytes / n_ext_launch,
-                     "avg_launch_ms": ms_stage["ms_extend"] / n_ext_launch, "per_ray": per_ray, **extra},
+                     "avg_launch_ms": dom_ms / n_ext_launch, "per_ray": per_ray, **extra},
     }
     if ppm:
         line["config"]["photons_per_step"] = photons
