@@ -568,6 +568,10 @@ __device__ __forceinline__ float gaussian_filter(float x, float y, float sigma) 
   return (float)(exp((double)(-(x * x + y * y) / (2 * sigma * sigma))) /
                  (double)(float)(2 * 3.14159265358979323846 * (double)sigma));
 }
+// HW2/Scene.cpp:12-14: the same without the float cast of the divisor
+__device__ __forceinline__ float gaussian_filter_hw2(float x, float y, float sigma) {
+  return (float)(exp((double)(-(x * x + y * y) / (2 * sigma * sigma))) / (2 * 3.14159265358979323846 * (double)sigma));
+}
 
 // ---- combine: fold children into parents, deepest wave first -------------------
 __global__ void k_combine(DScene S, Pool P, const WaveInfo* waves, int d, float4* accum) {
@@ -627,7 +631,9 @@ __global__ void k_combine(DScene S, Pool P, const WaveInfo* waves, int d, float4
             if (ai < 0 || ai >= W) continue;
             const float fx = ((float)i + sx) - ((float)ai + 0.5f);
             const float fy = ((float)j + sy) - ((float)aj + 0.5f);
-            const float w = gaussian_filter(fx, fy, S.semantics == B200RT_SEM_HW4 ? 1.5f / 3.0f : 1.0f / 3.0f);
+            const float w = S.semantics == B200RT_SEM_HW2
+                                ? gaussian_filter_hw2(fx, fy, 1.0f / 3.0f)
+                                : gaussian_filter(fx, fy, S.semantics == B200RT_SEM_HW4 ? 1.5f / 3.0f : 1.0f / 3.0f);
             // Pixel::add_color(color, w): one 16-byte vector atomic (sm_90+) instead of four scalar ones
             atomicAdd(accum + (size_t)aj * W + ai, make_float4(color.x * w, color.y * w, color.z * w, w));
           }

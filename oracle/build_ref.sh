@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw3f hw4f hw7f probe ppmeye)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -55,6 +55,20 @@ build_tree_driver() { # name dir : the tree's objects except main.cpp + our floa
   $CXX -pthread -Wl,--allow-multiple-definition "$drv" "${rest[@]}" -o "$OUT/${name}_raytracer"
   echo "built $OUT/${name}_raytracer"
 }
+build_flat_driver() { # name dir : HW2 lives in one flat directory; same float-dump twin as build_tree_driver
+  local name=$1 dir=$2; shift 2
+  local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
+  local objs=()
+  for f in "$dir"/*.cpp "$dir"/lodepng/*.cpp "$HERE/ref_driver_hdr.cpp"; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    local o="$objdir/$(basename "$f" .cpp).o"; objs+=("$o")
+    if [ ! -f "$o" ] || [ "$f" -nt "$o" ]; then $CXX $FLAGS "$@" -I"$dir" -c "$f" -o "$o" & fi
+  done
+  wait
+  local drv="$objdir/ref_driver_hdr.o"; local rest=(); for o in "${objs[@]}"; do [ "$o" = "$drv" ] || rest+=("$o"); done
+  $CXX -pthread -Wl,--allow-multiple-definition "$drv" "${rest[@]}" -o "$OUT/${name}_raytracer"
+  echo "built $OUT/${name}_raytracer"
+}
 build_probe() { # leaf known-answer probe: HW7's objects except main.cpp + oracle/ref_probe.cpp
   local dir="$REF/HW7" objdir="$OUT/obj_hw7"
   [ -d "$objdir" ] || build_tree hw7 "$dir"
@@ -89,6 +103,7 @@ for t in "${TREES[@]}"; do
     hw5) build_tree_driver hw5 "$REF/HW5" ;;
     hw6) build_tree_driver hw6 "$REF/HW6" ;;
     hw7) build_tree hw7 "$REF/HW7" ;;
+    hw2f) build_flat_driver hw2f "$REF/HW2" -DREF_RAW_PIXEL ;;
     hw3f) build_tree_driver hw3f "$REF/HW3" ;;   # float-dump twins of trees whose own main writes 8-bit PNGs:
     hw4f) build_tree_driver hw4f "$REF/HW4" ;;   # they pin the oracle at float level (tests/test_oracle_golden.py)
     hw7f) build_tree_driver hw7f "$REF/HW7" ;;

@@ -19,7 +19,7 @@ _TREE_BIN = {"hw1": "hw1_raytracer", "hw2": "hw2_raytracer", "hw3": "hw3_raytrac
              "hw4": "hw4_raytracer", "hw5": "hw5_raytracer", "hw6": "hw6_raytracer", "hw7": "hw7_raytracer",
              "ppm": "ppm_raytracer",
              # float-dump twins (oracle/ref_driver_hdr.cpp instead of the tree's main.cpp)
-             "hw3f": "hw3f_raytracer", "hw4f": "hw4f_raytracer", "hw7f": "hw7f_raytracer"}
+             "hw2f": "hw2f_raytracer", "hw3f": "hw3f_raytracer", "hw4f": "hw4f_raytracer", "hw7f": "hw7f_raytracer"}
 
 
 class Counters(C.Structure):

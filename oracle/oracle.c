@@ -1341,7 +1341,11 @@ static Ray camera_ray(const B200SceneDesc* d, const b200rt_camera* c, float x, f
   return r;
 }
 
-/* gaussian_filter — HW3/src/Scene.cpp:15-17 */
+/* gaussian_filter — HW3/src/Scene.cpp:15-17 divides by (float)(2 pi sigma); HW2/Scene.cpp:12-14 by the double
+ * 2 * M_PI * sigma (no cast): the weights differ by an ulp now and then (found by the replay against the HW2 tree) */
+static inline float gaussian_filter_hw2(float x, float y, float sigma) {
+  return (float)(exp(-(x * x + y * y) / (2 * sigma * sigma)) / (2 * M_PI * sigma));
+}
 static inline float gaussian_filter(float x, float y, float sigma) {
   return (float)(exp(-(x * x + y * y) / (2 * sigma * sigma)) / (float)(2 * M_PI * sigma));
 }
@@ -1495,7 +1499,8 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
                 if (ai < 0 || ai >= W) continue;
                 const float fx = (i + sx) - (ai + 0.5f);
                 const float fy = (j + sy) - (aj + 0.5f);
-                const float w = gaussian_filter(fx, fy, hw4ms ? 1.5f / 3.0f : 1.0f / 3.0f);
+                const float w = d->semantics == B200RT_SEM_HW2 ? gaussian_filter_hw2(fx, fy, 1.0f / 3.0f)
+                                                               : gaussian_filter(fx, fy, hw4ms ? 1.5f / 3.0f : 1.0f / 3.0f);
                 float* px = rgbw + 4 * (size_t)(aj * W + ai);
                 px[0] += col.x * w; px[1] += col.y * w; px[2] += col.z * w; px[3] += w;
               }

@@ -70,7 +70,11 @@ int main(int argc, char** argv) {
     const int32_t hdr[2] = {W, H};
     std::fwrite(hdr, sizeof(hdr), 1, f);
     for (size_t p = 0; p < film.size(); p++) {
+#ifdef REF_RAW_PIXEL   // HW2: get_color() truncates to clamped ints (HW2/Pixel.h:17-27); dump color / weight itself
+      const Vector3 c = film[p].weight == 0 ? Vector3(0.0f) : film[p].color / film[p].weight;
+#else
       const Vector3 c = film[p].get_color();
+#endif
       const float rgb[3] = {c.x, c.y, c.z};
       std::fwrite(rgb, sizeof(rgb), 1, f);
     }

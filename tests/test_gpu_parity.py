@@ -385,3 +385,19 @@ def test_device_built_tree_full_size(gpu):
     assert np.array_equal(ids1, ids0) and np.array_equal(t1.view(np.uint32), t0.view(np.uint32))
     print(f"LBVH build of 1 M triangles: {ms:.2f} ms; frame {st0.ms_total:.2f} ms (SAH) -> {st1.ms_total:.2f} ms (LBVH)")
     assert ms < 100.0
+
+
+@pytest.mark.parametrize("tree", ["hw2", "hw3"])
+def test_multisample_splat_matches_oracle(gpu, tree):
+    """HW2 / HW3 multi-sample frames (jitter + 3x3 Gaussian splat sigma 1/3; HW2 divides its weight by the double
+    2 pi sigma, HW3 by the float): matched samples on both sides, float atomics on the device."""
+    xml = scenes.cfg2_hw3(n=16, width=64, height=48, n_instances=0 if tree == "hw2" else 3, depth=3, glass=True)
+    assert "<NumSamples>1</NumSamples>" in xml
+    xml = xml.replace("<NumSamples>1</NumSamples>", "<NumSamples>9</NumSamples>")
+    sc = scene.Scene(xml, tree)
+    rgbw, st = sc.render_image(0, seed=3)
+    o_rgbw, _, _, cnt = cpu.render(sc.host, 0, seed=3)
+    assert (st.rays_primary, st.rays_shadow, st.rays_secondary) == (cnt.rays_primary, cnt.rays_shadow, cnt.rays_secondary)
+    assert np.allclose(rgbw[..., 3], o_rgbw[..., 3], rtol=2e-6)          # the sums of weights
+    a, b = rgbw[..., :3] / rgbw[..., 3:4], o_rgbw[..., :3] / o_rgbw[..., 3:4]
+    assert np.max(np.abs(a - b) / (np.abs(b) + 1.0)) < 1e-5

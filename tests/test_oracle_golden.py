@@ -167,7 +167,7 @@ def _replay(tree, xml, workdir):
         L.oracle_clock_mode(0, 0)
     got = rgbw[..., :3] / rgbw[..., 3:4]
     if sem in ("hw3", "hw4"):
-        got = np.clip(got, 0, 255)    # their Pixel::get_color clamps
+        got = np.clip(got, 0, 255)    # their Pixel::get_color clamps (the HW2 twin dumps color / weight itself)
     return got, want
 
 
@@ -204,6 +204,21 @@ def test_oracle_replays_dof_and_motion_blur_draw_for_draw(tmp_path, tree):
     from ceng795_b200 import scenes
     xml = scenes.cfg3_hw3(n=12, width=40, height=30, spp=9, depth=3, image_name="o.png")
     got, want = _replay(tree, xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
+def test_oracle_replays_hw2_multisample_draw_for_draw(tmp_path):
+    """HW2's multi-sample loop (one minstd_rand0 per pixel seeded from the clock, 3x3 Gaussian splat) through the float
+    twin of the HW2 tree.  HW2's Pixel::get_color truncates to ints, so its PNGs hide the accumulators; the twin dumps
+    color / weight itself.  This is where HW2's filter weight turned out to differ from HW3's by an ulp (its divisor
+    2 * M_PI * sigma is not cast to float, HW2/Scene.cpp:12-14)."""
+    if not cpu.have_ref("hw2f"):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.cfg2_hw3(n=16, width=48, height=36, n_instances=0, depth=3, glass=True, image_name="o.png")
+    assert "<NumSamples>1</NumSamples>" in xml
+    xml = xml.replace("<NumSamples>1</NumSamples>", "<NumSamples>9</NumSamples>")
+    got, want = _replay("hw2f", xml, str(tmp_path))
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
