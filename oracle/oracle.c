@@ -524,7 +524,7 @@ static float mt_u01(Mt19937* m) {
   if (r >= 1.0f) r = nextafterf(1.0f, 0.0f);
   return r;
 }
-static struct { int on; Mt19937 light, hemi, trace; float* state_out; int64_t state_cap; } g_mt;   /* test infrastructure: single-threaded use only */
+static struct { int on; Mt19937 light, hemi, trace, eye; float* state_out; int64_t state_cap; } g_mt;   /* test infrastructure: single-threaded use only */
 #define PPM_DRAW(stream, key, dim) (g_mt.on ? mt_u01(&g_mt.stream) : rng_u01((key), (dim)))
 /* state_out (optional): 5 floats per hit point {flux.rgb, radius_squared, n} written by the next oracle_ppm call */
 /* HW7 (and HW3-HW6, whose sites are a subset): one engine per draw site, all seeded from random_device —
@@ -567,7 +567,7 @@ void oracle_hw7_mt_mode(int on, uint32_t seed) {
 }
 void oracle_ppm_mt_mode(int on, uint32_t seed, float* state_out, int64_t state_cap) {
   g_mt.on = on; g_mt.state_out = on ? state_out : NULL; g_mt.state_cap = state_cap;
-  if (on) { mt_seed(&g_mt.light, seed); mt_seed(&g_mt.hemi, seed); mt_seed(&g_mt.trace, seed); }
+  if (on) { mt_seed(&g_mt.light, seed); mt_seed(&g_mt.hemi, seed); mt_seed(&g_mt.trace, seed); mt_seed(&g_mt.eye, seed); }
 }
 
 static v3 tex_color(const B200SceneDesc* d, const b200rt_texture* T, float u, float v);
@@ -1768,7 +1768,10 @@ int oracle_ppm(const B200SceneDesc* d, int camera_index, uint64_t seed, int64_t 
         for (int x = 0; x < ns; x++)
           for (int y = 0; y < ns; y++) {
             const uint32_t key = rng_mix(rng_mix(s0, (uint32_t)pix), (uint32_t)(x * ns + y));
-            const float sx = (x + rng_u01(key, 4)) / ns, sy = (y + rng_u01(key, 5)) / ns;
+            /* jitter of the multi-sample eye pass: one engine per eye_trace_lines call, PPM/src/Scene.cpp:264-274 */
+            const float jx = PPM_DRAW(eye, key, 4);
+            const float jy = PPM_DRAW(eye, key, 5);
+            const float sx = (x + jx) / ns, sy = (y + jy) / ns;
             Ray r = camera_ray(d, c, i + sx, j + sy, 0, 0, 0, 0.0f);
             ppm_eye_trace(&cx, &P, &r, 0, V(1, 1, 1), pix, 1.0f);
           }

@@ -150,8 +150,8 @@ def test_oracle_eye_pass_and_hash_grid_match_the_ppm_tree(tmp_path, kw):
     assert ref_cells.max() > 8 and (ref_cells == 0).any()
 
 
-@pytest.mark.parametrize("n_photons", [50_000])
-def test_oracle_photon_pass_replays_the_ppm_tree_draw_for_draw(tmp_path, n_photons):
+@pytest.mark.parametrize("n_photons,spp", [(50_000, 1), (20_000, 4)])
+def test_oracle_photon_pass_replays_the_ppm_tree_draw_for_draw(tmp_path, n_photons, spp):
     """Rows a18-a20 pinned EXACTLY.  The PPM tree draws from three mt19937 engines seeded by std::random_device;
     oracle/ref_driver_ppm.cpp defines random_device::_M_getval itself (constant seed) and runs the tree's own
     trace_n_photons + density_estimation on one thread.  With `oracle_ppm_mt_mode` the restatement draws from the same
@@ -165,7 +165,7 @@ def test_oracle_photon_pass_replays_the_ppm_tree_draw_for_draw(tmp_path, n_photo
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref not built on this box")
     w, h = 80, 60
-    xml = _scene_xml(width=w, height=h, depth=6)
+    xml = _scene_xml(width=w, height=h, depth=6, spp=spp)     # spp = 4: the jittered 2 x 2 eye pass is replayed too
     (tmp_path / "s.xml").write_text(xml)
     subprocess.run([exe, str(tmp_path / "s.xml"), str(tmp_path / "o.bin"), str(n_photons)], check=True,
                    capture_output=True, stdin=subprocess.DEVNULL, cwd=str(tmp_path))
@@ -184,7 +184,7 @@ def test_oracle_photon_pass_replays_the_ppm_tree_draw_for_draw(tmp_path, n_photo
         rgbw, _, _, cnt = cpu.ppm(hs, 0, seed=1, n_photons=n_photons, total_num_of_photons=n_photons)
     finally:
         L.oracle_ppm_mt_mode(0, 0, None, 0)
-    assert ref_state[:, 4].sum() > 100_000 and ref_state[:, 4].max() > 50          # a real workout
+    assert ref_state[:, 4].sum() > 100_000 and ref_state[:, 4].max() > 20          # a real workout
     assert np.array_equal(state[:, 4], ref_state[:, 4])                              # photon counts n
     assert np.array_equal(state[:, 3].view(np.uint32), ref_state[:, 3].view(np.uint32))     # radius^2
     assert np.array_equal(state[:, :3].view(np.uint32), ref_state[:, :3].view(np.uint32))   # flux
