@@ -549,12 +549,14 @@ def hw1_near_ties(width=96, height=72, layers=5, spacing=6e-7, seed=SEED, image_
             + "  </VertexData>\n  <Objects>\n" + mesh_xml + tri_xml + sph_xml + "  </Objects>\n</Scene>\n")
 
 
-def fuzz_scene(seed, width=61, height=47, depth=3) -> str:
+def fuzz_scene(seed, width=61, height=47, depth=3, spp=1, stochastic=False) -> str:
     """HW3-dialect scene for differential testing against the reference binaries (HW3 / HW4 / HW5 / HW6 / HW7 all load
     it): odd resolution and an axis-aligned camera (the centre ray is exactly (0,0,-1): the box test's skipped axes),
     meshes under random Scaling / Rotation / Translation chains including NEGATIVE (mirroring) scales, instances with
     and without resetTransform, transformed stand-alone triangles and spheres (non-uniform scale), zero-area and
-    edge-on triangles, a sphere around the camera, smooth and flat shading, mirror and glass, two point lights."""
+    edge-on triangles, a sphere around the camera, smooth and flat shading, mirror and glass, two point lights.
+    `stochastic` adds an area light, a glossy mirror, depth of field and a motion-blurred instance and sphere (for the
+    draw-for-draw replay tests; use with spp > 1)."""
     rng = np.random.default_rng(1000 + seed)
     verts = []
     nv = 0
@@ -568,7 +570,7 @@ def fuzz_scene(seed, width=61, height=47, depth=3) -> str:
 
     mats = (_material_xml(1, [0.2, 0.2, 0.2], rng.uniform(0.2, 0.8, 3), rng.uniform(0.1, 0.5, 3), 12.0)
             + _material_xml(2, [0.1, 0.15, 0.1], rng.uniform(0.2, 0.8, 3), rng.uniform(0.1, 0.5, 3), 40.0,
-                            mirror=[0.5, 0.5, 0.5])
+                            mirror=[0.5, 0.5, 0.5], roughness=(0.2 if stochastic else None))
             + _material_xml(3, [0.05, 0.05, 0.05], [0.05, 0.05, 0.05], [0.2, 0.2, 0.2], 60.0,
                             transparency=[0.9, 0.85, 0.95], refr=1.45)
             + _material_xml(4, [0.25, 0.2, 0.15], rng.uniform(0.2, 0.8, 3), [0, 0, 0], 1.0)
@@ -599,8 +601,9 @@ def fuzz_scene(seed, width=61, height=47, depth=3) -> str:
                      f'      <Faces vertexOffset="{b}">\n' + _rows(f + 1, "%d") + "      </Faces>\n    </Mesh>\n")
     inst = ""
     for k in range(4):
+        mb = f"      <MotionBlur>{_f(rng.uniform(-0.4, 0.4, 3))}</MotionBlur>\n" if (stochastic and k == 1) else ""
         inst += (f'    <MeshInstance id="{k + 1}" baseMeshId="{1 + k % 3}" resetTransform="{"true" if k % 2 else "false"}">\n'
-                 f"      <Material>{1 + int(rng.integers(0, 5))}</Material>\n"
+                 f"      <Material>{1 + int(rng.integers(0, 5))}</Material>\n{mb}"
                  f"      <Transformations>{chain()}</Transformations>\n    </MeshInstance>\n")
     # floor + back wall as stand-alone triangles, one of them transformed
     R = 6.0
@@ -616,20 +619,24 @@ def fuzz_scene(seed, width=61, height=47, depth=3) -> str:
     sph = ""
     for i, (r, mat, tr) in enumerate(((0.7, 2, ""), (0.6, 1, chain()), (0.5, 3, ""), (2.5, 4, ""))):
         tx = f"      <Transformations>{tr}</Transformations>\n" if tr else ""
-        sph += (f'    <Sphere id="{i + 1}">\n      <Material>{mat}</Material>\n{tx}      <Center>{cb + i + 1}</Center>\n'
+        mb = "      <MotionBlur>0.3 0.1 -0.2</MotionBlur>\n" if (stochastic and i == 0) else ""
+        sph += (f'    <Sphere id="{i + 1}">\n      <Material>{mat}</Material>\n{tx}{mb}      <Center>{cb + i + 1}</Center>\n'
                 f"      <Radius>{_f([r])}</Radius>\n    </Sphere>\n")
     allv = np.concatenate(verts, 0)
     aspect = width / height
+    dof = "      <FocusDistance>4.5</FocusDistance>\n      <ApertureSize>0.08</ApertureSize>\n" if stochastic else ""
+    area = ('    <AreaLight id="1">\n      <Position>-1 3.8 -3</Position>\n      <Intensity>1500 1400 1300</Intensity>\n'
+            "      <EdgeVector1>1.5 0 0</EdgeVector1>\n      <EdgeVector2>0 0 1.5</EdgeVector2>\n    </AreaLight>\n") if stochastic else ""
     return ("<Scene>\n  <BackgroundColor>12 18 30</BackgroundColor>\n  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
             f"  <MaxRecursionDepth>{depth}</MaxRecursionDepth>\n  <Cameras>\n    <Camera id=\"1\">\n"
             "      <Position>0 0 1</Position>\n      <Gaze>0 0 -1</Gaze>\n      <Up>0 1 0</Up>\n"
             f"      <NearPlane>{_f([-0.8 * aspect, 0.8 * aspect, -0.8, 0.8])}</NearPlane>\n      <NearDistance>1</NearDistance>\n"
-            f"      <ImageResolution>{width} {height}</ImageResolution>\n      <NumSamples>1</NumSamples>\n"
-            "      <ImageName>fuzz.png</ImageName>\n    </Camera>\n  </Cameras>\n  <Lights>\n"
+            f"      <ImageResolution>{width} {height}</ImageResolution>\n      <NumSamples>{spp}</NumSamples>\n" + dof
+            + "      <ImageName>fuzz.png</ImageName>\n    </Camera>\n  </Cameras>\n  <Lights>\n"
             "    <AmbientLight>20 20 20</AmbientLight>\n"
             f'    <PointLight id="1">\n      <Position>{_f(rng.uniform(-3, 3, 3) * [1, 0.3, 0.5] + [0, 3.5, 0])}</Position>\n'
             "      <Intensity>2500 2400 2200</Intensity>\n    </PointLight>\n"
             f'    <PointLight id="2">\n      <Position>{_f(rng.uniform(-2, 2, 3) + [0, 1, 0.5])}</Position>\n'
-            "      <Intensity>600 700 900</Intensity>\n    </PointLight>\n  </Lights>\n  <Materials>\n" + mats
+            "      <Intensity>600 700 900</Intensity>\n    </PointLight>\n" + area + "  </Lights>\n  <Materials>\n" + mats
             + "  </Materials>\n" + xf + "  <VertexData>\n" + _rows(allv, "%.9g") + "  </VertexData>\n  <Objects>\n"
             + mesh_xml + inst + tri_xml + sph + "  </Objects>\n</Scene>\n")

@@ -207,6 +207,19 @@ def test_oracle_replays_dof_and_motion_blur_draw_for_draw(tmp_path, tree):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
+@pytest.mark.parametrize("tree", ["hw3f", "hw4f", "hw5", "hw6", "hw7f"])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_oracle_replays_stochastic_fuzz_scenes(tmp_path, tree, seed):
+    """The awkward scenes of scenes.fuzz_scene with an area light, a glossy mirror, depth of field, a motion-blurred
+    instance and sphere, 4 samples per pixel: every float of the frame, on five trees, through the replay."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.fuzz_scene(seed, width=41, height=33, spp=4, stochastic=True)
+    got, want = _replay(tree, xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
 def test_oracle_replays_hw2_multisample_draw_for_draw(tmp_path):
     """HW2's multi-sample loop (one minstd_rand0 per pixel seeded from the clock, 3x3 Gaussian splat) through the float
     twin of the HW2 tree.  HW2's Pixel::get_color truncates to ints, so its PNGs hide the accumulators; the twin dumps
