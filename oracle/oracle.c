@@ -19,6 +19,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -1251,7 +1252,6 @@ static v3 trace_ray7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, u
   return radiance;
 }
 /* Scene::trace_path — HW7/src/Scene.cpp:312-414 */
-#include <stdio.h>
 static v3 trace_path7(const Ctx* cx, const Ray* ray, const Hit* hit, int level, uint32_t key) {
   const B200SceneDesc* d = cx->d;
   v3 radiance = V(0, 0, 0);
