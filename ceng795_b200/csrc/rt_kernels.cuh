@@ -320,7 +320,10 @@ __device__ __forceinline__ v3 light_position(const b200rt_light& L, uint32_t key
 }
 
 // ---- shade_a: surface record + shadow-ray emission ----------------------------
-__global__ void __launch_bounds__(RT_BLOCK) k_shade_a(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves, int d,
+#ifndef RT_SHADE3_MIN_BLOCKS
+#define RT_SHADE3_MIN_BLOCKS 8  // resident CTAs the HW1-HW3 shade kernels are held to (64 registers): they wait on memory (profiles/r01l)
+#endif
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE3_MIN_BLOCKS) k_shade_a(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves, int d,
                                                       Counters* C) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -398,7 +401,7 @@ __device__ __forceinline__ bool refract_ray(v3 du, v3 n, float index, v3* out) {
 }
 
 // ---- shade_b: Scene::trace_ray body (HW1/Scene.cpp:56-123, HW3/src/Scene.cpp:125-311)
-__global__ void __launch_bounds__(RT_BLOCK) k_shade_b(DScene S, Pool P, ShadowQueue Q, WaveInfo* waves, int d,
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE3_MIN_BLOCKS) k_shade_b(DScene S, Pool P, ShadowQueue Q, WaveInfo* waves, int d,
                                                       Counters* C) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   const uint32_t next_begin = waves[d + 1].begin;

@@ -9,5 +9,5 @@ mkdir -p build/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Xcompiler -ffp-contract=off \
   "$@" -c ceng795_b200/csrc/b200rt_api.cu -o build/variants/api_$name.o
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o build/variants/libb200rt_$name.so build/variants/api_$name.o \
-  build/fast_bvh.cpp.o build/host_build.cpp.o build/scene_cache.cpp.o
+  build/*.cpp.o
 echo build/variants/libb200rt_$name.so
