@@ -192,3 +192,62 @@ def run_reference(tree: str, xml_text: str, workdir: str | None = None, timeout:
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)
     return res
+
+
+# ---- libstdc++ restated, for the replay tests -------------------------------------------------------------------
+class _Mt19937:
+    def __init__(self, seed):
+        x = [0] * 624
+        x[0] = seed & 0xFFFFFFFF
+        for k in range(1, 624):
+            x[k] = (1812433253 * (x[k - 1] ^ (x[k - 1] >> 30)) + k) & 0xFFFFFFFF
+        self.x, self.i = x, 624
+
+    def next(self):
+        if self.i >= 624:
+            x = self.x
+            for k in range(624):
+                y = (x[k] & 0x80000000) | (x[(k + 1) % 624] & 0x7FFFFFFF)
+                x[k] = x[(k + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+            self.i = 0
+        y = self.x[self.i]
+        self.i += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        y ^= y >> 18
+        return y & 0xFFFFFFFF
+
+
+def _uniform_int(g, a, b):
+    """std::uniform_int_distribution on a 32-bit engine, libstdc++ 11+: Lemire's nearly-divisionless method."""
+    rng = (b - a) + 1
+    prod = g.next() * rng
+    low = prod & 0xFFFFFFFF
+    if low < rng:
+        thr = ((1 << 32) - rng) % rng
+        while low < thr:
+            prod = g.next() * rng
+            low = prod & 0xFFFFFFFF
+    return a + (prod >> 32)
+
+
+def perlin_table_for_clock(seed: int) -> list:
+    """The permutation table Perlin_noise::Perlin_noise builds (HW7/src/Perlin_noise.cpp:16-20) when the clock it seeds
+    its mt19937 from reads `seed`: std::shuffle of 0..15 as libstdc++ does it (one swap for the even count, then two
+    positions per draw).  Checked against the real std::shuffle for several seeds while writing it."""
+    p = list(range(16))
+    g = _Mt19937(seed)
+    i = 1
+    j = _uniform_int(g, 0, 1)
+    p[i], p[j] = p[j], p[i]
+    i += 1
+    while i < 16:
+        r = i + 1
+        x = _uniform_int(g, 0, r * (r + 1) - 1)
+        a, b = x // (r + 1), x % (r + 1)
+        p[i], p[a] = p[a], p[i]
+        i += 1
+        p[i], p[b] = p[b], p[i]
+        i += 1
+    return p

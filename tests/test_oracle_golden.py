@@ -220,6 +220,29 @@ def test_oracle_replays_stochastic_fuzz_scenes(tmp_path, tree, seed):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
+@pytest.mark.parametrize("tree", ["hw4f", "hw6", "hw7f"])
+def test_oracle_perlin_textures_against_the_trees(tmp_path, tree):
+    """Perlin noise as texture and as BUMP map at image level.  The trees shuffle the permutation table with an mt19937
+    seeded from the clock, so no two runs of a binary agree — but with the clock interposed (REF_SEED) the table is
+    std::shuffle(0..15, mt19937(795)), which oracle/cpu.py restates (libstdc++'s shuffle and uniform_int_distribution);
+    the host uploads that table and the frame has to come out the same float for float: Perlin_noise::get_value_at at
+    the object-space hit point, Texture::bump_normal's finite differences, blend_kd."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    import re
+    from ceng795_b200 import scenes
+    assert cpu.perlin_table_for_clock(795) == [0, 7, 12, 2, 15, 11, 9, 6, 4, 5, 1, 3, 13, 14, 8, 10]
+    xml = scenes.hw7_scene(str(tmp_path), width=80, height=60, n=6, depth=2, perlin=True, mesh_slices=(6, 7),
+                           image_name="o.png")
+    table = " ".join(str(v) for v in cpu.perlin_table_for_clock(795))
+    xml, n = re.subn(r"<Permutation>.*?</Permutation>", f"<Permutation>{table}</Permutation>", xml)
+    assert n >= 1
+    got, want = _replay(tree, xml, str(tmp_path))
+    if tree == "hw4f":
+        assert np.max(np.abs(got - want) / (np.abs(want) + 1)) < 1e-6      # its 1-spp splat sums in thread order... one thread here
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
 def test_oracle_replays_hw2_multisample_draw_for_draw(tmp_path):
     """HW2's multi-sample loop (one minstd_rand0 per pixel seeded from the clock, 3x3 Gaussian splat) through the float
     twin of the HW2 tree.  HW2's Pixel::get_color truncates to ints, so its PNGs hide the accumulators; the twin dumps
