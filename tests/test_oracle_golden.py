@@ -243,6 +243,26 @@ def test_oracle_perlin_textures_against_the_trees(tmp_path, tree):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
+@pytest.mark.parametrize("tree", ["hw6", "hw7f"])
+@pytest.mark.parametrize("variant", ["left", "simple"])
+def test_oracle_camera_variants_against_the_trees(tmp_path, tree, variant):
+    """Row a1: the left-handed camera (an HW7 attribute; HW6 ignores it) and the `type="simple"` camera (GazePoint +
+    FovY -> near plane through tanf, HW7/src/Scene.cpp:580-601) on the textured scene, float for float."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    import re
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=90, height=60, n=6, depth=2, mesh_slices=(6, 7), image_name="o.png")
+    if variant == "left":
+        xml = xml.replace('<Camera id="1">', '<Camera id="1" handedness="left">')
+    else:
+        xml = re.sub(r"      <Gaze>.*?</Gaze>\n", "      <GazePoint>0.2 0.6 -1.5</GazePoint>\n", xml)
+        xml = re.sub(r"      <NearPlane>.*?</NearPlane>\n", "      <FovY>52</FovY>\n", xml)
+        xml = xml.replace('<Camera id="1">', '<Camera id="1" type="simple">')
+    got, want = _replay(tree, xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
 def test_oracle_replays_hw2_multisample_draw_for_draw(tmp_path):
     """HW2's multi-sample loop (one minstd_rand0 per pixel seeded from the clock, 3x3 Gaussian splat) through the float
     twin of the HW2 tree.  HW2's Pixel::get_color truncates to ints, so its PNGs hide the accumulators; the twin dumps
