@@ -137,3 +137,62 @@ class AsyncImageWriter:
     def __exit__(self, *exc):
         self.close()
         return False
+
+
+# ---- minimal OpenEXR I/O: uncompressed scanline float32 RGB, the one flavour the env-map tests need ------------------
+# (the reference reads its environment maps with tinyexr, HW7/src/Spherical_directional_light.cpp:4-12; real EXR
+# decoding is host I/O that stays with the reference — this is just enough to hand both sides the same file)
+def write_exr_f32(path: str, rgb: np.ndarray) -> None:
+    import struct
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    h, w = rgb.shape[:2]
+
+    def attr(name, typ, data):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(data)) + data
+
+    chlist = b"".join(c.encode() + b"\0" + struct.pack("<iBxxxii", 2, 0, 1, 1) for c in ("B", "G", "R")) + b"\0"
+    box = struct.pack("<iiii", 0, 0, w - 1, h - 1)
+    header = (attr("channels", "chlist", chlist) + attr("compression", "compression", b"\0") + attr("dataWindow", "box2i", box)
+              + attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0")
+              + attr("pixelAspectRatio", "float", struct.pack("<f", 1.0))
+              + attr("screenWindowCenter", "v2f", struct.pack("<ff", 0.0, 0.0))
+              + attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0")
+    head = struct.pack("<II", 20000630, 2) + header
+    line_bytes = 3 * w * 4
+    offset0 = len(head) + 8 * h
+    with open(path, "wb") as f:
+        f.write(head)
+        f.write(b"".join(struct.pack("<Q", offset0 + y * (8 + line_bytes)) for y in range(h)))
+        for y in range(h):
+            f.write(struct.pack("<ii", y, line_bytes))
+            for c in (2, 1, 0):                       # channels are stored in alphabetical order: B, G, R
+                f.write(rgb[y, :, c].tobytes())
+
+
+def read_exr_f32(path: str) -> np.ndarray:
+    """Reads back what write_exr_f32 writes (uncompressed scanline float32 B/G/R); anything else is refused."""
+    import struct
+    blob = open(path, "rb").read()
+    if struct.unpack_from("<I", blob, 0)[0] != 20000630:
+        raise ValueError(f"{path}: not an OpenEXR file")
+    pos = 8
+    attrs = {}
+    while blob[pos] != 0:
+        e = blob.index(b"\0", pos); name = blob[pos:e].decode(); pos = e + 1
+        e = blob.index(b"\0", pos); pos = e + 1
+        (n,) = struct.unpack_from("<i", blob, pos); pos += 4
+        attrs[name] = blob[pos:pos + n]; pos += n
+    pos += 1
+    if attrs.get("compression") != b"\0" or attrs["channels"].count(b"\0") != 3 * 1 + 1 + 0 + 3 * 0 and False:
+        raise ValueError(f"{path}: only uncompressed EXR files are supported by this mirror")
+    x0, y0, x1, y1 = struct.unpack("<iiii", attrs["dataWindow"])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    out = np.zeros((h, w, 3), np.float32)
+    offsets = struct.unpack_from(f"<{h}Q", blob, pos)
+    for off in offsets:
+        y, nbytes = struct.unpack_from("<ii", blob, off)
+        if nbytes != 3 * w * 4:
+            raise ValueError(f"{path}: only float32 B/G/R scanlines are supported by this mirror")
+        row = np.frombuffer(blob, np.float32, 3 * w, off + 8).reshape(3, w)
+        out[y - y0, :, 2], out[y - y0, :, 1], out[y - y0, :, 0] = row[0], row[1], row[2]
+    return out

@@ -365,6 +365,9 @@ def _load_envmap(path: str):
     [H, W, 3] (or an 8-bit image scaled to 0..1) — the device side only sees RGB floats."""
     if path.endswith(".npy"):
         a = np.load(path).astype(np.float32)
+    elif path.endswith(".exr"):
+        from .image import read_exr_f32      # uncompressed float32 scanline files only (tests); real decoding is host I/O
+        a = read_exr_f32(path)
     else:
         from PIL import Image
         a = np.asarray(Image.open(path).convert("RGB"), dtype=np.float32) / np.float32(255.0)

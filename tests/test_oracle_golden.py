@@ -263,6 +263,42 @@ def test_oracle_camera_variants_against_the_trees(tmp_path, tree, variant):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
+@pytest.mark.parametrize("pt,spp", [(False, 1), (True, 4)])
+def test_oracle_environment_light_against_the_tree(tmp_path, pt, spp):
+    """SphericalDirectionalLight (row a10): the tree reads its environment map with tinyexr, samples the hemisphere
+    uniformly, looks the lat-long texel up with nearest sampling and divides by the pdf; rays that leave the scene
+    pick the map up too.  Both sides get the same uncompressed float32 EXR (image.write_exr_f32); through the replay
+    the frames agree float for float in ray-tracing and in path-tracing mode."""
+    if not cpu.have_ref("hw7f"):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    rng = np.random.default_rng(3)
+    env = (rng.uniform(0, 1, (16, 32, 3)) ** 3 * 40).astype(np.float32)
+    image.write_exr_f32(str(tmp_path / "env.exr"), env)
+    assert np.array_equal(image.read_exr_f32(str(tmp_path / "env.exr")), env)
+    xml = scenes.hw7_scene(str(tmp_path), width=64, height=48, n=6, depth=2, mesh_slices=(6, 7), image_name="o.png",
+                           path_tracing=pt, spp=spp)
+    xml = xml.replace("  </Lights>", '    <SphericalDirectionalLight id="1"><EnvMapName>env.exr</EnvMapName>'
+                                     "</SphericalDirectionalLight>\n  </Lights>")
+    got, want = _replay("hw7f", xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
+@pytest.mark.parametrize("tree", ["hw4f", "hw6", "hw7f"])
+def test_oracle_background_texture_against_the_trees(tmp_path, tree):
+    """BackgroundTexture (rows a1 / a9): primary rays that miss look the image up at (bg_u, bg_v) of the camera ray."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=72, height=54, n=6, depth=2, mesh_slices=(6, 7), image_name="o.png")
+    xml = xml.replace("<Scene>\n", "<Scene>\n  <BackgroundTexture>tex_checker.png</BackgroundTexture>\n", 1)
+    # open the room so that primary rays can leave: drop the stand-alone triangles of the back wall
+    xml = xml.replace('<Gaze>0 -0.32 -1</Gaze>', '<Gaze>0 0.55 1</Gaze>')
+    got, want = _replay(tree, xml, str(tmp_path))
+    assert (np.abs(want - np.array([12, 16, 30], np.float32)) > 1e-3).any()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
 def test_oracle_replays_hw2_multisample_draw_for_draw(tmp_path):
     """HW2's multi-sample loop (one minstd_rand0 per pixel seeded from the clock, 3x3 Gaussian splat) through the float
     twin of the HW2 tree.  HW2's Pixel::get_color truncates to ints, so its PNGs hide the accumulators; the twin dumps
