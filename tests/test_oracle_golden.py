@@ -299,6 +299,25 @@ def test_oracle_background_texture_against_the_trees(tmp_path, tree):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
+@pytest.mark.parametrize("pt", [False, True])
+def test_oracle_replays_transformed_light_shapes(tmp_path, pt):
+    """LightMesh and LightSphere under transformations (the light mesh keeps its OBJECT-space box in the tree's BVH,
+    HW7/include/Light_mesh.h:52-68; the sphere light is re-intersected to get its distance) and path tracing with the
+    UNIFORM hemisphere sample instead of importance sampling: float for float through the replay."""
+    if not cpu.have_ref("hw7f"):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=64, height=48, n=6, spp=4, depth=3, stochastic_lights=True,
+                           path_tracing=pt, importance=not pt, light_scale=0.5, mesh_slices=(6, 7), image_name="o.png")
+    xml = xml.replace('<LightMesh id="1">\n      <Material>1</Material>',
+                      '<LightMesh id="1">\n      <Material>1</Material>\n      <Transformations>r2 t3</Transformations>')
+    xml = xml.replace('<LightSphere id="1">\n      <Material>1</Material>',
+                      '<LightSphere id="1">\n      <Material>1</Material>\n      <Transformations>s2 t4</Transformations>')
+    assert "r2 t3" in xml and "s2 t4" in xml
+    got, want = _replay("hw7f", xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
 def test_oracle_replays_hw2_multisample_draw_for_draw(tmp_path):
     """HW2's multi-sample loop (one minstd_rand0 per pixel seeded from the clock, 3x3 Gaussian splat) through the float
     twin of the HW2 tree.  HW2's Pixel::get_color truncates to ints, so its PNGs hide the accumulators; the twin dumps
