@@ -1,0 +1,66 @@
+"""GPU: the corners of the HW7 path that the oracle is pinned on float for float by tests/test_oracle_golden.py —
+environment light, background texture, camera variants, transformed light shapes — device against oracle."""
+import re
+
+import numpy as np
+import pytest
+
+from ceng795_b200 import image, scene, scenes
+from oracle import cpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(sc, seed=0, stochastic=False):
+    rgbw, st = sc.render_image(0, seed=seed)
+    o_rgbw, o_ids, o_t, cnt = cpu.render(sc.host, 0, seed=seed, want_ids=True)
+    if o_ids is not None and sc.spec.cameras[0]["num_samples"] == 1:
+        ids, t = sc.primary_ids(0)
+        assert np.array_equal(ids, o_ids) and np.array_equal(t.view(np.uint32), o_t.view(np.uint32))
+    assert (st.rays_primary, st.rays_shadow, st.rays_secondary) == (cnt.rays_primary, cnt.rays_shadow, cnt.rays_secondary)
+    a, b = rgbw[..., :3] / rgbw[..., 3:4], o_rgbw[..., :3] / o_rgbw[..., 3:4]
+    rel = np.abs(a - b) / (np.abs(b) + 1.0)
+    if stochastic:   # libm ulps can flip a light sample on a bounce: robust statistics
+        assert np.median(rel) < 1e-5 and abs(a.mean() - b.mean()) <= 0.01 * b.mean(), (float(np.median(rel)), a.mean(), b.mean())
+    else:
+        assert np.mean(rel <= 1e-4) >= 0.999 and rel.max() < 5e-2, (float(np.mean(rel <= 1e-4)), float(rel.max()))
+
+
+@pytest.mark.parametrize("pt,spp", [(False, 1), (True, 4)])
+def test_environment_light(gpu, tmp_path, pt, spp):
+    rng = np.random.default_rng(3)
+    image.write_exr_f32(str(tmp_path / "env.exr"), (rng.uniform(0, 1, (16, 32, 3)) ** 3 * 40).astype(np.float32))
+    xml = scenes.hw7_scene(str(tmp_path), width=64, height=48, n=6, depth=2, mesh_slices=(6, 7), path_tracing=pt, spp=spp)
+    xml = xml.replace("  </Lights>", '    <SphericalDirectionalLight id="1"><EnvMapName>env.exr</EnvMapName>'
+                                     "</SphericalDirectionalLight>\n  </Lights>")
+    _check(scene.Scene(xml, "hw7", base_dir=str(tmp_path)), seed=2, stochastic=pt)
+
+
+@pytest.mark.parametrize("tree", ["hw4", "hw6", "hw7"])
+def test_background_texture(gpu, tmp_path, tree):
+    xml = scenes.hw7_scene(str(tmp_path), width=72, height=54, n=6, depth=2, mesh_slices=(6, 7))
+    xml = xml.replace("<Scene>\n", "<Scene>\n  <BackgroundTexture>tex_checker.png</BackgroundTexture>\n", 1)
+    xml = xml.replace('<Gaze>0 -0.32 -1</Gaze>', '<Gaze>0.35 0.1 -1</Gaze>')     # part room, part open front
+    _check(scene.Scene(xml, tree, base_dir=str(tmp_path)))
+
+
+@pytest.mark.parametrize("variant", ["left", "simple"])
+def test_camera_variants(gpu, tmp_path, variant):
+    xml = scenes.hw7_scene(str(tmp_path), width=90, height=60, n=6, depth=2, mesh_slices=(6, 7))
+    if variant == "left":
+        xml = xml.replace('<Camera id="1">', '<Camera id="1" handedness="left">')
+    else:
+        xml = re.sub(r"      <Gaze>.*?</Gaze>\n", "      <GazePoint>0.2 0.6 -1.5</GazePoint>\n", xml)
+        xml = re.sub(r"      <NearPlane>.*?</NearPlane>\n", "      <FovY>52</FovY>\n", xml)
+        xml = xml.replace('<Camera id="1">', '<Camera id="1" type="simple">')
+    _check(scene.Scene(xml, "hw7", base_dir=str(tmp_path)))
+
+
+def test_transformed_light_shapes(gpu, tmp_path):
+    xml = scenes.hw7_scene(str(tmp_path), width=64, height=48, n=6, spp=4, depth=3, stochastic_lights=True, light_scale=0.5,
+                           mesh_slices=(6, 7))
+    xml = xml.replace('<LightMesh id="1">\n      <Material>1</Material>',
+                      '<LightMesh id="1">\n      <Material>1</Material>\n      <Transformations>r2 t3</Transformations>')
+    xml = xml.replace('<LightSphere id="1">\n      <Material>1</Material>',
+                      '<LightSphere id="1">\n      <Material>1</Material>\n      <Transformations>s2 t4</Transformations>')
+    _check(scene.Scene(xml, "hw7", base_dir=str(tmp_path)), seed=4, stochastic=True)
