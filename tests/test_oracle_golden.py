@@ -318,6 +318,26 @@ def test_oracle_replays_transformed_light_shapes(tmp_path, pt):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
+@pytest.mark.parametrize("tree", ["hw5", "hw6", "hw7f"])
+def test_oracle_second_spot_and_directional_light(tmp_path, tree):
+    """A loader quirk that changes pixels: HW5 / HW6 walk SpotLight and DirectionalLight elements with
+    FirstChildElement instead of NextSiblingElement and so keep only the FIRST of each (HW6/src/Scene.cpp:661,678);
+    HW7 reads them all.  Two of each (and two point lights, read by every tree) — float for float per tree."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=64, height=48, n=6, depth=2, mesh_slices=(6, 7), image_name="o.png")
+    extra = ('    <SpotLight id="2"><Position>-3 5 2</Position><Direction>0.4 -1 -0.3</Direction>'
+             '<Intensity>2500 2000 1500</Intensity><CoverageAngle>40</CoverageAngle><FalloffAngle>20</FalloffAngle></SpotLight>\n'
+             '    <DirectionalLight id="2"><Direction>-0.4 -1 0.2</Direction><Radiance>15 20 25</Radiance></DirectionalLight>\n'
+             '    <PointLight id="2"><Position>2 6 -1</Position><Intensity>900 800 700</Intensity></PointLight>\n')
+    xml = xml.replace("  </Lights>", extra + "  </Lights>")
+    hs = scene.HostScene(scene.parse_xml(xml, tree.rstrip("f"), base_dir=str(tmp_path)))
+    assert hs.desc.n_lights == (6 if tree == "hw7f" else 4)
+    got, want = _replay(tree, xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
 def test_oracle_replays_hw2_multisample_draw_for_draw(tmp_path):
     """HW2's multi-sample loop (one minstd_rand0 per pixel seeded from the clock, 3x3 Gaussian splat) through the float
     twin of the HW2 tree.  HW2's Pixel::get_color truncates to ints, so its PNGs hide the accumulators; the twin dumps
