@@ -338,6 +338,30 @@ def test_oracle_second_spot_and_directional_light(tmp_path, tree):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
+@pytest.mark.parametrize("tree", ["hw4f", "hw6", "hw7f"])
+def test_oracle_transformed_textured_spheres(tmp_path, tree):
+    """Spheres under scale / rotate / translate chains with an image texture, an image BUMP map and a Perlin bump map
+    (uv from the object-space hit point, tangents of Sphere::intersect, the always-applied normal matrix), one of
+    them motion-blurred (per-ray inverse), 4 samples per pixel — float for float through the replay."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    import re
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=80, height=60, n=6, depth=2, mesh_slices=(6, 7), image_name="o.png",
+                           perlin=True)
+    table = " ".join(str(v) for v in cpu.perlin_table_for_clock(795))
+    xml = re.sub(r"<Permutation>.*?</Permutation>", f"<Permutation>{table}</Permutation>", xml)
+    n0 = xml.count("<Transformations>")
+    for sid, tr in ((1, "s2 r3 t2"), (4, "r1 s3"), (5, "s4 r2")):
+        xml = re.sub(rf'(<Sphere id="{sid}">\n      <Material>\d+</Material>\n)',
+                     rf'\1      <Transformations>{tr}</Transformations>\n', xml)
+    assert xml.count("<Transformations>") == n0 + 3
+    xml = re.sub(r'(<Sphere id="2">\n      <Material>\d+</Material>\n)', r'\1      <MotionBlur>0.2 0.1 0</MotionBlur>\n', xml)
+    xml = xml.replace("<NumSamples>1</NumSamples>", "<NumSamples>4</NumSamples>")
+    got, want = _replay(tree, xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
 def test_oracle_replays_hw2_multisample_draw_for_draw(tmp_path):
     """HW2's multi-sample loop (one minstd_rand0 per pixel seeded from the clock, 3x3 Gaussian splat) through the float
     twin of the HW2 tree.  HW2's Pixel::get_color truncates to ints, so its PNGs hide the accumulators; the twin dumps
