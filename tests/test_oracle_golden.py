@@ -362,6 +362,25 @@ def test_oracle_transformed_textured_spheres(tmp_path, tree):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 
 
+@pytest.mark.parametrize("tree", ["hw4f", "hw6", "hw7f"])
+def test_oracle_moving_bumped_mesh_and_textured_instances(tmp_path, tree):
+    """A motion-blurred, rotated mesh with an image BUMP map (dp/du, dp/dv from the texture coordinates, the normal
+    matrix of the per-ray inverse) and a base mesh WITHOUT texture coordinates given an image texture, which its
+    rotated / scaled instances inherit (constant uv: the degenerate-Jacobian guard) — float for float, 4 spp."""
+    if not cpu.have_ref(tree):
+        pytest.skip("oracle/_ref not built on this box")
+    from ceng795_b200 import scenes
+    xml = scenes.hw7_scene(str(tmp_path), width=80, height=60, n=6, depth=2, mesh_slices=(6, 7), image_name="o.png", spp=4)
+    a = '<Mesh id="1" shadingMode="smooth">\n      <Material>4</Material>\n      <Texture>1</Texture>\n'
+    b = '<Mesh id="2" shadingMode="smooth">\n      <Material>5</Material>\n'
+    assert a in xml and b in xml
+    xml = xml.replace(a, '<Mesh id="1" shadingMode="smooth">\n      <Material>4</Material>\n      <Texture>3</Texture>\n'
+                         '      <MotionBlur>0.15 0 0.1</MotionBlur>\n      <Transformations>r1 t1</Transformations>\n')
+    xml = xml.replace(b, b + '      <Texture>1</Texture>\n')
+    got, want = _replay(tree, xml, str(tmp_path))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
+
+
 def test_oracle_replays_hw2_multisample_draw_for_draw(tmp_path):
     """HW2's multi-sample loop (one minstd_rand0 per pixel seeded from the clock, 3x3 Gaussian splat) through the float
     twin of the HW2 tree.  HW2's Pixel::get_color truncates to ints, so its PNGs hide the accumulators; the twin dumps
