@@ -14,7 +14,12 @@
 // The output is a B200SceneDesc (include/b200rt.h).  tests/test_host_build.py
 // compares it against a dump made by walking the real reference objects
 // (oracle/ref_probe.cpp built into oracle/_ref/).
+#include <chrono>
+#include <future>
+#include <thread>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -213,7 +218,18 @@ void put_box(float* mn, float* mx, const Box& b) {
 }
 // BVH::BVH — HW3/src/Bounding_volume_hierarchy.cpp:3-29.  Returns the node's
 // index; `box_out` receives the node's own box (stored by the parent).
-uint32_t build_bvh(std::vector<Obj>& objs, int start, int end, int dim, BuildOut& out, Box& box_out) {
+//
+// A subtree over n >= 2 objects always holds n-1 inner nodes and n leaves, so
+// the depth-first slot of every node and leaf is known before the subtree is
+// built: `node_pos` / `leaf_pos` are this subtree's first slots in the
+// (pre-sized) output arrays.  That makes the two halves of a large range
+// independent — they touch disjoint slices of `objs`, `nodes`, `leaf_order` and
+// `gate` — and the left half is handed to another thread for the top
+// `par_levels` levels.  The result is the same array, byte for byte, as the
+// sequential recursion's.
+constexpr int kParMinObjs = 1 << 14;
+uint32_t build_bvh_at(std::vector<Obj>& objs, int start, int end, int dim, BuildOut& out, Box& box_out,
+                      uint32_t node_pos, uint32_t leaf_pos, int par_levels) {
   Box box;
   for (int i = start; i < end; i++) box.expand(objs[i].box);
   const float center = box.center[dim];
@@ -225,34 +241,61 @@ uint32_t build_bvh(std::vector<Obj>& objs, int start, int end, int dim, BuildOut
     }
   }
   if (mid == start || mid == end) mid = start + ((end - start) / 2);
-  const uint32_t me = (uint32_t)out.nodes->size();
-  out.nodes->push_back(b200rt_bvh_node());
+  const uint32_t me = node_pos;
+  const int nl = mid - start, nr = end - mid;
+  const uint32_t left_nodes = nl > 1 ? (uint32_t)(nl - 1) : 0u;
   b200rt_bvh_node n;
   std::memset(&n, 0, sizeof(n));
   Box lb, rb;
-  if (start + 1 == mid) {
+  std::future<uint32_t> left_task;
+  if (nl == 1) {
     n.left = objs[start].ref;
     lb = objs[start].box;
-    out.leaf_order->push_back(objs[start].ref);
+    (*out.leaf_order)[leaf_pos] = objs[start].ref;
     if (out.gate) (*out.gate)[B200RT_REF_INDEX(objs[start].ref)] = box;
+  } else if (par_levels > 0 && end - start >= kParMinObjs) {
+    left_task = std::async(std::launch::async, [&objs, &out, &lb, start, mid, dim, me, leaf_pos, par_levels]() {
+      return build_bvh_at(objs, start, mid, (dim + 1) % 3, out, lb, me + 1, leaf_pos, par_levels - 1);
+    });
   } else {
-    uint32_t c = build_bvh(objs, start, mid, (dim + 1) % 3, out, lb);
+    uint32_t c = build_bvh_at(objs, start, mid, (dim + 1) % 3, out, lb, me + 1, leaf_pos, 0);
     n.left = B200RT_REF(B200RT_KIND_INNER, c);
   }
-  if (mid + 1 == end) {
+  if (nr == 1) {
     n.right = objs[mid].ref;
     rb = objs[mid].box;
-    out.leaf_order->push_back(objs[mid].ref);
+    (*out.leaf_order)[leaf_pos + (uint32_t)nl] = objs[mid].ref;
     if (out.gate) (*out.gate)[B200RT_REF_INDEX(objs[mid].ref)] = box;
   } else {
-    uint32_t c = build_bvh(objs, mid, end, (dim + 1) % 3, out, rb);
+    uint32_t c = build_bvh_at(objs, mid, end, (dim + 1) % 3, out, rb, me + 1 + left_nodes, leaf_pos + (uint32_t)nl,
+                              par_levels > 0 ? par_levels - 1 : 0);
     n.right = B200RT_REF(B200RT_KIND_INNER, c);
   }
+  if (left_task.valid()) n.left = B200RT_REF(B200RT_KIND_INNER, left_task.get());
   put_box(n.lmin, n.lmax, lb);
   put_box(n.rmin, n.rmax, rb);
   (*out.nodes)[me] = n;
   box_out = box;
   return me;
+}
+int build_par_levels() {
+  if (const char* e = std::getenv("B200RT_BUILD_THREADS")) {
+    int t = std::atoi(e), l = 0;
+    while ((1 << l) < t) l++;
+    return l;
+  }
+  unsigned hc = std::thread::hardware_concurrency();
+  int l = 0;
+  while ((1u << l) < hc && l < 6) l++;
+  return l;
+}
+// Appends the tree over objs[start,end) (end - start >= 2) to out.nodes / out.leaf_order.
+uint32_t build_bvh(std::vector<Obj>& objs, int start, int end, int dim, BuildOut& out, Box& box_out) {
+  const uint32_t node_pos = (uint32_t)out.nodes->size();
+  const uint32_t leaf_pos = (uint32_t)out.leaf_order->size();
+  out.nodes->resize((size_t)node_pos + (size_t)(end - start - 1));
+  out.leaf_order->resize((size_t)leaf_pos + (size_t)(end - start));
+  return build_bvh_at(objs, start, end, dim, out, box_out, node_pos, leaf_pos, build_par_levels());
 }
 
 struct MeshIn {
@@ -663,6 +706,11 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
   for (size_t mi = 0; mi < b->meshes_in.size(); mi++) {
     const MeshIn& m = b->meshes_in[mi];
     const int nf = (int)(m.faces.size() / 3);
+    const auto T0 = std::chrono::steady_clock::now();
+    const auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double>(b - a).count();
+    };
+    double t_faces = 0.0, t_tree = 0.0;
     std::vector<Obj> objs((size_t)nf);
     std::vector<V3> normals((size_t)nf);
     for (int f = 0; f < nf; f++) {
@@ -703,10 +751,14 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
       root_box = objs[0].box;
       fm.root = B200RT_REF(B200RT_KIND_TRI, fm.tri_begin);
     } else {
+      const auto T1 = std::chrono::steady_clock::now();
       BuildOut bo{&b->nodes, &order, &gate};
       uint32_t r = build_bvh(objs, 0, nf, 0, bo, root_box);
       fm.root = B200RT_REF(B200RT_KIND_INNER, r);
+      t_faces = secs(T0, T1);
+      t_tree = secs(T1, std::chrono::steady_clock::now());
     }
+    const auto T2 = std::chrono::steady_clock::now();
     fm.node_count = (int)b->nodes.size() - fm.node_begin;
     put_box(fm.root_box, fm.root_box + 3, root_box);
     // local face id -> global triangle index in DFS order
@@ -748,6 +800,7 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
       put_box(gb, gb + 3, gate[f]);
       b->tri_gate.insert(b->tri_gate.end(), gb, gb + 6);
     }
+    const auto T3 = std::chrono::steady_clock::now();
     if (!hw1 && nf >= 2) {
       // SAH tree for the device over the same triangles (global ids = DFS order)
       std::vector<float> tb((size_t)nf * 6);
@@ -771,6 +824,9 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
         b->fast_tri_geom.insert(b->fast_tri_geom.end(), g, g + 12);
       }
     }
+    if (std::getenv("B200RT_BUILD_TIMING"))  // where a large mesh's load time goes (profiles/r01m_host_build.txt)
+      std::fprintf(stderr, "b200rt build: mesh %zu, %d faces: normals %.3f s, reference tree %.3f s, records %.3f s, SAH tree %.3f s\n",
+                   mi, nf, t_faces, t_tree, secs(T2, T3), secs(T3, std::chrono::steady_clock::now()));
     b->meshes.push_back(fm);
   }
   // HW1 stand-alone triangles are plain triangles scanned after the meshes

@@ -90,3 +90,25 @@ def test_cached_scene_renders_identically(gpu, tmp_path):
     ia, ta = sc.primary_ids(0)
     ib, tb = sc2.primary_ids(0)
     assert np.array_equal(ia, ib) and np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+
+
+@pytest.mark.parametrize("threads", ["2", "3", "8", "64"])
+def test_parallel_builder_is_byte_identical_to_sequential(tmp_path, monkeypatch, threads):
+    """The host builder hands the two halves of a large range to different threads (both trees: the reference-topology
+    BVH whose depth-first order ids, gates and ties hang on, and the SAH tree the device walks).  Depth-first slots are
+    fixed before the halves are built, so the flattened scene must not depend on the thread count: every array byte for
+    byte (80 000 triangles — above the 16 384-object threshold where the split begins, so several levels fork)."""
+    spec = scene.parse_xml(scenes.cfg2_hw3(n=200, width=64, height=36), "hw3")
+    monkeypatch.setenv("B200RT_BUILD_THREADS", "1")
+    seq = scene.HostScene(spec)
+    assert seq.desc.n_tris >= 4 * 16384
+    monkeypatch.setenv("B200RT_BUILD_THREADS", threads)
+    par = scene.HostScene(spec)
+    a, b = _arrays(seq.desc), _arrays(par.desc)
+    for k in a:
+        assert a[k] == b[k], k
+    assert seq.desc.root == par.desc.root and list(seq.desc.root_box) == list(par.desc.root_box)
+    p0, p1 = str(tmp_path / "seq.b200rt"), str(tmp_path / "par.b200rt")
+    seq.save(p0)
+    par.save(p1)
+    assert open(p0, "rb").read() == open(p1, "rb").read()
