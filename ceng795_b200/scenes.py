@@ -549,14 +549,19 @@ def hw1_near_ties(width=96, height=72, layers=5, spacing=6e-7, seed=SEED, image_
             + "  </VertexData>\n  <Objects>\n" + mesh_xml + tri_xml + sph_xml + "  </Objects>\n</Scene>\n")
 
 
-def fuzz_scene(seed, width=61, height=47, depth=3, spp=1, stochastic=False) -> str:
+def fuzz_scene(seed, width=61, height=47, depth=3, spp=1, stochastic=False, camera_sphere_radius=2.5) -> str:
     """HW3-dialect scene for differential testing against the reference binaries (HW3 / HW4 / HW5 / HW6 / HW7 all load
     it): odd resolution and an axis-aligned camera (the centre ray is exactly (0,0,-1): the box test's skipped axes),
     meshes under random Scaling / Rotation / Translation chains including NEGATIVE (mirroring) scales, instances with
     and without resetTransform, transformed stand-alone triangles and spheres (non-uniform scale), zero-area and
     edge-on triangles, a sphere around the camera, smooth and flat shading, mirror and glass, two point lights.
     `stochastic` adds an area light, a glossy mirror, depth of field and a motion-blurred instance and sphere (for the
-    draw-for-draw replay tests; use with spp > 1)."""
+    draw-for-draw replay tests; use with spp > 1).
+
+    `camera_sphere_radius`: the sphere around the camera.  At the default 2.5 it is a small room: most primary rays end
+    on its inside (the `t2 < 0 -> t1` branch everywhere) and only what happens to lie within 2.5 of the camera shows.
+    At 40 it is a backdrop behind everything, and the meshes, instances, triangles and spheres fill the frame — the
+    variant the `open` tests use."""
     rng = np.random.default_rng(1000 + seed)
     verts = []
     nv = 0
@@ -617,7 +622,7 @@ def fuzz_scene(seed, width=61, height=47, depth=3, spp=1, stochastic=False) -> s
     cs = np.array([[-1.5, 0.2, -3.5], [0, 0, 0], [1.2, -0.4, -2.6], [0.0, 0.0, 1.0]], np.float32)
     cb = push(cs)
     sph = ""
-    for i, (r, mat, tr) in enumerate(((0.7, 2, ""), (0.6, 1, chain()), (0.5, 3, ""), (2.5, 4, ""))):
+    for i, (r, mat, tr) in enumerate(((0.7, 2, ""), (0.6, 1, chain()), (0.5, 3, ""), (float(camera_sphere_radius), 4, ""))):
         tx = f"      <Transformations>{tr}</Transformations>\n" if tr else ""
         mb = "      <MotionBlur>0.3 0.1 -0.2</MotionBlur>\n" if (stochastic and i == 0) else ""
         sph += (f'    <Sphere id="{i + 1}">\n      <Material>{mat}</Material>\n{tx}{mb}      <Center>{cb + i + 1}</Center>\n'

@@ -5,7 +5,7 @@
 # forced standard includes and a case shim for HW1.
 # HW5/HW6: their main.cpp needs OpenCV (absent), so every OTHER translation unit of the tree is linked with
 # oracle/ref_driver_hdr.cpp, which calls the same Scene seam and dumps the float pixels.
-# Usage: oracle/build_ref.sh [tree ...]   (default: hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw4f hw7f probe)
+# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat3, b200main3)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${CENG795_REFERENCE:-/root/reference}"
@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat3 b200main3)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -94,6 +94,37 @@ build_ppm_eye() { # PPM's objects except main.cpp + oracle/ref_driver_ppm.cpp: e
   $CXX -pthread -Wl,--allow-multiple-definition "$objdir/ref_driver_ppm.o" "${objs[@]}" -o "$OUT/ppm_eye"
   echo "built $OUT/ppm_eye"
 }
+build_flatten3() { # HW3's objects except main.cpp + integration/flatten_hw3.cpp + oracle/ref_driver_flatten.cpp
+  local dir="$REF/HW3" objdir="$OUT/obj_hw3" repo; repo="$(dirname "$HERE")"
+  [ -d "$objdir" ] || build_tree hw3 "$dir"
+  local objs=()
+  for f in "$dir"/src/*.cpp; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    objs+=("$objdir/$(basename "$f" .cpp).o")
+  done
+  # the reference's own dialect and flags, as a maintainer of the tree would compile it
+  $CXX $FLAGS -fno-access-control -I"$dir/include" -I"$repo/include" -c "$repo/integration/flatten_hw3.cpp" -o "$objdir/flatten_hw3.o"
+  $CXX $FLAGS -I"$dir/include" -I"$repo/include" -c "$HERE/ref_driver_flatten.cpp" -o "$objdir/ref_driver_flatten.o"
+  $CXX -std=c++17 -O2 -c "$repo/ceng795_b200/csrc/scene_cache.cpp" -o "$objdir/scene_cache.o"
+  $CXX -pthread "${objs[@]}" "$objdir/flatten_hw3.o" "$objdir/ref_driver_flatten.o" "$objdir/scene_cache.o" -o "$OUT/flat3_flatten"
+  echo "built $OUT/flat3_flatten"
+}
+build_b200_main3() { # the drop-in: HW3's objects except main.cpp + integration/{flatten_hw3,main_hw3_b200}.cpp + libb200rt.so
+  local dir="$REF/HW3" objdir="$OUT/obj_hw3" repo; repo="$(dirname "$HERE")"
+  [ -d "$objdir" ] || build_tree hw3 "$dir"
+  if [ ! -f "$repo/ceng795_b200/libb200rt.so" ]; then echo "b200main3: libb200rt.so not built yet, skipped" >&2; return 0; fi
+  local objs=()
+  for f in "$dir"/src/*.cpp; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    objs+=("$objdir/$(basename "$f" .cpp).o")
+  done
+  $CXX $FLAGS -fno-access-control -I"$dir/include" -I"$repo/include" -c "$repo/integration/flatten_hw3.cpp" -o "$objdir/flatten_hw3.o"
+  $CXX $FLAGS -I"$dir/include" -I"$repo/include" -c "$repo/integration/main_hw3_b200.cpp" -o "$objdir/main_hw3_b200.o"
+  # found at run time next to the repo's package wherever the snapshot lands: oracle/_ref/../../ceng795_b200
+  $CXX -pthread "${objs[@]}" "$objdir/flatten_hw3.o" "$objdir/main_hw3_b200.o" -L"$repo/ceng795_b200" -lb200rt \
+    -Wl,-rpath,'$ORIGIN/../../ceng795_b200' -o "$OUT/hw3_b200_raytracer"
+  echo "built $OUT/hw3_b200_raytracer"
+}
 for t in "${TREES[@]}"; do
   case "$t" in
     hw1) build_flat hw1 "$REF/HW1" -I"$HERE/shim" ;;
@@ -108,6 +139,8 @@ for t in "${TREES[@]}"; do
     hw4f) build_tree_driver hw4f "$REF/HW4" ;;   # they pin the oracle at float level (tests/test_oracle_golden.py)
     hw7f) build_tree_driver hw7f "$REF/HW7" ;;
     probe) build_probe ;;
+    flat3) build_flatten3 ;;
+    b200main3) build_b200_main3 ;;
     ppmeye) build_ppm_eye ;;
     ppm) build_tree ppm "$REF/PPM" -DNDEBUG ;;
     *) echo "unknown tree $t" >&2; exit 2 ;;

@@ -1,0 +1,32 @@
+// TEST INFRASTRUCTURE ONLY — runs integration/flatten_hw3.cpp (the reference-side half of the drop-in boundary) on the
+// reference's own `Scene`.  Linked by oracle/build_ref.sh (target flat3) with the UNMODIFIED objects of
+// /root/reference/HW3 minus main.cpp, plus ceng795_b200/csrc/scene_cache.cpp for the file format:
+//   flat3_flatten <scene.xml> <out.b200rt>
+// parses the XML with the reference's loader, flattens the objects it built and writes the description with
+// b200rt_scene_desc_save.  tests/test_flatten_reference.py compares that file with what b200rt_builder_* makes of the
+// same XML.
+#include <cstdio>
+#include <string>
+
+#include "Scene.h"
+#include "b200rt.h"
+
+struct b200rt_flat_hw3;
+extern "C" b200rt_flat_hw3* b200rt_flatten_hw3(const Scene& scene);
+extern "C" const B200SceneDesc* b200rt_flat_hw3_desc(const b200rt_flat_hw3* f);
+extern "C" void b200rt_flat_hw3_free(b200rt_flat_hw3* f);
+static std::string g_err;
+extern "C" void b200rt_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }   // lives in the CUDA TU of the library
+
+int main(int argc, char** argv) {
+  if (argc < 3) {
+    std::fprintf(stderr, "usage: %s scene.xml out.b200rt\n", argv[0]);
+    return 1;
+  }
+  Scene scene(argv[1]);
+  b200rt_flat_hw3* flat = b200rt_flatten_hw3(scene);
+  const int rc = b200rt_scene_desc_save(b200rt_flat_hw3_desc(flat), argv[2]);
+  if (rc != B200RT_OK) std::fprintf(stderr, "save failed: %s\n", g_err.c_str());
+  b200rt_flat_hw3_free(flat);
+  return rc == B200RT_OK ? 0 : 2;
+}

@@ -37,6 +37,15 @@ CASES = {
     "hw7_whitted_depth1": ("hw7", "hw7_scene", dict(width=96, height=80, depth=1, n=8, light_scale=2.0, seed=801)),
 }
 
+#: PNGs of the unmodified HW3 binary that the DROP-IN binary (integration/main_hw3_b200.cpp: the reference's host with
+#: the render fan-out replaced by libb200rt.so) has to reproduce — tests/test_z_dropin_binary.py.  Kept apart from CASES:
+#: those parametrise the early GPU parity tests, these were added after the round's GPU budget was spent.
+DROPIN_CASES = {
+    # the open fuzz scene: meshes under mirroring transform chains, instances, transformed triangles and spheres,
+    # mirror and glass all in view
+    "fuzz_open_hw3": ("hw3", "fuzz_scene", dict(seed=1, width=96, height=72, camera_sphere_radius=40.0)),
+}
+
 
 #: float-level pins: name -> (semantics, reference binary, generator, kwargs).  The binary is the tree's own objects
 #: linked with oracle/ref_driver_hdr.cpp (HW5/HW6: their main.cpp needs OpenCV; hw7f: the same twin for HW7), which
@@ -54,7 +63,7 @@ ASSETS = os.path.join(HERE, "assets")   # texture images the HW7 scenes refer to
 
 
 def scene_xml(name):
-    tree, gen, kw = CASES[name]
+    tree, gen, kw = CASES[name] if name in CASES else DROPIN_CASES[name]
     if gen == "hw7_scene":
         os.makedirs(ASSETS, exist_ok=True)
         return tree, getattr(scenes, gen)(ASSETS, **kw)
@@ -79,9 +88,9 @@ if __name__ == "__main__":
         if f.endswith(".f32") or f == "scene.xml":
             os.remove(os.path.join(ASSETS, f))
     meta = {}
-    for name in CASES:
+    for name in list(CASES) + list(DROPIN_CASES):
         tree, xml = scene_xml(name)
-        res = cpu.run_reference(tree, xml, workdir=ASSETS if CASES[name][1] == "hw7_scene" else None)
+        res = cpu.run_reference(tree, xml, workdir=ASSETS if name in CASES and CASES[name][1] == "hw7_scene" else None)
         img = list(res["images"].values())[0]
         image.write_png(os.path.join(HERE, name + ".png"), img)
         meta[name] = {"tree": tree, "shape": list(img.shape), "threads": res["threads"]}

@@ -97,15 +97,17 @@ def test_oracle_tie_breaking_matches_live_reference(tree, spacing):
 
 
 @pytest.mark.parametrize("tree", ["hw1", "hw2", "hw3", "hw4", "hw5", "hw6", "hw7"])
-@pytest.mark.parametrize("seed", [0, 1, 2])
-def test_oracle_fuzz_scenes_match_live_reference(tree, seed):
+@pytest.mark.parametrize("seed,radius", [(0, 2.5), (1, 2.5), (2, 2.5), (0, 40.0), (1, 40.0), (3, 40.0)])
+def test_oracle_fuzz_scenes_match_live_reference(tree, seed, radius):
     """Differential test on scenes built to be awkward (scenes.fuzz_scene: mirroring scales, transform chains,
     resetTransform on and off, zero-area triangles, a sphere around the camera, an axis-aligned centre ray, mirror and
-    glass): PNG trees byte for byte, HW5 / HW6 float for float."""
+    glass): PNG trees byte for byte, HW5 / HW6 float for float.  Radius 2.5 is the closed room (nearly every primary
+    ray ends on the inside of the camera's sphere); radius 40 opens it, and 10-14 different objects, their shadows,
+    mirror images and refractions fill the frame."""
     if not cpu.have_ref(tree):
         pytest.skip("oracle/_ref not built on this box")
     from ceng795_b200 import scenes
-    xml = scenes.fuzz_scene(seed)
+    xml = scenes.fuzz_scene(seed, camera_sphere_radius=radius)
     res = cpu.run_reference(tree, xml)
     hs = scene.HostScene(scene.parse_xml(xml, tree))
     rgbw, _, _, _ = cpu.render(hs, 0)
@@ -208,14 +210,15 @@ def test_oracle_replays_dof_and_motion_blur_draw_for_draw(tmp_path, tree):
 
 
 @pytest.mark.parametrize("tree", ["hw3f", "hw4f", "hw5", "hw6", "hw7f"])
-@pytest.mark.parametrize("seed", [0, 1])
-def test_oracle_replays_stochastic_fuzz_scenes(tmp_path, tree, seed):
+@pytest.mark.parametrize("seed,radius", [(0, 2.5), (1, 2.5), (0, 40.0), (2, 40.0)])
+def test_oracle_replays_stochastic_fuzz_scenes(tmp_path, tree, seed, radius):
     """The awkward scenes of scenes.fuzz_scene with an area light, a glossy mirror, depth of field, a motion-blurred
-    instance and sphere, 4 samples per pixel: every float of the frame, on five trees, through the replay."""
+    instance and sphere, 4 samples per pixel: every float of the frame, on five trees, through the replay — the closed
+    room (radius 2.5) and the open variant where the moving instance, the glossy mirror and the glass are in view."""
     if not cpu.have_ref(tree):
         pytest.skip("oracle/_ref not built on this box")
     from ceng795_b200 import scenes
-    xml = scenes.fuzz_scene(seed, width=41, height=33, spp=4, stochastic=True)
+    xml = scenes.fuzz_scene(seed, width=41, height=33, spp=4, stochastic=True, camera_sphere_radius=radius)
     got, want = _replay(tree, xml, str(tmp_path))
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.mean(got == want))
 

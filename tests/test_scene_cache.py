@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from ceng795_b200 import _lib, scene, scenes
+from ceng795_b200 import _lib, image, scene, scenes
 from oracle import cpu
 from tests.golden.make_golden import ASSETS, scene_xml
 
@@ -112,3 +112,24 @@ def test_parallel_builder_is_byte_identical_to_sequential(tmp_path, monkeypatch,
     seq.save(p0)
     par.save(p1)
     assert open(p0, "rb").read() == open(p1, "rb").read()
+
+
+@pytest.mark.gpu
+def test_reference_flattened_scene_renders_like_the_oracle(gpu):
+    """The drop-in path end to end: tests/golden/flat3_fuzz0.b200rt is the description integration/flatten_hw3.cpp
+    made from the `Scene` the reference's own loader built (tests/test_flatten_reference.py).  It carries no SAH tree —
+    b200rt_scene_create builds it — and the device's ids, t and ray counts are the oracle's on the same description, the
+    image to 1 LSB (the bar of test_gpu_parity.py::test_fuzz_scenes_match_the_oracle, which renders this same scene
+    from the builder's description)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flat3_fuzz0.b200rt")
+    sc = scene.Scene.from_cache(path)
+    assert sc.host.desc.n_fast_tris == 0
+    o_rgbw, o_ids, o_t, cnt = cpu.render(sc.host, 0, want_ids=True)
+    for exact in (0, 1):
+        ids, t = sc.primary_ids(0, exact_traversal=exact)
+        assert np.array_equal(ids, o_ids) and np.array_equal(t.view(np.uint32), o_t.view(np.uint32))
+    rgbw, st = sc.render_image(0)
+    assert st.nodes_visited > 0
+    assert (st.rays_primary, st.rays_shadow, st.rays_secondary) == (cnt.rays_primary, cnt.rays_shadow, cnt.rays_secondary)
+    cmp = image.compare_8bit(image.quantise(rgbw, sc.semantics), image.quantise(o_rgbw, sc.semantics))
+    assert cmp["within1"] >= 0.999, cmp
