@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY — runs integration/flatten_hw3.cpp (the reference-side half of the drop-in boundary) on the
-// reference's own `Scene`.  Linked by oracle/build_ref.sh (target flat3) with the UNMODIFIED objects of
-// /root/reference/HW3 minus main.cpp, plus ceng795_b200/csrc/scene_cache.cpp for the file format:
+// reference's own `Scene`.  Linked by oracle/build_ref.sh (target flat3; flat7 with -DFLATTEN_HW7) with the UNMODIFIED
+// objects of /root/reference/HW3 (HW7) minus main.cpp, plus ceng795_b200/csrc/scene_cache.cpp for the file format:
 //   flat3_flatten <scene.xml> <out.b200rt>
 // parses the XML with the reference's loader, flattens the objects it built and writes the description with
 // b200rt_scene_desc_save.  tests/test_flatten_reference.py compares that file with what b200rt_builder_* makes of the
@@ -11,6 +11,12 @@
 #include "Scene.h"
 #include "b200rt.h"
 
+#ifdef FLATTEN_HW7   // the same driver against integration/flatten_hw7.cpp and the HW7 tree's objects (target flat7)
+#define b200rt_flat_hw3 b200rt_flat_hw7
+#define b200rt_flatten_hw3 b200rt_flatten_hw7
+#define b200rt_flat_hw3_desc b200rt_flat_hw7_desc
+#define b200rt_flat_hw3_free b200rt_flat_hw7_free
+#endif
 struct b200rt_flat_hw3;
 extern "C" b200rt_flat_hw3* b200rt_flatten_hw3(const Scene& scene);
 extern "C" const B200SceneDesc* b200rt_flat_hw3_desc(const b200rt_flat_hw3* f);

@@ -21,6 +21,7 @@ from tests.test_scene_cache import _arrays
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FLATTEN = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "flat3_flatten")
+FLATTEN7 = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "flat7_flatten")
 GOLDEN = os.path.join(HERE, "golden", "flat3_fuzz0.b200rt")
 
 # arrays that do not depend on how top-level objects are numbered
@@ -49,12 +50,43 @@ def _canonical(hs):
     return by_rank, nodes, relabel(d.root)
 
 
+def _lights(hs):
+    """lights[] as bytes, with the `object` of mesh / sphere lights (an instance / sphere LABEL) rewritten to the
+    depth-first rank of that object."""
+    d = hs.desc
+    out = []
+    for i in range(d.n_lights):
+        l = _lib.Light.from_buffer_copy(C.string_at(C.addressof(d.lights[i]), C.sizeof(_lib.Light)))
+        if l.kind == _lib.LIGHT_MESH:
+            l.object = d.instances[l.object].rank
+        elif l.kind == _lib.LIGHT_SPHERE:
+            l.object = d.spheres[l.object].rank
+        out.append(bytes(l))
+    return out
+
+
 def _assert_same_description(ref, own):
     a, b = _arrays(ref.desc), _arrays(own.desc)
     for k in PLAIN:
-        assert a[k] == b[k], k
+        if k == "materials":      # `degamma` is an INPUT flag of the builder (values already converted); the objects keep no trace of it
+            x, y = (np.frombuffer(v, np.uint32).reshape(-1, 24).copy() for v in (a[k], b[k]))
+            x[:, 19] = y[:, 19] = 0
+            assert np.array_equal(x, y), k
+        elif k == "lights":
+            assert _lights(ref) == _lights(own), k
+        elif k == "textures":     # Perlin tables: shuffled by a clock-seeded engine in every run of the reference
+            x, y = (np.frombuffer(v, np.uint32).reshape(-1, C.sizeof(_lib.Texture) // 4).copy() for v in (a[k], b[k]))
+            o = _lib.Texture.perm.offset // 4
+            for row in x:
+                if row[0] == _lib.TEX_PERLIN:
+                    assert sorted(row[o:o + 16].tolist()) == list(range(16))
+            x[:, o:o + 16] = y[:, o:o + 16] = 0
+            assert np.array_equal(x, y), k
+        else:
+            assert a[k] == b[k], k
     for f in ("semantics", "max_depth", "shadow_eps", "isect_eps", "n_tris", "n_nodes", "n_verts", "n_meshes",
-              "n_instances", "n_spheres", "n_triprims", "background_texture", "env_light", "integrator"):
+              "n_instances", "n_spheres", "n_triprims", "n_lights", "n_textures", "n_texels", "n_brdfs", "n_light_cdf",
+              "background_texture", "env_light", "integrator", "importance_sampling"):
         assert getattr(ref.desc, f) == getattr(own.desc, f), f
     for f in ("background", "ambient", "root_box"):
         assert list(getattr(ref.desc, f)) == list(getattr(own.desc, f)), f
@@ -72,12 +104,12 @@ def _assert_same_description(ref, own):
     assert np.array_equal(na, nb) and roota == rootb
 
 
-def _flatten(xml, tmp_path):
+def _flatten(xml, tmp_path, exe=FLATTEN):
     p = str(tmp_path / "scene.xml")
     with open(p, "w") as f:
         f.write(xml)
     out = str(tmp_path / "flat.b200rt")
-    r = subprocess.run([FLATTEN, p, out], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, p, out], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))   # textures: relative paths
     assert r.returncode == 0, r.stderr
     return out
 
@@ -122,3 +154,54 @@ def test_golden_flattened_scene_equals_builder_and_renders_the_same():
     assert np.array_equal(img_r.view(np.uint32), img_o.view(np.uint32))
     assert np.array_equal(t_r.view(np.uint32), t_o.view(np.uint32))
     assert np.array_equal(ids_r < 0, ids_o < 0)      # misses agree; hit labels differ only by the object numbering
+
+
+needs_ref7 = pytest.mark.skipif(not os.path.exists(FLATTEN7), reason="oracle/_ref/flat7_flatten not built on this box")
+
+
+@needs_ref7
+@pytest.mark.parametrize("case", ["textured", "lights_pathtraced", "perlin", "env_light", "background", "camera_left",
+                                  "camera_simple", "fuzz_open", "fuzz_stochastic"])
+def test_flattened_hw7_scene_equals_builder(tmp_path, case):
+    """integration/flatten_hw7.cpp on the HW7 tree's own objects: everything flatten_hw3 covers plus image textures (texels
+    as `Texture` holds them after degamma), Perlin textures, texture coordinates per triangle, the five BRDF classes,
+    the polymorphic light list in the order the shading loop walks it — point, area, spot, directional, environment
+    (its EXR texels), mesh lights with their area CDF over the BVH-reordered triangles, sphere lights — glass instances'
+    culling flag, the left-handed and the `simple` camera, the integrator switch.  Only two things are not compared
+    bit for bit, because the objects do not hold them: the builder's `degamma` input flag, and the Perlin table (the
+    reference shuffles a fresh one from the clock in every run; it must be a permutation of 0..15)."""
+    import re
+    d = str(tmp_path)
+    kw = dict(width=48, height=36, n=6, depth=2, mesh_slices=(6, 7))
+    if case == "textured":
+        xml = scenes.hw7_scene(d, width=64, height=48, light_scale=3.0)
+    elif case == "lights_pathtraced":
+        xml = scenes.hw7_scene(d, spp=4, stochastic_lights=True, path_tracing=True, importance=True, light_scale=0.5,
+                               **{**kw, "depth": 3})
+    elif case == "perlin":
+        xml = scenes.hw7_scene(d, perlin=True, **kw)
+    elif case == "env_light":
+        from ceng795_b200 import image
+        rng = np.random.default_rng(3)
+        image.write_exr_f32(str(tmp_path / "env.exr"), (rng.uniform(0, 1, (16, 32, 3)) ** 3 * 40).astype(np.float32))
+        xml = scenes.hw7_scene(d, **kw).replace(
+            "  </Lights>", '    <SphericalDirectionalLight id="1"><EnvMapName>env.exr</EnvMapName>'
+                           "</SphericalDirectionalLight>\n  </Lights>")
+    elif case == "background":
+        xml = scenes.hw7_scene(d, **kw).replace(
+            "<Scene>\n", "<Scene>\n  <BackgroundTexture>tex_checker.png</BackgroundTexture>\n", 1)
+    elif case == "camera_left":
+        xml = scenes.hw7_scene(d, **kw).replace('<Camera id="1">', '<Camera id="1" handedness="left">')
+    elif case == "camera_simple":
+        xml = scenes.hw7_scene(d, **kw)
+        xml = re.sub(r"      <Gaze>.*?</Gaze>\n", "      <GazePoint>0.2 0.6 -1.5</GazePoint>\n", xml)
+        xml = re.sub(r"      <NearPlane>.*?</NearPlane>\n", "      <FovY>52</FovY>\n", xml)
+        xml = xml.replace('<Camera id="1">', '<Camera id="1" type="simple">')
+    elif case == "fuzz_open":
+        xml = scenes.fuzz_scene(2, camera_sphere_radius=40.0)
+    else:
+        xml = scenes.fuzz_scene(1, spp=9, stochastic=True, camera_sphere_radius=40.0)
+    ref = scene.CachedHostScene(_flatten(xml, tmp_path, FLATTEN7))
+    own = scene.HostScene(scene.parse_xml(xml, "hw7", base_dir=d))
+    assert ref.desc.semantics == own.desc.semantics == 7
+    _assert_same_description(ref, own)
