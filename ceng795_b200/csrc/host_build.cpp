@@ -850,11 +850,14 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
       b->tri_tex.push_back(-1);
     }
   }
-  // Vertex::finalize_normal — HW3/src/Scene.cpp:872-877
+  // Vertex::finalize_normal — HW3/src/Scene.cpp:872-877.  The PPM tree finalises EVERY vertex, with or without a face
+  // on it (PPM/src/Scene.cpp:499-501): a vertex no face uses — a sphere centre — ends up 0/0 there.  Nothing reads
+  // those normals; they are kept only so that this description equals the one integration/flatten_ppm.cpp copies
+  // out of the tree's own objects.
   b->vert_normal.assign((size_t)nv * 3, 0.f);
   for (int i = 0; i < nv; i++) {
     V3 n = vnorm[i];
-    if (vhas[i]) n = normalize(n);
+    if (vhas[i] || b->semantics == B200RT_SEM_PPM) n = normalize(n);
     store3(&b->vert_normal[3 * (size_t)i], n);
   }
 

@@ -5,7 +5,7 @@
 # forced standard includes and a case shim for HW1.
 # HW5/HW6: their main.cpp needs OpenCV (absent), so every OTHER translation unit of the tree is linked with
 # oracle/ref_driver_hdr.cpp, which calls the same Scene seam and dumps the float pixels.
-# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat3, flat7, b200main3)
+# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat3, flat7, flatppm, b200main3)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${CENG795_REFERENCE:-/root/reference}"
@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat3 flat7 b200main3)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat3 flat7 flatppm b200main3)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -123,6 +123,20 @@ build_flatten7() { # HW7's objects except main.cpp + integration/flatten_hw7.cpp
   $CXX -pthread "${objs[@]}" "$objdir/flatten_hw7.o" "$objdir/ref_driver_flatten.o" "$objdir/scene_cache.o" -o "$OUT/flat7_flatten"
   echo "built $OUT/flat7_flatten"
 }
+build_flatten_ppm() { # PPM's objects except main.cpp + integration/flatten_ppm.cpp + the same driver
+  local dir="$REF/PPM" objdir="$OUT/obj_ppm" repo; repo="$(dirname "$HERE")"
+  [ -d "$objdir" ] || build_tree ppm "$dir" -DNDEBUG
+  local objs=()
+  for f in "$dir"/src/*.cpp; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    objs+=("$objdir/$(basename "$f" .cpp).o")
+  done
+  $CXX $FLAGS -DNDEBUG -fno-access-control -I"$dir/include" -I"$repo/include" -c "$repo/integration/flatten_ppm.cpp" -o "$objdir/flatten_ppm.o"
+  $CXX $FLAGS -DNDEBUG -DFLATTEN_PPM -I"$dir/include" -I"$repo/include" -c "$HERE/ref_driver_flatten.cpp" -o "$objdir/ref_driver_flatten.o"
+  $CXX -std=c++17 -O2 -c "$repo/ceng795_b200/csrc/scene_cache.cpp" -o "$objdir/scene_cache.o"
+  $CXX -pthread "${objs[@]}" "$objdir/flatten_ppm.o" "$objdir/ref_driver_flatten.o" "$objdir/scene_cache.o" -o "$OUT/flatppm_flatten"
+  echo "built $OUT/flatppm_flatten"
+}
 build_b200_main3() { # the drop-in: HW3's objects except main.cpp + integration/{flatten_hw3,main_hw3_b200}.cpp + libb200rt.so
   local dir="$REF/HW3" objdir="$OUT/obj_hw3" repo; repo="$(dirname "$HERE")"
   [ -d "$objdir" ] || build_tree hw3 "$dir"
@@ -155,6 +169,7 @@ for t in "${TREES[@]}"; do
     probe) build_probe ;;
     flat3) build_flatten3 ;;
     flat7) build_flatten7 ;;
+    flatppm) build_flatten_ppm ;;
     b200main3) build_b200_main3 ;;
     ppmeye) build_ppm_eye ;;
     ppm) build_tree ppm "$REF/PPM" -DNDEBUG ;;

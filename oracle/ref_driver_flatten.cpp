@@ -17,6 +17,12 @@
 #define b200rt_flat_hw3_desc b200rt_flat_hw7_desc
 #define b200rt_flat_hw3_free b200rt_flat_hw7_free
 #endif
+#ifdef FLATTEN_PPM   // ... and against integration/flatten_ppm.cpp and the PPM tree's objects (target flatppm)
+#define b200rt_flat_hw3 b200rt_flat_ppm
+#define b200rt_flatten_hw3 b200rt_flatten_ppm
+#define b200rt_flat_hw3_desc b200rt_flat_ppm_desc
+#define b200rt_flat_hw3_free b200rt_flat_ppm_free
+#endif
 struct b200rt_flat_hw3;
 extern "C" b200rt_flat_hw3* b200rt_flatten_hw3(const Scene& scene);
 extern "C" const B200SceneDesc* b200rt_flat_hw3_desc(const b200rt_flat_hw3* f);

@@ -205,3 +205,23 @@ def test_flattened_hw7_scene_equals_builder(tmp_path, case):
     own = scene.HostScene(scene.parse_xml(xml, "hw7", base_dir=d))
     assert ref.desc.semantics == own.desc.semantics == 7
     _assert_same_description(ref, own)
+
+
+FLATTEN_PPM = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "flatppm_flatten")
+
+
+@pytest.mark.skipif(not os.path.exists(FLATTEN_PPM), reason="oracle/_ref/flatppm_flatten not built on this box")
+@pytest.mark.parametrize("kw", [dict(width=64, height=48, mesh_slices=(12, 10)), dict(width=40, height=30, mesh_slices=(31, 29), seed=5)])
+def test_flattened_ppm_scene_equals_builder(tmp_path, kw):
+    """integration/flatten_ppm.cpp on the PPM tree's own objects (cfg5's scene at small size: glass and mirror spheres,
+    mesh instances with the culling-off flag, point light; spheres ahead of the meshes in Scene::bvh).  It is also how
+    the builder learned that this tree normalises the normal of EVERY vertex, so that a vertex no face uses (a sphere
+    centre) holds 0/0 — bit-equal now, NaN included."""
+    kw = dict(kw)
+    seed = kw.pop("seed", None)
+    xml = scenes.cfg5_ppm(photons_per_iteration=1000, iterations=2, **({"seed": seed} if seed is not None else {}), **kw)
+    ref = scene.CachedHostScene(_flatten(xml, tmp_path, FLATTEN_PPM))
+    own = scene.HostScene(scene.parse_xml(xml, "ppm"))
+    assert ref.desc.semantics == own.desc.semantics == 8
+    _assert_same_description(ref, own)
+    assert np.isnan(np.frombuffer(_arrays(own.desc)["vert_normal"], np.float32)).any()
