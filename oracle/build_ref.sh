@@ -5,7 +5,7 @@
 # forced standard includes and a case shim for HW1.
 # HW5/HW6: their main.cpp needs OpenCV (absent), so every OTHER translation unit of the tree is linked with
 # oracle/ref_driver_hdr.cpp, which calls the same Scene seam and dumps the float pixels.
-# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat3, flat7, flatppm, b200main3)
+# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat3, flat7, flatppm, b200main3, b200main7)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${CENG795_REFERENCE:-/root/reference}"
@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat3 flat7 flatppm b200main3)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat3 flat7 flatppm b200main3 b200main7)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -153,6 +153,21 @@ build_b200_main3() { # the drop-in: HW3's objects except main.cpp + integration/
     -Wl,-rpath,'$ORIGIN/../../ceng795_b200' -o "$OUT/hw3_b200_raytracer"
   echo "built $OUT/hw3_b200_raytracer"
 }
+build_b200_main7() { # the same drop-in for the HW7 tree
+  local dir="$REF/HW7" objdir="$OUT/obj_hw7" repo; repo="$(dirname "$HERE")"
+  [ -d "$objdir" ] || build_tree hw7 "$dir"
+  if [ ! -f "$repo/ceng795_b200/libb200rt.so" ]; then echo "b200main7: libb200rt.so not built yet, skipped" >&2; return 0; fi
+  local objs=()
+  for f in "$dir"/src/*.cpp; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    objs+=("$objdir/$(basename "$f" .cpp).o")
+  done
+  $CXX $FLAGS -fno-access-control -I"$dir/include" -I"$repo/include" -c "$repo/integration/flatten_hw7.cpp" -o "$objdir/flatten_hw7.o"
+  $CXX $FLAGS -fno-access-control -I"$dir/include" -I"$repo/include" -c "$repo/integration/main_hw7_b200.cpp" -o "$objdir/main_hw7_b200.o"
+  $CXX -pthread "${objs[@]}" "$objdir/flatten_hw7.o" "$objdir/main_hw7_b200.o" -L"$repo/ceng795_b200" -lb200rt \
+    -Wl,-rpath,'$ORIGIN/../../ceng795_b200' -o "$OUT/hw7_b200_raytracer"
+  echo "built $OUT/hw7_b200_raytracer"
+}
 for t in "${TREES[@]}"; do
   case "$t" in
     hw1) build_flat hw1 "$REF/HW1" -I"$HERE/shim" ;;
@@ -171,6 +186,7 @@ for t in "${TREES[@]}"; do
     flat7) build_flatten7 ;;
     flatppm) build_flatten_ppm ;;
     b200main3) build_b200_main3 ;;
+    b200main7) build_b200_main7 ;;
     ppmeye) build_ppm_eye ;;
     ppm) build_tree ppm "$REF/PPM" -DNDEBUG ;;
     *) echo "unknown tree $t" >&2; exit 2 ;;

@@ -44,6 +44,8 @@ DROPIN_CASES = {
     # the open fuzz scene: meshes under mirroring transform chains, instances, transformed triangles and spheres,
     # mirror and glass all in view
     "fuzz_open_hw3": ("hw3", "fuzz_scene", dict(seed=1, width=96, height=72, camera_sphere_radius=40.0)),
+    # HW7 with a Photographic tonemapping operator on the camera: the PNG is apply_tmo + the sRGB loop of main
+    "hw7_tonemapped": ("hw7", "hw7_scene", dict(width=96, height=72, light_scale=3.0, tonemap=True)),
 }
 
 
@@ -90,8 +92,10 @@ if __name__ == "__main__":
     meta = {}
     for name in list(CASES) + list(DROPIN_CASES):
         tree, xml = scene_xml(name)
-        res = cpu.run_reference(tree, xml, workdir=ASSETS if name in CASES and CASES[name][1] == "hw7_scene" else None)
-        img = list(res["images"].values())[0]
+        gen = (CASES[name] if name in CASES else DROPIN_CASES[name])[1]
+        res = cpu.run_reference(tree, xml, workdir=ASSETS if gen == "hw7_scene" else None)
+        pngs = [k for k in res["images"] if k.endswith(".png")]      # a tonemapped camera also leaves an .exr
+        img = res["images"][pngs[0]] if pngs else list(res["images"].values())[0]
         image.write_png(os.path.join(HERE, name + ".png"), img)
         meta[name] = {"tree": tree, "shape": list(img.shape), "threads": res["threads"]}
         print(name, img.shape)

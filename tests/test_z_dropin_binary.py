@@ -16,14 +16,15 @@ from tests.golden.make_golden import scene_xml
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BINARY = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "hw3_b200_raytracer")
+BINARY7 = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "hw7_b200_raytracer")
 needs_binary = pytest.mark.skipif(not os.path.exists(BINARY), reason="oracle/_ref/hw3_b200_raytracer not built")
 
 
-def _run(xml, tmp_path):
+def _run(xml, tmp_path, exe=BINARY):
     p = str(tmp_path / "scene.xml")
     with open(p, "w") as f:
         f.write(xml)
-    return subprocess.run([BINARY, p], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    return subprocess.run([exe, p], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
 
 
 @needs_binary
@@ -56,3 +57,39 @@ def test_dropin_binary_writes_the_reference_picture(gpu, tmp_path, name):
     cmp = image.compare_8bit(got, want)
     assert cmp["within1"] >= 0.999 and cmp["max"] <= 2, cmp
     assert "kernel launches" in r.stdout
+
+
+needs_binary7 = pytest.mark.skipif(not os.path.exists(BINARY7), reason="oracle/_ref/hw7_b200_raytracer not built")
+
+
+def _hw7_xml(name, tmp_path):
+    from ceng795_b200 import scenes
+    from tests.golden.make_golden import CASES, DROPIN_CASES
+    _, gen, kw = CASES[name] if name in CASES else DROPIN_CASES[name]
+    assert gen == "hw7_scene"
+    return scenes.hw7_scene(str(tmp_path), **kw)      # writes the texture images next to the XML
+
+
+@needs_binary7
+def test_hw7_dropin_binary_refuses_to_render_without_a_device(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    r = _run(_hw7_xml("hw7_whitted_depth1", tmp_path), tmp_path, BINARY7)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr and "Scene is parsed" in r.stdout
+
+
+@needs_binary7
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hw7_whitted_160", "hw7_whitted_depth1", "hw7_tonemapped"])
+def test_hw7_dropin_binary_writes_the_reference_picture(gpu, tmp_path, name):
+    """The HW7 tree's host (its loader, stb_image textures, BVHs, lodepng) with the fan-out replaced
+    (integration/main_hw7_b200.cpp + flatten_hw7.cpp): textures, five BRDFs, spot and directional lights, mirror and
+    glass — and, for `hw7_tonemapped`, Photographic_tmo::apply_tmo + the sRGB loop replaced by the device tonemap —
+    against the PNG of the unmodified HW7 binary."""
+    r = _run(_hw7_xml(name, tmp_path), tmp_path, BINARY7)
+    assert r.returncode == 0, r.stderr
+    got = image.read_png(str(tmp_path / "hw7.png"))[..., :3]
+    want = image.read_png(os.path.join(HERE, "golden", name + ".png"))[..., :3]
+    cmp = image.compare_8bit(got, want)
+    assert cmp["within1"] >= 0.999 and cmp["max"] <= 2, cmp
