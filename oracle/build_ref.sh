@@ -5,7 +5,7 @@
 # forced standard includes and a case shim for HW1.
 # HW5/HW6: their main.cpp needs OpenCV (absent), so every OTHER translation unit of the tree is linked with
 # oracle/ref_driver_hdr.cpp, which calls the same Scene seam and dumps the float pixels.
-# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat3, flat7, flatppm, b200main3, b200main7)
+# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat3, flat7, flatppm, b200main3, b200main7, b200mainppm)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${CENG795_REFERENCE:-/root/reference}"
@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat3 flat7 flatppm b200main3 b200main7)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat3 flat7 flatppm b200main3 b200main7 b200mainppm)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -168,6 +168,21 @@ build_b200_main7() { # the same drop-in for the HW7 tree
     -Wl,-rpath,'$ORIGIN/../../ceng795_b200' -o "$OUT/hw7_b200_raytracer"
   echo "built $OUT/hw7_b200_raytracer"
 }
+build_b200_main_ppm() { # the same drop-in for the PPM tree
+  local dir="$REF/PPM" objdir="$OUT/obj_ppm" repo; repo="$(dirname "$HERE")"
+  [ -d "$objdir" ] || build_tree ppm "$dir" -DNDEBUG
+  if [ ! -f "$repo/ceng795_b200/libb200rt.so" ]; then echo "b200mainppm: libb200rt.so not built yet, skipped" >&2; return 0; fi
+  local objs=()
+  for f in "$dir"/src/*.cpp; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    objs+=("$objdir/$(basename "$f" .cpp).o")
+  done
+  $CXX $FLAGS -DNDEBUG -fno-access-control -I"$dir/include" -I"$repo/include" -c "$repo/integration/flatten_ppm.cpp" -o "$objdir/flatten_ppm.o"
+  $CXX $FLAGS -DNDEBUG -I"$dir/include" -I"$repo/include" -c "$repo/integration/main_ppm_b200.cpp" -o "$objdir/main_ppm_b200.o"
+  $CXX -pthread "${objs[@]}" "$objdir/flatten_ppm.o" "$objdir/main_ppm_b200.o" -L"$repo/ceng795_b200" -lb200rt \
+    -Wl,-rpath,'$ORIGIN/../../ceng795_b200' -o "$OUT/ppm_b200_raytracer"
+  echo "built $OUT/ppm_b200_raytracer"
+}
 for t in "${TREES[@]}"; do
   case "$t" in
     hw1) build_flat hw1 "$REF/HW1" -I"$HERE/shim" ;;
@@ -187,6 +202,7 @@ for t in "${TREES[@]}"; do
     flatppm) build_flatten_ppm ;;
     b200main3) build_b200_main3 ;;
     b200main7) build_b200_main7 ;;
+    b200mainppm) build_b200_main_ppm ;;
     ppmeye) build_ppm_eye ;;
     ppm) build_tree ppm "$REF/PPM" -DNDEBUG ;;
     *) echo "unknown tree $t" >&2; exit 2 ;;

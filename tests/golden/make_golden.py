@@ -46,6 +46,10 @@ DROPIN_CASES = {
     "fuzz_open_hw3": ("hw3", "fuzz_scene", dict(seed=1, width=96, height=72, camera_sphere_radius=40.0)),
     # HW7 with a Photographic tonemapping operator on the camera: the PNG is apply_tmo + the sRGB loop of main
     "hw7_tonemapped": ("hw7", "hw7_scene", dict(width=96, height=72, light_scale=3.0, tonemap=True)),
+    # one run of the PPM binary (random_device seeds: a SAMPLE, compared statistically; two runs of the binary itself
+    # differ by an RMSE of 9.1 grey levels at this photon count)
+    "ppm_cfg5_small": ("ppm", "cfg5_ppm", dict(width=96, height=72, mesh_slices=(16, 14), photons_per_iteration=400,
+                                               iterations=500, depth=8)),
 }
 
 

@@ -93,3 +93,36 @@ def test_hw7_dropin_binary_writes_the_reference_picture(gpu, tmp_path, name):
     want = image.read_png(os.path.join(HERE, "golden", name + ".png"))[..., :3]
     cmp = image.compare_8bit(got, want)
     assert cmp["within1"] >= 0.999 and cmp["max"] <= 2, cmp
+
+
+BINARY_PPM = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "ppm_b200_raytracer")
+needs_binary_ppm = pytest.mark.skipif(not os.path.exists(BINARY_PPM), reason="oracle/_ref/ppm_b200_raytracer not built")
+
+
+@needs_binary_ppm
+def test_ppm_dropin_binary_refuses_to_render_without_a_device(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    _, xml = scene_xml("ppm_cfg5_small")
+    r = _run(xml, tmp_path, BINARY_PPM)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr and "Scene is parsed" in r.stdout
+
+
+@needs_binary_ppm
+@pytest.mark.gpu
+def test_ppm_dropin_binary_matches_the_reference_statistically(gpu, tmp_path):
+    """The PPM tree's host with its three passes replaced (integration/main_ppm_b200.cpp), same photon bookkeeping as
+    the tree's main (400 photons x 500 rounds; 400 divides by the 8 threads of the box the golden was made on and by
+    the GPU box's 16, so the normalisation is the same).  The reference seeds from random_device, so its PNG is one
+    sample: equal image mean (3 %) and an RMSE within 1.35x the binary's OWN run-to-run RMSE at this photon count
+    (9.1 grey levels, measured when the golden was made) — the bound tests/test_ppm.py uses for the oracle."""
+    _, xml = scene_xml("ppm_cfg5_small")
+    r = _run(xml, tmp_path, BINARY_PPM)
+    assert r.returncode == 0, r.stderr
+    got = image.read_png(str(tmp_path / "cfg5.png"))[..., :3].astype(np.float64)
+    want = image.read_png(os.path.join(HERE, "golden", "ppm_cfg5_small.png"))[..., :3].astype(np.float64)
+    assert abs(got.mean() - want.mean()) <= 0.03 * want.mean(), (got.mean(), want.mean())
+    rmse = np.sqrt(((got - want) ** 2).mean())
+    assert rmse <= 1.35 * 9.1 + 0.5, rmse
+    assert " photons, " in r.stdout and "kernel launches" in r.stdout
