@@ -225,3 +225,19 @@ def test_flattened_ppm_scene_equals_builder(tmp_path, kw):
     assert ref.desc.semantics == own.desc.semantics == 8
     _assert_same_description(ref, own)
     assert np.isnan(np.frombuffer(_arrays(own.desc)["vert_normal"], np.float32)).any()
+
+
+@needs_ref
+@needs_ref7
+def test_flatten_equals_builder_on_twenty_more_random_scenes(tmp_path):
+    """A sweep rather than a parametrisation: 20 more fuzz seeds (open and closed, deterministic and stochastic
+    features alternating) through both trees' flattens."""
+    for seed in range(10, 30):
+        xml = scenes.fuzz_scene(seed, stochastic=bool(seed % 2), spp=4 if seed % 2 else 1,
+                                camera_sphere_radius=40.0 if seed % 3 else 2.5)
+        for tree, exe in (("hw3", FLATTEN), ("hw7", FLATTEN7)):
+            d = tmp_path / f"{tree}_{seed}"
+            d.mkdir()
+            ref = scene.CachedHostScene(_flatten(xml, d, exe))
+            own = scene.HostScene(scene.parse_xml(xml, tree))
+            _assert_same_description(ref, own)
