@@ -5,7 +5,7 @@
 # forced standard includes and a case shim for HW1.
 # HW5/HW6: their main.cpp needs OpenCV (absent), so every OTHER translation unit of the tree is linked with
 # oracle/ref_driver_hdr.cpp, which calls the same Scene seam and dumps the float pixels.
-# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat3, flat7, flatppm, b200main3, b200main7, b200mainppm)
+# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat1, flat3, flat7, flatppm, b200main3, b200main7, b200mainppm)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${CENG795_REFERENCE:-/root/reference}"
@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat3 flat7 flatppm b200main3 b200main7 b200mainppm)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat1 flat3 flat7 flatppm b200main3 b200main7 b200mainppm)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -168,6 +168,26 @@ build_b200_main7() { # the same drop-in for the HW7 tree
     -Wl,-rpath,'$ORIGIN/../../ceng795_b200' -o "$OUT/hw7_b200_raytracer"
   echo "built $OUT/hw7_b200_raytracer"
 }
+build_hw1_binding() { # HW1 (flat directory, Ray.h shim): flatten driver and drop-in main
+  local dir="$REF/HW1" objdir="$OUT/obj_hw1" repo; repo="$(dirname "$HERE")"
+  [ -d "$objdir" ] || build_flat hw1 "$dir" -I"$HERE/shim"
+  local objs=()
+  for f in "$dir"/*.cpp "$dir"/lodepng/*.cpp; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    objs+=("$objdir/$(basename "$f" .cpp).o")
+  done
+  local inc=(-I"$dir" -I"$HERE/shim" -I"$repo/include")
+  $CXX $FLAGS -fno-access-control "${inc[@]}" -c "$repo/integration/flatten_hw1.cpp" -o "$objdir/flatten_hw1.o"
+  $CXX $FLAGS -DFLATTEN_HW1 "${inc[@]}" -c "$HERE/ref_driver_flatten.cpp" -o "$objdir/ref_driver_flatten.o"
+  $CXX -std=c++17 -O2 -c "$repo/ceng795_b200/csrc/scene_cache.cpp" -o "$objdir/scene_cache.o"
+  $CXX -pthread "${objs[@]}" "$objdir/flatten_hw1.o" "$objdir/ref_driver_flatten.o" "$objdir/scene_cache.o" -o "$OUT/flat1_flatten"
+  echo "built $OUT/flat1_flatten"
+  if [ ! -f "$repo/ceng795_b200/libb200rt.so" ]; then echo "b200main1: libb200rt.so not built yet, skipped" >&2; return 0; fi
+  $CXX $FLAGS "${inc[@]}" -c "$repo/integration/main_hw1_b200.cpp" -o "$objdir/main_hw1_b200.o"
+  $CXX -pthread "${objs[@]}" "$objdir/flatten_hw1.o" "$objdir/main_hw1_b200.o" -L"$repo/ceng795_b200" -lb200rt \
+    -Wl,-rpath,'$ORIGIN/../../ceng795_b200' -o "$OUT/hw1_b200_raytracer"
+  echo "built $OUT/hw1_b200_raytracer"
+}
 build_b200_main_ppm() { # the same drop-in for the PPM tree
   local dir="$REF/PPM" objdir="$OUT/obj_ppm" repo; repo="$(dirname "$HERE")"
   [ -d "$objdir" ] || build_tree ppm "$dir" -DNDEBUG
@@ -197,6 +217,7 @@ for t in "${TREES[@]}"; do
     hw4f) build_tree_driver hw4f "$REF/HW4" ;;   # they pin the oracle at float level (tests/test_oracle_golden.py)
     hw7f) build_tree_driver hw7f "$REF/HW7" ;;
     probe) build_probe ;;
+    flat1) build_hw1_binding ;;
     flat3) build_flatten3 ;;
     flat7) build_flatten7 ;;
     flatppm) build_flatten_ppm ;;

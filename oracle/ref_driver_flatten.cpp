@@ -17,6 +17,12 @@
 #define b200rt_flat_hw3_desc b200rt_flat_hw7_desc
 #define b200rt_flat_hw3_free b200rt_flat_hw7_free
 #endif
+#ifdef FLATTEN_HW1   // ... integration/flatten_hw1.cpp and the HW1 tree's objects (target flat1)
+#define b200rt_flat_hw3 b200rt_flat_hw1
+#define b200rt_flatten_hw3 b200rt_flatten_hw1
+#define b200rt_flat_hw3_desc b200rt_flat_hw1_desc
+#define b200rt_flat_hw3_free b200rt_flat_hw1_free
+#endif
 #ifdef FLATTEN_PPM   // ... and against integration/flatten_ppm.cpp and the PPM tree's objects (target flatppm)
 #define b200rt_flat_hw3 b200rt_flat_ppm
 #define b200rt_flatten_hw3 b200rt_flatten_ppm

@@ -241,3 +241,40 @@ def test_flatten_equals_builder_on_twenty_more_random_scenes(tmp_path):
             ref = scene.CachedHostScene(_flatten(xml, d, exe))
             own = scene.HostScene(scene.parse_xml(xml, tree))
             _assert_same_description(ref, own)
+
+
+FLATTEN1 = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "flat1_flatten")
+
+
+@pytest.mark.skipif(not os.path.exists(FLATTEN1), reason="oracle/_ref/flat1_flatten not built on this box")
+@pytest.mark.parametrize("case", ["cfg1", "near_ties", "fuzz_open"])
+def test_flattened_hw1_scene_equals_builder(tmp_path, case):
+    """integration/flatten_hw1.cpp on the HW1 tree's objects (cfg1's dialect: no BVH, no transforms; the scan order
+    meshes -> triangles -> spheres that HW1's order-dependent hit rule depends on).  Every array byte for byte,
+    including the object structs (nothing is renumbered here); the only difference is su / sv of the camera, which
+    the builder fills for uniformity and HW1's Camera does not have (the device does not read them for this tree)."""
+    xml = {"cfg1": lambda: scenes.cfg1_hw1(width=96, height=96),
+           "near_ties": lambda: scenes.hw1_near_ties(),
+           "fuzz_open": lambda: scenes.fuzz_scene(1, camera_sphere_radius=40.0)}[case]()
+    ref = scene.CachedHostScene(_flatten(xml, tmp_path, FLATTEN1))
+    own = scene.HostScene(scene.parse_xml(xml, "hw1"))
+    a, b = _arrays(ref.desc), _arrays(own.desc)
+    for k in a:
+        if k == "cameras":
+            x, y = (np.frombuffer(v, np.uint32).reshape(-1, C.sizeof(_lib.Camera) // 4).copy() for v in (a[k], b[k]))
+            o = _lib.Camera.su.offset // 4
+            assert not x[:, o:o + 6].any()
+            x[:, o:o + 6] = y[:, o:o + 6] = 0
+            assert np.array_equal(x, y)
+        else:
+            assert a[k] == b[k], k
+    for f in ("semantics", "max_depth", "shadow_eps", "isect_eps", "root", "n_tris", "n_nodes", "n_meshes", "n_spheres",
+              "n_instances", "n_triprims", "n_lights"):
+        assert getattr(ref.desc, f) == getattr(own.desc, f), f
+    for f in ("background", "ambient", "root_box"):
+        assert list(getattr(ref.desc, f)) == list(getattr(own.desc, f)), f
+    # and the oracle sees the same scene: ids, t and image bits
+    img_r, ids_r, t_r, _ = cpu.render(ref, 0, want_ids=True)
+    img_o, ids_o, t_o, _ = cpu.render(own, 0, want_ids=True)
+    assert np.array_equal(ids_r, ids_o) and np.array_equal(t_r.view(np.uint32), t_o.view(np.uint32))
+    assert np.array_equal(img_r.view(np.uint32), img_o.view(np.uint32))

@@ -126,3 +126,34 @@ def test_ppm_dropin_binary_matches_the_reference_statistically(gpu, tmp_path):
     rmse = np.sqrt(((got - want) ** 2).mean())
     assert rmse <= 1.35 * 9.1 + 0.5, rmse
     assert " photons, " in r.stdout and "kernel launches" in r.stdout
+
+
+BINARY1 = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "hw1_b200_raytracer")
+needs_binary1 = pytest.mark.skipif(not os.path.exists(BINARY1), reason="oracle/_ref/hw1_b200_raytracer not built")
+
+
+@needs_binary1
+def test_hw1_dropin_binary_refuses_to_render_without_a_device(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    _, xml = scene_xml("cfg1_hw1_depth0")
+    r = _run(xml, tmp_path, BINARY1)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr and "Scene is parsed" in r.stdout
+
+
+@needs_binary1
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg1_hw1_96", "cfg1_hw1_depth0", "hw1_near_ties"])
+def test_hw1_dropin_binary_writes_the_reference_picture(gpu, tmp_path, name):
+    """cfg1's tree: HW1's host with the fan-out replaced (integration/main_hw1_b200.cpp + flatten_hw1.cpp), including the
+    near-tie scene where HW1's `t < best - 1e-6` makes the order of the primitive list decide the pixel."""
+    _, xml = scene_xml(name)
+    r = _run(xml, tmp_path, BINARY1)
+    assert r.returncode == 0, r.stderr
+    pngs = [f for f in os.listdir(tmp_path) if f.endswith(".png")]
+    assert len(pngs) == 1
+    got = image.read_png(str(tmp_path / pngs[0]))[..., :3]
+    want = image.read_png(os.path.join(HERE, "golden", name + ".png"))[..., :3]
+    cmp = image.compare_8bit(got, want)
+    assert cmp["within1"] >= 0.999 and cmp["max"] <= 2, cmp
