@@ -13,9 +13,25 @@
 #include <map>
 #include <vector>
 
+// The HW5 and HW6 trees are earlier states of the same classes: -DB200RT_TREE=6 leaves out what HW7 added (the
+// integrator switch, Spherical_directional_light, Light_mesh, Light_sphere), -DB200RT_TREE=5 also the BRDF objects.
+#ifndef B200RT_TREE
+#define B200RT_TREE 7
+#endif
 #include "Scene.h"      // the reference's (HW7/include)
+#if B200RT_TREE >= 7
 #include "Light_mesh.h"
 #include "Light_sphere.h"
+#define TRI_I0(t) (t)->vertex_index_0
+#define TRI_I1(t) (t)->vertex_index_1
+#define TRI_I2(t) (t)->vertex_index_2
+#define TRI_OFFSET(t) (t)->vertex_offset
+#else   // HW7 renamed these members
+#define TRI_I0(t) (t)->index_0
+#define TRI_I1(t) (t)->index_1
+#define TRI_I2(t) (t)->index_2
+#define TRI_OFFSET(t) (t)->offset
+#endif
 #include "b200rt.h"     // this repo's include/
 
 namespace {
@@ -64,8 +80,7 @@ struct b200rt_flat_hw7 {
   // forms the same two differences per ray, HW7/src/Mesh_triangle.cpp:33-40), its vertex ids and its gate box.
   uint32_t add_tri(const Mesh_triangle* t, const Bounding_box& gate) {
     const uint32_t id = (uint32_t)tri_tex.size();
-    const int i0 = t->vertex_index_0 + t->vertex_offset, i1 = t->vertex_index_1 + t->vertex_offset,
-              i2 = t->vertex_index_2 + t->vertex_offset;
+    const int i0 = TRI_I0(t) + TRI_OFFSET(t), i1 = TRI_I1(t) + TRI_OFFSET(t), i2 = TRI_I2(t) + TRI_OFFSET(t);
     const Vector3& v0 = scene->get_vertex_at(i0).get_vertex_position();
     const Vector3& v1 = scene->get_vertex_at(i1).get_vertex_position();
     const Vector3& v2 = scene->get_vertex_at(i2).get_vertex_position();
@@ -82,7 +97,7 @@ struct b200rt_flat_hw7 {
     // no texture or the index falls outside the array: the device never reads them then)
     float uv[6] = {0, 0, 0, 0, 0, 0};
     const int ntc = (int)scene->texture_coord_data.size();
-    const int vi[3] = {t->vertex_index_0, t->vertex_index_1, t->vertex_index_2};
+    const int vi[3] = {TRI_I0(t), TRI_I1(t), TRI_I2(t)};
     if (t->texture_id >= 0)
       for (int c = 0; c < 3; c++) {
         const int ti = vi[c] + t->texture_offset;
@@ -141,12 +156,15 @@ struct b200rt_flat_hw7 {
     fi.material = mi->material_id;
     fi.texture = mi->texture_id;
     if (mi->velocity != Vector3(0.0f)) fi.flags |= B200RT_INST_MOVING;   // HW7/include/Mesh.h:66,95
+#if B200RT_TREE >= 7
     if (mi->is_refractive_) fi.flags |= B200RT_INST_REFRACTIVE;          // culling off inside glass: HW7/include/Mesh.h:73-75
+#endif
     fi.rank = rank++;
     fi.light = -1;
     instances.push_back(fi);
     return B200RT_REF(B200RT_KIND_INSTANCE, instances.size() - 1);
   }
+#if B200RT_TREE >= 7
   // Light_mesh sits in Scene::bvh itself: entered without a gate of its own, its box is the object-space mesh box,
   // rays go through base_transform (HW7/include/Light_mesh.h:52-68).
   uint32_t add_light_mesh(const Light_mesh* lm) {
@@ -164,6 +182,7 @@ struct b200rt_flat_hw7 {
     instances.push_back(fi);
     return B200RT_REF(B200RT_KIND_LIGHTINST, instances.size() - 1);
   }
+#endif
   uint32_t add_sphere(const Sphere* sp) {
     b200rt_sphere fs;
     std::memset(&fs, 0, sizeof(fs));
@@ -177,11 +196,13 @@ struct b200rt_flat_hw7 {
     if (sp->velocity != Vector3(0.0f)) fs.flags |= B200RT_XF_MOVING;    // HW7/include/Sphere.h:43,75,113
     fs.rank = rank++;
     fs.light = -1;
+#if B200RT_TREE >= 7
     if (const Light_sphere* ls = dynamic_cast<const Light_sphere*>(sp)) {   // HW7/include/Light_sphere.h:16-24
       fs.flags |= B200RT_XF_LIGHT;
       fs.light = light_index.at(static_cast<const Light*>(ls));
       lights[fs.light].object = (int32_t)spheres.size();
     }
+#endif
     spheres.push_back(fs);
     return B200RT_REF(B200RT_KIND_SPHERE, spheres.size() - 1);
   }
@@ -216,7 +237,9 @@ struct b200rt_flat_hw7 {
       return B200RT_REF(B200RT_KIND_INNER, me);
     }
     if (const Mesh_instance* mi = dynamic_cast<const Mesh_instance*>(s)) return add_instance(mi);
+#if B200RT_TREE >= 7
     if (const Light_mesh* lm = dynamic_cast<const Light_mesh*>(s)) return add_light_mesh(lm);
+#endif
     if (const Sphere* sp = dynamic_cast<const Sphere*>(s)) return add_sphere(sp);
     if (const Triangle* t = dynamic_cast<const Triangle*>(s)) return add_triprim(t);
     return B200RT_REF_NONE;
@@ -229,7 +252,7 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
   f->rank = 0;
   B200SceneDesc& d = f->desc;
   std::memset(&d, 0, sizeof(d));
-  d.semantics = B200RT_SEM_HW7;
+  d.semantics = B200RT_TREE;                    // B200RT_SEM_HW5 / HW6 / HW7 are 5 / 6 / 7
   d.max_depth = scene.max_recursion_depth;
   put3(d.background, scene.background_color);
   put3(d.ambient, scene.ambient_light);
@@ -237,8 +260,10 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
   d.isect_eps = intersection_test_epsilon;      // HW7/include/Vector3.h:10
   d.background_texture = -1;
   d.env_light = -1;
+#if B200RT_TREE >= 7
   d.integrator = scene.integrator_type == it_pathtracing ? 1 : 0;          // HW7/src/Scene.cpp:1573-1582
   d.importance_sampling = (scene.integrator_type == it_pathtracing && !scene.is_uniform_sampling) ? 1 : 0;
+#endif
 
   for (const Vertex& v : scene.vertex_data) {   // normals are final: Scene::Scene ends with finalize_normal (HW7/src/Scene.cpp:872-877)
     float p[3], n[3];
@@ -255,7 +280,11 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
     fm.roughness = m.roughness;
     fm.refraction_index = m.refraction_index;
     fm.phong_exponent = m.phong_exponent;
+#if B200RT_TREE >= 6
     fm.brdf = m.brdf_id;
+#else
+    fm.brdf = -1;
+#endif
     f->materials.push_back(fm);
   }
   // Texture objects: Scene::textures in order, then the background texture, then the environment map (the order the
@@ -281,13 +310,18 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
       ft.appearance = t.appearance_ == Texture::a_repeat ? B200RT_TEX_REPEAT : B200RT_TEX_CLAMP;
       ft.width = t.width_;
       ft.height = t.height_;
+#if B200RT_TREE >= 7
       f->texels.insert(f->texels.end(), t.texture_image_.begin(), t.texture_image_.end());   // after degamma
+#else   // HW5 / HW6 keep stb_image's bytes and convert per lookup (HW6/src/Texture.cpp:72-74): the same values as floats
+      for (size_t k = 0; k < (size_t)t.width_ * t.height_ * 3; k++) f->texels.push_back((float)t.texture_image_[k]);
+#endif
     }
     f->textures.push_back(ft);
     return (int32_t)f->textures.size() - 1;
   };
   for (const Texture& t : scene.textures) add_texture(t);
   if (scene.background_texture) d.background_texture = add_texture(*scene.background_texture);
+#if B200RT_TREE >= 6
   for (const BRDF* r : scene.brdfs) {
     b200rt_brdf fb;
     std::memset(&fb, 0, sizeof(fb));
@@ -306,6 +340,7 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
     }
     f->brdfs.push_back(fb);
   }
+#endif
   // Scene::lights, in the order calculate_diffuse_and_specular_radiance loops them (HW7/src/Scene.cpp:230-262)
   for (const Light* l : scene.lights) {
     b200rt_light fl;
@@ -325,6 +360,7 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
     } else if (const Directional_light* x = dynamic_cast<const Directional_light*>(l)) {
       fl.kind = B200RT_LIGHT_DIRECTIONAL;
       put3(fl.edge1, x->direction_); put3(fl.intensity, x->radiance_);
+#if B200RT_TREE >= 7
     } else if (const Spherical_directional_light* x = dynamic_cast<const Spherical_directional_light*>(l)) {
       fl.kind = B200RT_LIGHT_ENV;                            // the map rides along as one more image texture
       b200rt_texture ft;
@@ -345,6 +381,7 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
     } else if (const Light_sphere* x = dynamic_cast<const Light_sphere*>(l)) {
       fl.kind = B200RT_LIGHT_SPHERE;
       put3(fl.intensity, x->radiance_);
+#endif
     }
     f->light_index[l] = (int)f->lights.size();
     f->lights.push_back(fl);
@@ -362,6 +399,7 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
     f->cameras.push_back(fc);
   }
   for (const Mesh* m : scene.meshes) f->add_mesh(m);
+#if B200RT_TREE >= 7
   for (const Light* l : scene.lights)                        // a Light_mesh IS a Mesh, kept only in lights / the BVH
     if (const Light_mesh* lm = dynamic_cast<const Light_mesh*>(l)) {
       f->add_mesh(static_cast<const Mesh*>(lm));
@@ -373,6 +411,7 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
         f->light_tri.push_back((int32_t)f->tri_index.at(lm->triangles_[k]));
       }
     }
+#endif
   if (scene.bvh) {
     d.root = f->walk_top(scene.bvh);
     put_box(d.root_box, d.root_box + 3, scene.bvh->get_bounding_box());

@@ -5,7 +5,7 @@
 # forced standard includes and a case shim for HW1.
 # HW5/HW6: their main.cpp needs OpenCV (absent), so every OTHER translation unit of the tree is linked with
 # oracle/ref_driver_hdr.cpp, which calls the same Scene seam and dumps the float pixels.
-# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat1, flat3, flat7, flatppm, b200main3, b200main7, b200mainppm)
+# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat1, flat3, flat5, flat6, flat7, flatppm, b200main3, b200main7, b200mainppm)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${CENG795_REFERENCE:-/root/reference}"
@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat1 flat3 flat7 flatppm b200main3 b200main7 b200mainppm)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat1 flat3 flat5 flat6 flat7 flatppm b200main3 b200main7 b200mainppm)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -109,19 +109,23 @@ build_flatten3() { # HW3's objects except main.cpp + integration/flatten_hw3.cpp
   $CXX -pthread "${objs[@]}" "$objdir/flatten_hw3.o" "$objdir/ref_driver_flatten.o" "$objdir/scene_cache.o" -o "$OUT/flat3_flatten"
   echo "built $OUT/flat3_flatten"
 }
-build_flatten7() { # HW7's objects except main.cpp + integration/flatten_hw7.cpp + the same driver
-  local dir="$REF/HW7" objdir="$OUT/obj_hw7" repo; repo="$(dirname "$HERE")"
-  [ -d "$objdir" ] || build_tree hw7 "$dir"
+build_flatten567() { # n : HW<n>'s objects except main.cpp + integration/flatten_hw7.cpp (-DB200RT_TREE=n) + the same driver
+  local n=$1 repo; repo="$(dirname "$HERE")"
+  local dir="$REF/HW$n" objdir="$OUT/obj_hw$n"
+  if [ ! -d "$objdir" ]; then
+    if [ "$n" = 7 ]; then build_tree hw7 "$dir"; else build_tree_driver "hw$n" "$dir"; fi   # HW5 / HW6: main.cpp needs OpenCV
+  fi
   local objs=()
   for f in "$dir"/src/*.cpp; do
     [ "$(basename "$f")" = "main.cpp" ] && continue
     objs+=("$objdir/$(basename "$f" .cpp).o")
   done
-  $CXX $FLAGS -fno-access-control -I"$dir/include" -I"$repo/include" -c "$repo/integration/flatten_hw7.cpp" -o "$objdir/flatten_hw7.o"
-  $CXX $FLAGS -DFLATTEN_HW7 -I"$dir/include" -I"$repo/include" -c "$HERE/ref_driver_flatten.cpp" -o "$objdir/ref_driver_flatten.o"
-  $CXX -std=c++17 -O2 -c "$repo/ceng795_b200/csrc/scene_cache.cpp" -o "$objdir/scene_cache.o"
-  $CXX -pthread "${objs[@]}" "$objdir/flatten_hw7.o" "$objdir/ref_driver_flatten.o" "$objdir/scene_cache.o" -o "$OUT/flat7_flatten"
-  echo "built $OUT/flat7_flatten"
+  local fo="$objdir/flat_"
+  $CXX $FLAGS -fno-access-control -DB200RT_TREE=$n -I"$dir/include" -I"$repo/include" -c "$repo/integration/flatten_hw7.cpp" -o "${fo}flatten.o"
+  $CXX $FLAGS -DFLATTEN_HW7 -I"$dir/include" -I"$repo/include" -c "$HERE/ref_driver_flatten.cpp" -o "${fo}driver.o"
+  $CXX -std=c++17 -O2 -c "$repo/ceng795_b200/csrc/scene_cache.cpp" -o "${fo}scene_cache.o"
+  $CXX -pthread "${objs[@]}" "${fo}flatten.o" "${fo}driver.o" "${fo}scene_cache.o" -o "$OUT/flat${n}_flatten"
+  echo "built $OUT/flat${n}_flatten"
 }
 build_flatten_ppm() { # PPM's objects except main.cpp + integration/flatten_ppm.cpp + the same driver
   local dir="$REF/PPM" objdir="$OUT/obj_ppm" repo; repo="$(dirname "$HERE")"
@@ -219,7 +223,9 @@ for t in "${TREES[@]}"; do
     probe) build_probe ;;
     flat1) build_hw1_binding ;;
     flat3) build_flatten3 ;;
-    flat7) build_flatten7 ;;
+    flat5) build_flatten567 5 ;;
+    flat6) build_flatten567 6 ;;
+    flat7) build_flatten567 7 ;;
     flatppm) build_flatten_ppm ;;
     b200main3) build_b200_main3 ;;
     b200main7) build_b200_main7 ;;

@@ -278,3 +278,24 @@ def test_flattened_hw1_scene_equals_builder(tmp_path, case):
     img_o, ids_o, t_o, _ = cpu.render(own, 0, want_ids=True)
     assert np.array_equal(ids_r, ids_o) and np.array_equal(t_r.view(np.uint32), t_o.view(np.uint32))
     assert np.array_equal(img_r.view(np.uint32), img_o.view(np.uint32))
+
+
+@pytest.mark.parametrize("tree", ["hw5", "hw6"])
+@pytest.mark.parametrize("case", ["textured", "perlin", "fuzz_open", "fuzz_stochastic"])
+def test_flattened_hw5_hw6_scene_equals_builder(tmp_path, tree, case):
+    """The same flatten source compiled against the HW5 and HW6 trees (-DB200RT_TREE=5 / 6: earlier states of HW7's
+    classes — bytes instead of floats in `Texture`, no BRDF objects in HW5, no environment / mesh / sphere lights) on
+    the scenes whose loaders differ from HW7's: HW5 / HW6 keep only the FIRST spot and the first directional light,
+    convert `degamma` materials with a double pow, and ignore what they do not know."""
+    exe = os.path.join(os.path.dirname(HERE), "oracle", "_ref", f"flat{tree[-1]}_flatten")
+    if not os.path.exists(exe):
+        pytest.skip(f"oracle/_ref/flat{tree[-1]}_flatten not built on this box")
+    d = str(tmp_path)
+    xml = {"textured": lambda: scenes.hw7_scene(d, width=64, height=48, light_scale=3.0),
+           "perlin": lambda: scenes.hw7_scene(d, width=48, height=36, n=6, depth=2, perlin=True, mesh_slices=(6, 7)),
+           "fuzz_open": lambda: scenes.fuzz_scene(2, camera_sphere_radius=40.0),
+           "fuzz_stochastic": lambda: scenes.fuzz_scene(1, spp=9, stochastic=True, camera_sphere_radius=40.0)}[case]()
+    ref = scene.CachedHostScene(_flatten(xml, tmp_path, exe))
+    own = scene.HostScene(scene.parse_xml(xml, tree, base_dir=d))
+    assert ref.desc.semantics == own.desc.semantics == int(tree[-1])
+    _assert_same_description(ref, own)
