@@ -13,8 +13,9 @@
 #include <map>
 #include <vector>
 
-// The HW5 and HW6 trees are earlier states of the same classes: -DB200RT_TREE=6 leaves out what HW7 added (the
-// integrator switch, Spherical_directional_light, Light_mesh, Light_sphere), -DB200RT_TREE=5 also the BRDF objects.
+// The HW4, HW5 and HW6 trees are earlier states of the same classes: -DB200RT_TREE=6 leaves out what HW7 added (the
+// integrator switch, Spherical_directional_light, Light_mesh, Light_sphere), -DB200RT_TREE=5 also the BRDF objects,
+// -DB200RT_TREE=4 also the Light hierarchy (HW4 keeps HW3's point_lights / area_lights vectors).
 #ifndef B200RT_TREE
 #define B200RT_TREE 7
 #endif
@@ -72,7 +73,9 @@ struct b200rt_flat_hw7 {
   std::vector<int32_t> light_tri;
   std::map<const Mesh*, int> mesh_index;
   std::map<const Shape*, uint32_t> tri_index;     // Mesh_triangle -> its depth-first id (Light_mesh::triangles_)
+#if B200RT_TREE >= 5
   std::map<const Light*, int> light_index;
+#endif
   const Scene* scene;
   int rank;
 
@@ -341,6 +344,7 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
     f->brdfs.push_back(fb);
   }
 #endif
+#if B200RT_TREE >= 5
   // Scene::lights, in the order calculate_diffuse_and_specular_radiance loops them (HW7/src/Scene.cpp:230-262)
   for (const Light* l : scene.lights) {
     b200rt_light fl;
@@ -386,6 +390,25 @@ extern "C" b200rt_flat_hw7* b200rt_flatten_hw7(const Scene& scene) {
     f->light_index[l] = (int)f->lights.size();
     f->lights.push_back(fl);
   }
+#else   // HW4 still has HW3's two plain vectors; Scene::trace_ray loops the point lights, then the area lights
+  for (const Point_light& l : scene.point_lights) {
+    b200rt_light fl;
+    std::memset(&fl, 0, sizeof(fl));
+    fl.kind = B200RT_LIGHT_POINT;
+    put3(fl.position, l.position); put3(fl.intensity, l.intensity);
+    fl.object = -1;
+    f->lights.push_back(fl);
+  }
+  for (const Area_light& l : scene.area_lights) {
+    b200rt_light fl;
+    std::memset(&fl, 0, sizeof(fl));
+    fl.kind = B200RT_LIGHT_AREA;
+    put3(fl.position, l.position); put3(fl.intensity, l.intensity);
+    put3(fl.edge1, l.edge_vector_1); put3(fl.edge2, l.edge_vector_2); put3(fl.normal, l.normal);
+    fl.object = -1;
+    f->lights.push_back(fl);
+  }
+#endif
   for (const Camera& c : scene.cameras) {
     b200rt_camera fc;
     std::memset(&fc, 0, sizeof(fc));

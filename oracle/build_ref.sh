@@ -5,7 +5,7 @@
 # forced standard includes and a case shim for HW1.
 # HW5/HW6: their main.cpp needs OpenCV (absent), so every OTHER translation unit of the tree is linked with
 # oracle/ref_driver_hdr.cpp, which calls the same Scene seam and dumps the float pixels.
-# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat1, flat3, flat5, flat6, flat7, flatppm, b200main3, b200main7, b200mainppm)
+# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat1, flat3, flat4, flat5, flat6, flat7, flatppm, b200main3, b200main7, b200mainppm)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${CENG795_REFERENCE:-/root/reference}"
@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat1 flat3 flat5 flat6 flat7 flatppm b200main3 b200main7 b200mainppm)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat1 flat3 flat4 flat5 flat6 flat7 flatppm b200main3 b200main7 b200mainppm)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -109,11 +109,11 @@ build_flatten3() { # HW3's objects except main.cpp + integration/flatten_hw3.cpp
   $CXX -pthread "${objs[@]}" "$objdir/flatten_hw3.o" "$objdir/ref_driver_flatten.o" "$objdir/scene_cache.o" -o "$OUT/flat3_flatten"
   echo "built $OUT/flat3_flatten"
 }
-build_flatten567() { # n : HW<n>'s objects except main.cpp + integration/flatten_hw7.cpp (-DB200RT_TREE=n) + the same driver
+build_flatten567() { # n (4..7) : HW<n>'s objects except main.cpp + integration/flatten_hw7.cpp (-DB200RT_TREE=n) + the same driver
   local n=$1 repo; repo="$(dirname "$HERE")"
   local dir="$REF/HW$n" objdir="$OUT/obj_hw$n"
   if [ ! -d "$objdir" ]; then
-    if [ "$n" = 7 ]; then build_tree hw7 "$dir"; else build_tree_driver "hw$n" "$dir"; fi   # HW5 / HW6: main.cpp needs OpenCV
+    if [ "$n" = 7 ] || [ "$n" = 4 ]; then build_tree "hw$n" "$dir"; else build_tree_driver "hw$n" "$dir"; fi   # HW5 / HW6: main.cpp needs OpenCV
   fi
   local objs=()
   for f in "$dir"/src/*.cpp; do
@@ -223,6 +223,7 @@ for t in "${TREES[@]}"; do
     probe) build_probe ;;
     flat1) build_hw1_binding ;;
     flat3) build_flatten3 ;;
+    flat4) build_flatten567 4 ;;
     flat5) build_flatten567 5 ;;
     flat6) build_flatten567 6 ;;
     flat7) build_flatten567 7 ;;

@@ -280,11 +280,12 @@ def test_flattened_hw1_scene_equals_builder(tmp_path, case):
     assert np.array_equal(img_r.view(np.uint32), img_o.view(np.uint32))
 
 
-@pytest.mark.parametrize("tree", ["hw5", "hw6"])
+@pytest.mark.parametrize("tree", ["hw4", "hw5", "hw6"])
 @pytest.mark.parametrize("case", ["textured", "perlin", "fuzz_open", "fuzz_stochastic"])
-def test_flattened_hw5_hw6_scene_equals_builder(tmp_path, tree, case):
-    """The same flatten source compiled against the HW5 and HW6 trees (-DB200RT_TREE=5 / 6: earlier states of HW7's
-    classes — bytes instead of floats in `Texture`, no BRDF objects in HW5, no environment / mesh / sphere lights) on
+def test_flattened_hw4_hw5_hw6_scene_equals_builder(tmp_path, tree, case):
+    """The same flatten source compiled against the HW4, HW5 and HW6 trees (-DB200RT_TREE=4 / 5 / 6: earlier states of
+    HW7's classes — bytes instead of floats in `Texture`, no BRDF objects before HW6, HW3's plain light vectors in HW4,
+    no environment / mesh / sphere lights) on
     the scenes whose loaders differ from HW7's: HW5 / HW6 keep only the FIRST spot and the first directional light,
     convert `degamma` materials with a double pow, and ignore what they do not know."""
     exe = os.path.join(os.path.dirname(HERE), "oracle", "_ref", f"flat{tree[-1]}_flatten")
