@@ -24,7 +24,7 @@ def test_open_fuzz_scenes_match_the_oracle(gpu, tree, seed):
     xml = scenes.fuzz_scene(seed, camera_sphere_radius=40.0)
     sc = scene.Scene(xml, tree)
     o_rgbw, o_ids, o_t, cnt = cpu.render(sc.host, 0, want_ids=True)
-    assert len(np.unique(o_ids[..., 0])) >= 8          # the frame really is full of different objects
+    assert len(np.unique(o_ids[..., 0])) >= 5          # the frame really is full of different objects (HW2 has no instances: 5-6; others 10-21)
     for exact in (0, 1):
         ids, t = sc.primary_ids(0, exact_traversal=exact)
         assert np.array_equal(ids, o_ids), (exact, float(np.mean(np.all(ids == o_ids, -1))))
