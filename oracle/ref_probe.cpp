@@ -13,6 +13,10 @@
 #include "Blinn_phong_BRDF.h"
 #include "Bounding_box.h"
 #include "Hit_data.h"
+#include "Mesh_triangle.h"
+#include "Scene.h"
+#include "Vertex.h"
+#include <new>
 #include "Modified_blinn_phong_BRDF.h"
 #include "Modified_phong_BRDF.h"
 #include "Perlin_noise.h"
@@ -140,6 +144,51 @@ int main(int argc, char** argv) {
       }
       section((std::string("perlin_") + app[a]).c_str(), rows, 3, 1, d);
     }
+  }
+  {  // Mesh_triangle::intersect — HW7/src/Mesh_triangle.cpp:56-100 (the +-eps band on beta / gamma / t, no culling)
+    // The class reads its vertices through Scene::get_vertex_at, i.e. Scene::vertex_data; a Scene cannot be made
+    // without an XML file, so only that one member is brought to life inside raw storage (-fno-access-control).
+    alignas(Scene) static unsigned char scene_storage[sizeof(Scene)];
+    Scene* scene = reinterpret_cast<Scene*>(scene_storage);
+    new (&scene->vertex_data) std::vector<Vertex>();
+    Lcg r(400);
+    std::vector<float> d;
+    const int rows = 6144;
+    for (int k = 0; k < rows; k++) {
+      Vector3 v0(r.range(-2, 2), r.range(-2, 2), r.range(-2, 2)), v1(r.range(-2, 2), r.range(-2, 2), r.range(-2, 2)),
+          v2(r.range(-2, 2), r.range(-2, 2), r.range(-2, 2));
+      if (k % 32 == 7) v2 = v0 + (v1 - v0) * r.range(0.1f, 0.9f);            // zero-area triangle
+      if (k % 32 == 9) { v1 = v0 + Vector3(1e-4f, 0, 0); v2 = v0 + Vector3(0, 1e-4f, 0); }   // tiny
+      Vector3 o(r.range(-5, 5), r.range(-5, 5), r.range(-5, 5));
+      // aim at a point of the triangle's plane: inside, exactly on an edge, exactly on a vertex, just outside, far outside
+      float b = r.u01(), g = r.u01() * (1 - b);
+      switch (k % 8) {
+        case 1: g = 0.0f; break;                       // on the edge v0-v1
+        case 2: b = 0.0f; break;                       // on the edge v0-v2
+        case 3: g = 1.0f - b; break;                   // on the edge v1-v2
+        case 4: b = (k & 8) ? 1.0f : 0.0f; g = (k & 16) ? 0.0f : 1.0f - b; break;   // a vertex
+        case 5: b = -r.u01() * 2e-6f; break;           // inside the acceptance band, or just beyond it
+        case 6: b = r.range(-1.5f, 2.5f); g = r.range(-1.5f, 2.5f); break;
+        default: break;
+      }
+      const Vector3 target = v0 + (v1 - v0) * b + (v2 - v0) * g;
+      Vector3 dir = target - o;
+      if (k % 16 == 11) dir = dir * -1.0f;              // triangle behind the origin: t < 0
+      if (k % 4 != 0) dir = dir.normalize();            // un-normalised directions too (instances hand those down)
+      if (k % 64 == 13) dir = (v1 - v0) * 0.7f + (v2 - v0) * 0.2f;   // parallel to the plane: det = 0 or nearly
+      scene->vertex_data.clear();
+      scene->vertex_data.push_back(Vertex(v0));
+      scene->vertex_data.push_back(Vertex(v1));
+      scene->vertex_data.push_back(Vertex(v2));
+      const Mesh_triangle tri(scene, 0, 1, 2, 0, 0, 0, -1, tsm_flat);
+      Hit_data hd;
+      hd.t = -12345.0f;
+      const bool hit = tri.intersect(Ray(o, dir, r_primary), hd, false);
+      const float row[17] = {v0.x, v0.y, v0.z, v1.x, v1.y, v1.z, v2.x, v2.y, v2.z, o.x, o.y, o.z, dir.x, dir.y, dir.z,
+                             hit ? 1.0f : 0.0f, hit ? hd.t : 0.0f};
+      d.insert(d.end(), row, row + 17);
+    }
+    section("tri7", rows, 15, 2, d);
   }
   std::fclose(g_out);
   return 0;

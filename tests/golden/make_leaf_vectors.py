@@ -1,6 +1,6 @@
 """Regenerates tests/golden/leaf_vectors.bin: known-answer vectors of the reference's own leaf functions
 (Bounding_box::intersect, the five BRDFs, Texture::get_color_at in its four mode combinations, Perlin_noise with a
-fixed table), produced by oracle/_ref/ref_probe = HW7's unmodified objects + oracle/ref_probe.cpp.
+fixed table, Mesh_triangle::intersect), produced by oracle/_ref/ref_probe = HW7's unmodified objects + oracle/ref_probe.cpp.
 
     bash oracle/build_ref.sh probe && python tests/golden/make_leaf_vectors.py
 """

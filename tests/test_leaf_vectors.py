@@ -41,7 +41,7 @@ def _same_bits(got, want):
 
 def test_sections_present():
     assert {"box", "brdf0_e23", "brdf4_e60_r2.1", "tex_nearest_repeat", "tex_bilinear_clamp", "perlin_vein",
-            "perlin_patch"} <= set(SECTIONS)
+            "perlin_patch", "tri7"} <= set(SECTIONS)
     assert sum(len(v[0]) for v in SECTIONS.values()) > 20000
 
 
@@ -181,3 +181,28 @@ def test_device_perlin(gpu, appearance):
     # except for a handful of values one ulp away
     assert np.abs(got - want[:, 0]).max() < 1e-6
     assert np.mean(_same_bits(got, want[:, 0])) > 0.995
+
+
+def test_mesh_triangle_intersect():
+    """Mesh_triangle::intersect (HW7/src/Mesh_triangle.cpp:56-100) on 6144 seeded triangle / ray pairs aimed at the
+    awkward places: exactly on each edge and vertex, inside and just beyond the +-1e-6 acceptance band, zero-area and
+    1e-4-sized triangles, rays parallel to the plane, triangles behind the origin, un-normalised directions.  Same
+    accept / reject decision on every row and the same bits of t on every hit."""
+    L = cpu.load()
+    x, want = SECTIONS["tri7"]
+    x = np.ascontiguousarray(x)
+    hits = np.zeros(len(x), np.int32)
+    t = np.zeros(len(x), np.float32)
+    out = np.zeros(3, np.float32)
+    for k, r in enumerate(x):
+        v0, v1, v2 = r[0:3], r[3:6], r[6:9]
+        g = np.concatenate([v0, v0 - v1, v0 - v2, np.zeros(3, np.float32)]).astype(np.float32)
+        o, d = np.ascontiguousarray(r[9:12]), np.ascontiguousarray(r[12:15])
+        hits[k] = L.oracle_tri_intersect(g.ctypes.data, o.ctypes.data, d.ctypes.data, 7, C.c_float(1e-6), out.ctypes.data)
+        t[k] = out[0] if hits[k] else 0.0
+    w_hit = want[:, 0] > 0.5
+    assert np.array_equal(hits.astype(bool), w_hit), int((hits.astype(bool) != w_hit).sum())
+    assert _same_bits(t[w_hit], want[w_hit, 1]).all()
+    assert 0.2 < w_hit.mean() < 0.8                     # hits and misses are both well represented
+    edge = np.arange(len(x)) % 8 == 1                   # rows aimed exactly at the edge v0-v1: both outcomes occur
+    assert w_hit[edge].any() and (~w_hit[edge]).any()
