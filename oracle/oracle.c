@@ -1866,6 +1866,19 @@ float oracle_box_intersect(const float* mn, const float* mx, const float* o, con
 int oracle_tri_intersect(const float* g12, const float* o, const float* dd, int mode, float eps, float* out3) {
   return tri_core(g12, ld(o), ld(dd), mode, eps, out3, out3 + 1, out3 + 2);
 }
+/* Sphere::intersect on one sphere record: out5 = {t, normal.xyz, 0}.  `semantics` picks the tree's rules. */
+int oracle_sphere_intersect(const b200rt_sphere* s, int semantics, float eps, const float* o, const float* dd, float time,
+                            float* out4) {
+  B200SceneDesc d; memset(&d, 0, sizeof(d));
+  d.semantics = semantics; d.isect_eps = eps; d.spheres = s; d.n_spheres = 1;
+  OracleCounters c; memset(&c, 0, sizeof(c));
+  Ctx cx = {&d, &c};
+  Ray r; memset(&r, 0, sizeof(r)); r.o = ld(o); r.d = ld(dd); r.time = time;
+  Hit h; memset(&h, 0, sizeof(h));
+  if (!sphere_intersect(&cx, 0, &r, &h)) return 0;
+  out4[0] = h.t; out4[1] = h.normal.x; out4[2] = h.normal.y; out4[3] = h.normal.z;
+  return 1;
+}
 /* BRDF::get_reflectance, Texture::get_color_at, Perlin_noise::get_value_at (tests/test_leaf_vectors.py) */
 void oracle_brdf_eval(int kind, float exponent, int normalized, float refractive_index, const float* n, const float* kd,
                       const float* ks, const float* wi, const float* wo, float* out3) {

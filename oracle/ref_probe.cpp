@@ -15,6 +15,8 @@
 #include "Hit_data.h"
 #include "Mesh_triangle.h"
 #include "Scene.h"
+#include "Sphere.h"
+#include "Transformation.h"
 #include "Vertex.h"
 #include <new>
 #include "Modified_blinn_phong_BRDF.h"
@@ -189,6 +191,47 @@ int main(int argc, char** argv) {
       d.insert(d.end(), row, row + 17);
     }
     section("tri7", rows, 15, 2, d);
+  }
+  {  // Sphere::intersect — HW7/src/Sphere.cpp:32-110: per-ray Translation(time * velocity) * M, inverse, quadratic, the
+     // t2 < 0 -> t1 rule, normal through the normal matrix.  M is composed by the tree's own Scaling / Rotation /
+     // Translation classes and handed to the test as 16 floats.
+    Lcg r(500);
+    std::vector<float> d;
+    const int rows = 4096;
+    for (int k = 0; k < rows; k++) {
+      Matrix4x4 M(true);
+      if (k % 4 != 0) {
+        const Scaling S(r.range(0.3f, 2.0f) * ((k % 8 == 5) ? -1.0f : 1.0f), r.range(0.3f, 2.0f), r.range(0.3f, 2.0f));
+        const Rotation R(r.range(0, 360), r.range(-1, 1), r.range(-1, 1), r.range(-1, 1));
+        const Translation T(r.range(-2, 2), r.range(-2, 2), r.range(-2, 2));
+        M = T.get_transformation_matrix() * (R.get_transformation_matrix() * S.get_transformation_matrix());
+      }
+      const Vector3 center(r.range(-1, 1), r.range(-1, 1), r.range(-1, 1));
+      const float radius = r.range(0.2f, 1.5f);
+      const Vector3 velocity = (k % 4 == 3) ? Vector3(r.range(-0.5f, 0.5f), r.range(-0.5f, 0.5f), r.range(-0.5f, 0.5f)) : Vector3(0.0f);
+      const float time = (k % 4 == 3) ? r.u01() : 0.0f;
+      const Arbitrary_transformation xf(M);
+      const Sphere sphere(nullptr, center, radius, 0, -1, xf, velocity);
+      Vector3 o(r.range(-6, 6), r.range(-6, 6), r.range(-6, 6));
+      const Vector3 world_c = M.multiply(center);
+      if (k % 8 == 2) o = world_c + Vector3(r.range(-0.1f, 0.1f), r.range(-0.1f, 0.1f), r.range(-0.1f, 0.1f));   // origin inside: t2 < 0 -> t1
+      Vector3 aim = world_c + Vector3(r.range(-1, 1), r.range(-1, 1), r.range(-1, 1)) * (radius * ((k % 16 == 9) ? 2.5f : 0.9f));
+      Vector3 dir = aim - o;
+      if (k % 16 == 6) dir = dir * -1.0f;                 // sphere behind the origin: negative t is still returned
+      if (k % 2) dir = dir.normalize();
+      Hit_data hd;
+      hd.t = -12345.0f;
+      const bool hit = sphere.intersect(Ray(o, dir, r_primary, time), hd, false);
+      float row[35];
+      for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) row[4 * i + j] = M[i][j];
+      const float rest[14] = {center.x, center.y, center.z, radius, velocity.x, velocity.y, velocity.z, o.x, o.y, o.z,
+                              dir.x, dir.y, dir.z, time};
+      for (int i = 0; i < 14; i++) row[16 + i] = rest[i];
+      row[30] = hit ? 1.0f : 0.0f; row[31] = hit ? hd.t : 0.0f;
+      row[32] = hit ? hd.normal.x : 0.0f; row[33] = hit ? hd.normal.y : 0.0f; row[34] = hit ? hd.normal.z : 0.0f;
+      d.insert(d.end(), row, row + 35);
+    }
+    section("sphere7", rows, 30, 5, d);
   }
   std::fclose(g_out);
   return 0;

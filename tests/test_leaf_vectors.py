@@ -41,7 +41,7 @@ def _same_bits(got, want):
 
 def test_sections_present():
     assert {"box", "brdf0_e23", "brdf4_e60_r2.1", "tex_nearest_repeat", "tex_bilinear_clamp", "perlin_vein",
-            "perlin_patch", "tri7"} <= set(SECTIONS)
+            "perlin_patch", "tri7", "sphere7"} <= set(SECTIONS)
     assert sum(len(v[0]) for v in SECTIONS.values()) > 20000
 
 
@@ -206,3 +206,40 @@ def test_mesh_triangle_intersect():
     assert 0.2 < w_hit.mean() < 0.8                     # hits and misses are both well represented
     edge = np.arange(len(x)) % 8 == 1                   # rows aimed exactly at the edge v0-v1: both outcomes occur
     assert w_hit[edge].any() and (~w_hit[edge]).any()
+
+
+def test_sphere_intersect():
+    """Sphere::intersect (HW7/src/Sphere.cpp:32-110) on 4096 seeded spheres: identity, Scaling x Rotation x Translation
+    composed by the tree's own classes (mirroring scales included), moving spheres with a per-ray time; origins inside
+    the sphere (t2 < 0 -> t1), spheres behind the origin, rays that miss, un-normalised directions.  The record is
+    built from M the way the builder does (b200rt_xf_invert); decision, t and the world-space normal bit for bit."""
+    L = cpu.load()
+    lib = _lib.load()
+    L.oracle_sphere_intersect.restype = C.c_int
+    L.oracle_sphere_intersect.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    x, want = SECTIONS["sphere7"]
+    x = np.ascontiguousarray(x)
+    bad_hit = bad_t = bad_n = 0
+    out = np.zeros(4, np.float32)
+    inv = np.zeros(16, np.float32)
+    for r, w in zip(x, want):
+        M = np.ascontiguousarray(r[0:16])
+        assert lib.b200rt_xf_invert(_lib.fptr(M), _lib.fptr(inv)) == 0
+        s = _lib.Sphere()
+        s.center = (C.c_float * 3)(*r[16:19]); s.radius = float(r[19])
+        s.inv = (C.c_float * 12)(*inv[:12])
+        s.nrm = (C.c_float * 9)(*inv.reshape(4, 4).T[:3, :3].ravel())
+        s.fwd = (C.c_float * 16)(*M)
+        s.velocity = (C.c_float * 3)(*r[20:23])
+        s.material = 0; s.texture = -1; s.light = -1
+        s.flags = (1 if np.array_equal(M, np.eye(4, dtype=np.float32).ravel()) else 0) | (2 if r[20:23].any() else 0)
+        o, d = np.ascontiguousarray(r[23:26]), np.ascontiguousarray(r[26:29])
+        hit = L.oracle_sphere_intersect(C.addressof(s), 7, 1e-6, o.ctypes.data, d.ctypes.data, float(r[29]), out.ctypes.data)
+        if bool(hit) != (w[0] > 0.5):
+            bad_hit += 1
+        elif hit:
+            bad_t += int(not _same_bits(out[0], w[1]))
+            bad_n += int(not _same_bits(out[1:4], w[2:5]).all())
+    assert (bad_hit, bad_t, bad_n) == (0, 0, 0), (bad_hit, bad_t, bad_n)
+    hits = want[:, 0] > 0.5
+    assert 0.3 < hits.mean() < 0.95 and (want[hits, 1] < 0).any()       # misses, and negative t (sphere behind the origin)
