@@ -10,6 +10,7 @@
 //       -L <repo>/ceng795_b200 -lb200rt -pthread
 // Built here by `oracle/build_ref.sh b200main3` -> oracle/_ref/hw3_b200_raytracer; tests/test_z_dropin_binary.py runs it
 // on the GPU box and compares its PNG with the one the unmodified HW3 binary wrote for the same XML.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <iostream>

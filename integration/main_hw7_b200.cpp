@@ -9,6 +9,7 @@
 //
 // Built by `oracle/build_ref.sh b200main7` -> oracle/_ref/hw7_b200_raytracer (-fno-access-control: the operator's
 // three parameters are private); tests/test_z_dropin_binary.py compares its PNG with the unmodified binary's.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <iostream>

@@ -12,6 +12,7 @@
 // No CPU fallback: without a device the program says why and exits non-zero.
 //
 // Built by `oracle/build_ref.sh b200mainppm` -> oracle/_ref/ppm_b200_raytracer.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
