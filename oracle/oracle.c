@@ -1879,6 +1879,13 @@ int oracle_sphere_intersect(const b200rt_sphere* s, int semantics, float eps, co
   out4[0] = h.t; out4[1] = h.normal.x; out4[2] = h.normal.y; out4[3] = h.normal.z;
   return 1;
 }
+/* Light::incoming_radiance for the kinds that need no texture (point, area, spot, directional, mesh, sphere). */
+void oracle_light_radiance(const b200rt_light* L, const float* to_light, float prob, float* out3) {
+  B200SceneDesc d; memset(&d, 0, sizeof(d));
+  d.semantics = B200RT_SEM_HW7; d.lights = L; d.n_lights = 1;
+  const v3 r = light_radiance(&d, 0, ld(to_light), prob);
+  out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
 /* BRDF::get_reflectance, Texture::get_color_at, Perlin_noise::get_value_at (tests/test_leaf_vectors.py) */
 void oracle_brdf_eval(int kind, float exponent, int normalized, float refractive_index, const float* n, const float* kd,
                       const float* ks, const float* wi, const float* wo, float* out3) {

@@ -14,8 +14,11 @@
 #include "Bounding_box.h"
 #include "Hit_data.h"
 #include "Mesh_triangle.h"
+#include "Area_light.h"
 #include "Scene.h"
 #include "Sphere.h"
+#include "Spot_light.h"
+#include <cmath>
 #include "Transformation.h"
 #include "Vertex.h"
 #include <new>
@@ -232,6 +235,42 @@ int main(int argc, char** argv) {
       d.insert(d.end(), row, row + 35);
     }
     section("sphere7", rows, 30, 5, d);
+  }
+  {  // Light::incoming_radiance — HW7/src/Spot_light.cpp:24-46 (inside the falloff cone, the pow(c, 4) ramp, outside
+     // the coverage cone) and HW7/src/Area_light.cpp (cosine at the light over squared distance)
+    Lcg r(600);
+    std::vector<float> d;
+    const int rows = 3072;
+    for (int k = 0; k < rows; k++) {
+      const Vector3 pos(r.range(-3, 3), r.range(2, 5), r.range(-3, 3)), inten(r.range(100, 3000), r.range(100, 3000), r.range(100, 3000));
+      const float cov = r.range(30, 120) * (float)(M_PI / 180.0), fall = cov * r.range(0.2f, 0.9f);
+      const Spot_light L(pos, inten, Vector3(r.range(-0.4f, 0.4f), -1.0f, r.range(-0.4f, 0.4f)), cov, fall);
+      // a point around the axis: angle from the axis swept over all three zones
+      const float ang = r.range(0.0f, 1.3f) * cov * 0.5f, az = r.range(0, 6.2831853f);
+      const Vector3 ax = L.direction_;
+      const Vector3 t1 = ax.cross(Vector3(0.3f, 0.1f, 0.9f)).normalize(), t2 = ax.cross(t1);
+      const Vector3 w = ax * std::cos(ang) + (t1 * std::cos(az) + t2 * std::sin(az)) * std::sin(ang);
+      const Vector3 from = pos + w * r.range(0.5f, 8.0f);
+      float dist = 0, prob = 0;
+      const Vector3 to_light = L.direction_and_distance(from, Vector3(0, 1, 0), dist, prob);
+      const Vector3 rad = L.incoming_radiance(to_light, prob);
+      const float row[18] = {pos.x, pos.y, pos.z, inten.x, inten.y, inten.z, L.direction_.x, L.direction_.y, L.direction_.z,
+                             L.cos_half_of_coverage_angle_, L.cos_half_of_falloff_angle_, to_light.x, to_light.y, to_light.z,
+                             dist, rad.x, rad.y, rad.z};
+      d.insert(d.end(), row, row + 18);
+    }
+    section("light_spot", rows, 15, 3, d);
+    d.clear();
+    for (int k = 0; k < 2048; k++) {
+      const Vector3 pos(r.range(-3, 3), r.range(2, 5), r.range(-3, 3)), inten(r.range(100, 3000), r.range(100, 3000), r.range(100, 3000));
+      const Area_light L(pos, inten, Vector3(r.range(0.5f, 2), 0, r.range(-0.5f, 0.5f)), Vector3(r.range(-0.5f, 0.5f), 0, r.range(0.5f, 2)));
+      const Vector3 to_light(r.range(-4, 4), r.range(-4, 4), r.range(-4, 4));
+      const Vector3 rad = L.incoming_radiance(to_light, 1.0f);
+      const float row[12] = {inten.x, inten.y, inten.z, L.normal_.x, L.normal_.y, L.normal_.z, to_light.x, to_light.y, to_light.z,
+                             rad.x, rad.y, rad.z};
+      d.insert(d.end(), row, row + 12);
+    }
+    section("light_area", 2048, 9, 3, d);
   }
   std::fclose(g_out);
   return 0;

@@ -41,7 +41,7 @@ def _same_bits(got, want):
 
 def test_sections_present():
     assert {"box", "brdf0_e23", "brdf4_e60_r2.1", "tex_nearest_repeat", "tex_bilinear_clamp", "perlin_vein",
-            "perlin_patch", "tri7", "sphere7"} <= set(SECTIONS)
+            "perlin_patch", "tri7", "sphere7", "light_spot", "light_area"} <= set(SECTIONS)
     assert sum(len(v[0]) for v in SECTIONS.values()) > 20000
 
 
@@ -243,3 +243,33 @@ def test_sphere_intersect():
     assert (bad_hit, bad_t, bad_n) == (0, 0, 0), (bad_hit, bad_t, bad_n)
     hits = want[:, 0] > 0.5
     assert 0.3 < hits.mean() < 0.95 and (want[hits, 1] < 0).any()       # misses, and negative t (sphere behind the origin)
+
+
+def test_light_incoming_radiance():
+    """Spot_light::incoming_radiance in its three zones (full intensity inside the falloff cone, the pow(c, 4) ramp,
+    zero outside the coverage cone; HW7/src/Spot_light.cpp:24-46) on the vector direction_and_distance returned, and
+    Area_light::incoming_radiance (cosine at the light over the squared distance) — same bits."""
+    L = cpu.load()
+    L.oracle_light_radiance.restype = None
+    L.oracle_light_radiance.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    out = np.zeros(3, np.float32)
+    x, want = SECTIONS["light_spot"]
+    zones = [0, 0, 0]
+    for r, w in zip(np.ascontiguousarray(x), want):
+        l = _lib.Light()
+        l.kind = _lib.LIGHT_SPOT
+        l.position = (C.c_float * 3)(*r[0:3]); l.intensity = (C.c_float * 3)(*r[3:6]); l.edge1 = (C.c_float * 3)(*r[6:9])
+        l.edge2 = (C.c_float * 3)(float(r[9]), float(r[10]), 0.0)
+        to_light = np.ascontiguousarray(r[11:14])
+        L.oracle_light_radiance(C.addressof(l), to_light.ctypes.data, 0.0, out.ctypes.data)
+        assert _same_bits(out, w).all(), (out, w)
+        zones[0 if not w.any() else (1 if np.allclose(w, r[3:6] / np.dot(to_light, to_light), rtol=1e-5) else 2)] += 1
+    assert min(zones) > 200, zones          # outside / full / ramp are all well represented
+    x, want = SECTIONS["light_area"]
+    for r, w in zip(np.ascontiguousarray(x), want):
+        l = _lib.Light()
+        l.kind = _lib.LIGHT_AREA
+        l.intensity = (C.c_float * 3)(*r[0:3]); l.normal = (C.c_float * 3)(*r[3:6])
+        to_light = np.ascontiguousarray(r[6:9])
+        L.oracle_light_radiance(C.addressof(l), to_light.ctypes.data, 1.0, out.ctypes.data)
+        assert _same_bits(out, w).all(), (out, w)
