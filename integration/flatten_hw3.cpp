@@ -63,7 +63,7 @@ struct b200rt_flat_hw3 {
   int rank;
 
   // One mesh triangle, in the order the walk meets it: v0, v0-v1, v0-v2, the stored normal (Mesh_triangle::intersect
-  // forms the same two differences per ray, HW3/src/Mesh_triangle.cpp:44-52), its vertex ids and its gate box.
+  // forms the same two differences per ray, HW3/src/Mesh_triangle.cpp:77-86), its vertex ids and its gate box.
   uint32_t add_tri(const Mesh_triangle* t, const Bounding_box& gate) {
     const uint32_t id = (uint32_t)tri_tex.size();
     const int i0 = t->index_0 + t->offset, i1 = t->index_1 + t->offset, i2 = t->index_2 + t->offset;
@@ -200,7 +200,7 @@ extern "C" b200rt_flat_hw3* b200rt_flatten_hw3(const Scene& scene) {
   put3(d.background, scene.background_color);
   put3(d.ambient, scene.ambient_light);
   d.shadow_eps = scene.shadow_ray_epsilon;
-  d.isect_eps = kEpsilon;                       // HW3/include/Ray.h
+  d.isect_eps = kEpsilon;                       // HW3/include/Vector3.h:6
   d.background_texture = -1;
   d.env_light = -1;
 

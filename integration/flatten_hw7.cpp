@@ -80,7 +80,7 @@ struct b200rt_flat_hw7 {
   int rank;
 
   // One mesh triangle, in the order the walk meets it: v0, v0-v1, v0-v2, the stored normal (Mesh_triangle::intersect
-  // forms the same two differences per ray, HW7/src/Mesh_triangle.cpp:33-40), its vertex ids and its gate box.
+  // forms the same two differences per ray, HW7/src/Mesh_triangle.cpp:58-69), its vertex ids and its gate box.
   uint32_t add_tri(const Mesh_triangle* t, const Bounding_box& gate) {
     const uint32_t id = (uint32_t)tri_tex.size();
     const int i0 = TRI_I0(t) + TRI_OFFSET(t), i1 = TRI_I1(t) + TRI_OFFSET(t), i2 = TRI_I2(t) + TRI_OFFSET(t);

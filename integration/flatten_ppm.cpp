@@ -61,7 +61,7 @@ struct b200rt_flat_ppm {
   int rank;
 
   // One mesh triangle, in the order the walk meets it: v0, v0-v1, v0-v2, the stored normal (Mesh_triangle::intersect
-  // forms the same two differences per ray, PPM/src/Mesh_triangle.cpp:44-52), its vertex ids and its gate box.
+  // forms the same two differences per ray, PPM/src/Mesh_triangle.cpp:58-68), its vertex ids and its gate box.
   uint32_t add_tri(const Mesh_triangle* t, const Bounding_box& gate) {
     const uint32_t id = (uint32_t)tri_tex.size();
     const int i0 = t->vertex_index_0 + t->vertex_offset, i1 = t->vertex_index_1 + t->vertex_offset,
