@@ -12,7 +12,7 @@
 //   Scene scene(argv[1]);
 //   b200rt_flat_hw3* flat = b200rt_flatten_hw3(scene);           // owns the buffers
 //   b200rt_scene_create(b200rt_flat_hw3_desc(flat), 0, &gpu);    // libb200rt.so builds its SAH tree from tri_geom
-//   ... b200rt_render(gpu, camera_index, &opts, rgbw, &stats) instead of the std::thread fan-out (HW3/src/main.cpp:27-39)
+//   ... b200rt_render(gpu, camera_index, &opts, rgbw, &stats) instead of the std::thread fan-out (HW3/src/main.cpp:27-40)
 //   b200rt_flat_hw3_free(flat);
 //
 // tests/test_flatten_reference.py links this file with the UNTOUCHED objects of /root/reference/HW3 (oracle/build_ref.sh
@@ -130,7 +130,7 @@ struct b200rt_flat_hw3 {
     fi.mesh = mesh_index.at(mi->mesh_);
     fi.material = mi->material_id;
     fi.texture = mi->texture_id;
-    if (mi->velocity != Vector3(0.0f)) fi.flags |= B200RT_INST_MOVING;   // HW3/include/Mesh.h:61,76
+    if (mi->velocity != Vector3(0.0f)) fi.flags |= B200RT_INST_MOVING;   // HW3/include/Mesh.h:62,104
     fi.rank = rank++;
     fi.light = -1;
     instances.push_back(fi);
@@ -145,8 +145,8 @@ struct b200rt_flat_hw3 {
     put3(fs.velocity, sp->velocity);
     fs.material = sp->material_id;
     fs.texture = -1;
-    if (sp->is_identity_) fs.flags |= B200RT_XF_IDENTITY;               // HW3/include/Sphere.h:19,43
-    if (sp->velocity != Vector3(0.0f)) fs.flags |= B200RT_XF_MOVING;    // HW3/include/Sphere.h:43,75,113
+    if (sp->is_identity_) fs.flags |= B200RT_XF_IDENTITY;               // HW3/include/Sphere.h:20,46
+    if (sp->velocity != Vector3(0.0f)) fs.flags |= B200RT_XF_MOVING;    // HW3/include/Sphere.h:30,46,76
     fs.rank = rank++;
     fs.light = -1;
     spheres.push_back(fs);
@@ -247,7 +247,7 @@ extern "C" b200rt_flat_hw3* b200rt_flatten_hw3(const Scene& scene) {
     put3(fc.top_left, c.top_left_corner); put3(fc.su, c.s_u_constant); put3(fc.sv, c.s_v_constant);
     fc.left = ip.left; fc.right = ip.right; fc.bottom = ip.bottom; fc.top = ip.top; fc.distance = ip.distance;
     fc.width = ip.width; fc.height = ip.height;
-    fc.samples_sqrt = c.get_number_of_samples() > 0 ? c.get_number_of_samples() : 1;   // already (int)sqrt(NumSamples): HW3/src/Scene.cpp:412
+    fc.samples_sqrt = c.get_number_of_samples() > 0 ? c.get_number_of_samples() : 1;   // already (int)sqrt(NumSamples): HW3/src/Scene.cpp:411
     fc.aperture = c.get_aperture_size();
     f->cameras.push_back(fc);
   }

@@ -158,7 +158,7 @@ struct b200rt_flat_hw7 {
     fi.mesh = mesh_index.at(mi->mesh_);
     fi.material = mi->material_id;
     fi.texture = mi->texture_id;
-    if (mi->velocity != Vector3(0.0f)) fi.flags |= B200RT_INST_MOVING;   // HW7/include/Mesh.h:66,95
+    if (mi->velocity != Vector3(0.0f)) fi.flags |= B200RT_INST_MOVING;   // HW7/include/Mesh.h:76,134
 #if B200RT_TREE >= 7
     if (mi->is_refractive_) fi.flags |= B200RT_INST_REFRACTIVE;          // culling off inside glass: HW7/include/Mesh.h:73-75
 #endif
@@ -195,8 +195,8 @@ struct b200rt_flat_hw7 {
     put3(fs.velocity, sp->velocity);
     fs.material = sp->material_id;
     fs.texture = sp->texture_id;
-    if (sp->is_identity_) fs.flags |= B200RT_XF_IDENTITY;               // HW7/include/Sphere.h:19,43
-    if (sp->velocity != Vector3(0.0f)) fs.flags |= B200RT_XF_MOVING;    // HW7/include/Sphere.h:43,75,113
+    if (sp->is_identity_) fs.flags |= B200RT_XF_IDENTITY;               // HW7/src/Sphere.cpp:16-18
+    if (sp->velocity != Vector3(0.0f)) fs.flags |= B200RT_XF_MOVING;    // HW7/src/Sphere.cpp:24,34
     fs.rank = rank++;
     fs.light = -1;
 #if B200RT_TREE >= 7
