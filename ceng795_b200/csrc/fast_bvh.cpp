@@ -7,6 +7,7 @@
 #include <cstring>
 #include <future>
 #include <limits>
+#include <system_error>
 #include <thread>
 
 namespace b200rt_fast {
@@ -143,12 +144,17 @@ uint32_t build_rec(Ctx& cx, int s, int e, Bx* box) {
     std::vector<b200rt_bvh_node> sub_nodes;
     std::vector<int32_t> sub_order;
     Ctx lcx{cx.prims, &sub_nodes, &sub_order, cx.grow, cx.par_levels - 1};
-    auto left_task = std::async(std::launch::async, [&lcx, &lb, s, mid]() { return build_rec(lcx, s, mid, &lb); });
+    std::future<uint32_t> left_task;
+    try {
+      left_task = std::async(std::launch::async, [&lcx, &lb, s, mid]() { return build_rec(lcx, s, mid, &lb); });
+    } catch (const std::system_error&) {  // no thread to be had: same arrays, built here
+      l = build_rec(lcx, s, mid, &lb);
+    }
     std::vector<b200rt_bvh_node> r_nodes;
     std::vector<int32_t> r_order;
     Ctx rcx{cx.prims, &r_nodes, &r_order, cx.grow, cx.par_levels - 1};
     r = build_rec(rcx, mid, e, &rb);
-    l = left_task.get();
+    if (left_task.valid()) l = left_task.get();
     const uint32_t lnode_off = (uint32_t)cx.nodes->size(), lorder_off = (uint32_t)cx.order->size();
     const uint32_t rnode_off = lnode_off + (uint32_t)sub_nodes.size();
     const uint32_t rorder_off = lorder_off + (uint32_t)sub_order.size();

@@ -23,6 +23,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <system_error>
 #include <utility>
 #include <vector>
 
@@ -254,9 +255,14 @@ uint32_t build_bvh_at(std::vector<Obj>& objs, int start, int end, int dim, Build
     (*out.leaf_order)[leaf_pos] = objs[start].ref;
     if (out.gate) (*out.gate)[B200RT_REF_INDEX(objs[start].ref)] = box;
   } else if (par_levels > 0 && end - start >= kParMinObjs) {
-    left_task = std::async(std::launch::async, [&objs, &out, &lb, start, mid, dim, me, leaf_pos, par_levels]() {
-      return build_bvh_at(objs, start, mid, (dim + 1) % 3, out, lb, me + 1, leaf_pos, par_levels - 1);
-    });
+    try {
+      left_task = std::async(std::launch::async, [&objs, &out, &lb, start, mid, dim, me, leaf_pos, par_levels]() {
+        return build_bvh_at(objs, start, mid, (dim + 1) % 3, out, lb, me + 1, leaf_pos, par_levels - 1);
+      });
+    } catch (const std::system_error&) {  // no thread to be had: same slots, built here
+      uint32_t c = build_bvh_at(objs, start, mid, (dim + 1) % 3, out, lb, me + 1, leaf_pos, 0);
+      n.left = B200RT_REF(B200RT_KIND_INNER, c);
+    }
   } else {
     uint32_t c = build_bvh_at(objs, start, mid, (dim + 1) % 3, out, lb, me + 1, leaf_pos, 0);
     n.left = B200RT_REF(B200RT_KIND_INNER, c);
