@@ -5,7 +5,7 @@
 # forced standard includes and a case shim for HW1.
 # HW5/HW6: their main.cpp needs OpenCV (absent), so every OTHER translation unit of the tree is linked with
 # oracle/ref_driver_hdr.cpp, which calls the same Scene seam and dumps the float pixels.
-# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat1, flat3, flat4, flat5, flat6, flat7, flatppm, b200main3, b200main7, b200mainppm)
+# Usage: oracle/build_ref.sh [tree ...]   (default: every tree, the float-dump twins, probe, ppmeye, flat1, flat2, flat3, flat4, flat5, flat6, flat7, flatppm, b200main3, b200main7, b200mainppm)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${CENG795_REFERENCE:-/root/reference}"
@@ -14,7 +14,7 @@ OUT="$HERE/_ref"
 mkdir -p "$OUT"
 CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O3 -w -pthread -include limits -include algorithm -include stdexcept -include cstring -include chrono"
-TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat1 flat3 flat4 flat5 flat6 flat7 flatppm b200main3 b200main7 b200mainppm)
+TREES=("$@"); [ ${#TREES[@]} -eq 0 ] && TREES=(hw1 hw2 hw3 hw4 hw5 hw6 hw7 ppm hw2f hw3f hw4f hw7f probe ppmeye flat1 flat2 flat3 flat4 flat5 flat6 flat7 flatppm b200main3 b200main7 b200mainppm)
 build_flat() { # name dir extra
   local name=$1 dir=$2; shift 2
   local objdir="$OUT/obj_$name"; mkdir -p "$objdir"
@@ -192,6 +192,21 @@ build_hw1_binding() { # HW1 (flat directory, Ray.h shim): flatten driver and dro
     -Wl,-rpath,'$ORIGIN/../../ceng795_b200' -o "$OUT/hw1_b200_raytracer"
   echo "built $OUT/hw1_b200_raytracer"
 }
+build_flatten2() { # HW2 (flat directory): flatten driver
+  local dir="$REF/HW2" objdir="$OUT/obj_hw2" repo; repo="$(dirname "$HERE")"
+  [ -d "$objdir" ] || build_flat hw2 "$dir"
+  local objs=()
+  for f in "$dir"/*.cpp "$dir"/lodepng/*.cpp; do
+    [ "$(basename "$f")" = "main.cpp" ] && continue
+    objs+=("$objdir/$(basename "$f" .cpp).o")
+  done
+  local inc=(-I"$dir" -I"$repo/include")
+  $CXX $FLAGS -fno-access-control "${inc[@]}" -c "$repo/integration/flatten_hw2.cpp" -o "$objdir/flatten_hw2.o"
+  $CXX $FLAGS -DFLATTEN_HW2 "${inc[@]}" -c "$HERE/ref_driver_flatten.cpp" -o "$objdir/ref_driver_flatten.o"
+  $CXX -std=c++17 -O2 -c "$repo/ceng795_b200/csrc/scene_cache.cpp" -o "$objdir/scene_cache.o"
+  $CXX -pthread "${objs[@]}" "$objdir/flatten_hw2.o" "$objdir/ref_driver_flatten.o" "$objdir/scene_cache.o" -o "$OUT/flat2_flatten"
+  echo "built $OUT/flat2_flatten"
+}
 build_b200_main_ppm() { # the same drop-in for the PPM tree
   local dir="$REF/PPM" objdir="$OUT/obj_ppm" repo; repo="$(dirname "$HERE")"
   [ -d "$objdir" ] || build_tree ppm "$dir" -DNDEBUG
@@ -222,6 +237,7 @@ for t in "${TREES[@]}"; do
     hw7f) build_tree_driver hw7f "$REF/HW7" ;;
     probe) build_probe ;;
     flat1) build_hw1_binding ;;
+    flat2) build_flatten2 ;;
     flat3) build_flatten3 ;;
     flat4) build_flatten567 4 ;;
     flat5) build_flatten567 5 ;;

@@ -23,6 +23,12 @@
 #define b200rt_flat_hw3_desc b200rt_flat_hw1_desc
 #define b200rt_flat_hw3_free b200rt_flat_hw1_free
 #endif
+#ifdef FLATTEN_HW2   // ... integration/flatten_hw2.cpp and the HW2 tree's objects (target flat2)
+#define b200rt_flat_hw3 b200rt_flat_hw2
+#define b200rt_flatten_hw3 b200rt_flatten_hw2
+#define b200rt_flat_hw3_desc b200rt_flat_hw2_desc
+#define b200rt_flat_hw3_free b200rt_flat_hw2_free
+#endif
 #ifdef FLATTEN_PPM   // ... and against integration/flatten_ppm.cpp and the PPM tree's objects (target flatppm)
 #define b200rt_flat_hw3 b200rt_flat_ppm
 #define b200rt_flatten_hw3 b200rt_flatten_ppm
