@@ -36,3 +36,14 @@ def test_reference_arm_prints_the_contract_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_own_arm_refuses_to_run_without_a_device():
+    """The product arm never falls back: without a GPU it says so and exits non-zero instead of timing the oracle."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+    assert not any(l.startswith("{") for l in r.stdout.splitlines())
