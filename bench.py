@@ -338,60 +338,79 @@ def run_b200(args):
         return 0
 
     hbm, hbm_src = peaks()
-    if ppm:
-        n_closest = agg["photon_rays"]
-        ext_bytes = 64 * agg["nodes_visited"] + 48 * agg["tris_tested"] + (32 + 24) * n_closest
-        n_ext_launch = max(1, args.steps * (sc.spec.max_depth - 1))
-        per_ray = {"nodes": agg["nodes_visited"] / max(1, n_closest), "tris": agg["tris_tested"] / max(1, n_closest),
-                   "hit_points_scanned_per_photon_ray": agg["cell_scans"] / max(1, n_closest),
-                   "deposits_per_photon_ray": agg["deposits"] / max(1, n_closest)}
-        # the dominant kernel of a pass is the deposit (90 % of it, profiles/r01i_launches_summary.txt): per photon ray
-        # 52 B in + 56 B out of the pool, 16 B per scanned grid entry, 64 B record + 4 B count + 16 B flux per deposit
-        # ("32 k + 16 a", with this layout's record sizes)
-        dep_bytes = 108 * n_closest + 16 * agg["cell_scans"] + 84 * agg["deposits"]
-        trav_gbs = ext_bytes / (ms_stage["ms_extend"] * 1e-3) / 1e9 if ms_stage["ms_extend"] > 0 else None
-        extra = {"traversal_kernel": {"kernel": "k_trace_fast<false,7> (photon closest-hit traversal)",
-                                      "achieved": trav_gbs, "frac": (trav_gbs / hbm) if trav_gbs else None,
-                                      "avg_launch_ms": ms_stage["ms_extend"] / n_ext_launch}}
-        kernel = "k_ppm_photon_shade (scatter + cell scan + hit-point radius / flux update)"
-        ext_bytes = dep_bytes
-        ms_stage = dict(ms_stage, ms_extend_for_roofline=ms_stage["ms_deposit"])
-    else:
-        n_closest = agg["rays_primary"] + agg["rays_secondary"]
-        ext_bytes = (64 * agg["nodes_visited"] + 48 * agg["tris_tested"] + 20 * agg["spheres_tested"]
-                     + 112 * agg["instances_entered"] + (32 + 24) * n_closest)
-        sh_bytes = (64 * agg["sh_nodes_visited"] + 48 * agg["sh_tris_tested"] + 20 * agg["sh_spheres_tested"]
-                    + 112 * agg["sh_instances_entered"] + (36 + 1) * agg["rays_shadow"])
-        sh_gbs = sh_bytes / (ms_stage["ms_shadow"] * 1e-3) / 1e9 if ms_stage["ms_shadow"] > 0 else None
-        n_ext_launch = max(1, args.steps * (sc.spec.max_depth + 1))
-        kernel = ("k_trace_hw1_fast<false> (SAH tree over all triangles, HW1's order-dependent rule on the near-tie set)"
-                  if wl["tree"] == "hw1" else
-                  f"k_trace_fast<false,{7 if wl['tree'] == 'hw7' else 2}> (closest-hit traversal, SAH tree + reference gate)")
-        per_ray = {"nodes": agg["nodes_visited"] / max(1, n_closest), "tris": agg["tris_tested"] / max(1, n_closest)}
-        extra = {"shadow_kernel": {"achieved": sh_gbs, "frac": (sh_gbs / hbm) if sh_gbs else None,
-                                   "nodes_per_ray": agg["sh_nodes_visited"] / max(1, agg["rays_shadow"])}}
-    dom_ms = ms_stage.pop("ms_extend_for_roofline", None) if ppm else None   # PPM: the deposit stage is the dominant kernel
-    if dom_ms is None:
-        dom_ms = ms_stage["ms_extend"]
-    ext_gbs = ext_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
-    traffic = None
+    # second ceiling: scene fetches are served by L1/L2, so the traversal kernels are quoted against the L2
+    # read bandwidth measured here (48 MB working set, after the timed region); HBM is the ceiling only where ncu
+    # shows DRAM traffic of the order of the algorithmic bytes (the PPM deposit)
+    l2 = None
+    import ctypes as C
+    g = C.c_double(0.0)
+    if sc._L.b200rt_measure_read_bandwidth(local, 48 << 20, 50, C.byref(g)) == 0:
+        l2 = g.value
+    traffic_all = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.config, {}).get("dram_bytes_per_launch")
+            traffic_all = json.load(open(tp))
         except Exception:
-            traffic = None
+            traffic_all = {}
+    traffic_cfg = traffic_all.get(args.config, {})
+    nb = int(st.node_bytes) or 64
+
+    def kernel_line(name, bytes_, ms, launches, bound, traffic_key):
+        """achieved = algorithmic bytes / CUDA-event time of the stage; frac against the ceiling the counters name."""
+        gbs = bytes_ / (ms * 1e-3) / 1e9 if ms > 0 else None
+        peak = l2 if bound == "l2" else hbm
+        tr = traffic_cfg.get(traffic_key, {}).get("dram_bytes_per_launch") if isinstance(traffic_cfg.get(traffic_key), dict) else None
+        avg_ms = ms / max(1, launches)
+        return {"kernel": name, "bound": bound, "achieved": gbs, "peak": peak, "unit": "GB/s",
+                "frac": (gbs / peak) if (gbs and peak) else None,
+                "hbm_frac_algorithmic": (gbs / hbm) if gbs else None,
+                "traffic": tr, "dram_frac": (tr / (avg_ms * 1e-3) / 1e9 / hbm) if (tr and avg_ms > 0) else None,
+                "algorithmic_bytes_per_launch": bytes_ / max(1, launches), "avg_launch_ms": avg_ms,
+                "share_of_step": ms / ms_total if ms_total > 0 else None}
+
+    if ppm:
+        n_closest = agg["photon_rays"]
+        top_tests = int(st.top_objects) * n_closest
+        ext_bytes = (nb * (agg["nodes_visited"] - top_tests) + 32 * top_tests + 48 * agg["tris_tested"]
+                     + (32 + 24) * n_closest)
+        n_launch = max(1, args.steps * (sc.spec.max_depth - 1))
+        per_ray = {"nodes": (agg["nodes_visited"] - top_tests) / max(1, n_closest),
+                   "top_level_gates": int(st.top_objects), "tris": agg["tris_tested"] / max(1, n_closest),
+                   "hit_points_scanned_per_photon_ray": agg["cell_scans"] / max(1, n_closest),
+                   "deposits_per_photon_ray": agg["deposits"] / max(1, n_closest)}
+        # deposit: per photon ray 52 B in + 56 B out of the pool, 16 B per scanned grid entry, 64 B record + 4 B count
+        # + 16 B flux per deposit (SURVEY 8d: "32 k + 16 a", with this layout's record sizes)
+        dep_bytes = 108 * n_closest + 16 * agg["cell_scans"] + 84 * agg["deposits"]
+        kernels = [kernel_line("k_ppm_photon_shade (scatter + cell scan + hit-point radius / flux update)", dep_bytes,
+                               ms_stage["ms_deposit"], n_launch, "hbm", "deposit"),
+                   kernel_line(f"k_trace_{'wide' if nb == 80 else 'fast'}<false,7> (photon closest-hit traversal)",
+                               ext_bytes, ms_stage["ms_extend"], n_launch, "l2", "extend")]
+    else:
+        n_closest = agg["rays_primary"] + agg["rays_secondary"]
+        n_any = agg["rays_shadow"]
+        top_c, top_a = int(st.top_objects) * n_closest, int(st.top_objects) * n_any
+        ext_bytes = (nb * (agg["nodes_visited"] - top_c) + 32 * top_c + 48 * agg["tris_tested"]
+                     + 20 * agg["spheres_tested"] + 112 * agg["instances_entered"] + (32 + 24) * n_closest)
+        sh_bytes = (nb * (agg["sh_nodes_visited"] - top_a) + 32 * top_a + 48 * agg["sh_tris_tested"]
+                    + 20 * agg["sh_spheres_tested"] + 112 * agg["sh_instances_entered"] + (36 + 1) * n_any)
+        n_launch = max(1, args.steps * (sc.spec.max_depth + 1))
+        mode = 7 if wl["tree"] in ("hw4", "hw5", "hw6", "hw7", "ppm") else 2
+        if wl["tree"] == "hw1":
+            kn = "k_trace_hw1_fast<{}> (SAH tree over all triangles, HW1's order-dependent rule on the near-tie set)"
+        elif nb == 80:
+            kn = "k_trace_wide<{}," + str(mode) + "> (8-wide quantised tree, shared-memory stack, reference gate per candidate)"
+        else:
+            kn = "k_trace_fast<{}," + str(mode) + "> (binary SAH tree + reference gate)"
+        per_ray = {"nodes": (agg["nodes_visited"] - top_c) / max(1, n_closest), "top_level_gates": int(st.top_objects),
+                   "tris": agg["tris_tested"] / max(1, n_closest),
+                   "shadow_nodes": (agg["sh_nodes_visited"] - top_a) / max(1, n_any),
+                   "shadow_tris": agg["sh_tris_tested"] / max(1, n_any), "node_bytes": nb}
+        kernels = [kernel_line(kn.format("false") + " closest hit", ext_bytes, ms_stage["ms_extend"], n_launch, "l2", "extend"),
+                   kernel_line(kn.format("true") + " any hit (shadow rays)", sh_bytes, ms_stage["ms_shadow"], n_launch, "l2", "shadow")]
+    kernels.sort(key=lambda k: -(k["share_of_step"] or 0.0))
+    dom = kernels[0]
     frames = world if split == "cameras" else 1
-    # second ceiling: the scene fetches are served by L1/L2, so also quote the extend kernel's
-    # algorithmic GB/s against the L2 read bandwidth measured here (48 MB working set, after the timed region)
-    l2 = None
-    if rank == 0:
-        import ctypes as C
-        g = C.c_double(0.0)
-        if sc._L.b200rt_measure_read_bandwidth(local, 48 << 20, 50, C.byref(g)) == 0:
-            l2 = g.value
-    extra["l2"] = {"peak": l2, "unit": "GB/s", "peak_source": "measured here: b200rt_measure_read_bandwidth, 48 MB x 50 passes",
-                   "frac": (ext_gbs / l2) if (ext_gbs and l2) else None}
     line = {
         "metric": METRIC, "value": rays / ms_total / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -407,10 +426,16 @@ def run_b200(args):
                 "h2d_bytes_per_step": 176 + 64, "d2h_bytes_per_step": H * W * 16 * frames},
         "gpu_launches": launches_all,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": ext_gbs, "peak": hbm, "peak_source": hbm_src,
-                     "unit": "GB/s", "frac": (ext_gbs / hbm) if ext_gbs else None, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": ext_bytes / n_ext_launch,
-                     "avg_launch_ms": dom_ms / n_ext_launch, "per_ray": per_ray, **extra},
+        # the dominant kernel BY TIME, against the ceiling its counters name; the other kernels of the step follow
+        "roofline": {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
+                     "peak_source": ("measured here: b200rt_measure_read_bandwidth, 48 MB x 50 passes (L2 read)"
+                                     if dom["bound"] == "l2" else hbm_src),
+                     "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"], "dram_frac": dom["dram_frac"],
+                     "traffic_source": traffic_all.get("_source"),
+                     "hbm": {"peak": hbm, "peak_source": hbm_src, "frac_algorithmic": dom["hbm_frac_algorithmic"]},
+                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                     "avg_launch_ms": dom["avg_launch_ms"], "share_of_step": dom["share_of_step"],
+                     "per_ray": per_ray, "other_kernels": kernels[1:]},
     }
     if ppm:
         line["config"]["photons_per_step"] = photons

@@ -11,6 +11,7 @@
 #include <functional>
 
 #include "fast_bvh.h"
+#include "wide_bvh.h"
 #include "lbvh.cuh"
 #include "ppm_kernels.cuh"
 #include "rt_hw1_fast.cuh"
@@ -52,6 +53,8 @@ struct b200rt_scene {
   bool has_transparency, has_mirror;
   int sm_count;
   int n_meshes;
+  int wide_nodes, wide_depth;   // the 8-wide tree (0 nodes: the scene walks the binary tree)
+  int wide_blocks;              // resident CTAs per SM of k_trace_wide (4 / 6 / 8)
   // device allocations owned by the scene
   std::vector<void*> allocs;
   // cached wavefront state
@@ -63,6 +66,7 @@ struct b200rt_scene {
   size_t accum_pixels;
   cudaStream_t stream;
   cudaEvent_t ev[2];
+  std::vector<cudaEvent_t> ev_pool;   // stage marks (Timers)
   size_t scene_bytes;
   // PPM state
   HitPoints HP;
@@ -124,30 +128,54 @@ int ensure_accum(b200rt_scene* sc, size_t pixels) {
   return B200RT_OK;
 }
 
+// Stage marks of a frame.  The events come from a pool the scene owns and grows on first use, so a steady-state frame
+// creates and destroys nothing inside its timed region.
 struct Timers {
-  std::vector<cudaEvent_t> ev;
+  std::vector<cudaEvent_t>* pool;
   std::vector<int> stage;
+  size_t used;
   cudaStream_t s;
   bool on;
   void mark(int st) {
     if (!on) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, s);
-    ev.push_back(e);
+    if (used == pool->size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+      pool->push_back(e);
+    }
+    cudaEventRecord((*pool)[used++], s);
     stage.push_back(st);
   }
+  void reset() { used = 0; stage.clear(); }
   void collect(float* ms) {
     for (int i = 0; i < ST_COUNT; i++) ms[i] = 0.f;
-    for (size_t i = 1; i < ev.size(); i++) {
+    for (size_t i = 1; i < used; i++) {
       float t = 0.f;
-      cudaEventElapsedTime(&t, ev[i - 1], ev[i]);
+      cudaEventElapsedTime(&t, (*pool)[i - 1], (*pool)[i]);
       ms[stage[i]] += t;
     }
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
-    ev.clear(); stage.clear();
+    reset();
   }
 };
+
+// k_trace_wide<ANY, TRI_MODE, MINB> on the scene's stream, one persistent CTA set per SM
+void launch_wide(b200rt_scene* sc, bool any, bool mode7, int d) {
+  const int mb = sc->wide_blocks;
+  const int grid = sc->sm_count * mb;
+  cudaStream_t st = sc->stream;
+#define LW(A, M, B) k_trace_wide<A, M, B><<<grid, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters)
+#define LWB(A, M) do { if (mb == 4) LW(A, M, 4); else if (mb == 8) LW(A, M, 8); else LW(A, M, 6); } while (0)
+  if (any) { if (mode7) LWB(true, 7); else LWB(true, 2); }
+  else { if (mode7) LWB(false, 7); else LWB(false, 2); }
+#undef LWB
+#undef LW
+}
+
+Timers make_timers(b200rt_scene* sc, bool on) {
+  Timers tm;
+  tm.pool = &sc->ev_pool; tm.used = 0; tm.s = sc->stream; tm.on = on;
+  return tm;
+}
 
 // Runs the wave loop for paths already placed in wave 0 by k_generate / k_import_rays.
 // primary_only: stop after the first extend (parity hooks).
@@ -158,17 +186,23 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
   const int grid_p = sc->sm_count * (RT_FAST_MIN_BLOCKS > 8 ? RT_FAST_MIN_BLOCKS : 8);  // persistent traversal grid: resident CTAs of 128 threads per SM
   const int grid_s = sc->sm_count * 8;
   const bool hw1 = S.semantics == B200RT_SEM_HW1;
+  const bool wide = S.use_wide && !exact && !hw1;
+  const bool mode7 = S.semantics >= B200RT_SEM_HW4;
   const int max_d = primary_only ? 0 : S.max_depth;
   int d_last = 0;
+  // wave bookkeeping: one <<<1,1>>> launch per depth (k_finish_wave also opens the next wave); the shadow-queue clamp
+  // is done by the traversal kernel itself on the wide path
+  k_next_wave<<<1, 1, 0, st>>>(sc->d_waves, 0, sc->d_counters);
+  (*launches)++;
   for (int d = 0; d <= max_d; d++) {
-    k_next_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->d_counters);
-    (*launches)++;
     const bool hw1_fast = hw1 && S.hw1_fast_root != B200RT_REF_NONE && !exact;
     if (hw1_fast) {
       k_trace_hw1_fast<false><<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     } else if (hw1) {
       k_extend_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
-    } else if (S.semantics >= B200RT_SEM_HW4) {
+    } else if (wide) {
+      launch_wide(sc, false, mode7, d);
+    } else if (mode7) {
       if (exact) k_extend<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
       else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     } else {
@@ -184,14 +218,16 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     if (hw7) k_shade7_a<<<grid_s * RT_BLOCK / RT_SHADE7_BLOCK, RT_SHADE7_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     else if (hw4) k_shade4_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     else k_shade_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
-    k_clamp_shadow_count<<<1, 1, 0, st>>>(sc->Q, sc->d_counters);
-    (*launches) += 2;
+    (*launches)++;
+    if (!wide) { k_clamp_shadow_count<<<1, 1, 0, st>>>(sc->Q, sc->d_counters); (*launches)++; }
     tm.mark(ST_SHADE);
     if (hw1_fast) {
       k_trace_hw1_fast<true><<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     } else if (hw1) {
       k_shadow_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
-    } else if (S.semantics >= B200RT_SEM_HW4) {
+    } else if (wide) {
+      launch_wide(sc, true, mode7, d);
+    } else if (mode7) {
       if (exact) k_shadow<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
       else k_trace_fast<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     } else {
@@ -289,15 +325,14 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
     if (rc) return rc;
   }
 
-  Timers tm;
-  tm.s = st; tm.on = stats != nullptr;
+  Timers tm = make_timers(sc, stats != nullptr);
   int launches = 0, waves_total = 0;
   Counters hc;
   for (int attempt = 0;; attempt++) {
     CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), st));
     CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
     launches = 0; waves_total = 0;
-    if (tm.on) { float dummy[ST_COUNT]; tm.collect(dummy); }
+    tm.reset();
     cudaEventRecord(sc->ev[0], st);
     tm.mark(ST_GENERATE);
     for (int r0 = 0; r0 < R.n_rows; r0 += (int)rows_per_batch) {
@@ -343,6 +378,8 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
     stats->ms_shade = ms[ST_SHADE]; stats->ms_shadow = ms[ST_SHADOW];
     cudaEventElapsedTime(&stats->ms_total, sc->ev[0], sc->ev[1]);
     stats->waves = waves_total; stats->launches = launches;
+    stats->node_bytes = (sc->S.use_wide && !exact && sc->S.semantics != B200RT_SEM_HW1) ? 80 : 64;
+    stats->top_objects = exact ? 0 : sc->S.n_top;
   }
   return B200RT_OK;
 }
@@ -442,12 +479,14 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
   cudaEventRecord(e0, st);
   k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, R, sc->d_waves, sc->d_counters);
   launches++;
+  k_next_wave<<<1, 1, 0, st>>>(sc->d_waves, 0, sc->d_counters);
+  launches++;
   for (int d = 0; d <= sc->S.max_depth; d++) {
-    k_next_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->d_counters);
-    k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    if (sc->S.use_wide) launch_wide(sc, false, true, d);
+    else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
     k_ppm_eye_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->d_waves, d, sc->HP, sc->d_counters, sc->d_pc);
     k_finish_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->P, sc->d_counters);
-    launches += 4;
+    launches += 3;
   }
   cudaEventRecord(e1, st);
   CK(cudaStreamSynchronize(st));
@@ -541,8 +580,7 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
   PpmCounters hpc0, hpc1;
   CK(cudaMemcpy(&hpc0, sc->d_pc, sizeof(hpc0), cudaMemcpyDeviceToHost));
   CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
-  Timers tm;
-  tm.s = st; tm.on = stats != nullptr;
+  Timers tm = make_timers(sc, stats != nullptr);
   int launches = 0;
   cudaEventRecord(sc->ev[0], st);
   tm.mark(ST_GENERATE);
@@ -580,7 +618,8 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
     for (int d = 0; d + 1 < sc->S.max_depth; d++) {
       k_ppm_next_wave<<<1, 1, 0, st>>>(sc->d_waves, d, half, sc->d_counters);
       k_ppm_count_rays<<<1, 1, 0, st>>>(sc->d_waves, d, sc->d_pc);
-      k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+      if (sc->S.use_wide) launch_wide(sc, false, true, d);
+      else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
       tm.mark(ST_EXTEND);
       k_ppm_photon_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->d_waves, d, sc->HP, sc->G,
                                                                 sc->d_counters, sc->d_pc);
@@ -607,6 +646,8 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
     cudaEventElapsedTime(&stats->ms_photon, sc->ev[0], sc->ev[1]);
     stats->initial_radius = sc->G.r0;
     stats->launches = launches;
+    stats->node_bytes = sc->S.use_wide ? 80 : 64;
+    stats->top_objects = sc->S.n_top;
   }
   return B200RT_OK;
 }
@@ -731,43 +772,11 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   } while (0)
   UP(S.nodes, d->nodes, d->n_nodes, b200rt_bvh_node);
   {
-    // Flat list of the top-level objects, each with the innermost box of the reference's gate chain above it: an
-    // instance's own world box (Mesh_instance::intersect tests it itself), for a primitive the box of the BVH node
-    // that holds it.  Every outer box of the chain contains that one and the slab test is monotone in the box
-    // (DESIGN.md 4b), so "innermost gate passes" == "the reference reaches the object".  A short list tested by all
-    // lanes in lock step replaces the divergent walk of the top-level tree (25 % of the traversal kernels'
-    // instructions on cfg4, profiles/r01g).
+    // Flat list of the top-level objects with the innermost box of the reference's gate chain above each
+    // (b200rt_wide::flatten_top, csrc/wide_bvh.cpp): a short list tested by all lanes in lock step replaces the
+    // divergent walk of the top-level tree (25 % of the traversal kernels' instructions on cfg4, profiles/r01g).
     std::vector<float> flat;
-    bool ok = d->semantics != B200RT_SEM_HW1;
-    std::function<void(uint32_t, const float*, bool)> walk = [&](uint32_t ref, const float* box, bool own) {
-      const uint32_t kind = B200RT_REF_KIND(ref);
-      if (kind == B200RT_KIND_NONE || !ok) return;
-      if (kind == B200RT_KIND_INNER) {
-        const uint32_t idx = B200RT_REF_INDEX(ref);
-        if ((int)idx >= d->n_nodes) { ok = false; return; }
-        const b200rt_bvh_node& n = d->nodes[idx];
-        const uint32_t ch[2] = {n.left, n.right};
-        const float* cb[2] = {n.lmin, n.rmin};   // lmin,lmax / rmin,rmax are contiguous: 6 floats each
-        for (int c = 0; c < 2; c++) {
-          const uint32_t ck = B200RT_REF_KIND(ch[c]);
-          if (ck == B200RT_KIND_INNER) walk(ch[c], cb[c], true);
-          else if (ck == B200RT_KIND_INSTANCE) walk(ch[c], cb[c], true);     // its own box, as stored in the parent
-          else walk(ch[c], box, own);                                         // primitives: the node's own gate
-        }
-        return;
-      }
-      float rec[8] = {box ? box[0] : 0.f, box ? box[1] : 0.f, box ? box[2] : 0.f, 0.f,
-                      box ? box[3] : 0.f, box ? box[4] : 0.f, box ? box[5] : 0.f, 0.f};
-      memcpy(&rec[3], &ref, 4);
-      const uint32_t gated = (own && box) ? 1u : 0u;
-      memcpy(&rec[7], &gated, 4);
-      flat.insert(flat.end(), rec, rec + 8);
-    };
-    if (ok) {
-      const uint32_t rk = B200RT_REF_KIND(d->root);
-      // BVH::intersect and Mesh_instance::intersect test the root's box; a lone primitive has no gate at all
-      walk(d->root, d->root_box, rk == B200RT_KIND_INNER || rk == B200RT_KIND_INSTANCE);
-    }
+    const bool ok = b200rt_wide::flatten_top(d, flat);
     const size_t n_top = flat.size() / 8;
     if (!ok || n_top == 0 || n_top > RT_TOP_LINEAR_MAX || getenv("B200RT_TOP_TREE")) {
       S.n_top = 0; S.top_objs = nullptr;
@@ -854,6 +863,43 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   UP(S.fast_nodes, fast_nodes, n_fast_nodes, b200rt_bvh_node);
   UP(S.fast_tris, fast_geom, (size_t)n_fast_tris * 12, float);
   UP(S.fast_tri_ref, fast_ref, (size_t)n_fast_tris, int32_t);
+  {
+    // The tree the default kernel walks inside a mesh: the SAH tree collapsed 8 wide with quantised child boxes
+    // (csrc/wide_bvh.h).  Triangles are stored once more, in the order the wide leaves want them.
+    std::vector<b200rt_wide::Node> wnodes;
+    std::vector<int32_t> worder;
+    std::vector<int32_t> wroot((size_t)(d->n_meshes > 0 ? d->n_meshes : 1), -1);
+    b200rt_wide::Stats ws = {0, 0, 0, 0};
+    const bool want = d->semantics != B200RT_SEM_HW1 && S.n_top > 0 && n_fast_tris > 0 && !getenv("B200RT_NO_WIDE");
+    if (want) {
+      for (int mi = 0; mi < d->n_meshes; mi++) {
+        const b200rt_mesh& m = meshes[mi];
+        if (m.tri_count < 2 || m.fast_root == B200RT_REF_NONE) continue;
+        float ext = 0.f;
+        for (int a = 0; a < 3; a++) {
+          ext = fmaxf(ext, m.root_box[3 + a] - m.root_box[a]);
+          ext = fmaxf(ext, fmaxf(fabsf(m.root_box[a]), fabsf(m.root_box[3 + a])));
+        }
+        const float grow = ext * (3e-5f + 4.0f * d->isect_eps) + 1e-30f;
+        wroot[mi] = b200rt_wide::build(fast_nodes, m.fast_root, fast_geom, grow, wnodes, worder, &ws);
+      }
+    }
+    std::vector<float> wgeom(worder.size() * 12);
+    std::vector<int32_t> wref(worder.size());
+    for (size_t k = 0; k < worder.size(); k++) {
+      memcpy(&wgeom[12 * k], fast_geom + 12 * (size_t)worder[k], 48);
+      wref[k] = fast_ref[worder[k]];
+    }
+    UP(S.wide_nodes, wnodes.data(), wnodes.size() * 20, float);   // 80 bytes = 5 x float4 per node
+    UP(S.wide_tris, wgeom.data(), wgeom.size(), float);
+    UP(S.wide_tri_ref, wref.data(), wref.size(), int32_t);
+    UP(S.wide_root, wroot.data(), wroot.size(), int32_t);
+    // the shared-memory stack of k_trace_wide holds one node group per level
+    S.use_wide = (want && ws.depth <= RT_WSTACK) ? 1 : 0;
+    sc->wide_nodes = (int)wnodes.size(); sc->wide_depth = ws.depth;
+    sc->wide_blocks = RT_WIDE_MIN_BLOCKS;
+    if (const char* e = getenv("B200RT_WIDE_BLOCKS")) { const int v = atoi(e); if (v == 4 || v == 6 || v == 8) sc->wide_blocks = v; }
+  }
   UP(S.tri_gate, d->tri_gate, (size_t)d->n_tris * 6, float);
   UP(S.tri_info, d->tri_info, (size_t)d->n_tris * 2, int32_t);
   UP(S.tri_vidx, d->tri_vidx, (size_t)d->n_tris * 3, int32_t);
@@ -892,9 +938,9 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     const float* mr = d->materials[i].mirror;
     if (mr[0] != 0.f || mr[1] != 0.f || mr[2] != 0.f) sc->has_mirror = true;
   }
-  CK(cudaMalloc((void**)&sc->d_waves, sizeof(WaveInfo) * kMaxWaves));
+  CK(cudaMalloc((void**)&sc->d_waves, sizeof(WaveInfo) * (kMaxWaves + 2)));
   CK(cudaMalloc((void**)&sc->d_counters, sizeof(Counters)));
-  CK(cudaMemset(sc->d_waves, 0, sizeof(WaveInfo) * kMaxWaves));
+  CK(cudaMemset(sc->d_waves, 0, sizeof(WaveInfo) * (kMaxWaves + 2)));
   CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&sc->ev[0]));
   CK(cudaEventCreate(&sc->ev[1]));
@@ -915,6 +961,7 @@ void b200rt_scene_destroy(b200rt_scene* sc) {
   if (sc->stream) cudaStreamDestroy(sc->stream);
   if (sc->ev[0]) cudaEventDestroy(sc->ev[0]);
   if (sc->ev[1]) cudaEventDestroy(sc->ev[1]);
+  for (cudaEvent_t e : sc->ev_pool) cudaEventDestroy(e);
   delete sc;
 }
 
@@ -1161,6 +1208,7 @@ int b200rt_scene_build_bvh_device(b200rt_scene* sc, float* ms_out) {
   sc->S.fast_nodes = reinterpret_cast<const float4*>(d_nodes);
   sc->S.fast_tris = d_ftris;
   sc->S.fast_tri_ref = d_fref;
+  sc->S.use_wide = 0;   // the device-built tree is binary: k_trace_fast walks it
   return B200RT_OK;
 }
 
@@ -1219,7 +1267,7 @@ int b200rt_primary_ids(b200rt_scene* sc, int camera_index, const B200RenderOpts*
   }
   CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
   k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, R, sc->d_waves, sc->d_counters);
-  Timers tm; tm.s = st; tm.on = false;
+  Timers tm = make_timers(sc, false);
   int launches = 0, wr = 0;
   rc = run_waves(sc, opts && opts->exact_traversal, true, false, tm, &launches, &wr);
   if (rc) { cudaFree(d_ids); cudaFree(d_t); return rc; }
@@ -1251,7 +1299,7 @@ int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t ex
   CK(cudaMemcpyAsync(d_rays, rays, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
   k_import_rays<<<sc->sm_count * 4, 256, 0, st>>>(sc->P, d_rays, (uint32_t)n, sc->d_waves);
-  Timers tm; tm.s = st; tm.on = stats != nullptr;
+  Timers tm = make_timers(sc, stats != nullptr);
   tm.mark(ST_GENERATE);
   int launches = 0, wr = 0;
   rc = run_waves(sc, exact != 0, true, false, tm, &launches, &wr);
@@ -1271,6 +1319,8 @@ int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t ex
     tm.collect(ms);
     stats->ms_extend = ms[ST_EXTEND];
     stats->launches = launches; stats->waves = 1;
+    stats->node_bytes = (sc->S.use_wide && !exact && sc->S.semantics != B200RT_SEM_HW1) ? 80 : 64;
+    stats->top_objects = exact ? 0 : sc->S.n_top;
   }
   cudaFree(d_rays); cudaFree(d_ids); cudaFree(d_t);
   return B200RT_OK;

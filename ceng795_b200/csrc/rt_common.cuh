@@ -95,6 +95,12 @@ struct DScene {
   const float4* fast_tris;  // triangles again, in SAH leaf order
   const int* fast_tri_ref;  // leaf-order position -> triangle index (DFS order)
   const float* tri_gate;    // 6 floats per triangle: the reference's innermost gate box
+  // 8-wide tree with quantised child boxes (csrc/wide_bvh.h), walked by k_trace_wide
+  const float4* wide_nodes; // 5 x float4 per node
+  const float4* wide_tris;  // triangles in the wide leaves' order
+  const int* wide_tri_ref;  // wide-order position -> triangle index (DFS order)
+  const int* wide_root;     // per mesh: index of its root node, -1 none
+  int use_wide;             // 0: k_trace_fast (binary tree, top-level tree walk) — more than RT_TOP_LINEAR_MAX objects, device-built tree
   const int2* tri_info;     // material, flags
   const int* tri_vidx;      // 3 per triangle
   const float4* vnormal;    // per vertex

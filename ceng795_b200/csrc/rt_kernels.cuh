@@ -133,6 +133,7 @@ __device__ __forceinline__ void flush_counters(Counters* C, const TravCounters& 
 }
 
 #include "rt_fast.cuh"
+#include "rt_wide.cuh"
 
 // ---- extend (exact mode): closest hit, persistent warps pulling 32-ray batches
 template <bool EXACT, int TRI_MODE>
@@ -560,10 +561,14 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE3_MIN_BLOCKS) k_shade_b(DSce
   }
 }
 
+// Closes wave d+1 (clamped to the pool) and opens wave d+2 behind it: what k_next_wave(d+1) did as a launch of its own.
 __global__ void k_finish_wave(WaveInfo* waves, int d, Pool P, Counters* C) {
   const uint32_t room = P.capacity > waves[d + 1].begin ? P.capacity - waves[d + 1].begin : 0;
   if (waves[d + 1].count > room) { waves[d + 1].count = room; C->overflow = 1; }
   atomicAdd(&C->rays_secondary, (unsigned long long)waves[d + 1].count);
+  waves[d + 2].begin = waves[d + 1].begin + waves[d + 1].count;
+  waves[d + 2].count = 0;
+  C->work_extend = 0; C->work_shadow = 0; C->shadow_count = 0;
 }
 
 // gaussian_filter — HW3/src/Scene.cpp:15-17 (double exp, float divisor)

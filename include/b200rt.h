@@ -359,6 +359,9 @@ typedef struct B200RenderStats {
   uint64_t sh_nodes_visited, sh_tris_tested, sh_spheres_tested, sh_instances_entered;
   float ms_generate, ms_extend, ms_shade, ms_shadow, ms_total;
   int32_t waves, launches;
+  int32_t node_bytes;   /* bytes of one nodes_visited unit inside a mesh: 80 (8-wide tree) or 64 (binary tree) */
+  int32_t top_objects;  /* gate boxes of the flat top-level list (32 B each); every ray tests all of them and they are
+                           counted in nodes_visited.  0: the top-level tree is walked instead */
 } B200RenderStats;
 
 int b200rt_device_count(void);
@@ -405,6 +408,7 @@ typedef struct B200PpmStats {
   float ms_eye, ms_grid, ms_photon, ms_extend, ms_deposit, ms_density;
   float initial_radius;
   int32_t launches;
+  int32_t node_bytes, top_objects;
 } B200PpmStats;
 /* reset_hash_grid + eye_trace_lines + build_hash_grid for one camera */
 int b200rt_ppm_eye_pass(b200rt_scene*, int camera_index, uint64_t seed, B200PpmStats*);
