@@ -122,7 +122,7 @@ class SceneDesc(C.Structure):
 
 class RenderOpts(C.Structure):
     _fields_ = [("row_begin", c_i), ("row_end", c_i), ("row_stride", c_i), ("seed", C.c_uint64),
-                ("sample_begin", c_i), ("sample_end", c_i), ("exact_traversal", c_i), ("pad", c_i * 5)]
+                ("sample_begin", c_i), ("sample_end", c_i), ("exact_traversal", c_i), ("contexts", c_i), ("pad", c_i * 4)]
 
 
 class RenderStats(C.Structure):
@@ -132,7 +132,7 @@ class RenderStats(C.Structure):
                 ("sh_nodes_visited", C.c_uint64), ("sh_tris_tested", C.c_uint64), ("sh_spheres_tested", C.c_uint64),
                 ("sh_instances_entered", C.c_uint64),
                 ("ms_generate", c_f), ("ms_extend", c_f), ("ms_shade", c_f), ("ms_shadow", c_f),
-                ("ms_total", c_f), ("waves", c_i), ("launches", c_i), ("node_bytes", c_i), ("top_objects", c_i)]
+                ("ms_total", c_f), ("waves", c_i), ("launches", c_i), ("node_bytes", c_i), ("top_objects", c_i), ("contexts", c_i), ("pad", c_i)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

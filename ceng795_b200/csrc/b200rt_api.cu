@@ -11,6 +11,7 @@
 #include <functional>
 
 #include "fast_bvh.h"
+#include "api_guard.h"
 #include "wide_bvh.h"
 #include "lbvh.cuh"
 #include "ppm_kernels.cuh"
@@ -46,6 +47,22 @@ enum Stage { ST_GENERATE = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_COUNT };
 
 }  // namespace
 
+// One wavefront context: the vertex pool, the shadow queue, the wave table, the counters and the stream they are
+// driven on.  A frame is cut into row bands, one per context, and the contexts' launch trains run concurrently: the
+// persistent traversal kernels of one band fill the SMs that another band's tail wave (a few long rays on a grid sized
+// for the whole machine) leaves idle.  Context 0 also serves the single-stream entry points (PPM, parity hooks).
+struct WaveCtx {
+  Pool P;
+  ShadowQueue Q;
+  WaveInfo* d_waves;
+  Counters* d_counters;
+  cudaStream_t stream;
+  cudaEvent_t ev[2];
+  std::vector<cudaEvent_t> ev_pool;   // stage marks (Timers)
+};
+constexpr int kMaxCtx = 8;
+constexpr int kDefaultCtx = 1;   // swept on the device (profiles/r02*_tuning.txt)
+
 struct b200rt_scene {
   int device;
   DScene S;                    // device pointers (camera filled per render)
@@ -55,18 +72,14 @@ struct b200rt_scene {
   int n_meshes;
   int wide_nodes, wide_depth;   // the 8-wide tree (0 nodes: the scene walks the binary tree)
   int wide_blocks;              // resident CTAs per SM of k_trace_wide (4 / 6 / 8)
+  int n_ctx;                    // contexts a frame is cut into (B200RT_CONTEXTS, default kDefaultCtx)
   // device allocations owned by the scene
   std::vector<void*> allocs;
-  // cached wavefront state
-  Pool P;
-  ShadowQueue Q;
-  WaveInfo* d_waves;
-  Counters* d_counters;
+  // wavefront state
+  WaveCtx c0;
+  std::vector<WaveCtx*> more;   // contexts 1.. (created on first use)
   float4* d_accum;
   size_t accum_pixels;
-  cudaStream_t stream;
-  cudaEvent_t ev[2];
-  std::vector<cudaEvent_t> ev_pool;   // stage marks (Timers)
   size_t scene_bytes;
   // PPM state
   HitPoints HP;
@@ -84,38 +97,77 @@ struct b200rt_scene {
 namespace {
 
 template <typename T>
-int pool_alloc(b200rt_scene* sc, T** p, size_t n) {
+int pool_alloc(T** p, size_t n) {
   CK(cudaMalloc((void**)p, n * sizeof(T)));
   return B200RT_OK;
 }
 
-void pool_free(b200rt_scene* sc) {
-  Pool& P = sc->P;
+void pool_free(WaveCtx& cx) {
+  Pool& P = cx.P;
   void* ptrs[] = {P.ray_o, P.ray_d, P.key, P.pixel, P.sample, P.hit_a, P.hit_b, P.nrm, P.rec0, P.rec1, P.rec2,
-                  P.rec3, P.final_c, P.kd, P.rec4, sc->Q.o, sc->Q.d, sc->Q.time, sc->Q.vis, sc->Q.lv};
+                  P.rec3, P.final_c, P.kd, P.rec4, P.omask, cx.Q.o, cx.Q.d, cx.Q.time, cx.Q.vis, cx.Q.lv, cx.Q.omask};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  memset(&sc->P, 0, sizeof(Pool));
-  memset(&sc->Q, 0, sizeof(ShadowQueue));
+  memset(&cx.P, 0, sizeof(Pool));
+  memset(&cx.Q, 0, sizeof(ShadowQueue));
 }
 
-int ensure_pool(b200rt_scene* sc, size_t slots, size_t shadow_slots) {
-  if (sc->P.capacity >= slots && sc->Q.capacity >= shadow_slots) return B200RT_OK;
-  pool_free(sc);
-  Pool& P = sc->P;
+int ensure_pool(b200rt_scene* sc, WaveCtx& cx, size_t slots, size_t shadow_slots) {
+  if (cx.P.capacity >= slots && cx.Q.capacity >= shadow_slots) return B200RT_OK;
+  pool_free(cx);
+  Pool& P = cx.P;
   int rc;
-#define PA(field, n) if ((rc = pool_alloc(sc, &field, (n))) != B200RT_OK) return rc
+#define PA(field, n) if ((rc = pool_alloc(&field, (n))) != B200RT_OK) return rc
   PA(P.ray_o, slots); PA(P.ray_d, slots); PA(P.key, slots); PA(P.pixel, slots); PA(P.sample, slots);
   PA(P.hit_a, slots); PA(P.hit_b, slots); PA(P.nrm, slots); PA(P.rec0, slots); PA(P.rec1, slots);
   PA(P.rec2, slots); PA(P.rec3, slots); PA(P.final_c, slots);
   if (sc->S.semantics >= B200RT_SEM_HW4) { PA(P.kd, slots); PA(P.rec4, slots); }
+  if (sc->S.use_wide) { PA(P.omask, slots); PA(cx.Q.omask, shadow_slots); }
   P.capacity = (uint32_t)slots;
-  ShadowQueue& Q = sc->Q;
+  ShadowQueue& Q = cx.Q;
   PA(Q.o, shadow_slots); PA(Q.d, shadow_slots); PA(Q.time, shadow_slots);
   PA(Q.vis, slots * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1));
   if (sc->S.semantics >= B200RT_SEM_HW5 && sc->S.semantics <= B200RT_SEM_HW7) PA(Q.lv, slots * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1));
 #undef PA
   Q.capacity = (uint32_t)shadow_slots;
+  return B200RT_OK;
+}
+
+int ctx_init(WaveCtx& cx) {
+  memset(&cx.P, 0, sizeof(Pool));
+  memset(&cx.Q, 0, sizeof(ShadowQueue));
+  cx.d_waves = nullptr; cx.d_counters = nullptr; cx.stream = nullptr; cx.ev[0] = nullptr; cx.ev[1] = nullptr;
+  CK(cudaMalloc((void**)&cx.d_waves, sizeof(WaveInfo) * (kMaxWaves + 2)));
+  CK(cudaMalloc((void**)&cx.d_counters, sizeof(Counters)));
+  CK(cudaMemset(cx.d_waves, 0, sizeof(WaveInfo) * (kMaxWaves + 2)));
+  CK(cudaStreamCreateWithFlags(&cx.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&cx.ev[0]));
+  CK(cudaEventCreate(&cx.ev[1]));
+  return B200RT_OK;
+}
+
+void ctx_destroy(WaveCtx& cx) {
+  pool_free(cx);
+  if (cx.d_waves) cudaFree(cx.d_waves);
+  if (cx.d_counters) cudaFree(cx.d_counters);
+  if (cx.stream) cudaStreamDestroy(cx.stream);
+  if (cx.ev[0]) cudaEventDestroy(cx.ev[0]);
+  if (cx.ev[1]) cudaEventDestroy(cx.ev[1]);
+  for (cudaEvent_t e : cx.ev_pool) cudaEventDestroy(e);
+  cx.ev_pool.clear();
+  cx.d_waves = nullptr; cx.d_counters = nullptr; cx.stream = nullptr; cx.ev[0] = nullptr; cx.ev[1] = nullptr;
+}
+
+// Context k of the scene (0 = the scene's own), created on first use.
+int get_ctx(b200rt_scene* sc, int k, WaveCtx** out) {
+  if (k == 0) { *out = &sc->c0; return B200RT_OK; }
+  while ((int)sc->more.size() < k) {
+    WaveCtx* cx = new WaveCtx();
+    const int rc = ctx_init(*cx);
+    if (rc) { ctx_destroy(*cx); delete cx; return rc; }
+    sc->more.push_back(cx);
+  }
+  *out = sc->more[(size_t)k - 1];
   return B200RT_OK;
 }
 
@@ -158,12 +210,14 @@ struct Timers {
   }
 };
 
-// k_trace_wide<ANY, TRI_MODE, MINB> on the scene's stream, one persistent CTA set per SM
-void launch_wide(b200rt_scene* sc, bool any, bool mode7, int d) {
+// k_trace_wide<ANY, TRI_MODE, MINB> on the context's stream, one persistent CTA set per SM
+void launch_wide(b200rt_scene* sc, WaveCtx& cx, bool any, bool mode7, int d) {
   const int mb = sc->wide_blocks;
   const int grid = sc->sm_count * mb;
-  cudaStream_t st = sc->stream;
-#define LW(A, M, B) k_trace_wide<A, M, B><<<grid, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters)
+  cudaStream_t st = cx.stream;
+  if (any) k_top_mask<true><<<sc->sm_count * 8, 256, 0, st>>>(sc->S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
+  else k_top_mask<false><<<sc->sm_count * 8, 256, 0, st>>>(sc->S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
+#define LW(A, M, B) k_trace_wide<A, M, B><<<grid, RT_BLOCK, 0, st>>>(sc->S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters)
 #define LWB(A, M) do { if (mb == 4) LW(A, M, 4); else if (mb == 8) LW(A, M, 8); else LW(A, M, 6); } while (0)
   if (any) { if (mode7) LWB(true, 7); else LWB(true, 2); }
   else { if (mode7) LWB(false, 7); else LWB(false, 2); }
@@ -171,18 +225,18 @@ void launch_wide(b200rt_scene* sc, bool any, bool mode7, int d) {
 #undef LW
 }
 
-Timers make_timers(b200rt_scene* sc, bool on) {
+Timers make_timers(WaveCtx& cx, bool on) {
   Timers tm;
-  tm.pool = &sc->ev_pool; tm.used = 0; tm.s = sc->stream; tm.on = on;
+  tm.pool = &cx.ev_pool; tm.used = 0; tm.s = cx.stream; tm.on = on;
   return tm;
 }
 
-// Runs the wave loop for paths already placed in wave 0 by k_generate / k_import_rays.
+// Runs the wave loop of context cx for paths already placed in its wave 0 by k_generate / k_import_rays.
 // primary_only: stop after the first extend (parity hooks).
-int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading, Timers& tm, int* launches,
+int run_waves(b200rt_scene* sc, WaveCtx& cx, bool exact, bool primary_only, bool with_shading, Timers& tm, int* launches,
               int* waves_run) {
   const DScene& S = sc->S;
-  cudaStream_t st = sc->stream;
+  cudaStream_t st = cx.stream;
   const int grid_p = sc->sm_count * (RT_FAST_MIN_BLOCKS > 8 ? RT_FAST_MIN_BLOCKS : 8);  // persistent traversal grid: resident CTAs of 128 threads per SM
   const int grid_s = sc->sm_count * 8;
   const bool hw1 = S.semantics == B200RT_SEM_HW1;
@@ -192,22 +246,22 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
   int d_last = 0;
   // wave bookkeeping: one <<<1,1>>> launch per depth (k_finish_wave also opens the next wave); the shadow-queue clamp
   // is done by the traversal kernel itself on the wide path
-  k_next_wave<<<1, 1, 0, st>>>(sc->d_waves, 0, sc->d_counters);
+  k_next_wave<<<1, 1, 0, st>>>(cx.d_waves, 0, cx.d_counters);
   (*launches)++;
   for (int d = 0; d <= max_d; d++) {
     const bool hw1_fast = hw1 && S.hw1_fast_root != B200RT_REF_NONE && !exact;
     if (hw1_fast) {
-      k_trace_hw1_fast<false><<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+      k_trace_hw1_fast<false><<<grid_s, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
     } else if (hw1) {
-      k_extend_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
+      k_extend_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.d_waves, d, cx.d_counters);
     } else if (wide) {
-      launch_wide(sc, false, mode7, d);
+      launch_wide(sc, cx, false, mode7, d);
     } else if (mode7) {
-      if (exact) k_extend<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
-      else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+      if (exact) k_extend<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.d_waves, d, cx.d_counters);
+      else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
     } else {
-      if (exact) k_extend<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_counters);
-      else k_trace_fast<false, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+      if (exact) k_extend<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.d_waves, d, cx.d_counters);
+      else k_trace_fast<false, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
     }
     (*launches)++;
     tm.mark(ST_EXTEND);
@@ -215,38 +269,38 @@ int run_waves(b200rt_scene* sc, bool exact, bool primary_only, bool with_shading
     if (!with_shading) break;
     const bool hw7 = S.semantics >= B200RT_SEM_HW5;  // HW5/HW6 shade like HW7's ray-tracing mode (flags inside)
     const bool hw4 = S.semantics == B200RT_SEM_HW4;
-    if (hw7) k_shade7_a<<<grid_s * RT_BLOCK / RT_SHADE7_BLOCK, RT_SHADE7_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
-    else if (hw4) k_shade4_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
-    else k_shade_a<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+    if (hw7) k_shade7_a<<<grid_s * RT_BLOCK / RT_SHADE7_BLOCK, RT_SHADE7_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
+    else if (hw4) k_shade4_a<<<grid_s, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
+    else k_shade_a<<<grid_s, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
     (*launches)++;
-    if (!wide) { k_clamp_shadow_count<<<1, 1, 0, st>>>(sc->Q, sc->d_counters); (*launches)++; }
+    if (!wide) { k_clamp_shadow_count<<<1, 1, 0, st>>>(cx.Q, cx.d_counters); (*launches)++; }
     tm.mark(ST_SHADE);
     if (hw1_fast) {
-      k_trace_hw1_fast<true><<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+      k_trace_hw1_fast<true><<<grid_s, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
     } else if (hw1) {
-      k_shadow_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
+      k_shadow_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, cx.Q, cx.d_counters);
     } else if (wide) {
-      launch_wide(sc, true, mode7, d);
+      launch_wide(sc, cx, true, mode7, d);
     } else if (mode7) {
-      if (exact) k_shadow<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
-      else k_trace_fast<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+      if (exact) k_shadow<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.Q, cx.d_counters);
+      else k_trace_fast<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
     } else {
-      if (exact) k_shadow<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->Q, sc->d_counters);
-      else k_trace_fast<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+      if (exact) k_shadow<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.Q, cx.d_counters);
+      else k_trace_fast<true, 2><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
     }
     (*launches)++;
     tm.mark(ST_SHADOW);
-    if (hw7) k_shade7_b<<<grid_s * RT_BLOCK / RT_SHADE7_BLOCK, RT_SHADE7_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
-    else if (hw4) k_shade4_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
-    else k_shade_b<<<grid_s, RT_BLOCK, 0, st>>>(S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
-    k_finish_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->P, sc->d_counters);
+    if (hw7) k_shade7_b<<<grid_s * RT_BLOCK / RT_SHADE7_BLOCK, RT_SHADE7_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
+    else if (hw4) k_shade4_b<<<grid_s, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
+    else k_shade_b<<<grid_s, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
+    k_finish_wave<<<1, 1, 0, st>>>(cx.d_waves, d, cx.P, cx.d_counters);
     (*launches) += 2;
     tm.mark(ST_SHADE);
   }
   if (with_shading) {
     for (int d = d_last; d >= 0; d--) {
-      if (S.semantics >= B200RT_SEM_HW5) k_combine7<<<grid_s, 256, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_accum);
-      else k_combine<<<grid_s, 256, 0, st>>>(S, sc->P, sc->d_waves, d, sc->d_accum);
+      if (S.semantics >= B200RT_SEM_HW5) k_combine7<<<grid_s, 256, 0, st>>>(S, cx.P, cx.d_waves, d, sc->d_accum);
+      else k_combine<<<grid_s, 256, 0, st>>>(S, cx.P, cx.d_waves, d, sc->d_accum);
       (*launches)++;
     }
     tm.mark(ST_SHADE);
@@ -296,7 +350,24 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
   const size_t pixels = (size_t)c.width * c.height;
   int rc = ensure_accum(sc, pixels);
   if (rc) return rc;
-  cudaStream_t st = sc->stream;
+
+  // The rows of the frame are cut into K contiguous bands (multiples of 4 rows: k_generate's 8x4 tiles), one per
+  // wavefront context; each band runs its own generate -> (extend -> shade_a -> shadow -> shade_b)* -> combine train on
+  // its own stream.  Results do not depend on K: every sample's random stream is keyed by its pixel.
+  int K = (opts && opts->contexts > 0) ? opts->contexts : sc->n_ctx;
+  if (K > kMaxCtx) K = kMaxCtx;
+  while (K > 1 && R.n_rows < 16 * K) K--;
+  WaveCtx* cxs[kMaxCtx];
+  for (int k = 0; k < K; k++) {
+    rc = get_ctx(sc, k, &cxs[k]);
+    if (rc) return rc;
+  }
+  int band_begin[kMaxCtx + 1];
+  for (int k = 0; k <= K; k++) {
+    int b = (int)((long long)R.n_rows * k / K);
+    if (k > 0 && k < K) b &= ~3;
+    band_begin[k] = b;
+  }
 
   // batches of pixel rows so that the vertex pool stays bounded.  The recursion is a TREE
   // (mirror + two dielectric children + the path tracer's hemisphere sample), so the pool is
@@ -305,11 +376,13 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
   const size_t paths_per_row = (size_t)c.width * R.sample_count;
   const size_t fan = (sc->has_mirror ? 1 : 0) + (sc->has_transparency ? 2 : 0) + (sc->S.integrator ? 1 : 0);
   const size_t growth = 1 + (size_t)sc->S.max_depth * (fan > 1 ? fan : 1);
-  const size_t max_paths = (size_t)16 << 20;  // 16 Mi camera paths per batch
+  const size_t max_paths = ((size_t)16 << 20) / (size_t)K;  // 16 Mi camera paths per batch over all contexts
   size_t rows_per_batch = max_paths / (paths_per_row ? paths_per_row : 1);
   if (rows_per_batch < 1) rows_per_batch = 1;
   if (rows_per_batch >= 4) rows_per_batch &= ~(size_t)3;  // keeps k_generate's 8x4 tiling available
-  if (rows_per_batch > (size_t)R.n_rows) rows_per_batch = R.n_rows;
+  int max_band = 0;
+  for (int k = 0; k < K; k++) max_band = std::max(max_band, band_begin[k + 1] - band_begin[k]);
+  if (rows_per_batch > (size_t)max_band) rows_per_batch = (size_t)max_band;
   const size_t nl = (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1);
   {
     const size_t batch_paths = rows_per_batch * paths_per_row;
@@ -321,40 +394,73 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
       return B200RT_E_UNSUPPORTED;
     }
     const size_t per_wave = batch_paths * (fan > 1 ? 2 * fan : 1);
-    rc = ensure_pool(sc, slots, per_wave * nl + 1024);
-    if (rc) return rc;
+    for (int k = 0; k < K; k++) {
+      rc = ensure_pool(sc, *cxs[k], slots, per_wave * nl + 1024);
+      if (rc) return rc;
+    }
   }
 
-  Timers tm = make_timers(sc, stats != nullptr);
+  WaveCtx& c0 = sc->c0;
+  Timers tms[kMaxCtx];
+  for (int k = 0; k < K; k++) tms[k] = make_timers(*cxs[k], stats != nullptr);
   int launches = 0, waves_total = 0;
   Counters hc;
   for (int attempt = 0;; attempt++) {
-    CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), st));
-    CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
+    CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), c0.stream));
     launches = 0; waves_total = 0;
-    tm.reset();
-    cudaEventRecord(sc->ev[0], st);
-    tm.mark(ST_GENERATE);
-    for (int r0 = 0; r0 < R.n_rows; r0 += (int)rows_per_batch) {
-      RenderParams B = R;
-      const int nr = (int)((size_t)(R.n_rows - r0) < rows_per_batch ? (R.n_rows - r0) : rows_per_batch);
-      B.row_begin = R.row_begin + r0 * R.row_stride;
-      B.n_rows = nr;
-      B.n_paths = (uint32_t)((size_t)nr * paths_per_row);
-      k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, B, sc->d_waves, sc->d_counters);
-      launches++;
-      tm.mark(ST_GENERATE);
-      int wr = 0;
-      rc = run_waves(sc, exact, false, true, tm, &launches, &wr);
-      if (rc) return rc;
-      waves_total += wr;
+    CK(cudaEventRecord(c0.ev[0], c0.stream));   // the fork: every context starts after the frame buffer is cleared
+    for (int k = 0; k < K; k++) {
+      WaveCtx& cx = *cxs[k];
+      if (k > 0) CK(cudaStreamWaitEvent(cx.stream, c0.ev[0], 0));
+      CK(cudaMemsetAsync(cx.d_counters, 0, sizeof(Counters), cx.stream));
+      tms[k].reset();
+      tms[k].mark(ST_GENERATE);
     }
-    cudaEventRecord(sc->ev[1], st);
-    CK(cudaStreamSynchronize(st));
-    CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
+    // batch b of every context is issued before batch b+1 of any: the streams fill evenly from one host thread
+    int r0s[kMaxCtx];
+    for (int k = 0; k < K; k++) r0s[k] = band_begin[k];
+    for (bool any = true; any;) {
+      any = false;
+      for (int k = 0; k < K; k++) {
+        if (r0s[k] >= band_begin[k + 1]) continue;
+        any = true;
+        WaveCtx& cx = *cxs[k];
+        RenderParams B = R;
+        const int left = band_begin[k + 1] - r0s[k];
+        const int nr = (size_t)left < rows_per_batch ? left : (int)rows_per_batch;
+        B.row_begin = R.row_begin + r0s[k] * R.row_stride;
+        B.n_rows = nr;
+        B.n_paths = (uint32_t)((size_t)nr * paths_per_row);
+        k_generate<<<sc->sm_count * 8, 256, 0, cx.stream>>>(sc->S, cx.P, B, cx.d_waves, cx.d_counters);
+        launches++;
+        tms[k].mark(ST_GENERATE);
+        int wr = 0;
+        rc = run_waves(sc, cx, exact, false, true, tms[k], &launches, &wr);
+        if (rc) return rc;
+        waves_total += wr;
+        r0s[k] += nr;
+      }
+    }
+    for (int k = 1; k < K; k++) {   // the join: context 0 waits for the others
+      CK(cudaEventRecord(cxs[k]->ev[1], cxs[k]->stream));
+      CK(cudaStreamWaitEvent(c0.stream, cxs[k]->ev[1], 0));
+    }
+    CK(cudaEventRecord(c0.ev[1], c0.stream));
+    CK(cudaStreamSynchronize(c0.stream));
+    memset(&hc, 0, sizeof(hc));
+    for (int k = 0; k < K; k++) {
+      Counters one;
+      CK(cudaMemcpy(&one, cxs[k]->d_counters, sizeof(one), cudaMemcpyDeviceToHost));
+      hc.rays_primary += one.rays_primary; hc.rays_shadow += one.rays_shadow; hc.rays_secondary += one.rays_secondary;
+      hc.nodes_visited += one.nodes_visited; hc.tris_tested += one.tris_tested; hc.spheres_tested += one.spheres_tested;
+      hc.instances_entered += one.instances_entered;
+      hc.sh_nodes_visited += one.sh_nodes_visited; hc.sh_tris_tested += one.sh_tris_tested;
+      hc.sh_spheres_tested += one.sh_spheres_tested; hc.sh_instances_entered += one.sh_instances_entered;
+      if (one.overflow > hc.overflow) hc.overflow = one.overflow;
+    }
     if (!hc.overflow) break;
     if (hc.overflow == 2) {
-      b200rt_internal_set_error("traversal stack overflow (BVH deeper than RT_FSTACK)");
+      b200rt_internal_set_error("traversal stack overflow (BVH deeper than the traversal stack)");
       return B200RT_E_UNSUPPORTED;
     }
     if (rows_per_batch <= 1 || attempt >= 8) {
@@ -372,14 +478,20 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
     stats->instances_entered = hc.instances_entered;
     stats->sh_nodes_visited = hc.sh_nodes_visited; stats->sh_tris_tested = hc.sh_tris_tested;
     stats->sh_spheres_tested = hc.sh_spheres_tested; stats->sh_instances_entered = hc.sh_instances_entered;
-    float ms[ST_COUNT];
-    tm.collect(ms);
-    stats->ms_generate = ms[ST_GENERATE]; stats->ms_extend = ms[ST_EXTEND];
-    stats->ms_shade = ms[ST_SHADE]; stats->ms_shadow = ms[ST_SHADOW];
-    cudaEventElapsedTime(&stats->ms_total, sc->ev[0], sc->ev[1]);
+    // stage times: event intervals on each context's own stream, summed over the contexts.  With more than one
+    // context the intervals of different streams overlap in time (that is the point), so their sum exceeds ms_total;
+    // a one-context render (opts->contexts = 1) gives the serial per-kernel times the roofline is quoted on.
+    for (int k = 0; k < K; k++) {
+      float ms[ST_COUNT];
+      tms[k].collect(ms);
+      stats->ms_generate += ms[ST_GENERATE]; stats->ms_extend += ms[ST_EXTEND];
+      stats->ms_shade += ms[ST_SHADE]; stats->ms_shadow += ms[ST_SHADOW];
+    }
+    cudaEventElapsedTime(&stats->ms_total, c0.ev[0], c0.ev[1]);
     stats->waves = waves_total; stats->launches = launches;
     stats->node_bytes = (sc->S.use_wide && !exact && sc->S.semantics != B200RT_SEM_HW1) ? 80 : 64;
     stats->top_objects = exact ? 0 : sc->S.n_top;
+    stats->contexts = K;
   }
   return B200RT_OK;
 }
@@ -438,7 +550,7 @@ int ppm_ensure_rtab(b200rt_scene* sc) {
 
 extern "C" {
 
-int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200PpmStats* stats) {
+int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200PpmStats* stats) try {
   if (!sc || camera_index < 0 || camera_index >= (int)sc->cameras.size() || sc->S.semantics != B200RT_SEM_PPM) {
     b200rt_internal_set_error("b200rt_ppm_eye_pass: needs a PPM scene and a valid camera index");
     return B200RT_E_INVALID;
@@ -448,7 +560,7 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
   sc->ppm_camera = camera_index;
   const b200rt_camera& c = sc->S.cam;
   if (sc->S.max_depth + 2 > kMaxWaves) return B200RT_E_UNSUPPORTED;
-  cudaStream_t st = sc->stream;
+  cudaStream_t st = sc->c0.stream;
   RenderParams R;
   B200RenderOpts o;
   memset(&o, 0, sizeof(o));
@@ -459,7 +571,7 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
   // every glass vertex can fork: size for one fork per path and level, detect overflow otherwise
   const size_t slots = paths * (size_t)(1 + (sc->has_transparency ? 2 * sc->S.max_depth : sc->S.max_depth)) + 1024;
   if (slots > 0xF0000000ull) return B200RT_E_UNSUPPORTED;
-  int rc = ensure_pool(sc, slots, 1024);
+  int rc = ensure_pool(sc, sc->c0, slots, 1024);
   if (rc) return rc;
   rc = ppm_ensure_hit_points(sc, slots);
   if (rc) return rc;
@@ -471,27 +583,27 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
   for (int i = 0; i < 3; i++) { hpc.bbox[i] = 0xffffffffu; hpc.bbox[3 + i] = 0u; }
   CK(cudaMemcpyAsync(sc->d_pc, &hpc, sizeof(hpc), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(sc->HP.count, 0, sizeof(unsigned int), st));
-  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
+  CK(cudaMemsetAsync(sc->c0.d_counters, 0, sizeof(Counters), st));
   const int grid_p = sc->sm_count * (RT_FAST_MIN_BLOCKS > 8 ? RT_FAST_MIN_BLOCKS : 8);
   int launches = 0;
   cudaEvent_t e0, e1, e2;
   cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
   cudaEventRecord(e0, st);
-  k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, R, sc->d_waves, sc->d_counters);
+  k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->c0.P, R, sc->c0.d_waves, sc->c0.d_counters);
   launches++;
-  k_next_wave<<<1, 1, 0, st>>>(sc->d_waves, 0, sc->d_counters);
+  k_next_wave<<<1, 1, 0, st>>>(sc->c0.d_waves, 0, sc->c0.d_counters);
   launches++;
   for (int d = 0; d <= sc->S.max_depth; d++) {
-    if (sc->S.use_wide) launch_wide(sc, false, true, d);
-    else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
-    k_ppm_eye_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->d_waves, d, sc->HP, sc->d_counters, sc->d_pc);
-    k_finish_wave<<<1, 1, 0, st>>>(sc->d_waves, d, sc->P, sc->d_counters);
+    if (sc->S.use_wide) launch_wide(sc, sc->c0, false, true, d);
+    else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.Q, sc->c0.d_waves, d, sc->c0.d_counters);
+    k_ppm_eye_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.d_waves, d, sc->HP, sc->c0.d_counters, sc->d_pc);
+    k_finish_wave<<<1, 1, 0, st>>>(sc->c0.d_waves, d, sc->c0.P, sc->c0.d_counters);
     launches += 3;
   }
   cudaEventRecord(e1, st);
   CK(cudaStreamSynchronize(st));
   Counters hc;
-  CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&hc, sc->c0.d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&hpc, sc->d_pc, sizeof(hpc), cudaMemcpyDeviceToHost));
   unsigned int n_hp = 0;
   CK(cudaMemcpy(&n_hp, sc->HP.count, sizeof(n_hp), cudaMemcpyDeviceToHost));
@@ -558,9 +670,9 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   return B200RT_OK;
-}
+} B200RT_CATCH
 
-int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmStats* stats) {
+int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmStats* stats) try {
   if (!sc || !opts || opts->photons < 0 || sc->S.semantics != B200RT_SEM_PPM || sc->ppm_camera < 0) {
     b200rt_internal_set_error("b200rt_ppm_trace_photons: call b200rt_ppm_eye_pass on a PPM scene first");
     return B200RT_E_INVALID;
@@ -570,19 +682,19 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
     return B200RT_E_INVALID;
   }
   CK(cudaSetDevice(sc->device));
-  cudaStream_t st = sc->stream;
+  cudaStream_t st = sc->c0.stream;
   const size_t batch = (size_t)8 << 20;  // photons per wavefront batch
-  int rc = ensure_pool(sc, 2 * batch + 1024, 1024);
+  int rc = ensure_pool(sc, sc->c0, 2 * batch + 1024, 1024);
   if (rc) return rc;
-  const uint32_t half = (uint32_t)(sc->P.capacity / 2);
+  const uint32_t half = (uint32_t)(sc->c0.P.capacity / 2);
   const uint32_t s0 = rng_mix((uint32_t)opts->seed, (uint32_t)(opts->seed >> 32));
   const int grid_p = sc->sm_count * (RT_FAST_MIN_BLOCKS > 8 ? RT_FAST_MIN_BLOCKS : 8);
   PpmCounters hpc0, hpc1;
   CK(cudaMemcpy(&hpc0, sc->d_pc, sizeof(hpc0), cudaMemcpyDeviceToHost));
-  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
-  Timers tm = make_timers(sc, stats != nullptr);
+  CK(cudaMemsetAsync(sc->c0.d_counters, 0, sizeof(Counters), st));
+  Timers tm = make_timers(sc->c0, stats != nullptr);
   int launches = 0;
-  cudaEventRecord(sc->ev[0], st);
+  cudaEventRecord(sc->c0.ev[0], st);
   tm.mark(ST_GENERATE);
   for (int64_t done = 0; done < opts->photons && sc->S.max_depth > 1; done += (int64_t)batch) {
     const uint32_t n = (uint32_t)((opts->photons - done) < (int64_t)batch ? (opts->photons - done) : (int64_t)batch);
@@ -611,29 +723,29 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
       order = sc->d_sort[3];
       launches += 3;
     }
-    k_ppm_emit<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, sc->d_waves, s0, opts->first_photon + (uint64_t)done, n,
+    k_ppm_emit<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->c0.P, sc->c0.d_waves, s0, opts->first_photon + (uint64_t)done, n,
                                                  order);
     launches++;
     tm.mark(ST_GENERATE);
     for (int d = 0; d + 1 < sc->S.max_depth; d++) {
-      k_ppm_next_wave<<<1, 1, 0, st>>>(sc->d_waves, d, half, sc->d_counters);
-      k_ppm_count_rays<<<1, 1, 0, st>>>(sc->d_waves, d, sc->d_pc);
-      if (sc->S.use_wide) launch_wide(sc, false, true, d);
-      else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->Q, sc->d_waves, d, sc->d_counters);
+      k_ppm_next_wave<<<1, 1, 0, st>>>(sc->c0.d_waves, d, half, sc->c0.d_counters);
+      k_ppm_count_rays<<<1, 1, 0, st>>>(sc->c0.d_waves, d, sc->d_pc);
+      if (sc->S.use_wide) launch_wide(sc, sc->c0, false, true, d);
+      else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.Q, sc->c0.d_waves, d, sc->c0.d_counters);
       tm.mark(ST_EXTEND);
-      k_ppm_photon_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->P, sc->d_waves, d, sc->HP, sc->G,
-                                                                sc->d_counters, sc->d_pc);
+      k_ppm_photon_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.d_waves, d, sc->HP, sc->G,
+                                                                sc->c0.d_counters, sc->d_pc);
       tm.mark(ST_SHADE);
       launches += 4;
     }
   }
-  cudaEventRecord(sc->ev[1], st);
+  cudaEventRecord(sc->c0.ev[1], st);
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   if (stats) {
     CK(cudaMemcpy(&hpc1, sc->d_pc, sizeof(hpc1), cudaMemcpyDeviceToHost));
     Counters hc;
-    CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&hc, sc->c0.d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
     memset(stats, 0, sizeof(*stats));
     stats->hit_points = sc->n_hp; stats->photons = (uint64_t)opts->photons;
     stats->photon_rays = hpc1.photon_rays - hpc0.photon_rays;
@@ -643,33 +755,33 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
     float ms[ST_COUNT];
     tm.collect(ms);
     stats->ms_extend = ms[ST_EXTEND]; stats->ms_deposit = ms[ST_SHADE];
-    cudaEventElapsedTime(&stats->ms_photon, sc->ev[0], sc->ev[1]);
+    cudaEventElapsedTime(&stats->ms_photon, sc->c0.ev[0], sc->c0.ev[1]);
     stats->initial_radius = sc->G.r0;
     stats->launches = launches;
     stats->node_bytes = sc->S.use_wide ? 80 : 64;
     stats->top_objects = sc->S.n_top;
   }
   return B200RT_OK;
-}
+} B200RT_CATCH
 
-int b200rt_ppm_export(b200rt_scene* sc, float** d_S_n, int64_t* n_hit_points) {
+int b200rt_ppm_export(b200rt_scene* sc, float** d_S_n, int64_t* n_hit_points) try {
   if (!sc || !d_S_n || sc->ppm_camera < 0) return B200RT_E_INVALID;
   CK(cudaSetDevice(sc->device));
-  if (sc->n_hp) k_ppm_export<<<sc->sm_count * 4, 256, 0, sc->stream>>>(sc->HP, sc->n_hp, sc->d_export);
-  CK(cudaStreamSynchronize(sc->stream));
+  if (sc->n_hp) k_ppm_export<<<sc->sm_count * 4, 256, 0, sc->c0.stream>>>(sc->HP, sc->n_hp, sc->d_export);
+  CK(cudaStreamSynchronize(sc->c0.stream));
   *d_S_n = reinterpret_cast<float*>(sc->d_export);
   if (n_hit_points) *n_hit_points = sc->n_hp;
   return B200RT_OK;
-}
+} B200RT_CATCH
 
-int b200rt_ppm_density_from(b200rt_scene* sc, const float* d_S_n, double total, float* rgbw_out) {
+int b200rt_ppm_density_from(b200rt_scene* sc, const float* d_S_n, double total, float* rgbw_out) try {
   if (!sc || !rgbw_out || sc->ppm_camera < 0 || (!d_S_n && sc->n_hp)) return B200RT_E_INVALID;
   CK(cudaSetDevice(sc->device));
   const b200rt_camera& c = sc->cameras[sc->ppm_camera];
   const size_t pixels = (size_t)c.width * c.height;
   int rc = ensure_accum(sc, pixels);
   if (rc) return rc;
-  cudaStream_t st = sc->stream;
+  cudaStream_t st = sc->c0.stream;
   CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), st));
   if (sc->n_hp)
     k_ppm_density<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, sc->n_hp, reinterpret_cast<const float4*>(d_S_n), sc->G.r0sq,
@@ -678,16 +790,16 @@ int b200rt_ppm_density_from(b200rt_scene* sc, const float* d_S_n, double total, 
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   return B200RT_OK;
-}
+} B200RT_CATCH
 
-int b200rt_ppm_density(b200rt_scene* sc, double total, float* rgbw_out) {
+int b200rt_ppm_density(b200rt_scene* sc, double total, float* rgbw_out) try {
   float* p = nullptr;
   int rc = b200rt_ppm_export(sc, &p, nullptr);
   if (rc) return rc;
   return b200rt_ppm_density_from(sc, p, total, rgbw_out);
-}
+} B200RT_CATCH
 
-int b200rt_ppm_get_hit_points(b200rt_scene* sc, float* out16, int64_t capacity, int64_t* n_out) {
+int b200rt_ppm_get_hit_points(b200rt_scene* sc, float* out16, int64_t capacity, int64_t* n_out) try {
   if (!sc || sc->ppm_camera < 0) return B200RT_E_INVALID;
   CK(cudaSetDevice(sc->device));
   if (n_out) *n_out = sc->n_hp;
@@ -695,22 +807,22 @@ int b200rt_ppm_get_hit_points(b200rt_scene* sc, float* out16, int64_t capacity, 
   const uint32_t n = (uint32_t)((int64_t)sc->n_hp < capacity ? (int64_t)sc->n_hp : capacity);
   float* d = nullptr;
   CK(cudaMalloc((void**)&d, sizeof(float) * 16 * (size_t)n));
-  k_ppm_pack_hit_points<<<sc->sm_count * 4, 256, 0, sc->stream>>>(sc->HP, n, d);
-  CK(cudaMemcpyAsync(out16, d, sizeof(float) * 16 * (size_t)n, cudaMemcpyDeviceToHost, sc->stream));
-  CK(cudaStreamSynchronize(sc->stream));
+  k_ppm_pack_hit_points<<<sc->sm_count * 4, 256, 0, sc->c0.stream>>>(sc->HP, n, d);
+  CK(cudaMemcpyAsync(out16, d, sizeof(float) * 16 * (size_t)n, cudaMemcpyDeviceToHost, sc->c0.stream));
+  CK(cudaStreamSynchronize(sc->c0.stream));
   cudaFree(d);
   return B200RT_OK;
-}
+} B200RT_CATCH
 
-int b200rt_device_count(void) {
+int b200rt_device_count(void) try {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   return n;
-}
+} B200RT_CATCH
 
 const char* b200rt_version(void) { return "b200rt 0.1 (sm_100a)"; }
 
-int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) {
+int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) try {
   if (!d || !out) {
     b200rt_internal_set_error("b200rt_scene_create: null argument");
     return B200RT_E_INVALID;
@@ -733,12 +845,16 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   }
   CK(cudaSetDevice(device));
   b200rt_scene* sc = new b200rt_scene();
+  struct Guard {   // every early return below releases what has been allocated so far
+    b200rt_scene* p;
+    ~Guard() { if (p) b200rt_scene_destroy(p); }
+  } guard{sc};
+  sc->c0.d_waves = nullptr; sc->c0.d_counters = nullptr; sc->c0.stream = nullptr; sc->c0.ev[0] = nullptr; sc->c0.ev[1] = nullptr;
   memset(&sc->S, 0, sizeof(DScene));
-  memset(&sc->P, 0, sizeof(Pool));
-  memset(&sc->Q, 0, sizeof(ShadowQueue));
+  memset(&sc->c0.P, 0, sizeof(Pool));
+  memset(&sc->c0.Q, 0, sizeof(ShadowQueue));
   sc->device = device;
   sc->d_accum = nullptr; sc->accum_pixels = 0;
-  sc->d_waves = nullptr; sc->d_counters = nullptr;
   memset(&sc->HP, 0, sizeof(HitPoints));
   memset(&sc->G, 0, sizeof(PpmGrid));
   sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
@@ -765,7 +881,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   do {                                                                     \
     T* p_ = nullptr;                                                       \
     rc = upload<T>((const T*)(src), (size_t)(n), &p_);                     \
-    if (rc) { b200rt_scene_destroy(sc); return rc; }                       \
+    if (rc) return rc;                                                     \
     sc->allocs.push_back(p_);                                              \
     dst = reinterpret_cast<decltype(dst)>(p_);                             \
     bytes += (size_t)(n) * sizeof(T);                                      \
@@ -789,7 +905,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     // 12 floats per triangle -> 3 float4 (same bytes)
     float* p = nullptr;
     rc = upload<float>(d->tri_geom, (size_t)d->n_tris * 12, &p);
-    if (rc) { b200rt_scene_destroy(sc); return rc; }
+    if (rc) return rc;
     sc->allocs.push_back(p);
     S.tris = reinterpret_cast<const float4*>(p);
     bytes += (size_t)d->n_tris * 48;
@@ -938,35 +1054,29 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     const float* mr = d->materials[i].mirror;
     if (mr[0] != 0.f || mr[1] != 0.f || mr[2] != 0.f) sc->has_mirror = true;
   }
-  CK(cudaMalloc((void**)&sc->d_waves, sizeof(WaveInfo) * (kMaxWaves + 2)));
-  CK(cudaMalloc((void**)&sc->d_counters, sizeof(Counters)));
-  CK(cudaMemset(sc->d_waves, 0, sizeof(WaveInfo) * (kMaxWaves + 2)));
-  CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
-  CK(cudaEventCreate(&sc->ev[0]));
-  CK(cudaEventCreate(&sc->ev[1]));
+  rc = ctx_init(sc->c0);
+  if (rc) return rc;
+  sc->n_ctx = kDefaultCtx;
+  if (const char* e = getenv("B200RT_CONTEXTS")) sc->n_ctx = std::max(1, std::min(kMaxCtx, atoi(e)));
+  guard.p = nullptr;
   *out = sc;
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 void b200rt_scene_destroy(b200rt_scene* sc) {
   if (!sc) return;
   cudaSetDevice(sc->device);
-  pool_free(sc);
+  ctx_destroy(sc->c0);
+  for (WaveCtx* cx : sc->more) { ctx_destroy(*cx); delete cx; }
   for (void* p : sc->allocs)
     if (p) cudaFree(p);
   ppm_free(sc);
   if (sc->d_accum) cudaFree(sc->d_accum);
-  if (sc->d_waves) cudaFree(sc->d_waves);
-  if (sc->d_counters) cudaFree(sc->d_counters);
-  if (sc->stream) cudaStreamDestroy(sc->stream);
-  if (sc->ev[0]) cudaEventDestroy(sc->ev[0]);
-  if (sc->ev[1]) cudaEventDestroy(sc->ev[1]);
-  for (cudaEvent_t e : sc->ev_pool) cudaEventDestroy(e);
   delete sc;
 }
 
 int b200rt_tonemap_photographic(b200rt_scene* sc, int camera_index, float key, float burn_percent, float saturation,
-                                uint8_t* rgb8_out) {
+                                uint8_t* rgb8_out) try {
   if (!sc || !rgb8_out || camera_index < 0 || camera_index >= (int)sc->cameras.size() || !sc->d_accum) {
     b200rt_internal_set_error("b200rt_tonemap_photographic: render the camera first");
     return B200RT_E_INVALID;
@@ -975,7 +1085,7 @@ int b200rt_tonemap_photographic(b200rt_scene* sc, int camera_index, float key, f
   const b200rt_camera& c = sc->cameras[camera_index];
   const uint32_t n = (uint32_t)c.width * (uint32_t)c.height;
   if (n == 0 || n > sc->accum_pixels) return B200RT_E_INVALID;
-  cudaStream_t st = sc->stream;
+  cudaStream_t st = sc->c0.stream;
   float* d_f = nullptr;        // lum | scaled | keys | sorted
   double* d_sum = nullptr;
   unsigned char* d_rgb = nullptr;
@@ -1009,11 +1119,11 @@ int b200rt_tonemap_photographic(b200rt_scene* sc, int camera_index, float key, f
   if (d_rgb) cudaFree(d_rgb);
   if (d_tmp) cudaFree(d_tmp);
   return rc;
-}
+} B200RT_CATCH
 
-int b200rt_debug_pool(b200rt_scene* sc, int field, void* out, int64_t count) {
-  if (!sc || !out || count < 0 || (uint64_t)count > sc->P.capacity) return B200RT_E_INVALID;
-  const Pool& P = sc->P;
+int b200rt_debug_pool(b200rt_scene* sc, int field, void* out, int64_t count) try {
+  if (!sc || !out || count < 0 || (uint64_t)count > sc->c0.P.capacity) return B200RT_E_INVALID;
+  const Pool& P = sc->c0.P;
   const void* src[] = {P.ray_o, P.ray_d, P.hit_a, P.nrm, P.rec0, P.rec1, P.rec2, P.rec4, P.final_c, P.kd,
                        P.pixel, P.key, P.hit_b, P.rec3};
   const size_t esz[] = {16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 4, 4, 8, 4};
@@ -1021,9 +1131,9 @@ int b200rt_debug_pool(b200rt_scene* sc, int field, void* out, int64_t count) {
   CK(cudaSetDevice(sc->device));
   CK(cudaMemcpy(out, src[field], esz[field] * (size_t)count, cudaMemcpyDeviceToHost));
   return B200RT_OK;
-}
+} B200RT_CATCH
 
-void* b200rt_scene_stream(b200rt_scene* sc) { return sc ? (void*)sc->stream : nullptr; }
+void* b200rt_scene_stream(b200rt_scene* sc) { return sc ? (void*)sc->c0.stream : nullptr; }
 // Read-bandwidth probe ("L2 bandwidth is not in MEASURED_PEAKS.json, the builder must measure it").
 // Every thread streams 16-byte loads over `bytes` of device memory `iters` times; a working set below the
 // 126 MB L2 measures L2, one far above it HBM.  The sum is written so the loads cannot be dropped.
@@ -1041,7 +1151,7 @@ __global__ void __launch_bounds__(256) k_read_probe(const uint4* __restrict__ sr
   if (acc == 0x9e3779b9u) *sink = acc;
 }
 
-int b200rt_measure_read_bandwidth(int device, uint64_t bytes, int iters, double* gbs_out) {
+int b200rt_measure_read_bandwidth(int device, uint64_t bytes, int iters, double* gbs_out) try {
   if (!gbs_out || bytes < 4096 || iters < 1) {
     b200rt_internal_set_error("measure_read_bandwidth: bad argument");
     return B200RT_E_INVALID;
@@ -1070,7 +1180,7 @@ int b200rt_measure_read_bandwidth(int device, uint64_t bytes, int iters, double*
   cudaFree(buf); cudaFree(sink);
   *gbs_out = (double)n16 * 16.0 * iters / (ms * 1e-3) / 1e9;
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 // Leaf functions of the device path on caller-supplied inputs (tests/test_leaf_vectors.py feeds the known-answer
 // vectors produced by the reference's own functions).
@@ -1098,7 +1208,7 @@ __global__ void k_debug_leaf(int which, DScene S, b200rt_texture T, b200rt_brdf 
 }
 
 int b200rt_debug_leaf(int device, int which, const b200rt_texture* tex, const float* texels, int64_t n_texels,
-                      const b200rt_brdf* brdf, const float* in, int rows, int n_in, float* out, int n_out) {
+                      const b200rt_brdf* brdf, const float* in, int rows, int n_in, float* out, int n_out) try {
   if (which < 0 || which > 3 || !in || !out || rows <= 0 || n_in <= 0 || n_out <= 0) return B200RT_E_INVALID;
   CK(cudaSetDevice(device));
   DScene S;
@@ -1124,16 +1234,16 @@ int b200rt_debug_leaf(int device, int which, const b200rt_texture* tex, const fl
   CK(cudaMemcpy(out, d_out, (size_t)rows * n_out * 4, cudaMemcpyDeviceToHost));
   cudaFree(d_tex); cudaFree(d_in); cudaFree(d_out);
   return B200RT_OK;
-}
+} B200RT_CATCH
 
-int b200rt_scene_build_bvh_device(b200rt_scene* sc, float* ms_out) {
+int b200rt_scene_build_bvh_device(b200rt_scene* sc, float* ms_out) try {
   if (!sc) return B200RT_E_INVALID;
   if (sc->S.semantics == B200RT_SEM_HW1) {
     b200rt_internal_set_error("build_bvh_device: HW1 has no per-mesh trees");
     return B200RT_E_UNSUPPORTED;
   }
   CK(cudaSetDevice(sc->device));
-  cudaStream_t st = sc->stream;
+  cudaStream_t st = sc->c0.stream;
   const int n_meshes = sc->n_meshes;
   std::vector<b200rt_mesh> meshes((size_t)n_meshes);
   CK(cudaMemcpy(meshes.data(), sc->S.meshes, sizeof(b200rt_mesh) * n_meshes, cudaMemcpyDeviceToHost));
@@ -1210,20 +1320,20 @@ int b200rt_scene_build_bvh_device(b200rt_scene* sc, float* ms_out) {
   sc->S.fast_tri_ref = d_fref;
   sc->S.use_wide = 0;   // the device-built tree is binary: k_trace_fast walks it
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 uint64_t b200rt_scene_bytes(b200rt_scene* sc) { return sc ? (uint64_t)sc->scene_bytes : 0; }
 
 int b200rt_render_device(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, float** d_rgbw_out,
-                         B200RenderStats* stats) {
+                         B200RenderStats* stats) try {
   int rc = render_impl(sc, camera_index, opts, stats);
   if (rc) return rc;
   if (d_rgbw_out) *d_rgbw_out = reinterpret_cast<float*>(sc->d_accum);
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 int b200rt_render(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, float* rgbw_out,
-                  B200RenderStats* stats) {
+                  B200RenderStats* stats) try {
   if (!rgbw_out) {
     b200rt_internal_set_error("b200rt_render: null output");
     return B200RT_E_INVALID;
@@ -1233,10 +1343,10 @@ int b200rt_render(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts
   const b200rt_camera& c = sc->cameras[camera_index];
   CK(cudaMemcpy(rgbw_out, sc->d_accum, (size_t)c.width * c.height * sizeof(float4), cudaMemcpyDeviceToHost));
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 int b200rt_primary_ids(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, int32_t* ids_out,
-                       float* t_out) {
+                       float* t_out) try {
   if (!sc || !ids_out || !t_out || camera_index < 0 || camera_index >= (int)sc->cameras.size()) {
     b200rt_internal_set_error("b200rt_primary_ids: bad argument");
     return B200RT_E_INVALID;
@@ -1252,9 +1362,9 @@ int b200rt_primary_ids(b200rt_scene* sc, int camera_index, const B200RenderOpts*
   if (resolve_rows(c, opts, &R) != B200RT_OK) return B200RT_E_INVALID;
   R.n_paths = (uint32_t)((size_t)R.n_rows * c.width);
   const size_t pixels = (size_t)c.width * c.height;
-  int rc = ensure_pool(sc, R.n_paths + 1024, 1024);
+  int rc = ensure_pool(sc, sc->c0, R.n_paths + 1024, 1024);
   if (rc) return rc;
-  cudaStream_t st = sc->stream;
+  cudaStream_t st = sc->c0.stream;
   int32_t* d_ids = nullptr;
   float* d_t = nullptr;
   CK(cudaMalloc((void**)&d_ids, pixels * 2 * sizeof(int32_t)));
@@ -1265,31 +1375,31 @@ int b200rt_primary_ids(b200rt_scene* sc, int camera_index, const B200RenderOpts*
     CK(cudaMemcpyAsync(d_t, inf.data(), pixels * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
   }
-  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
-  k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->P, R, sc->d_waves, sc->d_counters);
-  Timers tm = make_timers(sc, false);
+  CK(cudaMemsetAsync(sc->c0.d_counters, 0, sizeof(Counters), st));
+  k_generate<<<sc->sm_count * 8, 256, 0, st>>>(sc->S, sc->c0.P, R, sc->c0.d_waves, sc->c0.d_counters);
+  Timers tm = make_timers(sc->c0, false);
   int launches = 0, wr = 0;
-  rc = run_waves(sc, opts && opts->exact_traversal, true, false, tm, &launches, &wr);
+  rc = run_waves(sc, sc->c0, opts && opts->exact_traversal, true, false, tm, &launches, &wr);
   if (rc) { cudaFree(d_ids); cudaFree(d_t); return rc; }
-  k_export_ids<<<sc->sm_count * 4, 256, 0, st>>>(sc->P, R.n_paths, d_ids, d_t);
+  k_export_ids<<<sc->sm_count * 4, 256, 0, st>>>(sc->c0.P, R.n_paths, d_ids, d_t);
   CK(cudaMemcpyAsync(ids_out, d_ids, pixels * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(t_out, d_t, pixels * sizeof(float), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   cudaFree(d_ids); cudaFree(d_t);
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t exact, int32_t* ids_out, float* t_out,
-                      B200RenderStats* stats) {
+                      B200RenderStats* stats) try {
   if (!sc || !rays || n < 0 || !ids_out || !t_out || n > 0x7fffffffll) {
     b200rt_internal_set_error("b200rt_trace_rays: bad argument");
     return B200RT_E_INVALID;
   }
   if (n == 0) return B200RT_OK;
   CK(cudaSetDevice(sc->device));
-  int rc = ensure_pool(sc, (size_t)n + 1024, 1024);
+  int rc = ensure_pool(sc, sc->c0, (size_t)n + 1024, 1024);
   if (rc) return rc;
-  cudaStream_t st = sc->stream;
+  cudaStream_t st = sc->c0.stream;
   float* d_rays = nullptr;
   int32_t* d_ids = nullptr;
   float* d_t = nullptr;
@@ -1297,20 +1407,20 @@ int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t ex
   CK(cudaMalloc((void**)&d_ids, (size_t)n * 2 * sizeof(int32_t)));
   CK(cudaMalloc((void**)&d_t, (size_t)n * sizeof(float)));
   CK(cudaMemcpyAsync(d_rays, rays, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(sc->d_counters, 0, sizeof(Counters), st));
-  k_import_rays<<<sc->sm_count * 4, 256, 0, st>>>(sc->P, d_rays, (uint32_t)n, sc->d_waves);
-  Timers tm = make_timers(sc, stats != nullptr);
+  CK(cudaMemsetAsync(sc->c0.d_counters, 0, sizeof(Counters), st));
+  k_import_rays<<<sc->sm_count * 4, 256, 0, st>>>(sc->c0.P, d_rays, (uint32_t)n, sc->c0.d_waves);
+  Timers tm = make_timers(sc->c0, stats != nullptr);
   tm.mark(ST_GENERATE);
   int launches = 0, wr = 0;
-  rc = run_waves(sc, exact != 0, true, false, tm, &launches, &wr);
+  rc = run_waves(sc, sc->c0, exact != 0, true, false, tm, &launches, &wr);
   if (rc) return rc;
-  k_export_ids<<<sc->sm_count * 4, 256, 0, st>>>(sc->P, (uint32_t)n, d_ids, d_t);
+  k_export_ids<<<sc->sm_count * 4, 256, 0, st>>>(sc->c0.P, (uint32_t)n, d_ids, d_t);
   CK(cudaMemcpyAsync(ids_out, d_ids, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(t_out, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (stats) {
     Counters hc;
-    CK(cudaMemcpy(&hc, sc->d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&hc, sc->c0.d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
     memset(stats, 0, sizeof(*stats));
     stats->nodes_visited = hc.nodes_visited; stats->tris_tested = hc.tris_tested;
     stats->spheres_tested = hc.spheres_tested; stats->instances_entered = hc.instances_entered;
@@ -1324,6 +1434,6 @@ int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t ex
   }
   cudaFree(d_rays); cudaFree(d_ids); cudaFree(d_t);
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 }  // extern "C"

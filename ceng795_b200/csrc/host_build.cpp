@@ -29,6 +29,7 @@
 
 #include "../../include/b200rt.h"
 #include "fast_bvh.h"
+#include "api_guard.h"
 
 namespace {
 
@@ -428,12 +429,12 @@ void b200rt_xf_rotation(float angle_deg, float x, float y, float z, float out[16
 void b200rt_xf_mul(const float a[16], const float b[16], float out[16]) {
   mul(M4::from(a), M4::from(b)).to(out);
 }
-int b200rt_xf_invert(const float m[16], float out[16]) {
+int b200rt_xf_invert(const float m[16], float out[16]) try {
   M4 inv;
   if (!invert(M4::from(m), inv)) return B200RT_E_SINGULAR;
   inv.to(out);
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 b200rt_builder* b200rt_builder_create(int semantics) {
   if (semantics < B200RT_SEM_HW1 || semantics > B200RT_SEM_PPM) return nullptr;
@@ -451,7 +452,7 @@ b200rt_builder* b200rt_builder_create(int semantics) {
 void b200rt_builder_destroy(b200rt_builder* b) { delete b; }
 
 int b200rt_builder_set_globals(b200rt_builder* b, const float bg[3], const float amb[3],
-                               float shadow_eps, int max_depth) {
+                               float shadow_eps, int max_depth) try {
   if (!b) return B200RT_E_INVALID;
   std::memcpy(b->desc.background, bg, 12);
   std::memcpy(b->desc.ambient, amb, 12);
@@ -459,11 +460,11 @@ int b200rt_builder_set_globals(b200rt_builder* b, const float bg[3], const float
   b->desc.max_depth = max_depth;
   if (b->semantics == B200RT_SEM_PPM && b->desc.max_depth > 20) b->desc.max_depth = 20;  // PPM/src/Scene.cpp:426-429
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 // Camera::Camera — HW3/include/Camera.h:11-34 (HW1/Camera.h:11-23 has no
 // s_u/s_v constants and no DOF; the fields are still filled for uniformity).
-int b200rt_builder_add_camera(b200rt_builder* b, const b200rt_camera_in* in) {
+int b200rt_builder_add_camera(b200rt_builder* b, const b200rt_camera_in* in) try {
   if (!b || !in) return B200RT_E_INVALID;
   b200rt_camera c;
   std::memset(&c, 0, sizeof(c));
@@ -510,9 +511,9 @@ int b200rt_builder_add_camera(b200rt_builder* b, const b200rt_camera_in* in) {
   c.aperture = (b->semantics >= B200RT_SEM_HW3) ? in->aperture_size : 0.0f;
   b->cameras.push_back(c);
   return (int)b->cameras.size() - 1;
-}
+} B200RT_CATCH
 
-int b200rt_builder_add_material(b200rt_builder* b, const b200rt_material* m) {
+int b200rt_builder_add_material(b200rt_builder* b, const b200rt_material* m) try {
   if (!b || !m) return B200RT_E_INVALID;
   b200rt_material c = *m;
   if (b->semantics < B200RT_SEM_HW6) c.brdf = -1;
@@ -527,8 +528,8 @@ int b200rt_builder_add_material(b200rt_builder* b, const b200rt_material* m) {
   }
   b->materials.push_back(c);
   return (int)b->materials.size() - 1;
-}
-int b200rt_builder_add_light(b200rt_builder* b, const b200rt_light* l) {
+} B200RT_CATCH
+int b200rt_builder_add_light(b200rt_builder* b, const b200rt_light* l) try {
   if (!b || !l) return B200RT_E_INVALID;
   b200rt_light c = *l;
   if (c.kind == B200RT_LIGHT_AREA) {
@@ -547,14 +548,14 @@ int b200rt_builder_add_light(b200rt_builder* b, const b200rt_light* l) {
   if (c.kind == B200RT_LIGHT_ENV) b->desc.env_light = (int)b->lights.size();
   b->lights.push_back(c);
   return (int)b->lights.size() - 1;
-}
-int b200rt_builder_set_vertices(b200rt_builder* b, const float* xyz, int n) {
+} B200RT_CATCH
+int b200rt_builder_set_vertices(b200rt_builder* b, const float* xyz, int n) try {
   if (!b || (n > 0 && !xyz)) return B200RT_E_INVALID;
   b->verts.assign(xyz, xyz + 3 * (size_t)n);
   return B200RT_OK;
-}
+} B200RT_CATCH
 int b200rt_builder_add_mesh(b200rt_builder* b, int material, int smooth, const int32_t* faces,
-                            int n_faces, const float base_xf[16], const float velocity[3]) {
+                            int n_faces, const float base_xf[16], const float velocity[3]) try {
   if (!b || n_faces < 0 || (n_faces > 0 && !faces)) return B200RT_E_INVALID;
   MeshIn m;
   m.material = material;
@@ -575,9 +576,9 @@ int b200rt_builder_add_mesh(b200rt_builder* b, int material, int smooth, const i
                               // all meshes are added first (the loader does so).
   }
   return id;
-}
+} B200RT_CATCH
 int b200rt_builder_add_instance(b200rt_builder* b, int base_mesh, int material,
-                                const float xf[16], const float velocity[3]) {
+                                const float xf[16], const float velocity[3]) try {
   if (!b || base_mesh < 0 || base_mesh >= (int)b->meshes_in.size() || !xf) return B200RT_E_INVALID;
   if (b->semantics < B200RT_SEM_HW3) return B200RT_E_UNSUPPORTED;
   InstIn i;
@@ -588,9 +589,9 @@ int b200rt_builder_add_instance(b200rt_builder* b, int base_mesh, int material,
   i.direct = false;
   b->inst_in.push_back(i);
   return (int)b->inst_in.size() - 1;
-}
+} B200RT_CATCH
 int b200rt_builder_add_triangle(b200rt_builder* b, int material, const int32_t idx[3],
-                                const float xf[16]) {
+                                const float xf[16]) try {
   if (!b || !idx) return B200RT_E_INVALID;
   TriIn t;
   t.material = material;
@@ -598,9 +599,9 @@ int b200rt_builder_add_triangle(b200rt_builder* b, int material, const int32_t i
   t.xf = xf ? M4::from(xf) : M4::identity();
   b->tri_in.push_back(t);
   return (int)b->tri_in.size() - 1;
-}
+} B200RT_CATCH
 int b200rt_builder_add_sphere(b200rt_builder* b, int material, int center_vertex, float radius,
-                              const float xf[16], const float velocity[3]) {
+                              const float xf[16], const float velocity[3]) try {
   if (!b) return B200RT_E_INVALID;
   SphIn s;
   s.material = material;
@@ -610,14 +611,14 @@ int b200rt_builder_add_sphere(b200rt_builder* b, int material, int center_vertex
   s.velocity = velocity ? load3(velocity) : V3(0.f);
   b->sph_in.push_back(s);
   return (int)b->sph_in.size() - 1;
-}
+} B200RT_CATCH
 
-int b200rt_builder_set_texcoords(b200rt_builder* b, const float* uv, int n) {
+int b200rt_builder_set_texcoords(b200rt_builder* b, const float* uv, int n) try {
   if (!b || (n > 0 && !uv)) return B200RT_E_INVALID;
   b->texcoords.assign(uv, uv + 2 * (size_t)n);
   return B200RT_OK;
-}
-int b200rt_builder_add_texture(b200rt_builder* b, const b200rt_texture* t, const float* texels) {
+} B200RT_CATCH
+int b200rt_builder_add_texture(b200rt_builder* b, const b200rt_texture* t, const float* texels) try {
   if (!b || !t) return B200RT_E_INVALID;
   b200rt_texture c = *t;
   c.texel_offset = (int64_t)b->texels.size();
@@ -627,25 +628,25 @@ int b200rt_builder_add_texture(b200rt_builder* b, const b200rt_texture* t, const
   }
   b->textures.push_back(c);
   return (int)b->textures.size() - 1;
-}
-int b200rt_builder_add_brdf(b200rt_builder* b, const b200rt_brdf* r) {
+} B200RT_CATCH
+int b200rt_builder_add_brdf(b200rt_builder* b, const b200rt_brdf* r) try {
   if (!b || !r) return B200RT_E_INVALID;
   b->brdfs.push_back(*r);
   return (int)b->brdfs.size() - 1;
-}
-int b200rt_builder_set_mesh_texture(b200rt_builder* b, int mesh, int texture, int texture_offset) {
+} B200RT_CATCH
+int b200rt_builder_set_mesh_texture(b200rt_builder* b, int mesh, int texture, int texture_offset) try {
   if (!b || mesh < 0 || mesh >= (int)b->meshes_in.size()) return B200RT_E_INVALID;
   b->meshes_in[mesh].texture = texture;
   b->meshes_in[mesh].texture_offset = texture_offset;
   return B200RT_OK;
-}
-int b200rt_builder_set_sphere_texture(b200rt_builder* b, int sphere, int texture) {
+} B200RT_CATCH
+int b200rt_builder_set_sphere_texture(b200rt_builder* b, int sphere, int texture) try {
   if (!b || sphere < 0 || sphere >= (int)b->sph_in.size()) return B200RT_E_INVALID;
   b->sph_in[sphere].texture = texture;
   return B200RT_OK;
-}
+} B200RT_CATCH
 int b200rt_builder_add_light_mesh(b200rt_builder* b, int material, const int32_t* faces, int n_faces,
-                                  const float xf[16], const float radiance[3]) {
+                                  const float xf[16], const float radiance[3]) try {
   if (!b || n_faces <= 0 || !faces || !radiance) return B200RT_E_INVALID;
   if (b->semantics < B200RT_SEM_HW7) return B200RT_E_UNSUPPORTED;
   MeshIn m;
@@ -666,9 +667,9 @@ int b200rt_builder_add_light_mesh(b200rt_builder* b, int material, const int32_t
   i.is_light = true;
   b->light_inst_in.push_back(i);
   return i.mesh;
-}
+} B200RT_CATCH
 int b200rt_builder_add_light_sphere(b200rt_builder* b, int material, int center_vertex, float radius,
-                                    const float xf[16], const float radiance[3]) {
+                                    const float xf[16], const float radiance[3]) try {
   if (!b || !radiance) return B200RT_E_INVALID;
   if (b->semantics < B200RT_SEM_HW7) return B200RT_E_UNSUPPORTED;
   SphIn s;
@@ -681,20 +682,20 @@ int b200rt_builder_add_light_sphere(b200rt_builder* b, int material, int center_
   s.radiance = load3(radiance);
   b->light_sph_in.push_back(s);
   return (int)b->light_sph_in.size() - 1;
-}
-int b200rt_builder_set_integrator(b200rt_builder* b, int path_tracing, int importance_sampling) {
+} B200RT_CATCH
+int b200rt_builder_set_integrator(b200rt_builder* b, int path_tracing, int importance_sampling) try {
   if (!b) return B200RT_E_INVALID;
   b->desc.integrator = path_tracing ? 1 : 0;
   b->desc.importance_sampling = importance_sampling ? 1 : 0;
   return B200RT_OK;
-}
-int b200rt_builder_set_background_texture(b200rt_builder* b, int texture) {
+} B200RT_CATCH
+int b200rt_builder_set_background_texture(b200rt_builder* b, int texture) try {
   if (!b) return B200RT_E_INVALID;
   b->desc.background_texture = texture;
   return B200RT_OK;
-}
+} B200RT_CATCH
 
-int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
+int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) try {
   if (!b || !out) return B200RT_E_INVALID;
   if (b->finished) {
     *out = &b->desc;
@@ -1089,6 +1090,6 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) {
   b->finished = true;
   *out = &b->desc;
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 }  // extern "C"

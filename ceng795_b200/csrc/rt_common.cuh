@@ -144,6 +144,7 @@ struct Pool {
   uint32_t* key;     // RNG stream of the vertex
   uint32_t* pixel;   // pixel index (wave 0: also sample id in the high bits via sample[])
   uint32_t* sample;  // stratum index of the camera sample (wave 0 only)
+  unsigned long long* omask;  // k_top_mask: top-level objects whose reference gate the ray passes (8-wide path)
   float4* hit_a;     // t, beta, gamma, as_float(top_ref)
   int2* hit_b;       // top_rank, tri
   float4* nrm;       // shading normal xyz, as_float(material)
@@ -162,6 +163,7 @@ struct ShadowQueue {
   float4* o;         // o.xyz, t_limit
   float4* d;         // d.xyz, as_float(result slot)
   float* time;
+  unsigned long long* omask;  // as Pool::omask, per queue entry
   uint8_t* vis;      // per (vertex slot * n_lights + light): 1 = lit, 0 = occluded / inactive
   float4* lv;        // HW7, same index: {vector to the light sample, pdf} drawn by shade_a, reused by shade_b
 };

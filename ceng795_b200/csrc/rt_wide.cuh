@@ -142,11 +142,11 @@ __device__ __forceinline__ uint32_t wide_node_hits(const float4 n0, const float4
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
       const float tf = fminf(fminf(tfx, tfy), tfz);
       const float tfa = __fmaf_rn(4e-6f, fmaxf(tn, fabsf(tf)), tf);
-      if (meta != 0u && tn <= tfa && tn <= bound_slack) {
-        const int slot = 4 * h + k;
-        if ((imask >> slot) & 1u) hits |= 1u << (24u + ((uint32_t)slot ^ r.oct_inv));
-        else hits |= (meta >> 5) << (meta & 31u);
-      }
+      // branch-free: eight divergent regions per node step cost more than the few instructions they would skip
+      const uint32_t slot = 4u * h + k;
+      const uint32_t bits = ((imask >> slot) & 1u) ? (1u << (24u + (slot ^ r.oct_inv))) : ((meta >> 5) << (meta & 31u));
+      const bool hit = (meta != 0u) & (tn <= tfa) & (tn <= bound_slack);
+      hits |= bits & (0u - (uint32_t)hit);
     }
   }
   return hits;
@@ -330,6 +330,28 @@ __device__ __forceinline__ bool wide_trace_one(const DScene& S, const float4* to
 
 // MINB: resident CTAs per SM the register budget is held to (4: 128 registers, 6: 80, 8: 64) — instantiated for all
 // three so that one run on the device can sweep it (B200RT_WIDE_BLOCKS), profiles/r02*_tuning.txt.
+// Phase 0 as a pass of its own: the reference's top-level gates of every ray of the wave, 32 lanes wide, one 64-bit
+// mask per ray.  The traversal kernel then starts a ray by loading 8 bytes, so topping a warp up costs next to
+// nothing and idle lanes are refilled early (S.refill_*) instead of waiting until the warp has almost drained.
+template <bool ANY>
+__global__ void __launch_bounds__(256) k_top_mask(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves, int d, Counters* C) {
+  __shared__ float4 s_top[2 * RT_TOP_LINEAR_MAX];
+  for (int i = threadIdx.x; i < 2 * S.n_top; i += blockDim.x) s_top[i] = __ldg(S.top_objs + i);
+  __syncthreads();
+  const uint32_t begin = ANY ? 0u : waves[d].begin;
+  const uint32_t count = ANY ? min(C->shadow_count, Q.capacity) : waves[d].count;
+  const float eps = S.isect_eps;
+  TravCounters tc = {0, 0, 0, 0};
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    const float4 ro = ANY ? Q.o[k] : P.ray_o[begin + k];
+    const float4 rd = ANY ? Q.d[k] : P.ray_d[begin + k];
+    const RayCtx wr = make_ray(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), eps);
+    const unsigned long long m = wide_top_mask(s_top, S.n_top, wr, eps, tc);
+    if (ANY) Q.omask[k] = m; else P.omask[begin + k] = m;
+  }
+  flush_counters(C, tc, ANY);
+}
+
 template <bool ANY, int TRI_MODE, int MINB>
 __global__ void __launch_bounds__(RT_BLOCK, MINB) k_trace_wide(DScene S, Pool P, ShadowQueue Q,
                                                                const WaveInfo* waves, int d, Counters* C) {
@@ -344,7 +366,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MINB) k_trace_wide(DScene S, Pool P,
   const float eps = S.isect_eps;
   // Topping a warp up before it has drained pays when ray costs inside a batch differ a lot (bounce waves, one sample
   // per pixel); it costs ~10 % when they do not: the strata of one pixel travel together and finish together
-  const int refill_idle = (d == 0 && S.cam.samples_sqrt > 1) ? 32 : (ANY ? S.refill_any : S.refill_closest);
+  const int refill_idle = ANY ? S.refill_any : S.refill_closest;
   const unsigned lane = lane_id();
   const unsigned tid = threadIdx.x;
   const bool hw7 = S.semantics >= B200RT_SEM_HW7;  // HW4 has the band triangle test (TRI_MODE 7) but no culling
@@ -385,8 +407,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MINB) k_trace_wide(DScene S, Pool P,
           wide_reset(L, hw7);
           sp = 0;
           has_ray = true;
-          const RayCtx wr = make_ray(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), eps);
-          L.objmask = wide_top_mask(s_top, S.n_top, wr, eps, tc);
+          L.objmask = ANY ? Q.omask[k] : P.omask[out_slot];   // phase 0 was done by k_top_mask
         }
       }
     }
@@ -397,6 +418,9 @@ __global__ void __launch_bounds__(RT_BLOCK, MINB) k_trace_wide(DScene S, Pool P,
       // lane with triangles to test, or with nothing left in its object, waits — but only until fewer than
       // S.node_vote lanes are still descending: then everybody goes through phase 2.
       for (;;) {
+        // a group without unvisited children: take the next one off the stack right here, a lane should not have to
+        // wait for phase 2 just to pop
+        if (has_ray && L.T.y == 0u && (L.G.y & 0xff000000u) == 0u && sp > 0) { sp--; L.G = s_stack[sp][tid]; }
         const bool want_node = has_ray && L.T.y == 0u && (L.G.y & 0xff000000u) != 0u;
         const unsigned mn = __ballot_sync(0xffffffffu, want_node);
         if (mn == 0u) break;

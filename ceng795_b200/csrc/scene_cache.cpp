@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/b200rt.h"
+#include "api_guard.h"
 
 extern "C" void b200rt_internal_set_error(const char* msg);
 
@@ -103,7 +104,7 @@ const void* member_ptr(const B200SceneDesc& d, size_t o) {
 
 extern "C" {
 
-int b200rt_scene_desc_save(const B200SceneDesc* d, const char* path) {
+int b200rt_scene_desc_save(const B200SceneDesc* d, const char* path) try {
   if (!d || !path) return fail("scene_desc_save: null argument");
   const std::vector<Section> secs = sections(*d);
   B200SceneDesc plain = *d;   // the desc as it goes to disk: pointer members zeroed (files are reproducible)
@@ -135,9 +136,9 @@ int b200rt_scene_desc_save(const B200SceneDesc* d, const char* path) {
   }
   ok = (std::fclose(f) == 0) && ok;
   return ok ? B200RT_OK : fail(std::string("scene_desc_save: short write to ") + path);
-}
+} B200RT_CATCH
 
-int b200rt_scene_desc_load(const char* path, B200SceneDesc** out) {
+int b200rt_scene_desc_load(const char* path, B200SceneDesc** out) try {
   if (!path || !out) return fail("scene_desc_load: null argument");
   *out = nullptr;
   std::FILE* f = std::fopen(path, "rb");
@@ -184,7 +185,7 @@ int b200rt_scene_desc_load(const char* path, B200SceneDesc** out) {
   if (sum != h.checksum) { std::free(blob); return fail("scene_desc_load: checksum mismatch (corrupt cache)"); }
   *out = d;
   return B200RT_OK;
-}
+} B200RT_CATCH
 
 void b200rt_scene_desc_free(B200SceneDesc* d) { std::free(d); }
 

@@ -383,6 +383,118 @@ def hw7_scene(asset_dir, width=160, height=120, n=12, spp=1, depth=3, path_traci
             + textures + "  <Objects>\n" + mesh_xml + inst + lobj + tri_xml + sph + "  </Objects>\n</Scene>\n")
 
 
+def cfg4_hw7(asset_dir, width=1920, height=1080, spp=4096, depth=4, mesh_slices=(224, 225), tex_size=1024,
+             seed=SEED, image_name="cfg4.png", radiance=15.0) -> str:
+    """BASELINE config 4 as SURVEY.md 8(d) words it: Cornell-style box (5 walls, stand-alone triangles) + a LightMesh
+    (2 triangles, radiance 15) + 1 LightSphere + 3 instances of a ~100 k-triangle smooth mesh carrying an image texture
+    (tex_size^2, bilinear / repeat, replace_kd), a Perlin `patch` bump texture, one material per BRDF type (5), one
+    mirror, one glass; PathTracing + ImportanceSampling, MaxRecursionDepth 4, Photographic TMO key .18 / 1 % burn,
+    NumSamples `spp` (64 x 64 strata at 4096).  No point / area lights: the two light shapes are the only emitters.
+    Writes the texture image into `asset_dir`; the XML refers to it by bare file name."""
+    import os
+    rng = np.random.default_rng(seed + 44)
+    tex_name = f"tex_cfg4_{tex_size}.png"
+    if not os.path.exists(os.path.join(asset_dir, tex_name)):
+        write_test_texture(os.path.join(asset_dir, tex_name), w=tex_size, h=tex_size, seed=SEED)
+    verts, tcs = [], []
+    nv = 0
+
+    def push(v, uv=None):
+        nonlocal nv
+        base = nv
+        v = np.asarray(v, np.float32)
+        verts.append(v)
+        tcs.append(np.zeros((len(v), 2), np.float32) if uv is None else np.asarray(uv, np.float32))
+        nv += len(v)
+        return base
+
+    R = 5.0
+    top = 2 * R - 1
+    room = np.array([[-R, -1, -R], [R, -1, -R], [R, -1, R], [-R, -1, R],
+                     [-R, top, -R], [R, top, -R], [R, top, R], [-R, top, R]], np.float32)
+    rb = push(room)
+    # floor, back wall, left wall (red), right wall (green), ceiling — wound to face the inside (HW7 culls back faces)
+    quads = [((0, 3, 2, 1), 1), ((0, 1, 5, 4), 1), ((0, 4, 7, 3), 2), ((1, 2, 6, 5), 3), ((4, 5, 6, 7), 1)]
+    tri_xml = ""
+    tid = 1
+    for q, mat in quads:
+        for tri in ((q[0], q[1], q[2]), (q[0], q[2], q[3])):
+            idx = [rb + t + 1 for t in tri]
+            tri_xml += (f'    <Triangle id="{tid}">\n      <Material>{mat}</Material>\n'
+                        f"      <Indices>{idx[0]} {idx[1]} {idx[2]}</Indices>\n    </Triangle>\n")
+            tid += 1
+    # the ~100 k-triangle base mesh: a UV sphere with latitude / longitude texture coordinates (4 x 2 repeats)
+    sv, sf = _uv_sphere((0, 0, 0), 1.0, mesh_slices[0], mesh_slices[1])
+    suv = np.stack([4.0 * (np.arctan2(sv[:, 2], sv[:, 0]) + np.pi) / (2 * np.pi),
+                    2.0 * np.arccos(np.clip(sv[:, 1], -1, 1)) / np.pi], -1)
+    sb = push(sv, suv)
+    mesh_xml = (f'    <Mesh id="1" shadingMode="smooth">\n      <Material>4</Material>\n      <Texture>1</Texture>\n'
+                f'      <Transformations>s1 t1</Transformations>\n'
+                f'      <Faces vertexOffset="{sb}" textureOffset="{sb}">\n' + _rows(sf + 1, "%d") + "      </Faces>\n    </Mesh>\n")
+    xf = ('  <Transformations>\n    <Scaling id="1">1.15 1.15 1.15</Scaling>\n    <Translation id="1">-2.6 0.15 -2.0</Translation>\n'
+          '    <Scaling id="2">0.9 1.25 0.9</Scaling>\n    <Translation id="2">0.1 0.25 -2.6</Translation>\n'
+          f'    <Rotation id="1">{_f([31.0, *rng.normal(size=3)])}</Rotation>\n'
+          '    <Scaling id="3">1.0 0.8 1.0</Scaling>\n    <Translation id="3">2.7 -0.2 -1.6</Translation>\n'
+          f'    <Rotation id="2">{_f([74.0, *rng.normal(size=3)])}</Rotation>\n  </Transformations>\n')
+    inst = ('    <MeshInstance id="1" baseMeshId="1" resetTransform="true">\n      <Material>5</Material>\n'
+            '      <Transformations>s2 r1 t2</Transformations>\n    </MeshInstance>\n'
+            '    <MeshInstance id="2" baseMeshId="1" resetTransform="true">\n      <Material>6</Material>\n'
+            '      <Transformations>s3 r2 t3</Transformations>\n    </MeshInstance>\n')
+    # spheres: Perlin-bumped (BRDF 4), Torrance-Sparrow (BRDF 5), mirror, glass
+    sph_c = np.array([[-1.5, -0.35, 1.0], [1.6, -0.3, 1.3], [-0.2, -0.1, 0.2], [0.9, -0.4, 2.4]], np.float32)
+    sph_r = [0.65, 0.7, 0.9, 0.6]
+    sph_mat = [7, 8, 9, 10]
+    cb = push(sph_c)
+    sph = ""
+    for i in range(4):
+        tx = "      <Texture>2</Texture>\n" if i == 0 else ""
+        sph += (f'    <Sphere id="{i + 1}">\n      <Material>{sph_mat[i]}</Material>\n{tx}'
+                f"      <Center>{cb + i + 1}</Center>\n      <Radius>{_f([sph_r[i]])}</Radius>\n    </Sphere>\n")
+    mats = (_material7(1, [0, 0, 0], [0.73, 0.73, 0.7], [0, 0, 0], 1)
+            + _material7(2, [0, 0, 0], [0.65, 0.08, 0.06], [0, 0, 0], 1)
+            + _material7(3, [0, 0, 0], [0.12, 0.48, 0.1], [0, 0, 0], 1)
+            + "".join(_material7(4 + k, [0, 0, 0], rng.uniform(0.25, 0.7, 3), rng.uniform(0.15, 0.4, 3),
+                                 float(20 + 10 * k), brdf=k + 1) for k in range(5))
+            + _material7(9, [0, 0, 0], [0.03, 0.03, 0.03], [0, 0, 0], 1, mirror=[0.9, 0.9, 0.9])
+            + _material7(10, [0, 0, 0], [0.02, 0.02, 0.02], [0, 0, 0], 1, transparency=[0.95, 0.97, 0.95], refr=1.5)
+            + _material7(11, [0, 0, 0], [0.5, 0.5, 0.5], [0, 0, 0], 1))
+    brdfs = ('  <BRDFs>\n    <OriginalPhong id="1"><Exponent>20</Exponent></OriginalPhong>\n'
+             '    <ModifiedPhong id="2" normalized="true"><Exponent>30</Exponent></ModifiedPhong>\n'
+             '    <OriginalBlinnPhong id="3"><Exponent>40</Exponent></OriginalBlinnPhong>\n'
+             '    <ModifiedBlinnPhong id="4" normalized="true"><Exponent>50</Exponent></ModifiedBlinnPhong>\n'
+             '    <TorranceSparrow id="5"><Exponent>60</Exponent><RefractiveIndex>2.1</RefractiveIndex></TorranceSparrow>\n'
+             "  </BRDFs>\n")
+    textures = ('  <Textures>\n'
+                f'    <Texture id="1"><ImageName>{tex_name}</ImageName><Interpolation>bilinear</Interpolation>'
+                '<DecalMode>replace_kd</DecalMode><Appearance>repeat</Appearance></Texture>\n'
+                '    <Texture id="2" bumpmap="true" bumpmapMultiplier="0.6"><ImageName>perlin</ImageName>'
+                '<DecalMode>blend_kd</DecalMode><Appearance>patch</Appearance><ScalingFactor>3.5</ScalingFactor>'
+                '<Permutation>11 3 7 0 14 9 2 13 5 8 1 15 6 12 4 10</Permutation></Texture>\n'
+                "  </Textures>\n")
+    lights = "  <Lights>\n    <AmbientLight>0 0 0</AmbientLight>\n  </Lights>\n"
+    lq = push(np.array([[-1.2, top - 0.02, -1.8], [1.2, top - 0.02, -1.8], [1.2, top - 0.02, 0.6], [-1.2, top - 0.02, 0.6]], np.float32))
+    lobj = (f'    <LightMesh id="1">\n      <Material>11</Material>\n      <Radiance>{_f([radiance] * 3)}</Radiance>\n'
+            f'      <Faces vertexOffset="{lq}">\n1 2 3\n1 3 4\n      </Faces>\n    </LightMesh>\n')
+    lc = push(np.array([[-3.4, 4.6, -3.0]], np.float32))
+    lobj += (f'    <LightSphere id="1">\n      <Material>11</Material>\n      <Center>{lc + 1}</Center>\n      <Radius>0.5</Radius>\n'
+             f"      <Radiance>{_f([radiance, radiance * 0.85, radiance * 0.7])}</Radiance>\n    </LightSphere>\n")
+    allv = np.concatenate(verts, 0)
+    alluv = np.concatenate(tcs, 0)
+    aspect = width / height
+    return ("<Scene>\n  <BackgroundColor>0 0 0</BackgroundColor>\n  <ShadowRayEpsilon>1e-3</ShadowRayEpsilon>\n"
+            f"  <MaxRecursionDepth>{depth}</MaxRecursionDepth>\n  <Integrator>PathTracing</Integrator>\n"
+            "  <IntegratorParams>ImportanceSampling</IntegratorParams>\n  <Cameras>\n    <Camera id=\"1\">\n"
+            "      <Position>0 3.0 4.9</Position>\n      <Gaze>0 -0.3 -1</Gaze>\n      <Up>0 1 0</Up>\n"
+            f"      <NearPlane>{_f([-0.6 * aspect, 0.6 * aspect, -0.6, 0.6])}</NearPlane>\n      <NearDistance>1</NearDistance>\n"
+            f"      <ImageResolution>{width} {height}</ImageResolution>\n      <NumSamples>{spp}</NumSamples>\n"
+            f"      <ImageName>{image_name}</ImageName>\n"
+            "      <Tonemap><TMO>Photographic</TMO><TMOOptions>0.18 1</TMOOptions><Saturation>1.0</Saturation></Tonemap>\n"
+            "    </Camera>\n  </Cameras>\n"
+            + brdfs + lights + "  <Materials>\n" + mats + "  </Materials>\n" + xf + "  <VertexData>\n"
+            + _rows(allv, "%.9g") + "  </VertexData>\n  <TexCoordData>\n" + _rows(alluv, "%.9g") + "  </TexCoordData>\n"
+            + textures + "  <Objects>\n" + mesh_xml + inst + lobj + tri_xml + sph + "  </Objects>\n</Scene>\n")
+
+
 # --------------------------------------------------------------------------- PPM
 def cfg5_ppm(width=1920, height=1080, mesh_slices=(160, 158), photons_per_iteration=10_000_000, iterations=100,
              depth=8, spp=1, seed=SEED, image_name="cfg5.png") -> str:

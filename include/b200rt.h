@@ -38,6 +38,7 @@ extern "C" {
 #define B200RT_E_CUDA (-2)      /* CUDA runtime error (see last_error)        */
 #define B200RT_E_NOGPU (-3)     /* no CUDA device: there is NO CPU fallback   */
 #define B200RT_E_UNSUPPORTED (-4)
+#define B200RT_E_NOMEM (-6)     /* host allocation failed inside the library (never thrown across the ABI) */
 #define B200RT_E_SINGULAR (-5)  /* reference exit(-1): "NOT INVERTIBLE MATRIX" HW3/src/Transformation.cpp:78-82 */
 
 /* ---- per-tree semantics -------------------------- */
@@ -348,7 +349,9 @@ typedef struct B200RenderOpts {
   uint64_t seed;              /* counter-based RNG key for stochastic configs */
   int32_t sample_begin, sample_end; /* strata subset [begin,end) of samples_sqrt^2 (0,0 = all) */
   int32_t exact_traversal;    /* 1 = visit every gated node like the reference (no t-pruning) */
-  int32_t pad[5];
+  int32_t contexts;           /* row bands of the frame rendered concurrently on streams of their own (0 = the scene's
+                                 default, 1 = one serial launch train); the result does not depend on it */
+  int32_t pad[4];
 } B200RenderOpts;
 
 typedef struct B200RenderStats {
@@ -362,6 +365,8 @@ typedef struct B200RenderStats {
   int32_t node_bytes;   /* bytes of one nodes_visited unit inside a mesh: 80 (8-wide tree) or 64 (binary tree) */
   int32_t top_objects;  /* gate boxes of the flat top-level list (32 B each); every ray tests all of them and they are
                            counted in nodes_visited.  0: the top-level tree is walked instead */
+  int32_t contexts;     /* row bands the frame was cut into; > 1: the ms_* stage times are sums over concurrent streams */
+  int32_t pad;
 } B200RenderStats;
 
 int b200rt_device_count(void);

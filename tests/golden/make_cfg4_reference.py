@@ -1,0 +1,80 @@
+"""Generates tests/golden/cfg4_ref_240x135_1024spp.npy: BASELINE config 4's scene (scenes.cfg4_hw7) at
+240 x 135 and 1024 samples per pixel, rendered by the UNMODIFIED HW7 tree (oracle/_ref/hw7f_raytracer = the tree's
+objects + oracle/ref_driver_hdr.cpp, which dumps Pixel::get_color() as float32).
+
+The tree seeds every mt19937 from std::random_device and shuffles its Perlin table from the clock; with REF_SEED the
+driver interposes both (one thread, seed 795), so this file is reproducible: run it twice, get the same bytes.  The
+Perlin table the tree then uses is oracle.cpu.perlin_table_for_clock(795); the scene XML carries it as <Permutation>
+for our side.  A second run with REF_SEED=796 gives an independent estimate of the same image: its RMSE against the
+first is the reference's own noise floor at this sample count, recorded in cfg4_ref.json next to the fixture.
+
+Runs only where /root/reference was compiled (oracle/build_ref.sh); takes ~10 minutes of CPU.  SURVEY.md 8(c) plan 2(i).
+"""
+import json
+import os
+import sys
+import tempfile
+import threading
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from ceng795_b200 import scenes  # noqa: E402
+from oracle import cpu  # noqa: E402
+
+W, H, SPP = 240, 135, 1024
+MESH = (224, 225)     # the full ~100 k-triangle base mesh
+TEX = 1024
+
+
+def scene_xml(asset_dir, seed_for_table=795):
+    xml = scenes.cfg4_hw7(asset_dir, width=W, height=H, spp=SPP, mesh_slices=MESH, tex_size=TEX)
+    table = " ".join(str(v) for v in cpu.perlin_table_for_clock(seed_for_table))
+    a = xml.index("<Permutation>")
+    b = xml.index("</Permutation>")
+    return xml[:a] + "<Permutation>" + table + xml[b:]
+
+
+def run(seed, out):
+    d = tempfile.mkdtemp(prefix=f"cfg4ref{seed}_")
+    xml = scene_xml(d, seed)
+    env_before = os.environ.get("REF_SEED")
+    # cpu.run_reference inherits os.environ; the two runs differ only in REF_SEED, so set it per subprocess
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "hw7f_raytracer")
+    with open(os.path.join(d, "scene.xml"), "w") as f:
+        f.write(xml)
+    r = subprocess.run([exe, os.path.join(d, "scene.xml")], cwd=d, capture_output=True, text=True,
+                       env=dict(os.environ, REF_SEED=str(seed)), stdin=subprocess.DEVNULL)
+    assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
+    p = os.path.join(d, "cfg4.png.f32")
+    wh = np.fromfile(p, np.int32, 2)
+    out[seed] = np.fromfile(p, np.float32, offset=8).reshape(int(wh[1]), int(wh[0]), 3)
+    del env_before
+
+
+def main():
+    res = {}
+    ts = [threading.Thread(target=run, args=(s, res)) for s in (795, 796)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    a, b = res[795], res[796]
+    fin = np.isfinite(a).all(-1) & np.isfinite(b).all(-1)
+    cap = float(np.percentile(a[fin], 99.5))
+    ac, bc = np.clip(a, 0, cap), np.clip(b, 0, cap)
+    info = {"width": W, "height": H, "spp": SPP, "mesh_slices": list(MESH), "tex_size": TEX, "ref_seed": 795,
+            "perlin_table": cpu.perlin_table_for_clock(795),
+            "mean": float(a[fin].mean()), "clip_at_p99_5": cap, "nonfinite_pixels": int((~np.isfinite(a).all(-1)).sum()),
+            "ref_vs_ref_rel_rmse": float(np.sqrt(np.mean((a[fin] - b[fin]) ** 2)) / a[fin].mean()),
+            "ref_vs_ref_rel_rmse_clipped": float(np.sqrt(np.mean((ac[fin] - bc[fin]) ** 2)) / ac[fin].mean()),
+            "ref_vs_ref_mean_ratio": float(b[fin].mean() / a[fin].mean())}
+    np.save(os.path.join(ROOT, "tests", "golden", "cfg4_ref_240x135_1024spp.npy"), a.astype(np.float16))
+    json.dump(info, open(os.path.join(ROOT, "tests", "golden", "cfg4_ref.json"), "w"), indent=1)
+    print(info)
+
+
+if __name__ == "__main__":
+    main()
