@@ -122,7 +122,7 @@ class SceneDesc(C.Structure):
 
 class RenderOpts(C.Structure):
     _fields_ = [("row_begin", c_i), ("row_end", c_i), ("row_stride", c_i), ("seed", C.c_uint64),
-                ("sample_begin", c_i), ("sample_end", c_i), ("exact_traversal", c_i), ("contexts", c_i), ("pad", c_i * 4)]
+                ("sample_begin", c_i), ("sample_end", c_i), ("exact_traversal", c_i), ("contexts", c_i), ("row_group", c_i), ("pad", c_i * 3)]
 
 
 class RenderStats(C.Structure):
@@ -226,6 +226,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_void_p, P(RenderStats)]),
         "b200rt_debug_pool": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+        "b200rt_debug_lit_counts": (C.c_int, [C.c_void_p, C.c_int]),
+        "b200rt_debug_get_lit_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
         "b200rt_tonemap_photographic": (C.c_int, [C.c_void_p, C.c_int, c_f, c_f, c_f, C.c_void_p]),
         "b200rt_ppm_eye_pass": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, P(PpmStats)]),
         "b200rt_ppm_trace_photons": (C.c_int, [C.c_void_p, P(PpmOpts), P(PpmStats)]),

@@ -80,6 +80,9 @@ struct b200rt_scene {
   std::vector<WaveCtx*> more;   // contexts 1.. (created on first use)
   float4* d_accum;
   size_t accum_pixels;
+  int* d_lit;            // parity hook: lit shadow tests per pixel x light (b200rt_debug_lit_counts)
+  size_t lit_entries;
+  bool lit_on;
   size_t scene_bytes;
   // PPM state
   HitPoints HP;
@@ -311,14 +314,18 @@ int run_waves(b200rt_scene* sc, WaveCtx& cx, bool exact, bool primary_only, bool
 }
 
 int resolve_rows(const b200rt_camera& c, const B200RenderOpts* o, RenderParams* R) {
-  int rb = 0, re = c.height, rs = 1;
+  int rb = 0, re = c.height, rs = 1, rg = 1;
   if (o) {
     if (o->row_end > 0) { rb = o->row_begin; re = o->row_end; }
+    if (o->row_group > 1) rg = o->row_group;
     if (o->row_stride > 1) rs = o->row_stride;
   }
+  if (rs < rg) rs = rg;   // groups do not overlap
   if (rb < 0 || re > c.height || rb > re) return B200RT_E_INVALID;
-  R->row_begin = rb; R->row_end = re; R->row_stride = rs;
-  R->n_rows = (re - rb + rs - 1) / rs;
+  R->row_begin = rb; R->row_end = re; R->row_stride = rs; R->row_group = rg; R->row_index0 = 0;
+  int rows = 0;
+  for (int start = rb; start < re; start += rs) rows += (re - start < rg) ? (re - start) : rg;
+  R->n_rows = rows;
   const int total = c.samples_sqrt * c.samples_sqrt;
   int sb = 0, se = total;
   if (o && o->sample_end > 0) { sb = o->sample_begin; se = o->sample_end; }
@@ -350,6 +357,17 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
   const size_t pixels = (size_t)c.width * c.height;
   int rc = ensure_accum(sc, pixels);
   if (rc) return rc;
+  sc->S.lit_count = nullptr;
+  if (sc->lit_on) {
+    const size_t need = pixels * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1);
+    if (sc->lit_entries < need) {
+      if (sc->d_lit) cudaFree(sc->d_lit);
+      sc->d_lit = nullptr; sc->lit_entries = 0;
+      CK(cudaMalloc((void**)&sc->d_lit, need * sizeof(int)));
+      sc->lit_entries = need;
+    }
+    sc->S.lit_count = sc->d_lit;
+  }
 
   // The rows of the frame are cut into K contiguous bands (multiples of 4 rows: k_generate's 8x4 tiles), one per
   // wavefront context; each band runs its own generate -> (extend -> shade_a -> shadow -> shade_b)* -> combine train on
@@ -407,6 +425,7 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
   Counters hc;
   for (int attempt = 0;; attempt++) {
     CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), c0.stream));
+    if (sc->S.lit_count) CK(cudaMemsetAsync(sc->d_lit, 0, sc->lit_entries * sizeof(int), c0.stream));
     launches = 0; waves_total = 0;
     CK(cudaEventRecord(c0.ev[0], c0.stream));   // the fork: every context starts after the frame buffer is cleared
     for (int k = 0; k < K; k++) {
@@ -428,7 +447,7 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
         RenderParams B = R;
         const int left = band_begin[k + 1] - r0s[k];
         const int nr = (size_t)left < rows_per_batch ? left : (int)rows_per_batch;
-        B.row_begin = R.row_begin + r0s[k] * R.row_stride;
+        B.row_index0 = r0s[k];
         B.n_rows = nr;
         B.n_paths = (uint32_t)((size_t)nr * paths_per_row);
         k_generate<<<sc->sm_count * 8, 256, 0, cx.stream>>>(sc->S, cx.P, B, cx.d_waves, cx.d_counters);
@@ -855,6 +874,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   memset(&sc->c0.Q, 0, sizeof(ShadowQueue));
   sc->device = device;
   sc->d_accum = nullptr; sc->accum_pixels = 0;
+  sc->d_lit = nullptr; sc->lit_entries = 0; sc->lit_on = false;
   memset(&sc->HP, 0, sizeof(HitPoints));
   memset(&sc->G, 0, sizeof(PpmGrid));
   sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
@@ -1072,6 +1092,7 @@ void b200rt_scene_destroy(b200rt_scene* sc) {
     if (p) cudaFree(p);
   ppm_free(sc);
   if (sc->d_accum) cudaFree(sc->d_accum);
+  if (sc->d_lit) cudaFree(sc->d_lit);
   delete sc;
 }
 
@@ -1119,6 +1140,22 @@ int b200rt_tonemap_photographic(b200rt_scene* sc, int camera_index, float key, f
   if (d_rgb) cudaFree(d_rgb);
   if (d_tmp) cudaFree(d_tmp);
   return rc;
+} B200RT_CATCH
+
+int b200rt_debug_lit_counts(b200rt_scene* sc, int enable) try {
+  if (!sc) return B200RT_E_INVALID;
+  sc->lit_on = enable != 0;
+  return B200RT_OK;
+} B200RT_CATCH
+
+int b200rt_debug_get_lit_counts(b200rt_scene* sc, int camera_index, int32_t* out) try {
+  if (!sc || !out || camera_index < 0 || camera_index >= (int)sc->cameras.size() || !sc->d_lit) return B200RT_E_INVALID;
+  const b200rt_camera& c = sc->cameras[camera_index];
+  const size_t n = (size_t)c.width * c.height * (size_t)(sc->S.n_lights > 0 ? sc->S.n_lights : 1);
+  if (n > sc->lit_entries) return B200RT_E_INVALID;
+  CK(cudaSetDevice(sc->device));
+  CK(cudaMemcpy(out, sc->d_lit, n * sizeof(int), cudaMemcpyDeviceToHost));
+  return B200RT_OK;
 } B200RT_CATCH
 
 int b200rt_debug_pool(b200rt_scene* sc, int field, void* out, int64_t count) try {

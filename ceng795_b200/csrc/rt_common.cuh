@@ -121,6 +121,7 @@ struct DScene {
   const float* light_cdf;
   const int* light_tri;
   int background_texture, env_light, integrator, importance_sampling;
+  int* lit_count;   // parity hook: per pixel x light, shadow tests that came out lit (HW5-HW7 shading); NULL = off
   b200rt_camera cam;
 };
 

@@ -28,7 +28,10 @@ __device__ __forceinline__ uint32_t warp_append(unsigned int* counter, bool want
 }
 
 struct RenderParams {
-  int row_begin, row_end, row_stride;  // rows rendered: row_begin, +stride, ... < row_end
+  // rows rendered: groups of row_group consecutive rows starting at row_begin, row_begin + row_stride, ... (< row_end);
+  // row_group 1 is the reference's own interleave `j += height_increase` (HW7/src/Scene.cpp:28)
+  int row_begin, row_end, row_stride, row_group;
+  int row_index0;   // index (among the rendered rows) of the first row of this batch
   int n_rows;
   int sample_begin, sample_count;      // strata [begin, begin+count) of samples_sqrt^2
   uint32_t seed_key;
@@ -75,7 +78,8 @@ __global__ void k_generate(DScene S, Pool P, RenderParams R, WaveInfo* waves, Co
       rowi = (tile / tiles_per_row) * 4u + (in >> 3);
       coli = (tile % tiles_per_row) * 8u + (in & 7u);
     }
-    const int row = R.row_begin + (int)rowi * R.row_stride;
+    const int ri = R.row_index0 + (int)rowi;
+    const int row = R.row_begin + (ri / R.row_group) * R.row_stride + (ri % R.row_group);
     const int col = (int)coli;
     const uint32_t pix = (uint32_t)row * (uint32_t)W + (uint32_t)col;
     const uint32_t key = rng_mix(rng_mix(R.seed_key, pix), ns == 1 ? 0u : sidx);

@@ -845,6 +845,7 @@ __global__ void __launch_bounds__(RT_SHADE7_BLOCK) k_shade7_b(DScene S, Pool P, 
 #endif
       const uint32_t vslot = slot * (uint32_t)S.n_lights + (uint32_t)li;
       if (!(shaded && !in_medium) || !Q.vis[vslot]) continue;
+      if (S.lit_count) atomicAdd(S.lit_count + (size_t)P.pixel[slot] * S.n_lights + li, 1);   // parity hook (b200rt_debug_lit_counts)
       const b200rt_material& m = S.mats[mat];
       const float4 ls = Q.lv[vslot];  // light_dir7's sample, drawn once in shade_a
       const v3 lvec = mk3(ls.x, ls.y, ls.z);

@@ -675,6 +675,18 @@ class Scene:
                    "b200rt_render")
         return out, st
 
+    def count_lit(self, enable: bool = True):
+        """Parity hook: later renders count, per pixel and light, the shadow tests that came out lit."""
+        self.upload()
+        _lib.check(self._L.b200rt_debug_lit_counts(self._scene, 1 if enable else 0), "b200rt_debug_lit_counts")
+
+    def lit_counts(self, camera_index: int = 0) -> np.ndarray:
+        w, h = self.image_size(camera_index)
+        out = np.zeros((h, w, max(1, self.host.desc.n_lights)), np.int32)
+        _lib.check(self._L.b200rt_debug_get_lit_counts(self._scene, camera_index, out.ctypes.data),
+                   "b200rt_debug_get_lit_counts")
+        return out
+
     def render_device(self, camera_index: int = 0, **opts):
         self.upload()
         st = _lib.RenderStats()

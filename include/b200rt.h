@@ -345,13 +345,16 @@ typedef struct b200rt_scene b200rt_scene;
 
 typedef struct B200RenderOpts {
   int32_t row_begin, row_end; /* render rows [begin,end) (0,0 = all) : multi-GPU tile split */
-  int32_t row_stride;         /* 1 = contiguous; >1 = reference-style interleave `j += height_increase` */
+  int32_t row_stride;         /* 1 = contiguous; >1 = reference-style interleave `j += height_increase`: groups of
+                                 row_group rows start at row_begin, row_begin + row_stride, ... */
   uint64_t seed;              /* counter-based RNG key for stochastic configs */
   int32_t sample_begin, sample_end; /* strata subset [begin,end) of samples_sqrt^2 (0,0 = all) */
   int32_t exact_traversal;    /* 1 = visit every gated node like the reference (no t-pruning) */
   int32_t contexts;           /* row bands of the frame rendered concurrently on streams of their own (0 = the scene's
                                  default, 1 = one serial launch train); the result does not depend on it */
-  int32_t pad[4];
+  int32_t row_group;          /* consecutive rows per interleave step (0 / 1 = single rows; b200rt_render_multi uses
+                                 bands of 8 rows dealt round-robin to the devices) */
+  int32_t pad[3];
 } B200RenderOpts;
 
 typedef struct B200RenderStats {
@@ -437,6 +440,13 @@ int b200rt_tonemap_photographic(b200rt_scene*, int camera_index, float image_key
  * host memory.  field: 0 ray_o(f4) 1 ray_d(f4) 2 hit_a(f4) 3 nrm(f4) 4 rec0(f4) 5 rec1(f4) 6 rec2(f4)
  * 7 rec4(f4) 8 final_c(f4) 9 kd(f4) 10 pixel(u32) 11 key(u32) 12 hit_b(i32x2) 13 rec3(u32). */
 int b200rt_debug_pool(b200rt_scene*, int field, void* out, int64_t count);
+
+/* Parity hook (HW5..HW7 shading): with enable != 0 every later render of the scene counts, per pixel and light, the
+ * shadow tests that came out "lit" (HW7/src/Scene.cpp:283-290) into a W*H*n_lights int32 array, cleared at the start
+ * of each render; b200rt_debug_get_lit_counts copies it to host memory.  tests/ compare it with the oracle's counts:
+ * decisions may differ only for the light SHAPES, whose own surface sits at t = dist - eps up to rounding. */
+int b200rt_debug_lit_counts(b200rt_scene*, int enable);
+int b200rt_debug_get_lit_counts(b200rt_scene*, int camera_index, int32_t* out);
 
 /* Test hook: the device's leaf functions on caller-supplied rows (host pointers).  which: 0 Bounding_box::intersect
  * (in 12: min, max, o, d; out 2: decision of the exact gate, of the filtered gate), 1 BRDF::get_reflectance (in 15:

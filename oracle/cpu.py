@@ -71,11 +71,19 @@ def _desc_addr(host_scene):
     return C.cast(host_scene.desc_ptr, C.c_void_p)
 
 
-def render(host_scene, camera_index=0, rows=(0, 0), seed=0, want_image=True, want_ids=False, threads=None):
-    """Returns (rgbw[H,W,4] or None, ids[H,W,2] or None, t[H,W] or None, Counters)."""
+def render(host_scene, camera_index=0, rows=(0, 0), seed=0, want_image=True, want_ids=False, threads=None,
+           lit_counts=None):
+    """Returns (rgbw[H,W,4] or None, ids[H,W,2] or None, t[H,W] or None, Counters).
+    lit_counts: int32[H, W, n_lights] array that receives, per pixel and light, the number of shadow tests that came
+    out lit (HW5-HW7 shading) — the device's b200rt_debug_lit_counts twin."""
     L = load()
     cam = host_scene.spec.cameras[camera_index]
     w, h = cam["width"], cam["height"]
+    if lit_counts is not None:
+        assert lit_counts.dtype == np.int32 and lit_counts.flags["C_CONTIGUOUS"]
+        L.oracle_set_lit_counts.restype = None
+        L.oracle_set_lit_counts.argtypes = [C.c_void_p]
+        L.oracle_set_lit_counts(lit_counts.ctypes.data)
     rgbw = np.zeros((h, w, 4), np.float32) if want_image else None
     ids = np.full((h, w, 2), -1, np.int32) if want_ids else None
     t = np.full((h, w), np.inf, np.float32) if want_ids else None
@@ -85,6 +93,8 @@ def render(host_scene, camera_index=0, rows=(0, 0), seed=0, want_image=True, wan
                          rgbw.ctypes.data if want_image else None,
                          ids.ctypes.data if want_ids else None, t.ctypes.data if want_ids else None,
                          C.byref(cnt))
+    if lit_counts is not None:
+        L.oracle_set_lit_counts(None)
     if rc != 0:
         raise RuntimeError(f"oracle_render rc={rc}")
     return rgbw, ids, t, cnt

@@ -76,6 +76,11 @@ typedef struct {
   const B200SceneDesc* d;
   OracleCounters* c;
 } Ctx;
+/* Parity hook: per pixel x light, how many shadow tests of direct7 came out "lit" (the device counts the same thing,
+ * b200rt_debug_lit_counts).  The pixel being rendered is thread-local; NULL buffer = off. */
+static int32_t* g_lit_count = NULL;
+static _Thread_local int tl_pixel = -1;
+void oracle_set_lit_counts(int32_t* buf) { g_lit_count = buf; }
 static inline int sem_hw7(const B200SceneDesc* d) { return d->semantics >= B200RT_SEM_HW7; }
 /* HW5 and HW6 shade like HW7's ray-tracing mode (unified light list, clamped cosine, BRDF objects from HW6 on:
  * HW6/src/Scene.cpp:119-301) but without back-face culling, without the n.w_i >= 0 gate in front of the shadow ray,
@@ -1137,6 +1142,7 @@ static v3 direct7(const Ctx* cx, const Ray* ray, const Hit* hit, v3 kd, uint32_t
       Hit sh;
       scene_intersect(cx, &sr, &sh);
       if (sh.t < (ldist - d->shadow_eps) && sh.t > 0.0f) continue;
+      if (g_lit_count && tl_pixel >= 0) __atomic_fetch_add(&g_lit_count[(size_t)tl_pixel * d->n_lights + li], 1, __ATOMIC_RELAXED);
       const v3 Li = light_radiance(d, li, lvec, prob);
       const float cti = fmaxf(0.0f, dot(n, w_i));
       if (B) {
@@ -1378,6 +1384,7 @@ int oracle_render(const B200SceneDesc* d, int camera_index, int row_begin, int r
     for (int j = row_begin; j < row_end; j++) {
       for (int i = col_begin; i < col_end; i++) {
         const int pix = j * W + i;
+        tl_pixel = pix;
         if (hw7 && ns > 1 && rgbw) {
           /* HW7/src/Scene.cpp:35-85: strata loop, box filter (GAUSSIAN_FILTER is off) */
           float acc[4] = {0, 0, 0, 0};

@@ -71,6 +71,14 @@ def main():
             "ref_vs_ref_rel_rmse": float(np.sqrt(np.mean((a[fin] - b[fin]) ** 2)) / a[fin].mean()),
             "ref_vs_ref_rel_rmse_clipped": float(np.sqrt(np.mean((ac[fin] - bc[fin]) ** 2)) / ac[fin].mean()),
             "ref_vs_ref_mean_ratio": float(b[fin].mean() / a[fin].mean())}
+    # 15 x 15 pixel block means (16 x 9 blocks): the per-pixel Monte-Carlo noise drops 15-fold, so a bias of a few per
+    # cent in any region of the image shows.  The second run's block means are kept as the yardstick.
+    blk = lambda x: x.reshape(H // 15, 15, W // 15, 15, 3).mean((1, 3))
+    ba, bb = blk(ac), blk(bc)
+    info["block"] = 15
+    info["ref_vs_ref_block_rel_rmse"] = float(np.sqrt(np.mean((ba - bb) ** 2)) / ba.mean())
+    info["ref_vs_ref_block_max_rel"] = float(np.max(np.abs(ba - bb) / (ba + 0.05 * ba.mean())))
+    info["second_run_block_means"] = [[[round(float(v), 5) for v in px] for px in row] for row in bb]
     np.save(os.path.join(ROOT, "tests", "golden", "cfg4_ref_240x135_1024spp.npy"), a.astype(np.float16))
     json.dump(info, open(os.path.join(ROOT, "tests", "golden", "cfg4_ref.json"), "w"), indent=1)
     print(info)
