@@ -11,11 +11,17 @@ the HW3 dialect, 1 048 352-triangle mesh + 8 instances + 4 spheres, 2 point ligh
 A step = one pass of the hot path over one batch of work per rank:
   cfg1..cfg4  one frame: generate -> (extend -> shade_a -> shadow -> shade_b)* -> combine
   cfg5        one photon pass (PhotonCountPerIteration photons): emit -> (extend -> deposit/scatter)*
-Multi-GPU (one process per GPU, scene replicated):
-  --split cameras  rank r renders frame r of a camera orbit; no data-path collective ("weak")      [default, cfg1-3]
-  --split rows     one frame, contiguous row bands, one all-gather of float4 bands over NCCL ("strong")
-  --split samples  one frame, strata split, one all-reduce(sum) of Pixel{sum c*w, sum w} ("strong") [default, cfg4]
-  cfg5             photons of the pass split, all-reduce(sum) of {S.rgb, n} per hit point ("strong")
+Multi-GPU (one process per GPU, scene replicated, SURVEY.md §8e, include/b200rt.h "multi-GPU"):
+  --split frame    ONE frame per step, shared by all ranks ("strong", the default): the Pixel array lives on rank 0's
+                   GPU; 1-sample cameras are cut into 8-row bands dealt round-robin and every rank's last combine kernel
+                   stores its pixels into rank 0's array over NVLink peer memory; multi-sample cameras are cut into
+                   batches of sample strata, accumulated locally and added with vector atomics over NVLink.  A
+                   system-scope counter at the end of the array tells rank 0's stream when all shares are in.
+                   ms_per_frame is that frame's latency (max over ranks).
+  --split cameras  rank r renders frame r of a camera orbit; no data-path exchange ("weak")
+  cfg5             photons of the pass split by index; after each pass the accepted-photon counts are all-reduced
+                   (NCCL on the scene's stream) so that every rank tests the next pass against the same radii; the
+                   flux sums S are added once per image ("strong")
 """
 from __future__ import annotations
 
@@ -40,7 +46,7 @@ def workloads(args):
     from ceng795_b200 import scenes
     assets = os.path.join(tempfile.gettempdir(), "b200rt_bench_assets")
     os.makedirs(assets, exist_ok=True)
-    spp4 = args.spp or 64
+    spp4 = args.spp or 4096
     return {
         "cfg1": dict(tree="hw1", xml=lambda r: scenes.cfg1_hw1(), base_dir=None,
                      desc="cfg1: HW1 scene, 64 spheres + 2 meshes (2000 tris) + 10 triangles, 3 point lights, "
@@ -52,18 +58,22 @@ def workloads(args):
                      desc=f"cfg3: HW3 distribution ray tracing, 262088-tri mesh, 2 area lights, DOF, glossy mirror, "
                           f"glass, motion blur, 1920x1080, {args.spp or 100} spp"),
         "cfg4": dict(tree="hw7", base_dir=assets,
-                     xml=lambda r: scenes.hw7_scene(assets, width=1920, height=1080, n=224, mesh_slices=(224, 225),
-                                                    spp=spp4, depth=4, path_tracing=True, importance=True,
-                                                    stochastic_lights=True, perlin=True, light_scale=0.25),
-                     desc=f"cfg4: HW7 path tracing (importance sampling, depth 4), 100k-tri textured heightfield + "
-                          f"7 instances of a 100k-tri mesh, 5 BRDFs, image + Perlin textures, LightMesh + LightSphere + "
-                          f"area/point/spot/directional lights, 1920x1080, {spp4} spp"
-                          + ("" if args.spp == 4096 else " (BASELINE: 4096 spp; --spp 4096 runs it)")),
+                     xml=lambda r: scenes.cfg4_hw7(assets, spp=spp4),
+                     desc=f"cfg4: HW7 path tracing (importance sampling, depth 4), Cornell box + LightMesh + LightSphere + "
+                          f"3 instances of a 100k-tri textured mesh, Perlin bump, 5 BRDFs, mirror, glass, 1920x1080, "
+                          f"{spp4} spp camera; a step = {args.strata_per_step or 64} strata of it"),
         "cfg5": dict(tree="ppm", xml=lambda r: scenes.cfg5_ppm(photons_per_iteration=args.photons or 10_000_000),
                      base_dir=None,
                      desc=f"cfg5: PPM, closed box + mirror sphere + glass sphere + 50240-tri mesh, 1 point light, depth 8, "
                           f"1920x1080 eye pass, {args.photons or 10_000_000} photons per pass (a step = one pass)"),
     }
+
+
+def config_dict(args, wl):
+    """The workload both arms are measured on — identical in the two JSON lines."""
+    split = "photons" if wl["tree"] == "ppm" else (args.split or "frame")
+    return {"workload": wl["desc"], "split": split,
+            "l2": "working set (scene + ~1 GB wavefront pool per step) exceeds the 126 MB L2; no explicit flush"}
 
 
 def peaks():
@@ -140,9 +150,10 @@ def reference_sample(args, wl, rays_per_step=None, sample_rays=None):
         xml = scenes.cfg3_hw3(spp=spp)
         frac, what = spp / full, f"{spp} of {full} spp of the same frame"
     elif name == "cfg4":
-        spp, full = 4, (args.spp or 64)
+        spp, full, per_step = 4, (args.spp or 4096), (args.strata_per_step or 64)
         xml = wl["xml"](0).replace(f"<NumSamples>{full}</NumSamples>", f"<NumSamples>{spp}</NumSamples>")
-        frac, what = spp / full, f"{spp} of {full} spp of the same frame"
+        assert f"<NumSamples>{spp}</NumSamples>" in xml
+        frac, what = spp / min(full, per_step), f"{spp} spp of the same frame (a step is {min(full, per_step)} of its {full} strata)"
     elif name == "cfg5":
         full = args.photons or 10_000_000
         n = 400_000
@@ -207,7 +218,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "rays_per_step": rays},
+            "config": config_dict(args, wl), "detail": {"rays_per_step": rays},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": s["cores"], "kind": s["kind"], "sample": s["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -228,19 +239,20 @@ def run_b200(args):
 
     wl = workloads(args)[args.config]
     ppm = wl["tree"] == "ppm"
-    split = args.split or ("samples" if args.config == "cfg4" else "cameras")
+    split = args.split or "frame"
     if ppm:
         split = "photons"
     xml = wl["xml"](rank if split == "cameras" else 0)
     sc = scene.Scene(xml, wl["tree"], device=local, base_dir=wl["base_dir"])
     W, H = sc.image_size(0)
-    opts = {}
-    if world > 1 and split == "rows":
-        b, e = rdist.split_rows(H, rank, world)
-        opts = dict(row_begin=b, row_end=e)
-    if world > 1 and split == "samples":
-        ns = sc.host.desc.cameras[0].samples_sqrt ** 2
-        opts = rdist.split_samples(ns, rank, world)
+    strata = sc.host.desc.cameras[0].samples_sqrt ** 2
+    # cfg4 at its BASELINE size is a 4096-spp camera; a step renders one batch of `strata_per_step` strata of it
+    strata_per_step = min(strata, args.strata_per_step or (64 if args.config == "cfg4" else strata))
+    batches = max(1, strata // strata_per_step)
+    step_no = [0]
+    shared = world > 1 and split == "frame"
+    if shared:
+        rdist.share_frame(sc, rank, world, 0)
     stream = torch.cuda.ExternalStream(sc._L.b200rt_scene_stream(sc._scene), device=local)
     photons = args.photons or (sc.spec.ppm["photon_count_per_iteration"] if ppm else 0)
     ph_first, ph_cnt = rdist.split_photons(photons, rank, world) if ppm else (0, 0)
@@ -253,21 +265,40 @@ def run_b200(args):
             tdist.barrier()
         torch.cuda.synchronize()
 
-    def one_step():
+    def step_opts():
+        """The strata batch of this step (cfg4: 64 of the 4096), then this rank's share of it."""
+        o = {}
+        if strata_per_step < strata:
+            b = (step_no[0] % batches) * strata_per_step
+            o = dict(sample_begin=b, sample_end=b + strata_per_step)
+        step_no[0] += 1
+        if shared:
+            if o:   # a strata batch is cut further by strata
+                b, e = rdist.split_rows(strata_per_step, rank, world)
+                o = dict(sample_begin=o["sample_begin"] + b, sample_end=o["sample_begin"] + e)
+            else:
+                o = {k: v for k, v in sc.multi_share(rank, world, 0).items() if k in
+                     ("row_begin", "row_end", "row_stride", "row_group", "sample_begin", "sample_end")}
+        return o
+
+    def one_step(out=None):
         if ppm:
             st = sc.trace_n_photons(ph_cnt, first_photon=pass_no[0] * photons + ph_first, seed=args.seed)
             pass_no[0] += 1
             if world > 1:
-                p, n = sc.ppm_export()
-                rdist.allreduce_sum(rdist.tensor_from_ptr(p, (n, 4), local).clone())   # {S.rgb, n} over NVLink
+                rdist.ppm_sync_counts(sc, local, stream)   # counts over NVLink (NCCL), on the scene's stream
             return st
-        p, st = sc.render_device(0, seed=args.seed, **opts)
-        if world > 1 and split == "rows":
-            frame = rdist.tensor_from_ptr(p, (H, W, 4), local)
-            rdist.gather_rows(frame[opts["row_begin"]:opts["row_end"]], H, rank, world)
-        elif world > 1 and split == "samples":
-            rdist.allreduce_sum(rdist.tensor_from_ptr(p, (H, W, 4), local))
-        return st
+        o = step_opts()
+        if shared:
+            if rank == 0:
+                sc.frame_begin()
+            st = sc.render_shared(0, seed=args.seed, **o)
+            if rank == 0:
+                sc.frame_collect(world, out)               # waits on the device for every rank's share
+            return st
+        if out is not None:
+            return sc.render_image(0, out=out, seed=args.seed, **o)[1]
+        return sc.render_device(0, seed=args.seed, **o)[1]
 
     for _ in range(args.warmup):
         one_step()
@@ -305,11 +336,15 @@ def run_b200(args):
 
     def e2e_step():
         if ppm:
-            st = sc.trace_n_photons(ph_cnt, first_photon=pass_no[0] * photons + ph_first, seed=args.seed)
-            pass_no[0] += 1
-            sc.density_estimation(photons * pass_no[0], out=out)
+            st = one_step()
+            if world > 1:
+                p, _ = rdist.ppm_sum_state(sc, local, stream)     # flux sums of all ranks, then the image on rank 0
+                if rank == 0:
+                    sc.density_estimation_from(p, photons * pass_no[0], out=out)
+            else:
+                sc.density_estimation(photons * pass_no[0], out=out)
             return st.photon_rays
-        _, st = sc.render_image(0, out=out, seed=args.seed, **opts)
+        st = one_step(out)
         return st.rays_total
 
     for _ in range(max(1, min(3, args.warmup))):
@@ -410,20 +445,20 @@ def run_b200(args):
                    kernel_line(kn.format("true") + " any hit (shadow rays)", sh_bytes, ms_stage["ms_shadow"], n_launch, "l2", "shadow")]
     kernels.sort(key=lambda k: -(k["share_of_step"] or 0.0))
     dom = kernels[0]
-    frames = world if split == "cameras" else 1
+    frames = (world if split == "cameras" else 1) * strata_per_step / strata
     line = {
         "metric": METRIC, "value": rays / ms_total / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak" if split == "cameras" else "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": wl["desc"], "split": split, "frames_per_step": frames,
-                   "rays_per_step": rays / args.steps,
-                   "l2": "working set (scene + ~1 GB wavefront pool per step) exceeds the 126 MB L2; no explicit flush",
+        "config": config_dict(args, wl),
+        "detail": {"rays_per_step": rays / args.steps, "frames_per_step": frames,
                    "scene_bytes": int(sc._L.b200rt_scene_bytes(sc._scene))},
-        "ms_per_frame": ms_total / args.steps,
+        "ms_per_frame": ms_total / args.steps * strata / strata_per_step,
         "stage_ms_per_step": {k: v / args.steps for k, v in ms_stage.items()},
         "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": UNIT, "ms_per_step": e2e_s * 1e3 / args.steps,
-                "h2d_bytes_per_step": 176 + 64, "d2h_bytes_per_step": H * W * 16 * frames},
+                "h2d_bytes_per_step": 176 + 64,
+                "d2h_bytes_per_step": H * W * 16 * (world if split == "cameras" else 1)},
         "gpu_launches": launches_all,
         "clocks": clocks,
         # the dominant kernel BY TIME, against the ceiling its counters name; the other kernels of the step follow
@@ -438,8 +473,8 @@ def run_b200(args):
                      "per_ray": per_ray, "other_kernels": kernels[1:]},
     }
     if ppm:
-        line["config"]["photons_per_step"] = photons
-        line["config"]["hit_points"] = int(eye.hit_points)
+        line["detail"]["photons_per_step"] = photons
+        line["detail"]["hit_points"] = int(eye.hit_points)
         line["photons_per_s"] = photons * args.steps / (ms_total * 1e-3)
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -460,7 +495,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
-    ap.add_argument("--split", default=None, choices=["cameras", "rows", "samples"])
+    ap.add_argument("--split", default=None, choices=["frame", "cameras"])
+    ap.add_argument("--strata-per-step", type=int, default=None,
+                    help="strata of the camera rendered per step (cfg4 default 64 of its 4096)")
     ap.add_argument("--spp", type=int, default=None, help="NumSamples override for cfg3 / cfg4")
     ap.add_argument("--photons", type=int, default=None, help="photons per pass override for cfg5")
     ap.add_argument("--seed", type=int, default=795)

@@ -125,6 +125,12 @@ class RenderOpts(C.Structure):
                 ("sample_begin", c_i), ("sample_end", c_i), ("exact_traversal", c_i), ("contexts", c_i), ("row_group", c_i), ("pad", c_i * 3)]
 
 
+class SharedFrame(C.Structure):
+    """include/b200rt.h: B200SharedFrame — plain bytes, `bytes(frame)` travels through any channel."""
+    _fields_ = [("ipc_handle", C.c_uint8 * 64), ("device_ptr", C.c_uint64), ("pid", C.c_int64),
+                ("tail_offset", C.c_uint64), ("device", c_i), ("width", c_i), ("height", c_i), ("direct", c_i)]
+
+
 class RenderStats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_secondary", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("spheres_tested", C.c_uint64),
@@ -235,6 +241,19 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_ppm_export": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_int64)]),
         "b200rt_ppm_density_from": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
         "b200rt_ppm_get_hit_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, P(C.c_int64)]),
+        "b200rt_frame_export": (C.c_int, [C.c_void_p, C.c_int, P(SharedFrame)]),
+        "b200rt_frame_attach": (C.c_int, [C.c_void_p, P(SharedFrame)]),
+        "b200rt_frame_detach": (C.c_int, [C.c_void_p]),
+        "b200rt_frame_begin": (C.c_int, [C.c_void_p]),
+        "b200rt_render_shared": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), P(RenderStats)]),
+        "b200rt_frame_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, P(C.c_void_p)]),
+        "b200rt_multi_share": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, P(RenderOpts)]),
+        "b200rt_render_multi": (C.c_int, [P(C.c_void_p), C.c_int, C.c_int, P(RenderOpts), C.c_void_p, P(RenderStats)]),
+        "b200rt_ppm_counts_delta": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_int64)]),
+        "b200rt_ppm_counts_apply": (C.c_int, [C.c_void_p]),
+        "b200rt_ppm_eye_pass_multi": (C.c_int, [P(C.c_void_p), C.c_int, C.c_int, C.c_uint64, P(PpmStats)]),
+        "b200rt_ppm_trace_photons_multi": (C.c_int, [P(C.c_void_p), C.c_int, P(PpmOpts), P(PpmStats)]),
+        "b200rt_ppm_density_multi": (C.c_int, [P(C.c_void_p), C.c_int, C.c_double, C.c_void_p]),
         "b200rt_scene_stream": (C.c_void_p, [C.c_void_p]),
         "b200rt_scene_bytes": (C.c_uint64, [C.c_void_p]),
         "b200rt_scene_build_bvh_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

@@ -17,6 +17,7 @@
 #include "ppm_kernels.cuh"
 #include "rt_hw1_fast.cuh"
 #include "tonemap_kernels.cuh"
+#include "multi_gpu.cuh"
 
 extern "C" void b200rt_internal_set_error(const char* msg);
 
@@ -95,6 +96,22 @@ struct b200rt_scene {
   size_t scan_tmp_bytes, items_capacity;
   uint32_t n_hp;
   int ppm_camera;
+  // multi-GPU (multi_gpu.cuh).  Transient, set around a render: where wave 0's combine writes, and what it waits for.
+  float4* rt_frame;                 // nullptr = d_accum
+  const unsigned int* rt_wait_flag; // awaited (>= rt_wait_target) before the first pixel of a frame is written
+  unsigned int rt_wait_target;
+  unsigned int* d_sync_err;         // raised by a wait kernel that timed out
+  // the frame this scene OWNS (exported): counters of b200rt_frame_begin / _collect
+  unsigned int own_frame_no, own_parts_seen;
+  int own_camera;
+  bool own_direct;
+  // the frame this scene CONTRIBUTES to (attached)
+  float4* tgt_frame;
+  FrameTail* tgt_tail;
+  size_t tgt_pixels;
+  int tgt_w, tgt_h;
+  bool tgt_direct, tgt_ipc, tgt_self;
+  unsigned int tgt_frame_no;        // render_shared calls since the attach
 };
 
 namespace {
@@ -178,7 +195,8 @@ int ensure_accum(b200rt_scene* sc, size_t pixels) {
   if (sc->accum_pixels >= pixels) return B200RT_OK;
   if (sc->d_accum) cudaFree(sc->d_accum);
   sc->d_accum = nullptr;
-  CK(cudaMalloc((void**)&sc->d_accum, pixels * sizeof(float4)));
+  CK(cudaMalloc((void**)&sc->d_accum, pixels * sizeof(float4) + sizeof(FrameTail)));   // FrameTail: multi_gpu.cuh
+  CK(cudaMemset(sc->d_accum + pixels, 0, sizeof(FrameTail)));
   sc->accum_pixels = pixels;
   return B200RT_OK;
 }
@@ -301,9 +319,14 @@ int run_waves(b200rt_scene* sc, WaveCtx& cx, bool exact, bool primary_only, bool
     tm.mark(ST_SHADE);
   }
   if (with_shading) {
+    float4* frame = sc->rt_frame ? sc->rt_frame : sc->d_accum;
     for (int d = d_last; d >= 0; d--) {
-      if (S.semantics >= B200RT_SEM_HW5) k_combine7<<<grid_s, 256, 0, st>>>(S, cx.P, cx.d_waves, d, sc->d_accum);
-      else k_combine<<<grid_s, 256, 0, st>>>(S, cx.P, cx.d_waves, d, sc->d_accum);
+      if (d == 0 && sc->rt_wait_flag) {   // a shared frame: its owner must have opened it (multi_gpu.cuh)
+        k_frame_wait<<<1, 1, 0, st>>>(sc->rt_wait_flag, sc->rt_wait_target, sc->d_sync_err, 20000000000ull);
+        (*launches)++;
+      }
+      if (S.semantics >= B200RT_SEM_HW5) k_combine7<<<grid_s, 256, 0, st>>>(S, cx.P, cx.d_waves, d, frame);
+      else k_combine<<<grid_s, 256, 0, st>>>(S, cx.P, cx.d_waves, d, frame);
       (*launches)++;
     }
     tm.mark(ST_SHADE);
@@ -424,7 +447,7 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
   int launches = 0, waves_total = 0;
   Counters hc;
   for (int attempt = 0;; attempt++) {
-    CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), c0.stream));
+    if (!sc->rt_frame) CK(cudaMemsetAsync(sc->d_accum, 0, pixels * sizeof(float4), c0.stream));   // a shared frame is its owner's to clear
     if (sc->S.lit_count) CK(cudaMemsetAsync(sc->d_lit, 0, sc->lit_entries * sizeof(int), c0.stream));
     launches = 0; waves_total = 0;
     CK(cudaEventRecord(c0.ev[0], c0.stream));   // the fork: every context starts after the frame buffer is cleared
@@ -517,7 +540,7 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
 
 void ppm_free(b200rt_scene* sc) {
   HitPoints& H = sc->HP;
-  void* ptrs[] = {H.count, H.pos, H.nrm, H.wo, H.att, H.n, H.state, H.dep, sc->G.cell_count, sc->G.cell_start, sc->G.items,
+  void* ptrs[] = {H.count, H.pos, H.nrm, H.wo, H.att, H.n, H.n_base, H.delta, H.state, H.dep, sc->G.cell_count, sc->G.cell_start, sc->G.items,
                   sc->G.cell_pos,
                   sc->d_pc, sc->d_rtab, sc->d_export, sc->d_scan_tmp, sc->d_sort[0], sc->d_sort[1], sc->d_sort[2],
                   sc->d_sort[3]};
@@ -533,15 +556,19 @@ void ppm_free(b200rt_scene* sc) {
 int ppm_ensure_hit_points(b200rt_scene* sc, size_t cap) {
   HitPoints& H = sc->HP;
   if (H.capacity >= cap) return B200RT_OK;
-  void* ptrs[] = {H.pos, H.nrm, H.wo, H.att, H.n, H.state, H.dep, sc->d_export};
+  void* ptrs[] = {H.pos, H.nrm, H.wo, H.att, H.n, H.n_base, H.delta, H.state, H.dep, sc->d_export};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  H.pos = H.nrm = H.wo = H.att = H.state = H.dep = nullptr; H.n = H.n_base = H.delta = nullptr;
+  sc->d_export = nullptr; H.capacity = 0;
   if (!H.count) CK(cudaMalloc((void**)&H.count, sizeof(unsigned int)));
   CK(cudaMalloc((void**)&H.pos, cap * sizeof(float4)));
   CK(cudaMalloc((void**)&H.nrm, cap * sizeof(float4)));
   CK(cudaMalloc((void**)&H.wo, cap * sizeof(float4)));
   CK(cudaMalloc((void**)&H.att, cap * sizeof(float4)));
   CK(cudaMalloc((void**)&H.n, cap * sizeof(unsigned int)));
+  CK(cudaMalloc((void**)&H.n_base, cap * sizeof(unsigned int)));
+  CK(cudaMalloc((void**)&H.delta, cap * sizeof(unsigned int)));
   CK(cudaMalloc((void**)&H.state, cap * sizeof(float4)));
   CK(cudaMalloc((void**)&H.dep, cap * 4 * sizeof(float4)));
   CK(cudaMalloc((void**)&sc->d_export, cap * sizeof(float4)));
@@ -563,6 +590,47 @@ int ppm_ensure_rtab(b200rt_scene* sc) {
   CK(cudaMalloc((void**)&sc->d_rtab, sizeof(float) * PPM_RTAB));
   CK(cudaMemcpy(sc->d_rtab, r.data(), sizeof(float) * PPM_RTAB, cudaMemcpyHostToDevice));
   return B200RT_OK;
+}
+
+// Canonical numbering of the hit points (multi_gpu.cuh): sort by (pixel, stratum, tree code), then — stable — by home
+// cell when `by_cell`.  cub radix sorts: library calls on a once-per-frame step.
+int ppm_order_hit_points(b200rt_scene* sc, uint32_t n_hp, bool by_cell) {
+  if (n_hp < 2) return B200RT_OK;
+  cudaStream_t st = sc->c0.stream;
+  HitPoints& H = sc->HP;
+  unsigned long long *k64a = nullptr, *k64b = nullptr;
+  uint32_t *ia = nullptr, *ib = nullptr, *k32a = nullptr, *k32b = nullptr;
+  void* tmp = nullptr;
+  int rc = B200RT_OK;
+  const int grid = sc->sm_count * 4;
+  do {
+    if (cudaMalloc((void**)&k64a, 8 * (size_t)n_hp) != cudaSuccess || cudaMalloc((void**)&k64b, 8 * (size_t)n_hp) != cudaSuccess ||
+        cudaMalloc((void**)&ia, 4 * (size_t)n_hp) != cudaSuccess || cudaMalloc((void**)&ib, 4 * (size_t)n_hp) != cudaSuccess) {
+      rc = B200RT_E_CUDA; break;
+    }
+    size_t need64 = 0, need32 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need64, k64a, k64b, ia, ib, (int)n_hp, 0, 64, st);
+    k32a = reinterpret_cast<uint32_t*>(k64a); k32b = reinterpret_cast<uint32_t*>(k64b);
+    cub::DeviceRadixSort::SortPairs(nullptr, need32, k32a, k32b, ia, ib, (int)n_hp, 0, 32, st);
+    const size_t need = std::max(need64, need32);
+    if (cudaMalloc(&tmp, need) != cudaSuccess) { rc = B200RT_E_CUDA; break; }
+    k_ppm_order_keys<<<grid, 256, 0, st>>>(H.wo, H.pos, n_hp, k64a, ia);
+    size_t n1 = need;
+    cub::DeviceRadixSort::SortPairs(tmp, n1, k64a, k64b, ia, ib, (int)n_hp, 0, 64, st);
+    k_ppm_gather4<<<grid, 256, 0, st>>>(H.pos, H.nrm, H.wo, H.att, ib, n_hp, H.dep);
+    k_ppm_scatter4<<<grid, 256, 0, st>>>(H.dep, n_hp, H.pos, H.nrm, H.wo, H.att);
+    if (by_cell) {
+      k_ppm_home_cell_keys<<<grid, 256, 0, st>>>(H.pos, sc->G, n_hp, k32a, ia);
+      size_t n2 = need;
+      cub::DeviceRadixSort::SortPairs(tmp, n2, k32a, k32b, ia, ib, (int)n_hp, 0, 32, st);
+      k_ppm_gather4<<<grid, 256, 0, st>>>(H.pos, H.nrm, H.wo, H.att, ib, n_hp, H.dep);
+      k_ppm_scatter4<<<grid, 256, 0, st>>>(H.dep, n_hp, H.pos, H.nrm, H.wo, H.att);
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = B200RT_E_CUDA;
+  } while (0);
+  if (rc) b200rt_internal_set_error("PPM: ordering the hit points failed (CUDA error / out of memory)");
+  cudaFree(k64a); cudaFree(k64b); cudaFree(ia); cudaFree(ib); cudaFree(tmp);
+  return rc;
 }
 
 }  // namespace
@@ -649,6 +717,14 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
     G.r0 = r0; G.r0sq = r0 * r0;
     G.bbox_min = mk3(mn[0] - r0, mn[1] - r0, mn[2] - r0);  // min_i fl(p_i - r0) == fl(min_i p_i - r0)
     G.hash_scale = (float)(1.0 / ((double)r0 * 2.0));
+    {
+      const char* e = getenv("B200RT_PPM_ORDER");   // "none": append order (one GPU only), "pixel", "cell" (default)
+      if (!(e && !strcmp(e, "none"))) {
+        rc = ppm_order_hit_points(sc, n_hp, !(e && !strcmp(e, "pixel")));
+        if (rc) return rc;
+        launches += 8;
+      }
+    }
     CK(cudaMalloc((void**)&G.cell_count, sizeof(unsigned int) * ((size_t)n_hp + 1)));
     CK(cudaMalloc((void**)&G.cell_start, sizeof(unsigned int) * ((size_t)n_hp + 1)));
     CK(cudaMemsetAsync(G.cell_count, 0, sizeof(unsigned int) * ((size_t)n_hp + 1), st));
@@ -880,6 +956,10 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
   for (int q = 0; q < 4; q++) sc->d_sort[q] = nullptr;
   sc->scan_tmp_bytes = 0; sc->items_capacity = 0; sc->n_hp = 0; sc->ppm_camera = -1;
+  sc->rt_frame = nullptr; sc->rt_wait_flag = nullptr; sc->rt_wait_target = 0; sc->d_sync_err = nullptr;
+  sc->own_frame_no = 0; sc->own_parts_seen = 0; sc->own_camera = -1; sc->own_direct = false;
+  sc->tgt_frame = nullptr; sc->tgt_tail = nullptr; sc->tgt_pixels = 0; sc->tgt_w = 0; sc->tgt_h = 0;
+  sc->tgt_direct = false; sc->tgt_ipc = false; sc->tgt_self = false; sc->tgt_frame_no = 0;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   sc->sm_count = prop.multiProcessorCount;
@@ -1076,6 +1156,8 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   }
   rc = ctx_init(sc->c0);
   if (rc) return rc;
+  CK(cudaMalloc((void**)&sc->d_sync_err, sizeof(unsigned int)));
+  CK(cudaMemset(sc->d_sync_err, 0, sizeof(unsigned int)));
   sc->n_ctx = kDefaultCtx;
   if (const char* e = getenv("B200RT_CONTEXTS")) sc->n_ctx = std::max(1, std::min(kMaxCtx, atoi(e)));
   guard.p = nullptr;
@@ -1091,6 +1173,8 @@ void b200rt_scene_destroy(b200rt_scene* sc) {
   for (void* p : sc->allocs)
     if (p) cudaFree(p);
   ppm_free(sc);
+  if (sc->tgt_frame && sc->tgt_ipc) cudaIpcCloseMemHandle(sc->tgt_frame);
+  if (sc->d_sync_err) cudaFree(sc->d_sync_err);
   if (sc->d_accum) cudaFree(sc->d_accum);
   if (sc->d_lit) cudaFree(sc->d_lit);
   delete sc;
@@ -1474,3 +1558,4 @@ int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t ex
 } B200RT_CATCH
 
 }  // extern "C"
+#include "api_multi.inc"

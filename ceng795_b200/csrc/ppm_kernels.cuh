@@ -33,6 +33,8 @@ struct HitPoints {
   unsigned int* n; // accepted-photon count: a dense 4-byte array (8.7 MB at 1080p) that stays L2-resident, so the
                    // radius test r2(n) of a scanned entry does not cost a DRAM round trip
   float4* state;   // S = sum f*phi/R(k) rgb
+  unsigned int* n_base;  // multi-GPU: n as of the last synchronisation of the counts (multi_gpu.cuh)
+  unsigned int* delta;   // multi-GPU: n - n_base of this GPU, summed over the GPUs in place, then applied
   float4* dep;   // 4 per hit point, 64 bytes: what a deposit reads — {normal, phong exponent}, {w_o, att.r},
                  // {kd, att.g}, {ks, att.b} (built once per eye pass by k_ppm_grid)
 };
@@ -154,7 +156,10 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_eye_shade(DScene S, Pool P, Wa
     const uint32_t hi = warp_append(HP.count, want_hp);
     if (want_hp) {
       if (hi < HP.capacity) {
-        HP.pos[hi] = make_float4(p.x, p.y, p.z, 0.f);
+        // pos.w: the vertex's place in its pixel's tree (stratum << 20 | reflect / transmit code) — with the pixel it
+        // is the canonical sort key of the hit points (multi_gpu.cuh: k_ppm_order_keys)
+        const uint32_t code = depth == 0 ? 0u : (P.key[slot] & 0xfffffu);
+        HP.pos[hi] = make_float4(p.x, p.y, p.z, __uint_as_float(((P.sample[slot] & 0xfffu) << 20) | code));
         HP.nrm[hi] = make_float4(n.x, n.y, n.z, __int_as_float(mat));
         HP.wo[hi] = make_float4(w_o.x, w_o.y, w_o.z, __uint_as_float(P.pixel[slot]));
         HP.att[hi] = make_float4(att.x, att.y, att.z, 1.0f);
@@ -178,7 +183,9 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_eye_shade(DScene S, Pool P, Wa
           P.ray_d[cs] = make_float4(cd.x, cd.y, cd.z, __uint_as_float(depth + 1));
           P.rec0[cs] = make_float4(ca.x, ca.y, ca.z, 0.f);
           P.pixel[cs] = P.pixel[slot];
-          P.key[cs] = 0;
+          P.sample[cs] = P.sample[slot];
+          // tree code of the child: parent * 3 + (1 reflect | 2 transmit); unique down to depth 12 (3^12 < 2^20)
+          P.key[cs] = ((depth == 0 ? 0u : P.key[slot]) * 3u + (uint32_t)(c + 1)) & 0xfffffu;
         } else {
           C->overflow = 1;
         }
@@ -195,7 +202,7 @@ __global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uin
     const float4 q = HP.pos[i];
     if (mode == 0) {
       HP.state[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      HP.n[i] = 0u;
+      HP.n[i] = 0u; HP.n_base[i] = 0u;
       const float4 n4 = HP.nrm[i], w4 = HP.wo[i], a4 = HP.att[i];
       const b200rt_material& m = mats[__float_as_int(n4.w)];
       HP.dep[4 * (size_t)i + 0] = make_float4(n4.x, n4.y, n4.z, m.phong_exponent);
@@ -219,6 +226,17 @@ __global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uin
             }
           }
         }
+  }
+}
+
+// Home cell of every hit point (the cell its position hashes to): second, stable sort key of the canonical numbering,
+// so that the hit points a photon meets while scanning one cell sit in a few runs of consecutive indices.
+__global__ void k_ppm_home_cell_keys(const float4* pos, PpmGrid G, uint32_t n_hp, uint32_t* keys, uint32_t* idx) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
+    const float4 q = pos[i];
+    const v3 hh = (mk3(q.x, q.y, q.z) - G.bbox_min) * G.hash_scale;
+    keys[i] = ppm_hash(G.num_hash, abs((int)hh.x), abs((int)hh.y), abs((int)hh.z));
+    idx[i] = i;
   }
 }
 

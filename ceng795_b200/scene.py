@@ -790,11 +790,143 @@ class Scene:
         rgbw = self.density_estimation(photons if total_num_of_photons is None else total_num_of_photons)
         return rgbw, s0, s1
 
+    # ---- multi-GPU, one process per GPU (include/b200rt.h "multi-GPU"): the handle is plain bytes ---------
+    def frame_export(self, camera_index: int = 0) -> bytes:
+        """Owner: the Pixel array of the camera as a handle other ranks attach to."""
+        self.upload()
+        f = _lib.SharedFrame()
+        _lib.check(self._L.b200rt_frame_export(self._scene, camera_index, C.byref(f)), "b200rt_frame_export")
+        return bytes(f)
+
+    def frame_attach(self, handle: bytes):
+        self.upload()
+        f = _lib.SharedFrame.from_buffer_copy(handle)
+        _lib.check(self._L.b200rt_frame_attach(self._scene, C.byref(f)), "b200rt_frame_attach")
+
+    def frame_detach(self):
+        _lib.check(self._L.b200rt_frame_detach(self._scene), "b200rt_frame_detach")
+
+    def frame_begin(self):
+        _lib.check(self._L.b200rt_frame_begin(self._scene), "b200rt_frame_begin")
+
+    def multi_share(self, part: int, parts: int, camera_index: int = 0, **opts) -> dict:
+        """RenderOpts of share `part` of `parts`, as b200rt_render_multi deals them (8-row bands round-robin, or
+        batches of sample strata)."""
+        o = self._opts(**opts)
+        _lib.check(self._L.b200rt_multi_share(self._scene, camera_index, part, parts, C.byref(o)), "b200rt_multi_share")
+        return {k: getattr(o, k) for k, _ in _lib.RenderOpts._fields_ if k != "pad"}
+
+    def render_shared(self, camera_index: int = 0, **opts):
+        st = _lib.RenderStats()
+        o = self._opts(**opts)
+        _lib.check(self._L.b200rt_render_shared(self._scene, camera_index, C.byref(o), C.byref(st)),
+                   "b200rt_render_shared")
+        return st
+
+    def frame_collect(self, parts: int, out: np.ndarray | None = None):
+        """Owner: waits on the device for `parts` shares; copies the frame into `out` when given.  Returns the frame's
+        device pointer."""
+        p = C.c_void_p()
+        _lib.check(self._L.b200rt_frame_collect(self._scene, parts, out.ctypes.data if out is not None else None,
+                                                C.byref(p)), "b200rt_frame_collect")
+        return p.value
+
+    def ppm_counts_delta(self):
+        """(device pointer of uint32 per hit point, count): photons this GPU accepted since the last sync — sum it
+        over the ranks in place (all-reduce), then ppm_counts_apply()."""
+        p = C.c_void_p()
+        n = C.c_int64()
+        _lib.check(self._L.b200rt_ppm_counts_delta(self._scene, C.byref(p), C.byref(n)), "b200rt_ppm_counts_delta")
+        return p.value, n.value
+
+    def ppm_counts_apply(self):
+        _lib.check(self._L.b200rt_ppm_counts_apply(self._scene), "b200rt_ppm_counts_apply")
+
     def close(self):
         if self._scene is not None:
             self._L.b200rt_scene_destroy(self._scene)
             self._scene = None
         self.host.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiScene:
+    """One host thread, one flattened description, one device scene per GPU: ``MultiScene(xml, "hw3", devices=[0, 1])
+    .render_image(0)`` is the reference's thread fan-out over rows (HW7/src/main.cpp:35-46) with GPUs for threads
+    (b200rt_render_multi), and ``render_ppm`` its photon fan-out (PPM/src/main.cpp:74-98)."""
+
+    def __init__(self, xml: str, semantics="hw3", devices=None, base_dir: str | None = None):
+        self._L = _lib.load()
+        if devices is None:
+            devices = list(range(self._L.b200rt_device_count()))
+        if not devices:
+            raise _lib.B200RTError("MultiScene: no CUDA device — the B200 core has no CPU fallback")
+        self.parts = [Scene(xml, semantics, device=devices[0], base_dir=base_dir)]
+        self.spec, self.host, self.semantics = self.parts[0].spec, self.parts[0].host, self.parts[0].semantics
+        for d in devices[1:]:   # replicas share the flattened host description
+            s = Scene.__new__(Scene)
+            s.spec, s.host, s.semantics, s.device, s._scene, s._L = self.spec, self.host, self.semantics, d, None, self._L
+            s.upload()
+            self.parts.append(s)
+        self.devices = list(devices)
+        self._handles = (C.c_void_p * len(self.parts))(*[p._scene for p in self.parts])
+        self._ppm_camera = 0
+
+    def image_size(self, camera_index=0):
+        return self.parts[0].image_size(camera_index)
+
+    def render_image(self, camera_index: int = 0, out: np.ndarray | None = None, **opts):
+        w, h = self.image_size(camera_index)
+        if out is None:
+            out = np.zeros((h, w, 4), np.float32)
+        st = _lib.RenderStats()
+        o = self.parts[0]._opts(**opts)
+        _lib.check(self._L.b200rt_render_multi(self._handles, len(self.parts), camera_index, C.byref(o), out.ctypes.data,
+                                               C.byref(st)), "b200rt_render_multi")
+        return out, st
+
+    def eye_trace_lines(self, camera_index: int = 0, seed: int = 0):
+        st = _lib.PpmStats()
+        _lib.check(self._L.b200rt_ppm_eye_pass_multi(self._handles, len(self.parts), camera_index, seed, C.byref(st)),
+                   "b200rt_ppm_eye_pass_multi")
+        self._ppm_camera = camera_index
+        return st
+
+    def trace_n_photons(self, n: int, first_photon: int = 0, seed: int = 0):
+        o = _lib.PpmOpts()
+        o.photons = int(n); o.first_photon = int(first_photon); o.seed = int(seed)
+        st = _lib.PpmStats()
+        _lib.check(self._L.b200rt_ppm_trace_photons_multi(self._handles, len(self.parts), C.byref(o), C.byref(st)),
+                   "b200rt_ppm_trace_photons_multi")
+        return st
+
+    def density_estimation(self, total_num_of_photons: float, out: np.ndarray | None = None):
+        w, h = self.image_size(self._ppm_camera)
+        if out is None:
+            out = np.zeros((h, w, 4), np.float32)
+        _lib.check(self._L.b200rt_ppm_density_multi(self._handles, len(self.parts), float(total_num_of_photons),
+                                                    out.ctypes.data), "b200rt_ppm_density_multi")
+        return out
+
+    def render_ppm(self, camera_index: int = 0, photons: int = 0, passes: int = 1, seed: int = 0):
+        """`passes` passes of `photons` photons each, counts synchronised after every pass."""
+        s0 = self.eye_trace_lines(camera_index, seed)
+        s1 = None
+        for k in range(passes):
+            s1 = self.trace_n_photons(photons, k * photons, seed)
+        return self.density_estimation(photons * passes), s0, s1
+
+    def close(self):
+        for p in self.parts[1:]:
+            if p._scene is not None:
+                p._L.b200rt_scene_destroy(p._scene)
+                p._scene = None
+        self.parts[0].close()
 
     def __del__(self):
         try:

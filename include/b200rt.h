@@ -430,6 +430,67 @@ int b200rt_ppm_density_from(b200rt_scene*, const float* d_S_n, double total_num_
 /* test hook: 16 floats per hit point {position, normal, w_o, attenuation, material, pixel, pixel_weight, n} */
 int b200rt_ppm_get_hit_points(b200rt_scene*, float* out16, int64_t capacity, int64_t* n_out);
 
+/* ---- multi-GPU -------------------------------------------------------------------------------
+ * The reference fans the rows of a frame out to its threads, `j = i; j += thread_count`, all of them writing one
+ * shared Pixel array (HW7/src/main.cpp:35-46, HW7/src/Scene.cpp:28,41), and hands photon_count / thread_count
+ * photons of a pass to each thread, all of them updating one shared Hit_point array (PPM/src/main.cpp:74-98,
+ * PPM/src/Scene.cpp:135-169).  Here the scene is replicated, one b200rt_scene per GPU, and
+ *   - an image is split into bands of 8 rows dealt round-robin to the GPUs (1-sample cameras: the final combine
+ *     kernel of every GPU stores its pixels straight into the owner GPU's Pixel array over NVLink peer memory) or into
+ *     batches of sample strata (multi-sample / splatting cameras: each GPU accumulates locally, then adds its frame
+ *     into the owner's with 16-byte vector atomics over NVLink);
+ *   - completion travels the same way: a system-scope counter at the end of the shared frame, bumped by each GPU's
+ *     stream after its stores and awaited by a kernel on the owner's stream.  No host thread, no library collective;
+ *   - a PPM pass is split by photon index (every photon is its own RNG stream) and the accepted-photon counts n are
+ *     summed over the GPUs after each pass, so every GPU tests the next pass against the same shared radii r2(n).
+ * Two ways in: b200rt_render_multi / b200rt_ppm_*_multi for ONE host thread (process) that owns all the GPUs — what the
+ * reference's main would call — and the export / attach primitives underneath for one process per GPU (the handle is
+ * plain bytes: send it through any channel; bench.py uses torch.distributed). */
+typedef struct B200SharedFrame {
+  uint8_t ipc_handle[64];   /* cudaIpcMemHandle_t of the owner's Pixel array (other processes)          */
+  uint64_t device_ptr;      /* the same array as a device pointer (threads of the exporting process)    */
+  int64_t pid;              /* exporting process                                                          */
+  uint64_t tail_offset;     /* bytes from the array to its hand-shake counters (csrc/multi_gpu.cuh: FrameTail) */
+  int32_t device, width, height;
+  int32_t direct;           /* 1: contributors store pixels in place (1-sample cameras); 0: they add     */
+} B200SharedFrame;
+/* Owner: (re)allocates the Pixel array of the camera and describes it. */
+int b200rt_frame_export(b200rt_scene* owner, int camera_index, B200SharedFrame* out);
+/* Contributor (the owner itself included): later b200rt_render_shared calls of this scene go to that frame. */
+int b200rt_frame_attach(b200rt_scene*, const B200SharedFrame*);
+int b200rt_frame_detach(b200rt_scene*);
+/* Owner, once per frame and before anybody's b200rt_render_shared of that frame: opens frame k = 1, 2, ... on the
+ * owner's stream (clears the array unless `direct`), after the previous frame has been collected. */
+int b200rt_frame_begin(b200rt_scene* owner);
+/* Every attached scene, exactly once per frame: renders its share (opts: row_begin / row_stride / row_group or
+ * sample_begin / sample_end) and delivers it into the shared frame, waiting on the device for frame_begin. */
+int b200rt_render_shared(b200rt_scene*, int camera_index, const B200RenderOpts*, B200RenderStats* stats_out);
+/* Owner: waits (on the device) until `parts` shares of the current frame have arrived, then copies the frame to host
+ * memory (rgbw_out NULL: it stays in HBM; d_rgbw_out optional). */
+int b200rt_frame_collect(b200rt_scene* owner, int parts, float* rgbw_out, float** d_rgbw_out);
+/* One host thread, n scenes of the same description on n devices (scenes[0] owns the frame): export + attach + begin +
+ * one worker thread per device for render_shared + collect.  The frame equals b200rt_render's on one device: bit for
+ * bit for 1-sample cameras, up to float summation order for splatting / multi-sample cameras (as the reference's own
+ * threads).  stats_out: sums over the devices; ms_total = the frame's latency on the owner's stream. */
+int b200rt_render_multi(b200rt_scene* const* scenes, int n_scenes, int camera_index, const B200RenderOpts*,
+                        float* rgbw_out, B200RenderStats* stats_out);
+/* Share of device `part` of `parts` for camera `camera_index`, as b200rt_render_multi deals it (exposed so a
+ * process-per-GPU host uses the same split). */
+int b200rt_multi_share(b200rt_scene*, int camera_index, int part, int parts, B200RenderOpts* opts_inout);
+
+/* PPM across GPUs.  Every GPU runs b200rt_ppm_eye_pass itself (hit points are numbered canonically, so index i is the
+ * same hit point everywhere).  After each pass's b200rt_ppm_trace_photons:
+ *   b200rt_ppm_counts_delta  device uint32 per hit point: photons accepted by THIS GPU since the last sync
+ *   (sum it over the GPUs in place: NCCL all-reduce, or b200rt_ppm_sync_counts_multi in one process)
+ *   b200rt_ppm_counts_apply  n = n_at_last_sync + the summed delta, on this GPU
+ * S = sum f*phi/R(k) stays local and additive: sum b200rt_ppm_export's float4 array once, when an image is wanted. */
+int b200rt_ppm_counts_delta(b200rt_scene*, uint32_t** d_delta, int64_t* n_hit_points);
+int b200rt_ppm_counts_apply(b200rt_scene*);
+int b200rt_ppm_eye_pass_multi(b200rt_scene* const* scenes, int n_scenes, int camera_index, uint64_t seed, B200PpmStats*);
+/* One pass: opts->photons photons split by index over the scenes, traced concurrently, counts synchronised. */
+int b200rt_ppm_trace_photons_multi(b200rt_scene* const* scenes, int n_scenes, const B200PpmOpts*, B200PpmStats*);
+int b200rt_ppm_density_multi(b200rt_scene* const* scenes, int n_scenes, double total_num_of_photons, float* rgbw_out);
+
 /* ---- next row: Photographic tonemap + sRGB of the frame b200rt_render* left in HBM ----
  * Replaces Photographic_tmo::apply_tmo + the gamma loop of main (HW7/src/Photographic_tmo.cpp:10-49,
  * HW7/src/main.cpp:59-91) + write_png's clamp: W*H*3 bytes into caller-owned host memory. */

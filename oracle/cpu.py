@@ -114,10 +114,15 @@ def trace_rays(host_scene, rays):
     return ids, t, cnt
 
 
-def ppm(host_scene, camera_index=0, seed=0, n_photons=0, total_num_of_photons=None, want_hit_points=True):
+def ppm(host_scene, camera_index=0, seed=0, n_photons=0, total_num_of_photons=None, want_hit_points=True,
+        reverse_order=False):
     """The PPM frame through the oracle (single sequential photon stream).  Returns
-    (rgbw[H,W,4], hit_points[n,16], initial_radius, Counters)."""
+    (rgbw[H,W,4], hit_points[n,16], initial_radius, Counters).  reverse_order traces the same photons last to first:
+    the reference's threads leave that order free, so two orders are the yardstick for device-vs-oracle bounds."""
     L = load()
+    L.oracle_ppm_photon_order.restype = None
+    L.oracle_ppm_photon_order.argtypes = [C.c_int]
+    L.oracle_ppm_photon_order(1 if reverse_order else 0)
     L.oracle_ppm.restype = C.c_int
     L.oracle_ppm.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                              C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(Counters)]
@@ -132,6 +137,7 @@ def ppm(host_scene, camera_index=0, seed=0, n_photons=0, total_num_of_photons=No
     total = float(n_photons if total_num_of_photons is None else total_num_of_photons)
     rc = L.oracle_ppm(_desc_addr(host_scene), camera_index, seed, int(n_photons), total, rgbw.ctypes.data,
                       hp.ctypes.data if hp is not None else None, cap, C.byref(n_hp), C.byref(r0), C.byref(cnt))
+    L.oracle_ppm_photon_order(0)
     if rc != 0:
         raise RuntimeError(f"oracle_ppm rc={rc}")
     return rgbw, (hp[: n_hp.value] if hp is not None else None), float(r0.value), cnt

@@ -1756,6 +1756,11 @@ static void ppm_photon_trace(const Ctx* cx, OraclePpm* P, Ray ray, v3 flux, uint
 /* The whole PPM frame: reset_hash_grid, eye_trace_lines, build_hash_grid, trace_n_photons (ONE sequential stream,
  * like the reference built without NDEBUG), density_estimation.  hp_out (optional): 16 floats per hit point
  * {position, normal, w_o, attenuation, material, pixel, pixel_weight, n}. */
+/* Test yardstick: 1 = trace the same photons in REVERSE index order.  The order photons reach a hit point in is free
+ * in the reference (its threads race for the mutex, PPM/src/Scene.cpp:135-169); two orders of one photon set bound
+ * what "same photons, any serialisation order" can differ by. */
+static int g_ppm_reverse = 0;
+void oracle_ppm_photon_order(int reverse) { g_ppm_reverse = reverse; }
 int oracle_ppm(const B200SceneDesc* d, int camera_index, uint64_t seed, int64_t n_photons, double total_num_of_photons,
                float* rgbw, float* hp_out, int64_t hp_cap, int64_t* n_hp, float* initial_radius, OracleCounters* counters) {
   if (!d || camera_index < 0 || camera_index >= d->n_cameras || d->n_lights < 1) return -1;
@@ -1789,7 +1794,8 @@ int oracle_ppm(const B200SceneDesc* d, int camera_index, uint64_t seed, int64_t 
   /* Point_light::generate_photon — PPM/src/Point_light.cpp:7-30 (theta = 2*pi*xi: Appendix B.6) */
   const b200rt_light* L = d->lights;
   OracleCounters pc; memset(&pc, 0, sizeof(pc));
-  for (int64_t i = 0; i < n_photons; i++) {
+  for (int64_t ii = 0; ii < n_photons; ii++) {
+    const int64_t i = g_ppm_reverse ? n_photons - 1 - ii : ii;
     const uint32_t key = rng_mix(rng_mix(s0 ^ 0x50484F54u, (uint32_t)i), (uint32_t)((uint64_t)i >> 32));
     const v3 flux = muls(ld(L->intensity), (float)(M_PI * 4.0f));
     const float le1 = PPM_DRAW(light, key, 0);

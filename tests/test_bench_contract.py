@@ -32,7 +32,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "Mrays/sec" and line["unit"] == "Mrays/s"
     assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1
     assert line["value"] > 0 and line["ms_per_step"] > 0
-    assert line["config"]["workload"].startswith("cfg2") and line["config"]["rays_per_step"] == 5939386
+    assert line["config"]["workload"].startswith("cfg2") and line["detail"]["rays_per_step"] == 5939386
+    assert set(line["config"]) == {"workload", "split", "l2"} and line["config"]["split"] == "frame"   # what the own arm prints too
     cb = line["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
