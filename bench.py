@@ -257,6 +257,8 @@ def run_b200(args):
     photons = args.photons or (sc.spec.ppm["photon_count_per_iteration"] if ppm else 0)
     ph_first, ph_cnt = rdist.split_photons(photons, rank, world) if ppm else (0, 0)
     pass_no = [0]
+    if ppm and world > 1:
+        sc.ppm_set_share(rank, world)
     eye = sc.eye_trace_lines(0, seed=args.seed) if ppm else None
 
     def barrier():

@@ -249,6 +249,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_frame_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, P(C.c_void_p)]),
         "b200rt_multi_share": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, P(RenderOpts)]),
         "b200rt_render_multi": (C.c_int, [P(C.c_void_p), C.c_int, C.c_int, P(RenderOpts), C.c_void_p, P(RenderStats)]),
+        "b200rt_ppm_set_share": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
         "b200rt_ppm_counts_delta": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_int64)]),
         "b200rt_ppm_counts_apply": (C.c_int, [C.c_void_p]),
         "b200rt_ppm_eye_pass_multi": (C.c_int, [P(C.c_void_p), C.c_int, C.c_int, C.c_uint64, P(PpmStats)]),

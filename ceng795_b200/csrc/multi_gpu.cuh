@@ -59,13 +59,18 @@ __global__ void __launch_bounds__(256) k_frame_add(const float4* __restrict__ lo
 }
 
 // ---- PPM: accepted-photon counts across GPUs -------------------------------------------------------------------
-__global__ void k_ppm_counts_delta(const unsigned int* n, const unsigned int* n_base, unsigned int* delta, uint32_t n_hp) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) delta[i] = n[i] - n_base[i];
+// A GPU that is share `part` of `parts` claims the indices n_base + part + j * parts (ppm_kernels.cuh: HitPoints), so its
+// n holds n_base + part + parts * (photons it accepted since the last sync).
+__global__ void k_ppm_counts_delta(const unsigned int* n, const unsigned int* n_base, unsigned int* delta, uint32_t n_hp,
+                                   uint32_t part, uint32_t parts) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x)
+    delta[i] = (n[i] - n_base[i] - part) / parts;
 }
-__global__ void k_ppm_counts_apply(unsigned int* n, unsigned int* n_base, const unsigned int* delta_sum, uint32_t n_hp) {
+__global__ void k_ppm_counts_apply(unsigned int* n, unsigned int* n_base, const unsigned int* delta_sum, uint32_t n_hp,
+                                   uint32_t part) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
     const unsigned int v = n_base[i] + delta_sum[i];
-    n_base[i] = v; n[i] = v;
+    n_base[i] = v; n[i] = v + part;
   }
 }
 struct PeerPtrs {
@@ -81,14 +86,14 @@ __global__ void k_ppm_sum_peer_counts(unsigned int* mine, PeerPtrs peers, uint32
   }
 }
 // Runs on the owner: out[i] = {sum of S.rgb over all devices, n} — the additive PPM state, fixed device order.
-__global__ void k_ppm_sum_peer_state(const float4* mine, PeerPtrs peers, const unsigned int* n, float4* out, uint32_t n_hp) {
+__global__ void k_ppm_sum_peer_state(const float4* mine, PeerPtrs peers, const unsigned int* n_base, float4* out, uint32_t n_hp) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
     float4 s = mine[i];
     for (int k = 0; k < peers.n; k++) {
       const float4 v = reinterpret_cast<const float4*>(peers.p[k])[i];
       s.x += v.x; s.y += v.y; s.z += v.z;
     }
-    s.w = (float)n[i];
+    s.w = (float)n_base[i];   // the counts as of the last synchronisation (= all of them after a pass)
     out[i] = s;
   }
 }

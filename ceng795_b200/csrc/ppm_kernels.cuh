@@ -34,11 +34,23 @@ struct HitPoints {
                    // radius test r2(n) of a scanned entry does not cost a DRAM round trip
   float4* state;   // S = sum f*phi/R(k) rgb
   unsigned int* n_base;  // multi-GPU: n as of the last synchronisation of the counts (multi_gpu.cuh)
-  unsigned int* delta;   // multi-GPU: n - n_base of this GPU, summed over the GPUs in place, then applied
+  unsigned int* delta;   // multi-GPU: photons this GPU accepted since then, summed over the GPUs in place, then applied
+  // multi-GPU: this GPU is share `part` of `parts`.  Between two synchronisations it claims the acceptance indices
+  // n_base + part, n_base + part + parts, ... — every parts-th one, because the other GPUs accept photons of the same
+  // stream at the same rate — so the radius a photon is tested against follows the GLOBAL count, not this GPU's
+  // fraction of it.  parts = 1 (one GPU): indices 0, 1, 2, ... as the reference's single array.
+  uint32_t part, parts;
   float4* dep;   // 4 per hit point, 64 bytes: what a deposit reads — {normal, phong exponent}, {w_o, att.r},
                  // {kd, att.g}, {ks, att.b} (built once per eye pass by k_ppm_grid)
 };
 __device__ __forceinline__ unsigned int* hp_n(const HitPoints& HP, unsigned int i) { return HP.n + i; }
+__device__ __forceinline__ unsigned int hp_stride(const HitPoints& HP) { return HP.parts > 1u ? HP.parts : 1u; }
+// accepted photons of hit point i as far as this GPU knows: all GPUs' up to the last sync + its own since
+__device__ __forceinline__ unsigned int hp_count(const HitPoints& HP, unsigned int i) {
+  if (HP.parts <= 1u) return HP.n[i];
+  const unsigned int b = HP.n_base[i];
+  return b + (HP.n[i] - b - HP.part) / HP.parts;
+}
 struct PpmGrid {
   uint32_t num_hash;
   unsigned int* cell_count;  // num_hash + 1 (becomes the fill cursor)
@@ -202,7 +214,7 @@ __global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uin
     const float4 q = HP.pos[i];
     if (mode == 0) {
       HP.state[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      HP.n[i] = 0u; HP.n_base[i] = 0u;
+      HP.n[i] = HP.parts > 1u ? HP.part : 0u; HP.n_base[i] = 0u;
       const float4 n4 = HP.nrm[i], w4 = HP.wo[i], a4 = HP.att[i];
       const b200rt_material& m = mats[__float_as_int(n4.w)];
       HP.dep[4 * (size_t)i + 0] = make_float4(n4.x, n4.y, n4.z, m.phong_exponent);
@@ -411,7 +423,7 @@ __global__ void __launch_bounds__(RT_BLOCK, PPM_MIN_BLOCKS) k_ppm_photon_shade(D
         bool accepted = false;
         for (;;) {
           if (!(d2 <= G.r0sq * ppm_R(G, n_old))) break;
-          const unsigned int prev = atomicCAS(hp_n(HP, hi), n_old, n_old + 1u);
+          const unsigned int prev = atomicCAS(hp_n(HP, hi), n_old, n_old + hp_stride(HP));
           if (prev == n_old) { accepted = true; break; }
           n_old = prev;
         }
@@ -531,7 +543,7 @@ __global__ void k_ppm_count_rays(const WaveInfo* waves, int d, PpmCounters* PC) 
 __global__ void k_ppm_export(HitPoints HP, uint32_t n_hp, float4* out) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
     const float4 s = HP.state[i];
-    out[i] = make_float4(s.x, s.y, s.z, (float)*hp_n(HP, i));
+    out[i] = make_float4(s.x, s.y, s.z, (float)hp_count(HP, i));
   }
 }
 // tau/(pi r2 N) = S/(pi r0^2 N) since tau = R(n) S and r2 = r0^2 R(n)
@@ -553,6 +565,6 @@ __global__ void k_ppm_pack_hit_points(HitPoints HP, uint32_t n_hp, float* out16)
     float* o = out16 + 16 * (size_t)i;
     o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = n.x; o[4] = n.y; o[5] = n.z; o[6] = w.x; o[7] = w.y; o[8] = w.z;
     o[9] = a.x; o[10] = a.y; o[11] = a.z; o[12] = (float)__float_as_int(n.w); o[13] = (float)__float_as_uint(w.w);
-    o[14] = a.w; o[15] = (float)*hp_n(HP, i);
+    o[14] = a.w; o[15] = (float)hp_count(HP, i);
   }
 }

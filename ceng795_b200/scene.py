@@ -831,6 +831,11 @@ class Scene:
                                                 C.byref(p)), "b200rt_frame_collect")
         return p.value
 
+    def ppm_set_share(self, part: int, parts: int):
+        """Before eye_trace_lines: this scene traces share `part` of `parts` of every photon pass."""
+        self.upload()
+        _lib.check(self._L.b200rt_ppm_set_share(self._scene, part, parts), "b200rt_ppm_set_share")
+
     def ppm_counts_delta(self):
         """(device pointer of uint32 per hit point, count): photons this GPU accepted since the last sync — sum it
         over the ranks in place (all-reduce), then ppm_counts_apply()."""

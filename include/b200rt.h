@@ -484,6 +484,11 @@ int b200rt_multi_share(b200rt_scene*, int camera_index, int part, int parts, B20
  *   (sum it over the GPUs in place: NCCL all-reduce, or b200rt_ppm_sync_counts_multi in one process)
  *   b200rt_ppm_counts_apply  n = n_at_last_sync + the summed delta, on this GPU
  * S = sum f*phi/R(k) stays local and additive: sum b200rt_ppm_export's float4 array once, when an image is wanted. */
+/* Before the eye pass: this scene is share `part` of `parts` of every photon pass.  Between two synchronisations it
+ * claims the acceptance indices n + part, n + part + parts, ... of a hit point (every parts-th one: the other GPUs
+ * accept photons of the same stream at the same rate), so the radius r2(index) it tests against follows the global
+ * count instead of lagging behind it by the other GPUs' share.  Default (1 GPU): part 0 of 1. */
+int b200rt_ppm_set_share(b200rt_scene*, int part, int parts);
 int b200rt_ppm_counts_delta(b200rt_scene*, uint32_t** d_delta, int64_t* n_hit_points);
 int b200rt_ppm_counts_apply(b200rt_scene*);
 int b200rt_ppm_eye_pass_multi(b200rt_scene* const* scenes, int n_scenes, int camera_index, uint64_t seed, B200PpmStats*);

@@ -97,12 +97,14 @@ def test_render_shared_without_begin_times_out_cleanly_is_not_needed_when_owner_
 @pytest.mark.gpu
 def test_ppm_hit_points_are_numbered_canonically_and_counts_synchronise(gpu):
     """Two scenes (two 'GPUs'): the same hit point has the same index in both — the eye pass appends with atomics, the
-    canonical sort undoes that — and with the counts summed after every pass the two-share run follows the one-share
-    run's radius schedule: accepted photons within 3 %, image mean within 2 %."""
+    canonical sort undoes that — and with every share claiming every second acceptance index and the counts summed after
+    every pass, the two-share run follows the one-share run's radius schedule: accepted photons within 3 %, image mean
+    within 2 %.  (Each share counting only its own photons between syncs accepts 7 % more: its radii lag.)"""
     import torch
     from ceng795_b200 import dist as rdist
     xml = scenes.cfg5_ppm(width=160, height=120, mesh_slices=(24, 22))
     a, b, one = (scene.Scene(xml, "ppm") for _ in range(3))
+    a.ppm_set_share(0, 2); b.ppm_set_share(1, 2)   # each claims every second acceptance index between two syncs
     for s in (a, b, one):
         s.eye_trace_lines(0, seed=5)
     ha, hb = a.hit_points(), b.hit_points()

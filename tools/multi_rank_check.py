@@ -73,6 +73,7 @@ def main():
             sc.close()
         # ---- (3) PPM: photons split by index, counts synchronised after every pass ----
         sc = scene.Scene(scenes.cfg5_ppm(width=160, height=120, mesh_slices=(24, 22)), "ppm", device=local)
+        sc.ppm_set_share(rank, world)
         s0 = sc.eye_trace_lines(0, seed=5)
         hp = sc.hit_points()
         passes, photons = 4, 200_000
