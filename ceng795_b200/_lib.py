@@ -257,6 +257,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_ppm_density_multi": (C.c_int, [P(C.c_void_p), C.c_int, C.c_double, C.c_void_p]),
         "b200rt_scene_stream": (C.c_void_p, [C.c_void_p]),
         "b200rt_scene_bytes": (C.c_uint64, [C.c_void_p]),
+        "b200rt_builder_set_instance_transform": (C.c_int, [C.c_void_p, C.c_int, fp, fp]),
+        "b200rt_builder_set_sphere_transform": (C.c_int, [C.c_void_p, C.c_int, fp, fp]),
+        "b200rt_builder_refit": (C.c_int, [C.c_void_p, P(P(SceneDesc))]),
+        "b200rt_scene_refit": (C.c_int, [C.c_void_p, P(SceneDesc), C.POINTER(C.c_float)]),
         "b200rt_scene_build_bvh_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
         "b200rt_lbvh_ranges": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
         "b200rt_lbvh_morton63": (C.c_uint64, [C.c_float, C.c_float, C.c_float]),

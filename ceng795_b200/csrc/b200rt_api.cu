@@ -71,6 +71,7 @@ struct b200rt_scene {
   bool has_transparency, has_mirror;
   int sm_count;
   int n_meshes;
+  int n_nodes, n_triprims, n_light_cdf, n_materials;   // what was uploaded (b200rt_scene_refit checks against it)
   int wide_nodes, wide_depth;   // the 8-wide tree (0 nodes: the scene walks the binary tree)
   int wide_blocks;              // resident CTAs per SM of k_trace_wide (4 / 6 / 8)
   int n_ctx;                    // contexts a frame is cut into (B200RT_CONTEXTS, default kDefaultCtx)
@@ -1128,6 +1129,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   }
   UP(S.meshes, meshes, d->n_meshes, b200rt_mesh);
   sc->n_meshes = d->n_meshes;
+  sc->n_nodes = d->n_nodes; sc->n_triprims = d->n_triprims; sc->n_light_cdf = d->n_light_cdf; sc->n_materials = d->n_materials;
   UP(S.inst, d->instances, d->n_instances, b200rt_instance);
   UP(S.spheres, d->spheres, d->n_spheres, b200rt_sphere);
   UP(S.triprims, d->triprims, d->n_triprims, b200rt_triprim);
@@ -1440,6 +1442,53 @@ int b200rt_scene_build_bvh_device(b200rt_scene* sc, float* ms_out) try {
   sc->S.fast_tris = d_ftris;
   sc->S.fast_tri_ref = d_fref;
   sc->S.use_wide = 0;   // the device-built tree is binary: k_trace_fast walks it
+  return B200RT_OK;
+} B200RT_CATCH
+
+// Moving geometry between frames: the description's top-level part (b200rt_builder_refit, or a producer that walked the
+// reference's objects again) replaces the resident one; meshes, their trees and every triangle record stay in HBM.
+int b200rt_scene_refit(b200rt_scene* sc, const B200SceneDesc* d, float* ms_out) try {
+  if (!sc || !d) {
+    b200rt_internal_set_error("b200rt_scene_refit: null argument");
+    return B200RT_E_INVALID;
+  }
+  const DScene& S = sc->S;
+  if (d->semantics != S.semantics || d->n_tris != S.n_tris || d->n_meshes != sc->n_meshes || d->n_nodes != sc->n_nodes ||
+      d->n_instances != S.n_inst || d->n_spheres != S.n_spheres || d->n_triprims != sc->n_triprims ||
+      d->n_lights != S.n_lights || d->n_light_cdf != sc->n_light_cdf || d->n_materials != sc->n_materials) {
+    b200rt_internal_set_error("b200rt_scene_refit: the description has other objects than the resident scene (refit moves objects, it does not add or remove them)");
+    return B200RT_E_INVALID;
+  }
+  std::vector<float> flat;
+  const bool ok = b200rt_wide::flatten_top(d, flat);
+  const size_t n_top = ok ? flat.size() / 8 : 0;
+  if ((S.n_top > 0) != (n_top > 0 && n_top <= RT_TOP_LINEAR_MAX) || (S.n_top > 0 && (int)n_top != S.n_top)) {
+    b200rt_internal_set_error("b200rt_scene_refit: the flat top-level list changed size");
+    return B200RT_E_UNSUPPORTED;
+  }
+  CK(cudaSetDevice(sc->device));
+  cudaStream_t st = sc->c0.stream;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+#define PUT(dst, src, n, T) \
+  if ((n) > 0) CK(cudaMemcpyAsync(const_cast<void*>(reinterpret_cast<const void*>(dst)), (src), sizeof(T) * (size_t)(n), cudaMemcpyHostToDevice, st))
+  PUT(S.nodes, d->nodes, d->n_nodes, b200rt_bvh_node);   // Scene::bvh's nodes follow the mesh trees' in one array
+  PUT(S.inst, d->instances, d->n_instances, b200rt_instance);
+  PUT(S.spheres, d->spheres, d->n_spheres, b200rt_sphere);
+  PUT(S.triprims, d->triprims, d->n_triprims, b200rt_triprim);
+  PUT(S.lights, d->lights, d->n_lights, b200rt_light);
+  PUT(S.light_cdf, d->light_cdf, d->n_light_cdf, float);
+  PUT(S.light_tri, d->light_tri, d->n_light_cdf, int32_t);
+  if (S.n_top > 0) PUT(S.top_objs, flat.data(), flat.size(), float);
+#undef PUT
+  CK(cudaEventRecord(e1, st));
+  CK(cudaStreamSynchronize(st));   // the host arrays may go away after the call
+  sc->S.root = d->root;
+  memcpy(sc->S.root_box, d->root_box, sizeof(sc->S.root_box));
+  if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return B200RT_OK;
 } B200RT_CATCH
 

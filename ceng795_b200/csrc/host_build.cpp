@@ -382,8 +382,246 @@ struct b200rt_builder {
   std::vector<b200rt_instance> instances;
   std::vector<b200rt_sphere> spheres;
   std::vector<b200rt_triprim> triprims;
+  size_t n_mesh_nodes, n_user_lights;   // what b->nodes / b->lights held before the top-level phase (refit truncates to it)
   bool finished;
 };
+
+namespace {
+
+// Second half of b200rt_builder_finish, and the whole of b200rt_builder_refit: the top-level objects with their
+// transforms and world boxes, Scene::bvh over them, and the objects' ranks.  Mesh trees are not touched.
+int finish_top(b200rt_builder* b) {
+  const int nv = (int)(b->verts.size() / 3);
+  auto vert = [&](int i) { return load3(&b->verts[3 * (size_t)i]); };
+  auto check_idx = [&](int i) { return i >= 0 && i < nv; };
+  const bool hw1 = b->semantics == B200RT_SEM_HW1;
+  // ---- top-level objects in the reference's push order ----------------------
+  std::vector<Obj> top;
+  b->instances.clear(); b->spheres.clear(); b->triprims.clear();
+  std::vector<InstIn> all_inst(b->inst_in);
+  all_inst.insert(all_inst.end(), b->light_inst_in.begin(), b->light_inst_in.end());
+  for (const InstIn& in : all_inst) {
+    b200rt_instance fi;
+    std::memset(&fi, 0, sizeof(fi));
+    fi.light = -1;
+    const b200rt_mesh& fm = b->meshes[in.mesh];
+    Box mb(load3(fm.root_box), load3(fm.root_box + 3));
+    Box ib;
+    if (in.is_light) {
+      // Light_mesh sits in Scene::bvh itself; its box is the OBJECT-space mesh box (SURVEY Appendix B.5)
+      // and it has no gate of its own (HW7/include/Light_mesh.h:52-68).
+      bool ok;
+      fill_xf(in.xf, fi.inv, fi.nrm, fi.fwd, ok);
+      if (!ok) {
+        g_host_error = "NOT INVERTIBLE MATRIX (light mesh)";
+        return B200RT_E_SINGULAR;
+      }
+      ib = mb;
+      fi.flags |= B200RT_INST_LIGHT;
+      // Light_mesh ctor: areas of the TRANSFORMED triangles in the (BVH-reordered) vector order
+      const MeshIn& lm = b->meshes_in[in.mesh];
+      b200rt_light L;
+      std::memset(&L, 0, sizeof(L));
+      L.kind = B200RT_LIGHT_MESH;
+      store3(L.intensity, lm.radiance);
+      L.object = (int)b->instances.size();
+      L.cdf_begin = (int)b->light_cdf.size();
+      L.cdf_count = fm.tri_count;
+      float total = 0.0f;
+      std::vector<float> areas;
+      for (int k = 0; k < fm.tri_count; k++) {
+        const int32_t* vi = &b->tri_vidx[3 * (size_t)(fm.tri_begin + k)];
+        const V3 v0 = mul_point(in.xf, vert(vi[0])), v1 = mul_point(in.xf, vert(vi[1])), v2 = mul_point(in.xf, vert(vi[2]));
+        const float area = length(cross(v1 - v0, v2 - v0)) / 2;
+        total += area;
+        areas.push_back(area);
+      }
+      float cum = 0.0f;
+      for (int k = 0; k < fm.tri_count; k++) {
+        cum += areas[k];
+        b->light_cdf.push_back(cum / total);
+        b->light_tri.push_back(fm.tri_begin + k);
+      }
+      L.total_area = total;
+      fi.light = (int)b->lights.size();
+      b->lights.push_back(L);
+    } else if (in.direct) {
+      ib = mb;  // HW2: Mesh::get_bounding_box = bvh box (HW2/Mesh.h:17-19)
+      M4 id = M4::identity();
+      bool ok;
+      fill_xf(id, fi.inv, fi.nrm, fi.fwd, ok);
+      fi.flags |= B200RT_INST_DIRECT;
+    } else {
+      bool ok;
+      fill_xf(in.xf, fi.inv, fi.nrm, fi.fwd, ok);
+      if (!ok) {
+        g_host_error = "NOT INVERTIBLE MATRIX (mesh instance)";
+        return B200RT_E_SINGULAR;
+      }
+      ib = apply_transform(mb, in.xf);  // Mesh_instance ctor HW3/include/Mesh.h:101-111
+      motion_expand(ib, in.velocity);
+      if (in.velocity != V3(0.f)) fi.flags |= B200RT_INST_MOVING;
+    }
+    put_box(fi.box, fi.box + 3, ib);
+    store3(fi.velocity, in.velocity);
+    fi.mesh = in.mesh;
+    fi.material = in.material;
+    fi.texture = b->meshes_in[in.mesh].texture;  // instances take the base mesh's texture (HW7/src/Scene.cpp:1182)
+    if (b->semantics >= B200RT_SEM_HW7 && in.material >= 0 && in.material < (int)b->materials.size()) {
+      const float* tr = b->materials[in.material].transparency;
+      const float* mr = b->materials[in.material].mirror;
+      bool refr = (tr[0] != 0.f || tr[1] != 0.f || tr[2] != 0.f);
+      // PPM: material_type == mt_refractive, and mirror wins over transparency (PPM/src/Material.cpp:55-61)
+      if (b->semantics == B200RT_SEM_PPM && (mr[0] != 0.f || mr[1] != 0.f || mr[2] != 0.f)) refr = false;
+      if (refr) fi.flags |= B200RT_INST_REFRACTIVE;
+    }
+    Obj o;
+    o.ref = B200RT_REF(in.is_light ? B200RT_KIND_LIGHTINST : B200RT_KIND_INSTANCE, b->instances.size());
+    o.box = ib;
+    top.push_back(o);
+    b->instances.push_back(fi);
+  }
+  if (!hw1) {
+    for (const TriIn& t : b->tri_in) {
+      if (!check_idx(t.idx[0]) || !check_idx(t.idx[1]) || !check_idx(t.idx[2])) {
+        g_host_error = "triangle index out of range";
+        return B200RT_E_INVALID;
+      }
+      b200rt_triprim ft;
+      std::memset(&ft, 0, sizeof(ft));
+      const V3 v0 = vert(t.idx[0]), v1 = vert(t.idx[1]), v2 = vert(t.idx[2]);
+      store3(ft.v0, v0); store3(ft.a1, v0 - v1); store3(ft.a2, v0 - v2);
+      store3(ft.normal, normalize(cross(v1 - v0, v2 - v0)));
+      Box tb = tri_box(v0, v1, v2);
+      const bool ident = is_identity(t.xf);  // Triangle ctor HW3/src/Triangle.cpp:20-41
+      bool ok;
+      fill_xf(t.xf, ft.inv, ft.nrm, nullptr, ok);
+      if (!ok) {
+        g_host_error = "NOT INVERTIBLE MATRIX (triangle)";
+        return B200RT_E_SINGULAR;
+      }
+      if (ident) ft.flags |= B200RT_XF_IDENTITY; else tb = apply_transform(tb, t.xf);
+      ft.material = t.material;
+      Obj o;
+      o.ref = B200RT_REF(B200RT_KIND_TRIPRIM, b->triprims.size());
+      o.box = tb;
+      top.push_back(o);
+      b->triprims.push_back(ft);
+    }
+  }
+  std::vector<SphIn> all_sph(b->light_sph_in);
+  all_sph.insert(all_sph.end(), b->sph_in.begin(), b->sph_in.end());
+  for (const SphIn& s : all_sph) {
+    if (!check_idx(s.center_vertex)) {
+      g_host_error = "sphere centre index out of range";
+      return B200RT_E_INVALID;
+    }
+    b200rt_sphere fs;
+    std::memset(&fs, 0, sizeof(fs));
+    const V3 c = vert(s.center_vertex);
+    store3(fs.center, c);
+    fs.radius = s.radius;
+    const bool ident = is_identity(s.xf);
+    bool ok;
+    fill_xf(s.xf, fs.inv, fs.nrm, fs.fwd, ok);
+    if (!ok) {
+      g_host_error = "NOT INVERTIBLE MATRIX (sphere)";
+      return B200RT_E_SINGULAR;
+    }
+    const V3 delta(s.radius);
+    Box sb(c - delta, c + delta);  // Sphere ctor HW3/include/Sphere.h:18-37
+    if (ident) fs.flags |= B200RT_XF_IDENTITY; else sb = apply_transform(sb, s.xf);
+    motion_expand(sb, s.velocity);
+    if (s.velocity != V3(0.f)) fs.flags |= B200RT_XF_MOVING;
+    store3(fs.velocity, s.velocity);
+    fs.material = s.material;
+    fs.texture = s.texture;
+    fs.light = -1;
+    if (s.is_light) {
+      fs.flags |= B200RT_XF_LIGHT;
+      b200rt_light L;
+      std::memset(&L, 0, sizeof(L));
+      L.kind = B200RT_LIGHT_SPHERE;
+      store3(L.intensity, s.radiance);
+      L.object = (int)b->spheres.size();
+      fs.light = (int)b->lights.size();
+      b->lights.push_back(L);
+    }
+    Obj o;
+    o.ref = B200RT_REF(B200RT_KIND_SPHERE, b->spheres.size());
+    o.box = sb;
+    top.push_back(o);
+    b->spheres.push_back(fs);
+  }
+
+  if (b->semantics == B200RT_SEM_PPM) {
+    // PPM loads spheres before meshes (PPM/src/Scene.cpp:487-498): objects = spheres, base instances, instances
+    std::vector<Obj> reordered;
+    for (const Obj& o : top)
+      if (B200RT_REF_KIND(o.ref) == B200RT_KIND_SPHERE) reordered.push_back(o);
+    for (const Obj& o : top)
+      if (B200RT_REF_KIND(o.ref) != B200RT_KIND_SPHERE) reordered.push_back(o);
+    top.swap(reordered);
+  }
+  // ---- Scene::bvh = BVH::create_bvh(objects) — HW3/src/Scene.cpp:871 --------
+  Box root_box;
+  std::vector<uint32_t> order;
+  if (hw1 || top.empty()) {
+    b->desc.root = B200RT_REF_NONE;
+    for (const Obj& o : top) order.push_back(o.ref);
+  } else if (top.size() == 1) {
+    b->desc.root = top[0].ref;
+    root_box = top[0].box;
+    order.push_back(top[0].ref);
+  } else {
+    BuildOut bo{&b->nodes, &order, nullptr};
+    uint32_t r = build_bvh(top, 0, (int)top.size(), 0, bo, root_box);
+    b->desc.root = B200RT_REF(B200RT_KIND_INNER, r);
+  }
+  put_box(b->desc.root_box, b->desc.root_box + 3, root_box);
+  for (size_t k = 0; k < order.size(); k++) {
+    const uint32_t r = order[k];
+    const uint32_t idx = B200RT_REF_INDEX(r);
+    switch (B200RT_REF_KIND(r)) {
+      case B200RT_KIND_LIGHTINST:
+      case B200RT_KIND_INSTANCE: b->instances[idx].rank = (int)k; break;
+      case B200RT_KIND_SPHERE: b->spheres[idx].rank = (int)k; break;
+      case B200RT_KIND_TRIPRIM: b->triprims[idx].rank = (int)k; break;
+      default: break;
+    }
+  }
+
+  return B200RT_OK;
+}
+
+void fill_desc(b200rt_builder* b) {
+  const int nv = (int)(b->verts.size() / 3);
+  B200SceneDesc& d = b->desc;
+  d.n_nodes = (int)b->nodes.size();           d.nodes = b->nodes.data();
+  d.n_tris = (int)(b->tri_info.size() / 2);   d.tri_geom = b->tri_geom.data();
+  d.tri_vidx = b->tri_vidx.data();            d.tri_info = b->tri_info.data();
+  d.n_fast_nodes = (int)b->fast_nodes.size(); d.fast_nodes = b->fast_nodes.data();
+  d.n_fast_tris = (int)b->fast_tri_ref.size();
+  d.fast_tri_geom = b->fast_tri_geom.data();  d.fast_tri_ref = b->fast_tri_ref.data();
+  d.tri_gate = b->tri_gate.data();
+  d.n_verts = nv;                             d.vert_pos = b->verts.data();
+  d.vert_normal = b->vert_normal.data();
+  d.n_meshes = (int)b->meshes.size();         d.meshes = b->meshes.data();
+  d.n_instances = (int)b->instances.size();   d.instances = b->instances.data();
+  d.n_spheres = (int)b->spheres.size();       d.spheres = b->spheres.data();
+  d.n_triprims = (int)b->triprims.size();     d.triprims = b->triprims.data();
+  d.n_materials = (int)b->materials.size();   d.materials = b->materials.data();
+  d.n_lights = (int)b->lights.size();         d.lights = b->lights.data();
+  d.n_cameras = (int)b->cameras.size();       d.cameras = b->cameras.data();
+  d.tri_uv = b->tri_uv.data();                d.tri_tex = b->tri_tex.data();
+  d.n_textures = (int)b->textures.size();     d.textures = b->textures.data();
+  d.n_texels = (int64_t)b->texels.size();     d.texels = b->texels.data();
+  d.n_brdfs = (int)b->brdfs.size();           d.brdfs = b->brdfs.data();
+  d.n_light_cdf = (int)b->light_cdf.size();   d.light_cdf = b->light_cdf.data();
+  d.light_tri = b->light_tri.data();
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -868,226 +1106,52 @@ int b200rt_builder_finish(b200rt_builder* b, const B200SceneDesc** out) try {
     store3(&b->vert_normal[3 * (size_t)i], n);
   }
 
-  // ---- top-level objects in the reference's push order ----------------------
-  std::vector<Obj> top;
-  b->instances.clear(); b->spheres.clear(); b->triprims.clear();
-  std::vector<InstIn> all_inst(b->inst_in);
-  all_inst.insert(all_inst.end(), b->light_inst_in.begin(), b->light_inst_in.end());
-  for (const InstIn& in : all_inst) {
-    b200rt_instance fi;
-    std::memset(&fi, 0, sizeof(fi));
-    fi.light = -1;
-    const b200rt_mesh& fm = b->meshes[in.mesh];
-    Box mb(load3(fm.root_box), load3(fm.root_box + 3));
-    Box ib;
-    if (in.is_light) {
-      // Light_mesh sits in Scene::bvh itself; its box is the OBJECT-space mesh box (SURVEY Appendix B.5)
-      // and it has no gate of its own (HW7/include/Light_mesh.h:52-68).
-      bool ok;
-      fill_xf(in.xf, fi.inv, fi.nrm, fi.fwd, ok);
-      if (!ok) {
-        g_host_error = "NOT INVERTIBLE MATRIX (light mesh)";
-        return B200RT_E_SINGULAR;
-      }
-      ib = mb;
-      fi.flags |= B200RT_INST_LIGHT;
-      // Light_mesh ctor: areas of the TRANSFORMED triangles in the (BVH-reordered) vector order
-      const MeshIn& lm = b->meshes_in[in.mesh];
-      b200rt_light L;
-      std::memset(&L, 0, sizeof(L));
-      L.kind = B200RT_LIGHT_MESH;
-      store3(L.intensity, lm.radiance);
-      L.object = (int)b->instances.size();
-      L.cdf_begin = (int)b->light_cdf.size();
-      L.cdf_count = fm.tri_count;
-      float total = 0.0f;
-      std::vector<float> areas;
-      for (int k = 0; k < fm.tri_count; k++) {
-        const int32_t* vi = &b->tri_vidx[3 * (size_t)(fm.tri_begin + k)];
-        const V3 v0 = mul_point(in.xf, vert(vi[0])), v1 = mul_point(in.xf, vert(vi[1])), v2 = mul_point(in.xf, vert(vi[2]));
-        const float area = length(cross(v1 - v0, v2 - v0)) / 2;
-        total += area;
-        areas.push_back(area);
-      }
-      float cum = 0.0f;
-      for (int k = 0; k < fm.tri_count; k++) {
-        cum += areas[k];
-        b->light_cdf.push_back(cum / total);
-        b->light_tri.push_back(fm.tri_begin + k);
-      }
-      L.total_area = total;
-      fi.light = (int)b->lights.size();
-      b->lights.push_back(L);
-    } else if (in.direct) {
-      ib = mb;  // HW2: Mesh::get_bounding_box = bvh box (HW2/Mesh.h:17-19)
-      M4 id = M4::identity();
-      bool ok;
-      fill_xf(id, fi.inv, fi.nrm, fi.fwd, ok);
-      fi.flags |= B200RT_INST_DIRECT;
-    } else {
-      bool ok;
-      fill_xf(in.xf, fi.inv, fi.nrm, fi.fwd, ok);
-      if (!ok) {
-        g_host_error = "NOT INVERTIBLE MATRIX (mesh instance)";
-        return B200RT_E_SINGULAR;
-      }
-      ib = apply_transform(mb, in.xf);  // Mesh_instance ctor HW3/include/Mesh.h:101-111
-      motion_expand(ib, in.velocity);
-      if (in.velocity != V3(0.f)) fi.flags |= B200RT_INST_MOVING;
-    }
-    put_box(fi.box, fi.box + 3, ib);
-    store3(fi.velocity, in.velocity);
-    fi.mesh = in.mesh;
-    fi.material = in.material;
-    fi.texture = b->meshes_in[in.mesh].texture;  // instances take the base mesh's texture (HW7/src/Scene.cpp:1182)
-    if (b->semantics >= B200RT_SEM_HW7 && in.material >= 0 && in.material < (int)b->materials.size()) {
-      const float* tr = b->materials[in.material].transparency;
-      const float* mr = b->materials[in.material].mirror;
-      bool refr = (tr[0] != 0.f || tr[1] != 0.f || tr[2] != 0.f);
-      // PPM: material_type == mt_refractive, and mirror wins over transparency (PPM/src/Material.cpp:55-61)
-      if (b->semantics == B200RT_SEM_PPM && (mr[0] != 0.f || mr[1] != 0.f || mr[2] != 0.f)) refr = false;
-      if (refr) fi.flags |= B200RT_INST_REFRACTIVE;
-    }
-    Obj o;
-    o.ref = B200RT_REF(in.is_light ? B200RT_KIND_LIGHTINST : B200RT_KIND_INSTANCE, b->instances.size());
-    o.box = ib;
-    top.push_back(o);
-    b->instances.push_back(fi);
-  }
-  if (!hw1) {
-    for (const TriIn& t : b->tri_in) {
-      if (!check_idx(t.idx[0]) || !check_idx(t.idx[1]) || !check_idx(t.idx[2])) {
-        g_host_error = "triangle index out of range";
-        return B200RT_E_INVALID;
-      }
-      b200rt_triprim ft;
-      std::memset(&ft, 0, sizeof(ft));
-      const V3 v0 = vert(t.idx[0]), v1 = vert(t.idx[1]), v2 = vert(t.idx[2]);
-      store3(ft.v0, v0); store3(ft.a1, v0 - v1); store3(ft.a2, v0 - v2);
-      store3(ft.normal, normalize(cross(v1 - v0, v2 - v0)));
-      Box tb = tri_box(v0, v1, v2);
-      const bool ident = is_identity(t.xf);  // Triangle ctor HW3/src/Triangle.cpp:20-41
-      bool ok;
-      fill_xf(t.xf, ft.inv, ft.nrm, nullptr, ok);
-      if (!ok) {
-        g_host_error = "NOT INVERTIBLE MATRIX (triangle)";
-        return B200RT_E_SINGULAR;
-      }
-      if (ident) ft.flags |= B200RT_XF_IDENTITY; else tb = apply_transform(tb, t.xf);
-      ft.material = t.material;
-      Obj o;
-      o.ref = B200RT_REF(B200RT_KIND_TRIPRIM, b->triprims.size());
-      o.box = tb;
-      top.push_back(o);
-      b->triprims.push_back(ft);
-    }
-  }
-  std::vector<SphIn> all_sph(b->light_sph_in);
-  all_sph.insert(all_sph.end(), b->sph_in.begin(), b->sph_in.end());
-  for (const SphIn& s : all_sph) {
-    if (!check_idx(s.center_vertex)) {
-      g_host_error = "sphere centre index out of range";
-      return B200RT_E_INVALID;
-    }
-    b200rt_sphere fs;
-    std::memset(&fs, 0, sizeof(fs));
-    const V3 c = vert(s.center_vertex);
-    store3(fs.center, c);
-    fs.radius = s.radius;
-    const bool ident = is_identity(s.xf);
-    bool ok;
-    fill_xf(s.xf, fs.inv, fs.nrm, fs.fwd, ok);
-    if (!ok) {
-      g_host_error = "NOT INVERTIBLE MATRIX (sphere)";
-      return B200RT_E_SINGULAR;
-    }
-    const V3 delta(s.radius);
-    Box sb(c - delta, c + delta);  // Sphere ctor HW3/include/Sphere.h:18-37
-    if (ident) fs.flags |= B200RT_XF_IDENTITY; else sb = apply_transform(sb, s.xf);
-    motion_expand(sb, s.velocity);
-    if (s.velocity != V3(0.f)) fs.flags |= B200RT_XF_MOVING;
-    store3(fs.velocity, s.velocity);
-    fs.material = s.material;
-    fs.texture = s.texture;
-    fs.light = -1;
-    if (s.is_light) {
-      fs.flags |= B200RT_XF_LIGHT;
-      b200rt_light L;
-      std::memset(&L, 0, sizeof(L));
-      L.kind = B200RT_LIGHT_SPHERE;
-      store3(L.intensity, s.radiance);
-      L.object = (int)b->spheres.size();
-      fs.light = (int)b->lights.size();
-      b->lights.push_back(L);
-    }
-    Obj o;
-    o.ref = B200RT_REF(B200RT_KIND_SPHERE, b->spheres.size());
-    o.box = sb;
-    top.push_back(o);
-    b->spheres.push_back(fs);
-  }
-
-  if (b->semantics == B200RT_SEM_PPM) {
-    // PPM loads spheres before meshes (PPM/src/Scene.cpp:487-498): objects = spheres, base instances, instances
-    std::vector<Obj> reordered;
-    for (const Obj& o : top)
-      if (B200RT_REF_KIND(o.ref) == B200RT_KIND_SPHERE) reordered.push_back(o);
-    for (const Obj& o : top)
-      if (B200RT_REF_KIND(o.ref) != B200RT_KIND_SPHERE) reordered.push_back(o);
-    top.swap(reordered);
-  }
-  // ---- Scene::bvh = BVH::create_bvh(objects) — HW3/src/Scene.cpp:871 --------
-  Box root_box;
-  std::vector<uint32_t> order;
-  if (hw1 || top.empty()) {
-    b->desc.root = B200RT_REF_NONE;
-    for (const Obj& o : top) order.push_back(o.ref);
-  } else if (top.size() == 1) {
-    b->desc.root = top[0].ref;
-    root_box = top[0].box;
-    order.push_back(top[0].ref);
-  } else {
-    BuildOut bo{&b->nodes, &order, nullptr};
-    uint32_t r = build_bvh(top, 0, (int)top.size(), 0, bo, root_box);
-    b->desc.root = B200RT_REF(B200RT_KIND_INNER, r);
-  }
-  put_box(b->desc.root_box, b->desc.root_box + 3, root_box);
-  for (size_t k = 0; k < order.size(); k++) {
-    const uint32_t r = order[k];
-    const uint32_t idx = B200RT_REF_INDEX(r);
-    switch (B200RT_REF_KIND(r)) {
-      case B200RT_KIND_LIGHTINST:
-      case B200RT_KIND_INSTANCE: b->instances[idx].rank = (int)k; break;
-      case B200RT_KIND_SPHERE: b->spheres[idx].rank = (int)k; break;
-      case B200RT_KIND_TRIPRIM: b->triprims[idx].rank = (int)k; break;
-      default: break;
-    }
-  }
-
-  B200SceneDesc& d = b->desc;
-  d.n_nodes = (int)b->nodes.size();           d.nodes = b->nodes.data();
-  d.n_tris = (int)(b->tri_info.size() / 2);   d.tri_geom = b->tri_geom.data();
-  d.tri_vidx = b->tri_vidx.data();            d.tri_info = b->tri_info.data();
-  d.n_fast_nodes = (int)b->fast_nodes.size(); d.fast_nodes = b->fast_nodes.data();
-  d.n_fast_tris = (int)b->fast_tri_ref.size();
-  d.fast_tri_geom = b->fast_tri_geom.data();  d.fast_tri_ref = b->fast_tri_ref.data();
-  d.tri_gate = b->tri_gate.data();
-  d.n_verts = nv;                             d.vert_pos = b->verts.data();
-  d.vert_normal = b->vert_normal.data();
-  d.n_meshes = (int)b->meshes.size();         d.meshes = b->meshes.data();
-  d.n_instances = (int)b->instances.size();   d.instances = b->instances.data();
-  d.n_spheres = (int)b->spheres.size();       d.spheres = b->spheres.data();
-  d.n_triprims = (int)b->triprims.size();     d.triprims = b->triprims.data();
-  d.n_materials = (int)b->materials.size();   d.materials = b->materials.data();
-  d.n_lights = (int)b->lights.size();         d.lights = b->lights.data();
-  d.n_cameras = (int)b->cameras.size();       d.cameras = b->cameras.data();
-  d.tri_uv = b->tri_uv.data();                d.tri_tex = b->tri_tex.data();
-  d.n_textures = (int)b->textures.size();     d.textures = b->textures.data();
-  d.n_texels = (int64_t)b->texels.size();     d.texels = b->texels.data();
-  d.n_brdfs = (int)b->brdfs.size();           d.brdfs = b->brdfs.data();
-  d.n_light_cdf = (int)b->light_cdf.size();   d.light_cdf = b->light_cdf.data();
-  d.light_tri = b->light_tri.data();
+  b->n_mesh_nodes = b->nodes.size();
+  b->n_user_lights = b->lights.size();
+  const int rc_top = finish_top(b);
+  if (rc_top) return rc_top;
+  fill_desc(b);
   b->finished = true;
+  *out = &b->desc;
+  return B200RT_OK;
+} B200RT_CATCH
+
+/* ---- moving geometry between frames (include/b200rt.h: "refit") ---- */
+int b200rt_builder_set_instance_transform(b200rt_builder* b, int instance, const float xf[16], const float velocity[3]) try {
+  if (!b || !xf || instance < 0 || instance >= (int)b->inst_in.size()) {
+    g_host_error = "b200rt_builder_set_instance_transform: bad instance index";
+    return B200RT_E_INVALID;
+  }
+  InstIn& i = b->inst_in[(size_t)instance];
+  if (i.direct) {
+    g_host_error = "b200rt_builder_set_instance_transform: HW2 meshes have no transform";
+    return B200RT_E_UNSUPPORTED;
+  }
+  i.xf = M4::from(xf);
+  i.velocity = velocity ? load3(velocity) : V3(0.f);
+  return B200RT_OK;
+} B200RT_CATCH
+int b200rt_builder_set_sphere_transform(b200rt_builder* b, int sphere, const float xf[16], const float velocity[3]) try {
+  if (!b || !xf || sphere < 0 || sphere >= (int)b->sph_in.size()) {
+    g_host_error = "b200rt_builder_set_sphere_transform: bad sphere index";
+    return B200RT_E_INVALID;
+  }
+  b->sph_in[(size_t)sphere].xf = M4::from(xf);
+  b->sph_in[(size_t)sphere].velocity = velocity ? load3(velocity) : V3(0.f);
+  return B200RT_OK;
+} B200RT_CATCH
+int b200rt_builder_refit(b200rt_builder* b, const B200SceneDesc** out) try {
+  if (!b || !out || !b->finished) {
+    g_host_error = "b200rt_builder_refit: b200rt_builder_finish first";
+    return B200RT_E_INVALID;
+  }
+  // everything the top-level phase appended goes; the mesh trees, triangle records and gates stay
+  b->nodes.resize(b->n_mesh_nodes);
+  b->lights.resize(b->n_user_lights);
+  b->light_cdf.clear(); b->light_tri.clear();
+  const int rc = finish_top(b);
+  if (rc) { b->finished = false; return rc; }
+  fill_desc(b);
   *out = &b->desc;
   return B200RT_OK;
 } B200RT_CATCH

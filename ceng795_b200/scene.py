@@ -560,6 +560,39 @@ class HostScene:
         d = self.desc
         return np.ctypeslib.as_array(d.tri_geom, shape=(d.n_tris, 12)) if d.n_tris else np.zeros((0, 12), np.float32)
 
+    def move_instance(self, instance: int, xf, velocity=(0.0, 0.0, 0.0)) -> None:
+        """New 4x4 matrix (row-major, 16 floats) and velocity of a top-level mesh instance; mesh m's base instance is
+        instance m, the XML's MeshInstance k is instance len(meshes) + k.  Takes effect at refit()."""
+        m = np.ascontiguousarray(xf, np.float32).reshape(16)
+        v = np.ascontiguousarray(velocity, np.float32).reshape(3)
+        _lib.check(self._L.b200rt_builder_set_instance_transform(self._b, int(instance), _lib.fptr(m), _lib.fptr(v)),
+                   "b200rt_builder_set_instance_transform")
+
+    def move_sphere(self, sphere: int, xf, velocity=(0.0, 0.0, 0.0)) -> None:
+        m = np.ascontiguousarray(xf, np.float32).reshape(16)
+        v = np.ascontiguousarray(velocity, np.float32).reshape(3)
+        _lib.check(self._L.b200rt_builder_set_sphere_transform(self._b, int(sphere), _lib.fptr(m), _lib.fptr(v)),
+                   "b200rt_builder_set_sphere_transform")
+
+    def refit(self) -> None:
+        """Re-runs the top-level half of the flattening (transforms, world boxes, Scene::bvh, ranks) after
+        move_instance / move_sphere; mesh trees and triangle records are reused."""
+        out = C.POINTER(_lib.SceneDesc)()
+        _lib.check(self._L.b200rt_builder_refit(self._b, C.byref(out)), "b200rt_builder_refit")
+        self.desc_ptr = out
+        self.desc = out.contents
+
+    def translation(self, x, y, z):
+        m = np.zeros(16, np.float32)
+        self._L.b200rt_xf_translation(float(x), float(y), float(z), _lib.fptr(m))
+        return m
+
+    def xf_mul(self, a, b_):
+        o = np.zeros(16, np.float32)
+        self._L.b200rt_xf_mul(_lib.fptr(np.ascontiguousarray(a, np.float32)), _lib.fptr(np.ascontiguousarray(b_, np.float32)),
+                              _lib.fptr(o))
+        return o
+
     def save(self, path: str) -> None:
         """Binary cache of the flattened description (include/b200rt.h: b200rt_scene_desc_save)."""
         _lib.check(self._L.b200rt_scene_desc_save(self.desc_ptr, os.fsencode(path)), "b200rt_scene_desc_save")
@@ -651,6 +684,15 @@ class Scene:
         for k, v in kw.items():
             setattr(o, k, v)
         return o
+
+    def refit(self) -> float:
+        """After host.move_instance / host.move_sphere: refits the host description and copies its top-level half
+        over the resident scene (b200rt_scene_refit).  Returns the device time of the copy in ms."""
+        self.host.refit()
+        self.upload()
+        ms = C.c_float(0.0)
+        _lib.check(self._L.b200rt_scene_refit(self._scene, self.host.desc_ptr, C.byref(ms)), "b200rt_scene_refit")
+        return float(ms.value)
 
     def build_bvh_device(self) -> float:
         """Rebuilds the device-walked tree of every mesh ON the device (LBVH); returns the build time in ms."""

@@ -548,6 +548,25 @@ int b200rt_scene_build_bvh_device(b200rt_scene*, float* ms_out);
 int b200rt_lbvh_ranges(const uint64_t* sorted_keys, int n, int32_t* first_last_split);
 uint64_t b200rt_lbvh_morton63(float x, float y, float z);
 
+/* ---- next row (second half): refit for geometry that moves between frames ----
+ * The reference has one answer to a moved object: parse and build everything again (its Scene is immutable;
+ * per-ray motion blur is Translation(velocity * time) * M inverted inside Mesh_instance::intersect,
+ * HW7/include/Mesh.h:92-104, which the device restates per ray because the 4x4 cofactor inverse of the composed matrix
+ * is what decides the hit bits).  For a host that animates a scene frame by frame:
+ *   b200rt_builder_set_instance_transform / _set_sphere_transform   new matrix and velocity of a top-level object
+ *       (instance index: as b200rt_builder_add_instance returned it; mesh m's base instance is index m when all meshes
+ *       are added first, as the loader does)
+ *   b200rt_builder_refit    re-runs ONLY the top-level half of b200rt_builder_finish — inverse and normal matrices,
+ *       world boxes (Mesh_instance ctor, HW3/include/Mesh.h:101-111), Scene::bvh over the objects, ranks; the result
+ *       equals a fresh build of the moved scene byte for byte; mesh trees, triangle records and gates are reused
+ *   b200rt_scene_refit      copies that top-level half over the resident scene: kilobytes instead of the whole
+ *       description; meshes, both of their trees and all triangle data stay in HBM.  ms_out: device time of the copy.
+ * Deforming meshes (vertices change) are the other half of rank 1: b200rt_scene_build_bvh_device above. */
+int b200rt_builder_set_instance_transform(b200rt_builder*, int instance, const float xf[16], const float velocity[3]);
+int b200rt_builder_set_sphere_transform(b200rt_builder*, int sphere, const float xf[16], const float velocity[3]);
+int b200rt_builder_refit(b200rt_builder*, const B200SceneDesc** out);
+int b200rt_scene_refit(b200rt_scene*, const B200SceneDesc*, float* ms_out);
+
 /* Measurement aid: streaming-read bandwidth over a `bytes` working set, `iters` passes, in GB/s.
  * 48 MB measures the L2 (the denominator for scene fetches when the tree is L2-resident), >= 1 GB measures HBM. */
 int b200rt_measure_read_bandwidth(int device, uint64_t bytes, int iters, double* gbs_out);
