@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "Scene.h"
+#include "b200_host.h"
 #include "b200rt.h"
 #include "lodepng/lodepng.h"
 
@@ -25,12 +26,12 @@ int main(int argc, char* argv[]) {
   Scene scene(argv[1]);
   std::cout << "Scene is parsed" << std::endl;
   b200rt_flat_hw1* flat = b200rt_flatten_hw1(scene);
-  b200rt_scene* gpu = nullptr;
-  if (b200rt_scene_create(b200rt_flat_hw1_desc(flat), /*device*/ 0, &gpu) != B200RT_OK) {
-    std::cerr << "b200rt: " << b200rt_last_error() << std::endl;
+  B200Devices gpus;                       // one replica per GPU: the reference's thread_count (b200_host.h)
+  if (gpus.create(b200rt_flat_hw1_desc(flat)) != 0) {
     b200rt_flat_hw1_free(flat);
     return 2;
   }
+  AsyncWriter writer;                     // camera i's encode overlaps camera i+1's render
   int rc = 0;
   for (int index = 0; index < (int)scene.cameras.size() && rc == 0; index++) {
     const Camera& camera = scene.cameras[index];
@@ -41,7 +42,7 @@ int main(int argc, char* argv[]) {
     opts.row_stride = 1;
     B200RenderStats stats = {};
     const auto start = std::chrono::steady_clock::now();
-    if (b200rt_render(gpu, index, &opts, rgbw.data(), &stats) != B200RT_OK) {
+    if (gpus.render(index, &opts, rgbw.data(), &stats) != B200RT_OK) {
       std::cerr << "b200rt: " << b200rt_last_error() << std::endl;
       rc = 3;
       break;
@@ -55,16 +56,22 @@ int main(int argc, char* argv[]) {
         image[4 * p + c] = (unsigned char)std::min(255, std::max(0, int(v)));
       }
     }
-    const unsigned error = lodepng::encode(camera.get_filename().c_str(), image.data(), width, height);
-    if (error) {
-      std::cout << "encoder error " << error << ": " << lodepng_error_text(error) << std::endl;
-      rc = 4;
-    }
+    const std::string filename = camera.get_filename();
+    writer.submit([filename, width, height, img = std::move(image)]() -> int {
+      const unsigned error = lodepng::encode(filename.c_str(), img.data(), width, height);
+      if (error) {
+        std::cout << "encoder error " << error << ": " << lodepng_error_text(error) << std::endl;
+        return 4;
+      }
+      return 0;
+    });
     std::cout << camera.get_filename() << "(" << width << "x" << height << ") is saved in: " << ms << " milliseconds ("
               << (stats.rays_primary + stats.rays_shadow + stats.rays_secondary) << " rays, " << stats.launches
-              << " kernel launches)" << std::endl;
+              << " kernel launches, " << gpus.size() << " GPU" << (gpus.size() > 1 ? "s" : "") << ")" << std::endl;
   }
-  b200rt_scene_destroy(gpu);
+  const int wrc = writer.finish();        // every file is on disk before the program reports success
+  if (!rc) rc = wrc;
+  gpus.destroy();
   b200rt_flat_hw1_free(flat);
   return rc;
 }

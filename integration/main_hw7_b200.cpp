@@ -18,6 +18,7 @@
 
 #include "Photographic_tmo.h"
 #include "Scene.h"
+#include "b200_host.h"
 #include "b200rt.h"
 #include "lodepng.h"
 
@@ -34,12 +35,12 @@ int main(int argc, char* argv[]) {
   Scene scene(argv[1]);
   std::cout << "Scene is parsed" << std::endl;
   b200rt_flat_hw7* flat = b200rt_flatten_hw7(scene);
-  b200rt_scene* gpu = nullptr;
-  if (b200rt_scene_create(b200rt_flat_hw7_desc(flat), /*device*/ 0, &gpu) != B200RT_OK) {
-    std::cerr << "b200rt: " << b200rt_last_error() << std::endl;
+  B200Devices gpus;                       // one replica per GPU: the reference's thread_count (b200_host.h)
+  if (gpus.create(b200rt_flat_hw7_desc(flat)) != 0) {
     b200rt_flat_hw7_free(flat);
     return 2;
   }
+  AsyncWriter writer;                     // camera i's encode overlaps camera i+1's render (HW7/src/main.cpp:105-198)
   int rc = 0;
   for (int index = 0; index < (int)scene.cameras.size() && rc == 0; index++) {
     const Camera& camera = scene.cameras[index];
@@ -51,7 +52,7 @@ int main(int argc, char* argv[]) {
     opts.seed = 795;
     B200RenderStats stats = {};
     const auto start = std::chrono::steady_clock::now();
-    if (b200rt_render(gpu, index, &opts, rgbw.data(), &stats) != B200RT_OK) {
+    if (gpus.render(index, &opts, rgbw.data(), &stats) != B200RT_OK) {
       std::cerr << "b200rt: " << b200rt_last_error() << std::endl;
       rc = 3;
       break;
@@ -60,7 +61,7 @@ int main(int argc, char* argv[]) {
     const Photographic_tmo* tmo = dynamic_cast<const Photographic_tmo*>(camera.get_tmo());
     if (tmo) {
       std::vector<unsigned char> rgb8(n * 3);
-      if (b200rt_tonemap_photographic(gpu, index, tmo->image_key_, tmo->saturation_percentage_, tmo->saturation_,
+      if (b200rt_tonemap_photographic(gpus.scenes[0], index, tmo->image_key_, tmo->saturation_percentage_, tmo->saturation_,
                                       rgb8.data()) != B200RT_OK) {
         std::cerr << "b200rt: " << b200rt_last_error() << std::endl;
         rc = 3;
@@ -79,16 +80,22 @@ int main(int argc, char* argv[]) {
     }
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - start).count();
     const std::string stem = camera.get_filename().substr(0, camera.get_filename().find_last_of("."));
-    const unsigned error = lodepng::encode((stem + ".png").c_str(), image.data(), width, height);
-    if (error) {
-      std::cout << "encoder error " << error << ": " << lodepng_error_text(error) << std::endl;
-      rc = 4;
-    }
+    const std::string png = stem + ".png";
+    writer.submit([png, width, height, img = std::move(image)]() -> int {
+      const unsigned error = lodepng::encode(png.c_str(), img.data(), width, height);
+      if (error) {
+        std::cout << "encoder error " << error << ": " << lodepng_error_text(error) << std::endl;
+        return 4;
+      }
+      return 0;
+    });
     std::cout << stem << "(" << width << "x" << height << ") is saved in: " << ms << " milliseconds ("
               << (stats.rays_primary + stats.rays_shadow + stats.rays_secondary) << " rays, " << stats.launches
-              << " kernel launches)" << std::endl;
+              << " kernel launches, " << gpus.size() << " GPU" << (gpus.size() > 1 ? "s" : "") << ")" << std::endl;
   }
-  b200rt_scene_destroy(gpu);
+  const int wrc = writer.finish();        // every file is on disk before the program reports success
+  if (!rc) rc = wrc;
+  gpus.destroy();
   b200rt_flat_hw7_free(flat);
   return rc;
 }

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "Scene.h"
+#include "b200_host.h"
 #include "b200rt.h"
 #include "lodepng.h"
 
@@ -45,12 +46,14 @@ int main(int argc, char* argv[]) {
   int thread_count = (int)std::thread::hardware_concurrency();
   if (thread_count == 0) thread_count = 1;
   b200rt_flat_ppm* flat = b200rt_flatten_ppm(scene);
-  b200rt_scene* gpu = nullptr;
-  if (b200rt_scene_create(b200rt_flat_ppm_desc(flat), /*device*/ 0, &gpu) != B200RT_OK) {
-    std::cerr << "b200rt: " << b200rt_last_error() << std::endl;
+  B200Devices gpus;                       // one replica per GPU: main's photon fan-out over threads, over GPUs
+  if (gpus.create(b200rt_flat_ppm_desc(flat)) != 0) {
     b200rt_flat_ppm_free(flat);
     return 2;
   }
+  b200rt_scene* gpu = gpus.scenes[0];
+  const int n_gpus = gpus.size();
+  AsyncWriter writer;                     // camera i's encode overlaps camera i+1's passes
   int rc = 0;
   for (int index = 0; index < (int)scene.cameras.size() && rc == 0; index++) {
     const Camera& camera = scene.cameras[index];
@@ -59,7 +62,8 @@ int main(int argc, char* argv[]) {
     const uint64_t seed = 795;
     B200PpmStats eye = {}, pass = {};
     const auto t0 = std::chrono::steady_clock::now();
-    if (b200rt_ppm_eye_pass(gpu, index, seed, &eye) != B200RT_OK) { rc = fail("eye pass"); break; }
+    if ((n_gpus > 1 ? b200rt_ppm_eye_pass_multi(gpus.scenes.data(), n_gpus, index, seed, &eye)
+                    : b200rt_ppm_eye_pass(gpu, index, seed, &eye)) != B200RT_OK) { rc = fail("eye pass"); break; }
     // main's bookkeeping, in 64 bits (the tree multiplies ints)
     const long long per_iteration = scene.photon_count_per_iteration;
     const long long photons_per_thread = height < thread_count ? per_iteration : per_iteration / thread_count;
@@ -68,10 +72,24 @@ int main(int argc, char* argv[]) {
     opts.photons = photons_per_thread * workers * (long long)scene.number_of_iterations;
     opts.first_photon = 0;
     opts.seed = seed;
-    if (b200rt_ppm_trace_photons(gpu, &opts, &pass) != B200RT_OK) { rc = fail("photon pass"); break; }
+    if (n_gpus > 1) {
+      // one call per iteration, as main's loop (PPM/src/main.cpp:74-98): the photons of an iteration are split over the
+      // GPUs by index and the accepted-photon counts are summed across them before the next iteration starts
+      const long long per_call = photons_per_thread * workers;
+      B200PpmStats one = {};
+      for (long long it = 0; it < (long long)scene.number_of_iterations && rc == 0; it++) {
+        B200PpmOpts o = opts;
+        o.photons = per_call;
+        o.first_photon = (uint64_t)(it * per_call);
+        if (b200rt_ppm_trace_photons_multi(gpus.scenes.data(), n_gpus, &o, &one) != B200RT_OK) { rc = fail("photon pass"); break; }
+        pass.photons += one.photons; pass.photon_rays += one.photon_rays; pass.launches += one.launches;
+      }
+      if (rc) break;
+    } else if (b200rt_ppm_trace_photons(gpu, &opts, &pass) != B200RT_OK) { rc = fail("photon pass"); break; }
     std::vector<float> rgbw(n * 4);
     const double total = (double)(per_iteration * (per_iteration / thread_count) * thread_count);   // PPM/src/main.cpp:97-98
-    if (b200rt_ppm_density(gpu, total, rgbw.data()) != B200RT_OK) { rc = fail("density estimation"); break; }
+    if ((n_gpus > 1 ? b200rt_ppm_density_multi(gpus.scenes.data(), n_gpus, total, rgbw.data())
+                    : b200rt_ppm_density(gpu, total, rgbw.data())) != B200RT_OK) { rc = fail("density estimation"); break; }
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::vector<unsigned char> image(n * 4, 255);
     for (size_t p = 0; p < n; p++) {
@@ -83,16 +101,22 @@ int main(int argc, char* argv[]) {
       }
     }
     const std::string stem = camera.get_filename().substr(0, camera.get_filename().find_last_of("."));
-    const unsigned error = lodepng::encode((stem + ".png").c_str(), image.data(), width, height);
-    if (error) {
-      std::cout << "encoder error " << error << ": " << lodepng_error_text(error) << std::endl;
-      rc = 4;
-    }
+    const std::string png = stem + ".png";
+    writer.submit([png, width, height, img = std::move(image)]() -> int {
+      const unsigned error = lodepng::encode(png.c_str(), img.data(), width, height);
+      if (error) {
+        std::cout << "encoder error " << error << ": " << lodepng_error_text(error) << std::endl;
+        return 4;
+      }
+      return 0;
+    });
     std::cout << stem << "(" << width << "x" << height << ") is saved in: " << ms << " milliseconds (" << eye.hit_points
               << " hit points, " << pass.photons << " photons, " << pass.photon_rays << " photon rays, "
               << (eye.launches + pass.launches) << " kernel launches)" << std::endl;
   }
-  b200rt_scene_destroy(gpu);
+  const int wrc = writer.finish();        // every file is on disk before the program reports success
+  if (!rc) rc = wrc;
+  gpus.destroy();
   b200rt_flat_ppm_free(flat);
   return rc;
 }

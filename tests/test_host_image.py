@@ -20,3 +20,17 @@ def test_async_png_writer_round_trips_and_reports_errors(tmp_path):
     w.submit(str(tmp_path / "no_such_dir" / "x.png"), frames[0])
     with pytest.raises(Exception):
         w.close()
+
+
+def test_cxx_async_writer_behind_the_dropin_mains(tmp_path):
+    """integration/b200_host.h: the C++ twin of AsyncImageWriter that main_hw*_b200.cpp use — jobs in order on a worker
+    thread, producer not blocked while the queue has room, bounded depth, first error code kept."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "async_writer_host")
+    subprocess.run(["g++", "-std=c++14", "-O1", "-pthread", "-I", os.path.join(root, "include"), "-I",
+                    os.path.join(root, "integration"), os.path.join(root, "tests", "async_writer_host.cpp"), "-o", exe],
+                   check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.count("-> ok") == 3, r.stdout + r.stderr

@@ -157,3 +157,51 @@ def test_hw1_dropin_binary_writes_the_reference_picture(gpu, tmp_path, name):
     want = image.read_png(os.path.join(HERE, "golden", name + ".png"))[..., :3]
     cmp = image.compare_8bit(got, want)
     assert cmp["within1"] >= 0.999 and cmp["max"] <= 2, cmp
+
+
+def _two_camera_xml():
+    """cfg2's small scene seen from two angles: the second <Camera> block spliced into the first XML."""
+    import re
+    from ceng795_b200 import scenes
+    a = scenes.cfg2_hw3(n=48, width=160, height=90, image_name="cam0.png")
+    b = scenes.cfg2_hw3(n=48, width=160, height=90, image_name="cam1.png", cam_angle_deg=60.0)
+    cam_b = re.search(r"<Camera\b.*?</Camera>", b, re.S).group(0).replace('id="1"', 'id="2"')
+    return a, b, a.replace("</Cameras>", cam_b + "\n  </Cameras>")
+
+
+@needs_binary
+@pytest.mark.gpu
+def test_dropin_binary_with_two_cameras_writes_the_same_bytes_as_two_runs(gpu, tmp_path):
+    """The encode of camera 0 runs on the writer thread while camera 1 renders (integration/b200_host.h: AsyncWriter,
+    replacing the serial encode of HW3/src/main.cpp:44-62): both files hold exactly the bytes two single-camera runs
+    wrote, and the program exits only when both are on disk."""
+    a, b, both = _two_camera_xml()
+    for sub, xml in (("a", a), ("b", b), ("both", both)):
+        os.makedirs(tmp_path / sub)
+        r = _run(xml, tmp_path / sub)
+        assert r.returncode == 0, r.stderr
+    assert sorted(os.listdir(tmp_path / "both")) == ["cam0.png", "cam1.png", "scene.xml"]
+    assert open(tmp_path / "both" / "cam0.png", "rb").read() == open(tmp_path / "a" / "cam0.png", "rb").read()
+    assert open(tmp_path / "both" / "cam1.png", "rb").read() == open(tmp_path / "b" / "cam1.png", "rb").read()
+    assert open(tmp_path / "a" / "cam0.png", "rb").read() != open(tmp_path / "b" / "cam1.png", "rb").read()
+
+
+@needs_binary
+@pytest.mark.gpu
+def test_dropin_binary_on_all_gpus_writes_the_one_gpu_picture(gpu, tmp_path):
+    """b200rt_render_multi behind the reference's main: B200RT_DEVICES caps the GPU count; the PNG bytes do not depend
+    on it (1-sample cameras are bit-equal across the split)."""
+    if gpu.b200rt_device_count() < 2:
+        pytest.skip("needs two devices (gpurun --gpus 2)")
+    _, xml = scene_xml("cfg2_hw3_n48_smooth")
+    outs = []
+    for k in (1, 2):
+        os.makedirs(tmp_path / str(k))
+        p = str(tmp_path / str(k) / "scene.xml")
+        open(p, "w").write(xml)
+        r = subprocess.run([BINARY, p], cwd=str(tmp_path / str(k)), capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, B200RT_DEVICES=str(k)))
+        assert r.returncode == 0 and f"{k} GPU" in r.stdout, r.stdout + r.stderr
+        png = [f for f in os.listdir(tmp_path / str(k)) if f.endswith(".png")][0]
+        outs.append(open(tmp_path / str(k) / png, "rb").read())
+    assert outs[0] == outs[1]
