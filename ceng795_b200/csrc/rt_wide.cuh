@@ -108,22 +108,41 @@ __device__ __forceinline__ int wide_select(const float4* top, unsigned long long
 }
 
 // ---- one node of the wide tree ---------------------------------------------------------------------------------
-// Hit mask of the 8 children of the node {n0..n4} for ray r, children entered beyond bound_slack dropped.
-__device__ __forceinline__ uint32_t wide_node_hits(const float4 n0, const float4 n1, const float4 n2,
-                                                            const float4 n3, const float4 n4, const WideRay& r,
-                                                            float bound_slack) {
+// 32768 + (byte k of w), as a float, in one byte-permute: the quantised plane dropped into mantissa bits 8..15 of 2^15.
+// (float)(byte) would be an I2F, which shares the quarter-rate conversion / special-function pipe with the divisions of
+// the triangle test: 48 of them per node step kept that pipe 57 % busy and made it the limiter of a node step
+// (profiles/r02f: 8 cycles per warp instruction there against 2 on the FMA and ALU pipes).  The 2^15 is taken out
+// again by the constant term of the plane's FMA (c = b - 32768 a), at a cost of a/1024 in precision — a thousandth of
+// a quantisation step, far inside the growth of the boxes.
+__device__ __forceinline__ float wide_q2f(uint32_t w, int k) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(__byte_perm(0x47000000u, w, 0x3040u | ((uint32_t)k << 4)));   // selector as an immediate
+#else
+  return __uint_as_float(0x47000000u | (((w >> (8 * k)) & 0xffu) << 8));
+#endif
+}
+
+// Slots (bit s = slot s) of the node {n0, n2..n4} whose child box ray r enters no later than bound_slack.  An empty slot
+// has an inside-out box and does not hit; if rounding ever let one through, it would name no inner child (imask bit 0)
+// and no triangle (meta 0), so nothing depends on it.  Written so that the per-child work is conversions, FMAs,
+// three-input min / max, one compare and one predicated OR: the ALU and conversion pipes are the busy ones in this
+// kernel (profiles/r02f), so what can be done once per node (telling inner from leaf slots, front-to-back order,
+// triangle bits) is done once per node, outside this loop.
+__device__ __forceinline__ uint32_t wide_node_hits(const float4 n0, const float4 n2, const float4 n3, const float4 n4,
+                                                            const WideRay& r, float bound_slack) {
   const uint32_t ei = __float_as_uint(n0.w);
-  const uint32_t imask = ei >> 24;
   // not an accept/reject decision of the reference: FMA allowed
   const float ax = __uint_as_float((ei & 0xffu) << 23) * r.inv.x;
   const float ay = __uint_as_float(((ei >> 8) & 0xffu) << 23) * r.inv.y;
   const float az = __uint_as_float(((ei >> 16) & 0xffu) << 23) * r.inv.z;
-  const float bx = (n0.x - r.o.x) * r.inv.x, by = (n0.y - r.o.y) * r.inv.y, bz = (n0.z - r.o.z) * r.inv.z;
+  // plane t = q * a + b = (32768 + q) * a + c; the far planes carry the slack of the comparison (1 + 4e-6) as well
+  const float cx = __fmaf_rn(-32768.0f, ax, (n0.x - r.o.x) * r.inv.x);
+  const float cy = __fmaf_rn(-32768.0f, ay, (n0.y - r.o.y) * r.inv.y);
+  const float cz = __fmaf_rn(-32768.0f, az, (n0.z - r.o.z) * r.inv.z);
   const bool px = !(r.inv.x < 0.0f), py = !(r.inv.y < 0.0f), pz = !(r.inv.z < 0.0f);
   uint32_t hits = 0u;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
-    const uint32_t meta4 = __float_as_uint(h ? n1.w : n1.z);
     const uint32_t lox = __float_as_uint(h ? n2.y : n2.x), loy = __float_as_uint(h ? n2.w : n2.z);
     const uint32_t loz = __float_as_uint(h ? n3.y : n3.x), hix = __float_as_uint(h ? n3.w : n3.z);
     const uint32_t hiy = __float_as_uint(h ? n4.y : n4.x), hiz = __float_as_uint(h ? n4.w : n4.z);
@@ -132,24 +151,27 @@ __device__ __forceinline__ uint32_t wide_node_hits(const float4 n0, const float4
     const uint32_t nz4 = pz ? loz : hiz, fz4 = pz ? hiz : loz;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const uint32_t meta = (meta4 >> (8 * k)) & 0xffu;
-      const float tnx = __fmaf_rn((float)((nx4 >> (8 * k)) & 0xffu), ax, bx);
-      const float tny = __fmaf_rn((float)((ny4 >> (8 * k)) & 0xffu), ay, by);
-      const float tnz = __fmaf_rn((float)((nz4 >> (8 * k)) & 0xffu), az, bz);
-      const float tfx = __fmaf_rn((float)((fx4 >> (8 * k)) & 0xffu), ax, bx);
-      const float tfy = __fmaf_rn((float)((fy4 >> (8 * k)) & 0xffu), ay, by);
-      const float tfz = __fmaf_rn((float)((fz4 >> (8 * k)) & 0xffu), az, bz);
+      const float tnx = __fmaf_rn(wide_q2f(nx4, k), ax, cx);
+      const float tny = __fmaf_rn(wide_q2f(ny4, k), ay, cy);
+      const float tnz = __fmaf_rn(wide_q2f(nz4, k), az, cz);
+      const float tfx = __fmaf_rn(wide_q2f(fx4, k), ax, cx);
+      const float tfy = __fmaf_rn(wide_q2f(fy4, k), ay, cy);
+      const float tfz = __fmaf_rn(wide_q2f(fz4, k), az, cz);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
       const float tf = fminf(fminf(tfx, tfy), tfz);
-      const float tfa = __fmaf_rn(4e-6f, fmaxf(tn, fabsf(tf)), tf);
-      // branch-free: eight divergent regions per node step cost more than the few instructions they would skip
-      const uint32_t slot = 4u * h + k;
-      const uint32_t bits = ((imask >> slot) & 1u) ? (1u << (24u + (slot ^ r.oct_inv))) : ((meta >> 5) << (meta & 31u));
-      const bool hit = (meta != 0u) & (tn <= tfa) & (tn <= bound_slack);
-      hits |= bits & (0u - (uint32_t)hit);
+      // slack of the comparison: relative to tf (a box behind the origin, tf < 0, misses either way)
+      if (tn <= fminf(tf * 1.000004f, bound_slack)) hits |= 1u << (4 * h + k);   // one compare, one predicated OR
     }
   }
   return hits;
+}
+
+// Bit s of x moves to bit s ^ oct (oct < 8): the order in which a ray with direction octant `oct` meets the slots.
+__device__ __forceinline__ uint32_t wide_octant_permute(uint32_t x, uint32_t oct) {
+  if (oct & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+  if (oct & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+  if (oct & 4u) x = ((x & 0x0fu) << 4) | (x >> 4);
+  return x;
 }
 
 // Takes the nearest unvisited child of the lane's node group, tests its 8 children and makes them the new groups.
@@ -163,12 +185,16 @@ __device__ __forceinline__ bool wide_node_step(const float4* wide_nodes, WideLan
   rest = make_uint2(L.G.x, L.G.y & ~(1u << bit));
   const bool more = (rest.y & 0xff000000u) != 0u;
   tc.nodes++;
-  const float4 n0 = __ldg(wide_nodes + 5 * idx), n1 = __ldg(wide_nodes + 5 * idx + 1);
+  const float4 n0 = __ldg(wide_nodes + 5 * idx);
+  const float child_base = __ldg(reinterpret_cast<const float*>(wide_nodes + 5 * idx + 1));
   const float4 n2 = __ldg(wide_nodes + 5 * idx + 2), n3 = __ldg(wide_nodes + 5 * idx + 3);
   const float4 n4 = __ldg(wide_nodes + 5 * idx + 4);
-  const uint32_t hits = wide_node_hits(n0, n1, n2, n3, n4, L.cr, bound_slack);
-  L.G = make_uint2(__float_as_uint(n1.x), (hits & 0xff000000u) | (__float_as_uint(n0.w) >> 24));
-  L.T = make_uint2(__float_as_uint(n1.y), hits & 0x00ffffffu);
+  const uint32_t hits = wide_node_hits(n0, n2, n3, n4, L.cr, bound_slack);
+  const uint32_t imask = __float_as_uint(n0.w) >> 24;
+  // inner slots: front to back for this ray is "highest bit first" after the octant permutation
+  L.G = make_uint2(__float_as_uint(child_base), (wide_octant_permute(hits & imask, L.cr.oct_inv) << 24) | imask);
+  // leaf slots: which triangles they hold is looked up when (and if) the lane gets to test them (wide_triangles)
+  L.T = make_uint2((uint32_t)idx, hits & ~imask);
   return more;
 }
 
@@ -177,12 +203,22 @@ __device__ __forceinline__ bool wide_node_step(const float4* wide_nodes, WideLan
 template <bool ANY, int TRI_MODE>
 __device__ __forceinline__ bool wide_triangles(const DScene& S, WideLane& L, float tlimit, float eps,
                                                         TravCounters& tc) {
-  uint32_t bits = L.T.y;
+  // L.T = {node, hit leaf slots}: the node's second float4 says where its triangles start and, per slot, how many
+  // (unary 1 / 3 / 7 in the top bits of the meta byte) at which offset (low 5 bits): up to 24 triangles per node
+  const float4 n1 = __ldg(S.wide_nodes + 5 * (size_t)L.T.x + 1);
+  const uint32_t tri_base = __float_as_uint(n1.y);
+  uint32_t slots = L.T.y, bits = 0u;
   L.T.y = 0u;
+  while (slots != 0u) {
+    const uint32_t s_ = (uint32_t)__ffs((int)slots) - 1u;
+    slots &= slots - 1u;
+    const uint32_t meta = (__float_as_uint(s_ < 4u ? n1.z : n1.w) >> (8u * (s_ & 3u))) & 0xffu;
+    bits |= (meta >> 5) << (meta & 31u);
+  }
   while (bits != 0u) {
     const uint32_t b = (uint32_t)__ffs((int)bits) - 1u;
     bits &= bits - 1u;
-    const size_t fi = (size_t)L.T.x + b;
+    const size_t fi = (size_t)tri_base + b;
     tc.tris++;
     const float4 t0 = __ldg(S.wide_tris + 3 * fi), t1 = __ldg(S.wide_tris + 3 * fi + 1), t2 = __ldg(S.wide_tris + 3 * fi + 2);
     float t, be, ga;

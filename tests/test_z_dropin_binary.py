@@ -191,7 +191,8 @@ def test_dropin_binary_with_two_cameras_writes_the_same_bytes_as_two_runs(gpu, t
 def test_dropin_binary_on_all_gpus_writes_the_one_gpu_picture(gpu, tmp_path):
     """b200rt_render_multi behind the reference's main: B200RT_DEVICES caps the GPU count; the PNG bytes do not depend
     on it (1-sample cameras are bit-equal across the split)."""
-    if gpu.b200rt_device_count() < 2:
+    from ceng795_b200 import _lib
+    if _lib.load().b200rt_device_count() < 2:
         pytest.skip("needs two devices (gpurun --gpus 2)")
     _, xml = scene_xml("cfg2_hw3_n48_smooth")
     outs = []
