@@ -305,7 +305,8 @@ def run_b200(args):
     for _ in range(args.warmup):
         one_step()
     if ppm:
-        keys = ("photon_rays", "cell_scans", "deposits", "nodes_visited", "tris_tested", "launches")
+        keys = ("photon_rays", "cell_scans", "entries_scanned", "deposits", "nodes_visited", "tris_tested", "launches",
+                "grid_rebuilds")
         ms_keys = ("ms_extend", "ms_deposit")
     else:
         keys = ("rays_primary", "rays_shadow", "rays_secondary", "nodes_visited", "tris_tested", "spheres_tested",
@@ -414,11 +415,14 @@ def run_b200(args):
         n_launch = max(1, args.steps * (sc.spec.max_depth - 1))
         per_ray = {"nodes": (agg["nodes_visited"] - top_tests) / max(1, n_closest),
                    "top_level_gates": int(st.top_objects), "tris": agg["tris_tested"] / max(1, n_closest),
-                   "hit_points_scanned_per_photon_ray": agg["cell_scans"] / max(1, n_closest),
+                   "hit_points_scanned_per_photon_ray": agg["entries_scanned"] / max(1, n_closest),
+                   "reference_loop_visits_per_photon_ray": agg["cell_scans"] / max(1, n_closest),
+                   "scan_cell_over_reference_cell": float(st.scan_cell) / (2.0 * float(eye.initial_radius)) if eye.initial_radius else None,
+                   "grid_rebuilds": agg["grid_rebuilds"],
                    "deposits_per_photon_ray": agg["deposits"] / max(1, n_closest)}
         # deposit: per photon ray 52 B in + 56 B out of the pool, 16 B per scanned grid entry, 64 B record + 4 B count
         # + 16 B flux per deposit ("32 k + 16 a", with this layout's record sizes)
-        dep_bytes = 108 * n_closest + 16 * agg["cell_scans"] + 84 * agg["deposits"]
+        dep_bytes = 108 * n_closest + 16 * agg["entries_scanned"] + 84 * agg["deposits"]
         kernels = [kernel_line("k_ppm_photon_shade (scatter + cell scan + hit-point radius / flux update)", dep_bytes,
                                ms_stage["ms_deposit"], n_launch, "hbm", "deposit"),
                    kernel_line(f"k_trace_{'wide' if nb == 80 else 'fast'}<false,7> (photon closest-hit traversal)",

@@ -157,7 +157,8 @@ class PpmStats(C.Structure):
                 ("photon_rays", C.c_uint64), ("cell_scans", C.c_uint64), ("deposits", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64),
                 ("ms_eye", c_f), ("ms_grid", c_f), ("ms_photon", c_f), ("ms_extend", c_f), ("ms_deposit", c_f),
-                ("ms_density", c_f), ("initial_radius", c_f), ("launches", c_i), ("node_bytes", c_i), ("top_objects", c_i)]
+                ("ms_density", c_f), ("initial_radius", c_f), ("launches", c_i), ("node_bytes", c_i), ("top_objects", c_i),
+                ("entries_scanned", C.c_uint64), ("scan_cell", c_f), ("grid_rebuilds", c_i)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -97,6 +97,12 @@ struct b200rt_scene {
   size_t scan_tmp_bytes, items_capacity;
   uint32_t n_hp;
   int ppm_camera;
+  // the scan grid of the photon pass, rebuilt as the radii shrink (ppm_kernels.cuh: PpmGrid::adaptive)
+  PpmGrid G2;
+  size_t entries2_capacity;
+  double g2_sumR;      // sum of R(n) over the hit points when G2 was built
+  bool g2_valid;
+  double* d_sumR;
   // multi-GPU (multi_gpu.cuh).  Transient, set around a render: where wave 0's combine writes, and what it waits for.
   float4* rt_frame;                 // nullptr = d_accum
   const unsigned int* rt_wait_flag; // awaited (>= rt_wait_target) before the first pixel of a frame is written
@@ -547,7 +553,16 @@ void ppm_free(b200rt_scene* sc) {
                   sc->d_sort[3]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  memset(&sc->HP, 0, sizeof(HitPoints));
+  void* g2[] = {sc->G2.cell_count, sc->G2.cell_start, sc->G2.cell_pos, sc->d_sumR};
+  for (void* p : g2)
+    if (p) cudaFree(p);
+  memset(&sc->G2, 0, sizeof(PpmGrid));
+  sc->entries2_capacity = 0; sc->g2_valid = false; sc->d_sumR = nullptr;
+  {
+    const uint32_t part = sc->HP.part, parts = sc->HP.parts;   // the share of a multi-GPU run outlives the buffers
+    memset(&sc->HP, 0, sizeof(HitPoints));
+    sc->HP.part = part; sc->HP.parts = parts;
+  }
   memset(&sc->G, 0, sizeof(PpmGrid));
   sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
   for (int q = 0; q < 4; q++) sc->d_sort[q] = nullptr;
@@ -590,6 +605,73 @@ int ppm_ensure_rtab(b200rt_scene* sc) {
   }
   CK(cudaMalloc((void**)&sc->d_rtab, sizeof(float) * PPM_RTAB));
   CK(cudaMemcpy(sc->d_rtab, r.data(), sizeof(float) * PPM_RTAB, cudaMemcpyHostToDevice));
+  return B200RT_OK;
+}
+
+// Rebuilds the scan grid of the photon pass when the radii have shrunk enough since the last build (or when there is
+// none yet and they have left r0 behind).  Cells become twice the typical current radius wide; a hit point is entered
+// into every cell its current radius reaches.  cub's scan: a library call on a step that runs a few dozen times a frame.
+int ppm_rebuild_scan_grid(b200rt_scene* sc, int* launches, int* rebuilds) {
+  const uint32_t n_hp = sc->n_hp;
+  if (n_hp == 0 || getenv("B200RT_PPM_STATIC_GRID")) return B200RT_OK;
+  cudaStream_t st = sc->c0.stream;
+  if (!sc->d_sumR) CK(cudaMalloc((void**)&sc->d_sumR, sizeof(double)));
+  CK(cudaMemsetAsync(sc->d_sumR, 0, sizeof(double), st));
+  k_ppm_sum_R<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, sc->G, n_hp, sc->d_sumR);
+  double sumR = 0.0;
+  CK(cudaMemcpyAsync(&sumR, sc->d_sumR, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  (*launches)++;
+  const double meanR = sumR / (double)n_hp;          // mean of r2 / r0^2
+  if (sc->g2_valid ? sumR > 0.8 * sc->g2_sumR : meanR > 0.7) return B200RT_OK;
+  PpmGrid& G2 = sc->G2;
+  unsigned int* cc = G2.cell_count;
+  unsigned int* cs = G2.cell_start;
+  float4* cp = G2.cell_pos;
+  G2 = sc->G;                                         // r0, r0sq, bbox_min, num_hash, rtab: the reference's
+  G2.cell_count = cc; G2.cell_start = cs; G2.cell_pos = cp; G2.items = nullptr;
+  G2.adaptive = 1;
+  if (!G2.cell_count) {
+    CK(cudaMalloc((void**)&G2.cell_count, sizeof(unsigned int) * ((size_t)n_hp + 1)));
+    CK(cudaMalloc((void**)&G2.cell_start, sizeof(unsigned int) * ((size_t)n_hp + 1)));
+  }
+  float cell_r = sc->G.r0 * (float)sqrt(meanR);       // the typical current radius
+  const size_t max_entries = (size_t)24 * n_hp + 1024;   // the reference's grid holds ~8 per hit point
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, G2.cell_count, G2.cell_start, (int)n_hp + 1, st);
+  if (need > sc->scan_tmp_bytes) {
+    if (sc->d_scan_tmp) cudaFree(sc->d_scan_tmp);
+    sc->d_scan_tmp = nullptr; sc->scan_tmp_bytes = 0;
+    CK(cudaMalloc(&sc->d_scan_tmp, need));
+    sc->scan_tmp_bytes = need;
+  }
+  unsigned int total = 0;
+  for (int attempt = 0;; attempt++) {
+    if (cell_r > sc->G.r0) cell_r = sc->G.r0;
+    G2.hash_scale = (float)(1.0 / ((double)cell_r * 2.0));
+    CK(cudaMemsetAsync(G2.cell_count, 0, sizeof(unsigned int) * ((size_t)n_hp + 1), st));
+    k_ppm_grid<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, G2, n_hp, 2, 0, sc->d_pc, sc->S.mats);
+    size_t nb = sc->scan_tmp_bytes;
+    cub::DeviceScan::ExclusiveSum(sc->d_scan_tmp, nb, G2.cell_count, G2.cell_start, (int)n_hp + 1, st);
+    CK(cudaMemcpyAsync(&total, G2.cell_start + n_hp, sizeof(total), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *launches += 2;
+    if (total <= max_entries || cell_r >= sc->G.r0 || attempt >= 6) break;
+    cell_r *= 1.3f;   // hit points that still have a large radius reach too many of the small cells: larger cells
+  }
+  if ((size_t)total + 1 > sc->entries2_capacity) {
+    if (G2.cell_pos) cudaFree(G2.cell_pos);
+    G2.cell_pos = nullptr; sc->entries2_capacity = 0;
+    CK(cudaMalloc((void**)&G2.cell_pos, sizeof(float4) * ((size_t)total + 1)));
+    sc->entries2_capacity = (size_t)total + 1;
+  }
+  CK(cudaMemcpyAsync(G2.cell_count, G2.cell_start, sizeof(unsigned int) * ((size_t)n_hp + 1), cudaMemcpyDeviceToDevice, st));
+  k_ppm_grid<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, G2, n_hp, 1, (uint32_t)sc->entries2_capacity, sc->d_pc, sc->S.mats);
+  CK(cudaGetLastError());
+  (*launches)++;
+  (*rebuilds)++;
+  sc->g2_valid = true;
+  sc->g2_sumR = sumR;
   return B200RT_OK;
 }
 
@@ -646,6 +728,7 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
   CK(cudaSetDevice(sc->device));
   sc->S.cam = sc->cameras[camera_index];
   sc->ppm_camera = camera_index;
+  sc->g2_valid = false;
   const b200rt_camera& c = sc->S.cam;
   if (sc->S.max_depth + 2 > kMaxWaves) return B200RT_E_UNSUPPORTED;
   cudaStream_t st = sc->c0.stream;
@@ -718,6 +801,7 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
     G.r0 = r0; G.r0sq = r0 * r0;
     G.bbox_min = mk3(mn[0] - r0, mn[1] - r0, mn[2] - r0);  // min_i fl(p_i - r0) == fl(min_i p_i - r0)
     G.hash_scale = (float)(1.0 / ((double)r0 * 2.0));
+    G.adaptive = 0;
     {
       const char* e = getenv("B200RT_PPM_ORDER");   // "none": append order (one GPU only), "pixel", "cell" (default)
       if (!(e && !strcmp(e, "none"))) {
@@ -792,8 +876,12 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
   int launches = 0;
   cudaEventRecord(sc->c0.ev[0], st);
   tm.mark(ST_GENERATE);
+  int rebuilds = 0;
   for (int64_t done = 0; done < opts->photons && sc->S.max_depth > 1; done += (int64_t)batch) {
     const uint32_t n = (uint32_t)((opts->photons - done) < (int64_t)batch ? (opts->photons - done) : (int64_t)batch);
+    rc = ppm_rebuild_scan_grid(sc, &launches, &rebuilds);   // before every batch: cheap when nothing is to be done
+    if (rc) return rc;
+    const PpmGrid& Gs = sc->g2_valid ? sc->G2 : sc->G;
     const uint32_t* order = nullptr;
     if (!getenv("B200RT_PPM_NO_SORT")) {
       // trace the batch in direction order (ppm_kernels.cuh: k_ppm_emit_keys); cub radix sort on 16-bit keys is a
@@ -829,8 +917,8 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
       if (sc->S.use_wide) launch_wide(sc, sc->c0, false, true, d);
       else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.Q, sc->c0.d_waves, d, sc->c0.d_counters);
       tm.mark(ST_EXTEND);
-      k_ppm_photon_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.d_waves, d, sc->HP, sc->G,
-                                                                sc->c0.d_counters, sc->d_pc);
+      k_ppm_photon_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.d_waves, d, sc->HP, Gs,
+                                                                sc->c0.d_counters, sc->d_pc, sc->G.cell_start, sc->G.hash_scale);
       tm.mark(ST_SHADE);
       launches += 4;
     }
@@ -847,6 +935,9 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
     stats->photon_rays = hpc1.photon_rays - hpc0.photon_rays;
     stats->cell_scans = hpc1.cell_scans - hpc0.cell_scans;
     stats->deposits = hpc1.deposits - hpc0.deposits;
+    stats->entries_scanned = hpc1.entries_scanned - hpc0.entries_scanned;
+    stats->scan_cell = 1.0f / (sc->g2_valid ? sc->G2.hash_scale : sc->G.hash_scale);
+    stats->grid_rebuilds = rebuilds;
     stats->nodes_visited = hc.nodes_visited; stats->tris_tested = hc.tris_tested;
     float ms[ST_COUNT];
     tm.collect(ms);
@@ -957,6 +1048,8 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
   for (int q = 0; q < 4; q++) sc->d_sort[q] = nullptr;
   sc->scan_tmp_bytes = 0; sc->items_capacity = 0; sc->n_hp = 0; sc->ppm_camera = -1;
+  memset(&sc->G2, 0, sizeof(PpmGrid));
+  sc->entries2_capacity = 0; sc->g2_sumR = 0.0; sc->g2_valid = false; sc->d_sumR = nullptr;
   sc->rt_frame = nullptr; sc->rt_wait_flag = nullptr; sc->rt_wait_target = 0; sc->d_sync_err = nullptr;
   sc->own_frame_no = 0; sc->own_parts_seen = 0; sc->own_camera = -1; sc->own_direct = false;
   sc->tgt_frame = nullptr; sc->tgt_tail = nullptr; sc->tgt_pixels = 0; sc->tgt_w = 0; sc->tgt_h = 0;
@@ -1113,6 +1206,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     UP(S.wide_root, wroot.data(), wroot.size(), int32_t);
     // the shared-memory stack of k_trace_wide holds one node group per level
     S.use_wide = (want && ws.depth <= RT_WSTACK) ? 1 : 0;
+    if (S.use_wide && !getenv("B200RT_NODE_VOTE")) S.node_vote = RT_WIDE_NODE_VOTE;
     sc->wide_nodes = (int)wnodes.size(); sc->wide_depth = ws.depth;
     sc->wide_blocks = RT_WIDE_MIN_BLOCKS;
     if (const char* e = getenv("B200RT_WIDE_BLOCKS")) { const int v = atoi(e); if (v == 4 || v == 6 || v == 8) sc->wide_blocks = v; }

@@ -61,9 +61,19 @@ struct PpmGrid {
   v3 bbox_min;
   float hash_scale, r0, r0sq;
   const float* rtab;         // R(n) for n < PPM_RTAB
+  // The SCAN grid of the photon pass (b200rt_api.cu: ppm_rebuild_scan_grid).  The reference keeps the grid it built
+  // from the initial radius for the whole run (cells 2 r0 wide, PPM/src/Scene.cpp:53-93), so a photon goes on testing
+  // the ~144 hit points of its cell when the radii have shrunk to a third and two or three of them can still accept
+  // it.  Which pairs ACCEPT depends only on |x - q|^2 <= r2(n) and the normals; the reference's cell structure merely
+  // finds a superset of them (a photon within r(n) <= r0 of a hit point always lies in a cell of the hit point's
+  // r0-box).  Any other superset finds the same pairs, so the device rebuilds the grid as the radii shrink:
+  // adaptive != 0: cells are 1 / hash_scale wide (about twice the typical current radius) and a hit point is entered
+  // into the cells its CURRENT radius reaches.  Radii only shrink, so a grid stays valid until the next rebuild.
+  int adaptive;
 };
 struct PpmCounters {
   unsigned long long photon_rays, cell_scans, deposits;
+  unsigned long long entries_scanned;   // grid entries the photons actually tested (== cell_scans on the reference's grid)
   unsigned int bbox[6];      // ordered-int min xyz / max xyz of the hit-point positions
   unsigned int grid_overflow;
 };
@@ -208,6 +218,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_ppm_eye_shade(DScene S, Pool P, Wa
 
 // ---- hash grid -------------------------------------------------------------------
 // mode 0: count entries per cell; mode 1: fill (cell_count is the running cursor, starting at cell_start)
+// mode 2: count for a rebuild of the scan grid (the hit points' state is NOT reset)
 __global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uint32_t items_capacity, PpmCounters* PC,
                            const b200rt_material* mats) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) {
@@ -222,8 +233,11 @@ __global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uin
       HP.dep[4 * (size_t)i + 2] = make_float4(m.diffuse[0], m.diffuse[1], m.diffuse[2], a4.y);
       HP.dep[4 * (size_t)i + 3] = make_float4(m.specular[0], m.specular[1], m.specular[2], a4.z);
     }
-    const v3 lo = (mk3(q.x - G.r0, q.y - G.r0, q.z - G.r0) - G.bbox_min) * G.hash_scale;
-    const v3 hi = (mk3(q.x + G.r0, q.y + G.r0, q.z + G.r0) - G.bbox_min) * G.hash_scale;
+    // reach of the hit point: the initial radius (the reference's grid), or its current radius with a margin that
+    // covers the rounding of the square root and of the cell arithmetic
+    const float rb = G.adaptive ? sqrtf(G.r0sq * ppm_R(G, HP.n[i])) * 1.0001f : G.r0;
+    const v3 lo = (mk3(q.x - rb, q.y - rb, q.z - rb) - G.bbox_min) * G.hash_scale;
+    const v3 hi = (mk3(q.x + rb, q.y + rb, q.z + rb) - G.bbox_min) * G.hash_scale;
     for (int iz = abs((int)lo.z); iz <= abs((int)hi.z); iz++)
       for (int iy = abs((int)lo.y); iy <= abs((int)hi.y); iy++)
         for (int ix = abs((int)lo.x); ix <= abs((int)hi.x); ix++) {
@@ -231,7 +245,7 @@ __global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uin
           const unsigned int at = atomicAdd(&G.cell_count[hv], 1u);
           if (mode == 1) {
             if (at < items_capacity) {
-              G.items[at] = i;
+              if (G.items) G.items[at] = i;
               G.cell_pos[at] = make_float4(q.x, q.y, q.z, __uint_as_float(i));
             } else {
               PC->grid_overflow = 1;
@@ -239,6 +253,15 @@ __global__ void k_ppm_grid(HitPoints HP, PpmGrid G, uint32_t n_hp, int mode, uin
           }
         }
   }
+}
+
+// sum over the hit points of R(n) = r2 / r0^2 (double): how far the radii have shrunk since the grid was built
+__global__ void k_ppm_sum_R(HitPoints HP, PpmGrid G, uint32_t n_hp, double* out) {
+  double acc = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hp; i += gridDim.x * blockDim.x) acc += (double)ppm_R(G, HP.n[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane_id() == 0) atomicAdd(out, acc);
 }
 
 // Home cell of every hit point (the cell its position hashes to): second, stable sort key of the canonical numbering,
@@ -308,13 +331,16 @@ __global__ void k_ppm_next_wave(WaveInfo* waves, int d, uint32_t half, Counters*
   waves[d + 1].count = 0;
   C->work_extend = 0;
 }
+// G: the grid the photons scan (the reference's, or the rebuilt one); ref_start / ref_scale: cell table and cell scale
+// of the reference's grid, for the count of hit points ITS loop would have visited (B200PpmStats::cell_scans).
 __global__ void __launch_bounds__(RT_BLOCK, PPM_MIN_BLOCKS) k_ppm_photon_shade(DScene S, Pool P, WaveInfo* waves, int d, HitPoints HP,
-                                                               PpmGrid G, Counters* C, PpmCounters* PC) {
+                                                               PpmGrid G, Counters* C, PpmCounters* PC,
+                                                               const unsigned int* ref_start, float ref_scale) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   const uint32_t next_begin = waves[d + 1].begin;
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t rounds = (count + stride - 1) / stride;
-  unsigned int scans = 0, deposits = 0;
+  unsigned int scans = 0, deposits = 0, scanned = 0;
   for (uint32_t r = 0; r < rounds; r++) {
     const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = k < count;
@@ -448,6 +474,14 @@ __global__ void __launch_bounds__(RT_BLOCK, PPM_MIN_BLOCKS) k_ppm_photon_shade(D
       const v3 hh = (p - G.bbox_min) * G.hash_scale;
       const uint32_t cell = ppm_hash(G.num_hash, abs((int)hh.x), abs((int)hh.y), abs((int)hh.z));
       my_c0 = G.cell_start[cell]; my_c1 = G.cell_start[cell + 1];
+      scanned += my_c1 - my_c0;
+      if (G.adaptive) {
+        const v3 hr = (p - G.bbox_min) * ref_scale;
+        const uint32_t rc = ppm_hash(G.num_hash, abs((int)hr.x), abs((int)hr.y), abs((int)hr.z));
+        scans += ref_start[rc + 1] - ref_start[rc];
+      } else {
+        scans += my_c1 - my_c0;
+      }
     }
     // The scan is a flat sequence of steps (photon, 32 x PPM_SCAN_LOADS entries of its cell), walked by the whole
     // warp; the entries of step k+1 are requested before step k is consumed, so a lane always has two rounds of
@@ -466,7 +500,6 @@ __global__ void __launch_bounds__(RT_BLOCK, PPM_MIN_BLOCKS) k_ppm_photon_shade(D
         dmask &= dmask - 1;
         n_base = __shfl_sync(0xffffffffu, my_c0, n_src);
         n_c1 = __shfl_sync(0xffffffffu, my_c1, n_src);
-        if (lane_id() == 0) scans += n_c1 - n_base;
         if (n_base < n_c1) return;
       }
     };
@@ -528,10 +561,12 @@ __global__ void __launch_bounds__(RT_BLOCK, PPM_MIN_BLOCKS) k_ppm_photon_shade(D
   for (int o = 16; o > 0; o >>= 1) {
     scans += __shfl_xor_sync(0xffffffffu, scans, o);
     deposits += __shfl_xor_sync(0xffffffffu, deposits, o);
+    scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
   }
   if (lane_id() == 0) {
     atomicAdd(&PC->cell_scans, (unsigned long long)scans);
     atomicAdd(&PC->deposits, (unsigned long long)deposits);
+    atomicAdd(&PC->entries_scanned, (unsigned long long)scanned);
   }
 }
 __global__ void k_ppm_count_rays(const WaveInfo* waves, int d, PpmCounters* PC) {

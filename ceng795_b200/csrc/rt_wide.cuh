@@ -23,6 +23,9 @@
 #include "rt_traverse.cuh"
 
 #define RT_WSTACK 16        // shared-memory stack entries per thread (node groups); scenes whose wide tree is deeper use k_trace_fast
+#ifndef RT_WIDE_NODE_VOTE
+#define RT_WIDE_NODE_VOTE 8   // lanes that must still want a node step for phase 1 to go on (swept: profiles/r02_tuning.txt)
+#endif
 #ifndef RT_TOP_LINEAR_MAX
 #define RT_TOP_LINEAR_MAX 40  // top-level objects up to which phase 0 scans a flat gate list (one bit each in the lane's object mask)
 #endif
@@ -122,6 +125,14 @@ __device__ __forceinline__ float wide_q2f(uint32_t w, int k) {
 #endif
 }
 
+// Planes converted the other way, with a plain (float)(byte) on the conversion pipe: after the byte-permutes the ALU pipe
+// is the busy one (62 %, profiles/r02h) and the conversion pipe idles at 14 %, so a share of the 48 conversions of a
+// node step goes back there.  0: none, 1: the z planes (16), 2: z planes and far y planes (24).  Swept on the device.
+#ifndef RT_WIDE_I2F_PLANES
+#define RT_WIDE_I2F_PLANES 1
+#endif
+__device__ __forceinline__ float wide_q2i(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+
 // Slots (bit s = slot s) of the node {n0, n2..n4} whose child box ray r enters no later than bound_slack.  An empty slot
 // has an inside-out box and does not hit; if rounding ever let one through, it would name no inner child (imask bit 0)
 // and no triangle (meta 0), so nothing depends on it.  Written so that the per-child work is conversions, FMAs,
@@ -136,9 +147,10 @@ __device__ __forceinline__ uint32_t wide_node_hits(const float4 n0, const float4
   const float ay = __uint_as_float(((ei >> 8) & 0xffu) << 23) * r.inv.y;
   const float az = __uint_as_float(((ei >> 16) & 0xffu) << 23) * r.inv.z;
   // plane t = q * a + b = (32768 + q) * a + c; the far planes carry the slack of the comparison (1 + 4e-6) as well
+  const float by = (n0.y - r.o.y) * r.inv.y, bz = (n0.z - r.o.z) * r.inv.z;
   const float cx = __fmaf_rn(-32768.0f, ax, (n0.x - r.o.x) * r.inv.x);
-  const float cy = __fmaf_rn(-32768.0f, ay, (n0.y - r.o.y) * r.inv.y);
-  const float cz = __fmaf_rn(-32768.0f, az, (n0.z - r.o.z) * r.inv.z);
+  const float cy = __fmaf_rn(-32768.0f, ay, by);
+  const float cz = __fmaf_rn(-32768.0f, az, bz);
   const bool px = !(r.inv.x < 0.0f), py = !(r.inv.y < 0.0f), pz = !(r.inv.z < 0.0f);
   uint32_t hits = 0u;
 #pragma unroll
@@ -153,10 +165,10 @@ __device__ __forceinline__ uint32_t wide_node_hits(const float4 n0, const float4
     for (int k = 0; k < 4; k++) {
       const float tnx = __fmaf_rn(wide_q2f(nx4, k), ax, cx);
       const float tny = __fmaf_rn(wide_q2f(ny4, k), ay, cy);
-      const float tnz = __fmaf_rn(wide_q2f(nz4, k), az, cz);
+      const float tnz = RT_WIDE_I2F_PLANES >= 1 ? __fmaf_rn(wide_q2i(nz4, k), az, bz) : __fmaf_rn(wide_q2f(nz4, k), az, cz);
       const float tfx = __fmaf_rn(wide_q2f(fx4, k), ax, cx);
-      const float tfy = __fmaf_rn(wide_q2f(fy4, k), ay, cy);
-      const float tfz = __fmaf_rn(wide_q2f(fz4, k), az, cz);
+      const float tfy = RT_WIDE_I2F_PLANES >= 2 ? __fmaf_rn(wide_q2i(fy4, k), ay, by) : __fmaf_rn(wide_q2f(fy4, k), ay, cy);
+      const float tfz = RT_WIDE_I2F_PLANES >= 1 ? __fmaf_rn(wide_q2i(fz4, k), az, bz) : __fmaf_rn(wide_q2f(fz4, k), az, cz);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
       const float tf = fminf(fminf(tfx, tfy), tfz);
       // slack of the comparison: relative to tf (a box behind the origin, tf < 0, misses either way)
@@ -361,7 +373,7 @@ __device__ __forceinline__ bool wide_trace_one(const DScene& S, const float4* to
 
 #ifdef __CUDACC__
 #ifndef RT_WIDE_MIN_BLOCKS
-#define RT_WIDE_MIN_BLOCKS 6  // default resident CTAs of 128 threads per SM the register budget is held to (80 registers)
+#define RT_WIDE_MIN_BLOCKS 8  // default resident CTAs of 128 threads per SM the register budget is held to (64 registers; swept: profiles/r02_tuning.txt)
 #endif
 
 // MINB: resident CTAs per SM the register budget is held to (4: 128 registers, 6: 80, 8: 64) — instantiated for all

@@ -417,6 +417,13 @@ typedef struct B200PpmStats {
   float initial_radius;
   int32_t launches;
   int32_t node_bytes, top_objects;
+  /* the scan grid of the photon pass (rebuilt as the radii shrink; the ACCEPTED pairs are the reference's either way):
+   * cell_scans above is what the reference's own loop over its r0 grid would have visited, entries_scanned what the
+   * device tested, scan_cell the width of a cell of the grid in use (2 * initial_radius = the reference's), grid_rebuilds
+   * the rebuilds this call did */
+  uint64_t entries_scanned;
+  float scan_cell;
+  int32_t grid_rebuilds;
 } B200PpmStats;
 /* reset_hash_grid + eye_trace_lines + build_hash_grid for one camera */
 int b200rt_ppm_eye_pass(b200rt_scene*, int camera_index, uint64_t seed, B200PpmStats*);
