@@ -425,7 +425,7 @@ def run_b200(args):
         dep_bytes = 108 * n_closest + 16 * agg["entries_scanned"] + 84 * agg["deposits"]
         kernels = [kernel_line("k_ppm_photon_shade (scatter + cell scan + hit-point radius / flux update)", dep_bytes,
                                ms_stage["ms_deposit"], n_launch, "hbm", "deposit"),
-                   kernel_line(f"k_trace_{'wide' if nb == 80 else 'fast'}<false,7> (photon closest-hit traversal)",
+                   kernel_line(f"k_trace_{'wide' if nb != 64 else 'fast'}<false,7> (photon closest-hit traversal)",
                                ext_bytes, ms_stage["ms_extend"], n_launch, "l2", "extend")]
     else:
         n_closest = agg["rays_primary"] + agg["rays_secondary"]
@@ -439,7 +439,7 @@ def run_b200(args):
         mode = 7 if wl["tree"] in ("hw4", "hw5", "hw6", "hw7", "ppm") else 2
         if wl["tree"] == "hw1":
             kn = "k_trace_hw1_fast<{}> (SAH tree over all triangles, HW1's order-dependent rule on the near-tie set)"
-        elif nb == 80:
+        elif nb != 64:
             kn = "k_trace_wide<{}," + str(mode) + "> (8-wide quantised tree, shared-memory stack, reference gate per candidate)"
         else:
             kn = "k_trace_fast<{}," + str(mode) + "> (binary SAH tree + reference gate)"

@@ -43,6 +43,14 @@ int upload(const T* src, size_t n, T** dst) {
   return B200RT_OK;
 }
 
+// Scratch device memory of one entry point: released on every return path.
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 constexpr int kMaxWaves = 66;
 enum Stage { ST_GENERATE = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_COUNT };
 
@@ -538,7 +546,7 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
     }
     cudaEventElapsedTime(&stats->ms_total, c0.ev[0], c0.ev[1]);
     stats->waves = waves_total; stats->launches = launches;
-    stats->node_bytes = (sc->S.use_wide && !exact && sc->S.semantics != B200RT_SEM_HW1) ? 80 : 64;
+    stats->node_bytes = (sc->S.use_wide && !exact && sc->S.semantics != B200RT_SEM_HW1) ? (int)sizeof(b200rt_wide::Node) : 64;
     stats->top_objects = exact ? 0 : sc->S.n_top;
     stats->contexts = K;
   }
@@ -606,6 +614,17 @@ int ppm_ensure_rtab(b200rt_scene* sc) {
   CK(cudaMalloc((void**)&sc->d_rtab, sizeof(float) * PPM_RTAB));
   CK(cudaMemcpy(sc->d_rtab, r.data(), sizeof(float) * PPM_RTAB, cudaMemcpyHostToDevice));
   return B200RT_OK;
+}
+
+// A traversal-stack or pool overflow inside a wave loop must not come back as B200RT_OK with wrong results.
+int check_overflow(b200rt_scene* sc, const char* who) {
+  unsigned int ov = 0;
+  CK(cudaMemcpy(&ov, &sc->c0.d_counters->overflow, sizeof(ov), cudaMemcpyDeviceToHost));
+  if (!ov) return B200RT_OK;
+  std::string msg = std::string(who) + (ov == 2 ? ": traversal stack overflow (BVH deeper than the traversal stack)"
+                                                : ": vertex pool / queue overflow");
+  b200rt_internal_set_error(msg.c_str());
+  return B200RT_E_UNSUPPORTED;
 }
 
 // Rebuilds the scan grid of the photon pass when the radii have shrunk enough since the last build (or when there is
@@ -926,6 +945,8 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
   cudaEventRecord(sc->c0.ev[1], st);
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
+  rc = check_overflow(sc, "b200rt_ppm_trace_photons");
+  if (rc) return rc;
   if (stats) {
     CK(cudaMemcpy(&hpc1, sc->d_pc, sizeof(hpc1), cudaMemcpyDeviceToHost));
     Counters hc;
@@ -945,7 +966,7 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
     cudaEventElapsedTime(&stats->ms_photon, sc->c0.ev[0], sc->c0.ev[1]);
     stats->initial_radius = sc->G.r0;
     stats->launches = launches;
-    stats->node_bytes = sc->S.use_wide ? 80 : 64;
+    stats->node_bytes = sc->S.use_wide ? (int)sizeof(b200rt_wide::Node) : 64;
     stats->top_objects = sc->S.n_top;
   }
   return B200RT_OK;
@@ -1200,7 +1221,7 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
       memcpy(&wgeom[12 * k], fast_geom + 12 * (size_t)worder[k], 48);
       wref[k] = fast_ref[worder[k]];
     }
-    UP(S.wide_nodes, wnodes.data(), wnodes.size() * 20, float);   // 80 bytes = 5 x float4 per node
+    UP(S.wide_nodes, wnodes.data(), wnodes.size() * (sizeof(b200rt_wide::Node) / 4), float);   // 5 or 8 float4 per node
     UP(S.wide_tris, wgeom.data(), wgeom.size(), float);
     UP(S.wide_tri_ref, wref.data(), wref.size(), int32_t);
     UP(S.wide_root, wroot.data(), wroot.size(), int32_t);
@@ -1437,19 +1458,19 @@ int b200rt_debug_leaf(int device, int which, const b200rt_texture* tex, const fl
   b200rt_brdf B;
   memset(&B, 0, sizeof(B));
   if (brdf) B = *brdf;
-  float *d_tex = nullptr, *d_in = nullptr, *d_out = nullptr;
+  DevBuf b_tex, b_in, b_out;
   if (texels && n_texels > 0) {
-    CK(cudaMalloc((void**)&d_tex, (size_t)n_texels * 4));
-    CK(cudaMemcpy(d_tex, texels, (size_t)n_texels * 4, cudaMemcpyHostToDevice));
-    S.texels = d_tex;
+    CK(b_tex.alloc((size_t)n_texels * 4));
+    CK(cudaMemcpy(b_tex.p, texels, (size_t)n_texels * 4, cudaMemcpyHostToDevice));
+    S.texels = b_tex.as<float>();
   }
-  CK(cudaMalloc((void**)&d_in, (size_t)rows * n_in * 4));
-  CK(cudaMalloc((void**)&d_out, (size_t)rows * n_out * 4));
+  CK(b_in.alloc((size_t)rows * n_in * 4));
+  CK(b_out.alloc((size_t)rows * n_out * 4));
+  float *d_in = b_in.as<float>(), *d_out = b_out.as<float>();
   CK(cudaMemcpy(d_in, in, (size_t)rows * n_in * 4, cudaMemcpyHostToDevice));
   k_debug_leaf<<<(rows + 127) / 128, 128>>>(which, S, T, B, d_in, rows, n_in, d_out, n_out);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, d_out, (size_t)rows * n_out * 4, cudaMemcpyDeviceToHost));
-  cudaFree(d_tex); cudaFree(d_in); cudaFree(d_out);
   return B200RT_OK;
 } B200RT_CATCH
 
@@ -1629,10 +1650,11 @@ int b200rt_primary_ids(b200rt_scene* sc, int camera_index, const B200RenderOpts*
   int rc = ensure_pool(sc, sc->c0, R.n_paths + 1024, 1024);
   if (rc) return rc;
   cudaStream_t st = sc->c0.stream;
-  int32_t* d_ids = nullptr;
-  float* d_t = nullptr;
-  CK(cudaMalloc((void**)&d_ids, pixels * 2 * sizeof(int32_t)));
-  CK(cudaMalloc((void**)&d_t, pixels * sizeof(float)));
+  DevBuf b_ids, b_t;
+  CK(b_ids.alloc(pixels * 2 * sizeof(int32_t)));
+  CK(b_t.alloc(pixels * sizeof(float)));
+  int32_t* d_ids = b_ids.as<int32_t>();
+  float* d_t = b_t.as<float>();
   CK(cudaMemsetAsync(d_ids, 0xff, pixels * 2 * sizeof(int32_t), st));
   {
     std::vector<float> inf(pixels, __builtin_inff());
@@ -1644,13 +1666,12 @@ int b200rt_primary_ids(b200rt_scene* sc, int camera_index, const B200RenderOpts*
   Timers tm = make_timers(sc->c0, false);
   int launches = 0, wr = 0;
   rc = run_waves(sc, sc->c0, opts && opts->exact_traversal, true, false, tm, &launches, &wr);
-  if (rc) { cudaFree(d_ids); cudaFree(d_t); return rc; }
+  if (rc) return rc;
   k_export_ids<<<sc->sm_count * 4, 256, 0, st>>>(sc->c0.P, R.n_paths, d_ids, d_t);
   CK(cudaMemcpyAsync(ids_out, d_ids, pixels * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(t_out, d_t, pixels * sizeof(float), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  cudaFree(d_ids); cudaFree(d_t);
-  return B200RT_OK;
+  return check_overflow(sc, "b200rt_primary_ids");
 } B200RT_CATCH
 
 int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t exact, int32_t* ids_out, float* t_out,
@@ -1664,12 +1685,13 @@ int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t ex
   int rc = ensure_pool(sc, sc->c0, (size_t)n + 1024, 1024);
   if (rc) return rc;
   cudaStream_t st = sc->c0.stream;
-  float* d_rays = nullptr;
-  int32_t* d_ids = nullptr;
-  float* d_t = nullptr;
-  CK(cudaMalloc((void**)&d_rays, (size_t)n * 8 * sizeof(float)));
-  CK(cudaMalloc((void**)&d_ids, (size_t)n * 2 * sizeof(int32_t)));
-  CK(cudaMalloc((void**)&d_t, (size_t)n * sizeof(float)));
+  DevBuf b_rays, b_ids, b_t;
+  CK(b_rays.alloc((size_t)n * 8 * sizeof(float)));
+  CK(b_ids.alloc((size_t)n * 2 * sizeof(int32_t)));
+  CK(b_t.alloc((size_t)n * sizeof(float)));
+  float* d_rays = b_rays.as<float>();
+  int32_t* d_ids = b_ids.as<int32_t>();
+  float* d_t = b_t.as<float>();
   CK(cudaMemcpyAsync(d_rays, rays, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(sc->c0.d_counters, 0, sizeof(Counters), st));
   k_import_rays<<<sc->sm_count * 4, 256, 0, st>>>(sc->c0.P, d_rays, (uint32_t)n, sc->c0.d_waves);
@@ -1682,6 +1704,8 @@ int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t ex
   CK(cudaMemcpyAsync(ids_out, d_ids, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(t_out, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  rc = check_overflow(sc, "b200rt_trace_rays");
+  if (rc) return rc;
   if (stats) {
     Counters hc;
     CK(cudaMemcpy(&hc, sc->c0.d_counters, sizeof(hc), cudaMemcpyDeviceToHost));
@@ -1693,10 +1717,9 @@ int b200rt_trace_rays(b200rt_scene* sc, const float* rays, int64_t n, int32_t ex
     tm.collect(ms);
     stats->ms_extend = ms[ST_EXTEND];
     stats->launches = launches; stats->waves = 1;
-    stats->node_bytes = (sc->S.use_wide && !exact && sc->S.semantics != B200RT_SEM_HW1) ? 80 : 64;
+    stats->node_bytes = (sc->S.use_wide && !exact && sc->S.semantics != B200RT_SEM_HW1) ? (int)sizeof(b200rt_wide::Node) : 64;
     stats->top_objects = exact ? 0 : sc->S.n_top;
   }
-  cudaFree(d_rays); cudaFree(d_ids); cudaFree(d_t);
   return B200RT_OK;
 } B200RT_CATCH
 

@@ -21,6 +21,9 @@
 // on the host (g++) against the oracle; only the warp scheduling below (#ifdef __CUDACC__) is device-only.
 #pragma once
 #include "rt_traverse.cuh"
+#include "wide_bvh.h"   // the node encoding (RT_WIDE_BF16) is shared with the host builder
+
+#define RT_WNODE_F4 (RT_WIDE_BF16 ? 8 : 5)   // float4 per node
 
 #define RT_WSTACK 16        // shared-memory stack entries per thread (node groups); scenes whose wide tree is deeper use k_trace_fast
 #ifndef RT_WIDE_NODE_VOTE
@@ -186,6 +189,43 @@ __device__ __forceinline__ uint32_t wide_octant_permute(uint32_t x, uint32_t oct
   return x;
 }
 
+#if RT_WIDE_BF16
+// The same answer for the bfloat16 encoding (wide_bvh.h).  A slot's word per axis is (hi << 16) | lo, both offsets from
+// the node's origin.  `w * 65536` is lo as a float, exactly; `w * 1` is hi with the lo bits left in its low mantissa,
+// which can only enlarge the box.  Which of the two is the near plane depends on the sign of the direction, and that
+// choice is the multiplier: one IMAD on the FMA pipe per plane, no select, no shift, nothing on the ALU pipe.
+__device__ __forceinline__ uint32_t wide_node_hits_bf16(const float4 n0, const float4* pl, const WideRay& r, float bound_slack) {
+  const float bx = (n0.x - r.o.x) * r.inv.x, by = (n0.y - r.o.y) * r.inv.y, bz = (n0.z - r.o.z) * r.inv.z;
+  // 65536 where the ray travels towards + on that axis (near = lo), else 1 (near = hi); the far multiplier is the other
+  const uint32_t ox = (r.oct_inv >> 2) & 1u, oy = (r.oct_inv >> 1) & 1u, oz = r.oct_inv & 1u;
+  const uint32_t mnx = 1u + 65535u * ox, mny = 1u + 65535u * oy, mnz = 1u + 65535u * oz;
+  const uint32_t mfx = 65536u - 65535u * ox, mfy = 65536u - 65535u * oy, mfz = 65536u - 65535u * oz;
+  const float fsx = r.inv.x * 1.000004f, fsy = r.inv.y * 1.000004f, fsz = r.inv.z * 1.000004f;   // far planes carry the slack
+  const float fbx = bx * 1.000004f, fby = by * 1.000004f, fbz = bz * 1.000004f;
+  uint32_t hits = 0u;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const float4 X = __ldg(pl + h), Y = __ldg(pl + 2 + h), Z = __ldg(pl + 4 + h);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t wx = __float_as_uint(k == 0 ? X.x : k == 1 ? X.y : k == 2 ? X.z : X.w);
+      const uint32_t wy = __float_as_uint(k == 0 ? Y.x : k == 1 ? Y.y : k == 2 ? Y.z : Y.w);
+      const uint32_t wz = __float_as_uint(k == 0 ? Z.x : k == 1 ? Z.y : k == 2 ? Z.z : Z.w);
+      const float tnx = __fmaf_rn(__uint_as_float(wx * mnx), r.inv.x, bx);
+      const float tny = __fmaf_rn(__uint_as_float(wy * mny), r.inv.y, by);
+      const float tnz = __fmaf_rn(__uint_as_float(wz * mnz), r.inv.z, bz);
+      const float tfx = __fmaf_rn(__uint_as_float(wx * mfx), fsx, fbx);
+      const float tfy = __fmaf_rn(__uint_as_float(wy * mfy), fsy, fby);
+      const float tfz = __fmaf_rn(__uint_as_float(wz * mfz), fsz, fbz);
+      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+      const float tf = fminf(fminf(tfx, tfy), tfz);
+      if (tn <= fminf(tf, bound_slack)) hits |= 1u << (4 * h + k);
+    }
+  }
+  return hits;
+}
+#endif
+
 // Takes the nearest unvisited child of the lane's node group, tests its 8 children and makes them the new groups.
 // Returns true when the old group still has unvisited children: the caller pushes `rest`.
 __device__ __forceinline__ bool wide_node_step(const float4* wide_nodes, WideLane& L, float bound_slack,
@@ -197,11 +237,15 @@ __device__ __forceinline__ bool wide_node_step(const float4* wide_nodes, WideLan
   rest = make_uint2(L.G.x, L.G.y & ~(1u << bit));
   const bool more = (rest.y & 0xff000000u) != 0u;
   tc.nodes++;
-  const float4 n0 = __ldg(wide_nodes + 5 * idx);
-  const float child_base = __ldg(reinterpret_cast<const float*>(wide_nodes + 5 * idx + 1));
+  const float4 n0 = __ldg(wide_nodes + RT_WNODE_F4 * idx);
+  const float child_base = __ldg(reinterpret_cast<const float*>(wide_nodes + RT_WNODE_F4 * idx + 1));
+#if RT_WIDE_BF16
+  const uint32_t hits = wide_node_hits_bf16(n0, wide_nodes + RT_WNODE_F4 * idx + 2, L.cr, bound_slack);
+#else
   const float4 n2 = __ldg(wide_nodes + 5 * idx + 2), n3 = __ldg(wide_nodes + 5 * idx + 3);
   const float4 n4 = __ldg(wide_nodes + 5 * idx + 4);
   const uint32_t hits = wide_node_hits(n0, n2, n3, n4, L.cr, bound_slack);
+#endif
   const uint32_t imask = __float_as_uint(n0.w) >> 24;
   // inner slots: front to back for this ray is "highest bit first" after the octant permutation
   L.G = make_uint2(__float_as_uint(child_base), (wide_octant_permute(hits & imask, L.cr.oct_inv) << 24) | imask);
@@ -217,7 +261,7 @@ __device__ __forceinline__ bool wide_triangles(const DScene& S, WideLane& L, flo
                                                         TravCounters& tc) {
   // L.T = {node, hit leaf slots}: the node's second float4 says where its triangles start and, per slot, how many
   // (unary 1 / 3 / 7 in the top bits of the meta byte) at which offset (low 5 bits): up to 24 triangles per node
-  const float4 n1 = __ldg(S.wide_nodes + 5 * (size_t)L.T.x + 1);
+  const float4 n1 = __ldg(S.wide_nodes + RT_WNODE_F4 * (size_t)L.T.x + 1);
   const uint32_t tri_base = __float_as_uint(n1.y);
   uint32_t slots = L.T.y, bits = 0u;
   L.T.y = 0u;

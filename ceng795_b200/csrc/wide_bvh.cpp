@@ -133,6 +133,12 @@ int build(const b200rt_bvh_node* bin, uint32_t root, const float* geom, float gr
     }
     Node nd;
     std::memset(&nd, 0, sizeof(nd));
+#if RT_WIDE_BF16
+    for (int a = 0; a < 3; a++) nd.p[a] = lo[a];
+    // bfloat16 of a non-negative float: the upper half of its bits; truncation rounds down, +0xffff first rounds up
+    auto bf_to_f = [](uint32_t h) { const uint32_t u = h << 16; float f; std::memcpy(&f, &u, 4); return f; };
+    auto f_bits = [](float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; };
+#else
     double scale[3];
     for (int a = 0; a < 3; a++) {
       nd.p[a] = lo[a];
@@ -143,10 +149,27 @@ int build(const b200rt_bvh_node* bin, uint32_t root, const float* geom, float gr
       nd.e[a] = (uint8_t)(e + 127);
       scale[a] = std::ldexp(1.0, e);
     }
+#endif
     nd.child_base = (uint32_t)nodes.size();
     nd.tri_base = (uint32_t)tri_order.size();
     for (int s = 0; s < 8; s++) {
       const int c = child_in[s];
+#if RT_WIDE_BF16
+      if (c < 0) {  // empty slot: meta 0, and a box that is inside out (min = 3.4e38, max = 0)
+        for (int a = 0; a < 3; a++) nd.planes[a][s] = 0x00007f7fu;
+        continue;
+      }
+      for (int a = 0; a < 3; a++) {
+        const double vl = std::max(0.0, (double)ch[c].mn[a] - (double)lo[a]);
+        const double vh = std::max(0.0, (double)ch[c].mx[a] - (double)lo[a]);
+        uint32_t ql = f_bits((float)vl) >> 16;
+        uint32_t qh = (f_bits((float)vh) + 0xffffu) >> 16;
+        // (float)v may have rounded the wrong way: step until the decoded plane is on the safe side of the exact one
+        while (ql > 0u && (double)lo[a] + (double)bf_to_f(ql) > (double)ch[c].mn[a]) ql--;
+        while (qh < 0x7f7fu && (double)lo[a] + (double)bf_to_f(qh) < (double)ch[c].mx[a]) qh++;
+        nd.planes[a][s] = (qh << 16) | ql;
+      }
+#else
       if (c < 0) {  // empty slot: meta 0, and a box that is inside out
         for (int a = 0; a < 3; a++) { nd.qlo[a][s] = 255; nd.qhi[a][s] = 0; }
         continue;
@@ -160,6 +183,7 @@ int build(const b200rt_bvh_node* bin, uint32_t root, const float* geom, float gr
         while (qh < 255.0 && (double)lo[a] + qh * scale[a] < (double)ch[c].mx[a]) qh += 1.0;
         nd.qlo[a][s] = (uint8_t)ql; nd.qhi[a][s] = (uint8_t)qh;
       }
+#endif
       if (expandable(ch[c].ref)) {
         nd.imask |= (uint8_t)(1u << s);
         nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));

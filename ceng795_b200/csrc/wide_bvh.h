@@ -19,6 +19,27 @@
 
 namespace b200rt_wide {
 
+// Two encodings of the child boxes, chosen when the library is compiled (RT_WIDE_BF16; both were measured on the device,
+// profiles/r02_tuning.txt).  0: 8-bit planes in a per-node power-of-two grid, 80 bytes.  1: planes as bfloat16 offsets
+// from the node's origin, (hi << 16) | lo per slot and axis, 128 bytes = one cache line: `lo` becomes a float by a
+// multiply by 65536 and `hi` by using the word as it is (its low half, the `lo` bits, can only enlarge the box), both on
+// the FMA pipe — the byte extraction of encoding 0 runs on the ALU pipe, which is the busy one in the traversal kernel.
+#ifndef RT_WIDE_BF16
+#define RT_WIDE_BF16 0   // measured: no faster (3.59-3.65 against 3.54 ms per cfg2 frame): the ALU pipe drops from 62 to 48 %
+                         // busy, but 128-byte nodes and 24 more live registers put it back into long-scoreboard stalls
+#endif
+#if RT_WIDE_BF16
+struct Node {            // 128 bytes = 8 x float4
+  float p[3];            // origin of the node's frame (its box minimum)
+  uint8_t e[3];          // unused in this encoding
+  uint8_t imask;         // bit s set: the child in slot s is an inner node
+  uint32_t child_base;   // inner children are stored contiguously in slot order from here
+  uint32_t tri_base;     // triangles of the leaf children: [tri_base, tri_base + 24) in the wide triangle order
+  uint8_t meta[8];       // 0 empty; inner: 0x20 | (24 + slot); leaf: unary count (1,3,7) << 5 | offset from tri_base
+  uint32_t planes[3][8]; // axis, slot: (bf16(max - p) rounded up) << 16 | bf16(min - p) rounded down
+};
+static_assert(sizeof(Node) == 128, "wide node must be 128 bytes");
+#else
 struct Node {            // 80 bytes = 5 x float4
   float p[3];            // origin of the node's quantisation frame (its box minimum)
   uint8_t e[3];          // biased exponents: plane = p + q * 2^(e-127)
@@ -30,6 +51,7 @@ struct Node {            // 80 bytes = 5 x float4
   uint8_t qhi[3][8];     // x, y, z maximum planes
 };
 static_assert(sizeof(Node) == 80, "wide node must be 80 bytes");
+#endif
 
 struct Stats {
   int nodes, depth, leaf_children, inner_children;
