@@ -283,7 +283,7 @@ def run_b200(args):
                      ("row_begin", "row_end", "row_stride", "row_group", "sample_begin", "sample_end")}
         return o
 
-    def one_step(out=None):
+    def one_step(out=None, pipelined=False):
         if ppm:
             st = sc.trace_n_photons(ph_cnt, first_photon=pass_no[0] * photons + ph_first, seed=args.seed)
             pass_no[0] += 1
@@ -296,8 +296,13 @@ def run_b200(args):
                 sc.frame_begin()
             st = sc.render_shared(0, seed=args.seed, **o)
             if rank == 0:
-                sc.frame_collect(world, out)               # waits on the device for every rank's share
+                if pipelined and out is not None:
+                    sc.frame_collect_async(world, out)     # the host copy overlaps the next frame (render_wait below)
+                else:
+                    sc.frame_collect(world, out)           # waits on the device for every rank's share
             return st
+        if out is not None and pipelined:
+            return sc.render_image_async(0, out, seed=args.seed, **o)
         if out is not None:
             return sc.render_image(0, out=out, seed=args.seed, **o)[1]
         return sc.render_device(0, seed=args.seed, **o)[1]
@@ -334,8 +339,12 @@ def run_b200(args):
     rays = agg["photon_rays"] if ppm else agg["rays_primary"] + agg["rays_shadow"] + agg["rays_secondary"]
 
     # ---- end to end through the C ABI with HOST buffers ---------------------------
-    pinned = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
-    out = pinned.numpy()
+    # two page-locked host frames: step k's frame is copied into buffer k % 2 while step k+1 renders
+    # (b200rt_render_async / b200rt_frame_collect_async); every step's frame reaches host memory inside the timed region
+    pinned = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    outs = [p.numpy() for p in pinned]
+    out = outs[0]
+    e2e_no = [0]
 
     def e2e_step():
         if ppm:
@@ -347,16 +356,21 @@ def run_b200(args):
             else:
                 sc.density_estimation(photons * pass_no[0], out=out)
             return st.photon_rays
-        st = one_step(out)
+        e2e_no[0] += 1
+        st = one_step(outs[e2e_no[0] % 2], pipelined=not args.no_pipeline)
         return st.rays_total
 
     for _ in range(max(1, min(3, args.warmup))):
         e2e_step()
+    if not ppm:
+        sc.render_wait()
     barrier()
     t0 = time.perf_counter()
     e2e_rays = 0
     for _ in range(args.steps):
         e2e_rays += e2e_step()
+    if not ppm:
+        sc.render_wait()            # the last frames' host copies
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
@@ -508,6 +522,8 @@ def main():
     ap.add_argument("--photons", type=int, default=None, help="photons per pass override for cfg5")
     ap.add_argument("--seed", type=int, default=795)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="e2e: wait for every frame's host copy before the next frame starts (b200rt_render)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3

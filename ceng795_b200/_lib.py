@@ -228,6 +228,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         "b200rt_scene_create": (C.c_int, [P(SceneDesc), C.c_int, P(C.c_void_p)]),
         "b200rt_scene_destroy": (None, [C.c_void_p]),
         "b200rt_render": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), C.c_void_p, P(RenderStats)]),
+        "b200rt_render_async": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), C.c_void_p, P(RenderStats)]),
+        "b200rt_render_wait": (C.c_int, [C.c_void_p]),
+        "b200rt_frame_collect_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
         "b200rt_render_device": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), P(C.c_void_p), P(RenderStats)]),
         "b200rt_primary_ids": (C.c_int, [C.c_void_p, C.c_int, P(RenderOpts), C.c_void_p, C.c_void_p]),
         "b200rt_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,

@@ -90,6 +90,13 @@ struct b200rt_scene {
   std::vector<WaveCtx*> more;   // contexts 1.. (created on first use)
   float4* d_accum;
   size_t accum_pixels;
+  // pipelined host copies (b200rt_render_async): two staging frames, a copy stream, events
+  float4* d_stage[2];
+  size_t stage_pixels;
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_staged[2], ev_copied[2];
+  bool copy_pending[2];
+  int stage_next;
   int* d_lit;            // parity hook: lit shadow tests per pixel x light (b200rt_debug_lit_counts)
   size_t lit_entries;
   bool lit_on;
@@ -616,6 +623,40 @@ int ppm_ensure_rtab(b200rt_scene* sc) {
   return B200RT_OK;
 }
 
+// Queues "frame in d_accum -> host memory" without waiting for it: a device-to-device copy into one of two staging
+// frames on the scene's stream (tens of microseconds), then the host copy on a stream of its own, so that the next
+// frame can be rendered into d_accum while this one crosses PCIe.  The staging frame is reused two frames later, after
+// its host copy has landed.
+int queue_host_copy(b200rt_scene* sc, float* out, size_t pixels) {
+  if (!sc->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaEventCreateWithFlags(&sc->ev_staged[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&sc->ev_copied[k], cudaEventDisableTiming));
+    }
+  }
+  if (sc->stage_pixels < pixels) {
+    CK(cudaStreamSynchronize(sc->copy_stream));
+    for (int k = 0; k < 2; k++) {
+      if (sc->d_stage[k]) cudaFree(sc->d_stage[k]);
+      sc->d_stage[k] = nullptr; sc->copy_pending[k] = false;
+    }
+    sc->stage_pixels = 0;
+    for (int k = 0; k < 2; k++) CK(cudaMalloc((void**)&sc->d_stage[k], pixels * sizeof(float4)));
+    sc->stage_pixels = pixels;
+  }
+  const int k = sc->stage_next;
+  sc->stage_next ^= 1;
+  if (sc->copy_pending[k]) CK(cudaEventSynchronize(sc->ev_copied[k]));
+  CK(cudaMemcpyAsync(sc->d_stage[k], sc->d_accum, pixels * sizeof(float4), cudaMemcpyDeviceToDevice, sc->c0.stream));
+  CK(cudaEventRecord(sc->ev_staged[k], sc->c0.stream));
+  CK(cudaStreamWaitEvent(sc->copy_stream, sc->ev_staged[k], 0));
+  CK(cudaMemcpyAsync(out, sc->d_stage[k], pixels * sizeof(float4), cudaMemcpyDeviceToHost, sc->copy_stream));
+  CK(cudaEventRecord(sc->ev_copied[k], sc->copy_stream));
+  sc->copy_pending[k] = true;
+  return B200RT_OK;
+}
+
 // A traversal-stack or pool overflow inside a wave loop must not come back as B200RT_OK with wrong results.
 int check_overflow(b200rt_scene* sc, const char* who) {
   unsigned int ov = 0;
@@ -1064,6 +1105,9 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
   sc->device = device;
   sc->d_accum = nullptr; sc->accum_pixels = 0;
   sc->d_lit = nullptr; sc->lit_entries = 0; sc->lit_on = false;
+  sc->d_stage[0] = sc->d_stage[1] = nullptr; sc->stage_pixels = 0; sc->copy_stream = nullptr;
+  sc->ev_staged[0] = sc->ev_staged[1] = sc->ev_copied[0] = sc->ev_copied[1] = nullptr;
+  sc->copy_pending[0] = sc->copy_pending[1] = false; sc->stage_next = 0;
   memset(&sc->HP, 0, sizeof(HitPoints));
   memset(&sc->G, 0, sizeof(PpmGrid));
   sc->d_pc = nullptr; sc->d_rtab = nullptr; sc->d_export = nullptr; sc->d_scan_tmp = nullptr;
@@ -1290,6 +1334,15 @@ void b200rt_scene_destroy(b200rt_scene* sc) {
   for (void* p : sc->allocs)
     if (p) cudaFree(p);
   ppm_free(sc);
+  if (sc->copy_stream) {
+    cudaStreamSynchronize(sc->copy_stream);
+    cudaStreamDestroy(sc->copy_stream);
+  }
+  for (int k = 0; k < 2; k++) {
+    if (sc->d_stage[k]) cudaFree(sc->d_stage[k]);
+    if (sc->ev_staged[k]) cudaEventDestroy(sc->ev_staged[k]);
+    if (sc->ev_copied[k]) cudaEventDestroy(sc->ev_copied[k]);
+  }
   if (sc->tgt_frame && sc->tgt_ipc) cudaIpcCloseMemHandle(sc->tgt_frame);
   if (sc->d_sync_err) cudaFree(sc->d_sync_err);
   if (sc->d_accum) cudaFree(sc->d_accum);
@@ -1627,6 +1680,29 @@ int b200rt_render(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts
   if (rc) return rc;
   const b200rt_camera& c = sc->cameras[camera_index];
   CK(cudaMemcpy(rgbw_out, sc->d_accum, (size_t)c.width * c.height * sizeof(float4), cudaMemcpyDeviceToHost));
+  return B200RT_OK;
+} B200RT_CATCH
+
+int b200rt_render_async(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, float* rgbw_out,
+                        B200RenderStats* stats) try {
+  if (!rgbw_out) {
+    b200rt_internal_set_error("b200rt_render_async: null output");
+    return B200RT_E_INVALID;
+  }
+  int rc = render_impl(sc, camera_index, opts, stats);
+  if (rc) return rc;
+  const b200rt_camera& c = sc->cameras[camera_index];
+  return queue_host_copy(sc, rgbw_out, (size_t)c.width * c.height);
+} B200RT_CATCH
+
+int b200rt_render_wait(b200rt_scene* sc) try {
+  if (!sc) return B200RT_E_INVALID;
+  CK(cudaSetDevice(sc->device));
+  for (int k = 0; k < 2; k++)
+    if (sc->copy_pending[k]) {
+      CK(cudaEventSynchronize(sc->ev_copied[k]));
+      sc->copy_pending[k] = false;
+    }
   return B200RT_OK;
 } B200RT_CATCH
 

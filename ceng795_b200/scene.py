@@ -717,6 +717,19 @@ class Scene:
                    "b200rt_render")
         return out, st
 
+    def render_image_async(self, camera_index: int, out: np.ndarray, **opts):
+        """render_image whose host copy is only queued: `out` (page-locked memory, kept alive by the caller) is valid
+        after render_wait(); the copy overlaps the next render of this scene.  Returns RenderStats."""
+        self.upload()
+        st = _lib.RenderStats()
+        o = self._opts(**opts)
+        _lib.check(self._L.b200rt_render_async(self._scene, camera_index, C.byref(o), out.ctypes.data, C.byref(st)),
+                   "b200rt_render_async")
+        return st
+
+    def render_wait(self):
+        _lib.check(self._L.b200rt_render_wait(self._scene), "b200rt_render_wait")
+
     def count_lit(self, enable: bool = True):
         """Parity hook: later renders count, per pixel and light, the shadow tests that came out lit."""
         self.upload()
@@ -864,6 +877,10 @@ class Scene:
         _lib.check(self._L.b200rt_render_shared(self._scene, camera_index, C.byref(o), C.byref(st)),
                    "b200rt_render_shared")
         return st
+
+    def frame_collect_async(self, parts: int, out: np.ndarray):
+        """frame_collect whose host copy is only queued (render_wait() waits for it)."""
+        _lib.check(self._L.b200rt_frame_collect_async(self._scene, parts, out.ctypes.data), "b200rt_frame_collect_async")
 
     def frame_collect(self, parts: int, out: np.ndarray | None = None):
         """Owner: waits on the device for `parts` shares; copies the frame into `out` when given.  Returns the frame's

@@ -383,6 +383,14 @@ void b200rt_scene_destroy(b200rt_scene*);
  * HOST memory. */
 int b200rt_render(b200rt_scene*, int camera_index, const B200RenderOpts*, float* rgbw_out,
                   B200RenderStats* stats_out);
+/* Pipelined form for a host that renders frame after frame: returns once the frame is complete in HBM and its copy
+ * into rgbw_out has been QUEUED (staged device-to-device, then copied on a stream of its own), so the copy crosses PCIe
+ * while the next b200rt_render* call of the scene computes.  rgbw_out should be page-locked for the overlap to happen
+ * and must stay valid until b200rt_render_wait, which blocks until every queued copy has landed.  At most two copies
+ * are in flight; a third call waits for the oldest. */
+int b200rt_render_async(b200rt_scene*, int camera_index, const B200RenderOpts*, float* rgbw_out,
+                        B200RenderStats* stats_out);
+int b200rt_render_wait(b200rt_scene*);
 /* Same, but the result stays in HBM (device pointer returned, owned by scene). */
 int b200rt_render_device(b200rt_scene*, int camera_index, const B200RenderOpts*,
                          float** d_rgbw_out, B200RenderStats* stats_out);
@@ -475,6 +483,8 @@ int b200rt_render_shared(b200rt_scene*, int camera_index, const B200RenderOpts*,
 /* Owner: waits (on the device) until `parts` shares of the current frame have arrived, then copies the frame to host
  * memory (rgbw_out NULL: it stays in HBM; d_rgbw_out optional). */
 int b200rt_frame_collect(b200rt_scene* owner, int parts, float* rgbw_out, float** d_rgbw_out);
+/* As b200rt_render_async: waits for the shares on the device, queues the host copy, returns; b200rt_render_wait. */
+int b200rt_frame_collect_async(b200rt_scene* owner, int parts, float* rgbw_out);
 /* One host thread, n scenes of the same description on n devices (scenes[0] owns the frame): export + attach + begin +
  * one worker thread per device for render_shared + collect.  The frame equals b200rt_render's on one device: bit for
  * bit for 1-sample cameras, up to float summation order for splatting / multi-sample cameras (as the reference's own

@@ -64,3 +64,23 @@ def test_transformed_light_shapes(gpu, tmp_path):
     xml = xml.replace('<LightSphere id="1">\n      <Material>1</Material>',
                       '<LightSphere id="1">\n      <Material>1</Material>\n      <Transformations>s2 t4</Transformations>')
     _check(scene.Scene(xml, "hw7", base_dir=str(tmp_path)), seed=4, stochastic=True)
+
+
+@pytest.mark.gpu
+def test_pipelined_host_copy_delivers_every_frame(gpu):
+    """b200rt_render_async / b200rt_render_wait: the copy of frame k overlaps the render of frame k+1; every frame
+    arrives, in its own buffer, with the bytes b200rt_render writes — also with more frames in flight than staging
+    buffers (the third call waits for the oldest copy)."""
+    import torch
+    sc = scene.Scene(scenes.cfg2_hw3(n=96, width=320, height=200), "hw3")
+    rows = (48, 96, 152, 200)                           # four different frames: the first `rows[k]` rows of the picture
+    want = [sc.render_image(0, row_begin=0, row_end=r)[0] for r in rows]
+    assert not np.array_equal(want[0], want[1])
+    bufs = [torch.empty((200, 320, 4), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+    for k, r in enumerate(rows):
+        st = sc.render_image_async(0, bufs[k].numpy(), row_begin=0, row_end=r)
+        assert st.rays_total > 0
+    sc.render_wait()
+    for k in range(4):
+        assert np.array_equal(bufs[k].numpy().view(np.uint32), want[k].view(np.uint32))
+    sc.render_wait()                                   # nothing pending: returns at once
