@@ -1,5 +1,6 @@
 // b200rt_api.cu — device side of the C ABI (include/b200rt.h): scene upload,
 // the wavefront driver, and the parity / measurement hooks.
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -268,6 +269,19 @@ void launch_wide(b200rt_scene* sc, WaveCtx& cx, bool any, bool mode7, int d) {
 #undef LW
 }
 
+// Which tree a wave loop walks.  The 8-wide kernel wins where the rays of a warp part company (1-sample frames with
+// their shadow and mirror waves, photon waves, caller-supplied rays: cfg2 3.54 against 3.99 ms); on a multi-sample
+// camera the strata of a pixel travel together through whole-warp batches and the binary walk's cheaper steps win
+// (cfg3 189 against 211 ms); path tracing is a draw (cfg4 858 / 860 ms).  B200RT_WIDE_MULTISAMPLE=1 forces the wide tree.
+bool wide_for(const b200rt_scene* sc, bool exact, bool frame) {
+  if (!sc->S.use_wide || exact || sc->S.semantics == B200RT_SEM_HW1) return false;
+  if (frame && sc->S.cam.samples_sqrt > 1 && !sc->S.integrator) {
+    const char* e = getenv("B200RT_WIDE_MULTISAMPLE");
+    return e && atoi(e) != 0;
+  }
+  return true;
+}
+
 Timers make_timers(WaveCtx& cx, bool on) {
   Timers tm;
   tm.pool = &cx.ev_pool; tm.used = 0; tm.s = cx.stream; tm.on = on;
@@ -283,7 +297,7 @@ int run_waves(b200rt_scene* sc, WaveCtx& cx, bool exact, bool primary_only, bool
   const int grid_p = sc->sm_count * (RT_FAST_MIN_BLOCKS > 8 ? RT_FAST_MIN_BLOCKS : 8);  // persistent traversal grid: resident CTAs of 128 threads per SM
   const int grid_s = sc->sm_count * 8;
   const bool hw1 = S.semantics == B200RT_SEM_HW1;
-  const bool wide = S.use_wide && !exact && !hw1;
+  const bool wide = wide_for(sc, exact, with_shading);
   const bool mode7 = S.semantics >= B200RT_SEM_HW4;
   const int max_d = primary_only ? 0 : S.max_depth;
   int d_last = 0;
@@ -553,7 +567,7 @@ int render_impl(b200rt_scene* sc, int camera_index, const B200RenderOpts* opts, 
     }
     cudaEventElapsedTime(&stats->ms_total, c0.ev[0], c0.ev[1]);
     stats->waves = waves_total; stats->launches = launches;
-    stats->node_bytes = (sc->S.use_wide && !exact && sc->S.semantics != B200RT_SEM_HW1) ? (int)sizeof(b200rt_wide::Node) : 64;
+    stats->node_bytes = wide_for(sc, exact, true) ? (int)sizeof(b200rt_wide::Node) : 64;
     stats->top_objects = exact ? 0 : sc->S.n_top;
     stats->contexts = K;
   }
@@ -684,6 +698,11 @@ int ppm_rebuild_scan_grid(b200rt_scene* sc, int* launches, int* rebuilds) {
   (*launches)++;
   const double meanR = sumR / (double)n_hp;          // mean of r2 / r0^2
   if (sc->g2_valid ? sumR > 0.8 * sc->g2_sumR : meanR > 0.7) return B200RT_OK;
+  const bool timing = getenv("B200RT_BUILD_TIMING") != nullptr;
+  const auto T0 = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point a) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+  };
   PpmGrid& G2 = sc->G2;
   unsigned int* cc = G2.cell_count;
   unsigned int* cs = G2.cell_start;
@@ -716,18 +735,26 @@ int ppm_rebuild_scan_grid(b200rt_scene* sc, int* launches, int* rebuilds) {
     CK(cudaMemcpyAsync(&total, G2.cell_start + n_hp, sizeof(total), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *launches += 2;
+    if (timing) fprintf(stderr, "b200rt ppm grid: attempt %d cell_r %.5f entries %u (max %zu) at %.2f ms\n", attempt, cell_r, total, max_entries, since(T0));
     if (total <= max_entries || cell_r >= sc->G.r0 || attempt >= 6) break;
     cell_r *= 1.3f;   // hit points that still have a large radius reach too many of the small cells: larger cells
   }
   if ((size_t)total + 1 > sc->entries2_capacity) {
+    // with half as much again: the entry count wanders by a per cent from rebuild to rebuild, and a cudaFree +
+    // cudaMalloc of 300 MB inside a pass was seen to cost anything between 1 and 270 ms
+    const size_t cap = (size_t)total + (size_t)total / 2 + 1024;
     if (G2.cell_pos) cudaFree(G2.cell_pos);
     G2.cell_pos = nullptr; sc->entries2_capacity = 0;
-    CK(cudaMalloc((void**)&G2.cell_pos, sizeof(float4) * ((size_t)total + 1)));
-    sc->entries2_capacity = (size_t)total + 1;
+    CK(cudaMalloc((void**)&G2.cell_pos, sizeof(float4) * cap));
+    sc->entries2_capacity = cap;
   }
   CK(cudaMemcpyAsync(G2.cell_count, G2.cell_start, sizeof(unsigned int) * ((size_t)n_hp + 1), cudaMemcpyDeviceToDevice, st));
   k_ppm_grid<<<sc->sm_count * 4, 256, 0, st>>>(sc->HP, G2, n_hp, 1, (uint32_t)sc->entries2_capacity, sc->d_pc, sc->S.mats);
   CK(cudaGetLastError());
+  if (timing) {
+    CK(cudaStreamSynchronize(st));
+    fprintf(stderr, "b200rt ppm grid: rebuilt, mean R %.4f, %u entries, capacity %zu, %.2f ms\n", meanR, total, sc->entries2_capacity, since(T0));
+  }
   (*launches)++;
   (*rebuilds)++;
   sc->g2_valid = true;
@@ -1271,7 +1298,8 @@ int b200rt_scene_create(const B200SceneDesc* d, int device, b200rt_scene** out) 
     UP(S.wide_root, wroot.data(), wroot.size(), int32_t);
     // the shared-memory stack of k_trace_wide holds one node group per level
     S.use_wide = (want && ws.depth <= RT_WSTACK) ? 1 : 0;
-    if (S.use_wide && !getenv("B200RT_NODE_VOTE")) S.node_vote = RT_WIDE_NODE_VOTE;
+    S.wide_node_vote = RT_WIDE_NODE_VOTE;
+    if (const char* e = getenv("B200RT_WIDE_NODE_VOTE")) S.wide_node_vote = std::max(1, std::min(32, atoi(e)));
     sc->wide_nodes = (int)wnodes.size(); sc->wide_depth = ws.depth;
     sc->wide_blocks = RT_WIDE_MIN_BLOCKS;
     if (const char* e = getenv("B200RT_WIDE_BLOCKS")) { const int v = atoi(e); if (v == 4 || v == 6 || v == 8) sc->wide_blocks = v; }

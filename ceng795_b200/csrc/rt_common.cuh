@@ -80,6 +80,7 @@ struct DScene {
   int semantics, max_depth;
   int refill_closest, refill_any;  // idle lanes before a traversal warp takes new rays (32 = whole-warp batches)
   int node_vote;                   // lanes that must hold an inner node for the warp to keep descending (rt_fast.cuh)
+  int wide_node_vote;   // the same threshold for k_trace_wide (its steps are longer: swept separately)
   v3 background, ambient;
   float shadow_eps, isect_eps;
   uint32_t root;

@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MINB) k_trace_wide(DScene S, Pool P,
     for (;;) {
       // ---- phase 1 (warp-synchronous): node steps, for as long as enough lanes hold an unvisited inner child.  A
       // lane with triangles to test, or with nothing left in its object, waits — but only until fewer than
-      // S.node_vote lanes are still descending: then everybody goes through phase 2.
+      // S.wide_node_vote lanes are still descending: then everybody goes through phase 2.
       for (;;) {
         // a group without unvisited children: take the next one off the stack right here, a lane should not have to
         // wait for phase 2 just to pop
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MINB) k_trace_wide(DScene S, Pool P,
         const bool want_node = has_ray && L.T.y == 0u && (L.G.y & 0xff000000u) != 0u;
         const unsigned mn = __ballot_sync(0xffffffffu, want_node);
         if (mn == 0u) break;
-        if (__popc(mn) < S.node_vote && __any_sync(0xffffffffu, has_ray && !want_node)) break;
+        if (__popc(mn) < S.wide_node_vote && __any_sync(0xffffffffu, has_ray && !want_node)) break;
         if (want_node) {
           const float bound = ANY ? tlimit : L.best.t;
           uint2 rest;
