@@ -316,7 +316,7 @@ def run_b200(args):
     else:
         keys = ("rays_primary", "rays_shadow", "rays_secondary", "nodes_visited", "tris_tested", "spheres_tested",
                 "instances_entered", "sh_nodes_visited", "sh_tris_tested", "sh_spheres_tested", "sh_instances_entered",
-                "launches")
+                "launches", "waves")
         ms_keys = ("ms_generate", "ms_extend", "ms_shade", "ms_shadow")
     agg = {k: 0 for k in keys}
     ms_stage = {k: 0.0 for k in ms_keys}
@@ -426,7 +426,7 @@ def run_b200(args):
         top_tests = int(st.top_objects) * n_closest
         ext_bytes = (nb * (agg["nodes_visited"] - top_tests) + 32 * top_tests + 48 * agg["tris_tested"]
                      + (32 + 24) * n_closest)
-        n_launch = max(1, args.steps * (sc.spec.max_depth - 1))
+        n_launch = max(1, args.steps * (sc.spec.max_depth - 1) * ((photons + (8 << 20) - 1) // (8 << 20)))   # per 8 Mi-photon batch
         per_ray = {"nodes": (agg["nodes_visited"] - top_tests) / max(1, n_closest),
                    "top_level_gates": int(st.top_objects), "tris": agg["tris_tested"] / max(1, n_closest),
                    "hit_points_scanned_per_photon_ray": agg["entries_scanned"] / max(1, n_closest),
@@ -449,7 +449,7 @@ def run_b200(args):
                      + 20 * agg["spheres_tested"] + 112 * agg["instances_entered"] + (32 + 24) * n_closest)
         sh_bytes = (nb * (agg["sh_nodes_visited"] - top_a) + 32 * top_a + 48 * agg["sh_tris_tested"]
                     + 20 * agg["sh_spheres_tested"] + 112 * agg["sh_instances_entered"] + (36 + 1) * n_any)
-        n_launch = max(1, args.steps * (sc.spec.max_depth + 1))
+        n_launch = max(1, agg["waves"])   # one closest-hit and one shadow launch per wave of every row / strata batch
         mode = 7 if wl["tree"] in ("hw4", "hw5", "hw6", "hw7", "ppm") else 2
         if wl["tree"] == "hw1":
             kn = "k_trace_hw1_fast<{}> (SAH tree over all triangles, HW1's order-dependent rule on the near-tie set)"

@@ -41,8 +41,10 @@ def to_bytes(v, unit):
 def main():
     commit = os.environ.get("B200RT_COMMIT") or subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT,
                                                              capture_output=True, text=True).stdout.strip()
-    res = {"_source": f"ncu --set full --clock-control none captures of bench.py at commit {commit} (tools/r02_evidence.sh); "
-                      "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the captured launches of a class"}
+    path0 = os.path.join(ROOT, "profiles", "traffic.json")
+    res = json.load(open(path0)) if (os.environ.get("B200RT_TRAFFIC_MERGE") and os.path.exists(path0)) else {}
+    res.update({"_source": f"ncu --set full --clock-control none captures of bench.py at commit {commit} (tools/r02_evidence.sh); "
+                      "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the captured launches of a class"})
     for arg in sys.argv[1:]:
         cfg, path = arg.split("=", 1)
         agg = {}
