@@ -66,3 +66,32 @@ def test_builder_rejects_what_a_tree_does_not_have():
         assert rc == _lib.E_UNSUPPORTED if hasattr(_lib, "E_UNSUPPORTED") else rc < 0
     finally:
         L.b200rt_builder_destroy(b)
+
+
+def test_multi_gpu_entry_points_refuse_bad_arguments_without_touching_a_device():
+    """The multi-GPU entry points of the C ABI check their arguments before anything else: error codes and a message,
+    no crash, on a box without a GPU too."""
+    import ctypes as C
+    L = _lib.load()
+    st = _lib.RenderStats()
+    out = np.zeros(4, np.float32)
+    null_scenes = (C.c_void_p * 2)(None, None)
+    assert L.b200rt_render_multi(null_scenes, 2, 0, None, out.ctypes.data, C.byref(st)) < 0
+    assert b"null scene" in L.b200rt_last_error()
+    assert L.b200rt_render_multi(null_scenes, 0, 0, None, out.ctypes.data, C.byref(st)) < 0
+    assert L.b200rt_render_multi(null_scenes, 17, 0, None, out.ctypes.data, C.byref(st)) < 0
+    assert b"1..16 scenes" in L.b200rt_last_error()
+    f = _lib.SharedFrame()
+    for fn, args in (("b200rt_frame_export", (None, 0, C.byref(f))), ("b200rt_frame_attach", (None, C.byref(f))),
+                     ("b200rt_frame_detach", (None,)), ("b200rt_frame_begin", (None,)),
+                     ("b200rt_render_shared", (None, 0, None, C.byref(st))),
+                     ("b200rt_frame_collect", (None, 1, None, None)), ("b200rt_frame_collect_async", (None, 1, out.ctypes.data)),
+                     ("b200rt_render_async", (None, 0, None, out.ctypes.data, C.byref(st))), ("b200rt_render_wait", (None,)),
+                     ("b200rt_ppm_set_share", (None, 0, 1)), ("b200rt_ppm_counts_apply", (None,)),
+                     ("b200rt_ppm_eye_pass_multi", (null_scenes, 2, 0, 0, None)),
+                     ("b200rt_ppm_trace_photons_multi", (null_scenes, 2, None, None)),
+                     ("b200rt_ppm_density_multi", (null_scenes, 2, 1.0, out.ctypes.data)),
+                     ("b200rt_scene_refit", (None, None, None))):
+        assert getattr(L, fn)(*args) < 0, fn
+    o = _lib.RenderOpts()
+    assert L.b200rt_multi_share(None, 0, 0, 1, C.byref(o)) < 0
