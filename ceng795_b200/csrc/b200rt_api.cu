@@ -313,6 +313,7 @@ int run_waves(b200rt_scene* sc, WaveCtx& cx, bool exact, bool primary_only, bool
       k_extend_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.d_waves, d, cx.d_counters);
     } else if (wide) {
       launch_wide(sc, cx, false, mode7, d);
+      (*launches)++;   // k_top_mask (the traversal kernel itself is counted below)
     } else if (mode7) {
       if (exact) k_extend<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.d_waves, d, cx.d_counters);
       else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
@@ -338,6 +339,7 @@ int run_waves(b200rt_scene* sc, WaveCtx& cx, bool exact, bool primary_only, bool
       k_shadow_hw1<<<grid_p, RT_BLOCK, 0, st>>>(S, cx.Q, cx.d_counters);
     } else if (wide) {
       launch_wide(sc, cx, true, mode7, d);
+      (*launches)++;   // k_top_mask
     } else if (mode7) {
       if (exact) k_shadow<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.Q, cx.d_counters);
       else k_trace_fast<true, 7><<<grid_p, RT_BLOCK, 0, st>>>(S, cx.P, cx.Q, cx.d_waves, d, cx.d_counters);
@@ -852,7 +854,7 @@ int b200rt_ppm_eye_pass(b200rt_scene* sc, int camera_index, uint64_t seed, B200P
   k_next_wave<<<1, 1, 0, st>>>(sc->c0.d_waves, 0, sc->c0.d_counters);
   launches++;
   for (int d = 0; d <= sc->S.max_depth; d++) {
-    if (sc->S.use_wide) launch_wide(sc, sc->c0, false, true, d);
+    if (sc->S.use_wide) { launch_wide(sc, sc->c0, false, true, d); launches++; }
     else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.Q, sc->c0.d_waves, d, sc->c0.d_counters);
     k_ppm_eye_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.d_waves, d, sc->HP, sc->c0.d_counters, sc->d_pc);
     k_finish_wave<<<1, 1, 0, st>>>(sc->c0.d_waves, d, sc->c0.P, sc->c0.d_counters);
@@ -1001,7 +1003,7 @@ int b200rt_ppm_trace_photons(b200rt_scene* sc, const B200PpmOpts* opts, B200PpmS
     for (int d = 0; d + 1 < sc->S.max_depth; d++) {
       k_ppm_next_wave<<<1, 1, 0, st>>>(sc->c0.d_waves, d, half, sc->c0.d_counters);
       k_ppm_count_rays<<<1, 1, 0, st>>>(sc->c0.d_waves, d, sc->d_pc);
-      if (sc->S.use_wide) launch_wide(sc, sc->c0, false, true, d);
+      if (sc->S.use_wide) { launch_wide(sc, sc->c0, false, true, d); launches++; }
       else k_trace_fast<false, 7><<<grid_p, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.Q, sc->c0.d_waves, d, sc->c0.d_counters);
       tm.mark(ST_EXTEND);
       k_ppm_photon_shade<<<sc->sm_count * 8, RT_BLOCK, 0, st>>>(sc->S, sc->c0.P, sc->c0.d_waves, d, sc->HP, Gs,

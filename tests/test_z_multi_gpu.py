@@ -85,6 +85,27 @@ def test_shared_frame_of_splatting_cameras_adds_up(gpu, tmp_path):
 
 
 @pytest.mark.gpu
+def test_shared_frame_through_the_hw7_kernels(gpu, tmp_path):
+    """The HW5-HW7 combine kernel (k_combine7) behind the same protocol: a 1-sample Whitted frame with textures, BRDFs
+    and every light class is bit-equal across three shares; a 16-spp path-traced frame (strata batches, box filter
+    adds) agrees to float summation order."""
+    xml = scenes.hw7_scene(str(tmp_path), width=96, height=72, light_scale=3.0)
+    cs = [scene.Scene(xml, "hw7", base_dir=str(tmp_path)) for _ in range(3)]
+    out, rays = _shared_render(cs, seed=5)
+    ref, st = cs[0].render_image(0, seed=5)
+    assert rays == st.rays_total and np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    xml_pt = scenes.hw7_scene(str(tmp_path), width=64, height=48, spp=16, depth=3, stochastic_lights=True,
+                              path_tracing=True, importance=True, light_scale=2.0)
+    cp = [scene.Scene(xml_pt, "hw7", base_dir=str(tmp_path)) for _ in range(2)]
+    assert _share(cp[0], 0, 2)["sample_end"] == 8
+    out, rays = _shared_render(cp, seed=6)
+    ref, st = cp[0].render_image(0, seed=6)
+    assert rays == st.rays_total
+    fin = np.isfinite(ref).all(-1) & np.isfinite(out).all(-1)
+    assert fin.mean() > 0.99 and np.allclose(out[fin], ref[fin], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
 def test_render_shared_without_begin_times_out_cleanly_is_not_needed_when_owner_opens(gpu):
     """Protocol errors are codes, not hangs: rendering into a frame that was never exported is refused."""
     sc = scene.Scene(scenes.cfg2_hw3(n=24, width=64, height=40), "hw3")
