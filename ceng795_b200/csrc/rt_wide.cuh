@@ -29,6 +29,12 @@
 #ifndef RT_WIDE_NODE_VOTE
 #define RT_WIDE_NODE_VOTE 8   // lanes that must still want a node step for phase 1 to go on (swept: profiles/r02_tuning.txt)
 #endif
+#ifndef RT_WIDE_TQ_CLOSEST
+#define RT_WIDE_TQ_CLOSEST 0   // the same for closest-hit rays (costs pruning: a queued leaf cannot shrink best.t yet)
+#endif
+#ifndef RT_WIDE_TQ
+#define RT_WIDE_TQ 4   // leaf steps a shadow ray may queue before it has to test them (0 = test at once; swept)
+#endif
 #ifndef RT_TOP_LINEAR_MAX
 #define RT_TOP_LINEAR_MAX 40  // top-level objects up to which phase 0 scans a flat gate list (one bit each in the lane's object mask)
 #endif
@@ -449,6 +455,13 @@ __global__ void __launch_bounds__(RT_BLOCK, MINB) k_trace_wide(DScene S, Pool P,
                                                                const WaveInfo* waves, int d, Counters* C) {
   __shared__ uint2 s_stack[RT_WSTACK][RT_BLOCK];
   __shared__ float4 s_top[2 * RT_TOP_LINEAR_MAX];
+#if RT_WIDE_TQ
+  // any-hit rays only: leaf steps are QUEUED (up to RT_WIDE_TQ per lane) while the lane goes on descending, and tested
+  // together in phase 2 — no pruning is lost (a shadow ray has no closest hit to shrink towards), an occluded ray
+  // merely learns it a little later
+  __shared__ uint2 s_tq[RT_WIDE_TQ][RT_BLOCK];
+#endif
+  int tqn = 0;
   for (int i = threadIdx.x; i < 2 * S.n_top; i += RT_BLOCK) s_top[i] = __ldg(S.top_objs + i);
   __syncthreads();
 
@@ -497,7 +510,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MINB) k_trace_wide(DScene S, Pool P,
             time = ro.w; tlimit = RT_INF;
           }
           wide_reset(L, hw7);
-          sp = 0;
+          sp = 0; tqn = 0;
           has_ray = true;
           L.objmask = ANY ? Q.omask[k] : P.omask[out_slot];   // phase 0 was done by k_top_mask
         }
@@ -524,12 +537,22 @@ __global__ void __launch_bounds__(RT_BLOCK, MINB) k_trace_wide(DScene S, Pool P,
             if (sp < RT_WSTACK) { s_stack[sp][tid] = rest; sp++; }
             else atomicExch(&C->overflow, 2u);
           }
+#if RT_WIDE_TQ
+          if ((ANY || RT_WIDE_TQ_CLOSEST) && L.T.y != 0u && tqn < (ANY ? RT_WIDE_TQ : RT_WIDE_TQ_CLOSEST)) { s_tq[tqn][tid] = L.T; tqn++; L.T.y = 0u; }
+#endif
         }
       }
       // ---- phase 2: triangles; then, with nothing pending in the group, the stack or the next top-level object
-      if (has_ray && !(L.T.y == 0u && (L.G.y & 0xff000000u) != 0u)) {
+      if (has_ray && (tqn > 0 || !(L.T.y == 0u && (L.G.y & 0xff000000u) != 0u))) {
         bool finished = false;
         if (L.T.y != 0u) finished = wide_triangles<ANY, TRI_MODE>(S, L, tlimit, eps, tc);
+#if RT_WIDE_TQ
+        while (!finished && tqn > 0) {
+          tqn--;
+          L.T = s_tq[tqn][tid];
+          finished = wide_triangles<ANY, TRI_MODE>(S, L, tlimit, eps, tc);
+        }
+#endif
         if (!finished && (L.G.y & 0xff000000u) == 0u) {
           if (sp > 0) {
             sp--;
