@@ -12,10 +12,13 @@
 // visiting order nor pruning can change it.
 //
 // Node step (one 80-byte fetch = five float4): the 8 child boxes are tested in the node's quantisation frame
-// (t = q * (2^e / d) + (p - o) / d, one FMA per plane); hit children set bits in a 32-bit mask — inner children at
-// bit 24 + (slot ^ octant), so "highest bit first" is front to back for this ray without sorting; triangles at
-// their offset from the node's tri_base.  The lane keeps the mask as its current group and pushes the previous
-// group only when it still has unvisited children: the stack depth is the tree depth (<= 16), 8 bytes per level.
+// (t = q * (2^e / d) + (p - o) / d, one FMA per plane; q reaches the FMA through a byte-permute, not a conversion:
+// wide_q2f) and leave one bit per hit SLOT.  Once per node, not per child, the inner slots among them are permuted by
+// the ray's octant — bit 24 + (slot ^ octant), so "highest bit first" is front to back without sorting — and become the
+// lane's current group {child base, unvisited inner slots}; the previous group is pushed only when it still has
+// unvisited members, so the stack depth is the tree depth (<= 16), 8 bytes per level.  The leaf slots are kept as
+// {node, slots}; which triangles they hold (unary count and offset in the node's meta bytes) is decoded when the lane
+// gets to test them — at once for a closest-hit ray, from a short queue in shared memory for a shadow ray.
 //
 // Everything a lane does is written as functions of a WideLane so that tests/wide_host.cpp can run the SAME source
 // on the host (g++) against the oracle; only the warp scheduling below (#ifdef __CUDACC__) is device-only.

@@ -67,6 +67,26 @@ def test_refit_equals_a_fresh_build_of_the_moved_scene(tree, xml):
         fresh.close()
 
 
+def test_refit_of_an_hw7_scene_rebuilds_the_light_objects_too(tmp_path):
+    """HW7: LightMesh / LightSphere are top-level objects that add a light each (with the mesh light's area CDF); the
+    refit has to drop and rebuild exactly those.  Moving an ordinary instance and a sphere, then refitting, equals a
+    fresh build — lights, CDF and all."""
+    xml = scenes.hw7_scene(str(tmp_path), width=48, height=36, stochastic_lights=True, perlin=True)
+    spec = scene.parse_xml(xml, "hw7", base_dir=str(tmp_path))
+    assert spec.light_meshes and spec.light_spheres and spec.instances
+    hs = scene.HostScene(spec)
+    n_lights = hs.desc.n_lights
+    spec2 = _moved_spec(spec, 0, (0.2, -0.1, 0.3))
+    fresh = scene.HostScene(spec2)
+    _refit_like(hs, spec2, 0)
+    hs.refit()
+    hs.refit()                                               # idempotent: nothing accumulates from call to call
+    a, b = _arrays(hs.desc), _arrays(fresh.desc)
+    for name in a:
+        assert a[name] == b[name], f"{name} differs after refit"
+    assert hs.desc.n_lights == fresh.desc.n_lights == n_lights and hs.desc.n_light_cdf == fresh.desc.n_light_cdf > 0
+
+
 def test_refit_refuses_nonsense():
     hs = scene.HostScene(scene.parse_xml(scenes.cfg2_hw3(n=16, width=32, height=20), "hw3"))
     ident = np.eye(4, dtype=np.float32).reshape(16)
