@@ -17,6 +17,7 @@ static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); ret
 static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 
 #include "../ceng795_b200/csrc/rt_traverse.cuh"
 
@@ -28,6 +29,56 @@ void hostleaf_box(const float* mn, const float* mx, const float* o, const float*
   out2[0] = box_gate_exact(O, D, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], eps, &entry) ? 1 : 0;
   const RayCtx r = make_ray(O, D, eps);
   out2[1] = box_gate(r, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], eps, &entry) ? 1 : 0;
+}
+// Adversarial boxes for the filtered gate: rays aimed exactly at corners, edges and faces of the box (the decision hangs
+// on the last bit), origins up to `far` box sizes away, on the box, inside it; directions with tiny and zero components.
+// Returns the number of cases in which the filter's decision differs from the exact gate's; stats[0..2] = cases,
+// accepted by the exact gate, decided by the filter without the exact fallback.
+static uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s; }
+static float urand(uint32_t& s) { return (float)(lcg(s) >> 8) * (1.0f / 16777216.0f); }
+int hostleaf_box_fuzz(int n, uint32_t seed, float far, float eps, long long* stats) {
+  uint32_t s = seed * 2654435761u + 12345u;
+  int bad = 0;
+  long long pass = 0, fast = 0;
+  for (int k = 0; k < n; k++) {
+    float mn[3], mx[3], o[3], d[3], aim[3];
+    const float scale = std::exp((urand(s) - 0.5f) * 12.0f);
+    for (int a = 0; a < 3; a++) {
+      const float c = (urand(s) - 0.5f) * 20.0f * scale, h = (0.01f + urand(s)) * scale;
+      mn[a] = c - h; mx[a] = c + h;
+      const int where = (int)(lcg(s) >> 30);   // 0: min plane, 1: max plane, 2/3: somewhere inside (or just outside)
+      aim[a] = where == 0 ? mn[a] : where == 1 ? mx[a] : mn[a] + (urand(s) * 1.2f - 0.1f) * (mx[a] - mn[a]);
+    }
+    const int kind = (int)(lcg(s) >> 29);
+    for (int a = 0; a < 3; a++) {
+      const float dist = (kind == 0 ? 0.0f : kind == 1 ? urand(s) : urand(s) * far) * (mx[a] - mn[a]);
+      o[a] = aim[a] + (urand(s) < 0.5f ? -dist : dist);
+      if (kind == 2) o[a] = aim[a];            // origin ON the aimed point for this axis
+    }
+    for (int a = 0; a < 3; a++) d[a] = aim[a] - o[a];
+    if ((lcg(s) >> 28) == 0) d[lcg(s) % 3] = 0.0f;
+    if ((lcg(s) >> 28) == 1) d[lcg(s) % 3] = (urand(s) - 0.5f) * 4e-6f;
+    if ((lcg(s) >> 27) == 2) for (int a = 0; a < 3; a++) d[a] = urand(s) - 0.5f;   // unrelated direction: mostly misses
+    if ((lcg(s) >> 28) == 3) for (int a = 0; a < 3; a++) d[a] = -d[a];            // box behind the origin
+    const v3 O = mk3(o[0], o[1], o[2]), D = mk3(d[0], d[1], d[2]);
+    float e0, e1;
+    const bool want = box_gate_exact(O, D, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], eps, &e0);
+    const RayCtx r = make_ray(O, D, eps);
+    const bool g1 = box_gate(r, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], eps, &e1);
+    bad += (g1 != want);
+    pass += want;
+    if (!r.slow) {   // would the filter have decided on its own?
+      const float ax = (mn[0] - r.o.x) * r.inv.x, bx = (mx[0] - r.o.x) * r.inv.x;
+      const float ay = (mn[1] - r.o.y) * r.inv.y, by = (mx[1] - r.o.y) * r.inv.y;
+      const float az = (mn[2] - r.o.z) * r.inv.z, bz = (mx[2] - r.o.z) * r.inv.z;
+      const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+      const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+      const float m = 5e-7f * fmaxf(fabsf(tn), fabsf(tf));
+      if ((tn + m < tf && tf > 1e-30f && tf < 1e30f && tn > -1e30f) || tn > tf + m || tf < -1e-30f) fast++;
+    }
+  }
+  if (stats) { stats[0] = n; stats[1] = pass; stats[2] = fast; }
+  return bad;
 }
 // g9 = v0, a1 = v0 - v1, a2 = v0 - v2; mode 1 / 2 / 7; out3 = {t, beta, gamma}
 int hostleaf_tri(const float* g9, const float* o, const float* d, int mode, float eps, float* out3) {

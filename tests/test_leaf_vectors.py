@@ -334,6 +334,16 @@ def test_device_source_on_the_host_takes_the_references_decisions():
         H.hostleaf_box(r[0:3].ctypes.data, r[3:6].ctypes.data, r[6:9].ctypes.data, r[9:12].ctypes.data, 1e-6, out2.ctypes.data)
         got[k] = out2 > 0
     assert np.array_equal(got[:, 0], ref_pass) and np.array_equal(got[:, 1], ref_pass)
+    # the filtered gate against the exact gate on adversarial boxes: rays through corners / edges / faces, origins on, in
+    # and far from the box, tiny and zero direction components.  Not one decision may differ.
+    H.hostleaf_box_fuzz.restype = C.c_int
+    H.hostleaf_box_fuzz.argtypes = [C.c_int, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_longlong)]
+    for seed, far in ((1, 4.0), (2, 100.0), (3, 1e4), (4, 1e6)):
+        st = (C.c_longlong * 3)()
+        bad = H.hostleaf_box_fuzz(500_000, seed, far, 1e-6, st)
+        assert bad == 0, (seed, far, bad)
+        assert 0.05 * st[0] < st[1] < 0.95 * st[0], list(st)        # hits and misses both well represented
+        assert st[2] > 0.1 * st[0], list(st)                          # and the filter decides a share itself even here
 
     x, want = SECTIONS["tri7"]
     out3 = np.zeros(3, np.float32)
