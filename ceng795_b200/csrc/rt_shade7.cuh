@@ -20,6 +20,87 @@
 #define RT_SHADE7_BLOCK 256  // threads per block of k_shade7_a/b: more warps behind each barrier
 #endif
 
+
+// Second measure against the same stall, and against the 15 of 32 lanes the two kernels keep busy (profiles/r01i): a
+// block takes the wave in tiles of RT_SHADE7_BLOCK * RT_SHADE7_ROUNDS slots and walks each tile grouped by CLASS — by
+// the kind of surface in shade_a (stand-alone triangle, sphere, mesh instance: the branches of surface7), by material
+// in shade_b (BRDF model, mirror, glass) — so that the 32 vertices of a warp, and the warps of a block, mostly run the
+// same branch.  Only the assignment of slots to threads changes: a vertex is still shaded from its own slot alone, so
+// every value written is the one it was before; the children of a tile merely enter the next wave class by class.
+// The grouping is a stable counting sort in shared memory (position = vertices of lower classes + vertices of the same
+// class in earlier warp-rounds + same-class lanes below this one), deterministic from run to run.  0 rounds: off.
+#ifndef RT_SHADE7_ROUNDS
+#define RT_SHADE7_ROUNDS 8   // swept on cfg4: 0 / 2 / 4 / 8 rounds = 842 / 759 / 731 / 720 ms per 64 strata (profiles/r02_tuning.txt)
+#endif
+#define RT_SHADE7_TILE (RT_SHADE7_BLOCK * (RT_SHADE7_ROUNDS > 0 ? RT_SHADE7_ROUNDS : 1))
+#ifndef RT_SHADE7_CLASSES
+#define RT_SHADE7_CLASSES 64   // a multiple of 32
+#endif
+#define RT_SHADE7_SEGS ((RT_SHADE7_BLOCK / 32) * (RT_SHADE7_ROUNDS > 0 ? RT_SHADE7_ROUNDS : 1))
+struct TileOrder7 {
+  unsigned short cnt[RT_SHADE7_CLASSES][RT_SHADE7_SEGS];   // vertices of a class in one warp-round, then their offset in the class
+  unsigned short first[RT_SHADE7_CLASSES];                  // vertices of a class, then the first position of the class
+  unsigned short perm[RT_SHADE7_TILE];                      // position in the walk -> vertex of the tile
+};
+// Fills T.perm[0 .. n_valid-1]; cls(i) = class of vertex i of the tile.  All threads of the block call it; position p of
+// the walk is taken by thread p % BLOCK in round p / BLOCK (tile_vertex7), and the block meets at a barrier before it
+// orders the next tile.
+template <class ClassOf>
+__device__ __forceinline__ void tile_order7(TileOrder7& T, uint32_t n_valid, ClassOf cls) {
+#if RT_SHADE7_ROUNDS > 0
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  for (uint32_t x = tid; x < RT_SHADE7_CLASSES * RT_SHADE7_SEGS; x += RT_SHADE7_BLOCK) (&T.cnt[0][0])[x] = 0;
+  __syncthreads();
+  uint32_t c[RT_SHADE7_ROUNDS], rank[RT_SHADE7_ROUNDS];
+#pragma unroll
+  for (int j = 0; j < RT_SHADE7_ROUNDS; j++) {
+    const uint32_t i = (uint32_t)j * RT_SHADE7_BLOCK + tid;
+    c[j] = (i < n_valid) ? (cls(i) & (RT_SHADE7_CLASSES - 1)) : RT_SHADE7_CLASSES;   // beyond the wave: in no class
+    const uint32_t same = __match_any_sync(0xffffffffu, c[j]);
+    rank[j] = __popc(same & ((1u << lane) - 1u));
+    if (rank[j] == 0 && c[j] < RT_SHADE7_CLASSES) T.cnt[c[j]][j * (RT_SHADE7_BLOCK / 32) + warp] = (unsigned short)__popc(same);
+  }
+  __syncthreads();
+  if (tid < RT_SHADE7_CLASSES) {
+    uint32_t run = 0;
+    for (int sgm = 0; sgm < RT_SHADE7_SEGS; sgm++) { const uint32_t v = T.cnt[tid][sgm]; T.cnt[tid][sgm] = (unsigned short)run; run += v; }
+    T.first[tid] = (unsigned short)run;
+  }
+  __syncthreads();
+  if (warp == 0) {   // exclusive scan of the class sizes, CLASSES / 32 consecutive classes per lane
+    constexpr int PER = RT_SHADE7_CLASSES / 32;
+    uint32_t sz[PER], mine = 0;
+#pragma unroll
+    for (int q = 0; q < PER; q++) { sz[q] = T.first[PER * lane + q]; mine += sz[q]; }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+    uint32_t at = incl - mine;
+#pragma unroll
+    for (int q = 0; q < PER; q++) { T.first[PER * lane + q] = (unsigned short)at; at += sz[q]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < RT_SHADE7_ROUNDS; j++)
+    if (c[j] < RT_SHADE7_CLASSES)
+      T.perm[T.first[c[j]] + T.cnt[c[j]][j * (RT_SHADE7_BLOCK / 32) + warp] + rank[j]] = (unsigned short)((uint32_t)j * RT_SHADE7_BLOCK + tid);
+  __syncthreads();
+#endif
+}
+__device__ __forceinline__ uint32_t tile_vertex7(const TileOrder7& T, uint32_t position) {
+#if RT_SHADE7_ROUNDS > 0
+  return T.perm[position];
+#else
+  return position;
+#endif
+}
+// Class of a closest hit for shade_a: kind of the top-level object first (the branch of surface7), then the object.
+__device__ __forceinline__ uint32_t surf_class7(uint32_t top_ref) {
+  const uint32_t kind = B200RT_REF_KIND(top_ref);
+  if (kind == B200RT_KIND_NONE) return RT_SHADE7_CLASSES - 1;
+  return (((kind & 7u) * (RT_SHADE7_CLASSES / 8)) | (B200RT_REF_INDEX(top_ref) & (RT_SHADE7_CLASSES / 8 - 1))) % (RT_SHADE7_CLASSES - 1);
+}
+
 __device__ __forceinline__ v3 operator/(v3 a, v3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
 
 // ---- textures ----------------------------------------------------------------
@@ -463,12 +544,15 @@ __device__ __noinline__ v3 light_radiance7(const DScene& S, int li, v3 to_light,
 __global__ void __launch_bounds__(RT_SHADE7_BLOCK) k_shade7_a(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves, int d,
                                                        Counters* C) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t rounds = (count + stride - 1) / stride;
-  for (uint32_t r = 0; r < rounds; r++) {
-    const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = k < count;
-    const uint32_t slot = begin + (act ? k : 0);
+  __shared__ TileOrder7 s_order;
+  for (uint32_t base = blockIdx.x * RT_SHADE7_TILE; base < count; base += gridDim.x * RT_SHADE7_TILE) {
+   const uint32_t n_valid = min((uint32_t)RT_SHADE7_TILE, count - base);
+   tile_order7(s_order, n_valid, [&](uint32_t i) { return surf_class7(__float_as_uint(P.hit_a[begin + base + i].w)); });
+#pragma unroll 1
+   for (int rj = 0; rj < (RT_SHADE7_ROUNDS > 0 ? RT_SHADE7_ROUNDS : 1); rj++) {
+    const uint32_t position = (uint32_t)rj * RT_SHADE7_BLOCK + threadIdx.x;
+    const bool act = position < n_valid;
+    const uint32_t slot = begin + base + (act ? tile_vertex7(s_order, position) : 0);
     const float4 ha = P.hit_a[slot];
     const uint32_t top_ref = __float_as_uint(ha.w);
     const bool hit = act && B200RT_REF_KIND(top_ref) != B200RT_KIND_NONE;
@@ -527,6 +611,8 @@ __global__ void __launch_bounds__(RT_SHADE7_BLOCK) k_shade7_a(DScene S, Pool P, 
         }
       }
     }
+   }
+   __syncthreads();   // s_order is rewritten for the next tile
   }
 }
 
@@ -767,13 +853,26 @@ __global__ void __launch_bounds__(RT_SHADE7_BLOCK) k_shade7_b(DScene S, Pool P, 
                                                        Counters* C) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   const uint32_t next_begin = waves[d + 1].begin;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t rounds = (count + stride - 1) / stride;
   const bool pt = S.integrator != 0;
-  for (uint32_t r = 0; r < rounds; r++) {
-    const uint32_t k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = k < count;
-    const uint32_t slot = begin + (act ? k : 0);
+  __shared__ TileOrder7 s_order;
+  for (uint32_t base = blockIdx.x * RT_SHADE7_TILE; base < count; base += gridDim.x * RT_SHADE7_TILE) {
+   const uint32_t n_valid = min((uint32_t)RT_SHADE7_TILE, count - base);
+   // by material (written by shade_a next to the normal); vertices that hit nothing go last
+   tile_order7(s_order, n_valid,
+               [&](uint32_t i) {
+                 const uint32_t sl = begin + base + i;
+                 const uint32_t top_ref = __float_as_uint(P.hit_a[sl].w);
+                 if (B200RT_REF_KIND(top_ref) == B200RT_KIND_NONE) return (uint32_t)(RT_SHADE7_CLASSES - 1);
+#ifdef RT_SHADE7_B_BY_OBJECT
+                 return surf_class7(top_ref);
+#endif
+                 return (uint32_t)__float_as_int(P.nrm[sl].w) % (RT_SHADE7_CLASSES - 1);
+               });
+#pragma unroll 1
+   for (int rj = 0; rj < (RT_SHADE7_ROUNDS > 0 ? RT_SHADE7_ROUNDS : 1); rj++) {
+    const uint32_t position = (uint32_t)rj * RT_SHADE7_BLOCK + threadIdx.x;
+    const bool act = position < n_valid;
+    const uint32_t slot = begin + base + (act ? tile_vertex7(s_order, position) : 0);
     const float4 ha = P.hit_a[slot];
     const float4 ro = P.ray_o[slot], rd = P.ray_d[slot];
     const uint32_t meta = __float_as_uint(rd.w);
@@ -993,6 +1092,8 @@ __global__ void __launch_bounds__(RT_SHADE7_BLOCK) k_shade7_b(DScene S, Pool P, 
       P.rec3[slot] = ct;
       P.rec4[slot] = make_float4(wdiff.x, wdiff.y, wdiff.z, __uint_as_float(cd));
     }
+   }
+   __syncthreads();   // s_order is rewritten for the next tile
   }
 }
 

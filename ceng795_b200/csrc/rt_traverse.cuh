@@ -75,17 +75,45 @@ __device__ __forceinline__ RayCtx make_ray(v3 o, v3 d, float eps) {
 // (|diff| <= 2^-24 + 2^-23 relative, margin 5e-7), and falls back to the exact
 // division-based test otherwise.  The accept/reject DECISION is therefore always
 // the reference's; only the instruction count changes.
+//   1 accept, 0 reject, -1 not clear.
+// Two levels.  The first compares the entry (largest near plane) with the exit (smallest far plane).  It can never
+// clear a FLAT box — an axis-aligned wall or light quad, mn == mx on one axis, gives near == far on that axis, so entry
+// and exit coincide for every ray that meets the wall's plane inside the box — and the Cornell-style scenes of HW7 /
+// PPM gate a dozen of those per ray (profiles/r02p: the gate pre-pass took 11 % of cfg4, most of it in the divisions
+// of the fallback).  The second level uses what the reference's loop really decides: it rejects iff some near_i
+// exceeds some far_j, and near_i <= far_i always holds (the same subtraction and division, rounded monotonically, then
+// ordered by the sign of d), so only the six CROSS-axis pairs matter, each with a margin of its own size.
+#ifndef RT_GATE_LEVELS
+#define RT_GATE_LEVELS 2   // 1: entry against exit only (A/B aid, tools/build_variant.sh)
+#endif
+__device__ __forceinline__ int box_gate_filter(const RayCtx& r, float mnx, float mny, float mnz, float mxx, float mxy,
+                                               float mxz, float* entry) {
+  const float ax = (mnx - r.o.x) * r.inv.x, bx = (mxx - r.o.x) * r.inv.x;
+  const float ay = (mny - r.o.y) * r.inv.y, by = (mxy - r.o.y) * r.inv.y;
+  const float az = (mnz - r.o.z) * r.inv.z, bz = (mxz - r.o.z) * r.inv.z;
+  const float lx = fminf(ax, bx), ly = fminf(ay, by), lz = fminf(az, bz);
+  const float hx = fmaxf(ax, bx), hy = fmaxf(ay, by), hz = fmaxf(az, bz);
+  const float tn = fmaxf(fmaxf(lx, ly), lz);
+  const float tf = fminf(fminf(hx, hy), hz);
+  const float m = 5e-7f * fmaxf(fabsf(tn), fabsf(tf));
+  const bool range_ok = tf > 1e-30f && tf < 1e30f && tn > -1e30f;   // bbox_t is positive and finite
+  if (tn + m < tf && range_ok) { *entry = fmaxf(tn, 0.0f); return 1; }
+  if (tn > tf + m || tf < -1e-30f) return 0;
+#if RT_GATE_LEVELS > 1
+  const float Lx = fmaxf(ly, lz), Ly = fmaxf(lx, lz), Lz = fmaxf(lx, ly);   // largest near plane of the OTHER two axes
+  const float qx = 5e-7f * fmaxf(fabsf(Lx), fabsf(hx)) + 1e-30f;
+  const float qy = 5e-7f * fmaxf(fabsf(Ly), fabsf(hy)) + 1e-30f;
+  const float qz = 5e-7f * fmaxf(fabsf(Lz), fabsf(hz)) + 1e-30f;
+  if (Lx + qx < hx && Ly + qy < hy && Lz + qz < hz && range_ok) { *entry = fmaxf(tn, 0.0f); return 1; }
+  if (Lx > hx + qx || Ly > hy + qy || Lz > hz + qz) return 0;
+#endif
+  return -1;
+}
 __device__ __forceinline__ bool box_gate(const RayCtx& r, float mnx, float mny, float mnz, float mxx, float mxy,
                                          float mxz, float eps, float* entry) {
   if (!r.slow) {
-    const float ax = (mnx - r.o.x) * r.inv.x, bx = (mxx - r.o.x) * r.inv.x;
-    const float ay = (mny - r.o.y) * r.inv.y, by = (mxy - r.o.y) * r.inv.y;
-    const float az = (mnz - r.o.z) * r.inv.z, bz = (mxz - r.o.z) * r.inv.z;
-    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-    const float m = 5e-7f * fmaxf(fabsf(tn), fabsf(tf));
-    if (tn + m < tf && tf > 1e-30f && tf < 1e30f && tn > -1e30f) { *entry = fmaxf(tn, 0.0f); return true; }
-    if (tn > tf + m || tf < -1e-30f) return false;
+    const int g = box_gate_filter(r, mnx, mny, mnz, mxx, mxy, mxz, entry);
+    if (g >= 0) return g != 0;
   }
   return box_gate_exact(r.o, r.d, mnx, mny, mnz, mxx, mxy, mxz, eps, entry);
 }

@@ -30,13 +30,20 @@ void hostleaf_box(const float* mn, const float* mx, const float* o, const float*
   const RayCtx r = make_ray(O, D, eps);
   out2[1] = box_gate(r, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], eps, &entry) ? 1 : 0;
 }
+// 1 / 0: the filter's own decision, -1: it would fall back to the divisions (slow rays always do)
+int hostleaf_box_filter(const float* mn, const float* mx, const float* o, const float* d, float eps) {
+  const RayCtx r = make_ray(mk3(o[0], o[1], o[2]), mk3(d[0], d[1], d[2]), eps);
+  float entry = 0.0f;
+  return r.slow ? -1 : box_gate_filter(r, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], &entry);
+}
 // Adversarial boxes for the filtered gate: rays aimed exactly at corners, edges and faces of the box (the decision hangs
-// on the last bit), origins up to `far` box sizes away, on the box, inside it; directions with tiny and zero components.
+// on the last bit), origins up to `far` box sizes away, on the box, inside it; directions with tiny and zero components;
+// `flat_share` of the boxes are flat on one or two axes (axis-aligned walls, the second level of the filter).
 // Returns the number of cases in which the filter's decision differs from the exact gate's; stats[0..2] = cases,
 // accepted by the exact gate, decided by the filter without the exact fallback.
 static uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s; }
 static float urand(uint32_t& s) { return (float)(lcg(s) >> 8) * (1.0f / 16777216.0f); }
-int hostleaf_box_fuzz(int n, uint32_t seed, float far, float eps, long long* stats) {
+int hostleaf_box_fuzz(int n, uint32_t seed, float far, float eps, float flat_share, long long* stats) {
   uint32_t s = seed * 2654435761u + 12345u;
   int bad = 0;
   long long pass = 0, fast = 0;
@@ -49,9 +56,16 @@ int hostleaf_box_fuzz(int n, uint32_t seed, float far, float eps, long long* sta
       const int where = (int)(lcg(s) >> 30);   // 0: min plane, 1: max plane, 2/3: somewhere inside (or just outside)
       aim[a] = where == 0 ? mn[a] : where == 1 ? mx[a] : mn[a] + (urand(s) * 1.2f - 0.1f) * (mx[a] - mn[a]);
     }
+    float ext[3];
+    for (int a = 0; a < 3; a++) ext[a] = mx[a] - mn[a];
+    if (urand(s) < flat_share) {
+      const int a = (int)(lcg(s) % 3u);
+      mx[a] = mn[a]; aim[a] = mn[a];
+      if ((lcg(s) >> 29) == 0) { const int b = (a + 1 + (int)(lcg(s) & 1u)) % 3; mx[b] = mn[b]; aim[b] = mn[b]; }
+    }
     const int kind = (int)(lcg(s) >> 29);
     for (int a = 0; a < 3; a++) {
-      const float dist = (kind == 0 ? 0.0f : kind == 1 ? urand(s) : urand(s) * far) * (mx[a] - mn[a]);
+      const float dist = (kind == 0 ? 0.0f : kind == 1 ? urand(s) : urand(s) * far) * ext[a];
       o[a] = aim[a] + (urand(s) < 0.5f ? -dist : dist);
       if (kind == 2) o[a] = aim[a];            // origin ON the aimed point for this axis
     }
@@ -67,15 +81,7 @@ int hostleaf_box_fuzz(int n, uint32_t seed, float far, float eps, long long* sta
     const bool g1 = box_gate(r, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], eps, &e1);
     bad += (g1 != want);
     pass += want;
-    if (!r.slow) {   // would the filter have decided on its own?
-      const float ax = (mn[0] - r.o.x) * r.inv.x, bx = (mx[0] - r.o.x) * r.inv.x;
-      const float ay = (mn[1] - r.o.y) * r.inv.y, by = (mx[1] - r.o.y) * r.inv.y;
-      const float az = (mn[2] - r.o.z) * r.inv.z, bz = (mx[2] - r.o.z) * r.inv.z;
-      const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-      const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-      const float m = 5e-7f * fmaxf(fabsf(tn), fabsf(tf));
-      if ((tn + m < tf && tf > 1e-30f && tf < 1e30f && tn > -1e30f) || tn > tf + m || tf < -1e-30f) fast++;
-    }
+    if (!r.slow && box_gate_filter(r, mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], &e1) >= 0) fast++;   // decided without the divisions
   }
   if (stats) { stats[0] = n; stats[1] = pass; stats[2] = fast; }
   return bad;

@@ -337,13 +337,30 @@ def test_device_source_on_the_host_takes_the_references_decisions():
     # the filtered gate against the exact gate on adversarial boxes: rays through corners / edges / faces, origins on, in
     # and far from the box, tiny and zero direction components.  Not one decision may differ.
     H.hostleaf_box_fuzz.restype = C.c_int
-    H.hostleaf_box_fuzz.argtypes = [C.c_int, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_longlong)]
-    for seed, far in ((1, 4.0), (2, 100.0), (3, 1e4), (4, 1e6)):
+    H.hostleaf_box_fuzz.argtypes = [C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_longlong)]
+    for seed, far, flat in ((1, 4.0, 0.0), (2, 100.0, 0.0), (3, 1e4, 0.0), (4, 1e6, 0.0),
+                            (5, 4.0, 1.0), (6, 100.0, 1.0), (7, 1e4, 0.5), (8, 1e6, 1.0)):
         st = (C.c_longlong * 3)()
-        bad = H.hostleaf_box_fuzz(500_000, seed, far, 1e-6, st)
-        assert bad == 0, (seed, far, bad)
+        bad = H.hostleaf_box_fuzz(500_000, seed, far, 1e-6, flat, st)
+        print("box fuzz", seed, far, flat, list(st))
+        assert bad == 0, (seed, far, flat, bad)
         assert 0.05 * st[0] < st[1] < 0.95 * st[0], list(st)        # hits and misses both well represented
         assert st[2] > 0.1 * st[0], list(st)                          # and the filter decides a share itself even here
+    # a wall as a Cornell box has it (flat gate box): rays from inside the room are decided without the divisions
+    rng = np.random.default_rng(5)
+    mn, mx = np.array([-5, -1, -5], np.float32), np.array([5, -1, 5], np.float32)
+    H.hostleaf_box_filter.restype = C.c_int
+    H.hostleaf_box_filter.argtypes = [C.c_void_p] * 4 + [C.c_float]
+    decided = hits = 0
+    for _ in range(4000):
+        o = rng.uniform([-5, -1, -5], [5, 9, 5]).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        g = H.hostleaf_box_filter(mn.ctypes.data, mx.ctypes.data, o.ctypes.data, d.ctypes.data, 1e-6)
+        H.hostleaf_box(mn.ctypes.data, mx.ctypes.data, o.ctypes.data, d.ctypes.data, 1e-6, out2.ctypes.data)
+        decided += g >= 0
+        hits += int(out2[0])
+        assert g < 0 or g == out2[0]
+    assert decided > 3950 and 500 < hits < 3500, (decided, hits)
 
     x, want = SECTIONS["tri7"]
     out3 = np.zeros(3, np.float32)
