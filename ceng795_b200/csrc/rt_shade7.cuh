@@ -29,8 +29,12 @@
 // every value written is the one it was before; the children of a tile merely enter the next wave class by class.
 // The grouping is a stable counting sort in shared memory (position = vertices of lower classes + vertices of the same
 // class in earlier warp-rounds + same-class lanes below this one), deterministic from run to run.  0 rounds: off.
-#ifndef RT_SHADE7_MIN_BLOCKS
-#define RT_SHADE7_MIN_BLOCKS 2   // resident blocks the register budget of k_shade7_a/b is held to (2: 128 registers, 3: 80)
+// Register budget of k_shade7_a/b: left to the compiler (128 / 127 registers, 2 resident blocks).  Holding it to 3 or 4
+// blocks (-DRT_SHADE7_MIN_BLOCKS=3: 80 registers, 4: 64) was measured and is no faster (profiles/r02_tuning.txt 18).
+#ifdef RT_SHADE7_MIN_BLOCKS
+#define RT_SHADE7_BOUNDS __launch_bounds__(RT_SHADE7_BLOCK, RT_SHADE7_MIN_BLOCKS)
+#else
+#define RT_SHADE7_BOUNDS __launch_bounds__(RT_SHADE7_BLOCK)
 #endif
 #ifndef RT_SHADE7_ROUNDS
 #define RT_SHADE7_ROUNDS 8   // swept on cfg4: 0 / 2 / 4 / 8 rounds = 842 / 759 / 731 / 720 ms per 64 strata (profiles/r02_tuning.txt)
@@ -544,7 +548,7 @@ __device__ __noinline__ v3 light_radiance7(const DScene& S, int li, v3 to_light,
 // ---- shade_a (HW7): surface record, emissive / replace_all short cuts, shadow-ray emission ----
 #define RT_KDF_REPLACE_ALL 1u
 #define RT_KDF_EMISSIVE 2u
-__global__ void __launch_bounds__(RT_SHADE7_BLOCK, RT_SHADE7_MIN_BLOCKS) k_shade7_a(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves, int d,
+__global__ void RT_SHADE7_BOUNDS k_shade7_a(DScene S, Pool P, ShadowQueue Q, const WaveInfo* waves, int d,
                                                        Counters* C) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   __shared__ TileOrder7 s_order;
@@ -852,7 +856,7 @@ __global__ void __launch_bounds__(RT_BLOCK) k_shade4_b(DScene S, Pool P, ShadowQ
 }
 
 // ---- shade_b (HW7): Scene::send_ray / trace_ray / trace_path bodies -------------------------
-__global__ void __launch_bounds__(RT_SHADE7_BLOCK, RT_SHADE7_MIN_BLOCKS) k_shade7_b(DScene S, Pool P, ShadowQueue Q, WaveInfo* waves, int d,
+__global__ void RT_SHADE7_BOUNDS k_shade7_b(DScene S, Pool P, ShadowQueue Q, WaveInfo* waves, int d,
                                                        Counters* C) {
   const uint32_t begin = waves[d].begin, count = waves[d].count;
   const uint32_t next_begin = waves[d + 1].begin;
