@@ -488,7 +488,10 @@ int b200rt_frame_collect_async(b200rt_scene* owner, int parts, float* rgbw_out);
 /* One host thread, n scenes of the same description on n devices (scenes[0] owns the frame): export + attach + begin +
  * one worker thread per device for render_shared + collect.  The frame equals b200rt_render's on one device: bit for
  * bit for 1-sample cameras, up to float summation order for splatting / multi-sample cameras (as the reference's own
- * threads).  stats_out: sums over the devices; ms_total = the frame's latency on the owner's stream. */
+ * threads).  stats_out: sums over the devices; ms_total = the frame's latency on the owner's stream.  If a share
+ * fails (or never arrives: the wait on the device gives up after 20 s) the call returns its error and the next call
+ * exports and attaches the frame afresh; a process-per-GPU host does the same after an error from
+ * b200rt_render_shared / b200rt_frame_collect (b200rt_frame_export, then b200rt_frame_attach on every rank). */
 int b200rt_render_multi(b200rt_scene* const* scenes, int n_scenes, int camera_index, const B200RenderOpts*,
                         float* rgbw_out, B200RenderStats* stats_out);
 /* Share of device `part` of `parts` for camera `camera_index`, as b200rt_render_multi deals it (exposed so a
@@ -498,7 +501,8 @@ int b200rt_multi_share(b200rt_scene*, int camera_index, int part, int parts, B20
 /* PPM across GPUs.  Every GPU runs b200rt_ppm_eye_pass itself (hit points are numbered canonically, so index i is the
  * same hit point everywhere).  After each pass's b200rt_ppm_trace_photons:
  *   b200rt_ppm_counts_delta  device uint32 per hit point: photons accepted by THIS GPU since the last sync
- *   (sum it over the GPUs in place: NCCL all-reduce, or b200rt_ppm_sync_counts_multi in one process)
+ *   (sum it over the GPUs in place: an NCCL all-reduce between processes; b200rt_ppm_trace_photons_multi does it
+ *   over peer memory inside one process)
  *   b200rt_ppm_counts_apply  n = n_at_last_sync + the summed delta, on this GPU
  * S = sum f*phi/R(k) stays local and additive: sum b200rt_ppm_export's float4 array once, when an image is wanted. */
 /* Before the eye pass: this scene is share `part` of `parts` of every photon pass.  Between two synchronisations it
